@@ -1,0 +1,155 @@
+/*
+ * libuad_b200 - C ABI of the B200 (sm_100a) hot path for unsupervised brain-MRI anomaly detection.
+ *
+ * The reference (StefanDenn3r/Unsupervised_Anomaly_Detection_Brain_MRI) has no FFI of its own: its hot path runs inside
+ * tf.Session.run (trainers/AE.py:83, trainers/VAE.py:96, trainers/ceVAE.py:107) on graphs built from
+ * models/customlayers.py:16-38 and lowered to TensorFlow library ops.  Each entry point below replaces one of those
+ * library ops (or a fused group of them); the reference interface it replaces is cited per function
+ * (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - every tensor pointer is a caller-owned DEVICE pointer, NHWC / row-major contiguous fp32 unless stated
+ *  - functions enqueue on `stream` (a cudaStream_t passed as void*) and return without synchronising
+ *  - no allocation inside hot calls: workspace is caller-provided (query with uad_conv_workspace_bytes)
+ *  - return 0 on success; non-zero on error with a message in uad_last_error() (thread-local)
+ *  - `accumulate` != 0 means "+=" into the gradient output (shared-weight branches, e.g. ceVAE), else overwrite
+ *  - all reductions are deterministic (two-stage, no floating-point atomics)
+ */
+#ifndef UAD_B200_H_
+#define UAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAD_ABI_VERSION 1
+
+#define UAD_ACT_NONE 0
+#define UAD_ACT_LEAKY 1   /* tf.keras.layers.LeakyReLU(alpha)  models/customlayers.py:23,36 */
+#define UAD_ACT_RELU 2    /* tf.keras.layers.ReLU              models/customlayers.py:31    */
+#define UAD_ACT_SIGMOID 3 /* models/fanogan.py:41,46 */
+#define UAD_ACT_TANH 4    /* models/fanogan.py:29    */
+
+#define UAD_OP_CONV_FWD 0
+#define UAD_OP_CONV_DGRAD 1
+#define UAD_OP_CONV_WGRAD 2
+#define UAD_OP_CONVT_FWD 3
+#define UAD_OP_CONVT_DGRAD 4
+#define UAD_OP_CONVT_WGRAD 5
+
+/* math mode of the conv kernels: 0 = fp32 SIMT FFMA; 1 = tcgen05 3xTF32 (fp32-accurate split); 2 = tcgen05 1xTF32 */
+#define UAD_MATH_FP32_SIMT 0
+#define UAD_MATH_TC_3XTF32 1
+#define UAD_MATH_TC_1XTF32 2
+
+const char* uad_last_error(void);
+int uad_abi_version(void);
+/* 1 if the tcgen05 (tensor-core) conv path is compiled in and usable for the given op/shape, else 0 */
+int uad_conv_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int ksize);
+
+/* Bytes of scratch an op needs. (H,W) is the spatial size of the op's LOW-resolution... see each op: it is always the
+ * size of the tensor called `x` in the forward direction of the layer (conv: input; convT: input). */
+size_t uad_conv_workspace_bytes(int op, int B, int H, int W, int Cin, int Cout, int ksize, int math_mode);
+
+/* ---- strided conv block: Conv2D(k, s=2, 'same') + bias -> frozen BatchNormalization -> activation
+ * replaces tf Conv2D + BatchNormalization(inference affine) + LeakyReLU  (models/customlayers.py:21-23)
+ * x [B,H,W,Cin], w HWIO [k,k,Cin,Cout], z_out/a_out [B,H/2,W/2,Cout].
+ * z = conv(x)+bias; a = act(gamma*bn_c*z + beta)  (gamma/beta NULL => identity affine).  z_out or a_out may be NULL. */
+int uad_conv2d_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                   float* z_out, float* a_out, int B, int H, int W, int Cin, int Cout, int ksize, int act, float alpha,
+                   float bn_c, int math_mode, void* ws, size_t ws_bytes, void* stream);
+/* input gradient of the conv (tf.gradients -> Conv2DBackpropInput): dz [B,H/2,W/2,Cout] -> dx [B,H,W,Cin] */
+int uad_conv2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout, int ksize,
+                     int math_mode, void* ws, size_t ws_bytes, void* stream);
+/* filter gradient (Conv2DBackpropFilter): dw HWIO */
+int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
+                     int accumulate, int math_mode, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- transposed conv block: Conv2DTranspose(k, s=2, 'same') + bias -> frozen BN -> activation
+ * replaces tf Conv2DTranspose + BatchNormalization + LeakyReLU (models/customlayers.py:34-36)
+ * x [B,H,W,Cin], w [k,k,Cout,Cin] (TF layout), outputs [B,2H,2W,Cout]. */
+int uad_convT2d_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                    float* z_out, float* a_out, int B, int H, int W, int Cin, int Cout, int ksize, int act, float alpha,
+                    float bn_c, int math_mode, void* ws, size_t ws_bytes, void* stream);
+int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout, int ksize,
+                      int math_mode, void* ws, size_t ws_bytes, void* stream);
+int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,
+                      int accumulate, int math_mode, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- backward of "z -> frozen BN -> activation" plus the bias gradient (tf.gradients through
+ * BatchNormalization/LeakyReLU/BiasAdd).  rows = B*H*W, C channels.
+ * du = da*act'(gamma*bn_c*z+beta); dgamma = bn_c*sum(du*z); dbeta = sum(du); dz = gamma*bn_c*du; dbias = sum(dz).
+ * dz may alias da.  gamma/beta NULL => identity affine (dgamma/dbeta ignored).  ws: >= uad_rowreduce_workspace_bytes. */
+size_t uad_rowreduce_workspace_bytes(long long rows, int C);
+int uad_act_bn_bwd(const float* da, const float* z, const float* gamma, const float* beta, float* dz, float* dgamma,
+                   float* dbeta, float* dbias, long long rows, int C, int act, float alpha, float bn_c, int accumulate,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- dense / 1x1-conv block: y = dropout(x.W + b) -> optional frozen BN -> activation
+ * replaces tf Dense / Keras Conv2D(1x1) / Dropout (models/autoencoder.py:20-30, variational_autoencoder.py:20-36)
+ * x [M,K], w [K,N], mask [M,N] of {0,1} or NULL, z = (x.W+b)*mask*mask_scale, a = act(gamma*bn_c*z+beta). */
+int uad_dense_fwd(const float* x, const float* w, const float* bias, const float* mask, float mask_scale,
+                  const float* gamma, const float* beta, float* z_out, float* a_out, int M, int K, int N, int act,
+                  float alpha, float bn_c, void* stream);
+/* dz [M,N] is the gradient w.r.t. z (post-dropout); dx may be NULL */
+int uad_dense_bwd(const float* x, const float* w, const float* dz, const float* mask, float mask_scale, float* dx,
+                  float* dw, float* dbias, int M, int K, int N, int accumulate, void* stream);
+
+/* ---- reparameterise + KL (models/variational_autoencoder.py:33-34, trainers/VAE.py:38)
+ * sigma=exp(ls); z=mu+eps*sigma; kl[b]=0.5*sum_j(mu^2+sigma^2-log(sigma^2)-1).  eps NULL => z=mu (ceVAE ce-branch) */
+int uad_reparam_kl_fwd(const float* mu, const float* log_sigma, const float* eps, float* sigma, float* z, float* kl,
+                       int B, int Z, void* stream);
+/* dmu = dz + kl_scale*mu ; dls = dz*eps*sigma + kl_scale*(sigma^2-1)   (kl_scale = 1/B for loss=mean_b(rec+kl)) */
+int uad_reparam_kl_bwd(const float* mu, const float* log_sigma, const float* eps, const float* dz, float kl_scale,
+                       float* dmu, float* dls, int B, int Z, void* stream);
+
+/* ---- fused final 1x1 conv (Cin->1) + L1 residual + per-sample sums
+ * replaces dec_Conv2D_final (models/customlayers.py:37) + tf.losses.absolute_difference + reduce_sum
+ * (trainers/AE.py:28-29).  a [B*HW, Cin], w [Cin], b [1], x [B*HW] -> xhat [B*HW], l1 [B*HW] (nullable), rec[B] (nullable) */
+int uad_final1x1_l1_fwd(const float* a, const float* w, const float* bias, const float* x, float* xhat, float* l1,
+                        float* rec, int B, int HW, int Cin, void* ws, size_t ws_bytes, void* stream);
+/* dxhat = sign(xhat-x)*scale (sign(0)=0); da[p,c] = dxhat*w[c]; dw[c] = sum dxhat*a[p,c]; db = sum dxhat. */
+int uad_final1x1_l1_bwd(const float* a, const float* w, const float* x, const float* xhat, float scale, float* da,
+                        float* dw, float* dbias, int B, int HW, int Cin, int accumulate, void* ws, size_t ws_bytes,
+                        void* stream);
+
+/* ---- loss scalars: out[0]=mean(rec), out[1]=mean(kl) (0 if kl NULL), out[2]=mean(rec+kl) (trainers/VAE.py:40-42) */
+int uad_loss_scalars(const float* rec, const float* kl, float* out3, int B, void* stream);
+
+/* ---- TF-form Adam on a flat buffer (trainers/DLMODEL.py:112-131; tf.train.AdamOptimizer):
+ * g = grad*grad_scale; m=b1*m+(1-b1)g; v=b2*v+(1-b2)g^2; p -= lr_t*m/(sqrt(v)+eps), lr_t precomputed by the host */
+int uad_adam_tf_step(float* params, const float* grads, float* m, float* v, size_t n, float lr_t, float b1, float b2,
+                     float eps, float grad_scale, const float* lr_t_dev, void* stream);
+/* lr_t_dev (nullable): device scalar that overrides lr_t - lets a captured CUDA graph see a fresh bias-corrected rate */
+
+/* ---- Philox-4x32-10 streams for the live graph RNG nodes (tf.random_normal variational_autoencoder.py:34; Dropout) */
+int uad_randn(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+int uad_dropout_mask(float* mask, size_t n, float rate, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                     void* stream);
+/* offset_dev (nullable): device counter added to `offset`, advanced with uad_counter_add (CUDA-graph friendly) */
+int uad_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
+
+/* ---- residual-map scoring (utils/Evaluation.py:282-291):
+ * d = keep_positive ? max(x-xhat,0) : |x-xhat| (fp32); d *= mask (uint8, nullable); if apply_prior and (double)x < prior: d=0 */
+int uad_residual_score(const float* x, const float* xhat, const uint8_t* mask, double prior_quantile, int keep_positive,
+                       int apply_prior, float* diff, size_t n, void* stream);
+/* ---- threshold + Dice counts (utils/Evaluation.py:453-457, trainers/Metrics.py:67-72):
+ * for each threshold t_i (float64): P = (double)diff > t_i; counts[i] = {sum P*G, sum P, sum G} as int64.
+ * mask_out (nullable, uint8 [n]) receives P for thresholds[0].  label uint8 (nullable => G=0). n_thr <= 32. */
+int uad_threshold_counts(const float* diff, const uint8_t* label, size_t n, const double* thresholds_host, int n_thr,
+                         int64_t* counts_dev, uint8_t* mask_out, void* stream);
+
+/* ---- ceVAE anomaly map (trainers/ceVAE.py:51): anomaly = l1 * |gx| */
+int uad_mul_abs(const float* l1, const float* gx, float* out, size_t n, void* stream);
+/* gx[i] += -sign(xhat[i]-x[i])*scale : the direct dependence of |xhat-x| on x in d loss_vae/dx (trainers/ceVAE.py:51) */
+int uad_l1_direct_term(const float* x, const float* xhat, float scale, float* gx, size_t n, void* stream);
+/* y = a*x + b*y elementwise (gradient bookkeeping on flat buffers) */
+int uad_axpby(float a, const float* x, float b, float* y, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAD_B200_H_ */

@@ -1,0 +1,364 @@
+"""Per-op parity of the CUDA kernels (through the C ABI) against the float64 oracle.  Tolerance 1e-4 relative
+(||a-b||_inf / ||b||_inf) as north_star states for fp32; integer / mask results bit-exact."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import naive64, scoring as oscore  # noqa: E402
+from oracle import tf_graph_cpu as O  # noqa: E402
+
+TOL = 1e-4
+MODES = [0]
+
+
+def _modes():
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    return [abi.MATH_FP32_SIMT, abi.MATH_TC_3XTF32]
+
+
+def t64(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).double()
+
+
+def oracle_conv(x, w, b):
+    return O.conv2d_same_s2(t64(x).permute(0, 3, 1, 2), t64(w), t64(b)).permute(0, 2, 3, 1).numpy()
+
+
+def oracle_convT(x, K, b):
+    return O.conv2dT_same_s2(t64(x).permute(0, 3, 1, 2), t64(K), t64(b)).permute(0, 2, 3, 1).numpy()
+
+
+CONV_SHAPES = [  # B, H, Cin, Cout
+    (2, 16, 32, 64), (3, 32, 32, 32), (2, 16, 64, 128), (1, 16, 128, 128), (2, 64, 32, 64), (5, 8, 16, 32),
+]
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('B,H,Cin,Cout', CONV_SHAPES)
+def test_conv2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    L = abi.lib()
+    rng = np.random.default_rng(B * 1000 + H + Cin + Cout)
+    x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
+    x[rng.uniform(size=x.shape) < 0.3] = 0
+    w = (rng.standard_normal((5, 5, Cin, Cout)) / math.sqrt(25 * Cin)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(Cout)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(Cout)).astype(np.float32)
+    bn_c = 1 / math.sqrt(1.001)
+    z_ref = oracle_conv(x, w, b)
+    u = gamma.astype(np.float64) * bn_c * z_ref + beta
+    a_ref = np.where(u > 0, u, 0.3 * u)
+    wsb = max(L.uad_conv_workspace_bytes(op, B, H, H, Cin, Cout, 5, mode) for op in (0, 1, 2))
+    ws = workspace(wsb)
+    dx_, dw_, db_, dg_, dbe_ = dev(x), dev(w), dev(b), dev(gamma), dev(beta)
+    z, a = empty(B, H // 2, H // 2, Cout), empty(B, H // 2, H // 2, Cout)
+    call('uad_conv2d_fwd', ptr(dx_), ptr(dw_), ptr(db_), ptr(dg_), ptr(dbe_), ptr(z), ptr(a), B, H, H, Cin, Cout, 5,
+         abi.ACT_LEAKY, 0.3, bn_c, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(z.cpu().numpy(), z_ref) < TOL
+    assert relerr(a.cpu().numpy(), a_ref) < TOL
+    # dgrad / wgrad against autograd of the float64 oracle
+    dz = rng.standard_normal(z_ref.shape).astype(np.float32)
+    xt, wt = t64(x).requires_grad_(True), t64(w).requires_grad_(True)
+    y = O.conv2d_same_s2(xt.permute(0, 3, 1, 2), wt, t64(b)).permute(0, 2, 3, 1)
+    gx, gw = torch.autograd.grad((y * t64(dz)).sum(), [xt, wt])
+    ddz = dev(dz)
+    gxd = empty(B, H, H, Cin)
+    call('uad_conv2d_dgrad', ptr(ddz), ptr(dw_), ptr(gxd), B, H, H, Cin, Cout, 5, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
+    gwd = empty(5, 5, Cin, Cout)
+    call('uad_conv2d_wgrad', ptr(dx_), ptr(ddz), ptr(gwd), B, H, H, Cin, Cout, 5, 0, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(gwd.cpu().numpy(), gw.numpy()) < TOL
+    # accumulate
+    call('uad_conv2d_wgrad', ptr(dx_), ptr(ddz), ptr(gwd), B, H, H, Cin, Cout, 5, 1, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(gwd.cpu().numpy(), 2 * gw.numpy()) < TOL
+
+
+CONVT_SHAPES = [  # B, H(in), Cin, Cout
+    (2, 8, 128, 128), (2, 16, 128, 64), (3, 16, 64, 32), (2, 32, 32, 32), (1, 64, 32, 32), (5, 8, 32, 32),
+]
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('B,H,Cin,Cout', CONVT_SHAPES)
+def test_convT2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    L = abi.lib()
+    rng = np.random.default_rng(B * 977 + H + Cin + Cout)
+    x = rng.standard_normal((B, H, H, Cin)).astype(np.float32)
+    K = (rng.standard_normal((5, 5, Cout, Cin)) / math.sqrt(25 * Cin / 4)).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(Cout)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(Cout)).astype(np.float32)
+    bn_c = 1 / math.sqrt(1.001)
+    z_ref = oracle_convT(x, K, b)
+    u = gamma.astype(np.float64) * bn_c * z_ref + beta
+    a_ref = np.where(u > 0, u, 0.3 * u)
+    wsb = max(L.uad_conv_workspace_bytes(op, B, H, H, Cin, Cout, 5, mode) for op in (3, 4, 5))
+    ws = workspace(wsb)
+    dx_, dK_, db_, dg_, dbe_ = dev(x), dev(K), dev(b), dev(gamma), dev(beta)
+    z, a = empty(B, 2 * H, 2 * H, Cout), empty(B, 2 * H, 2 * H, Cout)
+    call('uad_convT2d_fwd', ptr(dx_), ptr(dK_), ptr(db_), ptr(dg_), ptr(dbe_), ptr(z), ptr(a), B, H, H, Cin, Cout, 5,
+         abi.ACT_LEAKY, 0.3, bn_c, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(z.cpu().numpy(), z_ref) < TOL
+    assert relerr(a.cpu().numpy(), a_ref) < TOL
+    dz = rng.standard_normal(z_ref.shape).astype(np.float32)
+    xt, Kt = t64(x).requires_grad_(True), t64(K).requires_grad_(True)
+    y = O.conv2dT_same_s2(xt.permute(0, 3, 1, 2), Kt, t64(b)).permute(0, 2, 3, 1)
+    gx, gK = torch.autograd.grad((y * t64(dz)).sum(), [xt, Kt])
+    ddz = dev(dz)
+    gxd = empty(B, H, H, Cin)
+    call('uad_convT2d_dgrad', ptr(ddz), ptr(dK_), ptr(gxd), B, H, H, Cin, Cout, 5, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
+    gKd = empty(5, 5, Cout, Cin)
+    call('uad_convT2d_wgrad', ptr(dx_), ptr(ddz), ptr(gKd), B, H, H, Cin, Cout, 5, 0, mode, ptr(ws), wsb, st())
+    sync()
+    assert relerr(gKd.cpu().numpy(), gK.numpy()) < TOL
+
+
+@pytest.mark.parametrize('B,H,Cout', [(2, 32, 32), (3, 128, 32), (1, 256, 32), (2, 16, 64)])
+def test_conv_first_layer_c1(B, H, Cout):
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    L = abi.lib()
+    rng = np.random.default_rng(H + Cout)
+    x = O.synthetic_slices(B, H, seed=3)
+    w = (rng.standard_normal((5, 5, 1, Cout)) / 5).astype(np.float32)
+    b = rng.standard_normal(Cout).astype(np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(Cout)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(Cout)).astype(np.float32)
+    bn_c = 1 / math.sqrt(1.001)
+    z_ref = oracle_conv(x, w, b)
+    u = gamma.astype(np.float64) * bn_c * z_ref + beta
+    a_ref = np.where(u > 0, u, 0.3 * u)
+    wsb = max(L.uad_conv_workspace_bytes(op, B, H, H, 1, Cout, 5, 0) for op in (0, 1, 2))
+    ws = workspace(wsb)
+    z, a = empty(B, H // 2, H // 2, Cout), empty(B, H // 2, H // 2, Cout)
+    dx_, dw_ = dev(x), dev(w)
+    call('uad_conv2d_fwd', ptr(dx_), ptr(dw_), ptr(dev(b)), ptr(dev(gamma)), ptr(dev(beta)), ptr(z), ptr(a), B, H, H, 1, Cout,
+         5, abi.ACT_LEAKY, 0.3, bn_c, 0, ptr(ws), wsb, st())
+    sync()
+    assert relerr(z.cpu().numpy(), z_ref) < TOL
+    assert relerr(a.cpu().numpy(), a_ref) < TOL
+    dz = rng.standard_normal(z_ref.shape).astype(np.float32)
+    xt, wt = t64(x).requires_grad_(True), t64(w).requires_grad_(True)
+    y = O.conv2d_same_s2(xt.permute(0, 3, 1, 2), wt, t64(b)).permute(0, 2, 3, 1)
+    gx, gw = torch.autograd.grad((y * t64(dz)).sum(), [xt, wt])
+    ddz = dev(dz)
+    gwd = empty(5, 5, 1, Cout)
+    call('uad_conv2d_wgrad', ptr(dx_), ptr(ddz), ptr(gwd), B, H, H, 1, Cout, 5, 0, 0, ptr(ws), wsb, st())
+    gxd = empty(B, H, H, 1)
+    call('uad_conv2d_dgrad', ptr(ddz), ptr(dw_), ptr(gxd), B, H, H, 1, Cout, 5, 0, ptr(ws), wsb, st())
+    sync()
+    assert relerr(gwd.cpu().numpy(), gw.numpy()) < TOL
+    assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
+
+
+@pytest.mark.parametrize('M,K,N,act', [(64, 1024, 128, 0), (256, 128, 16, 0), (256, 16, 128, 2), (7, 33, 19, 1), (64, 128, 1024, 0)])
+def test_dense_fwd_bwd(M, K, N, act):
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync
+    rng = np.random.default_rng(M + K + N)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / math.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    mask = (rng.uniform(size=(M, N)) >= 0.2).astype(np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(N)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(N)).astype(np.float32)
+    bn_c = 1 / math.sqrt(1.001)
+    keep = 1 / 0.8
+    xt, wt, bt = t64(x).requires_grad_(True), t64(w).requires_grad_(True), t64(b).requires_grad_(True)
+    z_ref = (xt @ wt + bt) * t64(mask) * keep
+    u = t64(gamma) * bn_c * z_ref + t64(beta)
+    a_ref = {0: u, 1: F.leaky_relu(u, 0.3), 2: F.relu(u)}[act]
+    z, a = empty(M, N), empty(M, N)
+    dx_, dw_, dm_ = dev(x), dev(w), dev(mask)
+    call('uad_dense_fwd', ptr(dx_), ptr(dw_), ptr(dev(b)), ptr(dm_), keep, ptr(dev(gamma)), ptr(dev(beta)), ptr(z), ptr(a), M, K,
+         N, act, 0.3, bn_c, st())
+    sync()
+    assert relerr(z.cpu().numpy(), z_ref.detach().numpy()) < TOL
+    assert relerr(a.cpu().numpy(), a_ref.detach().numpy()) < TOL
+    dz = rng.standard_normal((M, N)).astype(np.float32)
+    gx, gw, gb = torch.autograd.grad((z_ref * t64(dz)).sum(), [xt, wt, bt])
+    gxd, gwd, gbd = empty(M, K), empty(K, N), empty(N)
+    call('uad_dense_bwd', ptr(dx_), ptr(dw_), ptr(dev(dz)), ptr(dm_), keep, ptr(gxd), ptr(gwd), ptr(gbd), M, K, N, 0, st())
+    sync()
+    assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
+    assert relerr(gwd.cpu().numpy(), gw.numpy()) < TOL
+    assert relerr(gbd.cpu().numpy(), gb.numpy()) < TOL
+
+
+@pytest.mark.parametrize('rows,C,act', [(4096, 32, 1), (1000, 64, 1), (513, 128, 2), (64, 128, 1)])
+def test_act_bn_bwd(rows, C, act):
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    L = abi.lib()
+    rng = np.random.default_rng(rows + C)
+    z = rng.standard_normal((rows, C)).astype(np.float32)
+    da = rng.standard_normal((rows, C)).astype(np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(C)).astype(np.float32)
+    bn_c = 1 / math.sqrt(1.001)
+    zt, gt, bt = t64(z).requires_grad_(True), t64(gamma).requires_grad_(True), t64(beta).requires_grad_(True)
+    bias = torch.zeros(C, dtype=torch.float64, requires_grad=True)
+    u = gt * bn_c * (zt + bias) + bt
+    a = F.leaky_relu(u, 0.3) if act == 1 else F.relu(u)
+    gz, gg, gb, gbias = torch.autograd.grad((a * t64(da)).sum(), [zt, gt, bt, bias])
+    wsb = L.uad_rowreduce_workspace_bytes(rows, C)
+    ws = workspace(wsb)
+    dz, dg, db, dbias = empty(rows, C), empty(C), empty(C), empty(C)
+    call('uad_act_bn_bwd', ptr(dev(da)), ptr(dev(z)), ptr(dev(gamma)), ptr(dev(beta)), ptr(dz), ptr(dg), ptr(db), ptr(dbias),
+         rows, C, act, 0.3, bn_c, 0, ptr(ws), wsb, st())
+    sync()
+    assert relerr(dz.cpu().numpy(), gz.numpy()) < TOL
+    assert relerr(dg.cpu().numpy(), gg.numpy()) < TOL
+    assert relerr(db.cpu().numpy(), gb.numpy()) < TOL
+    assert relerr(dbias.cpu().numpy(), gbias.numpy()) < TOL
+
+
+def test_reparam_kl():
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync
+    rng = np.random.default_rng(5)
+    B, Z = 16, 128
+    mu = rng.standard_normal((B, Z)).astype(np.float32)
+    ls = (0.5 * rng.standard_normal((B, Z))).astype(np.float32)
+    eps = rng.standard_normal((B, Z)).astype(np.float32)
+    sig, z, kl = empty(B, Z), empty(B, Z), empty(B)
+    dmu_, dls_, deps_ = dev(mu), dev(ls), dev(eps)
+    call('uad_reparam_kl_fwd', ptr(dmu_), ptr(dls_), ptr(deps_), ptr(sig), ptr(z), ptr(kl), B, Z, st())
+    sync()
+    assert relerr(kl.cpu().numpy(), naive64.kl_per_sample(mu, ls)) < TOL
+    assert relerr(z.cpu().numpy(), mu.astype(np.float64) + eps * np.exp(ls.astype(np.float64))) < TOL
+    assert relerr(sig.cpu().numpy(), np.exp(ls.astype(np.float64))) < TOL
+    dz = rng.standard_normal((B, Z)).astype(np.float32)
+    mt, lt = t64(mu).requires_grad_(True), t64(ls).requires_grad_(True)
+    s = torch.exp(lt)
+    zz = mt + t64(eps) * s
+    klt = 0.5 * (mt ** 2 + s ** 2 - torch.log(s ** 2) - 1).sum(1)
+    gm, gl = torch.autograd.grad((zz * t64(dz)).sum() + klt.mean(), [mt, lt])
+    gmd, gld = empty(B, Z), empty(B, Z)
+    call('uad_reparam_kl_bwd', ptr(dmu_), ptr(dls_), ptr(deps_), ptr(dev(dz)), 1.0 / B, ptr(gmd), ptr(gld), B, Z, st())
+    sync()
+    assert relerr(gmd.cpu().numpy(), gm.numpy()) < TOL
+    assert relerr(gld.cpu().numpy(), gl.numpy()) < TOL
+
+
+@pytest.mark.parametrize('B,S', [(2, 32), (3, 128)])
+def test_final1x1_l1(B, S):
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    rng = np.random.default_rng(S)
+    C = 32
+    a = rng.standard_normal((B, S, S, C)).astype(np.float32)
+    w = (rng.standard_normal(C) / 4).astype(np.float32)
+    b = np.array([0.1], np.float32)
+    x = O.synthetic_slices(B, S, seed=9)
+    at, wt, bt = t64(a).requires_grad_(True), t64(w).requires_grad_(True), t64(b).requires_grad_(True)
+    xh = (at * wt).sum(-1, keepdim=True) + bt
+    l1 = (xh - t64(x)).abs()
+    rec = l1.sum(dim=(1, 2, 3))
+    ga, gw, gb = torch.autograd.grad(rec.mean(), [at, wt, bt])
+    ws = workspace(1 << 20)
+    xhd, l1d, recd = empty(B, S, S, 1), empty(B, S, S, 1), empty(B)
+    da_, dw_, dx_ = dev(a), dev(w), dev(x)
+    call('uad_final1x1_l1_fwd', ptr(da_), ptr(dw_), ptr(dev(b)), ptr(dx_), ptr(xhd), ptr(l1d), ptr(recd), B, S * S, C, ptr(ws),
+         1 << 20, st())
+    sync()
+    assert relerr(xhd.cpu().numpy(), xh.detach().numpy()) < TOL
+    assert relerr(l1d.cpu().numpy(), l1.detach().numpy()) < TOL
+    assert relerr(recd.cpu().numpy(), rec.detach().numpy()) < TOL
+    gad, gwd, gbd = empty(B, S, S, C), empty(C), empty(1)
+    call('uad_final1x1_l1_bwd', ptr(da_), ptr(dw_), ptr(dx_), ptr(xhd), 1.0 / B, ptr(gad), ptr(gwd), ptr(gbd), B, S * S, C, 0,
+         ptr(ws), 1 << 20, st())
+    sync()
+    assert relerr(gad.cpu().numpy(), ga.numpy()) < TOL
+    assert relerr(gwd.cpu().numpy(), gw.numpy()) < 5 * TOL   # sum of +-1/B signs: cancellation-dominated
+    assert relerr(gbd.cpu().numpy(), gb.numpy()) < 5 * TOL
+
+
+def test_adam_tf():
+    from gpu_util import call, dev, ptr, relerr, st, sync
+    rng = np.random.default_rng(11)
+    n = 100003
+    p = rng.standard_normal(n).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    m = (0.1 * rng.standard_normal(n)).astype(np.float32)
+    v = (0.1 * rng.uniform(size=n)).astype(np.float32)
+    t, lr = 3, 1e-3
+    pr, mr, vr = naive64.adam_tf(p.astype(np.float64), 0.5 * g.astype(np.float64), m.astype(np.float64), v.astype(np.float64),
+                                 t, lr)
+    lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t)
+    pd, md, vd = dev(p), dev(m), dev(v)
+    call('uad_adam_tf_step', ptr(pd), ptr(dev(g)), ptr(md), ptr(vd), n, lr_t, 0.5, 0.999, 1e-8, 0.5, None, st())
+    sync()
+    assert relerr(pd.cpu().numpy(), pr) < 1e-6
+    assert relerr(md.cpu().numpy(), mr) < 1e-6
+    assert relerr(vd.cpu().numpy(), vr) < 1e-6
+
+
+def test_rng_streams():
+    from gpu_util import call, empty, ptr, st, sync
+    n = 1 << 20
+    a, b = empty(n), empty(n)
+    call('uad_randn', ptr(a), n, 1234, 0, None, st())
+    call('uad_randn', ptr(b), n, 1234, 0, None, st())
+    sync()
+    an = a.cpu().numpy()
+    assert np.array_equal(an, b.cpu().numpy())
+    assert abs(an.mean()) < 5e-3 and abs(an.std() - 1) < 5e-3
+    m = empty(n)
+    call('uad_dropout_mask', ptr(m), n, 0.2, 99, 0, None, st())
+    sync()
+    mn = m.cpu().numpy()
+    assert set(np.unique(mn)) <= {0.0, 1.0}
+    assert abs(mn.mean() - 0.8) < 5e-3
+
+
+@pytest.mark.parametrize('keep_positive,apply_prior', [(1, 1), (0, 1), (1, 0)])
+def test_residual_score_bitexact(keep_positive, apply_prior):
+    from gpu_util import call, dev, empty, ptr, st, sync
+    rng = np.random.default_rng(21)
+    N, S = 7, 64
+    x = O.synthetic_slices(N, S, seed=5)[..., 0]
+    xr = np.clip(x + 0.1 * rng.standard_normal(x.shape), 0, 1).astype(np.float32)
+    mask = np.stack([oscore.erode_brainmask(x[i] > 0, 3) for i in range(N)])
+    prior = float(np.quantile(x, 0.9))
+    ref = oscore.residual(x, xr, mask, prior, bool(keep_positive), bool(apply_prior))
+    d = empty(N, S, S)
+    call('uad_residual_score', ptr(dev(x)), ptr(dev(xr)), ptr(dev(mask.astype(np.uint8), torch.uint8)), prior, keep_positive,
+         apply_prior, ptr(d), x.size, st())
+    sync()
+    got = d.cpu().numpy()
+    assert np.array_equal(got.astype(np.float64), ref)
+
+
+def test_threshold_counts_bitexact():
+    from gpu_util import call, dev, ptr, st, sync
+    rng = np.random.default_rng(31)
+    n = 110 * 64 * 64 + 3
+    diff = np.maximum(rng.standard_normal(n) * 0.2, 0).astype(np.float32)
+    diff[::7] = np.float32(0.3)          # exact ties with a threshold that is not fp32-representable
+    label = (rng.uniform(size=n) < 0.05).astype(np.uint8)
+    thr = [0.0, 0.1, 0.2, 0.30000000000000004, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9]
+    arr = (ctypes.c_double * len(thr))(*thr)
+    counts = torch.zeros(len(thr) * 3, dtype=torch.int64, device='cuda:0')
+    mask = torch.zeros(n, dtype=torch.uint8, device='cuda:0')
+    call('uad_threshold_counts', ptr(dev(diff)), ptr(dev(label, torch.uint8)), n, arr, len(thr), ptr(counts), ptr(mask), st())
+    sync()
+    got = counts.cpu().numpy().reshape(-1, 3)
+    d64 = diff.astype(np.float64)
+    for i, t in enumerate(thr):
+        assert tuple(got[i]) == oscore.counts(d64, label.astype(np.int64), t)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), oscore.threshold_mask(d64, thr[0]))

@@ -1,0 +1,122 @@
+"""Whole-graph parity: forward, losses, every gradient and the post-Adam weights of the CUDA engine against the
+oracle restatement of the reference's TF graph, on identical synthetic inputs, weights, eps and dropout masks.
+Tolerance 1e-4 relative (north_star) on every tensor; BASELINE.json configs[0] (dense AE 128x128 B=16) included."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tf_graph_cpu as O  # noqa: E402
+
+TOL = 1e-4
+
+
+def _relerr(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+def _noise(arch, B, zDim, flat, rate, seed=3):
+    rng = np.random.default_rng(seed)
+    eps = rng.standard_normal((B, zDim)).astype(np.float32)
+
+    def mk(n):
+        return (rng.uniform(size=(B, n)) >= rate).astype(np.float32)
+
+    if arch == O.AE:
+        om = {'z': mk(zDim)}
+        em, emc = {'mu': om['z']}, None
+    else:
+        om = {'mu': mk(zDim), 'log_sigma': mk(zDim), 'dec': mk(flat)}
+        em, emc = {'mu': om['mu'], 'ls': om['log_sigma'], 'dec': om['dec']}, None
+        if arch == O.CEVAE:
+            om.update(mu_ce=mk(zDim), dec_ce=mk(flat))
+            emc = {'mu': om['mu_ce'], 'dec': om['dec_ce']}
+    return eps, om, em, emc
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('arch,S,B', [(O.AE, 128, 16), (O.VAE, 64, 4), (O.VAE, 256, 2), (O.CEVAE, 64, 3)])
+def test_train_step_parity(arch, S, B, mode):
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
+    rate, lr = 0.2, 1e-3
+    P = O.perturb_params(O.init_params(arch, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=1234)
+    x_ce = x.copy()
+    x_ce[:, S // 4:S // 4 + 20, S // 3:S // 3 + 20] = 0
+    eng = ConvAutoencoderEngine(arch, S, batch=B, math_mode=mode)
+    assert list(eng.specs.keys()) == list(P.keys())
+    eng.fp.load(P)
+    eps, om, em, emc = _noise(arch, B, 128, eng.flat, rate)
+    eng.set_inputs(x, x_ce if arch == O.CEVAE else None)
+    eng.set_noise(eps, em, emc)
+    want_anom = arch == O.CEVAE
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True, want_anomaly=want_anom)
+    torch.cuda.synchronize()
+
+    out, L, G = O.loss_and_grads(arch, P, x, x_ce=x_ce, eps=eps, masks=om, dropout_rate=rate, training=True,
+                                 dtype=torch.float64, want_anomaly=want_anom)
+    got = eng.losses()
+    assert abs(got['loss'] - float(L['loss'])) / abs(float(L['loss'])) < TOL
+    assert abs(got['reconstructionLoss'] - float(L['reconstructionLoss'])) / abs(float(L['reconstructionLoss'])) < TOL
+    if arch != O.AE:
+        assert abs(got['kl'] - float(L['kl'])) / abs(float(L['kl'])) < TOL
+    b0 = eng.br[0]
+    assert _relerr(b0.xhat.cpu().numpy(), out['x_hat'].numpy()) < TOL
+    if arch == O.CEVAE:
+        assert _relerr(eng.br[1].xhat.cpu().numpy(), out['x_hat_ce'].numpy()) < TOL
+        assert _relerr(eng.anomaly.cpu().numpy(), L['anomaly'].numpy()) < 5 * TOL
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    worst = max((_relerr(grads[k], G[k].numpy()), k) for k in P)
+    assert worst[0] < 5 * TOL, worst
+    # post-Adam weights: first step is ~ lr*sign(g), so compare the UPDATE relative to lr
+    Pn, _, _ = O.adam_tf({k: torch.from_numpy(v).double() for k, v in P.items()}, G,
+                         {k: torch.zeros_like(g) for k, g in G.items()}, {k: torch.zeros_like(g) for k, g in G.items()},
+                         1, lr, 0.5)
+    newp = eng.fp.to_numpy()
+    bad = 0
+    tot = 0
+    for k in P:
+        d = np.abs(newp[k].astype(np.float64) - Pn[k].numpy())
+        bad += int((d > 1e-3 * lr).sum())
+        tot += d.size
+        assert float(d.max()) <= 2.001 * lr, k
+    assert bad / tot < 1e-3, (bad, tot)     # sign flips only where |g| is at rounding level
+
+
+@pytest.mark.parametrize('arch', [O.AE, O.VAE])
+def test_inference_forward_matches_training_forward(arch):
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
+    S, B = 64, 4
+    P = O.perturb_params(O.init_params(arch, S, seed=2))
+    x = O.synthetic_slices(B, S, seed=7)
+    eng = ConvAutoencoderEngine(arch, S, batch=B)
+    eng.fp.load(P)
+    eps = np.random.default_rng(0).standard_normal((B, 128)).astype(np.float32)
+    eng.set_inputs(x)
+    eng.set_noise(eps)
+    eng.forward(training=False, dropout_rate=0.0)
+    torch.cuda.synchronize()
+    out = O.forward(arch, P, x, eps=eps, training=False, dtype=torch.float64)
+    assert _relerr(eng.br[0].xhat.cpu().numpy(), out['x_hat'].numpy()) < TOL
+
+
+def test_multi_step_training_tracks_oracle():
+    """5 optimiser steps of VAE 64x64: the loss trajectory must follow the oracle's."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
+    arch, S, B, lr = O.VAE, 64, 8, 1e-4
+    P = O.init_params(arch, S, seed=1)
+    eng = ConvAutoencoderEngine(arch, S, batch=B)
+    eng.fp.load(P)
+    tr = O.Trainer(arch, P, lr=lr, dropout_rate=0.2, dtype=torch.float64)
+    for step in range(5):
+        x = O.synthetic_slices(B, S, seed=100 + step)
+        eps, om, em, _ = _noise(arch, B, 128, eng.flat, 0.2, seed=step)
+        eng.set_inputs(x)
+        eng.set_noise(eps, em)
+        eng.train_step(lr, dropout_rate=0.2, dropout=True, parity_noise=True)
+        _, L, _ = tr.step(x, eps=eps, masks=om)
+        got = eng.losses()['loss']
+        assert abs(got - float(L['loss'])) / abs(float(L['loss'])) < 2e-4, (step, got, float(L['loss']))

@@ -1,0 +1,169 @@
+// Small dense / 1x1-conv GEMMs (bottleneck layers: < 0.1 % of the step's FLOPs) with the same fused epilogue as the convs.
+#include "uad_common.cuh"
+
+// C[M,N] = sum_k A(m,k) * B(k,n), A(m,k) = A[m*sa_m + k*sa_k] * (Amul ? Amul[...] * mulscale : 1), same for B.
+struct SmallGemm {
+  const float* A; const float* Amul; long long sa_m, sa_k;
+  const float* Bm; const float* Bmul; long long sb_k, sb_n;
+  float mulscale;
+  int M, N, K;
+  // epilogue
+  const float* bias; const float* mask; float mask_scale;
+  const float* gamma; const float* beta; float bn_c; int act; float alpha;
+  float* z_out; float* a_out;   // row-major [M,N]
+  int accumulate;               // z_out += (plain accumulation mode: no bias/mask/affine expected)
+};
+
+__global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__ SmallGemm g) {
+  constexpr int T = 64, BK = 16;
+  __shared__ float As[BK][T + 1];
+  __shared__ float Bs[BK][T + 1];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * T, n0 = blockIdx.y * T;
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    for (int i = tid; i < T * BK; i += 256) {
+      int kk, mm;
+      if (g.sa_k == 1) { kk = i % BK; mm = i / BK; } else { mm = i % T; kk = i / T; }
+      int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if (m < g.M && k < g.K) {
+        long long off = m * g.sa_m + k * g.sa_k;
+        v = g.A[off];
+        if (g.Amul) v *= g.Amul[off] * g.mulscale;
+      }
+      As[kk][mm] = v;
+    }
+    for (int i = tid; i < T * BK; i += 256) {
+      int kk, nn;
+      if (g.sb_n == 1) { nn = i % T; kk = i / T; } else { kk = i % BK; nn = i / BK; }
+      int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if (n < g.N && k < g.K) {
+        long long off = k * g.sb_k + n * g.sb_n;
+        v = g.Bm[off];
+        if (g.Bmul) v *= g.Bmul[off] * g.mulscale;
+      }
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty + 16 * i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx + 16 * j;
+      if (n >= g.N) continue;
+      size_t o = (size_t)m * g.N + n;
+      float z = acc[i][j];
+      if (g.accumulate) { g.z_out[o] += z; continue; }
+      if (g.bias) z += g.bias[n];
+      if (g.mask) z *= g.mask[o] * g.mask_scale;
+      if (g.z_out) g.z_out[o] = z;
+      if (g.a_out) {
+        float u = z;
+        if (g.gamma) u = g.gamma[n] * g.bn_c * z + g.beta[n];
+        g.a_out[o] = uad_act(u, g.act, g.alpha);
+      }
+    }
+  }
+}
+
+static int launch_small(const SmallGemm& g, cudaStream_t st) {
+  dim3 grid(uad_cdiv(g.M, 64), uad_cdiv(g.N, 64));
+  small_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  UAD_LAUNCH_CHECK("small_gemm");
+  return 0;
+}
+
+// dbias[n] (+)= sum_m dz[m,n] * (mask ? mask*scale : 1)      (one block per 32 columns, deterministic)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dz, const float* __restrict__ mask, float scale,
+                                                     float* __restrict__ out, int M, int N, int accumulate) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (n < N)
+    for (int m = warp; m < M; m += 8) {
+      float v = dz[(size_t)m * N + n];
+      if (mask) v *= mask[(size_t)m * N + n] * scale;
+      s += v;
+    }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[n] = accumulate ? out[n] + t : t;
+  }
+}
+
+extern "C" int uad_dense_fwd(const float* x, const float* w, const float* bias, const float* mask, float mask_scale,
+                             const float* gamma, const float* beta, float* z_out, float* a_out, int M, int K, int N,
+                             int act, float alpha, float bn_c, void* stream) {
+  UAD_REQUIRE(M > 0 && K > 0 && N > 0, "uad_dense_fwd: bad dims");
+  UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_dense_fwd: gamma/beta must both be set or both NULL");
+  SmallGemm g = {};
+  g.A = x; g.sa_m = K; g.sa_k = 1;
+  g.Bm = w; g.sb_k = N; g.sb_n = 1;
+  g.mulscale = 1.f;
+  g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.mask = mask; g.mask_scale = mask_scale;
+  g.gamma = gamma; g.beta = beta; g.bn_c = bn_c; g.act = act; g.alpha = alpha;
+  g.z_out = z_out; g.a_out = a_out;
+  return launch_small(g, (cudaStream_t)stream);
+}
+
+extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, const float* mask, float mask_scale,
+                             float* dx, float* dw, float* dbias, int M, int K, int N, int accumulate, void* stream) {
+  UAD_REQUIRE(M > 0 && K > 0 && N > 0, "uad_dense_bwd: bad dims");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {   // dx[M,K] = (dz*mask)[M,N] . W^T[N,K]
+    SmallGemm g = {};
+    g.A = dz; g.Amul = mask; g.sa_m = N; g.sa_k = 1;
+    g.Bm = w; g.sb_k = 1; g.sb_n = N;           // B(k'=n, n'=k) = W[k*N + n]
+    g.mulscale = mask_scale;
+    g.M = M; g.N = K; g.K = N;
+    g.z_out = dx;
+    if (int e = launch_small(g, st)) return e;
+  }
+  if (dw) {   // dw[K,N] (+)= x^T[K,M] . (dz*mask)[M,N]
+    SmallGemm g = {};
+    g.A = x; g.sa_m = 1; g.sa_k = K;            // A(m'=k, k'=m) = x[m*K + k]
+    g.Bm = dz; g.Bmul = mask; g.sb_k = N; g.sb_n = 1;
+    g.mulscale = mask_scale;
+    g.M = K; g.N = N; g.K = M;
+    g.z_out = dw; g.accumulate = accumulate;
+    if (!accumulate) {
+      // plain store path: no bias/mask/affine set -> z_out = acc
+    }
+    if (int e = launch_small(g, st)) return e;
+  }
+  if (dbias) {
+    colsum_kernel<<<uad_cdiv(N, 32), 256, 0, st>>>(dz, mask, mask_scale, dbias, M, N, accumulate);
+    UAD_LAUNCH_CHECK("colsum");
+  }
+  return 0;
+}

@@ -1,0 +1,468 @@
+// HBM-bound elementwise / reduction kernels of the hot path: BN+activation backward, reparameterise+KL, fused final
+// 1x1 conv + L1, loss scalars, TF-form Adam, Philox RNG, small helpers.  All reductions are two-stage and deterministic.
+#include "uad_common.cuh"
+
+// ------------------------------------------------------------------------------------------------ error plumbing
+static thread_local char g_uad_err[512] = "";
+
+int uad_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_uad_err, sizeof(g_uad_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+extern "C" const char* uad_last_error(void) { return g_uad_err; }
+extern "C" int uad_abi_version(void) { return UAD_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------ act + frozen-BN backward
+// stage 1: dz = gamma*bn_c * da * act'(u), per-block partial sums of du and du*z per channel
+__global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict__ da, const float* __restrict__ z,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float* __restrict__ dz, float* __restrict__ partial, long long rows,
+                                                         int C, int act, float alpha, float bn_c) {
+  __shared__ float red[2][256][4];
+  const int tpr = C / 4;                 // threads per row
+  const int cg = threadIdx.x % tpr;      // channel group (4 channels)
+  const int rl = threadIdx.x / tpr;
+  const int rpp = 256 / tpr;             // rows per pass
+  float sc[4], sf[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = gamma ? gamma[cg * 4 + j] * bn_c : 1.f;
+    sf[j] = beta ? beta[cg * 4 + j] : 0.f;
+  }
+  float s_du[4] = {0.f, 0.f, 0.f, 0.f}, s_duz[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = (long long)blockIdx.x * rpp + rl; r < rows; r += (long long)gridDim.x * rpp) {
+    const size_t o = (size_t)r * C + cg * 4;
+    const float4 g4 = *reinterpret_cast<const float4*>(da + o);
+    const float4 z4 = *reinterpret_cast<const float4*>(z + o);
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, zv[4] = {z4.x, z4.y, z4.z, z4.w};
+    float out[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = sc[j] * zv[j] + sf[j];
+      float du = gv[j] * uad_act_grad(u, act, alpha);
+      s_du[j] += du;
+      s_duz[j] += du * zv[j];
+      out[j] = sc[j] * du;
+    }
+    *reinterpret_cast<float4*>(dz + o) = make_float4(out[0], out[1], out[2], out[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][threadIdx.x][j] = s_du[j];
+    red[1][threadIdx.x][j] = s_duz[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    const int which = threadIdx.x / C, c = threadIdx.x % C;
+    float s = 0.f;
+    for (int k = 0; k < rpp; ++k) s += red[which][k * tpr + c / 4][c % 4];
+    partial[(size_t)blockIdx.x * 2 * C + threadIdx.x] = s;
+  }
+}
+
+// stage 2: reduce block partials, finalise dgamma / dbeta / dbias
+__global__ void act_bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ gamma,
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                        int C, float bn_c, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s_du = 0.f, s_duz = 0.f;
+  for (int b = 0; b < nblocks; ++b) {
+    s_du += partial[(size_t)b * 2 * C + c];
+    s_duz += partial[(size_t)b * 2 * C + C + c];
+  }
+  const float sc = gamma ? gamma[c] * bn_c : 1.f;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bn_c * s_duz;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + s_du;
+  if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + sc * s_du;
+}
+
+static int rowreduce_blocks(long long rows, int C) {
+  const int rpp = 256 / (C / 4);
+  long long b = (rows + rpp - 1) / rpp;
+  const long long cap = 4 * UAD_NUM_SMS;
+  return (int)(b < cap ? b : cap);
+}
+
+extern "C" size_t uad_rowreduce_workspace_bytes(long long rows, int C) {
+  if (C < 4 || C % 4) return 0;
+  return (size_t)rowreduce_blocks(rows, C) * 2 * C * sizeof(float) + 256;
+}
+
+extern "C" int uad_act_bn_bwd(const float* da, const float* z, const float* gamma, const float* beta, float* dz,
+                              float* dgamma, float* dbeta, float* dbias, long long rows, int C, int act, float alpha,
+                              float bn_c, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  UAD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 128 && 256 % (C / 4) == 0, "uad_act_bn_bwd: unsupported C=%d", C);
+  UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_act_bn_bwd: gamma/beta must both be set or both NULL");
+  const int nb = rowreduce_blocks(rows, C);
+  UAD_REQUIRE(ws && ws_bytes >= (size_t)nb * 2 * C * sizeof(float), "uad_act_bn_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  act_bn_bwd_kernel<<<nb, 256, 0, st>>>(da, z, gamma, beta, dz, (float*)ws, rows, C, act, alpha, bn_c);
+  UAD_LAUNCH_CHECK("act_bn_bwd");
+  act_bn_bwd_final_kernel<<<uad_cdiv(C, 128), 128, 0, st>>>((const float*)ws, nb, gamma, dgamma, dbeta, dbias, C, bn_c,
+                                                            accumulate);
+  UAD_LAUNCH_CHECK("act_bn_bwd_final");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ reparameterise + KL
+__global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
+                                      float* __restrict__ sigma, float* __restrict__ z, float* __restrict__ kl, int Z) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int j = threadIdx.x; j < Z; j += blockDim.x) {
+    const size_t o = (size_t)b * Z + j;
+    const float m = mu[o], sg = expf(ls[o]);
+    if (sigma) sigma[o] = sg;
+    if (z) z[o] = eps ? m + eps[o] * sg : m;
+    const float s2 = sg * sg;
+    s += m * m + s2 - logf(s2) - 1.f;     // trainers/VAE.py:38 literally
+  }
+  s = uad_warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    if (kl) kl[b] = 0.5f * t;
+  }
+}
+
+extern "C" int uad_reparam_kl_fwd(const float* mu, const float* log_sigma, const float* eps, float* sigma, float* z,
+                                  float* kl, int B, int Z, void* stream) {
+  UAD_REQUIRE(B > 0 && Z > 0, "uad_reparam_kl_fwd: bad dims");
+  reparam_kl_fwd_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(mu, log_sigma, eps, sigma, z, kl, Z);
+  UAD_LAUNCH_CHECK("reparam_kl_fwd");
+  return 0;
+}
+
+__global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
+                                      const float* __restrict__ dz, float kl_scale, float* __restrict__ dmu,
+                                      float* __restrict__ dls, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float sg = expf(ls[i]);
+  const float g = dz ? dz[i] : 0.f;
+  dmu[i] = g + kl_scale * mu[i];
+  // d/dls of 0.5*(sigma^2 - log(sigma^2) - 1) = sigma^2 - 1 ; z = mu + eps*sigma -> dz/dls = eps*sigma
+  dls[i] = (eps ? g * eps[i] * sg : 0.f) + kl_scale * (sg * sg - 1.f);
+}
+
+extern "C" int uad_reparam_kl_bwd(const float* mu, const float* log_sigma, const float* eps, const float* dz,
+                                  float kl_scale, float* dmu, float* dls, int B, int Z, void* stream) {
+  size_t n = (size_t)B * Z;
+  reparam_kl_bwd_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, log_sigma, eps, dz, kl_scale, dmu, dls, n);
+  UAD_LAUNCH_CHECK("reparam_kl_bwd");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ final 1x1 + L1
+// lanes-per-pixel LP = Cin/4; each lane holds a float4 of channels; a block covers `ppb` pixels of ONE sample.
+__global__ void __launch_bounds__(256) final1x1_l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const float* __restrict__ x,
+                                                              float* __restrict__ xhat, float* __restrict__ l1,
+                                                              float* __restrict__ partial, int HW, int Cin, int ppb) {
+  __shared__ float red[8];
+  const int LP = Cin / 4;
+  const int lp = threadIdx.x % LP;
+  const int pl = threadIdx.x / LP;
+  const int ppp = 256 / LP;                              // pixels per pass
+  const int bps = HW / ppb;                              // blocks per sample
+  const int b = blockIdx.x / bps;
+  const size_t pix0 = (size_t)b * HW + (size_t)(blockIdx.x % bps) * ppb;
+  const float4 w4 = *reinterpret_cast<const float4*>(w + lp * 4);
+  const float bv = bias ? bias[0] : 0.f;
+  float s = 0.f;
+  for (int q = pl; q < ppb; q += ppp) {
+    const size_t pix = pix0 + q;
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(a + pix * Cin + lp * 4));
+    float d = a4.x * w4.x + a4.y * w4.y + a4.z * w4.z + a4.w * w4.w;
+    for (int o = LP >> 1; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lp == 0) {
+      const float xh = d + bv;
+      const float e = fabsf(xh - x[pix]);
+      xhat[pix] = xh;
+      if (l1) l1[pix] = e;
+      s += e;
+    }
+  }
+  s = uad_warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0 && partial) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += red[wv];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void rec_final_kernel(const float* __restrict__ partial, int bps, float* __restrict__ rec, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f;
+  for (int k = 0; k < bps; ++k) s += partial[(size_t)b * bps + k];
+  rec[b] = s;
+}
+
+static int final_ppb(int HW) { return HW < 2048 ? HW : 2048; }
+
+extern "C" int uad_final1x1_l1_fwd(const float* a, const float* w, const float* bias, const float* x, float* xhat,
+                                   float* l1, float* rec, int B, int HW, int Cin, void* ws, size_t ws_bytes, void* stream) {
+  UAD_REQUIRE(Cin % 4 == 0 && uad_is_pow2(Cin / 4) && Cin <= 128, "uad_final1x1_l1_fwd: unsupported Cin=%d", Cin);
+  UAD_REQUIRE(uad_is_pow2(HW), "uad_final1x1_l1_fwd: HW=%d must be a power of two", HW);
+  const int ppb = final_ppb(HW), bps = HW / ppb;
+  UAD_REQUIRE(ppb % (256 / (Cin / 4)) == 0, "uad_final1x1_l1_fwd: HW=%d too small for Cin=%d", HW, Cin);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = nullptr;
+  if (rec) {
+    UAD_REQUIRE(ws && ws_bytes >= (size_t)B * bps * sizeof(float), "uad_final1x1_l1_fwd: workspace too small");
+    partial = (float*)ws;
+  }
+  final1x1_l1_fwd_kernel<<<B * bps, 256, 0, st>>>(a, w, bias, x, xhat, l1, partial, HW, Cin, ppb);
+  UAD_LAUNCH_CHECK("final1x1_l1_fwd");
+  if (rec) {
+    rec_final_kernel<<<uad_cdiv(B, 128), 128, 0, st>>>(partial, bps, rec, B);
+    UAD_LAUNCH_CHECK("rec_final");
+  }
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) final1x1_l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                                              const float* __restrict__ x, const float* __restrict__ xhat,
+                                                              float scale, float* __restrict__ da, float* __restrict__ partial,
+                                                              size_t npix, int Cin) {
+  __shared__ float red[256][5];
+  const int LP = Cin / 4;
+  const int lp = threadIdx.x % LP;
+  const int pl = threadIdx.x / LP;
+  const int ppp = 256 / LP;
+  const float4 w4 = *reinterpret_cast<const float4*>(w + lp * 4);
+  float sw[4] = {0.f, 0.f, 0.f, 0.f}, sb = 0.f;
+  for (size_t pix = (size_t)blockIdx.x * ppp + pl; pix < npix; pix += (size_t)gridDim.x * ppp) {
+    const float e = xhat[pix] - x[pix];
+    const float g = (e > 0.f ? scale : (e < 0.f ? -scale : 0.f));
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(a + pix * Cin + lp * 4));
+    sw[0] += g * a4.x; sw[1] += g * a4.y; sw[2] += g * a4.z; sw[3] += g * a4.w;
+    if (lp == 0) sb += g;
+    if (da) *reinterpret_cast<float4*>(da + pix * Cin + lp * 4) = make_float4(g * w4.x, g * w4.y, g * w4.z, g * w4.w);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.x][j] = sw[j];
+  red[threadIdx.x][4] = sb;
+  __syncthreads();
+  if (threadIdx.x <= Cin) {
+    float s = 0.f;
+    if (threadIdx.x < Cin) {
+      const int c = threadIdx.x;
+      for (int k = 0; k < ppp; ++k) s += red[k * LP + c / 4][c % 4];
+    } else {
+      for (int k = 0; k < ppp; ++k) s += red[k * LP][4];
+    }
+    partial[(size_t)blockIdx.x * (Cin + 1) + threadIdx.x] = s;
+  }
+}
+
+__global__ void final_bwd_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cin, float* __restrict__ dw,
+                                        float* __restrict__ dbias, int accumulate) {
+  const int c = threadIdx.x;
+  if (c > Cin) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * (Cin + 1) + c];
+  if (c < Cin) { if (dw) dw[c] = (accumulate ? dw[c] : 0.f) + s; }
+  else { if (dbias) dbias[0] = (accumulate ? dbias[0] : 0.f) + s; }
+}
+
+extern "C" int uad_final1x1_l1_bwd(const float* a, const float* w, const float* x, const float* xhat, float scale,
+                                   float* da, float* dw, float* dbias, int B, int HW, int Cin, int accumulate, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  UAD_REQUIRE(Cin % 4 == 0 && uad_is_pow2(Cin / 4) && Cin <= 128, "uad_final1x1_l1_bwd: unsupported Cin=%d", Cin);
+  const size_t npix = (size_t)B * HW;
+  const int ppp = 256 / (Cin / 4);
+  long long nb = (npix + ppp - 1) / ppp;
+  if (nb > 4 * UAD_NUM_SMS) nb = 4 * UAD_NUM_SMS;
+  UAD_REQUIRE(ws && ws_bytes >= (size_t)nb * (Cin + 1) * sizeof(float), "uad_final1x1_l1_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  final1x1_l1_bwd_kernel<<<(int)nb, 256, 0, st>>>(a, w, x, xhat, scale, da, (float*)ws, npix, Cin);
+  UAD_LAUNCH_CHECK("final1x1_l1_bwd");
+  final_bwd_reduce_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)nb, Cin, dw, dbias, accumulate);
+  UAD_LAUNCH_CHECK("final_bwd_reduce");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ loss scalars
+__global__ void loss_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl, float* __restrict__ out, int B) {
+  __shared__ float red[3][32];
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const float r = rec[i], k = kl ? kl[i] : 0.f;
+    a += r; b += k; c += r + k;
+  }
+  a = uad_warp_sum(a); b = uad_warp_sum(b); c = uad_warp_sum(c);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; red[2][threadIdx.x >> 5] = c; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < blockDim.x / 32; ++w) s += red[threadIdx.x][w];
+    out[threadIdx.x] = s / (float)B;
+  }
+}
+
+extern "C" int uad_loss_scalars(const float* rec, const float* kl, float* out3, int B, void* stream) {
+  loss_scalars_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rec, kl, out3, B);
+  UAD_LAUNCH_CHECK("loss_scalars");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ TF-form Adam
+__global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                               size_t n, float lr_t, float b1, float b2, float eps, float gs,
+                               const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = *lr_dev;
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 p4 = *reinterpret_cast<float4*>(p + i), g4 = *reinterpret_cast<const float4*>(g + i);
+    float4 m4 = *reinterpret_cast<float4*>(m + i), v4 = *reinterpret_cast<float4*>(v + i);
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gg[j] * gs;
+      mm[j] = b1 * mm[j] + (1.f - b1) * gj;
+      vv[j] = b2 * vv[j] + (1.f - b2) * gj * gj;
+      pp[j] = pp[j] - lr_t * mm[j] / (sqrtf(vv[j]) + eps);
+    }
+    *reinterpret_cast<float4*>(p + i) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  } else {
+    for (; i < n; ++i) {
+      const float gj = g[i] * gs;
+      const float mj = b1 * m[i] + (1.f - b1) * gj;
+      const float vj = b2 * v[i] + (1.f - b2) * gj * gj;
+      m[i] = mj; v[i] = vj;
+      p[i] = p[i] - lr_t * mj / (sqrtf(vj) + eps);
+    }
+  }
+}
+
+extern "C" int uad_adam_tf_step(float* params, const float* grads, float* m, float* v, size_t n, float lr_t, float b1,
+                                float b2, float eps, float grad_scale, const float* lr_t_dev, void* stream) {
+  UAD_REQUIRE(((uintptr_t)params % 16 == 0) && ((uintptr_t)grads % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
+              ((uintptr_t)v % 16 == 0), "uad_adam_tf_step: buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  adam_tf_kernel<<<uad_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr_t, b1, b2, eps,
+                                                                              grad_scale, lr_t_dev);
+  UAD_LAUNCH_CHECK("adam_tf");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Philox-4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void randn_kernel(float* __restrict__ out, size_t n, uint64_t seed, uint64_t offset,
+                             const uint64_t* __restrict__ offset_dev) {
+  if (offset_dev) offset += *offset_dev;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  const uint64_t ctr = offset + q;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0x5eedu, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float r[4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;      // (0,1]
+    const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    r[2 * h] = rad * cs;
+    r[2 * h + 1] = rad * sn;
+  }
+  for (int j = 0; j < 4 && q * 4 + j < n; ++j) out[q * 4 + j] = r[j];
+}
+
+extern "C" int uad_randn(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream) {
+  if (n == 0) return 0;
+  randn_kernel<<<uad_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, offset_dev);
+  UAD_LAUNCH_CHECK("randn");
+  return 0;
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ mask, size_t n, float rate, uint64_t seed, uint64_t offset,
+                                    const uint64_t* __restrict__ offset_dev) {
+  if (offset_dev) offset += *offset_dev;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  const uint64_t ctr = offset + q;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0xd509u, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int j = 0; j < 4 && q * 4 + j < n; ++j) {
+    const float u = (float)(c[j] >> 8) * 5.9604644775390625e-08f;             // [0,1)
+    mask[q * 4 + j] = (u >= rate) ? 1.f : 0.f;                                // Keras: keep where uniform >= rate
+  }
+}
+
+extern "C" int uad_dropout_mask(float* mask, size_t n, float rate, uint64_t seed, uint64_t offset,
+                                const uint64_t* offset_dev, void* stream) {
+  if (n == 0) return 0;
+  dropout_mask_kernel<<<uad_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, rate, seed, offset, offset_dev);
+  UAD_LAUNCH_CHECK("dropout_mask");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+__global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
+extern "C" int uad_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, inc);
+  UAD_LAUNCH_CHECK("counter_add");
+  return 0;
+}
+__global__ void mul_abs_kernel(const float* __restrict__ l1, const float* __restrict__ gx, float* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = l1[i] * fabsf(gx[i]);
+}
+extern "C" int uad_mul_abs(const float* l1, const float* gx, float* out, size_t n, void* stream) {
+  if (n == 0) return 0;
+  mul_abs_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(l1, gx, out, n);
+  UAD_LAUNCH_CHECK("mul_abs");
+  return 0;
+}
+
+__global__ void axpby_kernel(float a, const float* __restrict__ x, float b, float* __restrict__ y, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i] + (b != 0.f ? b * y[i] : 0.f);
+}
+extern "C" int uad_axpby(float a, const float* x, float b, float* y, size_t n, void* stream) {
+  if (n == 0) return 0;
+  axpby_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(a, x, b, y, n);
+  UAD_LAUNCH_CHECK("axpby");
+  return 0;
+}
+
+__global__ void l1_direct_term_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float scale,
+                                      float* __restrict__ gx, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float e = xhat[i] - x[i];
+  gx[i] += (e > 0.f ? -scale : (e < 0.f ? scale : 0.f));
+}
+extern "C" int uad_l1_direct_term(const float* x, const float* xhat, float scale, float* gx, size_t n, void* stream) {
+  if (n == 0) return 0;
+  l1_direct_term_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, xhat, scale, gx, n);
+  UAD_LAUNCH_CHECK("l1_direct_term");
+  return 0;
+}

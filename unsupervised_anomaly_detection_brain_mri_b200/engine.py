@@ -1,0 +1,519 @@
+"""Device-side executor of the conv encoder->decoder hot path (AE / VAE / ceVAE graphs).
+
+This is what replaces ``sess.run`` of the reference (trainers/AE.py:83, VAE.py:96, ceVAE.py:107): one object that owns
+the flat parameter / gradient / Adam buffers and the activation buffers in HBM and walks the layer list, issuing one
+C-ABI call (``libuad_b200.so``) per fused block.  PyTorch supplies device memory and streams only - no torch math op
+is on this path.
+
+HBM layout
+  * params / grads / adam-m / adam-v: four flat fp32 buffers, one slot per TF variable (256-byte aligned slots),
+    so the optimiser is ONE fused kernel and data-parallel training is ONE all-reduce.
+  * activations: NHWC fp32, per conv block the pre-BN output ``z`` (kept for backward) and the activation ``a``
+    (consumed by the next block); gradients ping-pong between two max-sized buffers.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import abi
+from .abi import (ACT_LEAKY, ACT_NONE, ACT_RELU, OP_CONV_DGRAD, OP_CONV_FWD, OP_CONV_WGRAD, OP_CONVT_DGRAD,
+                  OP_CONVT_FWD, OP_CONVT_WGRAD, call, ptr)
+
+BN_EPS = 1e-3           # tf.layers.BatchNormalization default epsilon
+BN_C = 1.0 / math.sqrt(1.0 + BN_EPS)   # frozen BN: moving_mean = 0, moving_var = 1
+LRELU_ALPHA = 0.3       # tf.keras.layers.LeakyReLU() default (models/customlayers.py:23,36)
+KSIZE = 5
+
+AE = 'autoencoder'
+VAE = 'variational_autoencoder'
+CEVAE = 'context_encoder_variational_autoencoder'
+ARCHS = (AE, VAE, CEVAE)
+
+
+def stack_plan(S, res=8):
+    """Channel plan of build_unified_encoder/decoder (reference models/customlayers.py:16-38)."""
+    n = int(math.log(S, 2) - math.log(float(res), 2))
+    return n, [int(min(128, 32 * 2 ** i)) for i in range(n)], [int(max(32, 128 / 2 ** i)) for i in range(n)]
+
+
+def _bn(k):
+    return 'batch_normalization' if k == 0 else f'batch_normalization_{k}'
+
+
+def param_specs(arch, S, C=1, zDim=128, res=8):
+    """TF variable names -> shapes, in creation order."""
+    assert arch in ARCHS, arch
+    n, enc, dec = stack_plan(S, res)
+    sp = OrderedDict()
+    cin, bn = C, 0
+    for i, co in enumerate(enc):
+        sp[f'Encoder/enc_conv2D_{i}/kernel'] = (KSIZE, KSIZE, cin, co)
+        sp[f'Encoder/enc_conv2D_{i}/bias'] = (co,)
+        sp[f'Encoder/{_bn(bn)}/gamma'] = (co,)
+        sp[f'Encoder/{_bn(bn)}/beta'] = (co,)
+        bn += 1
+        cin = co
+    cb = cin // 8
+    sp['Bottleneck/conv2d/kernel'] = (1, 1, cin, cb)
+    sp['Bottleneck/conv2d/bias'] = (cb,)
+    sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
+    sp['Bottleneck/conv2d_1/bias'] = (cin,)
+    flat = res * res * cb
+    heads = 1 if arch == AE else 2
+    for h in range(heads):
+        nm = 'dense' if h == 0 else f'dense_{h}'
+        sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
+        sp[f'Bottleneck/{nm}/bias'] = (zDim,)
+    sp[f'Bottleneck/dense_{heads}/kernel'] = (zDim, flat)
+    sp[f'Bottleneck/dense_{heads}/bias'] = (flat,)
+    sp[f'Decoder/{_bn(bn)}/gamma'] = (cin,)
+    sp[f'Decoder/{_bn(bn)}/beta'] = (cin,)
+    bn += 1
+    for i, co in enumerate(dec):
+        sp[f'Decoder/dec_Conv2DT_{i}/kernel'] = (KSIZE, KSIZE, co, cin)
+        sp[f'Decoder/dec_Conv2DT_{i}/bias'] = (co,)
+        sp[f'Decoder/{_bn(bn)}/gamma'] = (co,)
+        sp[f'Decoder/{_bn(bn)}/beta'] = (co,)
+        bn += 1
+        cin = co
+    sp['Decoder/dec_Conv2D_final/kernel'] = (1, 1, cin, C)
+    sp['Decoder/dec_Conv2D_final/bias'] = (C,)
+    return sp
+
+
+def glorot_init(specs, seed=1):
+    """Glorot-uniform kernels, zero biases, gamma=1, beta=0 - the TF defaults the reference relies on."""
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for name, shape in specs.items():
+        if name.endswith('/kernel'):
+            if len(shape) == 4:
+                kh, kw, a, b = shape
+                fan_in, fan_out = kh * kw * a, kh * kw * b
+            else:
+                fan_in, fan_out = shape
+            lim = math.sqrt(6.0 / (fan_in + fan_out))
+            out[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif name.endswith('/gamma'):
+            out[name] = np.ones(shape, np.float32)
+        else:
+            out[name] = np.zeros(shape, np.float32)
+    return out
+
+
+class FlatParams:
+    """Flat fp32 parameter / gradient / Adam-moment buffers with named views (TF variable names)."""
+    ALIGN = 64   # floats (256 B) per slot boundary: float4 / TMA friendly
+
+    def __init__(self, specs, device):
+        self.specs = OrderedDict(specs)
+        self.offsets = OrderedDict()
+        off = 0
+        for name, shape in self.specs.items():
+            self.offsets[name] = off
+            off += -(-int(np.prod(shape)) // self.ALIGN) * self.ALIGN
+        self.numel = off
+        self.n_params = sum(int(np.prod(s)) for s in self.specs.values())
+        self.params = torch.zeros(off, dtype=torch.float32, device=device)
+        self.grads = torch.zeros(off, dtype=torch.float32, device=device)
+        self.m = torch.zeros(off, dtype=torch.float32, device=device)
+        self.v = torch.zeros(off, dtype=torch.float32, device=device)
+
+    def _view(self, buf, name):
+        o = self.offsets[name]
+        n = int(np.prod(self.specs[name]))
+        return buf[o:o + n]
+
+    def p(self, name):
+        return self._view(self.params, name)
+
+    def g(self, name):
+        return self._view(self.grads, name)
+
+    def load(self, values, buf=None):
+        buf = self.params if buf is None else buf
+        host = torch.zeros(self.numel, dtype=torch.float32)
+        for name in self.specs:
+            v = np.asarray(values[name], np.float32).reshape(-1)
+            assert v.size == int(np.prod(self.specs[name])), name
+            host[self.offsets[name]:self.offsets[name] + v.size] = torch.from_numpy(v)
+        buf.copy_(host)
+
+    def to_numpy(self, buf=None):
+        buf = self.params if buf is None else buf
+        host = buf.detach().cpu().numpy()
+        return OrderedDict((n, host[self.offsets[n]:self.offsets[n] + int(np.prod(s))].reshape(s).copy())
+                           for n, s in self.specs.items())
+
+    def subset_ranges(self, prefix):
+        """Contiguous [lo, hi) range of slots whose names start with ``prefix`` (scope-contiguous layout)."""
+        names = [n for n in self.specs if n.startswith(prefix)]
+        lo = self.offsets[names[0]]
+        last = names[-1]
+        hi = self.offsets[last] + -(-int(np.prod(self.specs[last])) // self.ALIGN) * self.ALIGN
+        return lo, hi
+
+
+class _Branch:
+    """Activation storage of one pass through the shared layers (ceVAE runs two)."""
+    pass
+
+
+class ConvAutoencoderEngine:
+    """Forward / backward / Adam of the AE, VAE and ceVAE graphs on one GPU.
+
+    Restates (as fused device calls) reference models/autoencoder.py:9-40, variational_autoencoder.py:9-47,
+    context_encoder_variational_autoencoder.py:9-59 and the loss graphs of trainers/AE.py:28-29, VAE.py:36-42,
+    ceVAE.py:38-51.
+    """
+
+    def __init__(self, arch, S, C=1, zDim=128, res=8, batch=8, device='cuda:0', math_mode=abi.MATH_FP32_SIMT, seed=1,
+                 rng_seed=0x5eed, share_params=None):
+        if arch not in ARCHS:
+            raise ValueError(f'unsupported architecture {arch!r}; supported: {ARCHS}')
+        if C != 1:
+            raise NotImplementedError('the fused final-1x1+L1 path supports numChannels == 1 (all reference datasets are '
+                                      'single-channel: dataloaders/BRAINWEB.py:351-352)')
+        abi.lib()   # fail loudly if the CUDA library is missing
+        self.arch, self.S, self.C, self.zDim, self.res, self.B = arch, S, C, zDim, res, batch
+        self.device = torch.device(device)
+        self.math_mode = math_mode
+        self.n, self.enc_ch, self.dec_ch = stack_plan(S, res)
+        self.cb = self.enc_ch[-1] // 8
+        self.flat = res * res * self.cb
+        self.specs = param_specs(arch, S, C, zDim, res)
+        if share_params is not None:      # e.g. an evaluation engine with another batch size on the same weights
+            self.fp = share_params
+        else:
+            self.fp = FlatParams(self.specs, self.device)
+            self.fp.load(glorot_init(self.specs, seed))
+        self.t = 0
+        self.rng_seed = rng_seed
+        self._alloc()
+
+    # ------------------------------------------------------------------ buffers
+    def _new(self, *shape):
+        return torch.empty(*shape, dtype=torch.float32, device=self.device)
+
+    def _alloc_branch(self):
+        B, S = self.B, self.S
+        br = _Branch()
+        br.x = self._new(B, S, S, 1)
+        br.enc_z, br.enc_a = [], []
+        s = S
+        for co in self.enc_ch:
+            s //= 2
+            br.enc_z.append(self._new(B, s, s, co))
+            br.enc_a.append(self._new(B, s, s, co))
+        r = self.res
+        br.zb = self._new(B, r, r, self.cb)              # bottleneck 1x1 output == flatten input [B, flat]
+        br.mu = self._new(B, self.zDim)                  # AE: z
+        br.ls = self._new(B, self.zDim)
+        br.sigma = self._new(B, self.zDim)
+        br.zv = self._new(B, self.zDim)
+        br.kl = self._new(B)
+        br.d = self._new(B, self.flat)                   # dec_dense output (post-dropout)
+        br.zr = self._new(B, r, r, self.enc_ch[-1])      # conv2d_1 output (pre decoder-BN)
+        br.ar = self._new(B, r, r, self.enc_ch[-1])      # after decoder BN + ReLU
+        br.dec_z, br.dec_a = [], []
+        s = r
+        for co in self.dec_ch:
+            s *= 2
+            br.dec_z.append(self._new(B, s, s, co))
+            br.dec_a.append(self._new(B, s, s, co))
+        br.xhat = self._new(B, S, S, 1)
+        br.l1 = self._new(B, S, S, 1)
+        br.rec = self._new(B)
+        br.eps = self._new(B, self.zDim)
+        br.masks = {k: None for k in ('mu', 'ls', 'dec')}
+        br.mask_bufs = {'mu': self._new(B, self.zDim), 'ls': self._new(B, self.zDim), 'dec': self._new(B, self.flat)}
+        return br
+
+    def _alloc(self):
+        B, S = self.B, self.S
+        self.br = [self._alloc_branch()]
+        if self.arch == CEVAE:
+            self.br.append(self._alloc_branch())
+        big = B * S * S * max(32, self.dec_ch[-1])
+        self.gbuf = [self._new(big), self._new(big)]
+        self.gx = self._new(B, S, S, 1)                  # d loss / d x (ceVAE anomaly)
+        self.anomaly = self._new(B, S, S, 1)
+        self.small = {k: self._new(B, n) for k, n in (('dd', self.flat), ('dzv', self.zDim), ('dmu', self.zDim),
+                                                      ('dls', self.zDim), ('dflat', self.flat), ('dflat2', self.flat))}
+        self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # workspace: max over every op this engine issues
+        L = abi.lib()
+        need = 1 << 20
+        s, cin = S, 1
+        for co in self.enc_ch:
+            for op in (OP_CONV_FWD, OP_CONV_DGRAD, OP_CONV_WGRAD):
+                need = max(need, L.uad_conv_workspace_bytes(op, B, s, s, cin, co, KSIZE, self.math_mode))
+            need = max(need, L.uad_rowreduce_workspace_bytes(B * (s // 2) ** 2, co))
+            s //= 2
+            cin = co
+        for co in self.dec_ch:
+            for op in (OP_CONVT_FWD, OP_CONVT_DGRAD, OP_CONVT_WGRAD):
+                need = max(need, L.uad_conv_workspace_bytes(op, B, s, s, cin, co, KSIZE, self.math_mode))
+            need = max(need, L.uad_rowreduce_workspace_bytes(B * (2 * s) ** 2, co))
+            s *= 2
+            cin = co
+        self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self.ws_bytes = need
+
+    # ------------------------------------------------------------------ helpers
+    def _st(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _wsargs(self):
+        return self.ws.data_ptr(), self.ws_bytes
+
+    def set_inputs(self, x, x_ce=None):
+        """Stage a batch (numpy NHWC or a device tensor) into the static input buffers (the feed_dict of sess.run)."""
+        for br, v in zip(self.br, (x, x_ce)):
+            if v is None:
+                continue
+            if isinstance(v, np.ndarray):
+                v = torch.from_numpy(np.ascontiguousarray(v, np.float32))
+            br.x.copy_(v.reshape(br.x.shape), non_blocking=True)
+
+    def set_noise(self, eps=None, masks=None, masks_ce=None):
+        """Parity mode: caller-supplied eps / dropout masks ({0,1} arrays keyed 'mu','ls','dec'; AE uses 'mu' for z)."""
+        if eps is not None:
+            self.br[0].eps.copy_(torch.as_tensor(eps, dtype=torch.float32).reshape(self.br[0].eps.shape))
+        for br, ms in zip(self.br, (masks, masks_ce)):
+            if ms is None:
+                continue
+            for k, m in ms.items():
+                br.mask_bufs[k].copy_(torch.as_tensor(m, dtype=torch.float32).reshape(br.mask_bufs[k].shape))
+                br.masks[k] = br.mask_bufs[k]
+
+    def draw_noise(self, dropout, rate):
+        """Perf mode: fresh eps / masks from the in-library Philox streams (tf.random_normal / Dropout are always live)."""
+        st = self._st()
+        ctr = self.rng_ctr.data_ptr()
+        nb = 0
+        for bi, br in enumerate(self.br):
+            if self.arch != AE and bi == 0:
+                call('uad_randn', ptr(br.eps), br.eps.numel(), self.rng_seed, nb << 40, ctr, st)
+            nb += 1
+            for k in ('mu', 'ls', 'dec'):
+                if dropout and rate > 0 and not (self.arch == AE and k != 'mu') and not (bi == 1 and k == 'ls'):
+                    call('uad_dropout_mask', ptr(br.mask_bufs[k]), br.mask_bufs[k].numel(), float(rate), self.rng_seed,
+                         nb << 40, ctr, st)
+                    br.masks[k] = br.mask_bufs[k]
+                else:
+                    br.masks[k] = None
+                nb += 1
+        call('uad_counter_add', ctr, 1 << 20, st)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, training=True, dropout_rate=0.0, branches=None, need_l1=True):
+        """One pass x -> x_hat (+ per-sample rec / kl).  ``training`` keeps the pre-BN tensors for backward."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsargs()
+        keep = 1.0 / (1.0 - dropout_rate) if dropout_rate > 0 else 1.0
+        B = self.B
+        for bi, br in enumerate(self.br if branches is None else [self.br[i] for i in branches]):
+            is_ce = br is not self.br[0]
+            h, s, cin = br.x, self.S, 1
+            for i, co in enumerate(self.enc_ch):
+                pre = f'Encoder/enc_conv2D_{i}'
+                bnn = f'Encoder/{_bn(i)}'
+                call('uad_conv2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
+                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.enc_z[i]) if training else None,
+                     ptr(br.enc_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
+                h, s, cin = br.enc_a[i], s // 2, co
+            r2 = self.res * self.res
+            call('uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
+                 1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, st)
+            m = br.masks
+            if self.arch == AE:
+                # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity
+                call('uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
+                     ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, st)
+                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', None
+            else:
+                call('uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
+                     ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, st)
+                if not is_ce:
+                    call('uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')),
+                         ptr(fp.p('Bottleneck/dense_1/bias')), ptr(m['ls']), keep, None, None, ptr(br.ls), None, B,
+                         self.flat, self.zDim, ACT_NONE, 0.0, 1.0, st)
+                    call('uad_reparam_kl_fwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(br.sigma), ptr(br.zv), ptr(br.kl),
+                         B, self.zDim, st)
+                    zsrc = br.zv
+                else:
+                    zsrc = br.mu      # ce branch decodes z_mu_ce without sampling (ceVAE model :37,43)
+                dd_name, dec_mask = 'Bottleneck/dense_2', m['dec']
+            call('uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
+                 keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, st)
+            dbn = f'Decoder/{_bn(self.n)}'
+            call('uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
+                 None, 1.0, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(br.zr) if training else None,
+                 ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, st)
+            h, s = br.ar, self.res
+            for i, co in enumerate(self.dec_ch):
+                pre = f'Decoder/dec_Conv2DT_{i}'
+                bnn = f'Decoder/{_bn(self.n + 1 + i)}'
+                call('uad_convT2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
+                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_z[i]) if training else None,
+                     ptr(br.dec_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
+                h, s, cin = br.dec_a[i], s * 2, co
+            call('uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
+                 ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.x), ptr(br.xhat), ptr(br.l1) if need_l1 else None,
+                 ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
+        # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
+        b0 = self.br[0]
+        call('uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch != AE else None, ptr(self.scalars), B, st)
+        if self.arch == CEVAE and (branches is None or 1 in branches):
+            call('uad_loss_scalars', ptr(self.br[1].rec), None, ptr(self.scalars[3:]), B, st)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, want_input_grad=False):
+        """tf.gradients of losses['loss'] w.r.t. every trainable variable into the flat gradient buffer.
+
+        loss = mean_b(rec + kl) (+ mean_b rec_ce for ceVAE).  With ``want_input_grad`` the x-branch also produces
+        d loss_vae / d x (the ceVAE 'anomaly' term, trainers/ceVAE.py:51)."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsargs()
+        B = self.B
+        scale = 1.0 / B
+        r2 = self.res * self.res
+        for bi, br in enumerate(self.br):
+            acc = 1 if bi > 0 else 0
+            is_ce = bi > 0
+            g, gn = self.gbuf
+            cin = self.dec_ch[-1]
+            call('uad_final1x1_l1_bwd', ptr(br.dec_a[-1]), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x),
+                 ptr(br.xhat), scale, ptr(g), ptr(fp.g('Decoder/dec_Conv2D_final/kernel')),
+                 ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B, self.S * self.S, cin, acc, ws, wsb, st)
+            s = self.S
+            for i in reversed(range(self.n)):
+                co = self.dec_ch[i]
+                ci = self.dec_ch[i - 1] if i > 0 else self.enc_ch[-1]
+                pre = f'Decoder/dec_Conv2DT_{i}'
+                bnn = f'Decoder/{_bn(self.n + 1 + i)}'
+                call('uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                     ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
+                     LRELU_ALPHA, BN_C, acc, ws, wsb, st)
+                xin = br.dec_a[i - 1] if i > 0 else br.ar
+                call('uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
+                     acc, mm, ws, wsb, st)
+                call('uad_convT2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, s // 2, s // 2, ci, co, KSIZE, mm,
+                     ws, wsb, st)
+                g, gn = gn, g
+                s //= 2
+            # decoder-entry BN + ReLU on the 1x1 conv output, then the 1x1 conv (as a dense over B*res*res rows)
+            ctop = self.enc_ch[-1]
+            dbn = f'Decoder/{_bn(self.n)}'
+            call('uad_act_bn_bwd', ptr(g), ptr(br.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
+                 ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')), B * r2, ctop,
+                 ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
+            sm = self.small
+            call('uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, st)
+            m = br.masks
+            # keep factor is stored with the mask application: masks carry {0,1}, scale passed explicitly
+            keep = self._keep
+            if self.arch == AE:
+                call('uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
+                     ptr(sm['dmu']), ptr(fp.g('Bottleneck/dense_1/kernel')), ptr(fp.g('Bottleneck/dense_1/bias')), B,
+                     self.zDim, self.flat, acc, st)
+                call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(m['mu']), keep,
+                     ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B,
+                     self.flat, self.zDim, acc, st)
+            else:
+                zsrc = br.mu if is_ce else br.zv
+                call('uad_dense_bwd', ptr(zsrc), ptr(fp.p('Bottleneck/dense_2/kernel')), ptr(sm['dd']), ptr(m['dec']), keep,
+                     ptr(sm['dzv']), ptr(fp.g('Bottleneck/dense_2/kernel')), ptr(fp.g('Bottleneck/dense_2/bias')), B,
+                     self.zDim, self.flat, acc, st)
+                if not is_ce:
+                    call('uad_reparam_kl_bwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(sm['dzv']), scale, ptr(sm['dmu']),
+                         ptr(sm['dls']), B, self.zDim, st)
+                    dmu = sm['dmu']
+                else:
+                    dmu = sm['dzv']
+                call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(dmu), ptr(m['mu']), keep,
+                     ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B,
+                     self.flat, self.zDim, acc, st)
+                if not is_ce:
+                    call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dls']), ptr(m['ls']),
+                         keep, ptr(sm['dflat2']), ptr(fp.g('Bottleneck/dense_1/kernel')),
+                         ptr(fp.g('Bottleneck/dense_1/bias')), B, self.flat, self.zDim, acc, st)
+                    call('uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
+            # bottleneck 1x1 conv backward -> gradient w.r.t. the last encoder activation
+            call('uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
+                 ptr(g), ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb,
+                 acc, st)
+            s = self.res
+            for i in reversed(range(self.n)):
+                co = self.enc_ch[i]
+                ci = self.enc_ch[i - 1] if i > 0 else 1
+                pre = f'Encoder/enc_conv2D_{i}'
+                bnn = f'Encoder/{_bn(i)}'
+                call('uad_act_bn_bwd', ptr(g), ptr(br.enc_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                     ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
+                     LRELU_ALPHA, BN_C, acc, ws, wsb, st)
+                xin = br.enc_a[i - 1] if i > 0 else br.x
+                call('uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE, acc,
+                     mm, ws, wsb, st)
+                if i > 0:
+                    call('uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, 2 * s, 2 * s, ci, co, KSIZE, mm,
+                         ws, wsb, st)
+                    g, gn = gn, g
+                elif want_input_grad and bi == 0:
+                    call('uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(self.gx), B, 2 * s, 2 * s, ci, co,
+                         KSIZE, mm, ws, wsb, st)
+                s *= 2
+
+    _keep = 1.0
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0, lo=0, hi=None):
+        """tf.train.AdamOptimizer update on (a slice of) the flat buffers (reference trainers/DLMODEL.py:112-131)."""
+        self.t += 1
+        lr_t = lr * math.sqrt(1.0 - beta2 ** self.t) / (1.0 - beta1 ** self.t)
+        hi = self.fp.numel if hi is None else hi
+        fp = self.fp
+        call('uad_adam_tf_step', ptr(fp.params[lo:]), ptr(fp.grads[lo:]), ptr(fp.m[lo:]), ptr(fp.v[lo:]), hi - lo,
+             lr_t, beta1, beta2, eps, grad_scale, None, self._st())
+
+    # ------------------------------------------------------------------ one train step (process(TRAIN) body)
+    def train_step(self, lr, beta1=0.5, dropout_rate=0.0, dropout=True, allreduce=None, world=1, parity_noise=False,
+                   want_anomaly=False):
+        rate = dropout_rate if dropout else 0.0
+        self._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+        if not parity_noise:
+            self.draw_noise(dropout, rate)
+        self.forward(training=True, dropout_rate=rate)
+        self.backward(want_input_grad=want_anomaly)
+        if want_anomaly and self.arch == CEVAE:
+            self._finish_anomaly()
+        if allreduce is not None:
+            allreduce(self.fp.grads)
+        self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+
+    def _finish_anomaly(self):
+        """anomaly = L1_vae * |d loss_vae / d x| (ceVAE.py:51): add the direct term -sign(xhat - x)/B of the L1 on x."""
+        b0 = self.br[0]
+        st = self._st()
+        # gx currently holds the encoder-path term; the L1's own dependence on x contributes -dL/dxhat.
+        ws, wsb = self._wsargs()
+        call('uad_l1_direct_term', ptr(b0.x), ptr(b0.xhat), 1.0 / self.B, ptr(self.gx), b0.x.numel(), st)
+        call('uad_mul_abs', ptr(b0.l1), ptr(self.gx), ptr(self.anomaly), b0.x.numel(), st)
+
+    # ------------------------------------------------------------------ read-back
+    def losses(self):
+        s = self.scalars.detach().cpu().numpy()
+        if self.arch == AE:
+            return {'reconstructionLoss': float(s[0]), 'loss': float(s[0])}
+        if self.arch == VAE:
+            return {'reconstructionLoss': float(s[0]), 'kl': float(s[1]), 'loss': float(s[2])}
+        return {'Rec_vae': float(s[0]), 'kl': float(s[1]), 'loss_vae': float(s[2]), 'Rec_ce': float(s[3]),
+                'reconstructionLoss': 0.5 * float(s[0] + s[3]), 'loss': float(s[2] + s[3])}
