@@ -3,7 +3,10 @@ import sys
 
 import pytest
 
+HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if HERE not in sys.path:
+    sys.path.insert(0, HERE)
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -24,3 +27,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    try:
+        import gpu_util
+        gpu_util._KEEP.clear()
+    except Exception:
+        pass

@@ -33,3 +33,13 @@ def relerr(a, b):
 
 def sync():
     torch.cuda.synchronize()
+
+
+_KEEP = []
+
+
+def dptr(a, dtype=torch.float32):
+    """Upload and return the device pointer, keeping the tensor alive until the test ends (see conftest autouse fixture)."""
+    t = dev(a, dtype)
+    _KEEP.append(t)
+    return t.data_ptr()

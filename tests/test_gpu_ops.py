@@ -35,14 +35,14 @@ def oracle_convT(x, K, b):
 
 
 CONV_SHAPES = [  # B, H, Cin, Cout
-    (2, 16, 32, 64), (3, 32, 32, 32), (2, 16, 64, 128), (1, 16, 128, 128), (2, 64, 32, 64), (5, 8, 16, 32),
+    (2, 16, 32, 64), (3, 32, 32, 32), (2, 16, 64, 128), (1, 16, 128, 128), (2, 64, 32, 64), (5, 8, 32, 32),
 ]
 
 
 @pytest.mark.parametrize('mode', [0, 1])
 @pytest.mark.parametrize('B,H,Cin,Cout', CONV_SHAPES)
 def test_conv2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
     from unsupervised_anomaly_detection_brain_mri_b200 import abi
     L = abi.lib()
     rng = np.random.default_rng(B * 1000 + H + Cin + Cout)
@@ -93,7 +93,7 @@ CONVT_SHAPES = [  # B, H(in), Cin, Cout
 @pytest.mark.parametrize('mode', [0, 1])
 @pytest.mark.parametrize('B,H,Cin,Cout', CONVT_SHAPES)
 def test_convT2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
     from unsupervised_anomaly_detection_brain_mri_b200 import abi
     L = abi.lib()
     rng = np.random.default_rng(B * 977 + H + Cin + Cout)
@@ -132,7 +132,7 @@ def test_convT2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
 
 @pytest.mark.parametrize('B,H,Cout', [(2, 32, 32), (3, 128, 32), (1, 256, 32), (2, 16, 64)])
 def test_conv_first_layer_c1(B, H, Cout):
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
     from unsupervised_anomaly_detection_brain_mri_b200 import abi
     L = abi.lib()
     rng = np.random.default_rng(H + Cout)
@@ -149,7 +149,7 @@ def test_conv_first_layer_c1(B, H, Cout):
     ws = workspace(wsb)
     z, a = empty(B, H // 2, H // 2, Cout), empty(B, H // 2, H // 2, Cout)
     dx_, dw_ = dev(x), dev(w)
-    call('uad_conv2d_fwd', ptr(dx_), ptr(dw_), ptr(dev(b)), ptr(dev(gamma)), ptr(dev(beta)), ptr(z), ptr(a), B, H, H, 1, Cout,
+    call('uad_conv2d_fwd', ptr(dx_), ptr(dw_), dptr(b), dptr(gamma), dptr(beta), ptr(z), ptr(a), B, H, H, 1, Cout,
          5, abi.ACT_LEAKY, 0.3, bn_c, 0, ptr(ws), wsb, st())
     sync()
     assert relerr(z.cpu().numpy(), z_ref) < TOL
@@ -170,7 +170,7 @@ def test_conv_first_layer_c1(B, H, Cout):
 
 @pytest.mark.parametrize('M,K,N,act', [(64, 1024, 128, 0), (256, 128, 16, 0), (256, 16, 128, 2), (7, 33, 19, 1), (64, 128, 1024, 0)])
 def test_dense_fwd_bwd(M, K, N, act):
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync
     rng = np.random.default_rng(M + K + N)
     x = rng.standard_normal((M, K)).astype(np.float32)
     w = (rng.standard_normal((K, N)) / math.sqrt(K)).astype(np.float32)
@@ -186,7 +186,7 @@ def test_dense_fwd_bwd(M, K, N, act):
     a_ref = {0: u, 1: F.leaky_relu(u, 0.3), 2: F.relu(u)}[act]
     z, a = empty(M, N), empty(M, N)
     dx_, dw_, dm_ = dev(x), dev(w), dev(mask)
-    call('uad_dense_fwd', ptr(dx_), ptr(dw_), ptr(dev(b)), ptr(dm_), keep, ptr(dev(gamma)), ptr(dev(beta)), ptr(z), ptr(a), M, K,
+    call('uad_dense_fwd', ptr(dx_), ptr(dw_), dptr(b), ptr(dm_), keep, dptr(gamma), dptr(beta), ptr(z), ptr(a), M, K,
          N, act, 0.3, bn_c, st())
     sync()
     assert relerr(z.cpu().numpy(), z_ref.detach().numpy()) < TOL
@@ -194,7 +194,7 @@ def test_dense_fwd_bwd(M, K, N, act):
     dz = rng.standard_normal((M, N)).astype(np.float32)
     gx, gw, gb = torch.autograd.grad((z_ref * t64(dz)).sum(), [xt, wt, bt])
     gxd, gwd, gbd = empty(M, K), empty(K, N), empty(N)
-    call('uad_dense_bwd', ptr(dx_), ptr(dw_), ptr(dev(dz)), ptr(dm_), keep, ptr(gxd), ptr(gwd), ptr(gbd), M, K, N, 0, st())
+    call('uad_dense_bwd', ptr(dx_), ptr(dw_), dptr(dz), ptr(dm_), keep, ptr(gxd), ptr(gwd), ptr(gbd), M, K, N, 0, st())
     sync()
     assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
     assert relerr(gwd.cpu().numpy(), gw.numpy()) < TOL
@@ -203,7 +203,7 @@ def test_dense_fwd_bwd(M, K, N, act):
 
 @pytest.mark.parametrize('rows,C,act', [(4096, 32, 1), (1000, 64, 1), (513, 128, 2), (64, 128, 1)])
 def test_act_bn_bwd(rows, C, act):
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
     from unsupervised_anomaly_detection_brain_mri_b200 import abi
     L = abi.lib()
     rng = np.random.default_rng(rows + C)
@@ -220,7 +220,7 @@ def test_act_bn_bwd(rows, C, act):
     wsb = L.uad_rowreduce_workspace_bytes(rows, C)
     ws = workspace(wsb)
     dz, dg, db, dbias = empty(rows, C), empty(C), empty(C), empty(C)
-    call('uad_act_bn_bwd', ptr(dev(da)), ptr(dev(z)), ptr(dev(gamma)), ptr(dev(beta)), ptr(dz), ptr(dg), ptr(db), ptr(dbias),
+    call('uad_act_bn_bwd', dptr(da), dptr(z), dptr(gamma), dptr(beta), ptr(dz), ptr(dg), ptr(db), ptr(dbias),
          rows, C, act, 0.3, bn_c, 0, ptr(ws), wsb, st())
     sync()
     assert relerr(dz.cpu().numpy(), gz.numpy()) < TOL
@@ -230,7 +230,7 @@ def test_act_bn_bwd(rows, C, act):
 
 
 def test_reparam_kl():
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync
     rng = np.random.default_rng(5)
     B, Z = 16, 128
     mu = rng.standard_normal((B, Z)).astype(np.float32)
@@ -250,7 +250,7 @@ def test_reparam_kl():
     klt = 0.5 * (mt ** 2 + s ** 2 - torch.log(s ** 2) - 1).sum(1)
     gm, gl = torch.autograd.grad((zz * t64(dz)).sum() + klt.mean(), [mt, lt])
     gmd, gld = empty(B, Z), empty(B, Z)
-    call('uad_reparam_kl_bwd', ptr(dmu_), ptr(dls_), ptr(deps_), ptr(dev(dz)), 1.0 / B, ptr(gmd), ptr(gld), B, Z, st())
+    call('uad_reparam_kl_bwd', ptr(dmu_), ptr(dls_), ptr(deps_), dptr(dz), 1.0 / B, ptr(gmd), ptr(gld), B, Z, st())
     sync()
     assert relerr(gmd.cpu().numpy(), gm.numpy()) < TOL
     assert relerr(gld.cpu().numpy(), gl.numpy()) < TOL
@@ -258,7 +258,7 @@ def test_reparam_kl():
 
 @pytest.mark.parametrize('B,S', [(2, 32), (3, 128)])
 def test_final1x1_l1(B, S):
-    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
     rng = np.random.default_rng(S)
     C = 32
     a = rng.standard_normal((B, S, S, C)).astype(np.float32)
@@ -273,7 +273,7 @@ def test_final1x1_l1(B, S):
     ws = workspace(1 << 20)
     xhd, l1d, recd = empty(B, S, S, 1), empty(B, S, S, 1), empty(B)
     da_, dw_, dx_ = dev(a), dev(w), dev(x)
-    call('uad_final1x1_l1_fwd', ptr(da_), ptr(dw_), ptr(dev(b)), ptr(dx_), ptr(xhd), ptr(l1d), ptr(recd), B, S * S, C, ptr(ws),
+    call('uad_final1x1_l1_fwd', ptr(da_), ptr(dw_), dptr(b), ptr(dx_), ptr(xhd), ptr(l1d), ptr(recd), B, S * S, C, ptr(ws),
          1 << 20, st())
     sync()
     assert relerr(xhd.cpu().numpy(), xh.detach().numpy()) < TOL
@@ -289,7 +289,7 @@ def test_final1x1_l1(B, S):
 
 
 def test_adam_tf():
-    from gpu_util import call, dev, ptr, relerr, st, sync
+    from gpu_util import call, dev, dptr, ptr, relerr, st, sync
     rng = np.random.default_rng(11)
     n = 100003
     p = rng.standard_normal(n).astype(np.float32)
@@ -301,7 +301,7 @@ def test_adam_tf():
                                  t, lr)
     lr_t = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.5 ** t)
     pd, md, vd = dev(p), dev(m), dev(v)
-    call('uad_adam_tf_step', ptr(pd), ptr(dev(g)), ptr(md), ptr(vd), n, lr_t, 0.5, 0.999, 1e-8, 0.5, None, st())
+    call('uad_adam_tf_step', ptr(pd), dptr(g), ptr(md), ptr(vd), n, lr_t, 0.5, 0.999, 1e-8, 0.5, None, st())
     sync()
     assert relerr(pd.cpu().numpy(), pr) < 1e-6
     assert relerr(md.cpu().numpy(), mr) < 1e-6
@@ -328,7 +328,7 @@ def test_rng_streams():
 
 @pytest.mark.parametrize('keep_positive,apply_prior', [(1, 1), (0, 1), (1, 0)])
 def test_residual_score_bitexact(keep_positive, apply_prior):
-    from gpu_util import call, dev, empty, ptr, st, sync
+    from gpu_util import call, dev, dptr, empty, ptr, st, sync
     rng = np.random.default_rng(21)
     N, S = 7, 64
     x = O.synthetic_slices(N, S, seed=5)[..., 0]
@@ -337,7 +337,7 @@ def test_residual_score_bitexact(keep_positive, apply_prior):
     prior = float(np.quantile(x, 0.9))
     ref = oscore.residual(x, xr, mask, prior, bool(keep_positive), bool(apply_prior))
     d = empty(N, S, S)
-    call('uad_residual_score', ptr(dev(x)), ptr(dev(xr)), ptr(dev(mask.astype(np.uint8), torch.uint8)), prior, keep_positive,
+    call('uad_residual_score', dptr(x), dptr(xr), dptr(mask.astype(np.uint8), torch.uint8), prior, keep_positive,
          apply_prior, ptr(d), x.size, st())
     sync()
     got = d.cpu().numpy()
@@ -345,7 +345,7 @@ def test_residual_score_bitexact(keep_positive, apply_prior):
 
 
 def test_threshold_counts_bitexact():
-    from gpu_util import call, dev, ptr, st, sync
+    from gpu_util import call, dev, dptr, ptr, st, sync
     rng = np.random.default_rng(31)
     n = 110 * 64 * 64 + 3
     diff = np.maximum(rng.standard_normal(n) * 0.2, 0).astype(np.float32)
@@ -355,7 +355,7 @@ def test_threshold_counts_bitexact():
     arr = (ctypes.c_double * len(thr))(*thr)
     counts = torch.zeros(len(thr) * 3, dtype=torch.int64, device='cuda:0')
     mask = torch.zeros(n, dtype=torch.uint8, device='cuda:0')
-    call('uad_threshold_counts', ptr(dev(diff)), ptr(dev(label, torch.uint8)), n, arr, len(thr), ptr(counts), ptr(mask), st())
+    call('uad_threshold_counts', dptr(diff), dptr(label, torch.uint8), n, arr, len(thr), ptr(counts), ptr(mask), st())
     sync()
     got = counts.cpu().numpy().reshape(-1, 3)
     d64 = diff.astype(np.float64)
