@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: MRI slices/sec for one train step (fwd + L1/KL + bwd + TF-Adam [+ grad all-reduce]) of the VAE
+(variational_autoencoder) at 256x256 fp32, batch 64 per GPU - BASELINE.json configs[1] - on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (under torchrun for N > 1)
+  python bench.py --impl reference --steps K --warmup W    # the reference path on the box's host cores (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` = device-resident step throughput (CUDA events, max over ranks);
+`e2e` = the same metric through the public trainer API with host batches (pinned H2D + loss D2H inside the timed region).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+S, B_PER_GPU, ZDIM = 256, 64, 128
+METRIC = 'MRI slices/sec (train step, 256x256 fp32)'
+WORKLOAD = 'VAE (variational_autoencoder.py) 256x256 fp32, batch 64 per GPU, L1+KL, synthetic Brainweb slices'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace('.', '').isdigit())
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        mx = max((int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()), default=None)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def conv_work(B):
+    """Algorithmic FLOPs / bytes per launch of every conv-family op of the VAE-256 train step."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import stack_plan
+    n, enc, dec = stack_plan(S)
+    work = {}
+    s, cin = S, 1
+    for i, co in enumerate(enc):
+        fl = 2.0 * B * (s // 2) ** 2 * 25 * cin * co
+        xin, xout, w = B * s * s * cin * 4, B * (s // 2) ** 2 * co * 4, 25 * cin * co * 4
+        work[f'enc_conv2D_{i}:conv2d_fwd'] = (fl, xin + 2 * xout + w)
+        work[f'enc_conv2D_{i}:conv2d_dgrad'] = (fl, xout + xin + w)
+        work[f'enc_conv2D_{i}:conv2d_wgrad'] = (fl, xin + xout + w)
+        work[f'enc_conv2D_{i}:act_bn_bwd'] = (0.0, 3 * xout)
+        s, cin = s // 2, co
+    for i, co in enumerate(dec):
+        fl = 2.0 * B * s * s * 25 * cin * co
+        xin, xout, w = B * s * s * cin * 4, B * (2 * s) ** 2 * co * 4, 25 * cin * co * 4
+        work[f'dec_Conv2DT_{i}:convT2d_fwd'] = (fl, xin + 2 * xout + w)
+        work[f'dec_Conv2DT_{i}:convT2d_dgrad'] = (fl, xout + xin + w)
+        work[f'dec_Conv2DT_{i}:convT2d_wgrad'] = (fl, xin + xout + w)
+        work[f'dec_Conv2DT_{i}:act_bn_bwd'] = (0.0, 3 * xout)
+        s, cin = 2 * s, co
+    px = B * S * S
+    work['dec_Conv2D_final:final1x1_l1_fwd'] = (2.0 * px * cin, px * cin * 4 + 3 * px * 4)
+    work['dec_Conv2D_final:final1x1_l1_bwd'] = (4.0 * px * cin, 2 * px * cin * 4 + 2 * px * 4)
+    return work
+
+
+def step_flops(B):
+    return sum(f for k, (f, _) in conv_work(B).items())
+
+
+def cpu_reference_step_rate(batch, steps, warmup, threads):
+    """Times the oracle port of the reference train step (fwd + loss + bwd + TF-Adam) on the host cores."""
+    from oracle import tf_graph_cpu as O
+    torch.set_num_threads(threads)
+    P = O.init_params(O.VAE, S, seed=1)
+    tr = O.Trainer(O.VAE, P, lr=1e-4, dropout_rate=0.2, dtype=torch.float32)
+    x = O.synthetic_slices(batch, S, seed=1234)
+    rng = np.random.default_rng(0)
+    ts = []
+    for i in range(warmup + steps):
+        eps = rng.standard_normal((batch, ZDIM)).astype(np.float32)
+        masks = {'mu': (rng.uniform(size=(batch, ZDIM)) >= 0.2).astype(np.float32),
+                 'log_sigma': (rng.uniform(size=(batch, ZDIM)) >= 0.2).astype(np.float32),
+                 'dec': (rng.uniform(size=(batch, 1024)) >= 0.2).astype(np.float32)}
+        t0 = time.perf_counter()
+        tr.step(x, eps=eps, masks=masks)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return batch * len(ts) / sum(ts), 1e3 * sum(ts) / len(ts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    batch = 16      # bounded sample of the workload per step: 16 of the 64 slices of a mini-batch
+    rate, ms = cpu_reference_step_rate(batch, args.steps, max(1, min(args.warmup, 2)), cores)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU * args.gpus, 'parallelism': f'dp{args.gpus}'},
+            'cpu_baseline': {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'oracle torch-CPU restatement of the TF graph (TensorFlow 1.15 is not installable here); '
+                                       f'{batch}-slice train steps of the same VAE-256 workload'},
+            'e2e': {'value': rate, 'unit': 'slices/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--math', default='tc3', choices=['simt', 'tc3', 'tc1'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--layer-table', default=None, help='write the per-kernel timing table (json) here')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi, dist as udist
+    from unsupervised_anomaly_detection_brain_mri_b200.models import variational_autoencoder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.VAE import VAE
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.logger import Phase
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import make_volume
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_options
+
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    rank, world = udist.init_from_env('nccl')
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    B = B_PER_GPU
+    math_mode = {'simt': abi.MATH_FP32_SIMT, 'tc3': abi.MATH_TC_3XTF32, 'tc1': abi.MATH_TC_1XTF32}[args.math]
+
+    # ---- the public API a user of the reference calls: options -> config -> Trainer(sess, config, network)
+    options = get_options(batchsize=B, learningrate=1e-4, numEpochs=1, zDim=ZDIM, outputWidth=S, outputHeight=S)
+
+    class _DS:                                  # dataset stand-in only for get_config (type name + num_channels)
+        num_channels = 1
+    config = get_config(trainer=VAE, options=options, optimizer='ADAM', intermediateResolutions=[8, 8], dropout_rate=0.2, dataset=_DS())
+    config.useTensorboard = False
+    config.math_mode = math_mode
+    config.device = f'cuda:{local}'
+    config.checkpointDir = '/tmp/uad_bench_ckpt'
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, 'w')          # the trainer prints parameter counts; keep the JSON line clean
+    try:
+        model = VAE(None, config, network=variational_autoencoder.variational_autoencoder)
+        if world > 1:
+            model.enable_data_parallel()
+    finally:
+        sys.stdout = _stdout
+    eng = model.engine
+
+    # ---- synthetic data: a pool of distinct host batches (pinned), each rank its own shard
+    nb = 4
+    vol = np.concatenate([make_volume(S, B, seed=1000 + 17 * rank + j, lesions=False)[0] for j in range(nb)], 0)
+    host_batches = [vol[j * B:(j + 1) * B, :, :, None].copy() for j in range(nb)]
+    dev_batches = [torch.from_numpy(h).to(dev) for h in host_batches]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        eng.set_inputs(dev_batches[i % nb])     # device->device stage of the resident batch (the feed of sess.run)
+        eng.train_step(config.learningrate, beta1=config.beta1, dropout_rate=config.dropout_rate, dropout=True,
+                       allreduce=model._allreduce, world=world, use_graph=True)
+
+    # ---- warm-up (first call eager, second captures the CUDA graph)
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = abi.lib().uad_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+    e1.record()
+    barrier()
+    ms_total = udist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the trainer API: host batch -> pinned H2D -> step -> loss D2H, every step
+    for i in range(3):
+        model.run_batch(host_batches[i % nb], Phase.TRAIN)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        run = model.run_batch(host_batches[i % nb], Phase.TRAIN)
+    barrier()
+    e2e_s = udist.max_over_ranks(time.perf_counter() - t0, dev)
+    clocks = sampler.stop()
+    e2e_value = world * B * args.steps / e2e_s
+    assert math.isfinite(float(run['loss']))
+
+    # ---- kernels per step (graph replays launch the captured kernels; count one eager step)
+    eng.graph, eng._warm = None, None
+    c0 = abi.lib().uad_launch_count()
+    eng.set_inputs(dev_batches[0])
+    eng.train_step(config.learningrate, beta1=config.beta1, dropout_rate=config.dropout_rate, dropout=True,
+                   allreduce=model._allreduce, world=world, use_graph=False)
+    torch.cuda.synchronize()
+    per_step = abi.lib().uad_launch_count() - c0
+
+    # ---- per-kernel timing (eager, CUDA events on the launch stream) -> roofline of the dominant kernel
+    eng.probes = {}
+    for i in range(3):
+        eng.set_inputs(dev_batches[i % nb])
+        eng.train_step(config.learningrate, beta1=config.beta1, dropout_rate=config.dropout_rate, dropout=True,
+                       allreduce=model._allreduce, world=world, use_graph=False)
+    times = {k: float(np.mean(v[1:])) if len(v) > 1 else float(v[0]) for k, v in eng.probe_times_ms().items()}
+    eng.probes = None
+    peaks = load_peaks()
+    work = conv_work(B)
+    table = []
+    for k, ms in sorted(times.items(), key=lambda kv: -kv[1]):
+        fl, by = work.get(k, (0.0, 0.0))
+        t_hbm = by / (peaks['hbm_gbs'] * 1e9) * 1e3
+        t_tc = fl / (peaks['bf16_tflops_sustained'] * 1e12) * 1e3
+        bound = 'hbm' if t_hbm >= t_tc else 'tensor'
+        table.append({'op': k, 'ms': ms, 'gflop': fl / 1e9, 'mbytes': by / 1e6, 'bound': bound,
+                      'roofline_ms': max(t_hbm, t_tc), 'frac': max(t_hbm, t_tc) / ms if ms > 0 else None,
+                      'tflops': fl / ms / 1e9 if ms > 0 else None, 'gbs': by / ms / 1e6 if ms > 0 else None})
+    top = table[0]
+    if top['bound'] == 'hbm':
+        roof = {'kernel': top['op'], 'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source']}
+    else:
+        roof = {'kernel': top['op'], 'bound': 'tensor', 'achieved': top['tflops'], 'peak': peaks['bf16_tflops_sustained'],
+                'unit': 'TFLOP/s', 'frac': top['tflops'] / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'peak_source': peaks['source'] + ' (sustained dense bf16; the kernel computes fp32-accurate 3xTF32)'}
+    roof['kernel_ms'] = top['ms']
+    roof['kernel_share_of_step'] = top['ms'] / sum(times.values())
+    step_sum = sum(times.values())
+    if args.layer_table and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.layer_table)), exist_ok=True)
+        json.dump({'ms_per_step_graph': ms_step, 'sum_of_probed_kernels_ms': step_sum, 'peaks': peaks, 'table': table},
+                  open(args.layer_table, 'w'), indent=1)
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, ms = cpu_reference_step_rate(16, 3, 1, cores)
+        cpu = {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
+               'sample': 'oracle torch-CPU restatement (TF 1.15 not installable); 3 timed 16-slice train steps of the same VAE-256 workload'}
+    line = {'metric': METRIC, 'value': value, 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'global_batch': B * world, 'parallelism': f'dp{world}',
+                       'math': {'simt': 'fp32 FFMA', 'tc3': 'tcgen05 3xTF32 (fp32-accurate) where supported, fp32 FFMA elsewhere',
+                                'tc1': 'tcgen05 1xTF32'}[args.math],
+                       'l2': 'per-step working set (~2 GB of activations) >> 126 MB L2; 4 distinct input batches rotate',
+                       'cuda_graph': True},
+            'step_tflops': step_flops(B) * world / (ms_step / 1e3) / 1e12,
+            'e2e': {'value': e2e_value, 'unit': 'slices/s', 'h2d_bytes_per_step': int(host_batches[0].nbytes),
+                    'd2h_bytes_per_step': int(eng.scalars.numel() * 4)},
+            'gpu_launches': int(per_step * args.steps),
+            'gpu_launches_per_step': int(per_step),
+            'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()

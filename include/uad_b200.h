@@ -47,6 +47,8 @@ extern "C" {
 
 const char* uad_last_error(void);
 int uad_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (diagnostic; bench.py reports it) */
+long long uad_launch_count(void);
 /* 1 if the tcgen05 (tensor-core) conv path is compiled in and usable for the given op/shape, else 0 */
 int uad_conv_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int ksize);
 
@@ -122,8 +124,9 @@ int uad_loss_scalars(const float* rec, const float* kl, float* out3, int B, void
 /* ---- TF-form Adam on a flat buffer (trainers/DLMODEL.py:112-131; tf.train.AdamOptimizer):
  * g = grad*grad_scale; m=b1*m+(1-b1)g; v=b2*v+(1-b2)g^2; p -= lr_t*m/(sqrt(v)+eps), lr_t precomputed by the host */
 int uad_adam_tf_step(float* params, const float* grads, float* m, float* v, size_t n, float lr_t, float b1, float b2,
-                     float eps, float grad_scale, const float* lr_t_dev, void* stream);
-/* lr_t_dev (nullable): device scalar that overrides lr_t - lets a captured CUDA graph see a fresh bias-corrected rate */
+                     float eps, float grad_scale, const int64_t* step_dev, void* stream);
+/* step_dev (nullable): device step counter t (1-based).  When given, `lr_t` is the BASE learning rate and the kernel
+ * derives lr_t = lr*sqrt(1-b2^t)/(1-b1^t) itself (float64), so a captured CUDA graph needs no per-step host value. */
 
 /* ---- Philox-4x32-10 streams for the live graph RNG nodes (tf.random_normal variational_autoencoder.py:34; Dropout) */
 int uad_randn(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);

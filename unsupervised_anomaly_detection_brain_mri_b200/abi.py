@@ -22,6 +22,7 @@ _P, _I, _F, _D, _Z, _U64, _LL = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_
 SIGNATURES = {
     'uad_last_error': (C.c_char_p, []),
     'uad_abi_version': (_I, []),
+    'uad_launch_count': (_LL, []),
     'uad_conv_tc_supported': (_I, [_I] * 7),
     'uad_conv_workspace_bytes': (_Z, [_I] * 8),
     'uad_conv2d_fwd': (_I, [_P] * 7 + [_I] * 7 + [_F, _F, _I, _P, _Z, _P]),

@@ -13,8 +13,9 @@ int uad_set_error(const char* fmt, ...);
 #define UAD_REQUIRE(cond, ...) \
   do { if (!(cond)) return uad_set_error(__VA_ARGS__); } while (0)
 
+extern long long g_uad_launches;
 #define UAD_LAUNCH_CHECK(what) \
-  do { cudaError_t e__ = cudaGetLastError(); \
+  do { ++g_uad_launches; cudaError_t e__ = cudaGetLastError(); \
        if (e__ != cudaSuccess) return uad_set_error("%s: launch failed: %s", what, cudaGetErrorString(e__)); } while (0)
 
 #define UAD_CUDA(call) \

@@ -503,11 +503,15 @@ int uad_launch_conv_c1_wgrad(const float* x, const float* dz, float* dw, int B, 
   UAD_REQUIRE(ws && ws_bytes >= need, "conv_c1_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
   size_t smem = ((size_t)ksize * (W + ksize) + (size_t)(nthreads / 32) * n) * sizeof(float);
   float* partial = reinterpret_cast<float*>(ws);
+  static bool attr_set = false;   // set once, outside any stream capture in practice (first eager warm-up step)
+  if (!attr_set) {
+    UAD_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    UAD_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
   if (Cout == 32) {
-    UAD_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv_c1_wgrad_kernel<5, 1><<<blocks, nthreads, smem, st>>>(x, dz, partial, B, H, W, Cout, pad_lo);
   } else {
-    UAD_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv_c1_wgrad_kernel<5, 2><<<blocks, nthreads, smem, st>>>(x, dz, partial, B, H, W, Cout, pad_lo);
   }
   UAD_LAUNCH_CHECK("conv_c1_wgrad");

@@ -14,6 +14,8 @@ int uad_set_error(const char* fmt, ...) {
 }
 extern "C" const char* uad_last_error(void) { return g_uad_err; }
 extern "C" int uad_abi_version(void) { return UAD_ABI_VERSION; }
+long long g_uad_launches = 0;
+extern "C" long long uad_launch_count(void) { return g_uad_launches; }
 
 // ------------------------------------------------------------------------------------------------ act + frozen-BN backward
 // stage 1: dz = gamma*bn_c * da * act'(u), per-block partial sums of du and du*z per channel
@@ -321,8 +323,11 @@ extern "C" int uad_loss_scalars(const float* rec, const float* kl, float* out3, 
 // ------------------------------------------------------------------------------------------------ TF-form Adam
 __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                size_t n, float lr_t, float b1, float b2, float eps, float gs,
-                               const float* __restrict__ lr_dev) {
-  if (lr_dev) lr_t = *lr_dev;
+                               const long long* __restrict__ step_dev) {
+  if (step_dev) {
+    const double t = (double)(*step_dev);
+    lr_t = (float)((double)lr_t * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
   size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 p4 = *reinterpret_cast<float4*>(p + i), g4 = *reinterpret_cast<const float4*>(g + i);
@@ -351,12 +356,12 @@ __global__ void adam_tf_kernel(float* __restrict__ p, const float* __restrict__ 
 }
 
 extern "C" int uad_adam_tf_step(float* params, const float* grads, float* m, float* v, size_t n, float lr_t, float b1,
-                                float b2, float eps, float grad_scale, const float* lr_t_dev, void* stream) {
+                                float b2, float eps, float grad_scale, const int64_t* step_dev, void* stream) {
   UAD_REQUIRE(((uintptr_t)params % 16 == 0) && ((uintptr_t)grads % 16 == 0) && ((uintptr_t)m % 16 == 0) &&
               ((uintptr_t)v % 16 == 0), "uad_adam_tf_step: buffers must be 16-byte aligned");
   if (n == 0) return 0;
   adam_tf_kernel<<<uad_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, n, lr_t, b1, b2, eps,
-                                                                              grad_scale, lr_t_dev);
+                                                                              grad_scale, (const long long*)step_dev);
   UAD_LAUNCH_CHECK("adam_tf");
   return 0;
 }

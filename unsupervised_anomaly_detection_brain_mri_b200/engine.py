@@ -192,6 +192,8 @@ class ConvAutoencoderEngine:
             self.fp = FlatParams(self.specs, self.device)
             self.fp.load(glorot_init(self.specs, seed))
         self.t = 0
+        self.probes = None
+        self.graph = None
         self.rng_seed = rng_seed
         self._alloc()
 
@@ -247,6 +249,7 @@ class ConvAutoencoderEngine:
         self.scalars = torch.zeros(8, dtype=torch.float32, device=self.device)
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
         # workspace: max over every op this engine issues
         L = abi.lib()
         need = 1 << 20
@@ -267,6 +270,20 @@ class ConvAutoencoderEngine:
         self.ws_bytes = need
 
     # ------------------------------------------------------------------ helpers
+    def _op(self, label, fname, *args):
+        """Issue one ABI call; with ``self.probes`` set (eager mode only) bracket it with CUDA events for per-kernel timing."""
+        if self.probes is None:
+            return call(fname, *args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call(fname, *args)
+        e1.record()
+        self.probes.setdefault(f'{label}:{fname[4:]}', []).append((e0, e1))
+
+    def probe_times_ms(self):
+        torch.cuda.synchronize(self.device)
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in (self.probes or {}).items()}
+
     def _st(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -325,7 +342,7 @@ class ConvAutoencoderEngine:
             for i, co in enumerate(self.enc_ch):
                 pre = f'Encoder/enc_conv2D_{i}'
                 bnn = f'Encoder/{_bn(i)}'
-                call('uad_conv2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
+                self._op(pre.split('/')[-1], 'uad_conv2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
                      ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.enc_z[i]) if training else None,
                      ptr(br.enc_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.enc_a[i], s // 2, co
@@ -361,11 +378,11 @@ class ConvAutoencoderEngine:
             for i, co in enumerate(self.dec_ch):
                 pre = f'Decoder/dec_Conv2DT_{i}'
                 bnn = f'Decoder/{_bn(self.n + 1 + i)}'
-                call('uad_convT2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
+                self._op(pre.split('/')[-1], 'uad_convT2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
                      ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_z[i]) if training else None,
                      ptr(br.dec_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.dec_a[i], s * 2, co
-            call('uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
+            self._op('dec_Conv2D_final', 'uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
                  ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.x), ptr(br.xhat), ptr(br.l1) if need_l1 else None,
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
@@ -390,7 +407,7 @@ class ConvAutoencoderEngine:
             is_ce = bi > 0
             g, gn = self.gbuf
             cin = self.dec_ch[-1]
-            call('uad_final1x1_l1_bwd', ptr(br.dec_a[-1]), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x),
+            self._op('dec_Conv2D_final', 'uad_final1x1_l1_bwd', ptr(br.dec_a[-1]), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x),
                  ptr(br.xhat), scale, ptr(g), ptr(fp.g('Decoder/dec_Conv2D_final/kernel')),
                  ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B, self.S * self.S, cin, acc, ws, wsb, st)
             s = self.S
@@ -399,20 +416,20 @@ class ConvAutoencoderEngine:
                 ci = self.dec_ch[i - 1] if i > 0 else self.enc_ch[-1]
                 pre = f'Decoder/dec_Conv2DT_{i}'
                 bnn = f'Decoder/{_bn(self.n + 1 + i)}'
-                call('uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
                      ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.dec_a[i - 1] if i > 0 else br.ar
-                call('uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
+                self._op(pre.split('/')[-1], 'uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
                      acc, mm, ws, wsb, st)
-                call('uad_convT2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, s // 2, s // 2, ci, co, KSIZE, mm,
+                self._op(pre.split('/')[-1], 'uad_convT2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, s // 2, s // 2, ci, co, KSIZE, mm,
                      ws, wsb, st)
                 g, gn = gn, g
                 s //= 2
             # decoder-entry BN + ReLU on the 1x1 conv output, then the 1x1 conv (as a dense over B*res*res rows)
             ctop = self.enc_ch[-1]
             dbn = f'Decoder/{_bn(self.n)}'
-            call('uad_act_bn_bwd', ptr(g), ptr(br.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
+            self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
                  ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')), B * r2, ctop,
                  ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
             sm = self.small
@@ -457,18 +474,18 @@ class ConvAutoencoderEngine:
                 ci = self.enc_ch[i - 1] if i > 0 else 1
                 pre = f'Encoder/enc_conv2D_{i}'
                 bnn = f'Encoder/{_bn(i)}'
-                call('uad_act_bn_bwd', ptr(g), ptr(br.enc_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.enc_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
                      ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.enc_a[i - 1] if i > 0 else br.x
-                call('uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE, acc,
+                self._op(pre.split('/')[-1], 'uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE, acc,
                      mm, ws, wsb, st)
                 if i > 0:
-                    call('uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, 2 * s, 2 * s, ci, co, KSIZE, mm,
+                    self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, 2 * s, 2 * s, ci, co, KSIZE, mm,
                          ws, wsb, st)
                     g, gn = gn, g
                 elif want_input_grad and bi == 0:
-                    call('uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(self.gx), B, 2 * s, 2 * s, ci, co,
+                    self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(self.gx), B, 2 * s, 2 * s, ci, co,
                          KSIZE, mm, ws, wsb, st)
                 s *= 2
 
@@ -476,28 +493,59 @@ class ConvAutoencoderEngine:
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0, lo=0, hi=None):
-        """tf.train.AdamOptimizer update on (a slice of) the flat buffers (reference trainers/DLMODEL.py:112-131)."""
+        """tf.train.AdamOptimizer update on (a slice of) the flat buffers (reference trainers/DLMODEL.py:112-131).
+        The step counter lives on the device so the call is CUDA-graph capturable."""
         self.t += 1
-        lr_t = lr * math.sqrt(1.0 - beta2 ** self.t) / (1.0 - beta1 ** self.t)
         hi = self.fp.numel if hi is None else hi
-        fp = self.fp
+        fp, st = self.fp, self._st()
+        call('uad_counter_add', self.step_dev.data_ptr(), 1, st)
         call('uad_adam_tf_step', ptr(fp.params[lo:]), ptr(fp.grads[lo:]), ptr(fp.m[lo:]), ptr(fp.v[lo:]), hi - lo,
-             lr_t, beta1, beta2, eps, grad_scale, None, self._st())
+             lr, beta1, beta2, eps, grad_scale, self.step_dev.data_ptr(), st)
 
     # ------------------------------------------------------------------ one train step (process(TRAIN) body)
-    def train_step(self, lr, beta1=0.5, dropout_rate=0.0, dropout=True, allreduce=None, world=1, parity_noise=False,
-                   want_anomaly=False):
-        rate = dropout_rate if dropout else 0.0
-        self._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+    def _fwd_bwd(self, rate, dropout, parity_noise, want_anomaly):
         if not parity_noise:
             self.draw_noise(dropout, rate)
         self.forward(training=True, dropout_rate=rate)
         self.backward(want_input_grad=want_anomaly)
         if want_anomaly and self.arch == CEVAE:
             self._finish_anomaly()
+
+    def train_step(self, lr, beta1=0.5, dropout_rate=0.0, dropout=True, allreduce=None, world=1, parity_noise=False,
+                   want_anomaly=False, use_graph=False):
+        """Body of process(TRAIN) for one mini-batch already staged with set_inputs():
+        noise -> forward -> losses -> backward -> [gradient all-reduce] -> TF-Adam.
+
+        use_graph: the first call runs eagerly (warm-up), the second captures a CUDA graph, later calls replay it
+        (the ~90 kernel launches of a step collapse into one graph launch)."""
+        rate = dropout_rate if dropout else 0.0
+        self._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+        key = (lr, beta1, rate, dropout, world, want_anomaly, allreduce is None)
+        if use_graph and not parity_noise and self._warm == key:
+            if self.graph is None:
+                g = torch.cuda.CUDAGraph()
+                t_save = self.t
+                with torch.cuda.graph(g):
+                    self._fwd_bwd(rate, dropout, False, want_anomaly)
+                    if allreduce is None:
+                        self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+                self.t = t_save
+                self.graph = g
+            self.graph.replay()
+            if allreduce is not None:
+                allreduce(self.fp.grads)
+                self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+            else:
+                self.t += 1
+            return
+        self.graph = None
+        self._fwd_bwd(rate, dropout, parity_noise, want_anomaly)
         if allreduce is not None:
             allreduce(self.fp.grads)
         self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+        self._warm = key
+
+    _warm = None
 
     def _finish_anomaly(self):
         """anomaly = L1_vae * |d loss_vae / d x| (ceVAE.py:51): add the direct term -sign(xhat - x)/B of the L1 on x."""

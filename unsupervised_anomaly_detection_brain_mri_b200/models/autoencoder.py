@@ -1,0 +1,10 @@
+"""Mirror of reference models/autoencoder.py (same name, signature and output keys)."""
+from .customlayers import GraphSpec, GraphTensor, build_unified_decoder, build_unified_encoder
+
+
+def autoencoder(x, dropout_rate, dropout, config):
+    shape = x.get_shape().as_list()
+    encoder = build_unified_encoder(shape, config.intermediateResolutions)
+    decoder = build_unified_decoder(config.outputWidth, config.intermediateResolutions, config.numChannels)
+    graph = GraphSpec('autoencoder', shape, config, encoder, decoder)
+    return {key: GraphTensor(graph, key) for key in 'z,x_hat'.split(',')}

@@ -1,0 +1,224 @@
+"""AE base trainer (mirror of reference trainers/AEMODEL.py:12-79) driving the CUDA engine instead of a tf.Session."""
+import os
+from abc import ABC
+from collections import defaultdict
+from datetime import datetime
+from math import inf
+
+import numpy as np
+import torch
+
+from .. import abi
+from ..engine import ConvAutoencoderEngine
+from ..models.customlayers import Placeholder
+from ..utils.logger import Logger, Phase
+from . import trainer_utils
+from .DLMODEL import DLMODEL
+
+
+class AEMODEL(DLMODEL, ABC):
+    class Config(DLMODEL.Config):
+        def __init__(self, modelname='AE'):
+            super().__init__()
+            self.modelname = modelname
+            self.intermediateResolutions = [8, 8]
+            self.outputWidth = 256
+            self.outputHeight = 256
+            self.numChannels = 3
+            self.dropout = False
+            self.dropout_rate = 0.2
+            self.zDim = 128
+
+    TWO_INPUTS = False          # ceVAE feeds (x, x_ce)
+    LOSS_KEYS = ('loss',)
+
+    def __init__(self, sess, config=None, network=None):
+        super().__init__(sess, config if config is not None else self.Config())
+        self.losses = {}
+        self.network = network
+        self.dropout = Placeholder([], 'dropout')
+        self.dropout_rate = Placeholder([], 'dropout_rate')
+        self.checkpointDir = os.path.join(self.config.checkpointDir or 'checkpoints', self.network.__name__)
+        self.logDir = os.path.join(os.getcwd(), 'logs', self.network.__name__, self.model_dir, datetime.now().strftime('%Y%m%d_%H%M%S'))
+        self.logger = Logger(self.sess, self.logDir, enabled=bool(getattr(self.config, 'useTensorboard', False)))
+        cfg = self.config
+        self.x = Placeholder([None, cfg.outputHeight, cfg.outputWidth, cfg.numChannels], 'x')
+        if self.TWO_INPUTS:
+            self.x_ce = Placeholder([None, cfg.outputHeight, cfg.outputWidth, cfg.numChannels], 'x_ce')
+            self.outputs = self.network(self.x, self.x_ce, dropout_rate=self.dropout_rate, dropout=self.dropout, config=cfg)
+        else:
+            self.outputs = self.network(self.x, dropout_rate=self.dropout_rate, dropout=self.dropout, config=cfg)
+        self.reconstruction = self.outputs['x_hat']
+        self.graph = self.reconstruction.graph
+        # device / data-parallel context (one process per GPU; world > 1 when launched under torchrun)
+        self.device = getattr(cfg, 'device', None) or f'cuda:{int(os.environ.get("LOCAL_RANK", 0))}'
+        self.math_mode = int(getattr(cfg, 'math_mode', abi.MATH_TC_3XTF32))
+        self.world = 1
+        self._allreduce = None
+        torch.cuda.set_device(self.device)
+        self.engine = ConvAutoencoderEngine(self.graph.arch, self.graph.S, self.graph.C, self.graph.zDim, self.graph.res,
+                                            batch=cfg.batchsize, device=self.device, math_mode=self.math_mode,
+                                            seed=int(getattr(cfg, 'seed', 1)))
+        self._eval_engines = {}
+        self._pinned = {}
+        self.get_number_of_trainable_params()
+        self.saver = self           # reference attribute; save/load live on the trainer itself
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self):
+        """Shard mini-batches over ranks; one NCCL all-reduce on the flat gradient buffer per step."""
+        from .. import dist as udist
+        udist.init_from_env()
+        self.world = udist.world_size()
+        if self.world > 1:
+            udist.broadcast_(self.engine.fp.params, src=0)
+            self._allreduce = udist.allreduce_sum_
+
+    # ------------------------------------------------------------------ reference helpers
+    def log_to_tensorboard(self, epoch, scalars, visuals, phase: Phase, name='x'):
+        for key in scalars.keys():
+            scalars[key] = np.mean(scalars[key])
+        vis = [v for v in visuals if v is not None]
+        summaries = dict(scalars)
+        if vis:
+            summaries[name] = np.vstack(vis)[:50]
+        self.logger.summarize(epoch, phase=phase, summaries_dict=summaries)
+
+    def load_checkpoint(self):
+        could_load, checkpoint_counter = self.load(self.checkpointDir)
+        if could_load:
+            last_epoch = checkpoint_counter
+            print(" [*] Load SUCCESS")
+        else:
+            last_epoch = 0
+            print(" [!] Load failed...")
+        return last_epoch
+
+    @property
+    def model_dir(self):
+        return "{}_d{}_s{}x{}_{}_b{}_z{}_{}".format(self.config.modelname, self.config.dataset, self.config.outputWidth,
+                                                    self.config.outputHeight, self.network.__name__, self.config.batchsize,
+                                                    self.config.zDim, self.config.description)
+
+    # ------------------------------------------------------------------ the step (replaces sess.run)
+    def _stage(self, key, arr):
+        """Host batch -> pinned staging buffer -> device input buffer (async H2D on the compute stream)."""
+        arr = np.ascontiguousarray(arr, np.float32)
+        buf = self._pinned.get((key, arr.shape))
+        if buf is None:
+            buf = torch.empty(arr.shape, dtype=torch.float32).pin_memory()
+            self._pinned[(key, arr.shape)] = buf
+        buf.numpy()[...] = arr
+        return buf
+
+    def run_batch(self, batch, phase: Phase, batch_ce=None, fetch_maps=False, want_anomaly=False):
+        """One ``sess.run`` of the reference's process() loop (AE.py:70-83): feed a host batch, run the step on the GPU,
+        fetch the scalar losses (and, on request, the reconstruction / L1 maps the reference fetches every step)."""
+        eng, cfg = self.engine, self.config
+        eng.set_inputs(self._stage('x', batch), None if batch_ce is None else self._stage('x_ce', batch_ce))
+        if phase == Phase.TRAIN:
+            eng.train_step(cfg.learningrate, beta1=cfg.beta1, dropout_rate=cfg.dropout_rate, dropout=True,
+                           allreduce=self._allreduce, world=self.world, want_anomaly=want_anomaly,
+                           use_graph=bool(getattr(cfg, 'use_cuda_graph', True)))
+        else:
+            eng.draw_noise(False, 0.0)
+            eng.forward(training=False, dropout_rate=0.0)
+        run = dict(eng.losses())                      # device -> host read of the step's scalars
+        if fetch_maps:
+            run['reconstruction'] = eng.br[0].xhat.cpu().numpy()
+            run['L1'] = eng.br[0].l1.cpu().numpy()
+        run = {k: (np.float32(v) if np.ndim(v) == 0 else v) for k, v in run.items()}
+        return run
+
+    def _eval_engine(self, n):
+        n = int(n)
+        if n not in self._eval_engines:
+            g = self.graph
+            self._eval_engines[n] = ConvAutoencoderEngine(g.arch, g.S, g.C, g.zDim, g.res, batch=n, device=self.device,
+                                                          math_mode=self.math_mode, share_params=self.engine.fp)
+        return self._eval_engines[n]
+
+    def reconstruct(self, x, dropout=False):
+        """Forward-only pass (AE.py:92-110).  Accepts [H,W,C] or a whole stack [N,H,W,C] (batched on the device)."""
+        if x.ndim < 4:
+            x = np.expand_dims(x, 0)
+        x = np.ascontiguousarray(x, np.float32)
+        N = x.shape[0]
+        chunk = min(N, int(getattr(self.config, 'evalBatchsize', 128)))
+        eng = self._eval_engine(chunk)
+        rec = np.empty_like(x)
+        rate = self.config.dropout_rate if dropout else 0.0
+        for i in range(0, N, chunk):
+            xb = x[i:i + chunk]
+            n = xb.shape[0]
+            if n < chunk:
+                xb = np.concatenate([xb, np.zeros((chunk - n,) + xb.shape[1:], np.float32)], 0)
+            eng.set_inputs(xb, xb if self.TWO_INPUTS else None)
+            eng._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+            eng.draw_noise(dropout, rate)
+            eng.forward(training=False, dropout_rate=rate, branches=[0], need_l1=False)
+            rec[i:i + n] = eng.br[0].xhat.cpu().numpy()[:n]
+        results = {'reconstruction': rec}
+        results['l1err'] = np.sum(np.abs(x - rec))
+        results['l2err'] = np.sum(np.sqrt((x - rec) ** 2))
+        return results
+
+    # ------------------------------------------------------------------ epoch loops (AE.py:23-90)
+    def _make_ce_batch(self, batch, brainmasks, phase):
+        return None
+
+    def train(self, dataset):
+        self.variables = list(self.engine.specs.keys())
+        self.optim = self.create_optimizer(None, var_list=self.variables, learningrate=self.config.learningrate,
+                                           beta1=self.config.beta1, type=self.config.optimizer)
+        best_cost = inf
+        last_improvement = 0
+        last_epoch = self.load_checkpoint()
+        for epoch in range(last_epoch, self.config.numEpochs):
+            self.process(dataset, epoch, Phase.TRAIN, self.optim)
+            last_epoch += 1
+            self.save(self.checkpointDir, last_epoch)
+            val_scalars = self.process(dataset, epoch, Phase.VAL)
+            best_cost, last_improvement, stop = indicate_early_stopping(val_scalars['loss'], best_cost, last_improvement)
+            if stop:
+                print('Early stopping was triggered due to no improvement over the last 5 epochs')
+                break
+
+    def process(self, dataset, epoch, phase: Phase, optim=None, visualization_keys=None):
+        scalars = defaultdict(list)
+        visuals = []
+        num_batches = dataset.num_batches(self.config.batchsize, set=phase.value)
+        every = int(getattr(self.config, 'fetchMapsEvery', 0))      # the reference fetches the full maps EVERY step
+        verbose = bool(getattr(self.config, 'verbose', True))
+        for idx in range(0, num_batches):
+            if self.TWO_INPUTS:
+                batch, _, brainmasks = dataset.next_batch(self.config.batchsize, return_brainmask=True, set=phase.value)
+                batch_ce = self._make_ce_batch(batch, brainmasks, phase)
+            else:
+                batch, _, _ = dataset.next_batch(self.config.batchsize, set=phase.value)
+                batch_ce = None
+            fetch = every > 0 and idx % every == 0
+            run = self.run_batch(batch, phase, batch_ce=batch_ce, fetch_maps=fetch, want_anomaly=self.TWO_INPUTS)
+            if verbose:
+                print(f'Epoch ({phase.value}): [{epoch:2d}] [{idx:4d}/{num_batches:4d}] loss: {run["loss"]:.8f}')
+            update_log_dicts(*trainer_utils.get_summary_dict(batch, run, visualization_keys), scalars, visuals)
+        self.log_to_tensorboard(epoch, scalars, visuals, phase)
+        return scalars
+
+
+def update_log_dicts(scalars, visuals, train_scalars, train_visuals):
+    for k, v in list(scalars.items()):
+        train_scalars[k].append(v)
+    train_visuals.append(visuals)
+
+
+def indicate_early_stopping(current_cost, best_cost, last_improvement):
+    if current_cost < best_cost:
+        best_cost = current_cost
+        last_improvement = 0
+        return best_cost, last_improvement, False
+    else:
+        last_improvement += 1
+        if last_improvement >= 5:
+            return best_cost, last_improvement, True
+        return best_cost, last_improvement, False

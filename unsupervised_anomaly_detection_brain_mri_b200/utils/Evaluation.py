@@ -1,0 +1,201 @@
+"""Residual-map anomaly scoring and evaluation (mirror of the hot part of reference utils/Evaluation.py).
+
+Device side (hand-written kernels through the C ABI):
+  * the reconstruction of a WHOLE sub-volume in one batched forward pass (the reference calls ``reconstruct`` once
+    per slice with batch 1: Evaluation.py:246-250),
+  * the residual / brain-mask / hyper-intensity-prior arithmetic (:282-291) -> ``uad_residual_score``,
+  * ``diffs > t`` + Dice counts for every candidate threshold (:444-457, Metrics.py:138-162) -> ``uad_threshold_counts``.
+Host side (kept in scipy / sklearn exactly like the reference): brain-mask erosion (:84-89), 5x5x5 median filter
+(:108-110), connected-component filter (:113-127, scipy.ndimage.label because skimage is absent), ROC / PRC.
+PNG / NIfTI export and plots are out of scope."""
+import os
+import time
+
+import numpy as np
+import scipy.ndimage
+import torch
+
+from .. import abi
+from ..trainers import Metrics
+
+
+def should(options, key):
+    return key in options and options[key]
+
+
+def get_eval_dictionary():
+    return {'x': [], 'reconstructions': [], 'diffs': [], 'labelmaps': [], 'l1reconstructionErrors': [],
+            'l2reconstructionErrors': [], 'reconstructionTimes': [], 'epistemic_variance': []}
+
+
+def erode_brainmask(brainmask):
+    strel = scipy.ndimage.generate_binary_structure(2, 1)
+    return scipy.ndimage.binary_erosion(np.squeeze(brainmask), structure=strel, iterations=12)
+
+
+def apply_brainmask(x, brainmask, erode=True):
+    if erode:
+        brainmask = erode_brainmask(brainmask)
+    return np.multiply(np.squeeze(brainmask), np.squeeze(x))
+
+
+def apply_3d_median_filter(volume, kernelsize=5):
+    return scipy.ndimage.median_filter(volume, (kernelsize, kernelsize, kernelsize))
+
+
+def filter_3d_connected_components(volume):
+    """Remove 26-connected components with filled area <= 7 (Evaluation.py:113-127; skimage.label(connectivity=3))."""
+    sz = None
+    if volume.ndim > 3:
+        sz = volume.shape
+        volume = np.reshape(volume, [sz[0] * sz[1], sz[2], sz[3]])
+    cc, n = scipy.ndimage.label(volume, structure=np.ones((3, 3, 3)))
+    if n:
+        for idx, sl in enumerate(scipy.ndimage.find_objects(cc), start=1):
+            if sl is None:
+                continue
+            comp = cc[sl] == idx
+            if comp.sum() <= 7 and scipy.ndimage.binary_fill_holes(comp).sum() <= 7:
+                volume[sl][comp] = 0
+    if sz is not None:
+        volume = np.reshape(volume, sz)
+    return volume
+
+
+def residual_on_device(x, x_rec, mask, prior_quantile, keep_positive, apply_prior, device):
+    """[N,H,W] float32 stacks -> float64 sub-volume, via uad_residual_score (bit-exact with Evaluation.py:282-291)."""
+    xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(device)
+    rd = torch.from_numpy(np.ascontiguousarray(x_rec, np.float32)).to(device)
+    md = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8)).to(device)
+    out = torch.empty_like(xd)
+    abi.call('uad_residual_score', xd.data_ptr(), rd.data_ptr(), None if md is None else md.data_ptr(), float(prior_quantile),
+             int(bool(keep_positive)), int(bool(apply_prior)), out.data_ptr(), xd.numel(),
+             torch.cuda.current_stream().cuda_stream)
+    sub = np.zeros(x.shape, np.float64)
+    sub[...] = out.cpu().numpy()
+    return sub
+
+
+def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST"):
+    eval_dict = get_eval_dictionary()
+    patients = [datasetObj.patients[i] for i in datasetObj.get_patient_idx(split=split)]
+    H, W = options['train']['outputHeight'], options['train']['outputWidth']
+    device = modelObj.device
+    for p, patient in enumerate(patients):
+        filtered_files = patient['filtered_files']
+        if type(filtered_files) is not list:
+            filtered_files = [filtered_files]
+        done = False
+        for nii_filename in filtered_files:
+            if done:
+                continue
+            nii, nii_seg, nii_skullmap = datasetObj.load_volume_and_groundtruth(nii_filename, patient)
+            prior_quantile = np.quantile(nii.data, 0.9)
+            if min(nii.shape()) < (datasetObj.options.sliceEnd - datasetObj.options.sliceStart):
+                continue
+            slice_start = datasetObj.options.sliceStart or 0
+            slice_end = min(datasetObj.options.sliceEnd, nii.num_slices_along_axis(datasetObj.options.axis))
+            xs, segs, skulls = [], [], []
+            for s in range(slice_start, slice_end):
+                slice_data = nii.get_slice(s, datasetObj.options.axis)
+                slice_seg = nii_seg.get_slice(s, datasetObj.options.axis).astype(int)
+                slice_skullmap = nii_skullmap.get_slice(s, datasetObj.options.axis).astype(int)
+                if datasetObj.options.sliceResolution is not None and tuple(slice_data.shape) != tuple(datasetObj.options.sliceResolution):
+                    zoom_factor = tuple([i / j for (i, j) in zip(datasetObj.options.sliceResolution, slice_data.shape)])
+                    slice_data = scipy.ndimage.zoom(slice_data, zoom_factor)
+                    slice_seg = scipy.ndimage.zoom(slice_seg, zoom_factor, mode="nearest")
+                    slice_skullmap = scipy.ndimage.zoom(slice_skullmap, zoom_factor, mode="nearest")
+                xs.append(slice_data.astype(np.float32))
+                segs.append(slice_seg)
+                skulls.append(slice_skullmap)
+            x = np.stack(xs)                                       # [Z,H,W] float32
+            _tmp = time.time()
+            num_samples = options["numMonteCarloSamples"] if should(options, "numMonteCarloSamples") else 1
+            recs = []
+            for i in range(num_samples):                           # MC-dropout loop (:239-267), one batched pass per sample
+                results = modelObj.reconstruct(x[..., None], dropout=num_samples > 1)
+                recs.append(results['reconstruction'][..., 0])
+            x_rec = recs[0] if num_samples == 1 else np.mean(np.array(recs), axis=0).astype(np.float32)
+            eval_dict['reconstructionTimes'] += [(time.time() - _tmp) / max(len(xs), 1)] * len(xs)
+            erode = should(options, "erodeBrainmask")
+            masks = np.stack([erode_brainmask(m) if erode else np.squeeze(m).astype(bool) for m in skulls])
+            subvolume = residual_on_device(x, x_rec, masks, prior_quantile, should(options, "keepOnlyPositiveResiduals"),
+                                           should(options, "applyHyperIntensityPrior"), device)
+            if num_samples > 1:
+                var = Metrics.combined_predictive_uncertainty(np.array(recs), np.zeros_like(np.array(recs)), axis=0)
+                eval_dict['epistemic_variance'] += list(var)
+            if should(options, "medianFiltering"):
+                subvolume = apply_3d_median_filter(subvolume)
+            eval_dict['x'] += list(x[..., None])
+            eval_dict['reconstructions'] += list(x_rec[..., None])
+            eval_dict['labelmaps'] += segs
+            for i in range(len(xs)):
+                eval_dict['l1reconstructionErrors'] += [np.sum(np.abs(x[i] - x_rec[i]))]
+                eval_dict['l2reconstructionErrors'] += [np.sum(np.sqrt((x[i] - x_rec[i]) ** 2))]
+            eval_dict['diffs'] += [subvolume]
+            done = True
+    eval_dict['x'] = np.squeeze(np.array(eval_dict['x']))
+    eval_dict['reconstructions'] = np.squeeze(np.array(eval_dict['reconstructions']))
+    eval_dict['diffs'] = np.squeeze(np.array(eval_dict['diffs']))
+    if eval_dict['diffs'].ndim > 3:
+        d = eval_dict['diffs']
+        eval_dict['diffs'] = np.reshape(d, [d.shape[0] * d.shape[1], d.shape[2], d.shape[3]])
+    eval_dict['labelmaps'] = np.squeeze(np.array(eval_dict['labelmaps']))
+    eval_dict['l1reconstructionErrorMean'] = np.mean(eval_dict['l1reconstructionErrors'])
+    eval_dict['l1reconstructionErrorVariance'] = np.var(eval_dict['l1reconstructionErrors'])
+    eval_dict['l2reconstructionErrorMean'] = np.mean(eval_dict['l2reconstructionErrors'])
+    eval_dict['l2reconstructionErrorVariance'] = np.var(eval_dict['l2reconstructionErrors'])
+    eval_dict['reconstructionTimes'] = np.mean(np.array(eval_dict['reconstructionTimes']))
+    return eval_dict, patients
+
+
+def evaluate(datasetPC, gan, options, epoch='last', description=None):
+    """Evaluation.py:372-526 minus file export / plots: returns the evalPC dictionary (also saved as evalPC.npy)."""
+    model = gan
+    sample_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir, str(description or ''))
+    os.makedirs(sample_dir, exist_ok=True)
+    eval_pc, patients = _evaluate(datasetPC, model, sample_dir, options, "TEST")
+    diffs = eval_pc['diffs']
+    labels = (eval_pc['labelmaps'] > 0)
+    scorer = Metrics.DeviceScorer(diffs, labels, device=model.device)
+    flat_d, flat_l = diffs.flatten(), labels.flatten().astype(int)
+    if should(options, 'exportROC'):
+        eval_pc['AUC'], _fpr, _tpr, _ = Metrics.compute_roc(flat_d, flat_l)
+    if should(options, 'exportPRC'):
+        eval_pc['AUPRC'], _p, _r, _ = Metrics.compute_prc(flat_d, flat_l)
+    t0 = time.time()
+    best_dice, best_thresh = Metrics.compute_dice_curve_recursive(diffs, labels, granularity=10, scorer=scorer)
+    eval_pc['diceSearchTime'] = time.time() - t0
+    eval_pc['bestDiceScore'], eval_pc['bestThreshold'] = best_dice, best_thresh
+    threshold = best_thresh if options['threshold'] == 'bestdice' else float(options['threshold'])
+    eval_pc['threshold'] = threshold
+    mask = scorer.threshold_mask(threshold).cpu().numpy().astype(bool).reshape(diffs.shape)     # == diffs > threshold, bit-exact
+    mask = filter_3d_connected_components(mask.copy())
+    eval_pc['thresholded'] = mask
+    eval_pc['DICE'] = Metrics.dice(mask, labels)
+    eval_pc['TPR'] = Metrics.tpr(mask, labels)
+    eval_pc['FPR'] = Metrics.tpr(mask, labels)          # sic: the reference computes FPR with Metrics.tpr (Evaluation.py:490)
+    eval_pc['Precision'] = Metrics.precision(mask, labels)
+    n_per = diffs.shape[0] // max(len(patients), 1)
+    eval_pc['perPatientDice'] = [Metrics.dice(mask[i * n_per:(i + 1) * n_per], labels[i * n_per:(i + 1) * n_per])
+                                 for i in range(len(patients))]
+    np.save(os.path.join(sample_dir, 'evalPC.npy'), {k: v for k, v in eval_pc.items() if np.ndim(v) == 0})
+    with open(os.path.join(sample_dir, 'evalPC.txt'), 'w') as f:
+        for k, v in eval_pc.items():
+            if np.ndim(v) == 0:
+                f.write(f'{k}: {v}\n')
+    return eval_pc
+
+
+def determine_threshold_on_labeled_patients(datasets, model, options, description=''):
+    """Evaluation.py:529-567: best-Dice threshold over the labelled (validation) patients."""
+    diffs, labels = [], []
+    for ds in datasets:
+        sample_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir, str(description))
+        os.makedirs(sample_dir, exist_ok=True)
+        ev, _ = _evaluate(ds, model, sample_dir, options, "TEST")
+        diffs.append(ev['diffs'])
+        labels.append(ev['labelmaps'] > 0)
+    diffs, labels = np.concatenate(diffs, 0), np.concatenate(labels, 0)
+    scorer = Metrics.DeviceScorer(diffs, labels, device=model.device)
+    return Metrics.compute_dice_curve_recursive(diffs, labels, granularity=10, scorer=scorer)

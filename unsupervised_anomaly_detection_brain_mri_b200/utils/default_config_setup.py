@@ -1,0 +1,112 @@
+"""options / dataset / config plumbing (mirror of reference utils/default_config_setup.py:13-271, pure Python there too)."""
+import json
+import os
+from enum import Enum
+
+from ..dataloaders.SYNTHETIC import SYNTHETIC
+
+base_path = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+class Dataset(Enum):
+    BRAINWEB = 'BRAINWEBDIR'
+    MSSEG2008_UNC = 'MSSEG2008DIR'
+    MSSEG2008_CHB = 'MSSEG2008DIR'
+    MSISBI2015 = 'MSISBI2015DIR'
+    MSLUB = 'MSLUBDIR'
+    Brainweb = 'BRAINWEBDIR'      # reference run.py:67,73,84,90 spells it this way; accept both
+    SYNTHETIC = 'SYNTHETICDIR'
+
+
+def get_options(batchsize, learningrate, numEpochs, zDim, outputWidth, outputHeight, slices_start=20, slices_end=130,
+                numMonteCarloSamples=0, config=None):
+    options = {}
+    if config:
+        options["globals"] = config
+    else:
+        path = os.path.join(base_path, "config.default.json")
+        if os.path.isfile(path):
+            with open(path, 'r') as f:
+                options["globals"] = json.load(f)
+        else:
+            options["globals"] = {"CHECKPOINTDIR": "checkpoints", "SAMPLEDIR": "samples"}
+    options['debug'] = False
+    options['data'] = {}
+    options['train'] = {}
+    options['train']['checkpointDir'] = options["globals"]["CHECKPOINTDIR"]
+    options['train']['samplesDir'] = options["globals"]["SAMPLEDIR"]
+    options['train']['batchsize'] = batchsize
+    options['train']['learningrate'] = learningrate
+    options['train']['numEpochs'] = numEpochs
+    options['train']['zDim'] = zDim
+    options['train']['snapshotAfter'] = 1000
+    options['train']['outputWidth'] = outputWidth
+    options['train']['outputHeight'] = outputHeight
+    options['train']['useTensorboard'] = True
+    options['train']['useMatplotlib'] = False
+    options['train']['tensorboardPort'] = 9001
+    options['sliceStart'] = slices_start
+    options['sliceEnd'] = slices_end
+    options['threshold'] = 'bestdice'
+    options['exportVolumes'] = False
+    options['exportPRC'] = True
+    options['exportROC'] = True
+    options['numMonteCarloSamples'] = numMonteCarloSamples
+    options['keepOnlyPositiveResiduals'] = True
+    options['applyHyperIntensityPrior'] = True
+    options['medianFiltering'] = True
+    options['erodeBrainmask'] = True
+    return options
+
+
+def get_synthetic_dataset_options(options, lesions, num_patients=None):
+    o = SYNTHETIC.Options()
+    o.sliceResolution = [options['train']['outputHeight'], options['train']['outputWidth']]
+    o.sliceStart = options['sliceStart']
+    o.sliceEnd = options['sliceEnd']
+    o.lesions = lesions
+    if num_patients is not None:
+        o.numPatients = num_patients
+    elif 'numPatients' in options.get('data', {}):
+        o.numPatients = options['data']['numPatients']
+    return o
+
+
+def get_datasets(options, dataset: Dataset = Dataset.BRAINWEB):
+    """(healthy train/val set, lesion test set).  The real MINC / NIfTI loaders are out of scope: every Dataset member maps
+    to the synthetic BrainWeb-shaped generator (healthy slices for training, slices with lesions + labels for testing)."""
+    hc = get_synthetic_dataset_options(options, lesions=False)
+    hc.partition = {'TRAIN': 0.7, 'VAL': 0.3, 'TEST': 0.0}
+    pc = get_synthetic_dataset_options(options, lesions=True, num_patients=options.get('data', {}).get('numTestPatients', 2))
+    pc.partition = {'TRAIN': 0.0, 'VAL': 0.0, 'TEST': 1.0}
+    pc.seed = 4321
+    return SYNTHETIC(hc), SYNTHETIC(pc)
+
+
+def get_config(trainer, options, optimizer, intermediateResolutions, dropout_rate, dataset):
+    config = trainer.Config()
+    config.dataset = type(dataset).__name__
+    config.description = ''
+    config.numChannels = dataset.num_channels
+    config.batchsize = options['train']['batchsize']
+    config.checkpointDir = options['train']['checkpointDir']
+    config.snapShotAfter = options['train']['snapshotAfter']
+    config.sampleDir = options['train']['samplesDir']
+    config.learningrate = options['train']['learningrate']
+    config.numEpochs = options['train']['numEpochs']
+    config.zDim = options['train']['zDim']
+    config.beta1 = 0.5
+    config.outputHeight = options['train']['outputHeight']
+    config.outputWidth = options['train']['outputWidth']
+    config.useTensorboard = options['train']['useTensorboard']
+    config.useMatplotlib = options['train']['useMatplotlib']
+    config.tensorboardPort = options['train']['tensorboardPort']
+    config.debugGradients = options['debug']
+    config.optimizer = optimizer
+    config.intermediateResolutions = intermediateResolutions
+    config.weightRegularization = 0.0
+    config.dropout_rate = dropout_rate
+    config.dropout = False
+    config.l1_weight = 1.0
+    config.options = options
+    return config
