@@ -1,8 +1,450 @@
-// tcgen05 / TMA implicit-GEMM conv kernels (placeholder until the tensor-core path lands).
+// tcgen05 / TMEM / TMA implicit-GEMM kernel for the conv family (Form F and Form T of uad_conv.cuh), sm_100a only.
+//
+//   D[128 pixels, N] += A[128 pixels, 32 ch] . B[32 ch, N]     per k-block (one filter tap x one 32-channel block)
+//
+// fp32 parity on tensor cores: 3xTF32.  Every fp32 operand x is split exactly into hi = x & 0xffffe000 (tf32-exact)
+// and lo = x - hi; the product is accumulated as lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (dropped lo*lo
+// term ~2^-22 relative).  Weights are split once per call by a prep kernel into pre-swizzled smem images; the
+// activation tile is split on the fly by a converter warpgroup that moves it from shared memory INTO TENSOR MEMORY, so
+// the three MMA passes read A from TMEM (tcgen05.mma "ts" form) and only B from shared memory - in "ss" form the
+// A re-reads would make the kernel shared-memory-bandwidth bound at N <= 128.
+//
+// Pipeline (one 128-pixel tile per CTA, up to 2 CTAs per SM so one CTA's epilogue overlaps the other's main loop):
+//   warp 0      TMA producer: 5-D tiled tensor map on the NHWC input (im2col by coordinates; OOB zero fill == SAME padding),
+//               + one bulk copy of the pre-swizzled {hi,lo} weight image                          -> full[s]
+//   warps 4-7   converters: smem row -> registers -> hi/lo -> tcgen05.st into TMEM A slot t        -> afull[t]
+//   warp 1      MMA issuer (one thread): 12 x tcgen05.mma.kind::tf32 per k-block, tcgen05.commit   -> empty[s], aempty[t]
+//   warps 4-7   epilogue: tcgen05.ld accumulator -> +bias, frozen-BN affine, activation -> smem transpose ->
+//               coalesced 512-byte row stores of z and/or a
+#include <cuda.h>
+
 #include "uad_conv.cuh"
 
-int uad_tc_gather_supported(int, int, int, int) { return 0; }
-size_t uad_tc_gather_ws_bytes(int, int, int) { return 0; }
-int uad_launch_gather_tc(const GatherParams&, int, int, bool, const float*, int, void*, size_t, cudaStream_t) {
-  return uad_set_error("tcgen05 conv path not built");
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kKBlk = 32;                    // fp32 channels per k-block = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kKBlk * 4;  // 16 KB
+constexpr int kNumASlots = 2;
+constexpr int kTmemCols = 256;               // [0,128) accumulator, [128,256) two {hi,lo} A slots
+constexpr int kTmemAOff = 128;
+constexpr uint32_t kSpinLimit = 1u << 26;    // bounded mbarrier spins: trap instead of hanging the GPU
+
+struct TcParams {
+  int TW, TH, TB, lgTW, lgTH;
+  int tiles_w, tiles_h;
+  int B, C, Cblks, N;
+  int OH, OW, osh;
+  int stride2;
+  int stages;
+  float* z_out;
+  float* a_out;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float bn_c, alpha;
+  int act;
+  const float* wimg;   // [k*k][Cblks][2][N][32] pre-swizzled
+  TapSet taps[4];
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
+      "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);         // start address  [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset = 1024 B [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (sm_100) [46,48)
+  d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B [61,64)
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(256, 1)
+gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int N = p.N;
+  const uint32_t b_bytes = 2u * N * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int S = p.stages;
+  // bookkeeping lives after the pipeline stages
+  const uint32_t misc = smem_base + S * stage_bytes;
+  const uint32_t bar_full = misc;                       // S x 8
+  const uint32_t bar_empty = misc + 64;                 // S x 8
+  const uint32_t bar_afull = misc + 128;                // 2 x 8
+  const uint32_t bar_aempty = misc + 144;               // 2 x 8
+  const uint32_t bar_acc = misc + 160;
+  const uint32_t tmem_slot = misc + 168;
+  float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256);   // bias[N], scale[N], shift[N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TapSet& ts = p.taps[blockIdx.y];
+  const int nkb = ts.n * p.Cblks;
+
+  // tile origin on the M-grid
+  const int tile = blockIdx.x;
+  const int twi = tile % p.tiles_w;
+  const int thi = (tile / p.tiles_w) % p.tiles_h;
+  const int tbi = tile / (p.tiles_w * p.tiles_h);
+  const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kNumASlots; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {
+    for (int n = lane; n < N; n += 32) {
+      epi[n] = p.bias ? p.bias[n] : 0.f;
+      epi[N + n] = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
+      epi[2 * N + n] = p.beta ? p.beta[n] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      int tap = 0, cb = 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        const uint32_t ph = (i / S) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, kABytes + b_bytes);
+        const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
+        const uint32_t a_dst = smem_base + s * stage_bytes;
+        if (p.stride2)
+          tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
+        else
+          tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
+        const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
+        bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+        if (++cb == p.Cblks) { cb = 0; ++tap; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S, t = i % kNumASlots;
+        mbar_wait(bar_full + 8 * s, (i / S) & 1);               // weight image landed (async proxy -> visible)
+        mbar_wait(bar_afull + 8 * t, (i / kNumASlots) & 1);     // converters filled TMEM A slot t
+        tc_fence_after();
+        const uint32_t bhi = smem_base + s * stage_bytes + kABytes;
+        const uint32_t blo = bhi + N * 128;
+        const uint32_t a_hi = tmem_base + kTmemAOff + t * 64;
+        const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                           // K = 8 tf32 per instruction -> 32 bytes along the swizzle row
+          const uint64_t dhi = make_sw128_desc(bhi + j * 32);
+          const uint64_t dlo = make_sw128_desc(blo + j * 32);
+          mma_tf32_ts(tmem_base, a_lo + j * 8, dhi, idesc, (i | j) != 0);
+          mma_tf32_ts(tmem_base, a_hi + j * 8, dlo, idesc, 1u);
+          mma_tf32_ts(tmem_base, a_hi + j * 8, dhi, idesc, 1u);
+        }
+        tc_commit(bar_empty + 8 * s);                           // smem stage reusable once these MMAs retire
+        tc_commit(bar_aempty + 8 * t);                          // TMEM A slot reusable
+        if (i == nkb - 1) tc_commit(bar_acc);                   // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== converters, then epilogue
+    const int row = threadIdx.x - 128;                          // tile row == TMEM lane
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S, t = i % kNumASlots;
+      mbar_wait(bar_full + 8 * s, (i / S) & 1);
+      const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                             // 16-byte chunk j of this row sits at (j ^ (row & 7))
+        const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
+        const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
+          hi[4 * j + e] = h;
+          lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+        }
+      }
+      mbar_wait(bar_aempty + 8 * t, ((i / kNumASlots) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t a_slot = lane_base + kTmemAOff + t * 64;
+      tmem_st32(a_slot, hi);
+      tmem_st32(a_slot + 32, lo);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_afull + 8 * t);
+    }
+
+    // ---- epilogue: accumulator -> (z, a) -> smem transpose -> coalesced rows
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    // output pixel of THIS thread's row (shuffled to the storing lanes below)
+    const int tw = row & (p.TW - 1);
+    const int th = (row >> p.lgTW) & (p.TH - 1);
+    const int tb = row >> (p.lgTW + p.lgTH);
+    const int b = b0 + tb;
+    const long long my_off = (b < p.B)
+        ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
+        : -1;
+    const int ldw = N + 4;
+    float* stg = reinterpret_cast<float*>(smem_gen) + (size_t)q * 32 * ldw;     // this warp's 32 x (N+4) staging rows
+    const int lanes_per_row = N / 4;                    // float4 lanes covering one output row
+    const int rows_per_it = 32 / lanes_per_row;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float* out = pass == 0 ? p.z_out : p.a_out;
+      if (!out) continue;
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_base + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int n = c0 + j + e;
+            const float z = __uint_as_float(v[j + e]) + epi[n];
+            o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], p.act, p.alpha);
+          }
+          *reinterpret_cast<float4*>(stg + lane * ldw + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      __syncwarp();
+      for (int rr = 0; rr < 32; rr += rows_per_it) {
+        const int r = rr + lane / lanes_per_row;
+        const int c = (lane % lanes_per_row) * 4;
+        const long long off = __shfl_sync(0xffffffffu, my_off, r);
+        if (off >= 0) {
+          const float4 val = *reinterpret_cast<const float4*>(stg + r * ldw + c);
+          *reinterpret_cast<float4*>(out + off + c) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight images
+// raw weights -> per (tap, 32-channel block): {hi, lo} images of [N rows][32 k] fp32 in the SWIZZLE_128B byte order the
+// UMMA descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n]; true: raw[t][n][c].
+__global__ void weight_image_kernel(const float* __restrict__ w, float* __restrict__ img, int taps, int C, int N, int transposed) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)taps * C * N;
+  if (i >= total) return;
+  const int k = i % kKBlk;                 // channel within block
+  const int n = (i / kKBlk) % N;
+  const int cb = (i / ((size_t)kKBlk * N)) % (C / kKBlk);
+  const int t = i / ((size_t)C * N);
+  const int c = cb * kKBlk + k;
+  const float v = transposed ? w[((size_t)t * N + n) * C + c] : w[((size_t)t * C + c) * N + n];
+  const uint32_t h = __float_as_uint(v) & 0xffffe000u;
+  const float lo = v - __uint_as_float(h);
+  const size_t base = ((size_t)(t * (C / kKBlk) + cb)) * 2 * N * kKBlk;
+  const int pos = n * kKBlk + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3));
+  img[base + pos] = __uint_as_float(h);
+  img[base + (size_t)N * kKBlk + pos] = lo;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+}  // namespace
+
+int uad_tc_gather_supported(int Cin, int N, int lgMH, int lgMW) {
+  if (Cin % kKBlk != 0 || Cin < kKBlk) return 0;
+  if (!(N == 32 || N == 64 || N == 128)) return 0;
+  if (lgMH < 3 || lgMW < 3) return 0;          // M-grid at least 8x8 (two images per tile)
+  return 1;
+}
+
+size_t uad_tc_gather_ws_bytes(int ksize, int Cin, int N) {
+  if (Cin % kKBlk != 0) return 0;
+  return (size_t)ksize * ksize * Cin * N * 2 * sizeof(float) + 1024;
+}
+
+int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
+                         int math_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+  UAD_REQUIRE(math_mode == UAD_MATH_TC_3XTF32, "gather_gemm_tc: only the 3xTF32 mode is implemented (got %d)", math_mode);
+  const int C = g.Cin, N = g.N;
+  const size_t need = uad_tc_gather_ws_bytes(ksize, C, N);
+  UAD_REQUIRE(ws && ws_bytes >= need, "gather_gemm_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+  UAD_REQUIRE(((uintptr_t)ws % 128) == 0 && ((uintptr_t)g.in % 16) == 0, "gather_gemm_tc: unaligned buffers");
+  EncodeTiledFn encode = get_encode_fn();
+  UAD_REQUIRE(encode != nullptr, "gather_gemm_tc: cuTensorMapEncodeTiled entry point unavailable");
+
+  float* img = reinterpret_cast<float*>(ws);
+  {
+    const size_t total = (size_t)ksize * ksize * C * N;
+    weight_image_kernel<<<uad_cdiv(total, 256), 256, 0, st>>>(w_raw, img, ksize * ksize, C, N, weights_transposed ? 1 : 0);
+    UAD_LAUNCH_CHECK("weight_image");
+  }
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  const int MW = 1 << g.lgMW, MH = 1 << g.lgMH;
+  p.TW = MW < kTileM ? MW : kTileM;
+  p.TH = (kTileM / p.TW) < MH ? (kTileM / p.TW) : MH;
+  p.TB = kTileM / (p.TW * p.TH);
+  p.lgTW = uad_ilog2(p.TW);
+  p.lgTH = uad_ilog2(p.TH);
+  p.tiles_w = MW / p.TW;
+  p.tiles_h = MH / p.TH;
+  const int tiles_b = uad_cdiv(g.B, p.TB);
+  p.B = g.B; p.C = C; p.Cblks = C / kKBlk; p.N = N;
+  p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
+  p.stride2 = (g.sh == 2);
+  p.stages = (N == 128) ? 3 : 4;
+  p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
+  p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
+  p.wimg = img;
+  for (int c = 0; c < 4; ++c) p.taps[c] = g.taps[c];
+
+  // 5-D tensor map over the NHWC input: (channel [x parity], W, parity/1, H, B); box = (32 ch, TW, 1, TH, TB)
+  CUtensorMap tmap;
+  cuuint64_t dims[5], strides[4];
+  const cuuint64_t e = sizeof(float);
+  if (p.stride2) {
+    dims[0] = 2ull * C; dims[1] = g.IW / 2; dims[2] = 2; dims[3] = g.IH / 2; dims[4] = g.B;
+    strides[0] = 2ull * C * e; strides[1] = (cuuint64_t)g.IW * C * e; strides[2] = 2ull * g.IW * C * e;
+    strides[3] = (cuuint64_t)g.IH * g.IW * C * e;
+  } else {
+    dims[0] = C; dims[1] = g.IW; dims[2] = 1; dims[3] = g.IH; dims[4] = g.B;
+    strides[0] = (cuuint64_t)C * e; strides[1] = (cuuint64_t)g.IW * C * e; strides[2] = (cuuint64_t)g.IW * C * e;
+    strides[3] = (cuuint64_t)g.IH * g.IW * C * e;
+  }
+  cuuint32_t box[5] = {(cuuint32_t)kKBlk, (cuuint32_t)p.TW, 1u, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.in), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UAD_REQUIRE(cr == CUDA_SUCCESS, "gather_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  const size_t stage_bytes = kABytes + 2u * N * 128u;
+  const size_t smem = 1024 + p.stages * stage_bytes + 256 + 3 * N * sizeof(float) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, nclasses);
+  gather_gemm_tc<<<grid, 256, smem, st>>>(tmap, p);
+  UAD_LAUNCH_CHECK("gather_gemm_tc");
+  return 0;
 }
