@@ -95,10 +95,12 @@ int uad_act_bn_bwd(const float* da, const float* z, const float* gamma, const fl
  * x [M,K], w [K,N], mask [M,N] of {0,1} or NULL, z = (x.W+b)*mask*mask_scale, a = act(gamma*bn_c*z+beta). */
 int uad_dense_fwd(const float* x, const float* w, const float* bias, const float* mask, float mask_scale,
                   const float* gamma, const float* beta, float* z_out, float* a_out, int M, int K, int N, int act,
-                  float alpha, float bn_c, void* stream);
+                  float alpha, float bn_c, void* ws, size_t ws_bytes, void* stream);
+/* scratch for uad_dense_fwd / uad_dense_bwd (deterministic split-K partials); smaller buffers only reduce parallelism */
+size_t uad_dense_workspace_bytes(int M, int K, int N);
 /* dz [M,N] is the gradient w.r.t. z (post-dropout); dx may be NULL */
 int uad_dense_bwd(const float* x, const float* w, const float* dz, const float* mask, float mask_scale, float* dx,
-                  float* dw, float* dbias, int M, int K, int N, int accumulate, void* stream);
+                  float* dw, float* dbias, int M, int K, int N, int accumulate, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- reparameterise + KL (models/variational_autoencoder.py:33-34, trainers/VAE.py:38)
  * sigma=exp(ls); z=mu+eps*sigma; kl[b]=0.5*sum_j(mu^2+sigma^2-log(sigma^2)-1).  eps NULL => z=mu (ceVAE ce-branch) */

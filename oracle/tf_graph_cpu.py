@@ -242,11 +242,16 @@ def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, tr
     return out
 
 
-def losses(arch, out, x, x_ce=None, dtype=torch.float32):
-    """trainers/AE.py:28-29, VAE.py:36-42, ceVAE.py:38-50."""
+def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_ce=None):
+    """trainers/AE.py:28-29, VAE.py:36-42, ceVAE.py:38-50.
+
+    l1_sign / l1_sign_ce (test aid, default None = the literal |.|): evaluate |u| as u*sign with a CALLER-FIXED sign
+    pattern.  |u| is not differentiable at 0 and a 1e-7 perturbation of x_hat flips d|u|/du = sign(u) on pixels where
+    x_hat ~ x; fixing the pattern to the one of the implementation under test makes gradient comparisons measure the
+    arithmetic instead of that discontinuity (tests assert separately that the patterns differ on almost no pixel)."""
     xt = _t(x, dtype)
     L = {}
-    l1 = (out['x_hat'] - xt).abs()
+    l1 = (out['x_hat'] - xt).abs() if l1_sign is None else (out['x_hat'] - xt) * _t(l1_sign, dtype)
     rec = l1.sum(dim=(1, 2, 3))
     if arch == AE:
         L['L1'] = l1
@@ -261,7 +266,7 @@ def losses(arch, out, x, x_ce=None, dtype=torch.float32):
         L['loss'] = (rec + kl).mean()
         return L
     xc = _t(x_ce, dtype)
-    l1c = (out['x_hat_ce'] - xc).abs()
+    l1c = (out['x_hat_ce'] - xc).abs() if l1_sign_ce is None else (out['x_hat_ce'] - xc) * _t(l1_sign_ce, dtype)
     recc = l1c.sum(dim=(1, 2, 3))
     L['L1_vae'], L['L1_ce'] = l1, l1c
     L['L1'] = 0.5 * (l1 + l1c)
@@ -274,12 +279,12 @@ def losses(arch, out, x, x_ce=None, dtype=torch.float32):
 
 
 def loss_and_grads(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, training=True, dtype=torch.float32,
-                   want_anomaly=False):
+                   want_anomaly=False, l1_sign=None, l1_sign_ce=None):
     """tf.gradients of losses['loss'] w.r.t. every trainable variable (DLMODEL.py:112-131); ceVAE 'anomaly' (ceVAE.py:51)."""
     Pt = OrderedDict((k, _t(v, dtype).clone().requires_grad_(True)) for k, v in P.items())
     xt = _t(x, dtype).clone().requires_grad_(want_anomaly)
     out = forward(arch, Pt, xt, x_ce=x_ce, eps=eps, masks=masks, dropout_rate=dropout_rate, training=training, dtype=dtype)
-    L = losses(arch, out, xt, x_ce=x_ce, dtype=dtype)
+    L = losses(arch, out, xt, x_ce=x_ce, dtype=dtype, l1_sign=l1_sign, l1_sign_ce=l1_sign_ce)
     names = list(Pt.keys())
     grads = torch.autograd.grad(L['loss'], [Pt[k] for k in names], retain_graph=want_anomaly, allow_unused=True)
     G = OrderedDict((k, (g if g is not None else torch.zeros_like(Pt[k])).detach()) for k, g in zip(names, grads))

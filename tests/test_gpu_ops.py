@@ -168,7 +168,8 @@ def test_conv_first_layer_c1(B, H, Cout):
     assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
 
 
-@pytest.mark.parametrize('M,K,N,act', [(64, 1024, 128, 0), (256, 128, 16, 0), (256, 16, 128, 2), (7, 33, 19, 1), (64, 128, 1024, 0)])
+@pytest.mark.parametrize('M,K,N,act', [(64, 1024, 128, 0), (256, 128, 16, 0), (256, 16, 128, 2), (7, 33, 19, 1), (64, 128, 1024, 0),
+                                         (4096, 128, 16, 0), (4096, 16, 128, 2)])
 def test_dense_fwd_bwd(M, K, N, act):
     from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync
     rng = np.random.default_rng(M + K + N)
@@ -186,15 +187,20 @@ def test_dense_fwd_bwd(M, K, N, act):
     a_ref = {0: u, 1: F.leaky_relu(u, 0.3), 2: F.relu(u)}[act]
     z, a = empty(M, N), empty(M, N)
     dx_, dw_, dm_ = dev(x), dev(w), dev(mask)
+    from gpu_util import workspace
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    wsb = abi.lib().uad_dense_workspace_bytes(M, K, N)
+    ws = workspace(wsb)
     call('uad_dense_fwd', ptr(dx_), ptr(dw_), dptr(b), ptr(dm_), keep, dptr(gamma), dptr(beta), ptr(z), ptr(a), M, K,
-         N, act, 0.3, bn_c, st())
+         N, act, 0.3, bn_c, ptr(ws), wsb, st())
     sync()
     assert relerr(z.cpu().numpy(), z_ref.detach().numpy()) < TOL
     assert relerr(a.cpu().numpy(), a_ref.detach().numpy()) < TOL
     dz = rng.standard_normal((M, N)).astype(np.float32)
     gx, gw, gb = torch.autograd.grad((z_ref * t64(dz)).sum(), [xt, wt, bt])
     gxd, gwd, gbd = empty(M, K), empty(K, N), empty(N)
-    call('uad_dense_bwd', ptr(dx_), ptr(dw_), dptr(dz), ptr(dm_), keep, ptr(gxd), ptr(gwd), ptr(gbd), M, K, N, 0, st())
+    call('uad_dense_bwd', ptr(dx_), ptr(dw_), dptr(dz), ptr(dm_), keep, ptr(gxd), ptr(gwd), ptr(gbd), M, K, N, 0, ptr(ws), wsb,
+         st())
     sync()
     assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
     assert relerr(gwd.cpu().numpy(), gw.numpy()) < TOL

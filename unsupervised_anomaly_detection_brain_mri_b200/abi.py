@@ -33,8 +33,9 @@ SIGNATURES = {
     'uad_convT2d_wgrad': (_I, [_P] * 3 + [_I] * 8 + [_P, _Z, _P]),
     'uad_rowreduce_workspace_bytes': (_Z, [_LL, _I]),
     'uad_act_bn_bwd': (_I, [_P] * 8 + [_LL, _I, _I, _F, _F, _I, _P, _Z, _P]),
-    'uad_dense_fwd': (_I, [_P] * 4 + [_F] + [_P] * 4 + [_I] * 4 + [_F, _F, _P]),
-    'uad_dense_bwd': (_I, [_P] * 4 + [_F] + [_P] * 3 + [_I] * 4 + [_P]),
+    'uad_dense_fwd': (_I, [_P] * 4 + [_F] + [_P] * 4 + [_I] * 4 + [_F, _F, _P, _Z, _P]),
+    'uad_dense_workspace_bytes': (_Z, [_I, _I, _I]),
+    'uad_dense_bwd': (_I, [_P] * 4 + [_F] + [_P] * 3 + [_I] * 4 + [_P, _Z, _P]),
     'uad_reparam_kl_fwd': (_I, [_P] * 6 + [_I, _I, _P]),
     'uad_reparam_kl_bwd': (_I, [_P] * 4 + [_F] + [_P] * 2 + [_I, _I, _P]),
     'uad_final1x1_l1_fwd': (_I, [_P] * 7 + [_I] * 3 + [_P, _Z, _P]),

@@ -26,8 +26,11 @@ constexpr int kTileM = 128;
 constexpr int kKBlk = 32;                    // fp32 channels per k-block = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kKBlk * 4;  // 16 KB
 constexpr int kNumASlots = 2;
-constexpr int kTmemCols = 256;               // [0,128) accumulator, [128,256) two {hi,lo} A slots
-constexpr int kTmemAOff = 128;
+// TMEM columns: G "main" accumulators (hi*hi products, k-blocks dealt round-robin) + 1 "correction" accumulator
+// (lo*hi + hi*lo) of N columns each, then two {hi,lo} A slots of 64 columns.  The tensor core adds into its fp32
+// accumulator with truncation (measured: error grows linearly with the number of accumulations), so the large hi*hi
+// stream is spread over G accumulators and the small correction terms never disturb it; the epilogue sums them in
+// registers with round-to-nearest.
 constexpr uint32_t kSpinLimit = 1u << 26;    // bounded mbarrier spins: trap instead of hanging the GPU
 
 struct TcParams {
@@ -37,6 +40,8 @@ struct TcParams {
   int OH, OW, osh;
   int stride2;
   int stages;
+  int G;               // number of main accumulators (1 or 2)
+  int tmem_cols;       // power of two >= (G + 1) * N + 128
   float* z_out;
   float* a_out;
   const float* bias;
@@ -173,7 +178,7 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp == 3) {
@@ -215,6 +220,7 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // ===================================================================== MMA issuer
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t aoff = (p.G + 1) * N;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S, t = i % kNumASlots;
@@ -223,15 +229,17 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         tc_fence_after();
         const uint32_t bhi = smem_base + s * stage_bytes + kABytes;
         const uint32_t blo = bhi + N * 128;
-        const uint32_t a_hi = tmem_base + kTmemAOff + t * 64;
+        const uint32_t a_hi = tmem_base + aoff + t * 64;
         const uint32_t a_lo = a_hi + 32;
+        const uint32_t d_main = tmem_base + (i % p.G) * N;
+        const uint32_t d_corr = tmem_base + p.G * N;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                           // K = 8 tf32 per instruction -> 32 bytes along the swizzle row
           const uint64_t dhi = make_sw128_desc(bhi + j * 32);
           const uint64_t dlo = make_sw128_desc(blo + j * 32);
-          mma_tf32_ts(tmem_base, a_lo + j * 8, dhi, idesc, (i | j) != 0);
-          mma_tf32_ts(tmem_base, a_hi + j * 8, dlo, idesc, 1u);
-          mma_tf32_ts(tmem_base, a_hi + j * 8, dhi, idesc, 1u);
+          mma_tf32_ts(d_corr, a_lo + j * 8, dhi, idesc, (i | j) != 0);
+          mma_tf32_ts(d_corr, a_hi + j * 8, dlo, idesc, 1u);
+          mma_tf32_ts(d_main, a_hi + j * 8, dhi, idesc, (i >= p.G || j != 0) ? 1u : 0u);
         }
         tc_commit(bar_empty + 8 * s);                           // smem stage reusable once these MMAs retire
         tc_commit(bar_aempty + 8 * t);                          // TMEM A slot reusable
@@ -261,7 +269,7 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
       mbar_wait(bar_aempty + 8 * t, ((i / kNumASlots) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t a_slot = lane_base + kTmemAOff + t * 64;
+      const uint32_t a_slot = lane_base + (p.G + 1) * N + t * 64;
       tmem_st32(a_slot, hi);
       tmem_st32(a_slot + 32, lo);
       tmem_wait_st();
@@ -289,9 +297,18 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       float* out = pass == 0 ? p.z_out : p.a_out;
       if (!out) continue;
       for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + c0, v);
+        uint32_t v[32], u[32];
+        tmem_ld32(lane_base + c0, v);                           // main accumulator 0
+        tmem_ld32(lane_base + p.G * N + c0, u);                 // correction accumulator
         tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        if (p.G == 2) {
+          tmem_ld32(lane_base + N + c0, u);                     // main accumulator 1
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float o[4];
@@ -322,7 +339,7 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -411,6 +428,15 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
   p.stride2 = (g.sh == 2);
   p.stages = (N == 128) ? 3 : 4;
+  {
+    int max_taps = 0;
+    for (int c = 0; c < nclasses; ++c) max_taps = g.taps[c].n > max_taps ? g.taps[c].n : max_taps;
+    p.G = (max_taps * C > 640) ? 2 : 1;      // deep reductions: halve the accumulation chain length
+    int cols = (p.G + 1) * N + kNumASlots * 64;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < cols) p.tmem_cols <<= 1;
+    UAD_REQUIRE(p.tmem_cols <= 512, "gather_gemm_tc: TMEM budget exceeded");
+  }
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
   p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
   p.wimg = img;

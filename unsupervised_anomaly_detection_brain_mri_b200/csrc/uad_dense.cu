@@ -12,6 +12,8 @@ struct SmallGemm {
   const float* gamma; const float* beta; float bn_c; int act; float alpha;
   float* z_out; float* a_out;   // row-major [M,N]
   int accumulate;               // z_out += (plain accumulation mode: no bias/mask/affine expected)
+  float* partial;               // split-K: raw partial sums [splits][M][N] (epilogue runs in small_gemm_epilogue_kernel)
+  int kchunk;                   // K range per blockIdx.z
 };
 
 __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__ SmallGemm g) {
@@ -27,13 +29,15 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
+  const int kbeg = blockIdx.z * g.kchunk;
+  const int kend = min(g.K, kbeg + g.kchunk);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
     for (int i = tid; i < T * BK; i += 256) {
       int kk, mm;
       if (g.sa_k == 1) { kk = i % BK; mm = i / BK; } else { mm = i % T; kk = i / T; }
       int m = m0 + mm, k = k0 + kk;
       float v = 0.f;
-      if (m < g.M && k < g.K) {
+      if (m < g.M && k < kend) {
         long long off = m * g.sa_m + k * g.sa_k;
         v = g.A[off];
         if (g.Amul) v *= g.Amul[off] * g.mulscale;
@@ -45,7 +49,7 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__
       if (g.sb_n == 1) { nn = i % T; kk = i / T; } else { kk = i % BK; nn = i / BK; }
       int n = n0 + nn, k = k0 + kk;
       float v = 0.f;
-      if (n < g.N && k < g.K) {
+      if (n < g.N && k < kend) {
         long long off = k * g.sb_k + n * g.sb_n;
         v = g.Bm[off];
         if (g.Bmul) v *= g.Bmul[off] * g.mulscale;
@@ -77,6 +81,7 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__
       if (n >= g.N) continue;
       size_t o = (size_t)m * g.N + n;
       float z = acc[i][j];
+      if (g.partial) { g.partial[(size_t)blockIdx.z * g.M * g.N + o] = z; continue; }
       if (g.accumulate) { g.z_out[o] += z; continue; }
       if (g.bias) z += g.bias[n];
       if (g.mask) z *= g.mask[o] * g.mask_scale;
@@ -90,22 +95,80 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__
   }
 }
 
-static int launch_small(const SmallGemm& g, cudaStream_t st) {
+// split-K second stage: deterministic sum of the partials + the fused epilogue
+__global__ void small_gemm_epilogue_kernel(const __grid_constant__ SmallGemm g, int splits) {
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t MN = (size_t)g.M * g.N;
+  if (o >= MN) return;
+  const int n = (int)(o % g.N);
+  float z = 0.f;
+  for (int s = 0; s < splits; ++s) z += g.partial[(size_t)s * MN + o];
+  if (g.accumulate) { g.z_out[o] += z; return; }
+  if (g.bias) z += g.bias[n];
+  if (g.mask) z *= g.mask[o] * g.mask_scale;
+  if (g.z_out) g.z_out[o] = z;
+  if (g.a_out) {
+    float u = z;
+    if (g.gamma) u = g.gamma[n] * g.bn_c * z + g.beta[n];
+    g.a_out[o] = uad_act(u, g.act, g.alpha);
+  }
+}
+
+static int plan_splits(int M, int N, int K, int* kchunk) {
+  const int tiles = uad_cdiv(M, 64) * uad_cdiv(N, 64);
+  int splits = (2 * UAD_NUM_SMS) / tiles;
+  const int max_splits = uad_cdiv(K, 32);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  *kchunk = uad_cdiv(uad_cdiv(K, splits), 16) * 16;
+  return uad_cdiv(K, *kchunk);
+}
+
+static int launch_small(SmallGemm g, cudaStream_t st, void* ws, size_t ws_bytes) {
+  int kchunk;
+  const int splits = plan_splits(g.M, g.N, g.K, &kchunk);
+  if (splits > 1 && ws && ws_bytes >= (size_t)splits * g.M * g.N * sizeof(float)) {
+    g.partial = reinterpret_cast<float*>(ws);
+    g.kchunk = kchunk;
+    dim3 grid(uad_cdiv(g.M, 64), uad_cdiv(g.N, 64), splits);
+    small_gemm_kernel<<<grid, 256, 0, st>>>(g);
+    UAD_LAUNCH_CHECK("small_gemm");
+    small_gemm_epilogue_kernel<<<uad_cdiv((size_t)g.M * g.N, 256), 256, 0, st>>>(g, splits);
+    UAD_LAUNCH_CHECK("small_gemm_epilogue");
+    return 0;
+  }
+  g.partial = nullptr;
+  g.kchunk = g.K;
   dim3 grid(uad_cdiv(g.M, 64), uad_cdiv(g.N, 64));
   small_gemm_kernel<<<grid, 256, 0, st>>>(g);
   UAD_LAUNCH_CHECK("small_gemm");
   return 0;
 }
 
-// dbias[n] (+)= sum_m dz[m,n] * (mask ? mask*scale : 1)      (one block per 32 columns, deterministic)
+extern "C" size_t uad_dense_workspace_bytes(int M, int K, int N) {
+  // the three GEMMs of fwd/bwd: y[M,N] over K, dx[M,K] over N, dw[K,N] over M; plus the column-sum partials
+  int kc;
+  size_t a = (size_t)plan_splits(M, N, K, &kc) * M * N;
+  size_t b = (size_t)plan_splits(M, K, N, &kc) * M * K;
+  size_t c = (size_t)plan_splits(K, N, M, &kc) * K * N;
+  size_t d = (size_t)64 * N;
+  size_t mx = a > b ? a : b;
+  mx = mx > c ? mx : c;
+  mx = mx > d ? mx : d;
+  return mx * sizeof(float) + 256;
+}
+
+// dbias[n] (+)= sum_m dz[m,n] * (mask ? mask*scale : 1): grid (N/32, row-splits) -> partial[split][N] -> final (deterministic)
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dz, const float* __restrict__ mask, float scale,
-                                                     float* __restrict__ out, int M, int N, int accumulate) {
+                                                     float* __restrict__ partial, int M, int N, int rows_per_split) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + lane;
+  const int m0 = blockIdx.y * rows_per_split;
+  const int m1 = min(M, m0 + rows_per_split);
   float s = 0.f;
   if (n < N)
-    for (int m = warp; m < M; m += 8) {
+    for (int m = m0 + warp; m < m1; m += 8) {
       float v = dz[(size_t)m * N + n];
       if (mask) v *= mask[(size_t)m * N + n] * scale;
       s += v;
@@ -116,13 +179,21 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w][lane];
-    out[n] = accumulate ? out[n] + t : t;
+    partial[(size_t)blockIdx.y * N + n] = t;
   }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int splits, int N, float* __restrict__ out, int accumulate) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.f;
+  for (int s = 0; s < splits; ++s) t += partial[(size_t)s * N + n];
+  out[n] = accumulate ? out[n] + t : t;
 }
 
 extern "C" int uad_dense_fwd(const float* x, const float* w, const float* bias, const float* mask, float mask_scale,
                              const float* gamma, const float* beta, float* z_out, float* a_out, int M, int K, int N,
-                             int act, float alpha, float bn_c, void* stream) {
+                             int act, float alpha, float bn_c, void* ws, size_t ws_bytes, void* stream) {
   UAD_REQUIRE(M > 0 && K > 0 && N > 0, "uad_dense_fwd: bad dims");
   UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_dense_fwd: gamma/beta must both be set or both NULL");
   SmallGemm g = {};
@@ -133,11 +204,12 @@ extern "C" int uad_dense_fwd(const float* x, const float* w, const float* bias, 
   g.bias = bias; g.mask = mask; g.mask_scale = mask_scale;
   g.gamma = gamma; g.beta = beta; g.bn_c = bn_c; g.act = act; g.alpha = alpha;
   g.z_out = z_out; g.a_out = a_out;
-  return launch_small(g, (cudaStream_t)stream);
+  return launch_small(g, (cudaStream_t)stream, ws, ws_bytes);
 }
 
 extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, const float* mask, float mask_scale,
-                             float* dx, float* dw, float* dbias, int M, int K, int N, int accumulate, void* stream) {
+                             float* dx, float* dw, float* dbias, int M, int K, int N, int accumulate, void* ws, size_t ws_bytes,
+                             void* stream) {
   UAD_REQUIRE(M > 0 && K > 0 && N > 0, "uad_dense_bwd: bad dims");
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {   // dx[M,K] = (dz*mask)[M,N] . W^T[N,K]
@@ -147,7 +219,7 @@ extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, co
     g.mulscale = mask_scale;
     g.M = M; g.N = K; g.K = N;
     g.z_out = dx;
-    if (int e = launch_small(g, st)) return e;
+    if (int e = launch_small(g, st, ws, ws_bytes)) return e;
   }
   if (dw) {   // dw[K,N] (+)= x^T[K,M] . (dz*mask)[M,N]
     SmallGemm g = {};
@@ -156,14 +228,18 @@ extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, co
     g.mulscale = mask_scale;
     g.M = K; g.N = N; g.K = M;
     g.z_out = dw; g.accumulate = accumulate;
-    if (!accumulate) {
-      // plain store path: no bias/mask/affine set -> z_out = acc
-    }
-    if (int e = launch_small(g, st)) return e;
+    if (int e = launch_small(g, st, ws, ws_bytes)) return e;
   }
   if (dbias) {
-    colsum_kernel<<<uad_cdiv(N, 32), 256, 0, st>>>(dz, mask, mask_scale, dbias, M, N, accumulate);
+    int splits = uad_cdiv(M, 64);
+    if (splits > 64) splits = 64;
+    const int rps = uad_cdiv(M, splits);
+    splits = uad_cdiv(M, rps);
+    UAD_REQUIRE(ws && ws_bytes >= (size_t)splits * N * sizeof(float), "uad_dense_bwd: workspace too small");
+    colsum_kernel<<<dim3(uad_cdiv(N, 32), splits), 256, 0, st>>>(dz, mask, mask_scale, (float*)ws, M, N, rps);
     UAD_LAUNCH_CHECK("colsum");
+    colsum_final_kernel<<<uad_cdiv(N, 128), 128, 0, st>>>((const float*)ws, splits, N, dbias, accumulate);
+    UAD_LAUNCH_CHECK("colsum_final");
   }
   return 0;
 }

@@ -266,6 +266,10 @@ class ConvAutoencoderEngine:
             need = max(need, L.uad_rowreduce_workspace_bytes(B * (2 * s) ** 2, co))
             s *= 2
             cin = co
+        r2 = self.res * self.res
+        for (M, K, N) in ((B * r2, self.enc_ch[-1], self.cb), (B * r2, self.cb, self.enc_ch[-1]), (B, self.flat, self.zDim),
+                          (B, self.zDim, self.flat)):
+            need = max(need, L.uad_dense_workspace_bytes(M, K, N))
         self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         self.ws_bytes = need
 
@@ -347,33 +351,33 @@ class ConvAutoencoderEngine:
                      ptr(br.enc_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.enc_a[i], s // 2, co
             r2 = self.res * self.res
-            call('uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
-                 1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, st)
+            self._op('bneck01', 'uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
+                 1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             m = br.masks
             if self.arch == AE:
                 # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity
-                call('uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
-                     ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, st)
+                self._op('bneck02', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
+                     ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
                 zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', None
             else:
-                call('uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
-                     ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, st)
+                self._op('bneck03', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
+                     ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
                 if not is_ce:
-                    call('uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')),
+                    self._op('bneck04', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')),
                          ptr(fp.p('Bottleneck/dense_1/bias')), ptr(m['ls']), keep, None, None, ptr(br.ls), None, B,
-                         self.flat, self.zDim, ACT_NONE, 0.0, 1.0, st)
-                    call('uad_reparam_kl_fwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(br.sigma), ptr(br.zv), ptr(br.kl),
+                         self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+                    self._op('bneck05', 'uad_reparam_kl_fwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(br.sigma), ptr(br.zv), ptr(br.kl),
                          B, self.zDim, st)
                     zsrc = br.zv
                 else:
                     zsrc = br.mu      # ce branch decodes z_mu_ce without sampling (ceVAE model :37,43)
                 dd_name, dec_mask = 'Bottleneck/dense_2', m['dec']
-            call('uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
-                 keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, st)
+            self._op('bneck06', 'uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
+                 keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             dbn = f'Decoder/{_bn(self.n)}'
-            call('uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
+            self._op('bneck07', 'uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
                  None, 1.0, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(br.zr) if training else None,
-                 ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, st)
+                 ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, ws, wsb, st)
             h, s = br.ar, self.res
             for i, co in enumerate(self.dec_ch):
                 pre = f'Decoder/dec_Conv2DT_{i}'
@@ -387,9 +391,9 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        call('uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch != AE else None, ptr(self.scalars), B, st)
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch != AE else None, ptr(self.scalars), B, st)
         if self.arch == CEVAE and (branches is None or 1 in branches):
-            call('uad_loss_scalars', ptr(self.br[1].rec), None, ptr(self.scalars[3:]), B, st)
+            self._op('bneck09', 'uad_loss_scalars', ptr(self.br[1].rec), None, ptr(self.scalars[3:]), B, st)
 
     # ------------------------------------------------------------------ backward
     def backward(self, want_input_grad=False):
@@ -433,41 +437,41 @@ class ConvAutoencoderEngine:
                  ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')), B * r2, ctop,
                  ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
             sm = self.small
-            call('uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
-                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, st)
+            self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
             m = br.masks
             # keep factor is stored with the mask application: masks carry {0,1}, scale passed explicitly
             keep = self._keep
             if self.arch == AE:
-                call('uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
+                self._op('bneck11', 'uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
                      ptr(sm['dmu']), ptr(fp.g('Bottleneck/dense_1/kernel')), ptr(fp.g('Bottleneck/dense_1/bias')), B,
-                     self.zDim, self.flat, acc, st)
-                call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(m['mu']), keep,
+                     self.zDim, self.flat, acc, ws, wsb, st)
+                self._op('bneck12', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(m['mu']), keep,
                      ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B,
-                     self.flat, self.zDim, acc, st)
+                     self.flat, self.zDim, acc, ws, wsb, st)
             else:
                 zsrc = br.mu if is_ce else br.zv
-                call('uad_dense_bwd', ptr(zsrc), ptr(fp.p('Bottleneck/dense_2/kernel')), ptr(sm['dd']), ptr(m['dec']), keep,
+                self._op('bneck13', 'uad_dense_bwd', ptr(zsrc), ptr(fp.p('Bottleneck/dense_2/kernel')), ptr(sm['dd']), ptr(m['dec']), keep,
                      ptr(sm['dzv']), ptr(fp.g('Bottleneck/dense_2/kernel')), ptr(fp.g('Bottleneck/dense_2/bias')), B,
-                     self.zDim, self.flat, acc, st)
+                     self.zDim, self.flat, acc, ws, wsb, st)
                 if not is_ce:
-                    call('uad_reparam_kl_bwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(sm['dzv']), scale, ptr(sm['dmu']),
+                    self._op('bneck14', 'uad_reparam_kl_bwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(sm['dzv']), scale, ptr(sm['dmu']),
                          ptr(sm['dls']), B, self.zDim, st)
                     dmu = sm['dmu']
                 else:
                     dmu = sm['dzv']
-                call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(dmu), ptr(m['mu']), keep,
+                self._op('bneck15', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(dmu), ptr(m['mu']), keep,
                      ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B,
-                     self.flat, self.zDim, acc, st)
+                     self.flat, self.zDim, acc, ws, wsb, st)
                 if not is_ce:
-                    call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dls']), ptr(m['ls']),
+                    self._op('bneck16', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dls']), ptr(m['ls']),
                          keep, ptr(sm['dflat2']), ptr(fp.g('Bottleneck/dense_1/kernel')),
-                         ptr(fp.g('Bottleneck/dense_1/bias')), B, self.flat, self.zDim, acc, st)
-                    call('uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
+                         ptr(fp.g('Bottleneck/dense_1/bias')), B, self.flat, self.zDim, acc, ws, wsb, st)
+                    self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
             # bottleneck 1x1 conv backward -> gradient w.r.t. the last encoder activation
-            call('uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
+            self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
                  ptr(g), ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb,
-                 acc, st)
+                 acc, ws, wsb, st)
             s = self.res
             for i in reversed(range(self.n)):
                 co = self.enc_ch[i]
