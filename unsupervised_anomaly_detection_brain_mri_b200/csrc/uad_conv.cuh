@@ -65,3 +65,6 @@ int uad_tc_gather_supported(int Cin, int N, int lgMH, int lgMW);
 size_t uad_tc_gather_ws_bytes(int ksize, int Cin, int N);
 int uad_launch_gather_tc(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
                          int math_mode, void* ws, size_t ws_bytes, cudaStream_t st);
+int uad_tc_wgrad_supported(int Cg, int Co, int lgMH, int lgMW);
+size_t uad_tc_wgrad_ws_bytes(int Cg, int Co, int P);
+int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);

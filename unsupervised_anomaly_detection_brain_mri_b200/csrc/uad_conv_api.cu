@@ -55,6 +55,8 @@ extern "C" int uad_conv_tc_supported(int op, int B, int H, int W, int Cin, int C
     case UAD_OP_CONV_DGRAD:  return uad_tc_gather_supported(Cout, Cin, uad_ilog2(H / 2), uad_ilog2(W / 2));
     case UAD_OP_CONVT_FWD:   return uad_tc_gather_supported(Cin, Cout, uad_ilog2(H), uad_ilog2(W));
     case UAD_OP_CONVT_DGRAD: return uad_tc_gather_supported(Cout, Cin, uad_ilog2(H), uad_ilog2(W));
+    case UAD_OP_CONV_WGRAD:  return Cin > 1 && uad_tc_wgrad_supported(Cin, Cout, uad_ilog2(H / 2), uad_ilog2(W / 2));
+    case UAD_OP_CONVT_WGRAD: return uad_tc_wgrad_supported(Cout, Cin, uad_ilog2(H), uad_ilog2(W));
     default: return 0;
   }
 }
@@ -74,12 +76,18 @@ extern "C" size_t uad_conv_workspace_bytes(int op, int B, int H, int W, int Cin,
       if (Cin == 1) return (size_t)uad_conv_c1_wgrad_blocks(B, H) * ksize * ksize * Cout * sizeof(float) + 256;
       int splits, chunk;
       uad_wgrad_plan(ksize * ksize * Cin, Cout, B * (H / 2) * (W / 2), &splits, &chunk);
-      return (size_t)splits * wbytes + 256;
+      size_t simt = (size_t)splits * wbytes + 256;
+      size_t tc = (ksize == 5 && uad_tc_wgrad_supported(Cin, Cout, uad_ilog2(H / 2), uad_ilog2(W / 2)))
+                      ? uad_tc_wgrad_ws_bytes(Cin, Cout, B * (H / 2) * (W / 2)) : 0;
+      return simt > tc ? simt : tc;
     }
     case UAD_OP_CONVT_WGRAD: {
       int splits, chunk;
       uad_wgrad_plan(ksize * ksize * Cout, Cin, B * H * W, &splits, &chunk);
-      return (size_t)splits * wbytes + 256;
+      size_t simt = (size_t)splits * wbytes + 256;
+      size_t tc = (ksize == 5 && uad_tc_wgrad_supported(Cout, Cin, uad_ilog2(H), uad_ilog2(W)))
+                      ? uad_tc_wgrad_ws_bytes(Cout, Cin, B * H * W) : 0;
+      return simt > tc ? simt : tc;
     }
     default: return 0;
   }
@@ -133,7 +141,6 @@ extern "C" int uad_conv2d_dgrad(const float* dz, const float* w, float* dx, int 
 
 extern "C" int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout,
                                 int ksize, int accumulate, int math_mode, void* ws, size_t ws_bytes, void* stream) {
-  (void)math_mode;
   if (int e = check_geom("uad_conv2d_wgrad", B, H, W, Cin, Cout, ksize)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1) return uad_launch_conv_c1_wgrad(x, dz, dw, B, H, W, Cout, ksize, accumulate, ws, ws_bytes, st);
@@ -145,6 +152,8 @@ extern "C" int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int 
   p.Mp = ksize * ksize * Cin;
   p.P = B << (p.lgMH + p.lgMW);
   taps_full(&p.taps, ksize);
+  if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONV_WGRAD, B, H, W, Cin, Cout, ksize))
+    return uad_launch_wgrad_tc(p, dw, accumulate, ws, ws_bytes, st);
   return uad_launch_wgrad_simt(p, dw, accumulate, ws, ws_bytes, st);
 }
 
@@ -193,7 +202,6 @@ extern "C" int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int
 
 extern "C" int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout,
                                  int ksize, int accumulate, int math_mode, void* ws, size_t ws_bytes, void* stream) {
-  (void)math_mode;
   if (int e = check_geom("uad_convT2d_wgrad", B, H, W, Cin, Cout, ksize)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   WgradParams p;
@@ -204,5 +212,7 @@ extern "C" int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int
   p.Mp = ksize * ksize * Cout;
   p.P = B << (p.lgMH + p.lgMW);
   taps_full(&p.taps, ksize);
+  if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONVT_WGRAD, B, H, W, Cin, Cout, ksize))
+    return uad_launch_wgrad_tc(p, dw, accumulate, ws, ws_bytes, st);
   return uad_launch_wgrad_simt(p, dw, accumulate, ws, ws_bytes, st);
 }

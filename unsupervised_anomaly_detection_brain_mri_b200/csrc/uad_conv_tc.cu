@@ -17,6 +17,7 @@
 //   warps 4-7   epilogue: tcgen05.ld accumulator -> +bias, frozen-BN affine, activation -> smem transpose ->
 //               coalesced 512-byte row stores of z and/or a
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "uad_conv.cuh"
 
@@ -364,6 +365,260 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
   img[base + (size_t)N * kKBlk + pos] = lo;
 }
 
+// ================================================================================================ Form W (wgrad)
+// dW[(t, c), co] = sum_pix G[gather(pix, t), c] * O[pix, co]      (stride-2 gather; G fine tensor, O coarse tensor)
+//
+// GEMM roles: M = 128 rows = 4 "quads" (tap t, 32-channel block cb) x 32 channels, N = Co, K = pixels.
+//   * one CTA owns a channel block cb, a tap range (<= 4*QT taps -> QT accumulator tiles in TMEM) and a range of
+//     32-pixel blocks (split-K over pixels; partials reduced deterministically afterwards)
+//   * per pixel block (4 x 8 coarse pixels of one image) TMA loads the four stride-2 parity planes of the 6 x 10 halo
+//     of G ONCE (all taps gather from it) and the O tile
+//   * converters (warps 4-7): split the O tile into tf32 hi / lo in shared memory (B operand, MN-major SW128), and per
+//     accumulator tile gather-transpose 32 pixels x 32 channels per quad from the halo into a TMEM A slot as hi / lo
+//   * MMA issuer: 12 x tcgen05.mma.kind::tf32 (A from TMEM, B MN-major from smem) per (pixel block, tile)
+constexpr int kWPH = 4, kWPW = 8;                    // pixel block
+constexpr int kHaloRows = (kWPH + 2) * (kWPW + 2);   // 60 rows of 128 B per parity plane
+constexpr int kPlaneBytes = 8192;                    // 60 * 128 = 7680, padded to the 1024-byte swizzle alignment
+constexpr int kHaloBytes = 4 * kPlaneBytes;
+
+struct TcWgradParams {
+  int B, lgMH, lgMW;         // coarse (M-grid) dims
+  int Cg, Co, ncb;           // gathered channels, other channels, Cg/32
+  int ngroups, taps_per_group, QT;
+  int nblocks;               // number of 32-pixel blocks = B * (MH/4) * (MW/8)
+  int blocks_per_chunk;
+  int Mp;                    // 25 * Cg
+  int stages;
+  int debug;                 // developer switch (UAD_WGRAD_DEBUG): 1 = A forced to 1.0, 2 = accumulators pre-filled with 1.0
+  float* partial;            // [nchunks][Mp][Co]
+  signed char dh[UAD_MAX_TAPS], dw[UAD_MAX_TAPS];
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// MN-major, SWIZZLE_128B descriptor: K rows of 128 bytes (32 fp32 along N), 8-row groups 1024 B apart (SBO),
+// successive 32-wide N atoms `lbo_bytes` apart (LBO)
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_o,
+         const __grid_constant__ TcWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int Co = p.Co;
+  const uint32_t o_bytes = 32u * Co * 4u;                 // raw O tile [32 px][Co]; then K-major B_hi, B_lo [Co][32 px]
+  const uint32_t stage_bytes = kHaloBytes + 3 * o_bytes;
+  const int S = p.stages;
+  const uint32_t misc = smem_base + S * stage_bytes;
+  const uint32_t bar_full = misc, bar_empty = misc + 64, bar_oready = misc + 128, bar_afull = misc + 192,
+                 bar_aempty = misc + 208, bar_acc = misc + 224, tmem_slot = misc + 232;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int QT = p.QT;
+  // work assignment
+  const int grp = blockIdx.y % p.ngroups;
+  const int cb = blockIdx.y / p.ngroups;
+  const int t0 = grp * p.taps_per_group;
+  const int ntaps = min(p.taps_per_group, 25 - t0);
+  const int blk_begin = blockIdx.x * p.blocks_per_chunk;
+  const int blk_end = min(p.nblocks, blk_begin + p.blocks_per_chunk);
+  const int nkb = blk_end - blk_begin;
+  const int bw = (1 << p.lgMW) / kWPW, bh = (1 << p.lgMH) / kWPH;      // pixel blocks per image row / column
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); mbar_init(bar_oready + 8 * i, 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t aoff = QT * Co;                       // A slots after the QT accumulator tiles
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_g) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        mbar_wait(bar_empty + 8 * s, ((i / S) & 1) ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, 4u * kHaloRows * 128u + o_bytes);
+        const int blk = blk_begin + i;
+        const int bx = blk % bw, by = (blk / bw) % bh, b = blk / (bw * bh);
+        const int r0 = by * kWPH, s0 = bx * kWPW;
+        const uint32_t st_base = smem_base + s * stage_bytes;
+        for (int pl = 0; pl < 4; ++pl)                 // plane (ph, pw) = (pl >> 1, pl & 1)
+          tma_load_5d(st_base + pl * kPlaneBytes, &tmap_g, full, (pl & 1) * p.Cg + cb * 32, s0 - 1, pl >> 1, r0 - 1, b);
+        for (int a = 0; a < Co / 32; ++a)
+          tma_load_4d(st_base + kHaloBytes + a * 4096, &tmap_o, full, a * 32, s0, r0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int u = 0;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        mbar_wait(bar_full + 8 * s, (i / S) & 1);
+        mbar_wait(bar_oready + 8 * s, (i / S) & 1);           // O tile split into hi / lo (generic writes fenced to async proxy)
+        const uint32_t ohi = smem_base + s * stage_bytes + kHaloBytes + o_bytes;     // K-major [Co rows][32 px = 128 B]
+        const uint32_t olo = ohi + o_bytes;
+        for (int mt = 0; mt < QT; ++mt, ++u) {
+          const int t = u & 1;
+          mbar_wait(bar_afull + 8 * t, (u >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = tmem_base + aoff + t * 64, a_lo = a_hi + 32;
+          const uint32_t d = tmem_base + mt * Co;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                        // 8 pixels per instruction = 32 bytes along the swizzle row
+            const uint64_t dhi = make_sw128_desc(ohi + j * 32);
+            const uint64_t dlo = make_sw128_desc(olo + j * 32);
+            mma_tf32_ts(d, a_lo + j * 8, dhi, idesc, (i | j) != 0);
+            mma_tf32_ts(d, a_hi + j * 8, dlo, idesc, 1u);
+            mma_tf32_ts(d, a_hi + j * 8, dhi, idesc, 1u);
+          }
+          tc_commit(bar_aempty + 8 * t);
+        }
+        tc_commit(bar_empty + 8 * s);
+      }
+      tc_commit(bar_acc);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int tid = threadIdx.x - 128;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    int u = 0;
+    if (p.debug == 2) {
+      uint32_t ones[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ones[j] = __float_as_uint(1.0f);
+      for (int c = 0; c < QT * Co; c += 32) tmem_st32(lane_base + c, ones);
+      tmem_wait_st();
+    }
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S;
+      mbar_wait(bar_full + 8 * s, (i / S) & 1);
+      uint8_t* st = smem_gen + s * stage_bytes;
+      // ---- O tile: transpose [32 px][Co] (TMA, pixel rows) -> K-major B_hi / B_lo [Co rows][32 px] (the layout the fwd
+      //      kernel's weight images use), splitting into tf32 hi / lo on the way.  lane = channel, 4 pixels per store:
+      //      reads are one 128-byte row per warp, STS.128 quarter-warps hit 8 distinct swizzle chunks -> conflict-free.
+      {
+        const uint8_t* raw = st + kHaloBytes;
+        uint8_t* bhi = st + kHaloBytes + o_bytes;
+        uint8_t* blo = bhi + o_bytes;
+        for (int a = 0; a < Co / 32; ++a) {
+          const int n = a * 32 + lane;
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int pg = 2 * q + g2;                    // pixel group: pixels 4*pg .. 4*pg+3
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int px = 4 * pg + e;
+              const float v = *reinterpret_cast<const float*>(raw + a * 4096 + px * 128 + ((((lane >> 2) ^ (px & 7)) << 4) | ((lane & 3) << 2)));
+              h[e] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+              l[e] = v - h[e];
+            }
+            const uint32_t off = n * 128 + ((pg ^ (n & 7)) << 4);
+            *reinterpret_cast<float4*>(bhi + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(blo + off) = make_float4(l[0], l[1], l[2], l[3]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(bar_oready + 8 * s);
+      }
+      // ---- A tiles: quad q of accumulator tile mt is tap (t0 + 4*mt + q); lane = channel within the block
+      for (int mt = 0; mt < QT; ++mt, ++u) {
+        const int t = u & 1;
+        const int tap = 4 * mt + q;
+        uint32_t hi[32], lo[32];
+        if (tap < ntaps) {
+          const int dh = p.dh[t0 + tap], dw = p.dw[t0 + tap];
+          const uint8_t* plane = st + (((dh & 1) << 1) | (dw & 1)) * kPlaneBytes;
+          const int rbase = ((dh >> 1) + 1) * (kWPW + 2) + ((dw >> 1) + 1);
+#pragma unroll
+          for (int px = 0; px < 32; ++px) {
+            const int r = rbase + (px >> 3) * (kWPW + 2) + (px & 7);
+            const float v = *reinterpret_cast<const float*>(plane + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            const uint32_t h = __float_as_uint(v) & 0xffffe000u;
+            hi[px] = h;
+            lo[px] = __float_as_uint(v - __uint_as_float(h));
+            if (p.debug == 1) { hi[px] = __float_as_uint(1.0f); lo[px] = 0u; }
+          }
+        } else {
+#pragma unroll
+          for (int px = 0; px < 32; ++px) { hi[px] = 0u; lo[px] = 0u; }
+        }
+        mbar_wait(bar_aempty + 8 * t, ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a_slot = lane_base + aoff + t * 64;
+        tmem_st32(a_slot, hi);
+        tmem_st32(a_slot + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_afull + 8 * t);
+      }
+    }
+    // ---- epilogue: accumulator tiles -> partial[chunk][(tap, channel)][co]
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+    for (int mt = 0; mt < QT; ++mt) {
+      const int tap = 4 * mt + q;
+      for (int c0 = 0; c0 < Co; c0 += 32) {
+        uint32_t v[32];
+        if (nkb > 0) {
+          tmem_ld32(lane_base + mt * Co + c0, v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (tap < ntaps) {
+          const size_t row = (size_t)(t0 + tap) * p.Cg + cb * 32 + lane;
+          float* dst = p.partial + ((size_t)blockIdx.x * p.Mp + row) * Co + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -473,4 +728,86 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   gather_gemm_tc<<<grid, 256, smem, st>>>(tmap, p);
   UAD_LAUNCH_CHECK("gather_gemm_tc");
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Form W launcher
+int uad_tc_wgrad_supported(int Cg, int Co, int lgMH, int lgMW) {
+  if (Cg % 32 != 0 || Cg < 32) return 0;
+  if (!(Co == 32 || Co == 64 || Co == 128)) return 0;
+  if (lgMH < 2 || lgMW < 3) return 0;
+  return 1;
+}
+
+static void wgrad_tc_plan(int Cg, int Co, int P, int* ngroups, int* tpg, int* QT, int* nchunks, int* bpc) {
+  const int qt_max = (512 - 128) / Co;                  // accumulator tiles that fit beside the two A slots
+  int qt = qt_max > 7 ? 7 : qt_max;
+  *ngroups = uad_cdiv(25, 4 * qt);
+  *tpg = uad_cdiv(25, *ngroups);
+  *QT = uad_cdiv(*tpg, 4);
+  const int nblocks = P / 32;
+  int target = (4 * UAD_NUM_SMS) / ((*ngroups) * (Cg / 32));
+  if (target < 1) target = 1;
+  if (target > nblocks) target = nblocks;
+  *bpc = uad_cdiv(nblocks, target);
+  *nchunks = uad_cdiv(nblocks, *bpc);
+}
+
+size_t uad_tc_wgrad_ws_bytes(int Cg, int Co, int P) {
+  int ng, tpg, qt, nch, bpc;
+  wgrad_tc_plan(Cg, Co, P, &ng, &tpg, &qt, &nch, &bpc);
+  return (size_t)nch * 25 * Cg * Co * sizeof(float) + 1024;
+}
+
+int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int Cg = w.Cg, Co = w.Co;
+  UAD_REQUIRE(w.sh == 2 && w.taps.n == 25, "wgrad_tc: only the 5x5 stride-2 gather is implemented");
+  EncodeTiledFn encode = get_encode_fn();
+  UAD_REQUIRE(encode != nullptr, "wgrad_tc: cuTensorMapEncodeTiled entry point unavailable");
+  TcWgradParams p;
+  memset(&p, 0, sizeof(p));
+  int nchunks;
+  wgrad_tc_plan(Cg, Co, w.P, &p.ngroups, &p.taps_per_group, &p.QT, &nchunks, &p.blocks_per_chunk);
+  const size_t need = (size_t)nchunks * w.Mp * Co * sizeof(float);
+  UAD_REQUIRE(ws && ws_bytes >= need, "wgrad_tc: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.B = w.B; p.lgMH = w.lgMH; p.lgMW = w.lgMW; p.Cg = Cg; p.Co = Co; p.ncb = Cg / 32;
+  p.nblocks = w.P / 32; p.Mp = w.Mp;
+  p.partial = reinterpret_cast<float*>(ws);
+  for (int t = 0; t < 25; ++t) { p.dh[t] = w.taps.dh[t]; p.dw[t] = w.taps.dw[t]; }
+  const size_t stage_bytes = kHaloBytes + 3u * 32u * Co * 4u;
+  p.stages = (Co == 128) ? 2 : (Co == 64 ? 3 : 4);
+  { const char* dbg = getenv("UAD_WGRAD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+
+  const cuuint64_t e = sizeof(float);
+  const int MH = 1 << w.lgMH, MW = 1 << w.lgMW;
+  CUtensorMap tmap_g, tmap_o;
+  {   // gathered fine tensor [B, GH, GW, Cg] viewed as (2*Cg, GW/2, 2, GH/2, B); box = (32 ch, 10, 1, 6, 1)
+    cuuint64_t dims[5] = {2ull * Cg, (cuuint64_t)w.GW / 2, 2, (cuuint64_t)w.GH / 2, (cuuint64_t)w.B};
+    cuuint64_t strides[4] = {2ull * Cg * e, (cuuint64_t)w.GW * Cg * e, 2ull * w.GW * Cg * e, (cuuint64_t)w.GH * w.GW * Cg * e};
+    cuuint32_t box[5] = {32, kWPW + 2, 1, kWPH + 2, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = encode(&tmap_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(w.g), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAD_REQUIRE(cr == CUDA_SUCCESS, "wgrad_tc: cuTensorMapEncodeTiled(g) failed (%d)", (int)cr);
+  }
+  {   // coarse tensor [B, MH, MW, Co]; box = (32 ch, 8, 4, 1)
+    cuuint64_t dims[4] = {(cuuint64_t)Co, (cuuint64_t)MW, (cuuint64_t)MH, (cuuint64_t)w.B};
+    cuuint64_t strides[3] = {(cuuint64_t)Co * e, (cuuint64_t)MW * Co * e, (cuuint64_t)MH * MW * Co * e};
+    cuuint32_t box[4] = {32, kWPW, kWPH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(w.o), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAD_REQUIRE(cr == CUDA_SUCCESS, "wgrad_tc: cuTensorMapEncodeTiled(o) failed (%d)", (int)cr);
+  }
+  const size_t smem = 1024 + p.stages * stage_bytes + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UAD_CUDA(cudaFuncSetAttribute(wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(nchunks, p.ngroups * p.ncb);
+  wgrad_tc<<<grid, 256, smem, st>>>(tmap_g, tmap_o, p);
+  UAD_LAUNCH_CHECK("wgrad_tc");
+  return uad_launch_splitk_reduce(p.partial, nchunks, (size_t)w.Mp * Co, out, accumulate, st);
 }
