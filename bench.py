@@ -103,6 +103,18 @@ def step_flops(B):
     return sum(f for k, (f, _) in conv_work(B).items())
 
 
+def usable_cores():
+    """Host cores this process may actually use: scheduler affinity capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_reference_step_rate(batch, steps, warmup, threads):
     """Times the oracle port of the reference train step (fwd + loss + bwd + TF-Adam) on the host cores."""
     from oracle import tf_graph_cpu as O
@@ -128,7 +140,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     batch = 16      # bounded sample of the workload per step: 16 of the 64 slices of a mini-batch
     rate, ms = cpu_reference_step_rate(batch, args.steps, max(1, min(args.warmup, 2)), cores)
     line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': args.steps,
@@ -286,7 +298,7 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = usable_cores()
         rate, ms = cpu_reference_step_rate(16, 3, 1, cores)
         cpu = {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
                'sample': 'oracle torch-CPU restatement (TF 1.15 not installable); 3 timed 16-slice train steps of the same VAE-256 workload'}
@@ -309,3 +321,5 @@ def main():
 
 if __name__ == '__main__':
     main()
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()

@@ -1,0 +1,51 @@
+"""torchrun worker: N-rank data-parallel step == 1-rank step on the concatenated batch (SURVEY 4 'distributed tests').
+Each rank runs the engine on its shard with the NCCL all-reduce hook; rank 0 then runs the whole batch alone."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unsupervised_anomaly_detection_brain_mri_b200 import dist as udist  # noqa: E402
+from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import make_volume  # noqa: E402
+from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine, glorot_init  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    rank, world = udist.init_from_env('nccl')
+    arch, S, Bg, lr = 'variational_autoencoder', 64, 8, 1e-3
+    x = make_volume(S, Bg, seed=5, lesions=False)[0][..., None]
+    rng = np.random.default_rng(0)
+    eps = rng.standard_normal((Bg, 128)).astype(np.float32)
+    masks = {'mu': (rng.uniform(size=(Bg, 128)) >= 0.2).astype(np.float32), 'ls': (rng.uniform(size=(Bg, 128)) >= 0.2).astype(np.float32),
+             'dec': (rng.uniform(size=(Bg, 512 if S == 32 else 1024)) >= 0.2).astype(np.float32)}
+    eng = ConvAutoencoderEngine(arch, S, batch=Bg // world, device=f'cuda:{local}', seed=3)
+    masks['dec'] = masks['dec'][:, :eng.flat]
+    udist.broadcast_(eng.fp.params)
+    eng.set_inputs(udist.shard(x))
+    eng.set_noise(udist.shard(eps), {k: udist.shard(v) for k, v in masks.items()})
+    eng.train_step(lr, dropout_rate=0.2, dropout=True, parity_noise=True, allreduce=udist.allreduce_sum_, world=world)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref = ConvAutoencoderEngine(arch, S, batch=Bg, device=f'cuda:{local}', seed=3)
+        ref.set_inputs(x)
+        ref.set_noise(eps, masks)
+        ref.train_step(lr, dropout_rate=0.2, dropout=True, parity_noise=True)
+        torch.cuda.synchronize()
+        g_dp = eng.fp.grads.cpu().numpy() / world
+        g_1 = ref.fp.grads.cpu().numpy()
+        gerr = float(np.abs(g_dp - g_1).max() / np.abs(g_1).max())
+        w_dp, w_1 = eng.fp.params.cpu().numpy(), ref.fp.params.cpu().numpy()
+        werr = float(np.abs(w_dp - w_1).max())
+        frac = float((np.abs(w_dp - w_1) > 1e-3 * lr).mean())
+        print(f'DP_EQUIV world={world} grad_rel_err={gerr:.3e} max_weight_diff={werr:.3e} frac_diff={frac:.3e}', flush=True)
+        assert gerr < 1e-4 and werr <= 2.001 * lr and frac < 5e-3
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
