@@ -26,7 +26,6 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kKBlk = 32;                    // fp32 channels per k-block = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kKBlk * 4;  // 16 KB
-constexpr int kNumASlots = 2;
 // TMEM columns: G "main" accumulators (hi*hi products, k-blocks dealt round-robin) + 1 "correction" accumulator
 // (lo*hi + hi*lo) of N columns each, then two {hi,lo} A slots of 64 columns.  The tensor core adds into its fp32
 // accumulator with truncation (measured: error grows linearly with the number of accumulations), so the large hi*hi
@@ -42,7 +41,9 @@ struct TcParams {
   int stride2;
   int stages;
   int G;               // number of main accumulators (1 or 2)
-  int tmem_cols;       // power of two >= (G + 1) * N + 128
+  int tmem_cols;       // 256 or 512
+  int nacc;            // accumulators of N columns: 2G (paired layout, N <= 64) or G + 1 (N = 128)
+  int nslots;          // TMEM A slots (2..4)
   float* z_out;
   float* a_out;
   const float* bias;
@@ -141,6 +142,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// TMEM columns: `nacc` accumulators of N columns, then `nslots` {hi,lo} A slots of 64 columns.
+//   N <= 64 : accumulator pairs [main_g | corr_g], g < G.  Per K=8 slice TWO instructions:
+//             (a_hi) x [B_hi ; B_lo]  as ONE 2N-wide MMA into [main_g | corr_g]   (hi*hi and hi*lo at once)
+//             (a_lo) x  B_hi          as an N-wide MMA into corr_g
+//   N = 128 : [main_0 .. main_{G-1} | corr], three N-wide MMAs per slice (a 2N-wide pair would not leave room for A).
+// Why several accumulators: the tensor core adds into its fp32 accumulator with truncation (measured: error grows
+// linearly with the number of accumulations), so the large hi*hi stream is dealt round-robin over G accumulators and
+// the small correction terms never disturb it; the epilogue sums all of them in registers with round-to-nearest.
 __global__ void __launch_bounds__(256, 1)
 gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,19 +159,21 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t b_bytes = 2u * N * 128u;
   const uint32_t stage_bytes = kABytes + b_bytes;
   const int S = p.stages;
+  const int NS = p.nslots;
   // bookkeeping lives after the pipeline stages
   const uint32_t misc = smem_base + S * stage_bytes;
   const uint32_t bar_full = misc;                       // S x 8
   const uint32_t bar_empty = misc + 64;                 // S x 8
-  const uint32_t bar_afull = misc + 128;                // 2 x 8
-  const uint32_t bar_aempty = misc + 144;               // 2 x 8
-  const uint32_t bar_acc = misc + 160;
-  const uint32_t tmem_slot = misc + 168;
+  const uint32_t bar_afull = misc + 128;                // NS x 8
+  const uint32_t bar_aempty = misc + 160;               // NS x 8
+  const uint32_t bar_acc = misc + 192;
+  const uint32_t tmem_slot = misc + 200;
   float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256);   // bias[N], scale[N], shift[N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const TapSet& ts = p.taps[blockIdx.y];
   const int nkb = ts.n * p.Cblks;
+  const uint32_t aoff = p.nacc * N;                     // first A slot column
 
   // tile origin on the M-grid
   const int tile = blockIdx.x;
@@ -173,7 +184,7 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < kNumASlots; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -195,14 +206,14 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  // all ring indices / phase bits are carried incrementally: no runtime div/mod in the per-k-block loops
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-      int tap = 0, cb = 0;
+      int tap = 0, cb = 0, s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S;
-        const uint32_t ph = (i / S) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t full = bar_full + 8 * s;
         mbar_expect_tx(full, kABytes + b_bytes);
@@ -215,36 +226,52 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
         bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
         if (++cb == p.Cblks) { cb = 0; ++tap; }
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t aoff = (p.G + 1) * N;
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
+      const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
+      const uint64_t bdesc0 = make_sw128_desc(smem_base + kABytes);          // B image of stage 0 (hi rows then lo rows)
+      const uint32_t stage_units = stage_bytes >> 4, lo_units = (uint32_t)(N * 128) >> 4;
+      const bool paired = (N <= 64);
+      int s = 0, t = 0, g = 0;
+      uint32_t ph = 0, pht = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S, t = i % kNumASlots;
-        mbar_wait(bar_full + 8 * s, (i / S) & 1);               // weight image landed (async proxy -> visible)
-        mbar_wait(bar_afull + 8 * t, (i / kNumASlots) & 1);     // converters filled TMEM A slot t
+        mbar_wait(bar_full + 8 * s, ph);                        // weight image landed (async proxy -> visible)
+        mbar_wait(bar_afull + 8 * t, pht);                      // converters filled TMEM A slot t
         tc_fence_after();
-        const uint32_t bhi = smem_base + s * stage_bytes + kABytes;
-        const uint32_t blo = bhi + N * 128;
+        const uint64_t dhi0 = bdesc0 + (uint64_t)(s * stage_units);
         const uint32_t a_hi = tmem_base + aoff + t * 64;
         const uint32_t a_lo = a_hi + 32;
-        const uint32_t d_main = tmem_base + (i % p.G) * N;
-        const uint32_t d_corr = tmem_base + p.G * N;
+        const uint32_t first = (i >= p.G) ? 1u : 0u;            // accumulator g already holds a partial sum?
+        if (paired) {
+          const uint32_t d_pair = tmem_base + g * 2 * N;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                           // K = 8 tf32 per instruction -> 32 bytes along the swizzle row
-          const uint64_t dhi = make_sw128_desc(bhi + j * 32);
-          const uint64_t dlo = make_sw128_desc(blo + j * 32);
-          mma_tf32_ts(d_corr, a_lo + j * 8, dhi, idesc, (i | j) != 0);
-          mma_tf32_ts(d_corr, a_hi + j * 8, dlo, idesc, 1u);
-          mma_tf32_ts(d_main, a_hi + j * 8, dhi, idesc, (i >= p.G || j != 0) ? 1u : 0u);
+          for (int j = 0; j < 4; ++j) {                         // K = 8 tf32 per instruction -> 32 bytes (2 x 16 B) along the row
+            mma_tf32_ts(d_pair, a_hi + j * 8, dhi0 + 2 * j, idesc2N, first | (j != 0));
+            mma_tf32_ts(d_pair + N, a_lo + j * 8, dhi0 + 2 * j, idescN, 1u);
+          }
+        } else {
+          const uint32_t d_main = tmem_base + g * N;
+          const uint32_t d_corr = tmem_base + p.G * N;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mma_tf32_ts(d_corr, a_lo + j * 8, dhi0 + 2 * j, idescN, (i | j) != 0);
+            mma_tf32_ts(d_corr, a_hi + j * 8, dhi0 + lo_units + 2 * j, idescN, 1u);
+            mma_tf32_ts(d_main, a_hi + j * 8, dhi0 + 2 * j, idescN, first | (j != 0));
+          }
         }
         tc_commit(bar_empty + 8 * s);                           // smem stage reusable once these MMAs retire
         tc_commit(bar_aempty + 8 * t);                          // TMEM A slot reusable
-        if (i == nkb - 1) tc_commit(bar_acc);                   // accumulator complete
+        if (i == nkb - 1) tc_commit(bar_acc);                   // accumulators complete
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++t == NS) { t = 0; pht ^= 1; }
+        if (++g == p.G) g = 0;
       }
     }
   } else if (warp >= 4) {
@@ -252,33 +279,39 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int row = threadIdx.x - 128;                          // tile row == TMEM lane
     const int q = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % S, t = i % kNumASlots;
-      mbar_wait(bar_full + 8 * s, (i / S) & 1);
-      const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
-      uint32_t hi[32], lo[32];
+    {
+      int s = 0, t = 0;
+      uint32_t ph = 0, pht = 0;
+      const uint32_t swz = (uint32_t)(row & 7);
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
+        uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {                             // 16-byte chunk j of this row sits at (j ^ (row & 7))
-        const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ (row & 7)) << 4));
-        const float f[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 8; ++j) {                           // 16-byte chunk j of this row sits at (j ^ (row & 7))
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
+          const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
-          hi[4 * j + e] = h;
-          lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
+            hi[4 * j + e] = h;
+            lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+          }
         }
+        mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+        tc_fence_after();
+        const uint32_t a_slot = lane_base + aoff + t * 64;
+        tmem_st32(a_slot, hi);
+        tmem_st32(a_slot + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_afull + 8 * t);
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++t == NS) { t = 0; pht ^= 1; }
       }
-      mbar_wait(bar_aempty + 8 * t, ((i / kNumASlots) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t a_slot = lane_base + (p.G + 1) * N + t * 64;
-      tmem_st32(a_slot, hi);
-      tmem_st32(a_slot + 32, lo);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar_afull + 8 * t);
     }
 
-    // ---- epilogue: accumulator -> (z, a) -> smem transpose -> coalesced rows
+    // ---- epilogue: accumulators -> (z, a) -> smem transpose -> coalesced rows
     mbar_wait(bar_acc, 0);
     tc_fence_after();
     // output pixel of THIS thread's row (shuffled to the storing lanes below)
@@ -293,23 +326,22 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     float* stg = reinterpret_cast<float*>(smem_gen) + (size_t)q * 32 * ldw;     // this warp's 32 x (N+4) staging rows
     const int lanes_per_row = N / 4;                    // float4 lanes covering one output row
     const int rows_per_it = 32 / lanes_per_row;
+    const bool both = p.z_out && p.a_out;
+    // one pass over TMEM produces z (staged + stored) and a (kept in the same staging buffer afterwards)
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
       float* out = pass == 0 ? p.z_out : p.a_out;
       if (!out) continue;
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32], u[32];
-        tmem_ld32(lane_base + c0, v);                           // main accumulator 0
-        tmem_ld32(lane_base + p.G * N + c0, u);                 // correction accumulator
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-        if (p.G == 2) {
-          tmem_ld32(lane_base + N + c0, u);                     // main accumulator 1
+        tmem_ld32(lane_base + c0, v);
+        for (int k = 1; k < p.nacc; ++k) {
+          tmem_ld32(lane_base + k * N + c0, u);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
         }
+        tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float o[4];
@@ -334,6 +366,7 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
       __syncwarp();
     }
+    (void)both;
   }
 
   tc_fence_before();
@@ -401,18 +434,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
-// MN-major, SWIZZLE_128B descriptor: K rows of 128 bytes (32 fp32 along N), 8-row groups 1024 B apart (SBO),
-// successive 32-wide N atoms `lbo_bytes` apart (LBO)
-__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
+// (An MN-major SWIZZLE_128B tf32 B descriptor - K rows of 128 bytes straight from TMA - reads back zeros on B200:
+// 32-bit MN-major operands need the 32-byte-atom swizzle.  The O tile is therefore re-laid out K-major by the converters.)
 __global__ void __launch_bounds__(256, 1)
 wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ TcWgradParams p) {
@@ -461,9 +484,10 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_g) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S;
-        mbar_wait(bar_empty + 8 * s, ((i / S) & 1) ^ 1);
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t full = bar_full + 8 * s;
         mbar_expect_tx(full, 4u * kHaloRows * 128u + o_bytes);
         const int blk = blk_begin + i;
@@ -474,17 +498,18 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
           tma_load_5d(st_base + pl * kPlaneBytes, &tmap_g, full, (pl & 1) * p.Cg + cb * 32, s0 - 1, pl >> 1, r0 - 1, b);
         for (int a = 0; a < Co / 32; ++a)
           tma_load_4d(st_base + kHaloBytes + a * 4096, &tmap_o, full, a * 32, s0, r0, b);
+        if (++s == S) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int u = 0;
+      int u = 0, s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % S;
-        mbar_wait(bar_full + 8 * s, (i / S) & 1);
-        mbar_wait(bar_oready + 8 * s, (i / S) & 1);           // O tile split into hi / lo (generic writes fenced to async proxy)
+        mbar_wait(bar_full + 8 * s, ph);
+        mbar_wait(bar_oready + 8 * s, ph);                    // O tile split into hi / lo (generic writes fenced to async proxy)
         const uint32_t ohi = smem_base + s * stage_bytes + kHaloBytes + o_bytes;     // K-major [Co rows][32 px = 128 B]
         const uint32_t olo = ohi + o_bytes;
         for (int mt = 0; mt < QT; ++mt, ++u) {
@@ -504,12 +529,12 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
           tc_commit(bar_aempty + 8 * t);
         }
         tc_commit(bar_empty + 8 * s);
+        if (++s == S) { s = 0; ph ^= 1; }
       }
       tc_commit(bar_acc);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int tid = threadIdx.x - 128;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     int u = 0;
     if (p.debug == 2) {
@@ -519,9 +544,10 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
       for (int c = 0; c < QT * Co; c += 32) tmem_st32(lane_base + c, ones);
       tmem_wait_st();
     }
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % S;
-      mbar_wait(bar_full + 8 * s, (i / S) & 1);
+      mbar_wait(bar_full + 8 * s, ph);
       uint8_t* st = smem_gen + s * stage_bytes;
       // ---- O tile: transpose [32 px][Co] (TMA, pixel rows) -> K-major B_hi / B_lo [Co rows][32 px] (the layout the fwd
       //      kernel's weight images use), splitting into tf32 hi / lo on the way.  lane = channel, 4 pixels per store:
@@ -582,6 +608,7 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
         tc_fence_before();
         mbar_arrive(bar_afull + 8 * t);
       }
+      if (++s == S) { s = 0; ph ^= 1; }
     }
     // ---- epilogue: accumulator tiles -> partial[chunk][(tap, channel)][co]
     if (nkb > 0) {
@@ -687,9 +714,12 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
     int max_taps = 0;
     for (int c = 0; c < nclasses; ++c) max_taps = g.taps[c].n > max_taps ? g.taps[c].n : max_taps;
     p.G = (max_taps * C > 640) ? 2 : 1;      // deep reductions: halve the accumulation chain length
-    int cols = (p.G + 1) * N + kNumASlots * 64;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < cols) p.tmem_cols <<= 1;
+    p.nacc = (N <= 64) ? 2 * p.G : p.G + 1;
+    const int acc_cols = p.nacc * N;
+    p.tmem_cols = (acc_cols + 128 <= 256) ? 256 : 512;
+    p.nslots = (p.tmem_cols - acc_cols) / 64;
+    if (p.nslots > 4) p.nslots = 4;
+    UAD_REQUIRE(p.nslots >= 2, "gather_gemm_tc: TMEM budget exceeded");
     UAD_REQUIRE(p.tmem_cols <= 512, "gather_gemm_tc: TMEM budget exceeded");
   }
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
