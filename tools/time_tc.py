@@ -1,0 +1,54 @@
+"""Developer aid: event-times single TC conv ops (VAE-256 layer shapes) under the UAD_TC_DEBUG / UAD_WGRAD_DEBUG switches."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, '.')
+from unsupervised_anomaly_detection_brain_mri_b200 import abi
+from unsupervised_anomaly_detection_brain_mri_b200.abi import call
+DEV = 'cuda:0'
+L = abi.lib()
+st = lambda: torch.cuda.current_stream().cuda_stream
+
+def timeit(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+B = 64
+cases = {
+  'T4.fwd  (FormT N=32 C=32 128^2->256^2)': ('convT_fwd', 128, 32, 32),
+  'T4.dgrad(FormF N=32 C=32)': ('convT_dgrad', 128, 32, 32),
+  'T4.wgrad': ('convT_wgrad', 128, 32, 32),
+  'enc1.fwd (FormF N=64 C=32 128^2->64^2)': ('conv_fwd', 128, 32, 64),
+  'enc2.fwd (FormF N=128 C=64)': ('conv_fwd', 64, 64, 128),
+  'enc1.wgrad': ('conv_wgrad', 128, 32, 64),
+}
+for name, (op, H, Cin, Cout) in cases.items():
+    opid = {'conv_fwd': 0, 'conv_wgrad': 2, 'convT_fwd': 3, 'convT_dgrad': 4, 'convT_wgrad': 5}[op]
+    wsb = L.uad_conv_workspace_bytes(opid, B, H, H, Cin, Cout, 5, 1)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    if op.startswith('convT'):
+        x = torch.randn(B, H, H, Cin, device=DEV); y = torch.randn(B, 2 * H, 2 * H, Cout, device=DEV); w = torch.randn(5, 5, Cout, Cin, device=DEV) * 0.05
+    else:
+        x = torch.randn(B, H, H, Cin, device=DEV); y = torch.randn(B, H // 2, H // 2, Cout, device=DEV); w = torch.randn(5, 5, Cin, Cout, device=DEV) * 0.05
+    z = torch.empty_like(y)
+    dw = torch.empty_like(w); dx = torch.empty_like(x)
+    def run():
+        if op == 'conv_fwd': call('uad_conv2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, z.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
+        elif op == 'convT_fwd': call('uad_convT2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, z.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
+        elif op == 'convT_dgrad': call('uad_convT2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, 1, ws.data_ptr(), wsb, st())
+        elif op == 'conv_wgrad': call('uad_conv2d_wgrad', x.data_ptr(), y.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, 5, 0, 1, ws.data_ptr(), wsb, st())
+        elif op == 'convT_wgrad': call('uad_convT2d_wgrad', x.data_ptr(), y.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, 5, 0, 1, ws.data_ptr(), wsb, st())
+    res = []
+    var = 'UAD_WGRAD_DEBUG' if 'wgrad' in op else 'UAD_TC_DEBUG'
+    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0', '1', '2', '3']
+    for dbg in modes:
+        os.environ[var] = dbg
+        res.append(f'{dbg}:{timeit(run):.3f}ms')
+    os.environ[var] = '0'
+    print(f'{name:45s} ' + '  '.join(res), flush=True)
+print('gather modes: 0 normal, 1 no-convert, 2 no-MMA, 3 neither | wgrad modes: 0 normal, 2 no-convert, 4 no-MMA, 6 neither')

@@ -44,6 +44,7 @@ struct TcParams {
   int tmem_cols;       // 256 or 512
   int nacc;            // accumulators of N columns: 2G (paired layout, N <= 64) or G + 1 (N = 128)
   int nslots;          // TMEM A slots (2..4)
+  int debug;           // developer timing switches (UAD_TC_DEBUG): 1 = converters skip their work, 2 = MMA issuer skips the MMAs
   float* z_out;
   float* a_out;
   const float* bias;
@@ -91,6 +92,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// warp-converged single-lane election (elect.sync): keeps the surrounding values provably warp-uniform so the compiler
+// builds MMA descriptors in uniform registers instead of R2UR-ing them per instruction inside a divergent branch
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -231,8 +239,8 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    {
+      // the whole warp walks the loop (converged); one elected lane issues.  instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
       const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
@@ -249,7 +257,9 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         const uint32_t a_hi = tmem_base + aoff + t * 64;
         const uint32_t a_lo = a_hi + 32;
         const uint32_t first = (i >= p.G) ? 1u : 0u;            // accumulator g already holds a partial sum?
-        if (paired) {
+        if (elect_one()) {
+        if (p.debug & 2) {
+        } else if (paired) {
           const uint32_t d_pair = tmem_base + g * 2 * N;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                         // K = 8 tf32 per instruction -> 32 bytes (2 x 16 B) along the row
@@ -269,6 +279,8 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         tc_commit(bar_empty + 8 * s);                           // smem stage reusable once these MMAs retire
         tc_commit(bar_aempty + 8 * t);                          // TMEM A slot reusable
         if (i == nkb - 1) tc_commit(bar_acc);                   // accumulators complete
+        }
+        __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
         if (++t == NS) { t = 0; pht ^= 1; }
         if (++g == p.G) g = 0;
@@ -287,6 +299,13 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         mbar_wait(bar_full + 8 * s, ph);
         const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
         uint32_t hi[32], lo[32];
+        if (p.debug & 1) {
+          mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+          mbar_arrive(bar_afull + 8 * t);
+          if (++s == S) { s = 0; ph ^= 1; }
+          if (++t == NS) { t = 0; pht ^= 1; }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                           // 16-byte chunk j of this row sits at (j ^ (row & 7))
           const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
@@ -410,8 +429,11 @@ __global__ void weight_image_kernel(const float* __restrict__ w, float* __restri
 //     accumulator tile gather-transpose 32 pixels x 32 channels per quad from the halo into a TMEM A slot as hi / lo
 //   * MMA issuer: 12 x tcgen05.mma.kind::tf32 (A from TMEM, B MN-major from smem) per (pixel block, tile)
 constexpr int kWPH = 4, kWPW = 8;                    // pixel block
-constexpr int kHaloRows = (kWPH + 2) * (kWPW + 2);   // 60 rows of 128 B per parity plane
-constexpr int kPlaneBytes = 8192;                    // 60 * 128 = 7680, padded to the 1024-byte swizzle alignment
+constexpr int kHaloPitch = 16;                       // halo rows are loaded 16 pixels wide (10 needed): with a pitch that is a
+                                                     // multiple of 8 the 128B-swizzle phase of a gathered pixel depends only on
+                                                     // its column -> 8 precomputed bases + immediate offsets per tile
+constexpr int kHaloRows = (kWPH + 2) * kHaloPitch;   // 96 rows of 128 B per parity plane
+constexpr int kPlaneBytes = kHaloRows * 128;         // 12 KB (multiple of 1024)
 constexpr int kHaloBytes = 4 * kPlaneBytes;
 
 struct TcWgradParams {
@@ -422,7 +444,7 @@ struct TcWgradParams {
   int blocks_per_chunk;
   int Mp;                    // 25 * Cg
   int stages;
-  int debug;                 // developer switch (UAD_WGRAD_DEBUG): 1 = A forced to 1.0, 2 = accumulators pre-filled with 1.0
+  int debug;                 // developer switch (UAD_WGRAD_DEBUG): 1 = A forced to 1.0
   float* partial;            // [nchunks][Mp][Co]
   signed char dh[UAD_MAX_TAPS], dw[UAD_MAX_TAPS];
 };
@@ -436,7 +458,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 // (An MN-major SWIZZLE_128B tf32 B descriptor - K rows of 128 bytes straight from TMA - reads back zeros on B200:
 // 32-bit MN-major operands need the 32-byte-atom swizzle.  The O tile is therefore re-laid out K-major by the converters.)
-__global__ void __launch_bounds__(256, 1)
+//
+// 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc, 3 idle, 4-7 = converter group 0, 8-11 = converter group 1.
+// Accumulator tiles are converted alternately by the two groups (tile u -> group u & 1), each group owning two TMEM A
+// slots, so one group's smem->TMEM latency chain overlaps the other's and the MMAs of the tile in between.
+__global__ void __launch_bounds__(384, 1)
 wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_o,
          const __grid_constant__ TcWgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -448,7 +474,7 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
   const int S = p.stages;
   const uint32_t misc = smem_base + S * stage_bytes;
   const uint32_t bar_full = misc, bar_empty = misc + 64, bar_oready = misc + 128, bar_afull = misc + 192,
-                 bar_aempty = misc + 208, bar_acc = misc + 224, tmem_slot = misc + 232;
+                 bar_aempty = misc + 224, bar_acc = misc + 256, tmem_slot = misc + 264;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int QT = p.QT;
@@ -464,7 +490,7 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); mbar_init(bar_oready + 8 * i, 128); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -478,7 +504,7 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  const uint32_t aoff = QT * Co;                       // A slots after the QT accumulator tiles
+  const uint32_t aoff = QT * Co;                       // four A slots after the QT accumulator tiles
 
   if (warp == 0) {
     if (lane == 0) {
@@ -489,7 +515,7 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
         const uint32_t full = bar_full + 8 * s;
-        mbar_expect_tx(full, 4u * kHaloRows * 128u + o_bytes);
+        mbar_expect_tx(full, (uint32_t)kHaloBytes + o_bytes);
         const int blk = blk_begin + i;
         const int bx = blk % bw, by = (blk / bw) % bh, b = blk / (bw * bh);
         const int r0 = by * kWPH, s0 = bx * kWPW;
@@ -502,57 +528,56 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    {
+      // whole warp converged, one elected lane issues.  D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int u = 0, s = 0;
-      uint32_t ph = 0;
+      const uint64_t bdesc0 = make_sw128_desc(smem_base + kHaloBytes + o_bytes);
+      const uint32_t stage_units = stage_bytes >> 4, lo_units = o_bytes >> 4;
+      int s = 0;
+      uint32_t ph = 0, u = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(bar_full + 8 * s, ph);
-        mbar_wait(bar_oready + 8 * s, ph);                    // O tile split into hi / lo (generic writes fenced to async proxy)
-        const uint32_t ohi = smem_base + s * stage_bytes + kHaloBytes + o_bytes;     // K-major [Co rows][32 px = 128 B]
-        const uint32_t olo = ohi + o_bytes;
+        mbar_wait(bar_oready + 8 * s, ph);                    // O tile transposed + split (generic writes fenced to async proxy)
+        const uint64_t dhi0 = bdesc0 + (uint64_t)(s * stage_units);
         for (int mt = 0; mt < QT; ++mt, ++u) {
-          const int t = u & 1;
-          mbar_wait(bar_afull + 8 * t, (u >> 1) & 1);
+          const uint32_t slot = ((u & 1) << 1) | ((u >> 1) & 1);   // group (u & 1), its slot ((u >> 1) & 1)
+          mbar_wait(bar_afull + 8 * slot, (u >> 2) & 1);
           tc_fence_after();
-          const uint32_t a_hi = tmem_base + aoff + t * 64, a_lo = a_hi + 32;
+          const uint32_t a_hi = tmem_base + aoff + slot * 64, a_lo = a_hi + 32;
           const uint32_t d = tmem_base + mt * Co;
+          if (elect_one()) {
+          if (!(p.debug & 4))
 #pragma unroll
           for (int j = 0; j < 4; ++j) {                        // 8 pixels per instruction = 32 bytes along the swizzle row
-            const uint64_t dhi = make_sw128_desc(ohi + j * 32);
-            const uint64_t dlo = make_sw128_desc(olo + j * 32);
-            mma_tf32_ts(d, a_lo + j * 8, dhi, idesc, (i | j) != 0);
-            mma_tf32_ts(d, a_hi + j * 8, dlo, idesc, 1u);
-            mma_tf32_ts(d, a_hi + j * 8, dhi, idesc, 1u);
+            mma_tf32_ts(d, a_lo + j * 8, dhi0 + 2 * j, idesc, (i | j) != 0);
+            mma_tf32_ts(d, a_hi + j * 8, dhi0 + lo_units + 2 * j, idesc, 1u);
+            mma_tf32_ts(d, a_hi + j * 8, dhi0 + 2 * j, idesc, 1u);
           }
-          tc_commit(bar_aempty + 8 * t);
+          tc_commit(bar_aempty + 8 * slot);
+          }
+          __syncwarp();
         }
-        tc_commit(bar_empty + 8 * s);
+        if (elect_one()) tc_commit(bar_empty + 8 * s);
+        __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
       }
-      tc_commit(bar_acc);
+      if (elect_one()) tc_commit(bar_acc);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    const int cg = (warp - 4) >> 2;                            // converter group 0 / 1
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    int u = 0;
-    if (p.debug == 2) {
-      uint32_t ones[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) ones[j] = __float_as_uint(1.0f);
-      for (int c = 0; c < QT * Co; c += 32) tmem_st32(lane_base + c, ones);
-      tmem_wait_st();
-    }
+    const uint32_t chunk_swz = (uint32_t)(lane >> 2), word = (uint32_t)(lane & 3) << 2;
     int s = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, u = 0;
     for (int i = 0; i < nkb; ++i) {
       mbar_wait(bar_full + 8 * s, ph);
       uint8_t* st = smem_gen + s * stage_bytes;
-      // ---- O tile: transpose [32 px][Co] (TMA, pixel rows) -> K-major B_hi / B_lo [Co rows][32 px] (the layout the fwd
-      //      kernel's weight images use), splitting into tf32 hi / lo on the way.  lane = channel, 4 pixels per store:
-      //      reads are one 128-byte row per warp, STS.128 quarter-warps hit 8 distinct swizzle chunks -> conflict-free.
-      {
+      // ---- O tile (group 0): transpose [32 px][Co] (TMA, pixel rows) -> K-major B_hi / B_lo [Co rows][32 px] (the layout
+      //      the fwd kernel's weight images use), splitting into tf32 hi / lo on the way.  lane = channel, 4 pixels per
+      //      store: reads are one 128-byte row per warp, STS.128 quarter-warps hit 8 distinct swizzle chunks.
+      if (cg == 0) {
         const uint8_t* raw = st + kHaloBytes;
         uint8_t* bhi = st + kHaloBytes + o_bytes;
         uint8_t* blo = bhi + o_bytes;
@@ -565,7 +590,7 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int px = 4 * pg + e;
-              const float v = *reinterpret_cast<const float*>(raw + a * 4096 + px * 128 + ((((lane >> 2) ^ (px & 7)) << 4) | ((lane & 3) << 2)));
+              const float v = *reinterpret_cast<const float*>(raw + a * 4096 + px * 128 + (((chunk_swz ^ (px & 7)) << 4) | word));
               h[e] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
               l[e] = v - h[e];
             }
@@ -579,17 +604,28 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
       }
       // ---- A tiles: quad q of accumulator tile mt is tap (t0 + 4*mt + q); lane = channel within the block
       for (int mt = 0; mt < QT; ++mt, ++u) {
-        const int t = u & 1;
+        if ((int)(u & 1) != cg) continue;
+        const uint32_t slot = ((u & 1) << 1) | ((u >> 1) & 1);
         const int tap = 4 * mt + q;
         uint32_t hi[32], lo[32];
+        if (p.debug & 2) {
+          mbar_wait(bar_aempty + 8 * slot, ((u >> 2) & 1) ^ 1);
+          mbar_arrive(bar_afull + 8 * slot);
+          continue;
+        }
         if (tap < ntaps) {
           const int dh = p.dh[t0 + tap], dw = p.dw[t0 + tap];
           const uint8_t* plane = st + (((dh & 1) << 1) | (dw & 1)) * kPlaneBytes;
-          const int rbase = ((dh >> 1) + 1) * (kWPW + 2) + ((dw >> 1) + 1);
+          const int rbase = ((dh >> 1) + 1) * kHaloPitch + ((dw >> 1) + 1);
+          const uint8_t* colp[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {                         // swizzle phase depends only on the column (pitch % 8 == 0)
+            const int r = rbase + c;
+            colp[c] = plane + r * 128 + (((chunk_swz ^ (uint32_t)(r & 7)) << 4) | word);
+          }
 #pragma unroll
           for (int px = 0; px < 32; ++px) {
-            const int r = rbase + (px >> 3) * (kWPW + 2) + (px & 7);
-            const float v = *reinterpret_cast<const float*>(plane + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            const float v = *reinterpret_cast<const float*>(colp[px & 7] + (px >> 3) * (kHaloPitch * 128));
             const uint32_t h = __float_as_uint(v) & 0xffffe000u;
             hi[px] = h;
             lo[px] = __float_as_uint(v - __uint_as_float(h));
@@ -599,23 +635,23 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
 #pragma unroll
           for (int px = 0; px < 32; ++px) { hi[px] = 0u; lo[px] = 0u; }
         }
-        mbar_wait(bar_aempty + 8 * t, ((u >> 1) & 1) ^ 1);
+        mbar_wait(bar_aempty + 8 * slot, ((u >> 2) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a_slot = lane_base + aoff + t * 64;
+        const uint32_t a_slot = lane_base + aoff + slot * 64;
         tmem_st32(a_slot, hi);
         tmem_st32(a_slot + 32, lo);
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(bar_afull + 8 * t);
+        mbar_arrive(bar_afull + 8 * slot);
       }
       if (++s == S) { s = 0; ph ^= 1; }
     }
-    // ---- epilogue: accumulator tiles -> partial[chunk][(tap, channel)][co]
+    // ---- epilogue: accumulator tiles -> partial[chunk][(tap, channel)][co]; tiles split between the two groups
     if (nkb > 0) {
       mbar_wait(bar_acc, 0);
       tc_fence_after();
     }
-    for (int mt = 0; mt < QT; ++mt) {
+    for (int mt = cg; mt < QT; mt += 2) {
       const int tap = 4 * mt + q;
       for (int c0 = 0; c0 < Co; c0 += 32) {
         uint32_t v[32];
@@ -725,6 +761,7 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
   p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
   p.wimg = img;
+  { const char* dbg = getenv("UAD_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   for (int c = 0; c < 4; ++c) p.taps[c] = g.taps[c];
 
   // 5-D tensor map over the NHWC input: (channel [x parity], W, parity/1, H, B); box = (32 ch, TW, 1, TH, TB)
@@ -769,7 +806,7 @@ int uad_tc_wgrad_supported(int Cg, int Co, int lgMH, int lgMW) {
 }
 
 static void wgrad_tc_plan(int Cg, int Co, int P, int* ngroups, int* tpg, int* QT, int* nchunks, int* bpc) {
-  const int qt_max = (512 - 128) / Co;                  // accumulator tiles that fit beside the two A slots
+  const int qt_max = (512 - 256) / Co;                  // accumulator tiles that fit beside the four A slots
   int qt = qt_max > 7 ? 7 : qt_max;
   *ngroups = uad_cdiv(25, 4 * qt);
   *tpg = uad_cdiv(25, *ngroups);
@@ -804,16 +841,16 @@ int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* 
   p.partial = reinterpret_cast<float*>(ws);
   for (int t = 0; t < 25; ++t) { p.dh[t] = w.taps.dh[t]; p.dw[t] = w.taps.dw[t]; }
   const size_t stage_bytes = kHaloBytes + 3u * 32u * Co * 4u;
-  p.stages = (Co == 128) ? 2 : (Co == 64 ? 3 : 4);
+  p.stages = (Co == 128) ? 2 : 3;
   { const char* dbg = getenv("UAD_WGRAD_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
 
   const cuuint64_t e = sizeof(float);
   const int MH = 1 << w.lgMH, MW = 1 << w.lgMW;
   CUtensorMap tmap_g, tmap_o;
-  {   // gathered fine tensor [B, GH, GW, Cg] viewed as (2*Cg, GW/2, 2, GH/2, B); box = (32 ch, 10, 1, 6, 1)
+  {   // gathered fine tensor [B, GH, GW, Cg] viewed as (2*Cg, GW/2, 2, GH/2, B); box = (32 ch, 16, 1, 6, 1)
     cuuint64_t dims[5] = {2ull * Cg, (cuuint64_t)w.GW / 2, 2, (cuuint64_t)w.GH / 2, (cuuint64_t)w.B};
     cuuint64_t strides[4] = {2ull * Cg * e, (cuuint64_t)w.GW * Cg * e, 2ull * w.GW * Cg * e, (cuuint64_t)w.GH * w.GW * Cg * e};
-    cuuint32_t box[5] = {32, kWPW + 2, 1, kWPH + 2, 1};
+    cuuint32_t box[5] = {32, kHaloPitch, 1, kWPH + 2, 1};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult cr = encode(&tmap_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(w.g), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -837,7 +874,7 @@ int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* 
     attr_set = true;
   }
   dim3 grid(nchunks, p.ngroups * p.ncb);
-  wgrad_tc<<<grid, 256, smem, st>>>(tmap_g, tmap_o, p);
+  wgrad_tc<<<grid, 384, smem, st>>>(tmap_g, tmap_o, p);
   UAD_LAUNCH_CHECK("wgrad_tc");
   return uad_launch_splitk_reduce(p.partial, nchunks, (size_t)w.Mp * Co, out, accumulate, st);
 }
