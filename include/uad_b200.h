@@ -120,6 +120,14 @@ int uad_final1x1_l1_bwd(const float* a, const float* w, const float* x, const fl
                         float* dw, float* dbias, int B, int HW, int Cin, int accumulate, void* ws, size_t ws_bytes,
                         void* stream);
 
+/* fused variant for training: backward of the final 1x1+L1 AND of the preceding "z -> frozen BN -> act" block in one pass
+ * (reads z, x, xhat; writes dz; produces dw/dbias of the 1x1 and dgamma/dbeta/dbias_prev of the block) - equals
+ * uad_final1x1_l1_bwd followed by uad_act_bn_bwd without materialising da (saves ~3 activation-sized HBM passes). */
+int uad_final1x1_l1_bwd_fused(const float* z, const float* gamma, const float* beta, const float* w, const float* x,
+                              const float* xhat, float scale, float* dz, float* dgamma, float* dbeta, float* dbias_prev,
+                              float* dw, float* dbias, int B, int HW, int Cin, int act, float alpha, float bn_c,
+                              int accumulate, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- loss scalars: out[0]=mean(rec), out[1]=mean(kl) (0 if kl NULL), out[2]=mean(rec+kl) (trainers/VAE.py:40-42) */
 int uad_loss_scalars(const float* rec, const float* kl, float* out3, int B, void* stream);
 

@@ -368,3 +368,45 @@ def test_threshold_counts_bitexact():
     for i, t in enumerate(thr):
         assert tuple(got[i]) == oscore.counts(d64, label.astype(np.int64), t)
     assert np.array_equal(mask.cpu().numpy().astype(bool), oscore.threshold_mask(d64, thr[0]))
+
+
+def test_final_bwd_fused_equals_unfused_pair():
+    """uad_final1x1_l1_bwd_fused == uad_final1x1_l1_bwd followed by uad_act_bn_bwd (and both match the float64 oracle)."""
+    from gpu_util import call, dev, empty, ptr, relerr, st, sync, workspace
+    rng = np.random.default_rng(3)
+    B, S, C = 2, 64, 32
+    z = rng.standard_normal((B, S, S, C)).astype(np.float32)
+    w = (rng.standard_normal(C) / 4).astype(np.float32)
+    bfin = np.array([0.05], np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(C)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(C)).astype(np.float32)
+    x = O.synthetic_slices(B, S, seed=9)
+    bn_c = 1 / math.sqrt(1.001)
+    zt, gt, bt = t64(z).requires_grad_(True), t64(gamma).requires_grad_(True), t64(beta).requires_grad_(True)
+    bias = torch.zeros(C, dtype=torch.float64, requires_grad=True)
+    wt, bft = t64(w).requires_grad_(True), t64(bfin).requires_grad_(True)
+    a = F.leaky_relu(gt * bn_c * (zt + bias) + bt, 0.3)
+    xh = (a * wt).sum(-1, keepdim=True) + bft
+    sgn = torch.sign(xh.detach() - t64(x))
+    loss = ((xh - t64(x)) * sgn).sum(dim=(1, 2, 3)).mean()
+    gz, gg, gb, gbias, gw, gbf = torch.autograd.grad(loss, [zt, gt, bt, bias, wt, bft])
+    ws = workspace(1 << 22)
+    zd, wd, xd, gd, bd = dev(z), dev(w), dev(x), dev(gamma), dev(beta)
+    ad, xhd, recd = empty(B, S, S, C), empty(B, S, S, 1), empty(B)
+    # activation (numpy) + xhat with the library's own forward kernel
+    a_np = np.where((gamma * bn_c * z + beta) > 0, gamma * bn_c * z + beta, 0.3 * (gamma * bn_c * z + beta)).astype(np.float32)
+    ad = dev(a_np)
+    call('uad_final1x1_l1_fwd', ptr(ad), ptr(wd), ptr(dev(bfin)), ptr(xd), ptr(xhd), None, ptr(recd), B, S * S, C, ptr(ws), 1 << 22, st())
+    dzf, dgf, dbf, dbiasf, dwf, dbff = empty(B, S, S, C), empty(C), empty(C), empty(C), empty(C), empty(1)
+    call('uad_final1x1_l1_bwd_fused', ptr(zd), ptr(gd), ptr(bd), ptr(wd), ptr(xd), ptr(xhd), 1.0 / B, ptr(dzf), ptr(dgf), ptr(dbf),
+         ptr(dbiasf), ptr(dwf), ptr(dbff), B, S * S, C, 1, 0.3, bn_c, 0, ptr(ws), 1 << 22, st())
+    da, dwu, dbu = empty(B, S, S, C), empty(C), empty(1)
+    call('uad_final1x1_l1_bwd', ptr(ad), ptr(wd), ptr(xd), ptr(xhd), 1.0 / B, ptr(da), ptr(dwu), ptr(dbu), B, S * S, C, 0, ptr(ws),
+         1 << 22, st())
+    dzu, dgu, dbetau, dbiasu = empty(B, S, S, C), empty(C), empty(C), empty(C)
+    call('uad_act_bn_bwd', ptr(da), ptr(zd), ptr(gd), ptr(bd), ptr(dzu), ptr(dgu), ptr(dbetau), ptr(dbiasu), B * S * S, C, 1, 0.3,
+         bn_c, 0, ptr(ws), 1 << 22, st())
+    sync()
+    for f, u, ref in ((dzf, dzu, gz), (dgf, dgu, gg), (dbf, dbetau, gb), (dbiasf, dbiasu, gbias), (dwf, dwu, gw), (dbff, dbu, gbf)):
+        assert relerr(f.cpu().numpy(), u.cpu().numpy()) < 1e-5
+        assert relerr(f.cpu().numpy(), ref.numpy()) < 5 * TOL

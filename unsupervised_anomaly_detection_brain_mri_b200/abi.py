@@ -40,6 +40,7 @@ SIGNATURES = {
     'uad_reparam_kl_bwd': (_I, [_P] * 4 + [_F] + [_P] * 2 + [_I, _I, _P]),
     'uad_final1x1_l1_fwd': (_I, [_P] * 7 + [_I] * 3 + [_P, _Z, _P]),
     'uad_final1x1_l1_bwd': (_I, [_P] * 4 + [_F] + [_P] * 3 + [_I] * 4 + [_P, _Z, _P]),
+    'uad_final1x1_l1_bwd_fused': (_I, [_P] * 6 + [_F] + [_P] * 6 + [_I] * 4 + [_F, _F, _I, _P, _Z, _P]),
     'uad_loss_scalars': (_I, [_P] * 3 + [_I, _P]),
     'uad_adam_tf_step': (_I, [_P] * 4 + [_Z] + [_F] * 5 + [_P, _P]),
     'uad_randn': (_I, [_P, _Z, _U64, _U64, _P, _P]),

@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restric
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int kh = 0; kh < K; ++kh)
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
@@ -459,17 +459,23 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
       xs[i] = v;
     }
     __syncthreads();
-    for (int ow = warp; ow < Wo; ow += nwarps) {
-      float dv[Q];
+    for (int ow0 = warp * 4; ow0 < Wo; ow0 += nwarps * 4) {      // 4 pixels per iteration: 4 independent dz loads in flight
+      float dv[4][Q];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) dv[q] = dz[((size_t)row * Wo + ow) * Cout + lane + 32 * q];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < Q; ++q)
+          dv[u][q] = (ow0 + u < Wo) ? __ldg(dz + ((size_t)row * Wo + ow0 + u) * Cout + lane + 32 * q) : 0.f;
 #pragma unroll
       for (int kh = 0; kh < K; ++kh)
 #pragma unroll
         for (int kw = 0; kw < K; ++kw) {
-          float xv = xs[kh * XW + 2 * ow + kw];
 #pragma unroll
-          for (int q = 0; q < Q; ++q) acc[kh * K + kw][q] = fmaf(xv, dv[q], acc[kh * K + kw][q]);
+          for (int u = 0; u < 4; ++u) {
+            const float xv = xs[kh * XW + 2 * (ow0 + u) + kw];      // zero padded beyond the row (XW = W + K)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc[kh * K + kw][q] = fmaf(xv, dv[u][q], acc[kh * K + kw][q]);
+          }
         }
     }
   }
@@ -488,7 +494,7 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
 
 int uad_conv_c1_wgrad_blocks(int B, int H) {
   int rows = B * (H / 2);
-  return rows < 2 * UAD_NUM_SMS ? rows : 2 * UAD_NUM_SMS;
+  return rows < 4 * UAD_NUM_SMS ? rows : 4 * UAD_NUM_SMS;
 }
 
 int uad_launch_conv_c1_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cout, int ksize,

@@ -296,6 +296,112 @@ extern "C" int uad_final1x1_l1_bwd(const float* a, const float* w, const float* 
   return 0;
 }
 
+// ---- fused: backward of (final 1x1 conv + L1) AND of the preceding "z -> frozen BN -> activation" block.
+// Reads z (pre-BN output of the last transposed conv), x, xhat; writes dz; never materialises da or re-reads a.
+__global__ void __launch_bounds__(256) final_bwd_fused_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ w,
+                                                              const float* __restrict__ x, const float* __restrict__ xhat,
+                                                              float scale, float* __restrict__ dz, float* __restrict__ partial,
+                                                              size_t npix, int Cin, int act, float alpha, float bn_c) {
+  __shared__ float red[256][13];
+  const int LP = Cin / 4;
+  const int lp = threadIdx.x % LP;
+  const int pl = threadIdx.x / LP;
+  const int ppp = 256 / LP;
+  const float4 w4 = *reinterpret_cast<const float4*>(w + lp * 4);
+  const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+  float sc[4], sf[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = gamma ? gamma[lp * 4 + j] * bn_c : 1.f;
+    sf[j] = beta ? beta[lp * 4 + j] : 0.f;
+  }
+  float s_du[4] = {0.f, 0.f, 0.f, 0.f}, s_duz[4] = {0.f, 0.f, 0.f, 0.f}, s_w[4] = {0.f, 0.f, 0.f, 0.f}, s_b = 0.f;
+  for (size_t pix = (size_t)blockIdx.x * ppp + pl; pix < npix; pix += (size_t)gridDim.x * ppp) {
+    const float e = xhat[pix] - x[pix];
+    const float g = (e > 0.f ? scale : (e < 0.f ? -scale : 0.f));
+    const float4 z4 = __ldg(reinterpret_cast<const float4*>(z + pix * Cin + lp * 4));
+    const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float u = sc[j] * zv[j] + sf[j];
+      const float a = uad_act(u, act, alpha);
+      const float du = g * wv[j] * uad_act_grad(u, act, alpha);
+      s_w[j] += g * a;
+      s_du[j] += du;
+      s_duz[j] += du * zv[j];
+      o[j] = sc[j] * du;
+    }
+    if (lp == 0) s_b += g;
+    *reinterpret_cast<float4*>(dz + pix * Cin + lp * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[threadIdx.x][j] = s_du[j];
+    red[threadIdx.x][4 + j] = s_duz[j];
+    red[threadIdx.x][8 + j] = s_w[j];
+  }
+  red[threadIdx.x][12] = s_b;
+  __syncthreads();
+  // partial layout per block: [s_du(Cin) | s_duz(Cin) | s_w(Cin) | s_b]
+  for (int idx = threadIdx.x; idx < 3 * Cin + 1; idx += blockDim.x) {
+    float s = 0.f;
+    if (idx < 3 * Cin) {
+      const int which = idx / Cin, c = idx % Cin;
+      for (int k = 0; k < ppp; ++k) s += red[k * LP + c / 4][which * 4 + (c % 4)];
+    } else {
+      for (int k = 0; k < ppp; ++k) s += red[k * LP][12];
+    }
+    partial[(size_t)blockIdx.x * (3 * Cin + 1) + idx] = s;
+  }
+}
+
+__global__ void final_bwd_fused_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cin, const float* __restrict__ gamma,
+                                              float bn_c, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                              float* __restrict__ dbias_prev, float* __restrict__ dw, float* __restrict__ dbias,
+                                              int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = 3 * Cin + 1;
+  if (c < Cin) {
+    float a = 0.f, b = 0.f, d = 0.f;
+    for (int k = 0; k < nblocks; ++k) {
+      a += partial[(size_t)k * stride + c];
+      b += partial[(size_t)k * stride + Cin + c];
+      d += partial[(size_t)k * stride + 2 * Cin + c];
+    }
+    const float scv = gamma ? gamma[c] * bn_c : 1.f;
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bn_c * b;
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a;
+    if (dbias_prev) dbias_prev[c] = (accumulate ? dbias_prev[c] : 0.f) + scv * a;
+    if (dw) dw[c] = (accumulate ? dw[c] : 0.f) + d;
+  } else if (c == Cin) {
+    float s = 0.f;
+    for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * stride + 3 * Cin];
+    if (dbias) dbias[0] = (accumulate ? dbias[0] : 0.f) + s;
+  }
+}
+
+extern "C" int uad_final1x1_l1_bwd_fused(const float* z, const float* gamma, const float* beta, const float* w, const float* x,
+                                         const float* xhat, float scale, float* dz, float* dgamma, float* dbeta,
+                                         float* dbias_prev, float* dw, float* dbias, int B, int HW, int Cin, int act, float alpha,
+                                         float bn_c, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  UAD_REQUIRE(Cin % 4 == 0 && uad_is_pow2(Cin / 4) && Cin <= 128, "uad_final1x1_l1_bwd_fused: unsupported Cin=%d", Cin);
+  UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_final1x1_l1_bwd_fused: gamma/beta must both be set or both NULL");
+  const size_t npix = (size_t)B * HW;
+  const int ppp = 256 / (Cin / 4);
+  long long nb = (npix + ppp - 1) / ppp;
+  if (nb > 4 * UAD_NUM_SMS) nb = 4 * UAD_NUM_SMS;
+  UAD_REQUIRE(ws && ws_bytes >= (size_t)nb * (3 * Cin + 1) * sizeof(float), "uad_final1x1_l1_bwd_fused: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  final_bwd_fused_kernel<<<(int)nb, 256, 0, st>>>(z, gamma, beta, w, x, xhat, scale, dz, (float*)ws, npix, Cin, act, alpha, bn_c);
+  UAD_LAUNCH_CHECK("final_bwd_fused");
+  final_bwd_fused_reduce_kernel<<<uad_cdiv(Cin + 1, 128), 128, 0, st>>>((const float*)ws, (int)nb, Cin, gamma, bn_c, dgamma, dbeta,
+                                                                       dbias_prev, dw, dbias, accumulate);
+  UAD_LAUNCH_CHECK("final_bwd_fused_reduce");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ loss scalars
 __global__ void loss_scalars_kernel(const float* __restrict__ rec, const float* __restrict__ kl, float* __restrict__ out, int B) {
   __shared__ float red[3][32];

@@ -411,16 +411,23 @@ class ConvAutoencoderEngine:
             is_ce = bi > 0
             g, gn = self.gbuf
             cin = self.dec_ch[-1]
-            self._op('dec_Conv2D_final', 'uad_final1x1_l1_bwd', ptr(br.dec_a[-1]), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x),
-                 ptr(br.xhat), scale, ptr(g), ptr(fp.g('Decoder/dec_Conv2D_final/kernel')),
-                 ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B, self.S * self.S, cin, acc, ws, wsb, st)
+            last = self.n - 1
+            lpre = f'Decoder/dec_Conv2DT_{last}'
+            lbn = f'Decoder/{_bn(self.n + 1 + last)}'
+            # fused: final 1x1 + L1 backward AND the BN/LeakyReLU backward of the last transposed-conv block
+            self._op('dec_Conv2D_final', 'uad_final1x1_l1_bwd_fused', ptr(br.dec_z[last]), ptr(fp.p(lbn + '/gamma')),
+                     ptr(fp.p(lbn + '/beta')), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x), ptr(br.xhat), scale,
+                     ptr(g), ptr(fp.g(lbn + '/gamma')), ptr(fp.g(lbn + '/beta')), ptr(fp.g(lpre + '/bias')),
+                     ptr(fp.g('Decoder/dec_Conv2D_final/kernel')), ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B,
+                     self.S * self.S, cin, ACT_LEAKY, LRELU_ALPHA, BN_C, acc, ws, wsb, st)
             s = self.S
             for i in reversed(range(self.n)):
                 co = self.dec_ch[i]
                 ci = self.dec_ch[i - 1] if i > 0 else self.enc_ch[-1]
                 pre = f'Decoder/dec_Conv2DT_{i}'
                 bnn = f'Decoder/{_bn(self.n + 1 + i)}'
-                self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                if i != self.n - 1:      # the last block's BN/activation backward is fused into the final-1x1 backward above
+                  self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
                      ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.dec_a[i - 1] if i > 0 else br.ar
