@@ -31,7 +31,7 @@ constexpr int kABytes = kTileM * kKBlk * 4;  // 16 KB
 // accumulator with truncation (measured: error grows linearly with the number of accumulations), so the large hi*hi
 // stream is spread over G accumulators and the small correction terms never disturb it; the epilogue sums them in
 // registers with round-to-nearest.
-constexpr uint32_t kSpinLimit = 1u << 26;    // bounded mbarrier spins: trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 1u << 22;    // bounded mbarrier spins: trap instead of hanging the GPU
 
 struct TcParams {
   int TW, TH, TB, lgTW, lgTH;
@@ -44,6 +44,9 @@ struct TcParams {
   int tmem_cols;       // 256 or 512
   int nacc;            // accumulators of N columns: 2G (paired layout, N <= 64) or G + 1 (N = 128)
   int nslots;          // TMEM A slots (2..4)
+  int acc_bufs;        // accumulator sets in TMEM (2 = epilogue overlaps the next item's MMAs)
+  int n_items;         // work items = tiles * nclasses
+  int nclasses;
   int debug;           // developer timing switches (UAD_TC_DEBUG): 1 = converters skip their work, 2 = MMA issuer skips the MMAs
   float* z_out;
   float* a_out;
@@ -149,7 +152,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// ------------------------------------------------------------------------------------------------ the kernel
+// ------------------------------------------------------------------------------------------------ non-persistent variant
+// One (tile, class) per CTA, 256 threads (converters double as epilogue warps), up to 2 CTAs per SM.  Measured faster
+// than the persistent kernel below for N = 32 (two co-resident CTAs interleave their converter->MMA latency chains);
+// the persistent kernel wins for N >= 64.  Same pipeline, same numerics.
 // TMEM columns: `nacc` accumulators of N columns, then `nslots` {hi,lo} A slots of 64 columns.
 //   N <= 64 : accumulator pairs [main_g | corr_g], g < G.  Per K=8 slice TWO instructions:
 //             (a_hi) x [B_hi ; B_lo]  as ONE 2N-wide MMA into [main_g | corr_g]   (hi*hi and hi*lo at once)
@@ -159,7 +165,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // linearly with the number of accumulations), so the large hi*hi stream is dealt round-robin over G accumulators and
 // the small correction terms never disturb it; the epilogue sums all of them in registers with round-to-nearest.
 __global__ void __launch_bounds__(256, 1)
-gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -393,6 +399,287 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+// PERSISTENT: one CTA per SM walks work items (tile, output-parity class) = blockIdx.x + k * gridDim.x; the smem ring,
+// the TMEM A-slot ring and the mbarrier phases run on across items, so the TMA producer prefetches the next item's
+// operands while the epilogue warps drain the previous accumulators (double-buffered in TMEM when they fit).
+//
+// TMEM columns: `acc_bufs` accumulator sets of `nacc` x N columns, then `nslots` {hi,lo} A slots of 64 columns.
+//   N <= 64 : accumulator pairs [main_g | corr_g], g < G.  Per K=8 slice TWO instructions:
+//             (a_hi) x [B_hi ; B_lo]  as ONE 2N-wide MMA into [main_g | corr_g]   (hi*hi and hi*lo at once)
+//             (a_lo) x  B_hi          as an N-wide MMA into corr_g
+//   N = 128 : [main_0 .. main_{G-1} | corr], three N-wide MMAs per slice.
+// Why several accumulators: the tensor core adds into its fp32 accumulator with truncation (measured: error grows
+// linearly with the number of accumulations), so the large hi*hi stream is dealt round-robin over G accumulators and
+// the small correction terms never disturb it; the epilogue sums all of them in registers with round-to-nearest.
+//
+// 12 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM alloc | 3 epilogue constants | 4-7 converters | 8-11 epilogue.
+__global__ void __launch_bounds__(384, 1)
+gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int N = p.N;
+  const uint32_t b_bytes = 2u * N * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int S = p.stages;
+  const int NS = p.nslots;
+  // bookkeeping lives after the pipeline stages
+  const uint32_t misc = smem_base + S * stage_bytes;
+  const uint32_t bar_full = misc;                       // S x 8   (S <= 8)
+  const uint32_t bar_empty = misc + 64;                 // S x 8
+  const uint32_t bar_afull = misc + 128;                // NS x 8
+  const uint32_t bar_aempty = misc + 160;               // NS x 8
+  const uint32_t bar_accfull = misc + 192;              // 2 x 8
+  const uint32_t bar_accempty = misc + 208;             // 2 x 8
+  const uint32_t tmem_slot = misc + 224;
+  float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256);               // bias[N], scale[N], shift[N]
+  float* stg_base = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256 + 3 * N * 4);   // 4 x 32 x (N+4) staging
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t aoff = p.acc_bufs * p.nacc * N;        // first A slot column
+  const int nclasses = p.nclasses;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accempty + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {
+    for (int n = lane; n < N; n += 32) {
+      epi[n] = p.bias ? p.bias[n] : 0.f;
+      epi[N + n] = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
+      epi[2 * N + n] = p.beta ? p.beta[n] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // all ring indices / phase bits are carried incrementally: no runtime div/mod in the per-k-block loops
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int cls = item % nclasses, tile = item / nclasses;
+        const TapSet& ts = p.taps[cls];
+        const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tbi = tile / (p.tiles_w * p.tiles_h);
+        const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+        const int nkb = ts.n * p.Cblks;
+        int tap = 0, cb = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, kABytes + b_bytes);
+          const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
+          const uint32_t a_dst = smem_base + s * stage_bytes;
+          if (p.stride2)
+            tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
+          else
+            tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
+          const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
+          bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+          if (++cb == p.Cblks) { cb = 0; ++tap; }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    {
+      // the whole warp walks the loop (converged); one elected lane issues.
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
+      const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
+      const uint64_t bdesc0 = make_sw128_desc(smem_base + kABytes);          // B image of stage 0 (hi rows then lo rows)
+      const uint32_t stage_units = stage_bytes >> 4, lo_units = (uint32_t)(N * 128) >> 4;
+      const bool paired = (N <= 64);
+      int s = 0, t = 0, buf = 0;
+      uint32_t ph = 0, pht = 0, phb = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int nkb = p.taps[item % nclasses].n * p.Cblks;
+        mbar_wait(bar_accempty + 8 * buf, phb ^ 1);             // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + buf * p.nacc * N;
+        int g = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(bar_full + 8 * s, ph);                      // weight image landed (async proxy -> visible)
+          mbar_wait(bar_afull + 8 * t, pht);                    // converters filled TMEM A slot t
+          tc_fence_after();
+          const uint64_t dhi0 = bdesc0 + (uint64_t)(s * stage_units);
+          const uint32_t a_hi = tmem_base + aoff + t * 64;
+          const uint32_t a_lo = a_hi + 32;
+          const uint32_t first = (i >= p.G) ? 1u : 0u;          // accumulator g already holds a partial sum of this item?
+          if (elect_one()) {
+            if (p.debug & 2) {
+            } else if (paired) {
+              const uint32_t d_pair = acc0 + g * 2 * N;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {                     // K = 8 tf32 per instruction -> 32 bytes (2 x 16 B) along the row
+                mma_tf32_ts(d_pair, a_hi + j * 8, dhi0 + 2 * j, idesc2N, first | (j != 0));
+                mma_tf32_ts(d_pair + N, a_lo + j * 8, dhi0 + 2 * j, idescN, 1u);
+              }
+            } else {
+              const uint32_t d_main = acc0 + g * N;
+              const uint32_t d_corr = acc0 + p.G * N;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                mma_tf32_ts(d_corr, a_lo + j * 8, dhi0 + 2 * j, idescN, (i | j) != 0);
+                mma_tf32_ts(d_corr, a_hi + j * 8, dhi0 + lo_units + 2 * j, idescN, 1u);
+                mma_tf32_ts(d_main, a_hi + j * 8, dhi0 + 2 * j, idescN, first | (j != 0));
+              }
+            }
+            tc_commit(bar_empty + 8 * s);                       // smem stage reusable once these MMAs retire
+            tc_commit(bar_aempty + 8 * t);                      // TMEM A slot reusable
+            if (i == nkb - 1) tc_commit(bar_accfull + 8 * buf); // accumulators of this item complete
+          }
+          __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1; }
+          if (++t == NS) { t = 0; pht ^= 1; }
+          if (++g == p.G) g = 0;
+        }
+        if (++buf == p.acc_bufs) { buf = 0; phb ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================================== converters
+    const int row = threadIdx.x - 128;                          // tile row == TMEM lane
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    int s = 0, t = 0;
+    uint32_t ph = 0, pht = 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int nkb = p.taps[item % nclasses].n * p.Cblks;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(bar_full + 8 * s, ph);
+        const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
+        uint32_t hi[32], lo[32];
+        if (p.debug & 1) {
+          mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+          mbar_arrive(bar_afull + 8 * t);
+          if (++s == S) { s = 0; ph ^= 1; }
+          if (++t == NS) { t = 0; pht ^= 1; }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                           // 16-byte chunk j of this row sits at (j ^ (row & 7))
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
+          const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
+            hi[4 * j + e] = h;
+            lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+          }
+        }
+        mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+        tc_fence_after();
+        const uint32_t a_slot = lane_base + aoff + t * 64;
+        tmem_st32(a_slot, hi);
+        tmem_st32(a_slot + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_afull + 8 * t);
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++t == NS) { t = 0; pht ^= 1; }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================================================================== epilogue warps
+    const int row = threadIdx.x - 256;                          // tile row == TMEM lane
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ldw = N + 4;
+    float* stg = stg_base + (size_t)q * 32 * ldw;               // this warp's 32 x (N+4) staging rows
+    const int lanes_per_row = N / 4;                            // float4 lanes covering one output row
+    const int rows_per_it = 32 / lanes_per_row;
+    const int npass = (p.z_out ? 1 : 0) + (p.a_out ? 1 : 0);
+    int buf = 0;
+    uint32_t phb = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int cls = item % nclasses, tile = item / nclasses;
+      const TapSet& ts = p.taps[cls];
+      const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tbi = tile / (p.tiles_w * p.tiles_h);
+      const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+      // output pixel of THIS thread's row (shuffled to the storing lanes below)
+      const int tw = row & (p.TW - 1);
+      const int th = (row >> p.lgTW) & (p.TH - 1);
+      const int tb = row >> (p.lgTW + p.lgTH);
+      const int b = b0 + tb;
+      const long long my_off = (b < p.B)
+          ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
+          : -1;
+      mbar_wait(bar_accfull + 8 * buf, phb);
+      tc_fence_after();
+      const uint32_t acc0 = lane_base + buf * p.nacc * N;
+      int done = 0;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        float* out = pass == 0 ? p.z_out : p.a_out;
+        if (!out) continue;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t v[32], u[32];
+          tmem_ld32(acc0 + c0, v);
+          for (int k = 1; k < p.nacc; ++k) {
+            tmem_ld32(acc0 + k * N + c0, u);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = c0 + j + e;
+              const float z = __uint_as_float(v[j + e]) + epi[n];
+              o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], p.act, p.alpha);
+            }
+            *reinterpret_cast<float4*>(stg + lane * ldw + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        if (++done == npass) {                                  // last TMEM read of this item: hand the accumulators back
+          tc_fence_before();
+          mbar_arrive(bar_accempty + 8 * buf);
+        }
+        __syncwarp();
+        for (int rr = 0; rr < 32; rr += rows_per_it) {
+          const int r = rr + lane / lanes_per_row;
+          const int c = (lane % lanes_per_row) * 4;
+          const long long off = __shfl_sync(0xffffffffu, my_off, r);
+          if (off >= 0) {
+            const float4 val = *reinterpret_cast<const float4*>(stg + r * ldw + c);
+            *reinterpret_cast<float4*>(out + off + c) = val;
+          }
+        }
+        __syncwarp();
+      }
+      if (++buf == p.acc_bufs) { buf = 0; phb ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -745,24 +1032,26 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   p.B = g.B; p.C = C; p.Cblks = C / kKBlk; p.N = N;
   p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
   p.stride2 = (g.sh == 2);
-  p.stages = (N == 128) ? 3 : 4;
   {
     int max_taps = 0;
     for (int c = 0; c < nclasses; ++c) max_taps = g.taps[c].n > max_taps ? g.taps[c].n : max_taps;
     p.G = (max_taps * C > 640) ? 2 : 1;      // deep reductions: halve the accumulation chain length
     p.nacc = (N <= 64) ? 2 * p.G : p.G + 1;
-    const int acc_cols = p.nacc * N;
-    p.tmem_cols = (acc_cols + 128 <= 256) ? 256 : 512;
-    p.nslots = (p.tmem_cols - acc_cols) / 64;
+    p.acc_bufs = (2 * p.nacc * N + 128 <= 512) ? 2 : 1;
+    const int acc_cols = p.acc_bufs * p.nacc * N;
+    p.tmem_cols = 512;                         // one persistent CTA per SM owns all of TMEM
+    p.nslots = (512 - acc_cols) / 64;
     if (p.nslots > 4) p.nslots = 4;
     UAD_REQUIRE(p.nslots >= 2, "gather_gemm_tc: TMEM budget exceeded");
-    UAD_REQUIRE(p.tmem_cols <= 512, "gather_gemm_tc: TMEM budget exceeded");
   }
+  p.nclasses = nclasses;
+  p.n_items = p.tiles_w * p.tiles_h * tiles_b * nclasses;
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
   p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
   p.wimg = img;
   { const char* dbg = getenv("UAD_TC_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   for (int c = 0; c < 4; ++c) p.taps[c] = g.taps[c];
+  UAD_REQUIRE(p.z_out || p.a_out, "gather_gemm_tc: no output requested");
 
   // 5-D tensor map over the NHWC input: (channel [x parity], W, parity/1, H, B); box = (32 ch, TW, 1, TH, TB)
   CUtensorMap tmap;
@@ -785,14 +1074,37 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   UAD_REQUIRE(cr == CUDA_SUCCESS, "gather_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
   const size_t stage_bytes = kABytes + 2u * N * 128u;
-  const size_t smem = 1024 + p.stages * stage_bytes + 256 + 3 * N * sizeof(float) + 64;
+  if (N < 64) {
+    // ---- non-persistent variant: (tile, class) per CTA, TMEM sized for 2 CTAs per SM where possible
+    p.acc_bufs = 1;
+    const int acc_cols = p.nacc * N;
+    p.tmem_cols = (acc_cols + 128 <= 256) ? 256 : 512;
+    p.nslots = (p.tmem_cols - acc_cols) / 64;
+    if (p.nslots > 4) p.nslots = 4;
+    p.stages = 4;
+    const size_t smem_np = 1024 + p.stages * stage_bytes + 256 + 3 * N * sizeof(float) + 64;
+    static bool attr_np = false;
+    if (!attr_np) {
+      UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_np, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_np = true;
+    }
+    dim3 grid_np(p.tiles_w * p.tiles_h * tiles_b, nclasses);
+    gather_gemm_tc_np<<<grid_np, 256, smem_np, st>>>(tmap, p);
+    UAD_LAUNCH_CHECK("gather_gemm_tc_np");
+    return 0;
+  }
+  const size_t tail = 256 + 3 * N * sizeof(float) + 4 * 32 * (size_t)(N + 4) * sizeof(float) + 64;
+  p.stages = (int)((220 * 1024 - 1024 - tail) / stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  UAD_REQUIRE(p.stages >= 2, "gather_gemm_tc: shared-memory budget exceeded");
+  const size_t smem = 1024 + p.stages * stage_bytes + tail;
   static bool attr_set = false;
   if (!attr_set) {
-    UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, nclasses);
-  gather_gemm_tc<<<grid, 256, smem, st>>>(tmap, p);
+  const int grid = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
+  gather_gemm_tc<<<grid, 384, smem, st>>>(tmap, p);
   UAD_LAUNCH_CHECK("gather_gemm_tc");
   return 0;
 }
