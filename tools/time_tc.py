@@ -20,6 +20,7 @@ def timeit(fn, reps=10):
 
 B = 64
 cases = {
+  'T3.fwd  (FormT N=32 C=32 64^2->128^2)': ('convT_fwd', 64, 32, 32),
   'T4.fwd  (FormT N=32 C=32 128^2->256^2)': ('convT_fwd', 128, 32, 32),
   'T4.dgrad(FormF N=32 C=32)': ('convT_dgrad', 128, 32, 32),
   'T4.wgrad': ('convT_wgrad', 128, 32, 32),
@@ -45,10 +46,10 @@ for name, (op, H, Cin, Cout) in cases.items():
         elif op == 'convT_wgrad': call('uad_convT2d_wgrad', x.data_ptr(), y.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, 5, 0, 1, ws.data_ptr(), wsb, st())
     res = []
     var = 'UAD_WGRAD_DEBUG' if 'wgrad' in op else 'UAD_TC_DEBUG'
-    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0', '1', '2', '3']
+    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0', '3', '7', '11', '4', '8']
     for dbg in modes:
         os.environ[var] = dbg
         res.append(f'{dbg}:{timeit(run):.3f}ms')
     os.environ[var] = '0'
     print(f'{name:45s} ' + '  '.join(res), flush=True)
-print('gather modes: 0 normal, 1 no-convert, 2 no-MMA, 3 neither | wgrad modes: 0 normal, 2 no-convert, 4 no-MMA, 6 neither')
+print('gather modes (bits): 1 no-convert, 2 no-MMA, 4 no global stores, 8 no epilogue pass | wgrad: 2 no-convert, 4 no-MMA')

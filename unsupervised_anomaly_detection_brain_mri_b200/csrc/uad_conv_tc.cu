@@ -348,15 +348,13 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
         : -1;
     const int ldw = N + 4;
-    float* stg = reinterpret_cast<float*>(smem_gen) + (size_t)q * 32 * ldw;     // this warp's 32 x (N+4) staging rows
+    // two staging buffers (z, a) of 32 x (N+4) floats per warp inside the now idle pipeline stages:
+    // ONE pass over TMEM yields both outputs
+    float* stg_z = reinterpret_cast<float*>(smem_gen) + (size_t)q * 32 * ldw;
+    float* stg_a = stg_z + 4 * 32 * ldw;
     const int lanes_per_row = N / 4;                    // float4 lanes covering one output row
     const int rows_per_it = 32 / lanes_per_row;
-    const bool both = p.z_out && p.a_out;
-    // one pass over TMEM produces z (staged + stored) and a (kept in the same staging buffer afterwards)
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      float* out = pass == 0 ? p.z_out : p.a_out;
-      if (!out) continue;
+    if (!(p.debug & 8)) {
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32], u[32];
         tmem_ld32(lane_base + c0, v);
@@ -369,29 +367,30 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float o[4];
+          float zz[4], aa[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int n = c0 + j + e;
-            const float z = __uint_as_float(v[j + e]) + epi[n];
-            o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], p.act, p.alpha);
+            zz[e] = __uint_as_float(v[j + e]) + epi[n];
+            aa[e] = uad_act(epi[N + n] * zz[e] + epi[2 * N + n], p.act, p.alpha);
           }
-          *reinterpret_cast<float4*>(stg + lane * ldw + c0 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          if (p.z_out) *reinterpret_cast<float4*>(stg_z + lane * ldw + c0 + j) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+          if (p.a_out) *reinterpret_cast<float4*>(stg_a + lane * ldw + c0 + j) = make_float4(aa[0], aa[1], aa[2], aa[3]);
         }
       }
       __syncwarp();
-      for (int rr = 0; rr < 32; rr += rows_per_it) {
-        const int r = rr + lane / lanes_per_row;
-        const int c = (lane % lanes_per_row) * 4;
-        const long long off = __shfl_sync(0xffffffffu, my_off, r);
-        if (off >= 0) {
-          const float4 val = *reinterpret_cast<const float4*>(stg + r * ldw + c);
-          *reinterpret_cast<float4*>(out + off + c) = val;
+      if (!(p.debug & 4))
+        for (int rr = 0; rr < 32; rr += rows_per_it) {
+          const int r = rr + lane / lanes_per_row;
+          const int c = (lane % lanes_per_row) * 4;
+          const long long off = __shfl_sync(0xffffffffu, my_off, r);
+          if (off >= 0) {
+            if (p.z_out) *reinterpret_cast<float4*>(p.z_out + off + c) = *reinterpret_cast<const float4*>(stg_z + r * ldw + c);
+            if (p.a_out) *reinterpret_cast<float4*>(p.a_out + off + c) = *reinterpret_cast<const float4*>(stg_a + r * ldw + c);
+          }
         }
-      }
       __syncwarp();
     }
-    (void)both;
   }
 
   tc_fence_before();
