@@ -152,19 +152,13 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// ------------------------------------------------------------------------------------------------ non-persistent variant
-// One (tile, class) per CTA, 256 threads (converters double as epilogue warps), up to 2 CTAs per SM.  Measured faster
-// than the persistent kernel below for N = 32 (two co-resident CTAs interleave their converter->MMA latency chains);
-// the persistent kernel wins for N >= 64.  Same pipeline, same numerics.
-// TMEM columns: `nacc` accumulators of N columns, then `nslots` {hi,lo} A slots of 64 columns.
-//   N <= 64 : accumulator pairs [main_g | corr_g], g < G.  Per K=8 slice TWO instructions:
-//             (a_hi) x [B_hi ; B_lo]  as ONE 2N-wide MMA into [main_g | corr_g]   (hi*hi and hi*lo at once)
-//             (a_lo) x  B_hi          as an N-wide MMA into corr_g
-//   N = 128 : [main_0 .. main_{G-1} | corr], three N-wide MMAs per slice (a 2N-wide pair would not leave room for A).
-// Why several accumulators: the tensor core adds into its fp32 accumulator with truncation (measured: error grows
-// linearly with the number of accumulations), so the large hi*hi stream is dealt round-robin over G accumulators and
-// the small correction terms never disturb it; the epilogue sums all of them in registers with round-to-nearest.
-__global__ void __launch_bounds__(256, 1)
+// ------------------------------------------------------------------------------------------------ N = 32 variant
+// One 128-pixel tile per CTA, 256 threads (the converter warps double as epilogue warps), two CTAs per SM so that the
+// converter -> MMA latency chains of two tiles interleave (measured faster than the persistent kernel below for
+// N = 32; the persistent kernel wins for N >= 64).  For the transposed form the CTA walks all four output-parity
+// classes of its tile back to back: prologue / TMEM allocation are paid once per tile and the TMA producer keeps
+// prefetching the next class's operands while the current class is being written out.  Same numerics as below.
+__global__ void __launch_bounds__(256, 2)
 gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -174,7 +168,6 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   const uint32_t stage_bytes = kABytes + b_bytes;
   const int S = p.stages;
   const int NS = p.nslots;
-  // bookkeeping lives after the pipeline stages
   const uint32_t misc = smem_base + S * stage_bytes;
   const uint32_t bar_full = misc;                       // S x 8
   const uint32_t bar_empty = misc + 64;                 // S x 8
@@ -182,12 +175,12 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   const uint32_t bar_aempty = misc + 160;               // NS x 8
   const uint32_t bar_acc = misc + 192;
   const uint32_t tmem_slot = misc + 200;
-  float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256);   // bias[N], scale[N], shift[N]
+  float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256);                 // bias[N], scale[N], shift[N]
+  float* stg_base = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256 + 3 * N * 4);     // 4 x 32 x (N+4) staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TapSet& ts = p.taps[blockIdx.y];
-  const int nkb = ts.n * p.Cblks;
   const uint32_t aoff = p.nacc * N;                     // first A slot column
+  const int ncls = p.nclasses;
 
   // tile origin on the M-grid
   const int tile = blockIdx.x;
@@ -220,41 +213,46 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  // all ring indices / phase bits are carried incrementally: no runtime div/mod in the per-k-block loops
+  // all ring indices / phase bits are carried incrementally across k-blocks AND classes
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-      int tap = 0, cb = 0, s = 0;
+      int s = 0;
       uint32_t ph = 0;
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-        const uint32_t full = bar_full + 8 * s;
-        mbar_expect_tx(full, kABytes + b_bytes);
-        const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
-        const uint32_t a_dst = smem_base + s * stage_bytes;
-        if (p.stride2)
-          tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
-        else
-          tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
-        const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
-        bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
-        if (++cb == p.Cblks) { cb = 0; ++tap; }
-        if (++s == S) { s = 0; ph ^= 1; }
+      for (int cls = 0; cls < ncls; ++cls) {
+        const TapSet& ts = p.taps[cls];
+        const int nkb = ts.n * p.Cblks;
+        int tap = 0, cb = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, kABytes + b_bytes);
+          const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
+          const uint32_t a_dst = smem_base + s * stage_bytes;
+          if (p.stride2)
+            tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
+          else
+            tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
+          const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
+          bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+          if (++cb == p.Cblks) { cb = 0; ++tap; }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    {
-      // the whole warp walks the loop (converged); one elected lane issues.  instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
-      const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
-      const uint64_t bdesc0 = make_sw128_desc(smem_base + kABytes);          // B image of stage 0 (hi rows then lo rows)
-      const uint32_t stage_units = stage_bytes >> 4, lo_units = (uint32_t)(N * 128) >> 4;
-      const bool paired = (N <= 64);
-      int s = 0, t = 0, g = 0;
-      uint32_t ph = 0, pht = 0;
+    // ===================================================================== MMA issuer (whole warp converged, one elected lane issues)
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
+    const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
+    const uint64_t bdesc0 = make_sw128_desc(smem_base + kABytes);          // B image of stage 0 (hi rows then lo rows)
+    const uint32_t stage_units = stage_bytes >> 4;
+    int s = 0, t = 0;
+    uint32_t ph = 0, pht = 0;
+    for (int cls = 0; cls < ncls; ++cls) {
+      const int nkb = p.taps[cls].n * p.Cblks;
+      int g = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(bar_full + 8 * s, ph);                        // weight image landed (async proxy -> visible)
         mbar_wait(bar_afull + 8 * t, pht);                      // converters filled TMEM A slot t
@@ -262,29 +260,19 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const uint64_t dhi0 = bdesc0 + (uint64_t)(s * stage_units);
         const uint32_t a_hi = tmem_base + aoff + t * 64;
         const uint32_t a_lo = a_hi + 32;
-        const uint32_t first = (i >= p.G) ? 1u : 0u;            // accumulator g already holds a partial sum?
+        const uint32_t first = (i >= p.G) ? 1u : 0u;            // accumulator pair g already holds a partial sum of this class?
         if (elect_one()) {
-        if (p.debug & 2) {
-        } else if (paired) {
-          const uint32_t d_pair = tmem_base + g * 2 * N;
+          if (!(p.debug & 2)) {
+            const uint32_t d_pair = tmem_base + g * 2 * N;      // [main_g | corr_g]
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {                         // K = 8 tf32 per instruction -> 32 bytes (2 x 16 B) along the row
-            mma_tf32_ts(d_pair, a_hi + j * 8, dhi0 + 2 * j, idesc2N, first | (j != 0));
-            mma_tf32_ts(d_pair + N, a_lo + j * 8, dhi0 + 2 * j, idescN, 1u);
+            for (int j = 0; j < 4; ++j) {                       // K = 8 tf32 per instruction -> 32 bytes (2 x 16 B) along the row
+              mma_tf32_ts(d_pair, a_hi + j * 8, dhi0 + 2 * j, idesc2N, first | (j != 0));
+              mma_tf32_ts(d_pair + N, a_lo + j * 8, dhi0 + 2 * j, idescN, 1u);
+            }
           }
-        } else {
-          const uint32_t d_main = tmem_base + g * N;
-          const uint32_t d_corr = tmem_base + p.G * N;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mma_tf32_ts(d_corr, a_lo + j * 8, dhi0 + 2 * j, idescN, (i | j) != 0);
-            mma_tf32_ts(d_corr, a_hi + j * 8, dhi0 + lo_units + 2 * j, idescN, 1u);
-            mma_tf32_ts(d_main, a_hi + j * 8, dhi0 + 2 * j, idescN, first | (j != 0));
-          }
-        }
-        tc_commit(bar_empty + 8 * s);                           // smem stage reusable once these MMAs retire
-        tc_commit(bar_aempty + 8 * t);                          // TMEM A slot reusable
-        if (i == nkb - 1) tc_commit(bar_acc);                   // accumulators complete
+          tc_commit(bar_empty + 8 * s);                         // smem stage reusable once these MMAs retire
+          tc_commit(bar_aempty + 8 * t);                        // TMEM A slot reusable
+          if (i == nkb - 1) tc_commit(bar_acc);                 // accumulators of this class complete
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
@@ -293,103 +281,98 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== converters, then epilogue
+    // ===================================================================== converters, then this class's epilogue
     const int row = threadIdx.x - 128;                          // tile row == TMEM lane
     const int q = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    {
-      int s = 0, t = 0;
-      uint32_t ph = 0, pht = 0;
-      const uint32_t swz = (uint32_t)(row & 7);
-      for (int i = 0; i < nkb; ++i) {
-        mbar_wait(bar_full + 8 * s, ph);
-        const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
-        uint32_t hi[32], lo[32];
-        if (p.debug & 1) {
-          mbar_wait(bar_aempty + 8 * t, pht ^ 1);
-          mbar_arrive(bar_afull + 8 * t);
-          if (++s == S) { s = 0; ph ^= 1; }
-          if (++t == NS) { t = 0; pht ^= 1; }
-          continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {                           // 16-byte chunk j of this row sits at (j ^ (row & 7))
-          const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
-          const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
-            hi[4 * j + e] = h;
-            lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
-          }
-        }
-        mbar_wait(bar_aempty + 8 * t, pht ^ 1);
-        tc_fence_after();
-        const uint32_t a_slot = lane_base + aoff + t * 64;
-        tmem_st32(a_slot, hi);
-        tmem_st32(a_slot + 32, lo);
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_afull + 8 * t);
-        if (++s == S) { s = 0; ph ^= 1; }
-        if (++t == NS) { t = 0; pht ^= 1; }
-      }
-    }
-
-    // ---- epilogue: accumulators -> (z, a) -> smem transpose -> coalesced rows
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    // output pixel of THIS thread's row (shuffled to the storing lanes below)
+    const uint32_t swz = (uint32_t)(row & 7);
     const int tw = row & (p.TW - 1);
     const int th = (row >> p.lgTW) & (p.TH - 1);
     const int tb = row >> (p.lgTW + p.lgTH);
     const int b = b0 + tb;
-    const long long my_off = (b < p.B)
-        ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
-        : -1;
     const int ldw = N + 4;
-    // two staging buffers (z, a) of 32 x (N+4) floats per warp inside the now idle pipeline stages:
-    // ONE pass over TMEM yields both outputs
-    float* stg_z = reinterpret_cast<float*>(smem_gen) + (size_t)q * 32 * ldw;
-    float* stg_a = stg_z + 4 * 32 * ldw;
-    const int lanes_per_row = N / 4;                    // float4 lanes covering one output row
+    float* stg = stg_base + (size_t)q * 32 * ldw;               // this warp's 32 x (N+4) staging rows
+    const int lanes_per_row = N / 4;                            // float4 lanes covering one output row
     const int rows_per_it = 32 / lanes_per_row;
-    if (!(p.debug & 8)) {
-      for (int c0 = 0; c0 < N; c0 += 32) {
-        uint32_t v[32], u[32];
-        tmem_ld32(lane_base + c0, v);
-        for (int k = 1; k < p.nacc; ++k) {
-          tmem_ld32(lane_base + k * N + c0, u);
-          tmem_wait_ld();
+    int s = 0, t = 0;
+    uint32_t ph = 0, pht = 0;
+    for (int cls = 0; cls < ncls; ++cls) {
+      const TapSet& ts = p.taps[cls];
+      const int nkb = ts.n * p.Cblks;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(bar_full + 8 * s, ph);
+        if (p.debug & 1) {
+          mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+          mbar_arrive(bar_afull + 8 * t);
+        } else {
+          const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
+          uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+          for (int j = 0; j < 8; ++j) {                         // 16-byte chunk j of this row sits at (j ^ (row & 7))
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
+              hi[4 * j + e] = h;
+              lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+            }
+          }
+          mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+          tc_fence_after();
+          const uint32_t a_slot = lane_base + aoff + t * 64;
+          tmem_st32(a_slot, hi);
+          tmem_st32(a_slot + 32, lo);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_afull + 8 * t);
         }
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++t == NS) { t = 0; pht ^= 1; }
+      }
+
+      // ---- epilogue of this class: accumulators -> z, a -> smem transpose -> coalesced rows.  The next class's MMAs
+      //      cannot start before these warps convert its first k-block, i.e. after the TMEM reads below completed.
+      mbar_wait(bar_acc, (uint32_t)(cls & 1));
+      tc_fence_after();
+      if (p.debug & 8) continue;
+      const long long my_off = (b < p.B)
+          ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
+          : -1;
+      uint32_t v[32], u[32];                                    // N == 32 on this path: one 32-column chunk
+      tmem_ld32(lane_base, v);
+      for (int k = 1; k < p.nacc; ++k) {
+        tmem_ld32(lane_base + k * N, u);
         tmem_wait_ld();
 #pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {                    // z then a from the SAME registers, one staging buffer
+        float* out = pass == 0 ? p.z_out : p.a_out;
+        if (!out) continue;
+#pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          float zz[4], aa[4];
+          float o[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int n = c0 + j + e;
-            zz[e] = __uint_as_float(v[j + e]) + epi[n];
-            aa[e] = uad_act(epi[N + n] * zz[e] + epi[2 * N + n], p.act, p.alpha);
+            const float z = __uint_as_float(v[j + e]) + epi[j + e];
+            o[e] = pass == 0 ? z : uad_act(epi[N + j + e] * z + epi[2 * N + j + e], p.act, p.alpha);
           }
-          if (p.z_out) *reinterpret_cast<float4*>(stg_z + lane * ldw + c0 + j) = make_float4(zz[0], zz[1], zz[2], zz[3]);
-          if (p.a_out) *reinterpret_cast<float4*>(stg_a + lane * ldw + c0 + j) = make_float4(aa[0], aa[1], aa[2], aa[3]);
+          *reinterpret_cast<float4*>(stg + lane * ldw + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
+        __syncwarp();
+        if (!(p.debug & 4))
+          for (int rr = 0; rr < 32; rr += rows_per_it) {
+            const int r = rr + lane / lanes_per_row;
+            const int c = (lane % lanes_per_row) * 4;
+            const long long off = __shfl_sync(0xffffffffu, my_off, r);
+            if (off >= 0) *reinterpret_cast<float4*>(out + off + c) = *reinterpret_cast<const float4*>(stg + r * ldw + c);
+          }
+        __syncwarp();
       }
-      __syncwarp();
-      if (!(p.debug & 4))
-        for (int rr = 0; rr < 32; rr += rows_per_it) {
-          const int r = rr + lane / lanes_per_row;
-          const int c = (lane % lanes_per_row) * 4;
-          const long long off = __shfl_sync(0xffffffffu, my_off, r);
-          if (off >= 0) {
-            if (p.z_out) *reinterpret_cast<float4*>(p.z_out + off + c) = *reinterpret_cast<const float4*>(stg_z + r * ldw + c);
-            if (p.a_out) *reinterpret_cast<float4*>(p.a_out + off + c) = *reinterpret_cast<const float4*>(stg_a + r * ldw + c);
-          }
-        }
-      __syncwarp();
     }
   }
 
@@ -1073,22 +1056,21 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   UAD_REQUIRE(cr == CUDA_SUCCESS, "gather_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
   const size_t stage_bytes = kABytes + 2u * N * 128u;
-  if (N < 64) {
-    // ---- non-persistent variant: (tile, class) per CTA, TMEM sized for 2 CTAs per SM where possible
+  if (N == 32) {
+    // ---- N = 32 variant: one tile (all classes) per CTA, TMEM / smem sized for 2 CTAs per SM where possible
     p.acc_bufs = 1;
     const int acc_cols = p.nacc * N;
     p.tmem_cols = (acc_cols + 128 <= 256) ? 256 : 512;
     p.nslots = (p.tmem_cols - acc_cols) / 64;
     if (p.nslots > 4) p.nslots = 4;
-    p.stages = 4;
-    const size_t smem_np = 1024 + p.stages * stage_bytes + 256 + 3 * N * sizeof(float) + 64;
+    p.stages = 3;
+    const size_t smem_np = 1024 + p.stages * stage_bytes + 256 + 3 * N * sizeof(float) + 4 * 32 * (size_t)(N + 4) * sizeof(float) + 64;
     static bool attr_np = false;
     if (!attr_np) {
       UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_np, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_np = true;
     }
-    dim3 grid_np(p.tiles_w * p.tiles_h * tiles_b, nclasses);
-    gather_gemm_tc_np<<<grid_np, 256, smem_np, st>>>(tmap, p);
+    gather_gemm_tc_np<<<p.tiles_w * p.tiles_h * tiles_b, 256, smem_np, st>>>(tmap, p);
     UAD_LAUNCH_CHECK("gather_gemm_tc_np");
     return 0;
   }
