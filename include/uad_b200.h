@@ -145,6 +145,14 @@ int uad_dropout_mask(float* mask, size_t n, float rate, uint64_t seed, uint64_t 
 /* offset_dev (nullable): device counter added to `offset`, advanced with uad_counter_add (CUDA-graph friendly) */
 int uad_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream);
 
+/* ---- LayerNormalization(axis=[1,2]) + activation (models/customlayers.py:22,30,35 with use_batchnorm=False; f-AnoGAN G / D):
+ * mean / variance over (H,W) per (sample, channel), gamma / beta [H*W], y = act((x-mean)/sqrt(var+eps)*gamma[hw]+beta[hw]) */
+size_t uad_layernorm_hw_workspace_bytes(int B, int HW, int C);
+int uad_layernorm_hw_fwd(const float* x, const float* gamma_hw, const float* beta_hw, float* y, int B, int HW, int C,
+                         float eps, int act, float alpha, void* ws, size_t ws_bytes, void* stream);
+/* y = act(x) (tanh / sigmoid heads: models/fanogan.py:29,41,46) */
+int uad_activation(const float* x, float* y, size_t n, int act, float alpha, void* stream);
+
 /* ---- residual-map scoring (utils/Evaluation.py:282-291):
  * d = keep_positive ? max(x-xhat,0) : |x-xhat| (fp32); d *= mask (uint8, nullable); if apply_prior and (double)x < prior: d=0 */
 int uad_residual_score(const float* x, const float* xhat, const uint8_t* mask, double prior_quantile, int keep_positive,

@@ -410,3 +410,21 @@ def test_final_bwd_fused_equals_unfused_pair():
     for f, u, ref in ((dzf, dzu, gz), (dgf, dgu, gg), (dbf, dbetau, gb), (dbiasf, dbiasu, gbias), (dwf, dwu, gw), (dbff, dbu, gbf)):
         assert relerr(f.cpu().numpy(), u.cpu().numpy()) < 1e-5
         assert relerr(f.cpu().numpy(), ref.numpy()) < 5 * TOL
+
+
+@pytest.mark.parametrize('B,H,C,act', [(2, 8, 128, 2), (3, 32, 64, 1), (2, 128, 32, 1)])
+def test_layernorm_hw_fwd(B, H, C, act):
+    from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    rng = np.random.default_rng(H + C)
+    x = (rng.standard_normal((B, H, H, C)) * 2 + 0.7).astype(np.float32)
+    g = (1 + 0.3 * rng.standard_normal((H, H))).astype(np.float32)
+    b = (0.3 * rng.standard_normal((H, H))).astype(np.float32)
+    u = naive64.layernorm_hw(x, g.astype(np.float64), b.astype(np.float64))
+    ref = np.where(u > 0, u, (0.3 if act == 1 else 0.0) * u)
+    wsb = abi.lib().uad_layernorm_hw_workspace_bytes(B, H * H, C)
+    ws = workspace(wsb)
+    y = empty(B, H, H, C)
+    call('uad_layernorm_hw_fwd', dptr(x), dptr(g), dptr(b), ptr(y), B, H * H, C, 1e-3, act, 0.3, ptr(ws), wsb, st())
+    sync()
+    assert relerr(y.cpu().numpy(), ref) < TOL

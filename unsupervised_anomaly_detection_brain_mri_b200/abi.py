@@ -46,6 +46,9 @@ SIGNATURES = {
     'uad_randn': (_I, [_P, _Z, _U64, _U64, _P, _P]),
     'uad_dropout_mask': (_I, [_P, _Z, _F, _U64, _U64, _P, _P]),
     'uad_counter_add': (_I, [_P, _U64, _P]),
+    'uad_layernorm_hw_workspace_bytes': (_Z, [_I, _I, _I]),
+    'uad_layernorm_hw_fwd': (_I, [_P] * 4 + [_I] * 3 + [_F, _I, _F, _P, _Z, _P]),
+    'uad_activation': (_I, [_P, _P, _Z, _I, _F, _P]),
     'uad_residual_score': (_I, [_P] * 3 + [_D, _I, _I, _P, _Z, _P]),
     'uad_threshold_counts': (_I, [_P, _P, _Z, C.POINTER(C.c_double), _I, _P, _P, _P]),
     'uad_mul_abs': (_I, [_P] * 3 + [_Z, _P]),

@@ -577,3 +577,114 @@ extern "C" int uad_l1_direct_term(const float* x, const float* xhat, float scale
   UAD_LAUNCH_CHECK("l1_direct_term");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ LayerNormalization([1,2])
+// tf.keras.layers.LayerNormalization(axis=[1,2]) on NHWC (models/customlayers.py:22,30,35 with use_batchnorm=False; f-AnoGAN):
+// mean / variance over (H, W) per (sample, channel); gamma / beta of shape [H, W]; epsilon 1e-3.
+// stage 1: per (b, split) partial sum / sum of squares per channel (fp32, <= 256 terms per thread-level chain)
+__global__ void __launch_bounds__(256) ln_hw_partial_kernel(const float* __restrict__ x, double* __restrict__ partial, int HW, int C,
+                                                            int rows_per_split) {
+  __shared__ float red[2][256];
+  const int tpr = C;                                   // one thread per channel, 256 / C pixel lanes
+  const int c = threadIdx.x % tpr, pl = threadIdx.x / tpr, ppp = 256 / tpr;
+  const int b = blockIdx.x, sp = blockIdx.y;
+  const int r0 = sp * rows_per_split, r1 = min(HW, r0 + rows_per_split);
+  float s = 0.f, ss = 0.f;
+  for (int r = r0 + pl; r < r1; r += ppp) {
+    const float v = x[((size_t)b * HW + r) * C + c];
+    s += v;
+    ss = fmaf(v, v, ss);
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    double a = 0.0, q = 0.0;
+    for (int k = 0; k < ppp; ++k) { a += (double)red[0][k * tpr + threadIdx.x]; q += (double)red[1][k * tpr + threadIdx.x]; }
+    double* dst = partial + (((size_t)b * gridDim.y + sp) * C + threadIdx.x) * 2;
+    dst[0] = a;
+    dst[1] = q;
+  }
+}
+
+// stage 2: mean / rstd per (b, c) in float64, stored as float
+__global__ void ln_hw_stats_kernel(const double* __restrict__ partial, int splits, int HW, int BC_C, int C, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (b, c)
+  if (i >= BC_C) return;
+  const int b = i / C, c = i % C;
+  double a = 0.0, q = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const double* src = partial + (((size_t)b * splits + s) * C + c) * 2;
+    a += src[0];
+    q += src[1];
+  }
+  const double m = a / HW;
+  double var = q / HW - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// stage 3: y = act((x - mean) * rstd * gamma[h,w] + beta[h,w])
+__global__ void ln_hw_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                                   size_t n4, int HW, int C, int act, float alpha) {
+  const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= n4) return;
+  const size_t e = i4 * 4;
+  const int c = (int)(e % C);
+  const size_t pix = e / C;
+  const int hw = (int)(pix % HW);
+  const int b = (int)(pix / HW);
+  const float4 v = *reinterpret_cast<const float4*>(x + e);
+  const float4 m = *reinterpret_cast<const float4*>(mean + (size_t)b * C + c);
+  const float4 r = *reinterpret_cast<const float4*>(rstd + (size_t)b * C + c);
+  const float g = gamma[hw], bt = beta[hw];
+  float4 o;
+  o.x = uad_act((v.x - m.x) * r.x * g + bt, act, alpha);
+  o.y = uad_act((v.y - m.y) * r.y * g + bt, act, alpha);
+  o.z = uad_act((v.z - m.z) * r.z * g + bt, act, alpha);
+  o.w = uad_act((v.w - m.w) * r.w * g + bt, act, alpha);
+  *reinterpret_cast<float4*>(y + e) = o;
+}
+
+static int ln_splits(int HW) { int s = HW / 256; return s < 1 ? 1 : (s > 64 ? 64 : s); }
+
+extern "C" size_t uad_layernorm_hw_workspace_bytes(int B, int HW, int C) {
+  return (size_t)B * ln_splits(HW) * C * 2 * sizeof(double) + 2 * (size_t)B * C * sizeof(float) + 512;
+}
+
+extern "C" int uad_layernorm_hw_fwd(const float* x, const float* gamma_hw, const float* beta_hw, float* y, int B, int HW,
+                                    int C, float eps, int act, float alpha, void* ws, size_t ws_bytes, void* stream) {
+  UAD_REQUIRE(C % 4 == 0 && C <= 256 && 256 % C == 0, "uad_layernorm_hw_fwd: unsupported C=%d", C);
+  UAD_REQUIRE(ws && ws_bytes >= uad_layernorm_hw_workspace_bytes(B, HW, C), "uad_layernorm_hw_fwd: workspace too small");
+  UAD_REQUIRE(((uintptr_t)ws % 16) == 0, "uad_layernorm_hw_fwd: unaligned workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = ln_splits(HW);
+  const int rps = uad_cdiv(HW, splits);
+  double* partial = reinterpret_cast<double*>(ws);
+  size_t poff = ((size_t)B * splits * C * 2 * sizeof(double) + 255) / 256 * 256;
+  float* mean = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + poff);
+  float* rstd = mean + (size_t)B * C;
+  ln_hw_partial_kernel<<<dim3(B, splits), 256, 0, st>>>(x, partial, HW, C, rps);
+  UAD_LAUNCH_CHECK("ln_hw_partial");
+  ln_hw_stats_kernel<<<uad_cdiv(B * C, 128), 128, 0, st>>>(partial, splits, HW, B * C, C, eps, mean, rstd);
+  UAD_LAUNCH_CHECK("ln_hw_stats");
+  const size_t n4 = (size_t)B * HW * C / 4;
+  ln_hw_apply_kernel<<<uad_cdiv(n4, 256), 256, 0, st>>>(x, mean, rstd, gamma_hw, beta_hw, y, n4, HW, C, act, alpha);
+  UAD_LAUNCH_CHECK("ln_hw_apply");
+  return 0;
+}
+
+// y = act(x) elementwise (sigmoid / tanh heads of f-AnoGAN: models/fanogan.py:29,41,46)
+__global__ void activation_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int act, float alpha) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = uad_act(x[i], act, alpha);
+}
+extern "C" int uad_activation(const float* x, float* y, size_t n, int act, float alpha, void* stream) {
+  if (n == 0) return 0;
+  activation_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, act, alpha);
+  UAD_LAUNCH_CHECK("activation");
+  return 0;
+}
