@@ -65,17 +65,22 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict
   }
 }
 
-// stage 2: reduce block partials, finalise dgamma / dbeta / dbias
+// stage 2: reduce block partials, finalise dgamma / dbeta / dbias.  One warp per channel: lanes stride over the block
+// partials (independent loads in flight), fixed-order shuffle tree -> deterministic.
 __global__ void act_bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ gamma,
                                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
                                         int C, float bn_c, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float s_du = 0.f, s_duz = 0.f;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = lane; b < nblocks; b += 32) {
     s_du += partial[(size_t)b * 2 * C + c];
     s_duz += partial[(size_t)b * 2 * C + C + c];
   }
+  s_du = uad_warp_sum(s_du);
+  s_duz = uad_warp_sum(s_duz);
+  if (lane != 0) return;
   const float sc = gamma ? gamma[c] * bn_c : 1.f;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bn_c * s_duz;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + s_du;
@@ -104,7 +109,7 @@ extern "C" int uad_act_bn_bwd(const float* da, const float* z, const float* gamm
   cudaStream_t st = (cudaStream_t)stream;
   act_bn_bwd_kernel<<<nb, 256, 0, st>>>(da, z, gamma, beta, dz, (float*)ws, rows, C, act, alpha, bn_c);
   UAD_LAUNCH_CHECK("act_bn_bwd");
-  act_bn_bwd_final_kernel<<<uad_cdiv(C, 128), 128, 0, st>>>((const float*)ws, nb, gamma, dgamma, dbeta, dbias, C, bn_c,
+  act_bn_bwd_final_kernel<<<uad_cdiv(C * 32, 256), 256, 0, st>>>((const float*)ws, nb, gamma, dgamma, dbeta, dbias, C, bn_c,
                                                             accumulate);
   UAD_LAUNCH_CHECK("act_bn_bwd_final");
   return 0;
@@ -361,24 +366,28 @@ __global__ void final_bwd_fused_reduce_kernel(const float* __restrict__ partial,
                                               float bn_c, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                               float* __restrict__ dbias_prev, float* __restrict__ dw, float* __restrict__ dbias,
                                               int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // one warp per channel (+1 for the bias)
+  const int lane = threadIdx.x & 31;
   const int stride = 3 * Cin + 1;
   if (c < Cin) {
     float a = 0.f, b = 0.f, d = 0.f;
-    for (int k = 0; k < nblocks; ++k) {
+    for (int k = lane; k < nblocks; k += 32) {
       a += partial[(size_t)k * stride + c];
       b += partial[(size_t)k * stride + Cin + c];
       d += partial[(size_t)k * stride + 2 * Cin + c];
     }
+    a = uad_warp_sum(a); b = uad_warp_sum(b); d = uad_warp_sum(d);
+    if (lane != 0) return;
     const float scv = gamma ? gamma[c] * bn_c : 1.f;
     if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bn_c * b;
     if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a;
     if (dbias_prev) dbias_prev[c] = (accumulate ? dbias_prev[c] : 0.f) + scv * a;
     if (dw) dw[c] = (accumulate ? dw[c] : 0.f) + d;
   } else if (c == Cin) {
-    float s = 0.f;
-    for (int k = 0; k < nblocks; ++k) s += partial[(size_t)k * stride + 3 * Cin];
-    if (dbias) dbias[0] = (accumulate ? dbias[0] : 0.f) + s;
+    float sb = 0.f;
+    for (int k = lane; k < nblocks; k += 32) sb += partial[(size_t)k * stride + 3 * Cin];
+    sb = uad_warp_sum(sb);
+    if (lane == 0 && dbias) dbias[0] = (accumulate ? dbias[0] : 0.f) + sb;
   }
 }
 
@@ -396,7 +405,7 @@ extern "C" int uad_final1x1_l1_bwd_fused(const float* z, const float* gamma, con
   cudaStream_t st = (cudaStream_t)stream;
   final_bwd_fused_kernel<<<(int)nb, 256, 0, st>>>(z, gamma, beta, w, x, xhat, scale, dz, (float*)ws, npix, Cin, act, alpha, bn_c);
   UAD_LAUNCH_CHECK("final_bwd_fused");
-  final_bwd_fused_reduce_kernel<<<uad_cdiv(Cin + 1, 128), 128, 0, st>>>((const float*)ws, (int)nb, Cin, gamma, bn_c, dgamma, dbeta,
+  final_bwd_fused_reduce_kernel<<<uad_cdiv((Cin + 1) * 32, 256), 256, 0, st>>>((const float*)ws, (int)nb, Cin, gamma, bn_c, dgamma, dbeta,
                                                                        dbias_prev, dw, dbias, accumulate);
   UAD_LAUNCH_CHECK("final_bwd_fused_reduce");
   return 0;
