@@ -96,6 +96,7 @@ def conv_work(B):
     px = B * S * S
     work['dec_Conv2D_final:final1x1_l1_fwd'] = (2.0 * px * cin, px * cin * 4 + 3 * px * 4)
     work['dec_Conv2D_final:final1x1_l1_bwd'] = (4.0 * px * cin, 2 * px * cin * 4 + 2 * px * 4)
+    work['dec_Conv2D_final:final1x1_l1_bwd_fused'] = (8.0 * px * cin, 2 * px * cin * 4 + 2 * px * 4)   # read z, x, xhat; write dz
     return work
 
 
@@ -279,14 +280,20 @@ def main():
                       'roofline_ms': max(t_hbm, t_tc), 'frac': max(t_hbm, t_tc) / ms if ms > 0 else None,
                       'tflops': fl / ms / 1e9 if ms > 0 else None, 'gbs': by / ms / 1e6 if ms > 0 else None})
     top = table[0]
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    if os.path.isfile(tpath):
+        traffic = json.load(open(tpath)).get(top['op'])       # DRAM bytes per launch from the committed ncu --set full capture
     if top['bound'] == 'hbm':
         roof = {'kernel': top['op'], 'bound': 'hbm', 'achieved': top['gbs'], 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source']}
+                'frac': top['gbs'] / peaks['hbm_gbs'], 'traffic': traffic, 'peak_source': peaks['source']}
     else:
         roof = {'kernel': top['op'], 'bound': 'tensor', 'achieved': top['tflops'], 'peak': peaks['bf16_tflops_sustained'],
-                'unit': 'TFLOP/s', 'frac': top['tflops'] / peaks['bf16_tflops_sustained'], 'traffic': None,
+                'unit': 'TFLOP/s', 'frac': top['tflops'] / peaks['bf16_tflops_sustained'], 'traffic': traffic,
                 'peak_source': peaks['source'] + ' (sustained dense bf16; the kernel computes fp32-accurate 3xTF32)'}
     roof['kernel_ms'] = top['ms']
+    roof['algorithmic_bytes'] = top['mbytes'] * 1e6
+    roof['algorithmic_gflop'] = top['gflop']
     roof['kernel_share_of_step'] = top['ms'] / sum(times.values())
     step_sum = sum(times.values())
     if args.layer_table and rank == 0:
