@@ -167,6 +167,8 @@ int uad_threshold_counts(const float* diff, const uint8_t* label, size_t n, cons
 int uad_mul_abs(const float* l1, const float* gx, float* out, size_t n, void* stream);
 /* gx[i] += -sign(xhat[i]-x[i])*scale : the direct dependence of |xhat-x| on x in d loss_vae/dx (trainers/ceVAE.py:51) */
 int uad_l1_direct_term(const float* x, const float* xhat, float scale, float* gx, size_t n, void* stream);
+/* developer aid: clock64 trace (64 int64, host buffer) of one CTA of the last N=32 tcgen05 launch run with UAD_TC_DEBUG=16 */
+int uad_debug_trace(long long* out64_host);
 /* y = a*x + b*y elementwise (gradient bookkeeping on flat buffers) */
 int uad_axpby(float a, const float* x, float b, float* y, size_t n, void* stream);
 

@@ -53,6 +53,7 @@ SIGNATURES = {
     'uad_threshold_counts': (_I, [_P, _P, _Z, C.POINTER(C.c_double), _I, _P, _P, _P]),
     'uad_mul_abs': (_I, [_P] * 3 + [_Z, _P]),
     'uad_l1_direct_term': (_I, [_P, _P, _F, _P, _Z, _P]),
+    'uad_debug_trace': (_I, [C.POINTER(C.c_longlong)]),
     'uad_axpby': (_I, [_F, _P, _F, _P, _Z, _P]),
 }
 

@@ -31,6 +31,8 @@ constexpr int kABytes = kTileM * kKBlk * 4;  // 16 KB
 // accumulator with truncation (measured: error grows linearly with the number of accumulations), so the large hi*hi
 // stream is spread over G accumulators and the small correction terms never disturb it; the epilogue sums them in
 // registers with round-to-nearest.
+// developer trace (UAD_TC_DEBUG bit 16): clock64 stamps of one steady-state CTA of the N = 32 kernel
+__device__ long long g_tc_trace[64];
 constexpr uint32_t kSpinLimit = 1u << 22;    // bounded mbarrier spins: trap instead of hanging the GPU
 
 struct TcParams {
@@ -207,9 +209,13 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       epi[2 * N + n] = p.beta ? p.beta[n] : 0.f;
     }
   }
+  const bool tracer = (p.debug & 16) && blockIdx.x == gridDim.x / 2 && threadIdx.x == 128;
+  int tri = 0;
+  if (tracer) g_tc_trace[tri++] = clock64();            // [0] entry
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tracer) g_tc_trace[tri++] = clock64();            // [1] prologue done
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -333,8 +339,10 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 
       // ---- epilogue of this class: accumulators -> z, a -> smem transpose -> coalesced rows.  The next class's MMAs
       //      cannot start before these warps convert its first k-block, i.e. after the TMEM reads below completed.
+      if (tracer) g_tc_trace[tri++] = clock64();          // conversions of this class issued
       mbar_wait(bar_acc, (uint32_t)(cls & 1));
       tc_fence_after();
+      if (tracer) g_tc_trace[tri++] = clock64();          // accumulators complete
       if (p.debug & 8) continue;
       const long long my_off = (b < p.B)
           ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
@@ -349,35 +357,63 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       }
       tmem_wait_ld();
       tc_fence_before();
+      if (tracer) g_tc_trace[tri++] = clock64();          // TMEM read done
+      // N == 32 here: 8 float4 lanes cover one 128-byte output row, 4 rows per store instruction, 8 instructions per
+      // warp.  Row offsets are shuffled once; per pass all 8 smem reads are issued before the 8 global stores (a clock64
+      // trace showed the dependent shfl -> LDS -> STG chain per iteration cost ~6000 cycles per class).
+      long long offs[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + (lane >> 3));
+      const int cq = (lane & 7) * 4;
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {                    // z then a from the SAME registers, one staging buffer
         float* out = pass == 0 ? p.z_out : p.a_out;
         if (!out) continue;
+        if (pass == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * ldw + j) =
+                make_float4(__uint_as_float(v[j]) + epi[j], __uint_as_float(v[j + 1]) + epi[j + 1],
+                            __uint_as_float(v[j + 2]) + epi[j + 2], __uint_as_float(v[j + 3]) + epi[j + 3]);
+        } else if (p.act == UAD_ACT_LEAKY) {                    // the hot case: branch-free inner loop
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float z = __uint_as_float(v[j + e]) + epi[j + e];
-            o[e] = pass == 0 ? z : uad_act(epi[N + j + e] * z + epi[2 * N + j + e], p.act, p.alpha);
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float uu = epi[N + j + e] * (__uint_as_float(v[j + e]) + epi[j + e]) + epi[2 * N + j + e];
+              o[e] = uu > 0.f ? uu : p.alpha * uu;
+            }
+            *reinterpret_cast<float4*>(stg + lane * ldw + j) = make_float4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<float4*>(stg + lane * ldw + j) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = uad_act(epi[N + j + e] * (__uint_as_float(v[j + e]) + epi[j + e]) + epi[2 * N + j + e], p.act, p.alpha);
+            *reinterpret_cast<float4*>(stg + lane * ldw + j) = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
         __syncwarp();
-        if (!(p.debug & 4))
-          for (int rr = 0; rr < 32; rr += rows_per_it) {
-            const int r = rr + lane / lanes_per_row;
-            const int c = (lane % lanes_per_row) * 4;
-            const long long off = __shfl_sync(0xffffffffu, my_off, r);
-            if (off >= 0) *reinterpret_cast<float4*>(out + off + c) = *reinterpret_cast<const float4*>(stg + r * ldw + c);
-          }
+        if (!(p.debug & 4)) {
+          float4 vals[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) vals[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * ldw + cq);
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (offs[it] >= 0) *reinterpret_cast<float4*>(out + offs[it] + cq) = vals[it];
+        }
         __syncwarp();
       }
+      if (tracer) g_tc_trace[tri++] = clock64();          // stores of this class issued
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (tracer) { g_tc_trace[tri++] = clock64(); g_tc_trace[63] = tri; }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -642,13 +678,22 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           mbar_arrive(bar_accempty + 8 * buf);
         }
         __syncwarp();
-        for (int rr = 0; rr < 32; rr += rows_per_it) {
-          const int r = rr + lane / lanes_per_row;
+        {
+          // batches of 8 store instructions: all row offsets and smem reads first, then the global stores (the
+          // dependent shfl -> LDS -> STG chain per row group is latency-bound otherwise)
           const int c = (lane % lanes_per_row) * 4;
-          const long long off = __shfl_sync(0xffffffffu, my_off, r);
-          if (off >= 0) {
-            const float4 val = *reinterpret_cast<const float4*>(stg + r * ldw + c);
-            *reinterpret_cast<float4*>(out + off + c) = val;
+          for (int rr = 0; rr < 32; rr += 8 * rows_per_it) {
+            long long offs[8];
+            float4 vals[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = (rr + it * rows_per_it + lane / lanes_per_row) & 31;
+              offs[it] = __shfl_sync(0xffffffffu, my_off, r);
+              vals[it] = *reinterpret_cast<const float4*>(stg + r * ldw + c);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (rr + it * rows_per_it < 32 && offs[it] >= 0) *reinterpret_cast<float4*>(out + offs[it] + c) = vals[it];
           }
         }
         __syncwarp();
@@ -1170,4 +1215,10 @@ int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* 
   wgrad_tc<<<grid, 384, smem, st>>>(tmap_g, tmap_o, p);
   UAD_LAUNCH_CHECK("wgrad_tc");
   return uad_launch_splitk_reduce(p.partial, nchunks, (size_t)w.Mp * Co, out, accumulate, st);
+}
+
+// developer aid: copy the clock64 trace of the last traced gather_gemm_tc_np launch (UAD_TC_DEBUG bit 16)
+extern "C" int uad_debug_trace(long long* out64) {
+  UAD_CUDA(cudaMemcpyFromSymbol(out64, g_tc_trace, sizeof(long long) * 64));
+  return 0;
 }
