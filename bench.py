@@ -240,11 +240,11 @@ def main():
 
     # ---- end to end through the trainer API: host batch -> pinned H2D -> step -> loss D2H, every step
     for i in range(3):
-        model.run_batch(host_batches[i % nb], Phase.TRAIN)
+        model.run_batch(host_batches[i % nb], Phase.TRAIN, prefetch=host_batches[(i + 1) % nb])
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        run = model.run_batch(host_batches[i % nb], Phase.TRAIN)
+    for i in range(args.steps):                 # every step: H2D of a host batch (overlapped look-ahead, as process() does) + loss D2H
+        run = model.run_batch(host_batches[i % nb], Phase.TRAIN, prefetch=host_batches[(i + 1) % nb])
     barrier()
     e2e_s = udist.max_over_ranks(time.perf_counter() - t0, dev)
     clocks = sampler.stop()

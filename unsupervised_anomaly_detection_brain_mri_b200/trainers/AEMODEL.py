@@ -111,11 +111,44 @@ class AEMODEL(DLMODEL, ABC):
         buf.numpy()[...] = arr
         return buf
 
-    def run_batch(self, batch, phase: Phase, batch_ce=None, fetch_maps=False, want_anomaly=False):
+    def _prefetch(self, key, arr):
+        """Start the host->device copy of a FUTURE batch on a side stream (pinned staging, double-buffered) so it overlaps
+        the step that is about to run; run_batch() picks it up by identity of the host array."""
+        if arr is None:
+            return
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._pf = {}
+            self._pf_flip = {}
+        flip = self._pf_flip.get(key, 0)
+        self._pf_flip[key] = flip ^ 1
+        pinned = self._stage((key, flip), arr)
+        dev = self._pinned.get(('dev', key, flip, pinned.shape))
+        if dev is None:
+            dev = torch.empty(pinned.shape, dtype=torch.float32, device=self.device)
+            self._pinned[('dev', key, flip, pinned.shape)] = dev
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            dev.copy_(pinned, non_blocking=True)
+            ev.record()
+        self._pf[key] = (id(arr), dev, ev)
+
+    def _feed(self, key, arr):
+        """Device-side source for this batch: the prefetched copy if one was started for exactly this array, else a
+        pinned host buffer (async H2D on the compute stream)."""
+        pf = getattr(self, '_pf', {}).pop(key, None)
+        if pf is not None and pf[0] == id(arr):
+            torch.cuda.current_stream(self.device).wait_event(pf[2])
+            return pf[1]
+        return self._stage(key, arr)
+
+    def run_batch(self, batch, phase: Phase, batch_ce=None, fetch_maps=False, want_anomaly=False, prefetch=None,
+                  prefetch_ce=None):
         """One ``sess.run`` of the reference's process() loop (AE.py:70-83): feed a host batch, run the step on the GPU,
-        fetch the scalar losses (and, on request, the reconstruction / L1 maps the reference fetches every step)."""
+        fetch the scalar losses (and, on request, the reconstruction / L1 maps the reference fetches every step).
+        ``prefetch`` (optional): the NEXT host batch - its H2D copy is overlapped with this step."""
         eng, cfg = self.engine, self.config
-        eng.set_inputs(self._stage('x', batch), None if batch_ce is None else self._stage('x_ce', batch_ce))
+        eng.set_inputs(self._feed('x', batch), None if batch_ce is None else self._feed('x_ce', batch_ce))
         if phase == Phase.TRAIN:
             eng.train_step(cfg.learningrate, beta1=cfg.beta1, dropout_rate=cfg.dropout_rate, dropout=True,
                            allreduce=self._allreduce, world=self.world, want_anomaly=want_anomaly,
@@ -123,6 +156,8 @@ class AEMODEL(DLMODEL, ABC):
         else:
             eng.draw_noise(False, 0.0)
             eng.forward(training=False, dropout_rate=0.0)
+        self._prefetch('x', prefetch)                 # the GPU is busy with the step: stage the next batch meanwhile
+        self._prefetch('x_ce', prefetch_ce)
         run = dict(eng.losses())                      # device -> host read of the step's scalars
         if fetch_maps:
             run['reconstruction'] = eng.br[0].xhat.cpu().numpy()
@@ -190,15 +225,19 @@ class AEMODEL(DLMODEL, ABC):
         num_batches = dataset.num_batches(self.config.batchsize, set=phase.value)
         every = int(getattr(self.config, 'fetchMapsEvery', 0))      # the reference fetches the full maps EVERY step
         verbose = bool(getattr(self.config, 'verbose', True))
-        for idx in range(0, num_batches):
+        def fetch():
             if self.TWO_INPUTS:
-                batch, _, brainmasks = dataset.next_batch(self.config.batchsize, return_brainmask=True, set=phase.value)
-                batch_ce = self._make_ce_batch(batch, brainmasks, phase)
-            else:
-                batch, _, _ = dataset.next_batch(self.config.batchsize, set=phase.value)
-                batch_ce = None
-            fetch = every > 0 and idx % every == 0
-            run = self.run_batch(batch, phase, batch_ce=batch_ce, fetch_maps=fetch, want_anomaly=self.TWO_INPUTS)
+                b, _, masks = dataset.next_batch(self.config.batchsize, return_brainmask=True, set=phase.value)
+                return b, self._make_ce_batch(b, masks, phase)
+            b, _, _ = dataset.next_batch(self.config.batchsize, set=phase.value)
+            return b, None
+        nxt = fetch() if num_batches > 0 else None
+        for idx in range(0, num_batches):
+            batch, batch_ce = nxt
+            nxt = fetch() if idx + 1 < num_batches else (None, None)      # look-ahead: its H2D overlaps this step
+            fetch_m = every > 0 and idx % every == 0
+            run = self.run_batch(batch, phase, batch_ce=batch_ce, fetch_maps=fetch_m, want_anomaly=self.TWO_INPUTS,
+                                 prefetch=nxt[0], prefetch_ce=nxt[1])
             if verbose:
                 print(f'Epoch ({phase.value}): [{epoch:2d}] [{idx:4d}/{num_batches:4d}] loss: {run["loss"]:.8f}')
             update_log_dicts(*trainer_utils.get_summary_dict(batch, run, visualization_keys), scalars, visuals)

@@ -24,17 +24,18 @@ class ceVAE(AEMODEL):
         # ceVAE.py:105: masked batch only in TRAIN, the plain batch otherwise
         return retrieve_masked_batch(batch, brainmasks) if phase == Phase.TRAIN else batch
 
-    def run_batch(self, batch, phase, batch_ce=None, fetch_maps=False, want_anomaly=True):
+    def run_batch(self, batch, phase, batch_ce=None, fetch_maps=False, want_anomaly=True, prefetch=None, prefetch_ce=None):
         if batch_ce is None:
             batch_ce = batch
         if phase != Phase.TRAIN:
             eng = self.engine
-            eng.set_inputs(self._stage('x', batch), self._stage('x_ce', batch_ce))
+            eng.set_inputs(self._feed('x', batch), self._feed('x_ce', batch_ce))
             eng.draw_noise(False, 0.0)
             eng.forward(training=False, dropout_rate=0.0)
             import numpy as np
             return {k: np.float32(v) for k, v in eng.losses().items()}
-        run = super().run_batch(batch, phase, batch_ce=batch_ce, fetch_maps=fetch_maps, want_anomaly=True)
+        run = super().run_batch(batch, phase, batch_ce=batch_ce, fetch_maps=fetch_maps, want_anomaly=True, prefetch=prefetch,
+                                prefetch_ce=prefetch_ce)
         if fetch_maps:
             run['reconstruction_ce'] = self.engine.br[1].xhat.cpu().numpy()
             run['anomaly'] = self.engine.anomaly.cpu().numpy()
