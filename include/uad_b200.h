@@ -172,6 +172,50 @@ int uad_debug_trace(long long* out64_host);
 /* y = a*x + b*y elementwise (gradient bookkeeping on flat buffers) */
 int uad_axpby(float a, const float* x, float b, float* y, size_t n, void* stream);
 
+
+/* ================= f-AnoGAN training (trainers/fAnoGAN.py:50-77; models/fanogan.py:50-82) =================
+ * LayerNormalization([1,2]) with saved statistics, its backward, forward-mode derivative and joint backward: the pieces
+ * of the WGAN-GP critic step (tf.gradients(d_hat, x_hat) differentiated again w.r.t. the critic weights, fAnoGAN.py:55-58).
+ * stats = {mean[B*C], rstd[B*C]}; jstats = {mean(xdot)[B*C], mean(xdot*xhat)[B*C]}.  C in {8..128} power of two. */
+size_t uad_layernorm_hw_train_workspace_bytes(int B, int HW, int C);
+int uad_layernorm_hw_fwd_train(const float* x, const float* gamma_hw, const float* beta_hw, float* y, float* stats, int B,
+                               int HW, int C, float eps, int act, float alpha, void* ws, size_t ws_bytes, void* stream);
+/* dy = gradient w.r.t. the activated output; dx may alias dy; dgamma/dbeta [HW] nullable (both or neither) */
+int uad_layernorm_hw_bwd(const float* dy, const float* x, const float* stats, const float* gamma_hw, const float* beta_hw,
+                         float* dx, float* dgamma, float* dbeta, int B, int HW, int C, int act, float alpha, int accumulate,
+                         void* ws, size_t ws_bytes, void* stream);
+/* ydot = d/de act(LN(x + e*xdot)) at e = 0 */
+int uad_layernorm_hw_jvp(const float* xdot, const float* x, const float* stats, const float* gamma_hw, const float* beta_hw,
+                         float* ydot, float* jstats, int B, int HW, int C, int act, float alpha, void* ws, size_t ws_bytes,
+                         void* stream);
+/* reverse of the pair (y, ydot): adjoints dydot and dy (nullable) -> dxdot, dx, dgamma/dbeta */
+int uad_layernorm_hw_bwd2(const float* dydot, const float* dy, const float* x, const float* xdot, const float* stats,
+                          const float* jstats, const float* gamma_hw, const float* beta_hw, float* dxdot, float* dx,
+                          float* dgamma, float* dbeta, int B, int HW, int C, int act, float alpha, int accumulate, void* ws,
+                          size_t ws_bytes, void* stream);
+/* backward of the final 1x1 conv (Cin -> 1) for an arbitrary incoming gradient dxhat [B*HW] (generator head, fanogan.py:41,46) */
+int uad_final1x1_bwd(const float* a, const float* w, const float* dxhat, float* da, float* dw, float* dbias, int B, int HW,
+                     int Cin, int accumulate, void* ws, size_t ws_bytes, void* stream);
+/* dx = dy * act'(u), u the pre-activation (sigmoid / tanh heads) */
+int uad_activation_bwd(const float* dy, const float* u, float* dx, size_t n, int act, float alpha, void* stream);
+int uad_fill(float* y, float v, size_t n, void* stream);
+/* uniform [0,1) Philox stream (tf.random_uniform, fanogan.py:67) */
+int uad_uniform(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
+/* x_hat = x + alpha[b]*(x_gen - x)  (fanogan.py:67-69) */
+int uad_interpolate(const float* x, const float* x_gen, const float* alpha, float* out, int B, size_t per_sample,
+                    void* stream);
+/* deterministic reductions: out = scale*sum(x);  loss = loss_scale*sum((a-b)^2) and grad_a = grad_scale*(a-b) (nullable) */
+size_t uad_reduce_workspace_bytes(void);
+int uad_sum_scaled(const float* x, size_t n, double scale, float* out_dev, void* ws, size_t ws_bytes, void* stream);
+int uad_mse(const float* a, const float* b, size_t n, float grad_scale, float* grad_a, double loss_scale, float* loss_out_dev,
+            void* ws, size_t ws_bytes, void* stream);
+/* gradient penalty (fAnoGAN.py:56-57): slope[b,j] = sqrt(sum_h ddx[b,h,j]^2) (axis 1 ONLY, as the reference),
+ * gp = scale*mean((slope-1)^2), u = d gp / d ddx.  ddx [B,H,WC]; ws >= B*WC floats. */
+int uad_gradient_penalty(const float* ddx, int B, int H, int WC, float scale, float* u_out, float* gp_out_dev, void* ws,
+                         size_t ws_bytes, void* stream);
+/* l1 = |xhat - x| (nullable), rec[b] = sum_hw l1 (nullable)  (fAnoGAN.py:65-66) */
+int uad_l1_map(const float* x, const float* xhat, float* l1, float* rec, int B, int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,9 +1,9 @@
-"""fp32/fp64 torch-CPU restatement of the f-AnoGAN graph's FORWARD paths (oracle; PARITY UNPINNED; TEST INFRASTRUCTURE ONLY).
+"""fp32/fp64 torch-CPU restatement of the f-AnoGAN graph and its three train ops (oracle; PARITY UNPINNED; TEST INFRASTRUCTURE ONLY).
 
 Restates models/fanogan.py:11-84: Encoder (unified encoder with BatchNorm + 1x1 conv + Dense + dropout + tanh), Generator
 (Dense + dropout + 1x1 conv + unified decoder with LayerNormalization([1,2]) + sigmoid) and the Discriminator feature
-stack (unified encoder with LayerNormalization) + Dense(1) on the channel axis.  The WGAN-GP training
-graph (trainers/fAnoGAN.py:50-77) is NOT restated yet."""
+stack (unified encoder with LayerNormalization) + Dense(1) on the channel axis, and the WGAN-GP / izi_f
+losses and optimiser steps of trainers/fAnoGAN.py:50-77 (torch autograd, create_graph=True for the gradient penalty)."""
 from __future__ import annotations
 
 import math
@@ -149,3 +149,98 @@ def discriminate(P, x, dtype=torch.float32):
 def reconstruct(P, x, dtype=torch.float32):
     """trainers/fAnoGAN.py:220-239: x_enc = sigmoid(G(E(x))) with dropout off."""
     return generate(P, encode(P, x, dtype=dtype), dtype=dtype)
+
+
+# --------------------------------------------------------------------------- training graph (trainers/fAnoGAN.py:50-77)
+SCOPES = ('Encoder', 'Generator', 'Discriminator')
+
+
+def as_leaves(P, dtype=torch.float32):
+    """{name: ndarray} -> {name: leaf tensor requiring grad} (shared by every sub-graph of one step)."""
+    return OrderedDict((k, _t(v, dtype).clone().requires_grad_(True)) for k, v in P.items())
+
+
+def gradient_penalty(P, x_hat, scale, dtype=torch.float32):
+    """fAnoGAN.py:55-57: ddx = d sum(d_hat) / d x_hat; slopes = sqrt(sum(ddx^2, axis=1)) (axis 1 = H only, as written);
+    gp = mean((slopes-1)^2)*scale.  x_hat is NHWC and must require grad."""
+    _, d_hat = discriminate(P, x_hat, dtype)
+    ddx = torch.autograd.grad(d_hat.sum(), x_hat, create_graph=True)[0]
+    slopes = torch.sqrt((ddx * ddx).sum(dim=1))
+    return ((slopes - 1.0) ** 2).mean() * scale, ddx
+
+
+def wgan_graph(P, x, z, alpha, mask_enc=None, mask_gen_z=None, mask_gen_enc=None, dropout_rate=0.0, training=True, scale=10.0,
+               kappa=1.0, dtype=torch.float32, want=('gen', 'disc', 'enc')):
+    """All losses of fAnoGAN.train (fAnoGAN.py:50-66) on one feed.  P: dict of tensors (as_leaves).  alpha [B,1] is the
+    tf.random_uniform draw of fanogan.py:67; the three masks are the three Dropout applications (Encoder z, dec_dense(z),
+    dec_dense(z_enc))."""
+    x = _t(x, dtype)
+    out = {}
+    if 'gen' in want or 'disc' in want:
+        x_ = generate(P, z, mask_gen_z, dropout_rate, training, dtype)
+        _, d_ = discriminate(P, x_, dtype)
+        out['x_'] = x_
+        out['disc_fake'] = d_.mean()
+        out['gen_loss'] = -out['disc_fake']
+    if 'disc' in want:
+        _, d = discriminate(P, x, dtype)
+        out['disc_real'] = d.mean()
+        a = _t(alpha, dtype).reshape(-1, 1, 1, 1)
+        x_hat = (x + a * (x_.detach() - x)).requires_grad_(True)        # only the critic weights receive this gradient
+        # (the generator path into x_hat carries gradient in TF too, but disc_loss is minimised w.r.t. dis_vars only)
+        gp, ddx = gradient_penalty(P, x_hat, scale, dtype)
+        out['x_hat'], out['ddx'], out['gp'] = x_hat, ddx, gp
+        out['disc_loss'] = out['disc_fake'] - out['disc_real'] + gp
+    if 'enc' in want:
+        z_enc = encode(P, x, mask_enc, dropout_rate, training, dtype)
+        x_enc = generate(P, z_enc, mask_gen_enc, dropout_rate, training, dtype)
+        f_enc, _ = discriminate(P, x_enc, dtype)
+        f_real, _ = discriminate(P, x, dtype)
+        out['z_enc'], out['x_enc'] = z_enc, x_enc
+        out['loss_img'] = ((x - x_enc) ** 2).mean(dim=(1, 2, 3)).mean()
+        out['loss_fts'] = ((f_enc - f_real) ** 2).mean(dim=(1, 2, 3)).mean()
+        out['enc_loss'] = out['loss_img'] + kappa * out['loss_fts']
+        out['L1'] = (x_enc - x).abs()
+        out['reconstructionLoss'] = out['L1'].sum(dim=(1, 2, 3)).mean()
+    return out
+
+
+def scope_grads(P, loss, scope):
+    """tf.train.Optimizer.minimize(loss, var_list=[v for v in t_vars if scope in v.name]) gradients (fAnoGAN.py:71-77)."""
+    names = [k for k in P if k.startswith(scope + '/')]
+    gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True, retain_graph=True)
+    return OrderedDict((k, torch.zeros_like(P[k]) if g is None else g.detach()) for k, g in zip(names, gs))
+
+
+class WganTrainer:
+    """The three AdamOptimizer(lr, beta1=0.5, beta2=0.9) train ops of fAnoGAN.py:75-77 with their own step counters."""
+
+    def __init__(self, P, lr=1e-4, dropout_rate=0.0, scale=10.0, kappa=1.0, dtype=torch.float32):
+        self.dtype, self.lr, self.rate, self.scale, self.kappa = dtype, lr, dropout_rate, scale, kappa
+        self.P = OrderedDict((k, _t(v, dtype).clone()) for k, v in P.items())
+        self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in self.P.items())
+        self.v = OrderedDict((k, torch.zeros_like(v)) for k, v in self.P.items())
+        self.t = {s: 0 for s in SCOPES}
+
+    def _apply(self, scope, G):
+        from .tf_graph_cpu import adam_tf
+        self.t[scope] += 1
+        names = list(G)
+        Pn, mn, vn = adam_tf(OrderedDict((k, self.P[k]) for k in names), G, OrderedDict((k, self.m[k]) for k in names),
+                             OrderedDict((k, self.v[k]) for k in names), self.t[scope], self.lr, 0.5, 0.9, 1e-8)
+        for k in names:
+            self.P[k], self.m[k], self.v[k] = Pn[k].detach(), mn[k], vn[k]
+
+    def step(self, which, x, z, alpha=None, mask_enc=None, mask_gen=None, training=True):
+        """which in {'gen','disc','enc'}: one sess.run of optim_gen / optim_dis / optim_enc.  Returns (losses, grads)."""
+        L = as_leaves(self.P, self.dtype)
+        kw = dict(dropout_rate=self.rate, training=training, scale=self.scale, kappa=self.kappa, dtype=self.dtype, want=(which,))
+        if which == 'enc':
+            out = wgan_graph(L, x, z, alpha, mask_enc=mask_enc, mask_gen_enc=mask_gen, **kw)
+            loss, scope = out['enc_loss'], 'Encoder'
+        else:
+            out = wgan_graph(L, x, z, alpha, mask_gen_z=mask_gen, **kw)
+            loss, scope = (out['gen_loss'], 'Generator') if which == 'gen' else (out['disc_loss'], 'Discriminator')
+        G = scope_grads(L, loss, scope)
+        self._apply(scope, G)
+        return {k: v.detach() for k, v in out.items()}, G

@@ -55,6 +55,21 @@ SIGNATURES = {
     'uad_l1_direct_term': (_I, [_P, _P, _F, _P, _Z, _P]),
     'uad_debug_trace': (_I, [C.POINTER(C.c_longlong)]),
     'uad_axpby': (_I, [_F, _P, _F, _P, _Z, _P]),
+    'uad_layernorm_hw_train_workspace_bytes': (_Z, [_I, _I, _I]),
+    'uad_layernorm_hw_fwd_train': (_I, [_P] * 5 + [_I] * 3 + [_F, _I, _F, _P, _Z, _P]),
+    'uad_layernorm_hw_bwd': (_I, [_P] * 8 + [_I] * 4 + [_F, _I, _P, _Z, _P]),
+    'uad_layernorm_hw_jvp': (_I, [_P] * 7 + [_I] * 4 + [_F, _P, _Z, _P]),
+    'uad_layernorm_hw_bwd2': (_I, [_P] * 12 + [_I] * 4 + [_F, _I, _P, _Z, _P]),
+    'uad_final1x1_bwd': (_I, [_P] * 6 + [_I] * 4 + [_P, _Z, _P]),
+    'uad_activation_bwd': (_I, [_P] * 3 + [_Z, _I, _F, _P]),
+    'uad_fill': (_I, [_P, _F, _Z, _P]),
+    'uad_uniform': (_I, [_P, _Z, _U64, _U64, _P, _P]),
+    'uad_interpolate': (_I, [_P] * 4 + [_I, _Z, _P]),
+    'uad_reduce_workspace_bytes': (_Z, []),
+    'uad_sum_scaled': (_I, [_P, _Z, _D, _P, _P, _Z, _P]),
+    'uad_mse': (_I, [_P, _P, _Z, _F, _P, _D, _P, _P, _Z, _P]),
+    'uad_gradient_penalty': (_I, [_P] + [_I] * 3 + [_F, _P, _P, _P, _Z, _P]),
+    'uad_l1_map': (_I, [_P] * 4 + [_I, _I, _P]),
 }
 
 

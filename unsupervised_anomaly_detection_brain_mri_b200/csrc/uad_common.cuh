@@ -28,6 +28,10 @@ static inline int uad_cdiv(long long a, long long b) { return (int)((a + b - 1) 
 
 #define UAD_NUM_SMS 148
 
+// y = act((x - mean) * rstd * gamma[hw] + beta[hw])  (uad_elementwise.cu; shared with the training forward in uad_fanogan.cu)
+int uad_layernorm_hw_apply(const float* x, const float* mean, const float* rstd, const float* gamma_hw, const float* beta_hw,
+                           float* y, int B, int HW, int C, int act, float alpha, cudaStream_t st);
+
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ float uad_act(float u, int act, float alpha) {
   switch (act) {

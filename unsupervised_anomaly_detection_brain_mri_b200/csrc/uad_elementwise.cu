@@ -251,8 +251,13 @@ __global__ void __launch_bounds__(256) final1x1_l1_bwd_kernel(const float* __res
   const float4 w4 = *reinterpret_cast<const float4*>(w + lp * 4);
   float sw[4] = {0.f, 0.f, 0.f, 0.f}, sb = 0.f;
   for (size_t pix = (size_t)blockIdx.x * ppp + pl; pix < npix; pix += (size_t)gridDim.x * ppp) {
-    const float e = xhat[pix] - x[pix];
-    const float g = (e > 0.f ? scale : (e < 0.f ? -scale : 0.f));
+    float g;
+    if (xhat) {
+      const float e = xhat[pix] - x[pix];
+      g = (e > 0.f ? scale : (e < 0.f ? -scale : 0.f));
+    } else {
+      g = x[pix] * scale;                      // direct mode: x holds the incoming gradient d/dxhat
+    }
     const float4 a4 = __ldg(reinterpret_cast<const float4*>(a + pix * Cin + lp * 4));
     sw[0] += g * a4.x; sw[1] += g * a4.y; sw[2] += g * a4.z; sw[3] += g * a4.w;
     if (lp == 0) sb += g;
@@ -296,6 +301,24 @@ extern "C" int uad_final1x1_l1_bwd(const float* a, const float* w, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   final1x1_l1_bwd_kernel<<<(int)nb, 256, 0, st>>>(a, w, x, xhat, scale, da, (float*)ws, npix, Cin);
   UAD_LAUNCH_CHECK("final1x1_l1_bwd");
+  final_bwd_reduce_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)nb, Cin, dw, dbias, accumulate);
+  UAD_LAUNCH_CHECK("final_bwd_reduce");
+  return 0;
+}
+
+// backward of the final 1x1 conv alone for an arbitrary incoming gradient dxhat [B*HW] (f-AnoGAN generator, whose head is
+// sigmoid(conv1x1) rather than an L1 residual: models/fanogan.py:41,46)
+extern "C" int uad_final1x1_bwd(const float* a, const float* w, const float* dxhat, float* da, float* dw, float* dbias, int B,
+                                int HW, int Cin, int accumulate, void* ws, size_t ws_bytes, void* stream) {
+  UAD_REQUIRE(Cin % 4 == 0 && uad_is_pow2(Cin / 4) && Cin <= 128, "uad_final1x1_bwd: unsupported Cin=%d", Cin);
+  const size_t npix = (size_t)B * HW;
+  const int ppp = 256 / (Cin / 4);
+  long long nb = (npix + ppp - 1) / ppp;
+  if (nb > 4 * UAD_NUM_SMS) nb = 4 * UAD_NUM_SMS;
+  UAD_REQUIRE(ws && ws_bytes >= (size_t)nb * (Cin + 1) * sizeof(float), "uad_final1x1_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  final1x1_l1_bwd_kernel<<<(int)nb, 256, 0, st>>>(a, w, dxhat, nullptr, 1.f, da, (float*)ws, npix, Cin);
+  UAD_LAUNCH_CHECK("final1x1_bwd");
   final_bwd_reduce_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)nb, Cin, dw, dbias, accumulate);
   UAD_LAUNCH_CHECK("final_bwd_reduce");
   return 0;
@@ -544,6 +567,25 @@ extern "C" int uad_dropout_mask(float* mask, size_t n, float rate, uint64_t seed
   return 0;
 }
 
+// uniform [0,1) stream (tf.random_uniform of the WGAN-GP interpolation, models/fanogan.py:67)
+__global__ void uniform_kernel(float* __restrict__ out, size_t n, uint64_t seed, uint64_t offset,
+                               const uint64_t* __restrict__ offset_dev) {
+  if (offset_dev) offset += *offset_dev;
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= n) return;
+  const uint64_t ctr = offset + q;
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0xa1fau, 0u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int j = 0; j < 4 && q * 4 + j < n; ++j) out[q * 4 + j] = (float)(c[j] >> 8) * 5.9604644775390625e-08f;
+}
+
+extern "C" int uad_uniform(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream) {
+  if (n == 0) return 0;
+  uniform_kernel<<<uad_cdiv((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, offset_dev);
+  UAD_LAUNCH_CHECK("uniform");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ helpers
 __global__ void counter_add_kernel(uint64_t* c, uint64_t inc) { *c += inc; }
 extern "C" int uad_counter_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
@@ -656,6 +698,14 @@ __global__ void ln_hw_apply_kernel(const float* __restrict__ x, const float* __r
   o.z = uad_act((v.z - m.z) * r.z * g + bt, act, alpha);
   o.w = uad_act((v.w - m.w) * r.w * g + bt, act, alpha);
   *reinterpret_cast<float4*>(y + e) = o;
+}
+
+int uad_layernorm_hw_apply(const float* x, const float* mean, const float* rstd, const float* gamma_hw, const float* beta_hw,
+                           float* y, int B, int HW, int C, int act, float alpha, cudaStream_t st) {
+  const size_t n4 = (size_t)B * HW * C / 4;
+  ln_hw_apply_kernel<<<uad_cdiv(n4, 256), 256, 0, st>>>(x, mean, rstd, gamma_hw, beta_hw, y, n4, HW, C, act, alpha);
+  UAD_LAUNCH_CHECK("ln_hw_apply");
+  return 0;
 }
 
 static int ln_splits(int HW) { int s = HW / 256; return s < 1 ? 1 : (s > 64 ? 64 : s); }

@@ -1,10 +1,9 @@
-"""f-AnoGAN trainer surface (mirror of reference trainers/fAnoGAN.py).
+"""f-AnoGAN trainer (mirror of reference trainers/fAnoGAN.py) on the CUDA engine.
 
-Implemented on the device this round: construction, checkpoint save/load, ``reconstruct`` (x_enc = sigmoid(G(E(x))),
-fAnoGAN.py:220-239) and therefore residual scoring through utils/Evaluation.  NOT yet implemented: ``train`` - the
-WGAN-GP critic step needs the gradient of ||d D(x_hat)/d x_hat|| w.r.t. the critic weights, i.e. a double backward
-through conv / LayerNormalization (fAnoGAN.py:55-57); it raises NotImplementedError rather than training something
-that is not the reference's objective."""
+``train``: phase A = WGAN-GP (per mini-batch one generator step and ``d_iters = 5`` critic steps, fAnoGAN.py:87-140), phase B
+= encoder training (izi_f) with validation and early stopping (fAnoGAN.py:142-210); ``reconstruct`` = sigmoid(G(E(x)))
+(fAnoGAN.py:220-239).  The three optimisers are tf.train.AdamOptimizer(lr, beta1=0.5, beta2=0.9) on the scope-contiguous
+slices of the flat parameter buffer (fAnoGAN.py:71-77)."""
 import os
 from datetime import datetime
 
@@ -46,8 +45,10 @@ class fAnoGAN(DLMODEL):
         torch.cuda.set_device(self.device)
         g = self.graph
         self.engine = FanoganEngine(g.S, g.C, g.zDim, g.res, batch=cfg.batchsize, device=self.device, math_mode=self.math_mode,
-                                    seed=int(getattr(cfg, 'seed', 1)))
+                                    seed=int(getattr(cfg, 'seed', 1)), kappa=float(cfg.kappa), scale=float(cfg.scale))
         self._eval = {}
+        self.world, self._allreduce = 1, None
+        self.logger = Logger(self.sess, self.logDir, enabled=bool(getattr(cfg, 'useTensorboard', False)))
         self.get_number_of_trainable_params()
         self.saver = self
 
@@ -61,13 +62,104 @@ class fAnoGAN(DLMODEL):
         ok, counter = self.load(self.checkpointDir)
         return counter if ok else 0
 
-    def sample_z(self):
-        return np.random.normal(size=[self.config.batchsize, self.config.zDim])     # float64, as fAnoGAN.py:241-242
+    def sample_z(self, batch_size=None):
+        return np.random.normal(size=[batch_size if batch_size else self.config.batchsize, self.config.zDim])   # fAnoGAN.py:241-242
+
+    def enable_data_parallel(self):
+        """Shard mini-batches over ranks; one all-reduce of the updated scope's gradient slice per train op."""
+        from .. import dist as udist
+        udist.init_from_env()
+        self.world = udist.world_size()
+        if self.world > 1:
+            udist.broadcast_(self.engine.fp.params, src=0)
+            self._allreduce = udist.allreduce_sum_
+
+    def _feed(self, batch):
+        """get_feed_dict (fAnoGAN.py:212-218): x <- batch, z <- sample_z()."""
+        self.engine.set_inputs(np.ascontiguousarray(batch, np.float32))
+        self._z = self.sample_z()
+        self.engine.set_latent(self._z.astype(np.float32))
 
     def train(self, dataset):
-        raise NotImplementedError('f-AnoGAN WGAN-GP training (trainers/fAnoGAN.py:45-210) is not implemented on the B200 path yet: '
-                                  'the gradient penalty needs a double backward through conv / LayerNormalization. '
-                                  'Weights can be loaded with .load(); .reconstruct() and Evaluation.evaluate() run on the device.')
+        from collections import defaultdict
+        from math import inf
+
+        from . import trainer_utils
+        from .AEMODEL import indicate_early_stopping, update_log_dicts
+        cfg, eng = self.config, self.engine
+        eng.kappa, eng.scale = float(cfg.kappa), float(cfg.scale)
+        eng.enable_training()
+        self.variables = list(eng.specs.keys())
+        lr, rate = float(cfg.learningrate), float(cfg.dropout_rate)
+        kw = dict(dropout_rate=rate, dropout=True, allreduce=getattr(self, '_allreduce', None), world=getattr(self, 'world', 1))
+        verbose = bool(getattr(cfg, 'verbose', True))
+        all_losses = bool(getattr(cfg, 'fetchAllLosses', True))
+        best_cost = inf
+        last_improvement = 0
+        last_epoch = self.load_checkpoint()
+
+        for epoch in range(last_epoch, cfg.numEpochs):                    # ---- TRAINING WGAN (fAnoGAN.py:87-140)
+            phase = Phase.TRAIN
+            scalars, visuals = defaultdict(list), []
+            d_iters = 5
+            num_batches = dataset.num_batches(cfg.batchsize, set=phase.value)
+            for idx in range(num_batches):
+                batch, _, _ = dataset.next_batch(cfg.batchsize, set=phase.value)
+                self._feed(batch)
+                run = dict(eng.step_gen(lr, **kw))
+                for _ in range(d_iters):
+                    self._feed(batch)                                     # every sess.run draws a fresh z (fAnoGAN.py:125)
+                    run.update(eng.step_disc(lr, **kw))
+                run['generated'] = eng.x_gen.cpu().numpy()
+                if verbose:
+                    print(f'Epoch ({phase.value} WGAN): [{epoch:2d}] [{idx:4d}/{num_batches:4d}]'
+                          f' gen_loss: {run["gen_loss"]:.8f}, disc_loss: {run["disc_loss"]:.8f}')
+                update_log_dicts(*trainer_utils.get_summary_dict(batch, run, visualization_keys=['generated']), scalars, visuals)
+            self.log_to_tensorboard(epoch, scalars, visuals, phase, name='wgan_x')
+            last_epoch += 1
+            self.save(self.checkpointDir, last_epoch)
+
+        def encoder_pass(phase, epoch):
+            scalars, visuals = defaultdict(list), []
+            num_batches = dataset.num_batches(cfg.batchsize, set=phase.value)
+            for idx in range(num_batches):
+                batch, _, _ = dataset.next_batch(cfg.batchsize, set=phase.value)
+                self._feed(batch)
+                train = phase == Phase.TRAIN
+                run = dict(eng.step_enc(lr, dropout_rate=rate, dropout=train, allreduce=kw['allreduce'], world=kw['world'],
+                                        train=train))
+                run['reconstruction'] = eng.x_enc.cpu().numpy()
+                run['L1'] = eng.l1.cpu().numpy()
+                if train:
+                    run['z_enc'], run['z'] = eng.z_enc.cpu().numpy(), self._z
+                if all_losses:                                            # **self.losses (fAnoGAN.py:157,190)
+                    run.update(eng.wgan_scalars(rate, dropout=train))
+                if verbose:
+                    tag = f'{phase.value} Encoder' if train else phase.value
+                    print(f'Epoch ({tag}): [{epoch:2d}] [{idx:4d}/{num_batches:4d}]  reconstructionLoss: '
+                          f'{run["reconstructionLoss"]:.8f}')
+                update_log_dicts(*trainer_utils.get_summary_dict(batch, run), scalars, visuals)
+            self.log_to_tensorboard(epoch, scalars, visuals, phase)
+            return scalars
+
+        for epoch in range(last_epoch, 2 * cfg.numEpochs):                # ---- TRAINING / VALIDATION Encoder (:142-210)
+            encoder_pass(Phase.TRAIN, epoch)
+            last_epoch += 1
+            self.save(self.checkpointDir, last_epoch)
+            val = encoder_pass(Phase.VAL, epoch)
+            best_cost, last_improvement, stop = indicate_early_stopping(val['reconstructionLoss'], best_cost, last_improvement)
+            if stop:
+                print('Early stopping was triggered due to no improvement over the last 5 epochs')
+                break
+
+    def log_to_tensorboard(self, epoch, scalars, visuals, phase, name='x'):
+        for key in scalars.keys():
+            scalars[key] = np.mean(scalars[key])
+        vis = [v for v in visuals if v is not None]
+        summaries = dict(scalars)
+        if vis:
+            summaries[name] = np.vstack(vis)[:50]
+        self.logger.summarize(epoch, phase=phase, summaries_dict=summaries)
 
     def _engine_for(self, n):
         if n not in self._eval:
