@@ -13,8 +13,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .tf_graph_cpu import (LRELU_ALPHA, _glorot, _t, bn_frozen, conv1x1, conv2d_same_s2, conv2dT_same_s2, dropout, lrelu,
-                           stack_plan)
+from .tf_graph_cpu import LRELU_ALPHA, _glorot, _t, bn_frozen, conv1x1, conv2d_same_s2, conv2dT_same_s2, dropout, stack_plan
 
 LN_EPS = 1e-3
 
@@ -90,19 +89,30 @@ def layernorm_hw(x, gamma, beta):
     return (x - mu) / torch.sqrt(var + LN_EPS) * gamma[None, None] + beta[None, None]
 
 
+def _act(n, sign, alpha):
+    """LeakyReLU(alpha) / ReLU (alpha = 0).  ``sign`` (optional, NHWC {0,1} array = "pre-activation > 0") pins the sub-gradient
+    branch per element: the derivative jumps at 0, so two fp32 evaluations whose pre-activations differ by round-off near 0
+    legitimately pick different branches; parity tests pass the implementation's pattern (same device as l1_sign in
+    tf_graph_cpu.losses)."""
+    if sign is None:
+        return F.leaky_relu(n, alpha) if alpha else F.relu(n)
+    m = torch.as_tensor(np.asarray(sign)).to(torch.bool).permute(0, 3, 1, 2)
+    return torch.where(m, n, alpha * n)
+
+
 def _names(P, scope, stem):
     return [k[:-len('/gamma')] for k in P if k.startswith(scope + '/' + stem) and k.endswith('/gamma')]
 
 
-def encode(P, x, mask=None, dropout_rate=0.0, training=False, dtype=torch.float32):
+def encode(P, x, mask=None, dropout_rate=0.0, training=False, dtype=torch.float32, signs=None):
     """fanogan.py:15-29 -> z_enc [B, zDim]."""
     P = {k: _t(v, dtype) for k, v in P.items()}
     h = _t(x, dtype).permute(0, 3, 1, 2)
     bns = _names(P, 'Encoder', 'batch_normalization')
     i = 0
     while f'Encoder/enc_conv2D_{i}/kernel' in P:
-        h = lrelu(bn_frozen(conv2d_same_s2(h, P[f'Encoder/enc_conv2D_{i}/kernel'], P[f'Encoder/enc_conv2D_{i}/bias']),
-                            P[bns[i] + '/gamma'], P[bns[i] + '/beta']))
+        h = _act(bn_frozen(conv2d_same_s2(h, P[f'Encoder/enc_conv2D_{i}/kernel'], P[f'Encoder/enc_conv2D_{i}/bias']),
+                           P[bns[i] + '/gamma'], P[bns[i] + '/beta']), None if signs is None else signs[i], LRELU_ALPHA)
         i += 1
     h = conv1x1(h, P['Encoder/conv2d/kernel'], P['Encoder/conv2d/bias'])
     flat = h.permute(0, 2, 3, 1).reshape(h.shape[0], -1)
@@ -111,7 +121,7 @@ def encode(P, x, mask=None, dropout_rate=0.0, training=False, dtype=torch.float3
     return torch.tanh(dropout(z, m, dropout_rate, training))
 
 
-def generate(P, z, mask=None, dropout_rate=0.0, training=False, dtype=torch.float32):
+def generate(P, z, mask=None, dropout_rate=0.0, training=False, dtype=torch.float32, signs=None):
     """fanogan.py:33-46 -> sigmoid(G(z)) as NHWC."""
     P = {k: _t(v, dtype) for k, v in P.items()}
     z = _t(z, dtype)
@@ -122,17 +132,18 @@ def generate(P, z, mask=None, dropout_rate=0.0, training=False, dtype=torch.floa
     res = int(round(math.sqrt(d.shape[1] // cb)))
     h = d.reshape(d.shape[0], res, res, cb).permute(0, 3, 1, 2)
     h = conv1x1(h, P['Generator/conv2d_1/kernel'], P['Generator/conv2d_1/bias'])
-    h = F.relu(layernorm_hw(h, P[lns[0] + '/gamma'], P[lns[0] + '/beta']))
+    h = _act(layernorm_hw(h, P[lns[0] + '/gamma'], P[lns[0] + '/beta']), None if signs is None else signs[0], 0.0)
     i = 0
     while f'Generator/dec_Conv2DT_{i}/kernel' in P:
         h = conv2dT_same_s2(h, P[f'Generator/dec_Conv2DT_{i}/kernel'], P[f'Generator/dec_Conv2DT_{i}/bias'])
-        h = lrelu(layernorm_hw(h, P[lns[i + 1] + '/gamma'], P[lns[i + 1] + '/beta']))
+        h = _act(layernorm_hw(h, P[lns[i + 1] + '/gamma'], P[lns[i + 1] + '/beta']), None if signs is None else signs[i + 1],
+                 LRELU_ALPHA)
         i += 1
     h = conv1x1(h, P['Generator/dec_Conv2D_final/kernel'], P['Generator/dec_Conv2D_final/bias'])
     return torch.sigmoid(h).permute(0, 2, 3, 1)
 
 
-def discriminate(P, x, dtype=torch.float32):
+def discriminate(P, x, dtype=torch.float32, signs=None):
     """fanogan.py:50-58 -> (features [B,r,r,128] NHWC, critic [B,r,r,1]: Dense(1) acts on the channel axis)."""
     P = {k: _t(v, dtype) for k, v in P.items()}
     h = _t(x, dtype).permute(0, 3, 1, 2)
@@ -140,7 +151,7 @@ def discriminate(P, x, dtype=torch.float32):
     i = 0
     while f'Discriminator/enc_conv2D_{i}/kernel' in P:
         h = conv2d_same_s2(h, P[f'Discriminator/enc_conv2D_{i}/kernel'], P[f'Discriminator/enc_conv2D_{i}/bias'])
-        h = lrelu(layernorm_hw(h, P[lns[i] + '/gamma'], P[lns[i] + '/beta']))
+        h = _act(layernorm_hw(h, P[lns[i] + '/gamma'], P[lns[i] + '/beta']), None if signs is None else signs[i], LRELU_ALPHA)
         i += 1
     f = h.permute(0, 2, 3, 1)
     return f, f @ P['Discriminator/dense_2/kernel'] + P['Discriminator/dense_2/bias']
@@ -160,42 +171,43 @@ def as_leaves(P, dtype=torch.float32):
     return OrderedDict((k, _t(v, dtype).clone().requires_grad_(True)) for k, v in P.items())
 
 
-def gradient_penalty(P, x_hat, scale, dtype=torch.float32):
+def gradient_penalty(P, x_hat, scale, dtype=torch.float32, signs=None):
     """fAnoGAN.py:55-57: ddx = d sum(d_hat) / d x_hat; slopes = sqrt(sum(ddx^2, axis=1)) (axis 1 = H only, as written);
     gp = mean((slopes-1)^2)*scale.  x_hat is NHWC and must require grad."""
-    _, d_hat = discriminate(P, x_hat, dtype)
+    _, d_hat = discriminate(P, x_hat, dtype, signs)
     ddx = torch.autograd.grad(d_hat.sum(), x_hat, create_graph=True)[0]
     slopes = torch.sqrt((ddx * ddx).sum(dim=1))
     return ((slopes - 1.0) ** 2).mean() * scale, ddx
 
 
 def wgan_graph(P, x, z, alpha, mask_enc=None, mask_gen_z=None, mask_gen_enc=None, dropout_rate=0.0, training=True, scale=10.0,
-               kappa=1.0, dtype=torch.float32, want=('gen', 'disc', 'enc')):
+               kappa=1.0, dtype=torch.float32, want=('gen', 'disc', 'enc'), signs=None):
     """All losses of fAnoGAN.train (fAnoGAN.py:50-66) on one feed.  P: dict of tensors (as_leaves).  alpha [B,1] is the
     tf.random_uniform draw of fanogan.py:67; the three masks are the three Dropout applications (Encoder z, dec_dense(z),
-    dec_dense(z_enc))."""
+    dec_dense(z_enc)).  signs: optional {'gen_z','d_fake','d_real','d_hat','enc','gen_enc','d_enc'} -> per-level sign patterns."""
     x = _t(x, dtype)
     out = {}
+    sg = (signs or {}).get
     if 'gen' in want or 'disc' in want:
-        x_ = generate(P, z, mask_gen_z, dropout_rate, training, dtype)
-        _, d_ = discriminate(P, x_, dtype)
+        x_ = generate(P, z, mask_gen_z, dropout_rate, training, dtype, sg('gen_z'))
+        _, d_ = discriminate(P, x_, dtype, sg('d_fake'))
         out['x_'] = x_
         out['disc_fake'] = d_.mean()
         out['gen_loss'] = -out['disc_fake']
     if 'disc' in want:
-        _, d = discriminate(P, x, dtype)
+        _, d = discriminate(P, x, dtype, sg('d_real'))
         out['disc_real'] = d.mean()
         a = _t(alpha, dtype).reshape(-1, 1, 1, 1)
         x_hat = (x + a * (x_.detach() - x)).requires_grad_(True)        # only the critic weights receive this gradient
         # (the generator path into x_hat carries gradient in TF too, but disc_loss is minimised w.r.t. dis_vars only)
-        gp, ddx = gradient_penalty(P, x_hat, scale, dtype)
+        gp, ddx = gradient_penalty(P, x_hat, scale, dtype, sg('d_hat'))
         out['x_hat'], out['ddx'], out['gp'] = x_hat, ddx, gp
         out['disc_loss'] = out['disc_fake'] - out['disc_real'] + gp
     if 'enc' in want:
-        z_enc = encode(P, x, mask_enc, dropout_rate, training, dtype)
-        x_enc = generate(P, z_enc, mask_gen_enc, dropout_rate, training, dtype)
-        f_enc, _ = discriminate(P, x_enc, dtype)
-        f_real, _ = discriminate(P, x, dtype)
+        z_enc = encode(P, x, mask_enc, dropout_rate, training, dtype, sg('enc'))
+        x_enc = generate(P, z_enc, mask_gen_enc, dropout_rate, training, dtype, sg('gen_enc'))
+        f_enc, _ = discriminate(P, x_enc, dtype, sg('d_enc'))
+        f_real, _ = discriminate(P, x, dtype, sg('d_real'))
         out['z_enc'], out['x_enc'] = z_enc, x_enc
         out['loss_img'] = ((x - x_enc) ** 2).mean(dim=(1, 2, 3)).mean()
         out['loss_fts'] = ((f_enc - f_real) ** 2).mean(dim=(1, 2, 3)).mean()
@@ -231,10 +243,11 @@ class WganTrainer:
         for k in names:
             self.P[k], self.m[k], self.v[k] = Pn[k].detach(), mn[k], vn[k]
 
-    def step(self, which, x, z, alpha=None, mask_enc=None, mask_gen=None, training=True):
+    def step(self, which, x, z, alpha=None, mask_enc=None, mask_gen=None, training=True, signs=None):
         """which in {'gen','disc','enc'}: one sess.run of optim_gen / optim_dis / optim_enc.  Returns (losses, grads)."""
         L = as_leaves(self.P, self.dtype)
-        kw = dict(dropout_rate=self.rate, training=training, scale=self.scale, kappa=self.kappa, dtype=self.dtype, want=(which,))
+        kw = dict(dropout_rate=self.rate, training=training, scale=self.scale, kappa=self.kappa, dtype=self.dtype, want=(which,),
+                  signs=signs)
         if which == 'enc':
             out = wgan_graph(L, x, z, alpha, mask_enc=mask_enc, mask_gen_enc=mask_gen, **kw)
             loss, scope = out['enc_loss'], 'Encoder'

@@ -1,7 +1,7 @@
 """f-AnoGAN training path (trainers/fAnoGAN.py:50-77): the LayerNormalization backward / JVP / joint-backward kernels, the
 WGAN-GP element-wise kernels, and the three train ops (optim_gen / optim_dis / optim_enc) of the CUDA engine against the
 oracle's torch-autograd restatement (double backward for the gradient penalty).  Tolerance 1e-4 relative on forward
-quantities and losses; gradients 5e-4 (3xTF32 products summed over up to 1e6 terms), as in test_gpu_step."""
+quantities and losses; gradients 1e-4 with the LeakyReLU / ReLU sub-gradient branches pinned to the implementation's sign pattern (FO._act)."""
 import numpy as np
 import pytest
 import torch
@@ -14,7 +14,7 @@ from oracle import tf_graph_cpu as O  # noqa: E402
 from gpu_util import dptr  # noqa: E402
 
 TOL = 1e-4
-GTOL = 5e-4
+GTOL = 1e-4
 
 
 def _rel(a, b):
@@ -63,7 +63,7 @@ def test_layernorm_train_kernels(B, H, C, act):
     ty = _ln_ref(tz, tg, tb, act)
     assert _rel(y.cpu().numpy(), ty.detach().numpy()) < TOL
     # backward
-    gz, gg, gb = torch.autograd.grad((ty * torch.from_numpy(dy).double()).sum(), (tz, tg, tb))
+    gz, gg, gb = torch.autograd.grad((ty * torch.from_numpy(dy).double()).sum(), (tz, tg, tb), retain_graph=True)
     dx = torch.empty_like(dz_)
     dgam = torch.zeros(HW, device='cuda')
     dbet = torch.zeros(HW, device='cuda')
@@ -117,7 +117,7 @@ def test_wgan_elementwise_kernels():
     t = torch.from_numpy(ddx).double().requires_grad_(True)
     gp = ((torch.sqrt((t * t).sum(dim=1)) - 1.0) ** 2).mean() * 10.0
     gu, = torch.autograd.grad(gp, t)
-    assert abs(float(out[0]) - float(gp)) / float(gp) < 1e-6
+    assert abs(float(out[0]) - float(gp.detach())) / float(gp.detach()) < 1e-6
     assert _rel(u.cpu().numpy(), gu.numpy()) < 1e-5
     # sums / mse
     a = rng.standard_normal(100003).astype(np.float32)
@@ -135,11 +135,11 @@ def test_wgan_elementwise_kernels():
     xg = rng.random((B, H, W, 1), dtype=np.float32)
     al = rng.random(B, dtype=np.float32)
     o = torch.empty(B, H, W, 1, device='cuda')
-    abi.call('uad_interpolate', dptr(_dev(x)), dptr(_dev(xg)), dptr(_dev(al)), o.data_ptr(), B, H * W, st)
+    abi.call('uad_interpolate', dptr(x), dptr(xg), dptr(al), o.data_ptr(), B, H * W, st)
     assert np.allclose(o.cpu().numpy(), x + al[:, None, None, None] * (xg - x), rtol=0, atol=1e-7)
     l1 = torch.empty(B, H, W, 1, device='cuda')
     rec = torch.empty(B, device='cuda')
-    abi.call('uad_l1_map', dptr(_dev(x)), dptr(_dev(xg)), l1.data_ptr(), rec.data_ptr(), B, H * W, st)
+    abi.call('uad_l1_map', dptr(x), dptr(xg), l1.data_ptr(), rec.data_ptr(), B, H * W, st)
     assert np.array_equal(l1.cpu().numpy(), np.abs(xg - x))
     assert _rel(rec.cpu().numpy(), np.abs(xg.astype(np.float64) - x).sum(axis=(1, 2, 3))) < 1e-6
     for act, f in ((3, lambda t: torch.sigmoid(t)), (4, lambda t: torch.tanh(t))):
@@ -161,22 +161,55 @@ def test_wgan_elementwise_kernels():
     dact = torch.empty(npx, Cin, device='cuda')
     dw = torch.empty(Cin, device='cuda')
     dbias = torch.empty(1, device='cuda')
-    abi.call('uad_final1x1_bwd', dptr(_dev(act_in)), dptr(_dev(w)), dptr(_dev(dxh)), dact.data_ptr(), dw.data_ptr(), dbias.data_ptr(),
+    abi.call('uad_final1x1_bwd', dptr(act_in), dptr(w), dptr(dxh), dact.data_ptr(), dw.data_ptr(), dbias.data_ptr(),
              B, H * W, Cin, 0, ws.data_ptr(), wsb, st)
     assert np.allclose(dact.cpu().numpy(), dxh[:, None] * w[None, :], rtol=1e-6, atol=1e-7)
     assert _rel(dw.cpu().numpy(), act_in.astype(np.float64).T @ dxh) < 1e-5
     assert abs(float(dbias) - dxh.astype(np.float64).sum()) < 1e-3
 
 
-def _feed(S, B, rate, seed=21):
+def _feed(S, B, rate, flat, seed=21):
     rng = np.random.default_rng(seed)
     x = O.synthetic_slices(B, S, seed=seed)
     z = rng.standard_normal((B, 128)).astype(np.float32)
     alpha = rng.random((B, 1), dtype=np.float32)
-    flat = 64 * 16
     m_enc = (rng.uniform(size=(B, 128)) >= rate).astype(np.float32)
     m_gen = (rng.uniform(size=(B, flat)) >= rate).astype(np.float32)
     return x, z, alpha, m_enc, m_gen
+
+
+def _signs(eng, which, rate):
+    """Activation sign patterns of the implementation's own forward passes (deterministic, so identical to the ones the train
+    op computes): the oracle differentiates with the same sub-gradient branch at LeakyReLU / ReLU kinks (see FO._act)."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    keep = 1.0 / (1.0 - rate)
+
+    def pat(ts):
+        return [(t > 0).cpu().numpy() for t in ts]
+
+    def critic(x_dev):
+        eng._critic_forward(eng.pass1, x_dev, critic=False)
+        return pat(eng.pass1.a)
+
+    sg = {}
+    if which in ('gen', 'disc'):
+        eng.generate(eng.z_in, eng.mask_gen, keep, out=eng.x_gen)
+        sg['gen_z'] = pat([eng.ar] + eng.gen_a)
+        sg['d_fake'] = critic(eng.x_gen)
+    if which == 'disc':
+        sg['d_real'] = critic(eng.x)
+        abi.call('uad_interpolate', eng.x.data_ptr(), eng.x_gen.data_ptr(), eng.alpha.data_ptr(), eng.x_hat.data_ptr(), eng.B,
+                 eng.S * eng.S, torch.cuda.current_stream().cuda_stream)
+        sg['d_hat'] = critic(eng.x_hat)
+    if which == 'enc':
+        z_enc = eng.encode(eng.mask_enc, keep)
+        sg['enc'] = pat(eng.enc_a)
+        x_enc = eng.generate(z_enc, eng.mask_gen, keep, out=eng.x_enc)
+        sg['gen_enc'] = pat([eng.ar] + eng.gen_a)
+        sg['d_enc'] = critic(x_enc)
+        sg['d_real'] = critic(eng.x)
+    torch.cuda.synchronize()
+    return sg
 
 
 def _compare_grads(eng, G, scope, skip_ln_bias=True):
@@ -202,8 +235,8 @@ def test_fanogan_train_ops_match_oracle(which, S, B, mode):
     from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
     rate, lr = 0.2, 1e-3
     P = FO.perturb(FO.init_params(S, seed=1))
-    x, z, alpha, m_enc, m_gen = _feed(S, B, rate)
     eng = FanoganEngine(S, batch=B, math_mode=mode, kappa=1.0, scale=10.0)
+    x, z, alpha, m_enc, m_gen = _feed(S, B, rate, eng.flat)
     eng.fp.load(P)
     eng.enable_training()
     eng.set_inputs(x)
@@ -212,7 +245,7 @@ def test_fanogan_train_ops_match_oracle(which, S, B, mode):
     eng.mask_enc.copy_(torch.from_numpy(m_enc))
     eng.mask_gen.copy_(torch.from_numpy(m_gen))
     tr = FO.WganTrainer(P, lr=lr, dropout_rate=rate, scale=10.0, kappa=1.0, dtype=torch.float64)
-    out, G = tr.step(which, x, z, alpha, mask_enc=m_enc, mask_gen=m_gen)
+    out, G = tr.step(which, x, z, alpha, mask_enc=m_enc, mask_gen=m_gen, signs=_signs(eng, which, rate))
     step = {'gen': eng.step_gen, 'disc': eng.step_disc, 'enc': eng.step_enc}[which]
     scope = {'gen': 'Generator', 'disc': 'Discriminator', 'enc': 'Encoder'}[which]
     before = eng.fp.to_numpy()
@@ -254,6 +287,8 @@ def test_fanogan_trainer_train_loop(tmp_path):
     config.batchsize = 4
     config.numEpochs = 1
     config.zDim = 128
+    config.numChannels = 1
+    config.intermediateResolutions = [8, 8]
     config.dropout_rate = 0.1
     config.learningrate = 1e-4
     config.checkpointDir = str(tmp_path / 'ckpt')
