@@ -216,6 +216,13 @@ int uad_gradient_penalty(const float* ddx, int B, int H, int WC, float scale, fl
 /* l1 = |xhat - x| (nullable), rec[b] = sum_hw l1 (nullable)  (fAnoGAN.py:65-66) */
 int uad_l1_map(const float* x, const float* xhat, float* l1, float* rec, int B, int HW, void* stream);
 
+/* ================= evaluation post-processing stencils (utils/Evaluation.py:84-89, 108-110, 311-312) =================
+ * brain-mask erosion: scipy.ndimage.binary_erosion(mask, generate_binary_structure(2,1), iterations) per [H,W] slice of
+ * mask [N,H,W] uint8, border_value 0.  iterations in [1,24] (the reference uses 12). */
+int uad_binary_erosion_cross(const uint8_t* mask, uint8_t* out, int N, int H, int W, int iterations, void* stream);
+/* scipy.ndimage.median_filter(volume, (5,5,5)) on a float32 volume [Z,H,W], boundary mode 'reflect'; out != vol */
+int uad_median_filter3d_5(const float* vol, float* out, int Z, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

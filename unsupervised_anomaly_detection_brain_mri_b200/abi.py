@@ -70,6 +70,8 @@ SIGNATURES = {
     'uad_mse': (_I, [_P, _P, _Z, _F, _P, _D, _P, _P, _Z, _P]),
     'uad_gradient_penalty': (_I, [_P] + [_I] * 3 + [_F, _P, _P, _P, _Z, _P]),
     'uad_l1_map': (_I, [_P] * 4 + [_I, _I, _P]),
+    'uad_binary_erosion_cross': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'uad_median_filter3d_5': (_I, [_P, _P, _I, _I, _I, _P]),
 }
 
 

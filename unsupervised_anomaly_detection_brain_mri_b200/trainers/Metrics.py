@@ -76,8 +76,11 @@ class DeviceScorer:
     """Holds the stacked residual volume and labels on the GPU and answers (sum P*G, sum P, sum G) per threshold."""
     MAX_THR = 32
 
-    def __init__(self, predictions, labels, device=None):
+    def __init__(self, predictions, labels, device=None, allreduce=None):
+        """allreduce: in-place sum over ranks of an int64 device tensor (data-parallel scoring shards by volume; the Dice
+        counts are integers, so the reduced result - hence argmax - is identical for every world size)."""
         abi.lib()
+        self.allreduce = allreduce
         device = device or f'cuda:{torch.cuda.current_device()}'
         if isinstance(predictions, torch.Tensor):
             self.diff = predictions.reshape(-1).to(device=device, dtype=torch.float32)
@@ -102,6 +105,8 @@ class DeviceScorer:
             abi.call('uad_threshold_counts', self.diff.data_ptr(), self.label.data_ptr(), self.n, arr, len(chunk),
                      self.counts.data_ptr(), None if (mask_out is None or i > 0) else mask_out.data_ptr(),
                      torch.cuda.current_stream().cuda_stream)
+            if self.allreduce is not None:
+                self.allreduce(self.counts[:3 * len(chunk)])
             c = self.counts[:3 * len(chunk)].cpu().numpy().reshape(-1, 3)
             out.extend((int(a), int(b), int(g)) for a, b, g in c)
         return out

@@ -64,21 +64,44 @@ def filter_3d_connected_components(volume):
 
 def residual_on_device(x, x_rec, mask, prior_quantile, keep_positive, apply_prior, device):
     """[N,H,W] float32 stacks -> float64 sub-volume, via uad_residual_score (bit-exact with Evaluation.py:282-291)."""
+    return score_volume_on_device(x, x_rec, mask, 0, prior_quantile, keep_positive, apply_prior, False, device)
+
+
+def score_volume_on_device(x, x_rec, brainmask, erode_iterations, prior_quantile, keep_positive, apply_prior, median, device):
+    """One patient's residual sub-volume entirely on the GPU (Evaluation.py:282-291 + :311-312):
+    brain-mask erosion (uad_binary_erosion_cross) -> residual / mask / prior (uad_residual_score) -> 5x5x5 median
+    (uad_median_filter3d_5).  All three are bit-exact against the scipy / numpy reference; the float32 result is widened
+    into the float64 ``subvolume`` exactly as the reference's ``subvolume[s] = x_diff`` store does."""
+    st = torch.cuda.current_stream().cuda_stream
     xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(device)
     rd = torch.from_numpy(np.ascontiguousarray(x_rec, np.float32)).to(device)
-    md = None if mask is None else torch.from_numpy(np.ascontiguousarray(mask).astype(np.uint8)).to(device)
+    md = None
+    if brainmask is not None:
+        md = torch.from_numpy(np.ascontiguousarray(np.asarray(brainmask) != 0).astype(np.uint8).reshape(x.shape)).to(device)
+        if erode_iterations:
+            er = torch.empty_like(md)
+            abi.call('uad_binary_erosion_cross', md.data_ptr(), er.data_ptr(), x.shape[0], x.shape[1], x.shape[2],
+                     int(erode_iterations), st)
+            md = er
     out = torch.empty_like(xd)
     abi.call('uad_residual_score', xd.data_ptr(), rd.data_ptr(), None if md is None else md.data_ptr(), float(prior_quantile),
-             int(bool(keep_positive)), int(bool(apply_prior)), out.data_ptr(), xd.numel(),
-             torch.cuda.current_stream().cuda_stream)
+             int(bool(keep_positive)), int(bool(apply_prior)), out.data_ptr(), xd.numel(), st)
+    if median:
+        filt = torch.empty_like(out)
+        abi.call('uad_median_filter3d_5', out.data_ptr(), filt.data_ptr(), x.shape[0], x.shape[1], x.shape[2], st)
+        out = filt
     sub = np.zeros(x.shape, np.float64)
     sub[...] = out.cpu().numpy()
     return sub
 
 
-def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST"):
+def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST", shard=None):
+    """shard = (rank, world): score only this rank's volumes (volumes are the unit: the 5x5x5 median couples neighbouring
+    slices); the integer Dice counts are all-reduced by Metrics.DeviceScorer."""
     eval_dict = get_eval_dictionary()
     patients = [datasetObj.patients[i] for i in datasetObj.get_patient_idx(split=split)]
+    if shard is not None and shard[1] > 1:
+        patients = patients[shard[0]::shard[1]]
     H, W = options['train']['outputHeight'], options['train']['outputWidth']
     device = modelObj.device
     for p, patient in enumerate(patients):
@@ -117,15 +140,14 @@ def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST"):
                 recs.append(results['reconstruction'][..., 0])
             x_rec = recs[0] if num_samples == 1 else np.mean(np.array(recs), axis=0).astype(np.float32)
             eval_dict['reconstructionTimes'] += [(time.time() - _tmp) / max(len(xs), 1)] * len(xs)
-            erode = should(options, "erodeBrainmask")
-            masks = np.stack([erode_brainmask(m) if erode else np.squeeze(m).astype(bool) for m in skulls])
-            subvolume = residual_on_device(x, x_rec, masks, prior_quantile, should(options, "keepOnlyPositiveResiduals"),
-                                           should(options, "applyHyperIntensityPrior"), device)
+            subvolume = score_volume_on_device(x, x_rec, np.stack([np.squeeze(m) for m in skulls]),
+                                               12 if should(options, "erodeBrainmask") else 0, prior_quantile,
+                                               should(options, "keepOnlyPositiveResiduals"),
+                                               should(options, "applyHyperIntensityPrior"), should(options, "medianFiltering"),
+                                               device)
             if num_samples > 1:
                 var = Metrics.combined_predictive_uncertainty(np.array(recs), np.zeros_like(np.array(recs)), axis=0)
                 eval_dict['epistemic_variance'] += list(var)
-            if should(options, "medianFiltering"):
-                subvolume = apply_3d_median_filter(subvolume)
             eval_dict['x'] += list(x[..., None])
             eval_dict['reconstructions'] += list(x_rec[..., None])
             eval_dict['labelmaps'] += segs
@@ -149,15 +171,25 @@ def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST"):
     return eval_dict, patients
 
 
+def _dp_context(model):
+    """(shard, int64 all-reduce) when the trainer runs data-parallel (enable_data_parallel), else (None, None)."""
+    world = int(getattr(model, 'world', 1) or 1)
+    if world <= 1:
+        return None, None
+    from .. import dist as udist
+    return (udist.rank(), world), udist.allreduce_sum_
+
+
 def evaluate(datasetPC, gan, options, epoch='last', description=None):
     """Evaluation.py:372-526 minus file export / plots: returns the evalPC dictionary (also saved as evalPC.npy)."""
     model = gan
     sample_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir, str(description or ''))
     os.makedirs(sample_dir, exist_ok=True)
-    eval_pc, patients = _evaluate(datasetPC, model, sample_dir, options, "TEST")
+    shard, reduce_ = _dp_context(model)
+    eval_pc, patients = _evaluate(datasetPC, model, sample_dir, options, "TEST", shard=shard)
     diffs = eval_pc['diffs']
     labels = (eval_pc['labelmaps'] > 0)
-    scorer = Metrics.DeviceScorer(diffs, labels, device=model.device)
+    scorer = Metrics.DeviceScorer(diffs, labels, device=model.device, allreduce=reduce_)
     flat_d, flat_l = diffs.flatten(), labels.flatten().astype(int)
     if should(options, 'exportROC'):
         eval_pc['AUC'], _fpr, _tpr, _ = Metrics.compute_roc(flat_d, flat_l)
@@ -172,10 +204,20 @@ def evaluate(datasetPC, gan, options, epoch='last', description=None):
     mask = scorer.threshold_mask(threshold).cpu().numpy().astype(bool).reshape(diffs.shape)     # == diffs > threshold, bit-exact
     mask = filter_3d_connected_components(mask.copy())
     eval_pc['thresholded'] = mask
-    eval_pc['DICE'] = Metrics.dice(mask, labels)
-    eval_pc['TPR'] = Metrics.tpr(mask, labels)
-    eval_pc['FPR'] = Metrics.tpr(mask, labels)          # sic: the reference computes FPR with Metrics.tpr (Evaluation.py:490)
-    eval_pc['Precision'] = Metrics.precision(mask, labels)
+    if reduce_ is None:
+        eval_pc['DICE'] = Metrics.dice(mask, labels)
+        eval_pc['TPR'] = Metrics.tpr(mask, labels)
+        eval_pc['FPR'] = Metrics.tpr(mask, labels)      # sic: the reference computes FPR with Metrics.tpr (Evaluation.py:490)
+        eval_pc['Precision'] = Metrics.precision(mask, labels)
+    else:                                               # same formulas on the rank-summed integer counts
+        tp, fp, tn, fn = (int(v) for v in Metrics.confusion_matrix(mask, labels))
+        c = torch.tensor([tp, fp, tn, fn], dtype=torch.int64, device=model.device)
+        reduce_(c)
+        tp, fp, tn, fn = (np.int64(v) for v in c.cpu().numpy())
+        with np.errstate(divide='ignore', invalid='ignore'):
+            eval_pc['DICE'] = (2 * tp) / ((tp + fp) + (tp + fn))
+            eval_pc['TPR'] = eval_pc['FPR'] = tp / (tp + fn)
+            eval_pc['Precision'] = tp / (tp + fp)
     n_per = diffs.shape[0] // max(len(patients), 1)
     eval_pc['perPatientDice'] = [Metrics.dice(mask[i * n_per:(i + 1) * n_per], labels[i * n_per:(i + 1) * n_per])
                                  for i in range(len(patients))]
@@ -190,12 +232,13 @@ def evaluate(datasetPC, gan, options, epoch='last', description=None):
 def determine_threshold_on_labeled_patients(datasets, model, options, description=''):
     """Evaluation.py:529-567: best-Dice threshold over the labelled (validation) patients."""
     diffs, labels = [], []
+    shard, reduce_ = _dp_context(model)
     for ds in datasets:
         sample_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir, str(description))
         os.makedirs(sample_dir, exist_ok=True)
-        ev, _ = _evaluate(ds, model, sample_dir, options, "TEST")
+        ev, _ = _evaluate(ds, model, sample_dir, options, "TEST", shard=shard)
         diffs.append(ev['diffs'])
         labels.append(ev['labelmaps'] > 0)
     diffs, labels = np.concatenate(diffs, 0), np.concatenate(labels, 0)
-    scorer = Metrics.DeviceScorer(diffs, labels, device=model.device)
+    scorer = Metrics.DeviceScorer(diffs, labels, device=model.device, allreduce=reduce_)
     return Metrics.compute_dice_curve_recursive(diffs, labels, granularity=10, scorer=scorer)
