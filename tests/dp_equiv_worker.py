@@ -44,7 +44,63 @@ def main():
         print(f'DP_EQUIV world={world} grad_rel_err={gerr:.3e} max_weight_diff={werr:.3e} frac_diff={frac:.3e}', flush=True)
         assert gerr < 1e-4 and werr <= 2.001 * lr and frac < 5e-3
     torch.distributed.barrier()
+    fanogan_part(rank, world, local)
+    scoring_part(rank, world, local)
+    torch.distributed.barrier()
     torch.distributed.destroy_process_group()
+
+
+def fanogan_part(rank, world, local):
+    """f-AnoGAN critic step (WGAN-GP): each rank on its shard + all-reduce of the Discriminator slice == whole batch."""
+    from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
+    S, Bg, lr = 64, 8, 1e-3
+    x = make_volume(S, Bg, seed=7, lesions=False)[0][..., None]
+    rng = np.random.default_rng(1)
+    z = rng.standard_normal((Bg, 128)).astype(np.float32)
+    alpha = rng.random(Bg, dtype=np.float32)
+
+    def run(batch, xs, zs, al, hook, w):
+        e = FanoganEngine(S, batch=batch, device=f'cuda:{local}', seed=3)
+        e.enable_training()
+        if hook is not None:
+            udist.broadcast_(e.fp.params)
+        e.set_inputs(xs)
+        e.set_latent(zs)
+        e.alpha.copy_(torch.from_numpy(np.ascontiguousarray(al)))
+        res = e.step_disc(lr, dropout_rate=0.0, dropout=False, parity_noise=True, allreduce=hook, world=w)
+        torch.cuda.synchronize()
+        return e, res
+
+    eng, _ = run(Bg // world, udist.shard(x), udist.shard(z), udist.shard(alpha), udist.allreduce_sum_, world)
+    if rank == 0:
+        ref, _ = run(Bg, x, z, alpha, None, 1)
+        lo, hi = ref.fp.subset_ranges('Discriminator/')
+        g_dp = eng.fp.grads[lo:hi].cpu().numpy() / world
+        g_1 = ref.fp.grads[lo:hi].cpu().numpy()
+        gerr = float(np.abs(g_dp - g_1).max() / np.abs(g_1).max())
+        same_rest = bool(torch.equal(eng.fp.params[:lo], ref.fp.params[:lo]))
+        print(f'DP_EQUIV_FANOGAN world={world} grad_rel_err={gerr:.3e} other_scopes_untouched={same_rest}', flush=True)
+        assert gerr < 1e-4 and same_rest
+    torch.distributed.barrier()
+
+
+def scoring_part(rank, world, local):
+    """Volume-sharded Dice counts: int64 all-reduce of (sum P*G, sum P, sum G) == the counts over the whole stack."""
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers import Metrics
+    rng = np.random.default_rng(2)
+    nvol, Z, S = 4, 6, 32
+    diffs = rng.random((nvol, Z, S, S), dtype=np.float32)
+    labels = rng.uniform(size=diffs.shape) < 0.05
+    mine = slice(rank, None, world)
+    sc = Metrics.DeviceScorer(diffs[mine].reshape(-1, S, S), labels[mine].reshape(-1, S, S), device=f'cuda:{local}',
+                              allreduce=udist.allreduce_sum_)
+    best = Metrics.compute_dice_curve_recursive(None, None, granularity=6, scorer=sc)
+    if rank == 0:
+        full = Metrics.DeviceScorer(diffs.reshape(-1, S, S), labels.reshape(-1, S, S), device=f'cuda:{local}')
+        ref = Metrics.compute_dice_curve_recursive(None, None, granularity=6, scorer=full)
+        print(f'DP_EQUIV_SCORING world={world} best={best} ref={ref}', flush=True)
+        assert best == ref
+    torch.distributed.barrier()
 
 
 if __name__ == '__main__':
