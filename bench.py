@@ -71,8 +71,11 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def conv_work(B):
-    """Algorithmic FLOPs / bytes per launch of every conv-family op of the VAE-256 train step."""
+def conv_work(B, keep_preact=False):
+    """Algorithmic FLOPs / bytes per launch of every conv-family op of the VAE-256 train step.
+    A training forward writes ONE copy of each block output (the activation a; the backward recovers the pre-BN value
+    from it) unless the engine runs with keep_preact=True (z and a)."""
+    nout = 2 if keep_preact else 1
     from unsupervised_anomaly_detection_brain_mri_b200.engine import stack_plan
     n, enc, dec = stack_plan(S)
     work = {}
@@ -80,7 +83,7 @@ def conv_work(B):
     for i, co in enumerate(enc):
         fl = 2.0 * B * (s // 2) ** 2 * 25 * cin * co
         xin, xout, w = B * s * s * cin * 4, B * (s // 2) ** 2 * co * 4, 25 * cin * co * 4
-        work[f'enc_conv2D_{i}:conv2d_fwd'] = (fl, xin + 2 * xout + w)
+        work[f'enc_conv2D_{i}:conv2d_fwd'] = (fl, xin + nout * xout + w)
         work[f'enc_conv2D_{i}:conv2d_dgrad'] = (fl, xout + xin + w)
         work[f'enc_conv2D_{i}:conv2d_wgrad'] = (fl, xin + xout + w)
         work[f'enc_conv2D_{i}:act_bn_bwd'] = (0.0, 3 * xout)
@@ -88,7 +91,7 @@ def conv_work(B):
     for i, co in enumerate(dec):
         fl = 2.0 * B * s * s * 25 * cin * co
         xin, xout, w = B * s * s * cin * 4, B * (2 * s) ** 2 * co * 4, 25 * cin * co * 4
-        work[f'dec_Conv2DT_{i}:convT2d_fwd'] = (fl, xin + 2 * xout + w)
+        work[f'dec_Conv2DT_{i}:convT2d_fwd'] = (fl, xin + nout * xout + w)
         work[f'dec_Conv2DT_{i}:convT2d_dgrad'] = (fl, xout + xin + w)
         work[f'dec_Conv2DT_{i}:convT2d_wgrad'] = (fl, xin + xout + w)
         work[f'dec_Conv2DT_{i}:act_bn_bwd'] = (0.0, 3 * xout)
@@ -269,7 +272,7 @@ def main():
     times = {k: float(np.mean(v[1:])) if len(v) > 1 else float(v[0]) for k, v in eng.probe_times_ms().items()}
     eng.probes = None
     peaks = load_peaks()
-    work = conv_work(B)
+    work = conv_work(B, eng.keep_preact)
     table = []
     for k, ms in sorted(times.items(), key=lambda kv: -kv[1]):
         fl, by = work.get(k, (0.0, 0.0))

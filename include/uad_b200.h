@@ -32,6 +32,10 @@ extern "C" {
 #define UAD_ACT_RELU 2    /* tf.keras.layers.ReLU              models/customlayers.py:31    */
 #define UAD_ACT_SIGMOID 3 /* models/fanogan.py:41,46 */
 #define UAD_ACT_TANH 4    /* models/fanogan.py:29    */
+/* OR-ed into `act` of uad_act_bn_bwd / uad_final1x1_l1_bwd_fused: the `z` argument holds the block's OUTPUT
+ * a = act(gamma*bn_c*z+beta) instead of z (piecewise-linear activations only), so a training forward need not write z
+ * at all (z_out = NULL): halves the forward's HBM write volume.  Requires gamma != 0 (dgamma divides by gamma). */
+#define UAD_ACT_FROM_OUTPUT 0x100
 
 #define UAD_OP_CONV_FWD 0
 #define UAD_OP_CONV_DGRAD 1

@@ -233,6 +233,18 @@ def test_act_bn_bwd(rows, C, act):
     assert relerr(dg.cpu().numpy(), gg.numpy()) < TOL
     assert relerr(db.cpu().numpy(), gb.numpy()) < TOL
     assert relerr(dbias.cpu().numpy(), gbias.numpy()) < TOL
+    # UAD_ACT_FROM_OUTPUT: the same gradients from the block's fp32 OUTPUT a (the training forward then never writes z)
+    u32 = (gamma * np.float32(bn_c)) * z + beta
+    a32 = np.where(u32 > 0, u32, (np.float32(0.3) * u32) if act == 1 else np.float32(0)).astype(np.float32)
+    dz2, dg2, db2, dbias2 = empty(rows, C), empty(C), empty(C), empty(C)
+    call('uad_act_bn_bwd', dptr(da), dptr(a32), dptr(gamma), dptr(beta), ptr(dz2), ptr(dg2), ptr(db2), ptr(dbias2),
+         rows, C, act | abi.ACT_FROM_OUTPUT, 0.3, bn_c, 0, ptr(ws), wsb, st())
+    sync()
+    sure = np.abs(u32) > 1e-5                                       # away from the kink both paths take the same branch
+    assert np.array_equal(dz2.cpu().numpy()[sure], dz.cpu().numpy()[sure])
+    assert relerr(db2.cpu().numpy(), gb.numpy()) < TOL
+    assert relerr(dbias2.cpu().numpy(), gbias.numpy()) < TOL
+    assert relerr(dg2.cpu().numpy(), gg.numpy()) < TOL
 
 
 def test_reparam_kl():
@@ -409,6 +421,16 @@ def test_final_bwd_fused_equals_unfused_pair():
     sync()
     for f, u, ref in ((dzf, dzu, gz), (dgf, dgu, gg), (dbf, dbetau, gb), (dbiasf, dbiasu, gbias), (dwf, dwu, gw), (dbff, dbu, gbf)):
         assert relerr(f.cpu().numpy(), u.cpu().numpy()) < 1e-5
+        assert relerr(f.cpu().numpy(), ref.numpy()) < 5 * TOL
+    # UAD_ACT_FROM_OUTPUT: same call fed with the activation a instead of z
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    dza, dga, dba, dbiasa, dwa, dbfa = empty(B, S, S, C), empty(C), empty(C), empty(C), empty(C), empty(1)
+    call('uad_final1x1_l1_bwd_fused', ptr(ad), ptr(gd), ptr(bd), ptr(wd), ptr(xd), ptr(xhd), 1.0 / B, ptr(dza), ptr(dga), ptr(dba),
+         ptr(dbiasa), ptr(dwa), ptr(dbfa), B, S * S, C, 1 | abi.ACT_FROM_OUTPUT, 0.3, bn_c, 0, ptr(ws), 1 << 22, st())
+    sync()
+    sure = np.abs(a_np) > 1e-5
+    assert np.array_equal(dza.cpu().numpy()[sure], dzf.cpu().numpy()[sure])
+    for f, ref in ((dga, gg), (dba, gb), (dbiasa, gbias), (dwa, gw), (dbfa, gbf)):
         assert relerr(f.cpu().numpy(), ref.numpy()) < 5 * TOL
 
 

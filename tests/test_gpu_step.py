@@ -37,16 +37,16 @@ def _noise(arch, B, zDim, flat, rate, seed=3):
     return eps, om, em, emc
 
 
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode,keep_preact', [(0, False), (1, False), (1, True)])
 @pytest.mark.parametrize('arch,S,B', [(O.AE, 128, 16), (O.VAE, 64, 4), (O.VAE, 256, 2), (O.CEVAE, 64, 3)])
-def test_train_step_parity(arch, S, B, mode):
+def test_train_step_parity(arch, S, B, mode, keep_preact):
     from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
     rate, lr = 0.2, 1e-3
     P = O.perturb_params(O.init_params(arch, S, seed=1))
     x = O.synthetic_slices(B, S, seed=1234)
     x_ce = x.copy()
     x_ce[:, S // 4:S // 4 + 20, S // 3:S // 3 + 20] = 0
-    eng = ConvAutoencoderEngine(arch, S, batch=B, math_mode=mode)
+    eng = ConvAutoencoderEngine(arch, S, batch=B, math_mode=mode, keep_preact=keep_preact)
     assert list(eng.specs.keys()) == list(P.keys())
     eng.fp.load(P)
     eps, om, em, emc = _noise(arch, B, 128, eng.flat, rate)

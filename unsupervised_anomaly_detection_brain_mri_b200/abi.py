@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libuad_b200.so')
 
 ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+ACT_FROM_OUTPUT = 0x100   # UAD_ACT_FROM_OUTPUT: backward kernels read the block's output a instead of its pre-BN input z
 OP_CONV_FWD, OP_CONV_DGRAD, OP_CONV_WGRAD, OP_CONVT_FWD, OP_CONVT_DGRAD, OP_CONVT_WGRAD = range(6)
 MATH_FP32_SIMT, MATH_TC_3XTF32, MATH_TC_1XTF32 = 0, 1, 2
 

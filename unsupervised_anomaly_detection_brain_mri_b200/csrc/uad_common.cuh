@@ -54,6 +54,13 @@ __device__ __forceinline__ float uad_act_grad(float u, int act, float alpha) {
   }
 }
 
+// pre-activation u recovered from the OUTPUT a = act(u) of a piecewise-linear activation (UAD_ACT_FROM_OUTPUT mode of the
+// backward kernels).  LeakyReLU: exact up to one rounding, sign(u) == sign(a).  ReLU: u is unknown where a == 0, but the
+// activation gradient there is 0 and every use of u is multiplied by it.
+__device__ __forceinline__ float uad_preact_from_output(float a, int act, float inv_alpha) {
+  return (act == UAD_ACT_LEAKY && !(a > 0.f)) ? a * inv_alpha : a;
+}
+
 __device__ __forceinline__ float uad_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

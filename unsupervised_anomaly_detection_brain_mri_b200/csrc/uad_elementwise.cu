@@ -18,7 +18,12 @@ long long g_uad_launches = 0;
 extern "C" long long uad_launch_count(void) { return g_uad_launches; }
 
 // ------------------------------------------------------------------------------------------------ act + frozen-BN backward
-// stage 1: dz = gamma*bn_c * da * act'(u), per-block partial sums of du and du*z per channel
+// stage 1: dz = gamma*bn_c * da * act'(u), per-block partial sums of du and du*z per channel.
+// FROM_A (act | UAD_ACT_FROM_OUTPUT): the second operand is the block's OUTPUT a = act(u) instead of its pre-BN input z
+// (the forward then never writes z).  For the piecewise-linear activations u is recovered exactly up to one rounding
+// (LeakyReLU: u = a > 0 ? a : a/alpha, same sign as a; ReLU: du = 0 wherever u is unknown); the second partial sum
+// becomes sum du*(u - beta) = gamma*bn_c * sum du*z, and stage 2 divides by gamma instead of multiplying by bn_c.
+template <bool FROM_A>
 __global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict__ da, const float* __restrict__ z,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          float* __restrict__ dz, float* __restrict__ partial, long long rows,
@@ -35,6 +40,7 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict
     sf[j] = beta ? beta[cg * 4 + j] : 0.f;
   }
   float s_du[4] = {0.f, 0.f, 0.f, 0.f}, s_duz[4] = {0.f, 0.f, 0.f, 0.f};
+  const float inv_alpha = alpha != 0.f ? 1.f / alpha : 0.f;
   for (long long r = (long long)blockIdx.x * rpp + rl; r < rows; r += (long long)gridDim.x * rpp) {
     const size_t o = (size_t)r * C + cg * 4;
     const float4 g4 = *reinterpret_cast<const float4*>(da + o);
@@ -43,10 +49,17 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict
     float out[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float u = sc[j] * zv[j] + sf[j];
-      float du = gv[j] * uad_act_grad(u, act, alpha);
+      float du;
+      if (FROM_A) {
+        const float u = uad_preact_from_output(zv[j], act, inv_alpha);
+        du = gv[j] * uad_act_grad(u, act, alpha);
+        s_duz[j] += du * (u - sf[j]);
+      } else {
+        const float u = sc[j] * zv[j] + sf[j];
+        du = gv[j] * uad_act_grad(u, act, alpha);
+        s_duz[j] += du * zv[j];
+      }
       s_du[j] += du;
-      s_duz[j] += du * zv[j];
       out[j] = sc[j] * du;
     }
     *reinterpret_cast<float4*>(dz + o) = make_float4(out[0], out[1], out[2], out[3]);
@@ -69,7 +82,7 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict
 // partials (independent loads in flight), fixed-order shuffle tree -> deterministic.
 __global__ void act_bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ gamma,
                                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                                        int C, float bn_c, int accumulate) {
+                                        int C, float bn_c, int accumulate, int from_a) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (c >= C) return;
@@ -82,7 +95,9 @@ __global__ void act_bn_bwd_final_kernel(const float* __restrict__ partial, int n
   s_duz = uad_warp_sum(s_duz);
   if (lane != 0) return;
   const float sc = gamma ? gamma[c] * bn_c : 1.f;
-  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bn_c * s_duz;
+  // from_a: s_duz = sum du*(u - beta) = gamma*bn_c*sum du*z  ->  dgamma = s_duz / gamma
+  const float dg = from_a ? (gamma ? s_duz / gamma[c] : 0.f) : bn_c * s_duz;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + dg;
   if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + s_du;
   if (dbias) dbias[c] = (accumulate ? dbias[c] : 0.f) + sc * s_du;
 }
@@ -104,13 +119,20 @@ extern "C" int uad_act_bn_bwd(const float* da, const float* z, const float* gamm
                               float bn_c, int accumulate, void* ws, size_t ws_bytes, void* stream) {
   UAD_REQUIRE(C % 4 == 0 && C >= 4 && C <= 128 && 256 % (C / 4) == 0, "uad_act_bn_bwd: unsupported C=%d", C);
   UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_act_bn_bwd: gamma/beta must both be set or both NULL");
+  const int from_a = (act & UAD_ACT_FROM_OUTPUT) ? 1 : 0;
+  act &= ~UAD_ACT_FROM_OUTPUT;
+  UAD_REQUIRE(!from_a || act == UAD_ACT_NONE || act == UAD_ACT_RELU || (act == UAD_ACT_LEAKY && alpha > 0.f),
+              "uad_act_bn_bwd: UAD_ACT_FROM_OUTPUT needs a piecewise-linear activation (act=%d alpha=%g)", act, (double)alpha);
   const int nb = rowreduce_blocks(rows, C);
   UAD_REQUIRE(ws && ws_bytes >= (size_t)nb * 2 * C * sizeof(float), "uad_act_bn_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  act_bn_bwd_kernel<<<nb, 256, 0, st>>>(da, z, gamma, beta, dz, (float*)ws, rows, C, act, alpha, bn_c);
+  if (from_a)
+    act_bn_bwd_kernel<true><<<nb, 256, 0, st>>>(da, z, gamma, beta, dz, (float*)ws, rows, C, act, alpha, bn_c);
+  else
+    act_bn_bwd_kernel<false><<<nb, 256, 0, st>>>(da, z, gamma, beta, dz, (float*)ws, rows, C, act, alpha, bn_c);
   UAD_LAUNCH_CHECK("act_bn_bwd");
   act_bn_bwd_final_kernel<<<uad_cdiv(C * 32, 256), 256, 0, st>>>((const float*)ws, nb, gamma, dgamma, dbeta, dbias, C, bn_c,
-                                                            accumulate);
+                                                            accumulate, from_a);
   UAD_LAUNCH_CHECK("act_bn_bwd_final");
   return 0;
 }
@@ -326,6 +348,8 @@ extern "C" int uad_final1x1_bwd(const float* a, const float* w, const float* dxh
 
 // ---- fused: backward of (final 1x1 conv + L1) AND of the preceding "z -> frozen BN -> activation" block.
 // Reads z (pre-BN output of the last transposed conv), x, xhat; writes dz; never materialises da or re-reads a.
+// FROM_A: reads the block's output a instead of z (see act_bn_bwd_kernel).
+template <bool FROM_A>
 __global__ void __launch_bounds__(256) final_bwd_fused_kernel(const float* __restrict__ z, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ w,
                                                               const float* __restrict__ x, const float* __restrict__ xhat,
@@ -345,6 +369,7 @@ __global__ void __launch_bounds__(256) final_bwd_fused_kernel(const float* __res
     sf[j] = beta ? beta[lp * 4 + j] : 0.f;
   }
   float s_du[4] = {0.f, 0.f, 0.f, 0.f}, s_duz[4] = {0.f, 0.f, 0.f, 0.f}, s_w[4] = {0.f, 0.f, 0.f, 0.f}, s_b = 0.f;
+  const float inv_alpha = alpha != 0.f ? 1.f / alpha : 0.f;
   for (size_t pix = (size_t)blockIdx.x * ppp + pl; pix < npix; pix += (size_t)gridDim.x * ppp) {
     const float e = xhat[pix] - x[pix];
     const float g = (e > 0.f ? scale : (e < 0.f ? -scale : 0.f));
@@ -353,12 +378,20 @@ __global__ void __launch_bounds__(256) final_bwd_fused_kernel(const float* __res
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float u = sc[j] * zv[j] + sf[j];
-      const float a = uad_act(u, act, alpha);
-      const float du = g * wv[j] * uad_act_grad(u, act, alpha);
+      float a, du;
+      if (FROM_A) {
+        a = zv[j];
+        const float u = uad_preact_from_output(a, act, inv_alpha);
+        du = g * wv[j] * uad_act_grad(u, act, alpha);
+        s_duz[j] += du * (u - sf[j]);
+      } else {
+        const float u = sc[j] * zv[j] + sf[j];
+        a = uad_act(u, act, alpha);
+        du = g * wv[j] * uad_act_grad(u, act, alpha);
+        s_duz[j] += du * zv[j];
+      }
       s_w[j] += g * a;
       s_du[j] += du;
-      s_duz[j] += du * zv[j];
       o[j] = sc[j] * du;
     }
     if (lp == 0) s_b += g;
@@ -388,7 +421,7 @@ __global__ void __launch_bounds__(256) final_bwd_fused_kernel(const float* __res
 __global__ void final_bwd_fused_reduce_kernel(const float* __restrict__ partial, int nblocks, int Cin, const float* __restrict__ gamma,
                                               float bn_c, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                               float* __restrict__ dbias_prev, float* __restrict__ dw, float* __restrict__ dbias,
-                                              int accumulate) {
+                                              int accumulate, int from_a) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // one warp per channel (+1 for the bias)
   const int lane = threadIdx.x & 31;
   const int stride = 3 * Cin + 1;
@@ -402,7 +435,8 @@ __global__ void final_bwd_fused_reduce_kernel(const float* __restrict__ partial,
     a = uad_warp_sum(a); b = uad_warp_sum(b); d = uad_warp_sum(d);
     if (lane != 0) return;
     const float scv = gamma ? gamma[c] * bn_c : 1.f;
-    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + bn_c * b;
+    const float dg = from_a ? (gamma ? b / gamma[c] : 0.f) : bn_c * b;
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + dg;
     if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a;
     if (dbias_prev) dbias_prev[c] = (accumulate ? dbias_prev[c] : 0.f) + scv * a;
     if (dw) dw[c] = (accumulate ? dw[c] : 0.f) + d;
@@ -420,16 +454,24 @@ extern "C" int uad_final1x1_l1_bwd_fused(const float* z, const float* gamma, con
                                          float bn_c, int accumulate, void* ws, size_t ws_bytes, void* stream) {
   UAD_REQUIRE(Cin % 4 == 0 && uad_is_pow2(Cin / 4) && Cin <= 128, "uad_final1x1_l1_bwd_fused: unsupported Cin=%d", Cin);
   UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_final1x1_l1_bwd_fused: gamma/beta must both be set or both NULL");
+  const int from_a = (act & UAD_ACT_FROM_OUTPUT) ? 1 : 0;
+  act &= ~UAD_ACT_FROM_OUTPUT;
+  UAD_REQUIRE(!from_a || act == UAD_ACT_NONE || act == UAD_ACT_RELU || (act == UAD_ACT_LEAKY && alpha > 0.f),
+              "uad_final1x1_l1_bwd_fused: UAD_ACT_FROM_OUTPUT needs a piecewise-linear activation (act=%d alpha=%g)", act,
+              (double)alpha);
   const size_t npix = (size_t)B * HW;
   const int ppp = 256 / (Cin / 4);
   long long nb = (npix + ppp - 1) / ppp;
   if (nb > 4 * UAD_NUM_SMS) nb = 4 * UAD_NUM_SMS;
   UAD_REQUIRE(ws && ws_bytes >= (size_t)nb * (3 * Cin + 1) * sizeof(float), "uad_final1x1_l1_bwd_fused: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  final_bwd_fused_kernel<<<(int)nb, 256, 0, st>>>(z, gamma, beta, w, x, xhat, scale, dz, (float*)ws, npix, Cin, act, alpha, bn_c);
+  if (from_a)
+    final_bwd_fused_kernel<true><<<(int)nb, 256, 0, st>>>(z, gamma, beta, w, x, xhat, scale, dz, (float*)ws, npix, Cin, act, alpha, bn_c);
+  else
+    final_bwd_fused_kernel<false><<<(int)nb, 256, 0, st>>>(z, gamma, beta, w, x, xhat, scale, dz, (float*)ws, npix, Cin, act, alpha, bn_c);
   UAD_LAUNCH_CHECK("final_bwd_fused");
   final_bwd_fused_reduce_kernel<<<uad_cdiv((Cin + 1) * 32, 256), 256, 0, st>>>((const float*)ws, (int)nb, Cin, gamma, bn_c, dgamma, dbeta,
-                                                                       dbias_prev, dw, dbias, accumulate);
+                                                                       dbias_prev, dw, dbias, accumulate, from_a);
   UAD_LAUNCH_CHECK("final_bwd_fused_reduce");
   return 0;
 }

@@ -172,7 +172,7 @@ class ConvAutoencoderEngine:
     """
 
     def __init__(self, arch, S, C=1, zDim=128, res=8, batch=8, device='cuda:0', math_mode=abi.MATH_FP32_SIMT, seed=1,
-                 rng_seed=0x5eed, share_params=None):
+                 rng_seed=0x5eed, share_params=None, keep_preact=False):
         if arch not in ARCHS:
             raise ValueError(f'unsupported architecture {arch!r}; supported: {ARCHS}')
         if C != 1:
@@ -195,6 +195,10 @@ class ConvAutoencoderEngine:
         self.probes = None
         self.graph = None
         self.rng_seed = rng_seed
+        # keep_preact=False (default): conv blocks never write their pre-BN tensor z; the backward recovers what it needs
+        # from the activation a (UAD_ACT_FROM_OUTPUT, LeakyReLU is invertible) - half the forward HBM write volume and
+        # ~1 GB less activation memory at 256x256, B=64.  keep_preact=True restores the z-based backward.
+        self.keep_preact = bool(keep_preact)
         self._alloc()
 
     # ------------------------------------------------------------------ buffers
@@ -209,7 +213,7 @@ class ConvAutoencoderEngine:
         s = S
         for co in self.enc_ch:
             s //= 2
-            br.enc_z.append(self._new(B, s, s, co))
+            br.enc_z.append(self._new(B, s, s, co) if self.keep_preact else None)
             br.enc_a.append(self._new(B, s, s, co))
         r = self.res
         br.zb = self._new(B, r, r, self.cb)              # bottleneck 1x1 output == flatten input [B, flat]
@@ -225,7 +229,7 @@ class ConvAutoencoderEngine:
         s = r
         for co in self.dec_ch:
             s *= 2
-            br.dec_z.append(self._new(B, s, s, co))
+            br.dec_z.append(self._new(B, s, s, co) if self.keep_preact else None)
             br.dec_a.append(self._new(B, s, s, co))
         br.xhat = self._new(B, S, S, 1)
         br.l1 = self._new(B, S, S, 1)
@@ -347,7 +351,7 @@ class ConvAutoencoderEngine:
                 pre = f'Encoder/enc_conv2D_{i}'
                 bnn = f'Encoder/{_bn(i)}'
                 self._op(pre.split('/')[-1], 'uad_conv2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
-                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.enc_z[i]) if training else None,
+                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.enc_z[i]) if training and self.keep_preact else None,
                      ptr(br.enc_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.enc_a[i], s // 2, co
             r2 = self.res * self.res
@@ -383,7 +387,7 @@ class ConvAutoencoderEngine:
                 pre = f'Decoder/dec_Conv2DT_{i}'
                 bnn = f'Decoder/{_bn(self.n + 1 + i)}'
                 self._op(pre.split('/')[-1], 'uad_convT2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
-                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_z[i]) if training else None,
+                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_z[i]) if training and self.keep_preact else None,
                      ptr(br.dec_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.dec_a[i], s * 2, co
             self._op('dec_Conv2D_final', 'uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
@@ -406,6 +410,8 @@ class ConvAutoencoderEngine:
         B = self.B
         scale = 1.0 / B
         r2 = self.res * self.res
+        kp = self.keep_preact
+        act_blk = ACT_LEAKY if kp else (ACT_LEAKY | abi.ACT_FROM_OUTPUT)
         for bi, br in enumerate(self.br):
             acc = 1 if bi > 0 else 0
             is_ce = bi > 0
@@ -415,11 +421,11 @@ class ConvAutoencoderEngine:
             lpre = f'Decoder/dec_Conv2DT_{last}'
             lbn = f'Decoder/{_bn(self.n + 1 + last)}'
             # fused: final 1x1 + L1 backward AND the BN/LeakyReLU backward of the last transposed-conv block
-            self._op('dec_Conv2D_final', 'uad_final1x1_l1_bwd_fused', ptr(br.dec_z[last]), ptr(fp.p(lbn + '/gamma')),
+            self._op('dec_Conv2D_final', 'uad_final1x1_l1_bwd_fused', ptr(br.dec_z[last] if kp else br.dec_a[last]), ptr(fp.p(lbn + '/gamma')),
                      ptr(fp.p(lbn + '/beta')), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x), ptr(br.xhat), scale,
                      ptr(g), ptr(fp.g(lbn + '/gamma')), ptr(fp.g(lbn + '/beta')), ptr(fp.g(lpre + '/bias')),
                      ptr(fp.g('Decoder/dec_Conv2D_final/kernel')), ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B,
-                     self.S * self.S, cin, ACT_LEAKY, LRELU_ALPHA, BN_C, acc, ws, wsb, st)
+                     self.S * self.S, cin, act_blk, LRELU_ALPHA, BN_C, acc, ws, wsb, st)
             s = self.S
             for i in reversed(range(self.n)):
                 co = self.dec_ch[i]
@@ -427,8 +433,8 @@ class ConvAutoencoderEngine:
                 pre = f'Decoder/dec_Conv2DT_{i}'
                 bnn = f'Decoder/{_bn(self.n + 1 + i)}'
                 if i != self.n - 1:      # the last block's BN/activation backward is fused into the final-1x1 backward above
-                  self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
-                     ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
+                  self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.dec_z[i] if kp else br.dec_a[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                     ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, act_blk,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.dec_a[i - 1] if i > 0 else br.ar
                 self._op(pre.split('/')[-1], 'uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
@@ -485,8 +491,8 @@ class ConvAutoencoderEngine:
                 ci = self.enc_ch[i - 1] if i > 0 else 1
                 pre = f'Encoder/enc_conv2D_{i}'
                 bnn = f'Encoder/{_bn(i)}'
-                self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.enc_z[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
-                     ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, ACT_LEAKY,
+                self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.enc_z[i] if kp else br.enc_a[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(g),
+                     ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, act_blk,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.enc_a[i - 1] if i > 0 else br.x
                 self._op(pre.split('/')[-1], 'uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE, acc,

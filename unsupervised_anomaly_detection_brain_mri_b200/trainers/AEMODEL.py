@@ -58,7 +58,8 @@ class AEMODEL(DLMODEL, ABC):
         torch.cuda.set_device(self.device)
         self.engine = ConvAutoencoderEngine(self.graph.arch, self.graph.S, self.graph.C, self.graph.zDim, self.graph.res,
                                             batch=cfg.batchsize, device=self.device, math_mode=self.math_mode,
-                                            seed=int(getattr(cfg, 'seed', 1)))
+                                            seed=int(getattr(cfg, 'seed', 1)),
+                                            keep_preact=bool(getattr(cfg, 'keep_preact', False)))
         self._eval_engines = {}
         self._pinned = {}
         self.get_number_of_trainable_params()
