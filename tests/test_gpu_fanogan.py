@@ -312,3 +312,55 @@ def test_fanogan_trainer_train_loop(tmp_path):
     assert model.engine.t['Generator'] > 0 and model.engine.t['Encoder'] > 0
     rec = model.reconstruct(ds.next_batch(4, set='VAL')[0][0])
     assert rec['reconstruction'].shape == (1, 32, 32, 1) and np.isfinite(rec['l1err'])
+
+
+@pytest.mark.parametrize('which', ['gen', 'disc', 'enc'])
+def test_fanogan_graph_replay_equals_eager(which):
+    """A train op replayed from its CUDA graph (eager warm-up, capture, replays) leaves bit-identical weights, Adam moments
+    and loss scalars to the same op issued eagerly (all reductions are deterministic)."""
+    from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
+    S, B, rate, lr, steps = 32, 4, 0.2, 1e-3, 5
+    P = FO.perturb(FO.init_params(S, seed=1))
+    runs = []
+    for use_graph in (False, True):
+        eng = FanoganEngine(S, batch=B, math_mode=1)
+        x, z, alpha, m_enc, m_gen = _feed(S, B, rate, eng.flat)
+        eng.fp.load(P)
+        eng.enable_training()
+        eng.set_inputs(x)
+        eng.set_latent(z)
+        eng.alpha.copy_(torch.from_numpy(alpha.reshape(-1)))
+        eng.mask_enc.copy_(torch.from_numpy(m_enc))
+        eng.mask_gen.copy_(torch.from_numpy(m_gen))
+        step = {'gen': eng.step_gen, 'disc': eng.step_disc, 'enc': eng.step_enc}[which]
+        res = [step(lr, dropout_rate=rate, dropout=True, parity_noise=True, use_graph=use_graph) for _ in range(steps)]
+        torch.cuda.synchronize()
+        assert (len(eng._graphs) == 1) == use_graph
+        runs.append((eng.fp.to_numpy(), eng.fp.to_numpy(eng.fp.m), eng.fp.to_numpy(eng.fp.v), res, dict(eng.t)))
+    (w0, m0, v0, r0, t0), (w1, m1, v1, r1, t1) = runs
+    assert t0 == t1
+    assert r0 == r1
+    for k in w0:
+        assert np.array_equal(w0[k], w1[k]), k
+        assert np.array_equal(m0[k], m1[k]) and np.array_equal(v0[k], v1[k]), k
+
+
+def test_fanogan_graph_noise_advances():
+    """Perf-mode noise under graph replay: the Philox offset lives on the device, so every replay draws fresh dropout
+    masks / interpolation coefficients."""
+    from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
+    S, B = 32, 4
+    eng = FanoganEngine(S, batch=B, math_mode=1)
+    eng.enable_training()
+    eng.set_inputs(O.synthetic_slices(B, S, seed=5))
+    eng.set_latent(np.random.default_rng(0).standard_normal((B, 128)).astype(np.float32))
+    seen = []
+    for _ in range(4):
+        eng.step_disc(1e-4, dropout_rate=0.2, dropout=True, use_graph=True)
+        seen.append((eng.alpha.cpu().numpy().copy(), eng.mask_gen.cpu().numpy().copy()))
+    assert len(eng._graphs) == 1
+    for i in range(1, 4):
+        assert not np.array_equal(seen[i][0], seen[i - 1][0])
+        assert not np.array_equal(seen[i][1], seen[i - 1][1])
+    keep = np.mean([m.mean() for _, m in seen])
+    assert 0.75 < keep < 0.85

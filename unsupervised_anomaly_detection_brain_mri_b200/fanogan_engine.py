@@ -211,7 +211,8 @@ class FanoganEngine:
         self.sc = torch.zeros(16, dtype=torch.float32, device=self.device)
         self.steps = {k: torch.zeros(1, dtype=torch.int64, device=self.device) for k in ('Encoder', 'Generator', 'Discriminator')}
         self.t = {k: 0 for k in self.steps}
-        self.rng_calls = 0
+        self.rng_ctr = torch.zeros(1, dtype=torch.int64, device=self.device)   # Philox offset lives on the device (graph-capturable)
+        self._graphs, self._warm, self._graph_scopes = {}, {}, {}
         self._train_ready = True
 
     def _st(self):
@@ -474,19 +475,45 @@ class FanoganEngine:
                      ws, wsb, st)
 
     # ------------------------------------------------------------------ noise, optimiser
-    def _next_offset(self):
-        self.rng_calls += 1
-        return self.rng_calls << 32
-
+    # Each draw uses its own Philox sub-stream (id << 40) plus the device-resident counter, which advances once per train op:
+    # nothing about the noise is baked into a captured CUDA graph.
     def draw_masks(self, rate, enc=False, gen=False):
         st = self._st()
+        ctr = self.rng_ctr.data_ptr()
         if enc:
-            call('uad_dropout_mask', ptr(self.mask_enc), self.mask_enc.numel(), float(rate), self.seed, self._next_offset(), None, st)
+            call('uad_dropout_mask', ptr(self.mask_enc), self.mask_enc.numel(), float(rate), self.seed, 1 << 40, ctr, st)
         if gen:
-            call('uad_dropout_mask', ptr(self.mask_gen), self.mask_gen.numel(), float(rate), self.seed, self._next_offset(), None, st)
+            call('uad_dropout_mask', ptr(self.mask_gen), self.mask_gen.numel(), float(rate), self.seed, 2 << 40, ctr, st)
 
     def draw_alpha(self):
-        call('uad_uniform', ptr(self.alpha), self.alpha.numel(), self.seed, self._next_offset(), None, self._st())
+        call('uad_uniform', ptr(self.alpha), self.alpha.numel(), self.seed, 3 << 40, self.rng_ctr.data_ptr(), self._st())
+
+    def _advance_rng(self):
+        call('uad_counter_add', self.rng_ctr.data_ptr(), 1 << 20, self._st())
+
+    def _run(self, name, key, body, use_graph):
+        """Issue ``body`` (the kernel sequence of one train op): eagerly, or - with use_graph - eagerly once (warm-up), then
+        captured into a CUDA graph and replayed (a critic step is ~320 launches; at the 16-slice per-GPU shard of
+        BASELINE config 5 the op is launch-bound without this)."""
+        if not use_graph:
+            body()
+            return
+        k = (name, key)
+        g = self._graphs.get(k)
+        if g is None and self._warm.get(name) == key:
+            t_save = dict(self.t)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            self.t = t_save                       # capture does not execute: undo the host-side step bookkeeping
+            self._graphs[k] = g
+        if g is not None:
+            g.replay()
+            for scope in self._graph_scopes.get(k, ()):
+                self.t[scope] += 1
+            return
+        body()
+        self._warm[name] = key
 
     def set_latent(self, z):
         if isinstance(z, np.ndarray):
@@ -517,91 +544,123 @@ class FanoganEngine:
         return on, (1.0 / (1.0 - rate) if on else 1.0)
 
     # ------------------------------------------------------------------ the three train ops
-    def step_gen(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True):
+    def step_gen(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True,
+                 use_graph=False):
         """optim_gen: minimise gen_loss = -mean(D(G(z))) over the Generator variables (fAnoGAN.py:52,76,99-112)."""
         self.enable_training()
-        st = self._st()
-        ws, wsb = self._wsp()
         on, keep = self._mask_args(dropout_rate, dropout)
-        if on and not parity_noise:
-            self.draw_masks(dropout_rate, gen=True)
-        self.generate(self.z_in, self.mask_gen if on else None, keep, out=self.x_gen)
-        _, d = self._critic_forward(self.pass0, self.x_gen)
-        nd = d.numel()
-        call('uad_sum_scaled', ptr(d), nd, 1.0 / nd, self.sc[0:].data_ptr(), ws, wsb, st)
-        self._critic_top(self.pass0, -1.0 / nd, params=False)
-        self._critic_backward(self.pass0, self.x_gen, params=False, dx_out=self.dxi)
-        self._zero_grads('Generator')
-        self._generator_backward(self.dxi, params=True)
-        if apply:
+
+        def body():
+            st = self._st()
+            ws, wsb = self._wsp()
+            if on and not parity_noise:
+                self.draw_masks(dropout_rate, gen=True)
+                self._advance_rng()
+            self.generate(self.z_in, self.mask_gen if on else None, keep, out=self.x_gen)
+            _, d = self._critic_forward(self.pass0, self.x_gen)
+            nd = d.numel()
+            call('uad_sum_scaled', ptr(d), nd, 1.0 / nd, self.sc[0:].data_ptr(), ws, wsb, st)
+            self._critic_top(self.pass0, -1.0 / nd, params=False)
+            self._critic_backward(self.pass0, self.x_gen, params=False, dx_out=self.dxi)
+            self._zero_grads('Generator')
+            self._generator_backward(self.dxi, params=True)
+            if apply and allreduce is None:
+                self._adam('Generator', lr, None, world)
+
+        key = (float(lr), float(dropout_rate), bool(dropout), bool(parity_noise), allreduce is None, world, bool(apply))
+        self._graph_scopes[('gen', key)] = ('Generator',) if (apply and allreduce is None) else ()
+        self._run('gen', key, body, use_graph)
+        if apply and allreduce is not None:
             self._adam('Generator', lr, allreduce, world)
         s = self._scalars(['disc_fake'])
         return {'gen_loss': -s['disc_fake'], 'disc_fake': s['disc_fake']}
 
-    def step_disc(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True):
+    def step_disc(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True,
+                  use_graph=False):
         """optim_dis: minimise mean(D(x_)) - mean(D(x)) + gp over the Discriminator variables (fAnoGAN.py:50-58,75,114-129)."""
         self.enable_training()
-        st = self._st()
-        ws, wsb = self._wsp()
         on, keep = self._mask_args(dropout_rate, dropout)
-        if not parity_noise:
-            if on:
-                self.draw_masks(dropout_rate, gen=True)
-            self.draw_alpha()
-        self.generate(self.z_in, self.mask_gen if on else None, keep, out=self.x_gen)
-        self._zero_grads('Discriminator')
-        _, d_f = self._critic_forward(self.pass0, self.x_gen)
-        nd = d_f.numel()
-        call('uad_sum_scaled', ptr(d_f), nd, 1.0 / nd, self.sc[0:].data_ptr(), ws, wsb, st)
-        self._critic_top(self.pass0, 1.0 / nd, params=True)
-        self._critic_backward(self.pass0, self.x_gen, params=True, dx_out=None)
-        _, d_r = self._critic_forward(self.pass0, self.x)
-        call('uad_sum_scaled', ptr(d_r), nd, 1.0 / nd, self.sc[1:].data_ptr(), ws, wsb, st)
-        self._critic_top(self.pass0, -1.0 / nd, params=True)
-        self._critic_backward(self.pass0, self.x, params=True, dx_out=None)
-        call('uad_interpolate', ptr(self.x), ptr(self.x_gen), ptr(self.alpha), ptr(self.x_hat), self.B, self.S * self.S * self.C, st)
-        self._critic_forward(self.pass0, self.x_hat, critic=False)
-        self._critic_gp(self.pass0, self.x_hat)
-        if apply:
+
+        def body():
+            st = self._st()
+            ws, wsb = self._wsp()
+            if not parity_noise:
+                if on:
+                    self.draw_masks(dropout_rate, gen=True)
+                self.draw_alpha()
+                self._advance_rng()
+            self.generate(self.z_in, self.mask_gen if on else None, keep, out=self.x_gen)
+            self._zero_grads('Discriminator')
+            _, d_f = self._critic_forward(self.pass0, self.x_gen)
+            nd = d_f.numel()
+            call('uad_sum_scaled', ptr(d_f), nd, 1.0 / nd, self.sc[0:].data_ptr(), ws, wsb, st)
+            self._critic_top(self.pass0, 1.0 / nd, params=True)
+            self._critic_backward(self.pass0, self.x_gen, params=True, dx_out=None)
+            _, d_r = self._critic_forward(self.pass0, self.x)
+            call('uad_sum_scaled', ptr(d_r), nd, 1.0 / nd, self.sc[1:].data_ptr(), ws, wsb, st)
+            self._critic_top(self.pass0, -1.0 / nd, params=True)
+            self._critic_backward(self.pass0, self.x, params=True, dx_out=None)
+            call('uad_interpolate', ptr(self.x), ptr(self.x_gen), ptr(self.alpha), ptr(self.x_hat), self.B, self.S * self.S * self.C, st)
+            self._critic_forward(self.pass0, self.x_hat, critic=False)
+            self._critic_gp(self.pass0, self.x_hat)
+            if apply and allreduce is None:
+                self._adam('Discriminator', lr, None, world)
+
+        key = (float(lr), float(dropout_rate), bool(dropout), bool(parity_noise), allreduce is None, world, bool(apply), self.scale)
+        self._graph_scopes[('disc', key)] = ('Discriminator',) if (apply and allreduce is None) else ()
+        self._run('disc', key, body, use_graph)
+        if apply and allreduce is not None:
             self._adam('Discriminator', lr, allreduce, world)
         s = self._scalars(['disc_fake', 'disc_real', 'gp'])
         s['disc_loss'] = s['disc_fake'] - s['disc_real'] + s['gp']
         return s
 
-    def step_enc(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True, train=True):
+    def step_enc(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True, train=True,
+                 use_graph=False):
         """optim_enc: minimise mean((x-x_enc)^2) + kappa*mean((f(x_enc)-f(x))^2) over the Encoder variables
         (fAnoGAN.py:60-66,77,150-166).  train=False evaluates the losses only (validation loop, fAnoGAN.py:181-199)."""
         self.enable_training()
-        st = self._st()
-        ws, wsb = self._wsp()
         on, keep = self._mask_args(dropout_rate, dropout)
-        if on and not parity_noise:
-            self.draw_masks(dropout_rate, enc=True, gen=True)
         self._e_mask, self._e_keep = (self.mask_enc if on else None), keep
-        z_enc = self.encode(self._e_mask, keep)
-        x_enc = self.generate(z_enc, self.mask_gen if on else None, keep, out=self.x_enc)
-        f_real, _ = self._critic_forward(self.pass1, self.x, critic=False)
-        f_enc, _ = self._critic_forward(self.pass0, x_enc, critic=False)
-        nx, nf = x_enc.numel(), f_enc.numel()
-        # d enc_loss / d f_enc -> dis_g1[-1];  d loss_img / d x_enc -> dxi2 (added after the critic's input gradient)
-        call('uad_mse', ptr(f_enc), ptr(f_real), nf, 2.0 * self.kappa / nf, ptr(self.dis_g1[-1]), 1.0 / nf, self.sc[4:].data_ptr(),
-             ws, wsb, st)
-        call('uad_mse', ptr(x_enc), ptr(self.x), nx, 2.0 / nx, ptr(self.u), 1.0 / nx, self.sc[3:].data_ptr(), ws, wsb, st)
-        call('uad_l1_map', ptr(self.x), ptr(x_enc), ptr(self.l1), ptr(self.rec), self.B, self.S * self.S * self.C, st)
-        call('uad_sum_scaled', ptr(self.rec), self.B, 1.0 / self.B, self.sc[5:].data_ptr(), ws, wsb, st)
-        if train:
-            self._critic_backward(self.pass0, x_enc, params=False, dx_out=self.dxi)
-            call('uad_axpby', 1.0, ptr(self.u), 1.0, ptr(self.dxi), nx, st)
-            self._generator_backward(self.dxi, params=False, dz_out=self.dz_lat)
-            self._encoder_backward(self.dz_lat)
-            if apply:
-                self._adam('Encoder', lr, allreduce, world)
+        kappa = self.kappa
+
+        def body():
+            st = self._st()
+            ws, wsb = self._wsp()
+            if on and not parity_noise:
+                self.draw_masks(dropout_rate, enc=True, gen=True)
+                self._advance_rng()
+            z_enc = self.encode(self._e_mask, keep)
+            x_enc = self.generate(z_enc, self.mask_gen if on else None, keep, out=self.x_enc)
+            f_real, _ = self._critic_forward(self.pass1, self.x, critic=False)
+            f_enc, _ = self._critic_forward(self.pass0, x_enc, critic=False)
+            nx, nf = x_enc.numel(), f_enc.numel()
+            # d enc_loss / d f_enc -> dis_g1[-1];  d loss_img / d x_enc -> dxi2 (added after the critic's input gradient)
+            call('uad_mse', ptr(f_enc), ptr(f_real), nf, 2.0 * kappa / nf, ptr(self.dis_g1[-1]), 1.0 / nf, self.sc[4:].data_ptr(),
+                 ws, wsb, st)
+            call('uad_mse', ptr(x_enc), ptr(self.x), nx, 2.0 / nx, ptr(self.u), 1.0 / nx, self.sc[3:].data_ptr(), ws, wsb, st)
+            call('uad_l1_map', ptr(self.x), ptr(x_enc), ptr(self.l1), ptr(self.rec), self.B, self.S * self.S * self.C, st)
+            call('uad_sum_scaled', ptr(self.rec), self.B, 1.0 / self.B, self.sc[5:].data_ptr(), ws, wsb, st)
+            if train:
+                self._critic_backward(self.pass0, x_enc, params=False, dx_out=self.dxi)
+                call('uad_axpby', 1.0, ptr(self.u), 1.0, ptr(self.dxi), nx, st)
+                self._generator_backward(self.dxi, params=False, dz_out=self.dz_lat)
+                self._encoder_backward(self.dz_lat)
+                if apply and allreduce is None:
+                    self._adam('Encoder', lr, None, world)
+
+        key = (float(lr), float(dropout_rate), bool(dropout), bool(parity_noise), allreduce is None, world, bool(apply), bool(train),
+               kappa)
+        self._graph_scopes[('enc', key)] = ('Encoder',) if (train and apply and allreduce is None) else ()
+        self._run('enc', key, body, use_graph)
+        if train and apply and allreduce is not None:
+            self._adam('Encoder', lr, allreduce, world)
         s = self._scalars(['loss_img', 'loss_fts', 'reconstructionLoss'])
         s['enc_loss'] = s['loss_img'] + self.kappa * s['loss_fts']
         s['loss'] = s['reconstructionLoss']
         return s
 
-    def wgan_scalars(self, dropout_rate=0.0, dropout=True):
+    def wgan_scalars(self, dropout_rate=0.0, dropout=True, use_graph=False):
         """disc_real / disc_fake / gen_loss / disc_loss on the current x, z (the reference fetches **self.losses in the encoder
         phase, fAnoGAN.py:157,190; none of them depends on the Encoder, so evaluating them after its update is equivalent)."""
-        return self.step_disc(0.0, dropout_rate, dropout, apply=False)
+        return self.step_disc(0.0, dropout_rate, dropout, apply=False, use_graph=use_graph)

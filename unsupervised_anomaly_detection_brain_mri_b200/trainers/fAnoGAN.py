@@ -91,7 +91,9 @@ class fAnoGAN(DLMODEL):
         eng.enable_training()
         self.variables = list(eng.specs.keys())
         lr, rate = float(cfg.learningrate), float(cfg.dropout_rate)
-        kw = dict(dropout_rate=rate, dropout=True, allreduce=getattr(self, '_allreduce', None), world=getattr(self, 'world', 1))
+        graphs = bool(getattr(cfg, 'useCudaGraph', True))                 # replay each train op as one CUDA graph launch
+        kw = dict(dropout_rate=rate, dropout=True, allreduce=getattr(self, '_allreduce', None), world=getattr(self, 'world', 1),
+                  use_graph=graphs)
         verbose = bool(getattr(cfg, 'verbose', True))
         all_losses = bool(getattr(cfg, 'fetchAllLosses', True))
         best_cost = inf
@@ -127,13 +129,13 @@ class fAnoGAN(DLMODEL):
                 self._feed(batch)
                 train = phase == Phase.TRAIN
                 run = dict(eng.step_enc(lr, dropout_rate=rate, dropout=train, allreduce=kw['allreduce'], world=kw['world'],
-                                        train=train))
+                                        train=train, use_graph=graphs))
                 run['reconstruction'] = eng.x_enc.cpu().numpy()
                 run['L1'] = eng.l1.cpu().numpy()
                 if train:
                     run['z_enc'], run['z'] = eng.z_enc.cpu().numpy(), self._z
                 if all_losses:                                            # **self.losses (fAnoGAN.py:157,190)
-                    run.update(eng.wgan_scalars(rate, dropout=train))
+                    run.update(eng.wgan_scalars(rate, dropout=train, use_graph=graphs))
                 if verbose:
                     tag = f'{phase.value} Encoder' if train else phase.value
                     print(f'Epoch ({tag}): [{epoch:2d}] [{idx:4d}/{num_batches:4d}]  reconstructionLoss: '
