@@ -227,6 +227,18 @@ int uad_binary_erosion_cross(const uint8_t* mask, uint8_t* out, int N, int H, in
 /* scipy.ndimage.median_filter(volume, (5,5,5)) on a float32 volume [Z,H,W], boundary mode 'reflect'; out != vol */
 int uad_median_filter3d_5(const float* vol, float* out, int Z, int H, int W, void* stream);
 
+/* ================= iterative MAP restoration (trainers/VAE_You.py:53-54,125-147; GMVAE.py:166-197) =================
+ * One iteration = forward, g = dL/dxhat seed, dgrad chain to the input (uad_final1x1_bwd, uad_act_bn_bwd with NULL
+ * parameter-gradient outputs, uad_conv*_dgrad, uad_dense_bwd with dw = NULL), update - all resident on the device.
+ * seed: g = sign(xhat - x) - tv_lambda * dTV(d)/dd at d = x - xhat (tf.image.total_variation, sign(0) = 0);
+ *       tv[b] (nullable) = TV(x - xhat) per image.  x, xhat, g: [B,H,W] single channel.  ws >= uad_tv_restore_workspace_bytes. */
+size_t uad_tv_restore_workspace_bytes(int B, int H, int W);
+int uad_tv_restore_seed(const float* x, const float* xhat, float tv_lambda, float* g, float* tv, int B, int H, int W, void* ws,
+                        size_t ws_bytes, void* stream);
+/* x <- x - lr*(gx - g)   (gx: gradient through the network; -g: direct dependence of the L1 and TV terms on x);
+ * grads_out (nullable) receives gx - g, the tensor the reference fetches as losses['grads'] (VAE_You.py:54). */
+int uad_restore_update(float* x, const float* gx, const float* g, float lr, float* grads_out, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

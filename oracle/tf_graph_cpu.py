@@ -296,6 +296,50 @@ def loss_and_grads(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=
     return out, L, G
 
 
+def total_variation(d):
+    """tf.image.total_variation on NHWC images (TF 1.15 image_ops_impl.py): sum |d[:,1:]-d[:,:-1]| + sum |d[:,:,1:]-d[:,:,:-1]|
+    per image."""
+    return (d[:, 1:] - d[:, :-1]).abs().sum(dim=(1, 2, 3)) + (d[:, :, 1:] - d[:, :, :-1]).abs().sum(dim=(1, 2, 3))
+
+
+def restore_gradient(arch, P, x, *, eps=None, tv_lambda=0.0, masks=None, dropout_rate=0.0, training=False, dtype=torch.float32,
+                     sign_from=None):
+    """losses['grads'] of reference trainers/VAE_You.py:47-54:
+        pixel_loss = sum_hwc |x_hat - x| + kl   (per sample);  restore = tv_lambda * total_variation(x - x_hat)
+        grads = tf.gradients(pixel_loss + restore, x)[0]       (gradient of the SUM over samples; x also enters directly)
+    sign_from (test aid, default None = literal |.|): an x_hat array (the implementation's) whose sign patterns
+    sign(x_hat - x) and sign of the neighbour differences of x - x_hat replace d|u|/du, see ``losses``.
+    Returns (grads NHWC, out dict, per-sample tv)."""
+    xt = _t(x, dtype).clone().requires_grad_(True)
+    out = forward(arch, P, xt, eps=eps, masks=masks, dropout_rate=dropout_rate, training=training, dtype=dtype)
+    xh = out['x_hat']
+    d = xt - xh
+    if sign_from is None:
+        rec = (xh - xt).abs().sum(dim=(1, 2, 3))
+        tv = total_variation(d)
+    else:
+        xs = _t(x, dtype)
+        ds = xs - _t(sign_from, dtype)
+        rec = ((xh - xt) * torch.sign(-ds)).sum(dim=(1, 2, 3))
+        tv = ((d[:, 1:] - d[:, :-1]) * torch.sign(ds[:, 1:] - ds[:, :-1])).sum(dim=(1, 2, 3)) + \
+             ((d[:, :, 1:] - d[:, :, :-1]) * torch.sign(ds[:, :, 1:] - ds[:, :, :-1])).sum(dim=(1, 2, 3))
+    total = rec + tv_lambda * tv
+    if arch != AE:
+        mu, sg = out['z_mu'], out['z_sigma']
+        total = total + 0.5 * (mu ** 2 + sg ** 2 - torch.log(sg ** 2) - 1).sum(dim=1)
+    g = torch.autograd.grad(total.sum(), xt)[0]
+    return g.detach(), {k: v.detach() for k, v in out.items()}, tv.detach()
+
+
+def restore(arch, P, x, *, steps, restore_lr, tv_lambda, eps_list, dtype=torch.float32):
+    """VAE_You.reconstruct (trainers/VAE_You.py:125-139): restored -= restore_lr * grads, ``steps`` times, a fresh eps each run."""
+    restored = np.array(x, dtype=np.float64 if dtype == torch.float64 else np.float32, copy=True)
+    for k in range(steps):
+        g, _, _ = restore_gradient(arch, P, restored, eps=eps_list[k], tv_lambda=tv_lambda, dtype=dtype)
+        restored = restored - restore_lr * g.numpy()
+    return restored
+
+
 def adam_tf(P, G, m, v, t, lr, beta1=0.5, beta2=0.999, eps=1e-8):
     """tf.train.AdamOptimizer update: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); theta -= lr_t*m/(sqrt(v)+eps).
     t is the 1-based step count.  Works on dicts of torch tensors; returns new (P, m, v)."""

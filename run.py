@@ -100,6 +100,9 @@ if __name__ == '__main__':
     args.add_argument('-d', '--ds', default=None, type=lambda s: Dataset[s], help='Only evaluate on given dataset')
     args.add_argument('-n', '--numMonteCarloSamples', default=0, type=int, help='Amount of Monte Carlos Samples during restoration')
     args.add_argument('-G', '--use_gradient_based_restoration', default=False, type=bool, help='only for ceVAE')
+    args.add_argument('-L', '--restore_lr', default=1e-3, type=float, help='only for VAE_You / GMVAE')
+    args.add_argument('-S', '--restore_steps', default=150, type=int, help='only for VAE_You / GMVAE')
+    args.add_argument('-T', '--tv_lambda', default=-1.0, type=float, help='only for VAE_You / GMVAE')
     args.add_argument('-K', '--kappa', default=1.0, type=float, help='only for GANs')
     args.add_argument('-M', '--scale', default=10.0, type=float, help='only for GANs')
     args.add_argument('--numPatients', default=0, type=int, help='synthetic dataset size (patients x 110 slices)')

@@ -1,5 +1,5 @@
 """Device time of the three f-AnoGAN train ops at full size (developer aid; CUDA events, resident inputs).
-usage: python tools/fanogan_time.py [S] [B] [math_mode] [iters]"""
+usage: python tools/fanogan_time.py [S] [B] [math_mode] [iters] [graph 0|1]"""
 import json
 import sys
 
@@ -15,20 +15,21 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+graph = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
 eng = FanoganEngine(S, batch=B, math_mode=mode)
 eng.enable_training()
 eng.set_inputs(synthetic_slices(B, S, seed=3))
 eng.set_latent(np.random.default_rng(0).standard_normal((B, 128)).astype(np.float32))
-res = {'S': S, 'B': B, 'math_mode': mode}
+res = {'S': S, 'B': B, 'math_mode': mode, 'cuda_graph': graph}
 for name, fn in (('gen', eng.step_gen), ('disc', eng.step_disc), ('enc', eng.step_enc)):
-    for _ in range(2):
-        fn(1e-4, dropout_rate=0.2)
+    for _ in range(3):
+        fn(1e-4, dropout_rate=0.2, use_graph=graph)
     torch.cuda.synchronize()
     l0 = abi.lib().uad_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        out = fn(1e-4, dropout_rate=0.2)
+        out = fn(1e-4, dropout_rate=0.2, use_graph=graph)
     e1.record()
     torch.cuda.synchronize()
     res[name + '_ms'] = e0.elapsed_time(e1) / iters

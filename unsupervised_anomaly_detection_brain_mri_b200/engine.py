@@ -274,6 +274,7 @@ class ConvAutoencoderEngine:
         for (M, K, N) in ((B * r2, self.enc_ch[-1], self.cb), (B * r2, self.cb, self.enc_ch[-1]), (B, self.flat, self.zDim),
                           (B, self.zDim, self.flat)):
             need = max(need, L.uad_dense_workspace_bytes(M, K, N))
+        need = max(need, L.uad_tv_restore_workspace_bytes(B, S, S))
         self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         self.ws_bytes = need
 
@@ -507,6 +508,121 @@ class ConvAutoencoderEngine:
                 s *= 2
 
     _keep = 1.0
+
+    # ------------------------------------------------------------------ gradient w.r.t. the input only (restoration)
+    def backward_to_input(self, seed, kl_scale=1.0):
+        """d/dx of  <seed, x_hat(x)> + kl_scale * sum_b kl_b(x)  through the x-branch: the dgrad-only chain (no weight
+        gradients are formed, every parameter-gradient output is NULL).  Needs the activations of a preceding
+        ``forward`` (training or not): the BN/activation backward works from the block outputs (UAD_ACT_FROM_OUTPUT).
+        Result in ``self.gx``.  This is tf.gradients(..., self.x) of reference trainers/VAE_You.py:54."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsargs()
+        B, br, sm = self.B, self.br[0], self.small
+        r2 = self.res * self.res
+        g, gn = self.gbuf
+        FO = abi.ACT_FROM_OUTPUT
+        cin = self.dec_ch[-1]
+        self._op('dec_Conv2D_final', 'uad_final1x1_bwd', ptr(br.dec_a[-1]), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(seed),
+                 ptr(g), None, None, B, self.S * self.S, cin, 0, ws, wsb, st)
+        s = self.S
+        for i in reversed(range(self.n)):
+            co = self.dec_ch[i]
+            ci = self.dec_ch[i - 1] if i > 0 else self.enc_ch[-1]
+            pre = f'Decoder/dec_Conv2DT_{i}'
+            bnn = f'Decoder/{_bn(self.n + 1 + i)}'
+            self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.dec_a[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')),
+                     ptr(g), None, None, None, B * s * s, co, ACT_LEAKY | FO, LRELU_ALPHA, BN_C, 0, ws, wsb, st)
+            self._op(pre.split('/')[-1], 'uad_convT2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, s // 2, s // 2, ci, co,
+                     KSIZE, mm, ws, wsb, st)
+            g, gn = gn, g
+            s //= 2
+        ctop = self.enc_ch[-1]
+        dbn = f'Decoder/{_bn(self.n)}'
+        self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.ar), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
+                 None, None, None, B * r2, ctop, ACT_RELU | FO, 0.0, BN_C, 0, ws, wsb, st)
+        self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                 None, None, B * r2, self.cb, ctop, 0, ws, wsb, st)
+        m, keep = br.masks, self._keep
+        if self.arch == AE:
+            self._op('bneck11', 'uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
+                     ptr(sm['dmu']), None, None, B, self.zDim, self.flat, 0, ws, wsb, st)
+            self._op('bneck12', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(m['mu']), keep,
+                     ptr(sm['dflat']), None, None, B, self.flat, self.zDim, 0, ws, wsb, st)
+        else:
+            self._op('bneck13', 'uad_dense_bwd', ptr(br.zv), ptr(fp.p('Bottleneck/dense_2/kernel')), ptr(sm['dd']), ptr(m['dec']), keep,
+                     ptr(sm['dzv']), None, None, B, self.zDim, self.flat, 0, ws, wsb, st)
+            self._op('bneck14', 'uad_reparam_kl_bwd', ptr(br.mu), ptr(br.ls), ptr(br.eps), ptr(sm['dzv']), float(kl_scale),
+                     ptr(sm['dmu']), ptr(sm['dls']), B, self.zDim, st)
+            self._op('bneck15', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(m['mu']), keep,
+                     ptr(sm['dflat']), None, None, B, self.flat, self.zDim, 0, ws, wsb, st)
+            self._op('bneck16', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dls']), ptr(m['ls']), keep,
+                     ptr(sm['dflat2']), None, None, B, self.flat, self.zDim, 0, ws, wsb, st)
+            self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
+        self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
+                 ptr(g), None, None, B * r2, ctop, self.cb, 0, ws, wsb, st)
+        s = self.res
+        for i in reversed(range(self.n)):
+            co = self.enc_ch[i]
+            ci = self.enc_ch[i - 1] if i > 0 else 1
+            pre = f'Encoder/enc_conv2D_{i}'
+            bnn = f'Encoder/{_bn(i)}'
+            self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.enc_a[i]), ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')),
+                     ptr(g), None, None, None, B * s * s, co, ACT_LEAKY | FO, LRELU_ALPHA, BN_C, 0, ws, wsb, st)
+            dst = gn if i > 0 else self.gx
+            self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(dst), B, 2 * s, 2 * s, ci, co, KSIZE,
+                     mm, ws, wsb, st)
+            g, gn = gn, g
+            s *= 2
+
+    def restore_step(self, restore_lr, tv_lambda, dropout=False, dropout_rate=0.0, parity_noise=False, keep_grads=False):
+        """One iteration of the MAP restoration loop of reference trainers/VAE_You.py:125-139 on the batch resident in
+        ``br[0].x`` (updated IN PLACE):  x <- x - restore_lr * d/dx [ sum|x_hat-x| + kl + tv_lambda*TV(x - x_hat) ].
+        The whole iteration stays on the device (the reference pays one sess.run + two host<->device image copies per step)."""
+        br = self.br[0]
+        rate = dropout_rate if dropout else 0.0
+        self._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+        if not parity_noise:
+            self.draw_noise(dropout, rate)
+        self.forward(training=False, dropout_rate=rate, branches=[0], need_l1=False)
+        st = self._st()
+        ws, wsb = self._wsargs()
+        if not hasattr(self, 'gseed'):
+            self.gseed = self._new(self.B, self.S, self.S, 1)
+            self.tv = self._new(self.B)
+            self.restore_grads = self._new(self.B, self.S, self.S, 1)
+        self._op('restore', 'uad_tv_restore_seed', ptr(br.x), ptr(br.xhat), float(tv_lambda), ptr(self.gseed), ptr(self.tv), self.B,
+                 self.S, self.S, ws, wsb, st)
+        self.backward_to_input(self.gseed, kl_scale=1.0)
+        self._op('restore', 'uad_restore_update', ptr(br.x), ptr(self.gx), ptr(self.gseed), float(restore_lr),
+                 ptr(self.restore_grads) if keep_grads else None, br.x.numel(), st)
+
+    def restore(self, steps, restore_lr, tv_lambda, dropout=False, dropout_rate=0.0, use_graph=True):
+        """``steps`` restoration iterations; after one eager iteration the rest replay a CUDA graph of the iteration
+        (the Philox offset lives on the device, so every replay draws a fresh eps as tf.random_normal does)."""
+        if steps <= 0:
+            return
+        if not hasattr(self, 'gseed'):
+            self.gseed = self._new(self.B, self.S, self.S, 1)
+            self.tv = self._new(self.B)
+            self.restore_grads = self._new(self.B, self.S, self.S, 1)
+        key = (float(restore_lr), float(tv_lambda), bool(dropout), float(dropout_rate))
+        done = 0
+        if not use_graph or getattr(self, '_restore_key', None) != key:
+            self.restore_step(restore_lr, tv_lambda, dropout, dropout_rate)
+            done = 1
+            self._restore_graph = None
+            self._restore_key = key
+        if not use_graph:
+            for _ in range(done, steps):
+                self.restore_step(restore_lr, tv_lambda, dropout, dropout_rate)
+            return
+        if self._restore_graph is None and steps > done:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.restore_step(restore_lr, tv_lambda, dropout, dropout_rate)
+            self._restore_graph = g
+        for _ in range(done, steps):
+            self._restore_graph.replay()
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0, lo=0, hi=None):
