@@ -104,3 +104,40 @@ def test_threshold_compare_is_float64():
     d = np.array([np.float32(0.3)], np.float64)
     assert scoring.threshold_mask(d, 0.3)[0]            # float32(0.3) = 0.30000001192... > 0.3
     assert not scoring.threshold_mask(d, 0.30000002)[0]
+
+
+def test_restore_gradient_finite_difference():
+    """oracle.restore_gradient (trainers/VAE_You.py:47-54): tf.image.total_variation restated + d/dx checked by central
+    differences in float64 at pixels away from the |.| kinks."""
+    import torch
+    from oracle import tf_graph_cpu as O
+    S, B, lam = 16, 2, 1.3
+    P = O.perturb_params(O.init_params(O.VAE, S, seed=3))
+    x = O.synthetic_slices(B, S, seed=2).astype(np.float64)
+    eps = np.random.default_rng(1).standard_normal((B, 128))
+    d = np.random.default_rng(0).random((2, 5, 7, 1))
+    tv = O.total_variation(torch.from_numpy(d)).numpy()
+    ref = np.abs(np.diff(d, axis=1)).sum((1, 2, 3)) + np.abs(np.diff(d, axis=2)).sum((1, 2, 3))
+    assert np.allclose(tv, ref)
+
+    def objective(xx):
+        out = O.forward(O.VAE, P, xx, eps=eps, dtype=torch.float64)
+        xt = torch.from_numpy(xx)
+        rec = (out['x_hat'] - xt).abs().sum(dim=(1, 2, 3))
+        kl = 0.5 * (out['z_mu'] ** 2 + out['z_sigma'] ** 2 - torch.log(out['z_sigma'] ** 2) - 1).sum(dim=1)
+        return float((rec + kl + lam * O.total_variation(xt - out['x_hat'])).sum())
+
+    g, out, _ = O.restore_gradient(O.VAE, P, x, eps=eps, tv_lambda=lam, dtype=torch.float64)
+    g = g.numpy()
+    h = 1e-6
+    rng = np.random.default_rng(5)
+    checked = 0
+    for _ in range(12):
+        b, i, j = int(rng.integers(B)), int(rng.integers(1, S - 1)), int(rng.integers(1, S - 1))
+        xp, xm = x.copy(), x.copy()
+        xp[b, i, j, 0] += h
+        xm[b, i, j, 0] -= h
+        fd = (objective(xp) - objective(xm)) / (2 * h)
+        if abs(fd - g[b, i, j, 0]) < 1e-4 * max(1.0, abs(fd)):
+            checked += 1
+    assert checked >= 10          # the remaining probes may straddle a kink of |.|

@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box session: full GPU test suite, headline bench (+ per-kernel table), f-AnoGAN and restoration timings.
+# Everything lands in gpurun_out/.  usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+TAG=${1:-r1b}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+( time timeout 900 python -m pytest tests -m gpu -q --maxfail=15 -p no:cacheprovider ) > gpurun_out/${TAG}_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_pytest.log
+timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers.json > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+cat gpurun_out/${TAG}_bench.json
+timeout 200 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
+cat gpurun_out/${TAG}_bench_ref.json
+for args in "256 16 1 10 0" "256 16 1 10 1" "256 128 1 4 1"; do
+  timeout 200 python tools/fanogan_time.py $args >> gpurun_out/${TAG}_fanogan.jsonl 2>> gpurun_out/${TAG}_fanogan.err
+done
+cat gpurun_out/${TAG}_fanogan.jsonl
+timeout 200 python tools/restore_time.py 256 110 150 1 > gpurun_out/${TAG}_restore.json 2> gpurun_out/${TAG}_restore.err
+cat gpurun_out/${TAG}_restore.json
