@@ -227,6 +227,14 @@ int uad_binary_erosion_cross(const uint8_t* mask, uint8_t* out, int N, int H, in
 /* scipy.ndimage.median_filter(volume, (5,5,5)) on a float32 volume [Z,H,W], boundary mode 'reflect'; out != vol */
 int uad_median_filter3d_5(const float* vol, float* out, int Z, int H, int W, void* stream);
 
+/* ================= spatial-bottleneck models (models/autoencoder_spatial.py:16-23) =================
+ * z = x*(mask ? mask*keep : 1) (tf.keras Dropout on the encoder output), a = act(gamma*bn_c*z + beta) (the decoder's leading
+ * BatchNormalization + ReLU, models/customlayers.py:30-31).  x, mask, z_out, a_out: [rows, C]; z_out / a_out nullable. */
+int uad_mask_bn_act_fwd(const float* x, const float* mask, float keep, const float* gamma, const float* beta, float bn_c, int act,
+                        float alpha, float* z_out, float* a_out, long long rows, int C, void* stream);
+/* y = x*(mask ? mask : 1)*scale  (Dropout backward; y may alias x) */
+int uad_mask_scale(const float* x, const float* mask, float scale, float* y, size_t n, void* stream);
+
 /* ================= iterative MAP restoration (trainers/VAE_You.py:53-54,125-147; GMVAE.py:166-197) =================
  * One iteration = forward, g = dL/dxhat seed, dgrad chain to the input (uad_final1x1_bwd, uad_act_bn_bwd with NULL
  * parameter-gradient outputs, uad_conv*_dgrad, uad_dense_bwd with dw = NULL), update - all resident on the device.

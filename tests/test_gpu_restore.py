@@ -33,7 +33,7 @@ def _tv_seed_numpy(x, xh, lam):
 
 @pytest.mark.parametrize('B,H,W,lam', [(3, 40, 72, 1.8), (2, 8, 32, -0.5), (1, 256, 256, 1.0), (2, 33, 5, 0.0)])
 def test_tv_restore_seed_bitexact(B, H, W, lam):
-    from gpu_util import call, dev, empty, ptr, st, sync, workspace
+    from gpu_util import call, dev, dptr, empty, ptr, st, sync, workspace
     from unsupervised_anomaly_detection_brain_mri_b200 import abi
     rng = np.random.default_rng(B * H + W)
     x = rng.random((B, H, W), dtype=np.float32)
@@ -43,7 +43,7 @@ def test_tv_restore_seed_bitexact(B, H, W, lam):
     wsb = abi.lib().uad_tv_restore_workspace_bytes(B, H, W)
     ws = workspace(wsb)
     g, tv = empty(B, H, W), empty(B)
-    call('uad_tv_restore_seed', ptr(dev(x)), ptr(dev(xh)), lam, ptr(g), ptr(tv), B, H, W, ptr(ws), wsb, st())
+    call('uad_tv_restore_seed', dptr(x), dptr(xh), lam, ptr(g), ptr(tv), B, H, W, ptr(ws), wsb, st())
     sync()
     g_ref, tv_ref = _tv_seed_numpy(x, xh, lam)
     assert np.array_equal(g.cpu().numpy(), g_ref)
@@ -51,7 +51,7 @@ def test_tv_restore_seed_bitexact(B, H, W, lam):
     # the update kernel:  x <- x - lr*(gx - g)
     gx = rng.standard_normal((B, H, W)).astype(np.float32)
     xd, grads = dev(x), empty(B, H, W)
-    call('uad_restore_update', ptr(xd), ptr(dev(gx)), ptr(g), 1e-3, ptr(grads), x.size, st())
+    call('uad_restore_update', ptr(xd), dptr(gx), ptr(g), 1e-3, ptr(grads), x.size, st())
     sync()
     assert np.array_equal(grads.cpu().numpy(), gx - g_ref)
     assert np.allclose(xd.cpu().numpy(), x - np.float32(1e-3) * (gx - g_ref), rtol=0, atol=1e-7)

@@ -27,9 +27,11 @@ cases = {
   'enc1.fwd (FormF N=64 C=32 128^2->64^2)': ('conv_fwd', 128, 32, 64),
   'enc2.fwd (FormF N=128 C=64)': ('conv_fwd', 64, 64, 128),
   'enc1.wgrad': ('conv_wgrad', 128, 32, 64),
+  'enc2.dgrad (FormT N=64 C=128)': ('conv_dgrad', 64, 64, 128),
+  'enc3.fwd (FormF N=128 C=128)': ('conv_fwd', 32, 128, 128),
 }
 for name, (op, H, Cin, Cout) in cases.items():
-    opid = {'conv_fwd': 0, 'conv_wgrad': 2, 'convT_fwd': 3, 'convT_dgrad': 4, 'convT_wgrad': 5}[op]
+    opid = {'conv_fwd': 0, 'conv_dgrad': 1, 'conv_wgrad': 2, 'convT_fwd': 3, 'convT_dgrad': 4, 'convT_wgrad': 5}[op]
     wsb = L.uad_conv_workspace_bytes(opid, B, H, H, Cin, Cout, 5, 1)
     ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     if op.startswith('convT'):
@@ -39,17 +41,18 @@ for name, (op, H, Cin, Cout) in cases.items():
     z = torch.empty_like(y)
     dw = torch.empty_like(w); dx = torch.empty_like(x)
     def run():
-        if op == 'conv_fwd': call('uad_conv2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, z.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
-        elif op == 'convT_fwd': call('uad_convT2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, z.data_ptr(), y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
+        if op == 'conv_fwd': call('uad_conv2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, None, y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
+        elif op == 'conv_dgrad': call('uad_conv2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, 1, ws.data_ptr(), wsb, st())
+        elif op == 'convT_fwd': call('uad_convT2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, None, y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
         elif op == 'convT_dgrad': call('uad_convT2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, 1, ws.data_ptr(), wsb, st())
         elif op == 'conv_wgrad': call('uad_conv2d_wgrad', x.data_ptr(), y.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, 5, 0, 1, ws.data_ptr(), wsb, st())
         elif op == 'convT_wgrad': call('uad_convT2d_wgrad', x.data_ptr(), y.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, 5, 0, 1, ws.data_ptr(), wsb, st())
     res = []
     var = 'UAD_WGRAD_DEBUG' if 'wgrad' in op else 'UAD_TC_DEBUG'
-    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0', '3', '7', '11', '4', '8']
+    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0', '1', '2', '3', '96', '99']
     for dbg in modes:
         os.environ[var] = dbg
         res.append(f'{dbg}:{timeit(run):.3f}ms')
     os.environ[var] = '0'
     print(f'{name:45s} ' + '  '.join(res), flush=True)
-print('gather modes (bits): 1 no-convert, 2 no-MMA, 4 no global stores, 8 no epilogue pass | wgrad: 2 no-convert, 4 no-MMA')
+print('gather modes (bits): 1 no-convert, 2 no-MMA, 4 no global stores, 8 no epilogue pass, 32 no A load, 64 no B load | wgrad: 2 no-convert, 4 no-MMA')

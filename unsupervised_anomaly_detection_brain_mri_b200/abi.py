@@ -73,6 +73,8 @@ SIGNATURES = {
     'uad_l1_map': (_I, [_P] * 4 + [_I, _I, _P]),
     'uad_binary_erosion_cross': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'uad_median_filter3d_5': (_I, [_P, _P, _I, _I, _I, _P]),
+    'uad_mask_bn_act_fwd': (_I, [_P, _P, _F, _P, _P, _F, _I, _F, _P, _P, _LL, _I, _P]),
+    'uad_mask_scale': (_I, [_P, _P, _F, _P, _Z, _P]),
     'uad_tv_restore_workspace_bytes': (_Z, [_I, _I, _I]),
     'uad_tv_restore_seed': (_I, [_P, _P, _F, _P, _P, _I, _I, _I, _P, _Z, _P]),
     'uad_restore_update': (_I, [_P, _P, _P, _F, _P, _Z, _P]),

@@ -49,7 +49,8 @@ struct TcParams {
   int acc_bufs;        // accumulator sets in TMEM (2 = epilogue overlaps the next item's MMAs)
   int n_items;         // work items = tiles * nclasses
   int nclasses;
-  int debug;           // developer timing switches (UAD_TC_DEBUG): 1 = converters skip their work, 2 = MMA issuer skips the MMAs
+  int debug;           // developer timing switches (UAD_TC_DEBUG): 1 = converters skip their work, 2 = MMA issuer skips the MMAs,
+                       // 4 / 8 = N=32 kernel: no global stores / no epilogue pass, 16 = clock64 trace, 32 / 64 = no A / no B load
   float* z_out;
   float* a_out;
   const float* bias;
@@ -233,15 +234,17 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
-          mbar_expect_tx(full, kABytes + b_bytes);
+          // developer timing switches: 32 = skip the activation (A) load, 64 = skip the weight (B) load
+          mbar_expect_tx(full, ((p.debug & 32) ? 0u : (uint32_t)kABytes) + ((p.debug & 64) ? 0u : b_bytes));
           const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
           const uint32_t a_dst = smem_base + s * stage_bytes;
-          if (p.stride2)
+          if (p.debug & 32) {
+          } else if (p.stride2)
             tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
           else
             tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
           const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
-          bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+          if (!(p.debug & 64)) bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
           if (++cb == p.Cblks) { cb = 0; ++tap; }
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -502,15 +505,17 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
-          mbar_expect_tx(full, kABytes + b_bytes);
+          // developer timing switches: 32 = skip the activation (A) load, 64 = skip the weight (B) load
+          mbar_expect_tx(full, ((p.debug & 32) ? 0u : (uint32_t)kABytes) + ((p.debug & 64) ? 0u : b_bytes));
           const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
           const uint32_t a_dst = smem_base + s * stage_bytes;
-          if (p.stride2)
+          if (p.debug & 32) {
+          } else if (p.stride2)
             tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
           else
             tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
           const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
-          bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+          if (!(p.debug & 64)) bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
           if (++cb == p.Cblks) { cb = 0; ++tap; }
           if (++s == S) { s = 0; ph ^= 1; }
         }

@@ -137,6 +137,48 @@ extern "C" int uad_act_bn_bwd(const float* da, const float* z, const float* gamm
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ dropout -> frozen BN -> act
+// z = x * (mask ? mask*keep : 1);  a = act(gamma*bn_c*z + beta).  The spatial-bottleneck models (reference
+// models/autoencoder_spatial.py:16-23) feed the dropped-out encoder output straight into the decoder's BN + ReLU.
+__global__ void mask_bn_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ mask, float keep,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float bn_c, int act,
+                                       float alpha, float* __restrict__ z_out, float* __restrict__ a_out, size_t n, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  float z = x[i];
+  if (mask) z *= mask[i] * keep;
+  if (z_out) z_out[i] = z;
+  if (a_out) {
+    const float u = gamma ? gamma[c] * bn_c * z + beta[c] : z;
+    a_out[i] = uad_act(u, act, alpha);
+  }
+}
+
+extern "C" int uad_mask_bn_act_fwd(const float* x, const float* mask, float keep, const float* gamma, const float* beta, float bn_c,
+                                   int act, float alpha, float* z_out, float* a_out, long long rows, int C, void* stream) {
+  UAD_REQUIRE(rows > 0 && C > 0, "uad_mask_bn_act_fwd: bad dims");
+  UAD_REQUIRE((gamma == nullptr) == (beta == nullptr), "uad_mask_bn_act_fwd: gamma/beta must both be set or both NULL");
+  const size_t n = (size_t)rows * C;
+  mask_bn_act_fwd_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, keep, gamma, beta, bn_c, act, alpha, z_out,
+                                                                            a_out, n, C);
+  UAD_LAUNCH_CHECK("mask_bn_act_fwd");
+  return 0;
+}
+
+// y = x * (mask ? mask : 1) * scale   (dropout backward; y may alias x)
+__global__ void mask_scale_kernel(const float* __restrict__ x, const float* __restrict__ mask, float scale, float* __restrict__ y,
+                                  size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[i] * (mask ? mask[i] * scale : scale);
+}
+
+extern "C" int uad_mask_scale(const float* x, const float* mask, float scale, float* y, size_t n, void* stream) {
+  mask_scale_kernel<<<uad_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, scale, y, n);
+  UAD_LAUNCH_CHECK("mask_scale");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ reparameterise + KL
 __global__ void reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
                                       float* __restrict__ sigma, float* __restrict__ z, float* __restrict__ kl, int Z) {

@@ -31,7 +31,8 @@ KSIZE = 5
 AE = 'autoencoder'
 VAE = 'variational_autoencoder'
 CEVAE = 'context_encoder_variational_autoencoder'
-ARCHS = (AE, VAE, CEVAE)
+AES = 'autoencoder_spatial'      # encoder -> Dropout -> decoder, no dense bottleneck (reference models/autoencoder_spatial.py)
+ARCHS = (AE, VAE, CEVAE, AES)
 
 
 def stack_plan(S, res=8):
@@ -58,18 +59,19 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         bn += 1
         cin = co
     cb = cin // 8
-    sp['Bottleneck/conv2d/kernel'] = (1, 1, cin, cb)
-    sp['Bottleneck/conv2d/bias'] = (cb,)
-    sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
-    sp['Bottleneck/conv2d_1/bias'] = (cin,)
-    flat = res * res * cb
-    heads = 1 if arch == AE else 2
-    for h in range(heads):
-        nm = 'dense' if h == 0 else f'dense_{h}'
-        sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
-        sp[f'Bottleneck/{nm}/bias'] = (zDim,)
-    sp[f'Bottleneck/dense_{heads}/kernel'] = (zDim, flat)
-    sp[f'Bottleneck/dense_{heads}/bias'] = (flat,)
+    if arch != AES:
+        sp['Bottleneck/conv2d/kernel'] = (1, 1, cin, cb)
+        sp['Bottleneck/conv2d/bias'] = (cb,)
+        sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
+        sp['Bottleneck/conv2d_1/bias'] = (cin,)
+        flat = res * res * cb
+        heads = 1 if arch == AE else 2
+        for h in range(heads):
+            nm = 'dense' if h == 0 else f'dense_{h}'
+            sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
+            sp[f'Bottleneck/{nm}/bias'] = (zDim,)
+        sp[f'Bottleneck/dense_{heads}/kernel'] = (zDim, flat)
+        sp[f'Bottleneck/dense_{heads}/bias'] = (flat,)
     sp[f'Decoder/{_bn(bn)}/gamma'] = (cin,)
     sp[f'Decoder/{_bn(bn)}/beta'] = (cin,)
     bn += 1
@@ -235,8 +237,10 @@ class ConvAutoencoderEngine:
         br.l1 = self._new(B, S, S, 1)
         br.rec = self._new(B)
         br.eps = self._new(B, self.zDim)
-        br.masks = {k: None for k in ('mu', 'ls', 'dec')}
+        br.masks = {k: None for k in ('mu', 'ls', 'dec', 'sp')}
         br.mask_bufs = {'mu': self._new(B, self.zDim), 'ls': self._new(B, self.zDim), 'dec': self._new(B, self.flat)}
+        if self.arch == AES:
+            br.mask_bufs['sp'] = self._new(B, r, r, self.enc_ch[-1])      # Dropout on the spatial code z [B,res,res,C]
         return br
 
     def _alloc(self):
@@ -324,6 +328,15 @@ class ConvAutoencoderEngine:
         st = self._st()
         ctr = self.rng_ctr.data_ptr()
         nb = 0
+        if self.arch == AES:
+            br = self.br[0]
+            if dropout and rate > 0:
+                call('uad_dropout_mask', ptr(br.mask_bufs['sp']), br.mask_bufs['sp'].numel(), float(rate), self.rng_seed, 1 << 40, ctr, st)
+                br.masks['sp'] = br.mask_bufs['sp']
+            else:
+                br.masks['sp'] = None
+            call('uad_counter_add', ctr, 1 << 20, st)
+            return
         for bi, br in enumerate(self.br):
             if self.arch != AE and bi == 0:
                 call('uad_randn', ptr(br.eps), br.eps.numel(), self.rng_seed, nb << 40, ctr, st)
@@ -356,10 +369,18 @@ class ConvAutoencoderEngine:
                      ptr(br.enc_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.enc_a[i], s // 2, co
             r2 = self.res * self.res
-            self._op('bneck01', 'uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
-                 1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             m = br.masks
-            if self.arch == AE:
+            if self.arch == AES:
+                # autoencoder_spatial.py:16-23: z = Dropout(encoder(x)); decoder = BN -> ReLU -> ...
+                dbn = f'Decoder/{_bn(self.n)}'
+                self._op('bneck01', 'uad_mask_bn_act_fwd', ptr(h), ptr(m['sp']), keep, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')),
+                         BN_C, ACT_RELU, 0.0, ptr(br.zr), ptr(br.ar), B * r2, cin, st)
+            else:
+              self._op('bneck01', 'uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
+                 1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+            if self.arch == AES:
+                pass
+            elif self.arch == AE:
                 # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity
                 self._op('bneck02', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
                      ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
@@ -377,10 +398,11 @@ class ConvAutoencoderEngine:
                 else:
                     zsrc = br.mu      # ce branch decodes z_mu_ce without sampling (ceVAE model :37,43)
                 dd_name, dec_mask = 'Bottleneck/dense_2', m['dec']
-            self._op('bneck06', 'uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
+            if self.arch != AES:
+              self._op('bneck06', 'uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
                  keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, ws, wsb, st)
-            dbn = f'Decoder/{_bn(self.n)}'
-            self._op('bneck07', 'uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
+              dbn = f'Decoder/{_bn(self.n)}'
+              self._op('bneck07', 'uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
                  None, 1.0, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(br.zr) if training else None,
                  ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, ws, wsb, st)
             h, s = br.ar, self.res
@@ -396,7 +418,7 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch != AE else None, ptr(self.scalars), B, st)
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES) else None, ptr(self.scalars), B, st)
         if self.arch == CEVAE and (branches is None or 1 in branches):
             self._op('bneck09', 'uad_loss_scalars', ptr(self.br[1].rec), None, ptr(self.scalars[3:]), B, st)
 
@@ -448,15 +470,21 @@ class ConvAutoencoderEngine:
             ctop = self.enc_ch[-1]
             dbn = f'Decoder/{_bn(self.n)}'
             self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
-                 ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')), B * r2, ctop,
-                 ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
+                 ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')) if self.arch != AES else None,
+                 B * r2, ctop, ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
             sm = self.small
-            self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
-                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
             m = br.masks
             # keep factor is stored with the mask application: masks carry {0,1}, scale passed explicitly
             keep = self._keep
-            if self.arch == AE:
+            if self.arch == AES:
+                if m['sp'] is not None:
+                    self._op('bneck10', 'uad_mask_scale', ptr(g), ptr(m['sp']), keep, ptr(g), B * r2 * ctop, st)
+            else:
+              self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
+            if self.arch == AES:
+                pass
+            elif self.arch == AE:
                 self._op('bneck11', 'uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
                      ptr(sm['dmu']), ptr(fp.g('Bottleneck/dense_1/kernel')), ptr(fp.g('Bottleneck/dense_1/bias')), B,
                      self.zDim, self.flat, acc, ws, wsb, st)
@@ -483,7 +511,8 @@ class ConvAutoencoderEngine:
                          ptr(fp.g('Bottleneck/dense_1/bias')), B, self.flat, self.zDim, acc, ws, wsb, st)
                     self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
             # bottleneck 1x1 conv backward -> gradient w.r.t. the last encoder activation
-            self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
+            if self.arch != AES:
+              self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
                  ptr(g), ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb,
                  acc, ws, wsb, st)
             s = self.res
@@ -540,10 +569,16 @@ class ConvAutoencoderEngine:
         dbn = f'Decoder/{_bn(self.n)}'
         self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.ar), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
                  None, None, None, B * r2, ctop, ACT_RELU | FO, 0.0, BN_C, 0, ws, wsb, st)
-        self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
-                 None, None, B * r2, self.cb, ctop, 0, ws, wsb, st)
         m, keep = br.masks, self._keep
-        if self.arch == AE:
+        if self.arch == AES:
+            if m['sp'] is not None:
+                self._op('bneck10', 'uad_mask_scale', ptr(g), ptr(m['sp']), keep, ptr(g), B * r2 * ctop, st)
+        else:
+            self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                     None, None, B * r2, self.cb, ctop, 0, ws, wsb, st)
+        if self.arch == AES:
+            pass
+        elif self.arch == AE:
             self._op('bneck11', 'uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
                      ptr(sm['dmu']), None, None, B, self.zDim, self.flat, 0, ws, wsb, st)
             self._op('bneck12', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(m['mu']), keep,
@@ -558,8 +593,9 @@ class ConvAutoencoderEngine:
             self._op('bneck16', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dls']), ptr(m['ls']), keep,
                      ptr(sm['dflat2']), None, None, B, self.flat, self.zDim, 0, ws, wsb, st)
             self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
-        self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
-                 ptr(g), None, None, B * r2, ctop, self.cb, 0, ws, wsb, st)
+        if self.arch != AES:
+            self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
+                     ptr(g), None, None, B * r2, ctop, self.cb, 0, ws, wsb, st)
         s = self.res
         for i in reversed(range(self.n)):
             co = self.enc_ch[i]
@@ -692,7 +728,7 @@ class ConvAutoencoderEngine:
     # ------------------------------------------------------------------ read-back
     def losses(self):
         s = self.scalars.detach().cpu().numpy()
-        if self.arch == AE:
+        if self.arch in (AE, AES):
             return {'reconstructionLoss': float(s[0]), 'loss': float(s[0])}
         if self.arch == VAE:
             return {'reconstructionLoss': float(s[0]), 'kl': float(s[1]), 'loss': float(s[2])}
