@@ -27,7 +27,8 @@ LRELU_ALPHA = 0.3      # tf.keras.layers.LeakyReLU() default alpha (models/custo
 AE = 'autoencoder'
 VAE = 'variational_autoencoder'
 CEVAE = 'context_encoder_variational_autoencoder'
-ARCHS = (AE, VAE, CEVAE)
+AES = 'autoencoder_spatial'
+ARCHS = (AE, VAE, CEVAE, AES)
 
 
 # --------------------------------------------------------------------------- layer plan
@@ -64,19 +65,20 @@ def init_params(arch: str, S: int, C: int = 1, zDim: int = 128, res: int = 8, se
         bn += 1
         cin = co
     cb = cin // 8
-    P['Bottleneck/conv2d/kernel'] = _glorot(rng, (1, 1, cin, cb), cin, cb)
-    P['Bottleneck/conv2d/bias'] = np.zeros(cb, np.float32)
-    P['Bottleneck/conv2d_1/kernel'] = _glorot(rng, (1, 1, cb, cin), cb, cin)
-    P['Bottleneck/conv2d_1/bias'] = np.zeros(cin, np.float32)
-    flat = res * res * cb
-    heads = 1 if arch == AE else 2
-    for h in range(heads):
-        nm = 'dense' if h == 0 else f'dense_{h}'
-        P[f'Bottleneck/{nm}/kernel'] = _glorot(rng, (flat, zDim), flat, zDim)
-        P[f'Bottleneck/{nm}/bias'] = np.zeros(zDim, np.float32)
-    nm = f'dense_{heads}'
-    P[f'Bottleneck/{nm}/kernel'] = _glorot(rng, (zDim, flat), zDim, flat)
-    P[f'Bottleneck/{nm}/bias'] = np.zeros(flat, np.float32)
+    if arch != AES:                      # autoencoder_spatial.py has no Bottleneck scope at all
+        P['Bottleneck/conv2d/kernel'] = _glorot(rng, (1, 1, cin, cb), cin, cb)
+        P['Bottleneck/conv2d/bias'] = np.zeros(cb, np.float32)
+        P['Bottleneck/conv2d_1/kernel'] = _glorot(rng, (1, 1, cb, cin), cb, cin)
+        P['Bottleneck/conv2d_1/bias'] = np.zeros(cin, np.float32)
+        flat = res * res * cb
+        heads = 1 if arch == AE else 2
+        for h in range(heads):
+            nm = 'dense' if h == 0 else f'dense_{h}'
+            P[f'Bottleneck/{nm}/kernel'] = _glorot(rng, (flat, zDim), flat, zDim)
+            P[f'Bottleneck/{nm}/bias'] = np.zeros(zDim, np.float32)
+        nm = f'dense_{heads}'
+        P[f'Bottleneck/{nm}/kernel'] = _glorot(rng, (zDim, flat), zDim, flat)
+        P[f'Bottleneck/{nm}/bias'] = np.zeros(flat, np.float32)
     P[f'Decoder/{bn_name(bn)}/gamma'] = np.ones(cin, np.float32)
     P[f'Decoder/{bn_name(bn)}/beta'] = np.zeros(cin, np.float32)
     bn += 1
@@ -205,13 +207,22 @@ def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, tr
     xt = _t(x, dtype).permute(0, 3, 1, 2)
     out = {}
     h = encoder(P, xt)
-    h = conv1x1(h, P['Bottleneck/conv2d/kernel'], P['Bottleneck/conv2d/bias'])
-    res, cb = h.shape[2], h.shape[1]
-    flat = _flatten_nhwc(h)
 
     def M(name):
         m = masks.get(name)
         return None if m is None else _t(m, dtype)
+
+    if arch == AES:
+        # models/autoencoder_spatial.py:12-25: z = Dropout(encoder(x), training=dropout) on the NHWC code; x_hat = decoder(z).
+        # masks['z']: {0,1} array [B, res, res, C] (NHWC, as the tensor the Keras layer sees)
+        m = M('z')
+        zs = dropout(h.permute(0, 2, 3, 1), m, dropout_rate, training)
+        out['z'] = zs
+        out['x_hat'] = decoder(P, zs.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+        return out
+    h = conv1x1(h, P['Bottleneck/conv2d/kernel'], P['Bottleneck/conv2d/bias'])
+    res, cb = h.shape[2], h.shape[1]
+    flat = _flatten_nhwc(h)
 
     if arch == AE:
         # autoencoder.py:29-30: dropout on z honours the flag; dropout on dec_dense(z) is called WITHOUT the flag -> identity
@@ -253,7 +264,7 @@ def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_c
     L = {}
     l1 = (out['x_hat'] - xt).abs() if l1_sign is None else (out['x_hat'] - xt) * _t(l1_sign, dtype)
     rec = l1.sum(dim=(1, 2, 3))
-    if arch == AE:
+    if arch in (AE, AES):
         L['L1'] = l1
         L['reconstructionLoss'] = L['loss'] = rec.mean()
         return L

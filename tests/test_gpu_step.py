@@ -127,3 +127,40 @@ def test_multi_step_training_tracks_oracle():
         _, L, _ = tr.step(x, eps=eps, masks=om)
         got = eng.losses()['loss']
         assert abs(got - float(L['loss'])) / abs(float(L['loss'])) < 2e-4, (step, got, float(L['loss']))
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('S,B', [(64, 4), (128, 2)])
+def test_spatial_autoencoder_step_parity(S, B, mode):
+    """models/autoencoder_spatial.py through the AE loss (trainers/AE.py:28-29): encoder -> Dropout on the spatial code ->
+    decoder.  Forward tensors, loss, every gradient and the dropped-out code z against the float64 oracle."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import AES, ConvAutoencoderEngine
+    rate, lr = 0.2, 1e-3
+    P = O.perturb_params(O.init_params(O.AES, S, seed=1))
+    assert not any(k.startswith('Bottleneck/') for k in P)
+    x = O.synthetic_slices(B, S, seed=77)
+    eng = ConvAutoencoderEngine(AES, S, batch=B, math_mode=mode)
+    assert list(eng.specs.keys()) == list(P.keys())
+    eng.fp.load(P)
+    m = (np.random.default_rng(5).uniform(size=(B, 8, 8, eng.enc_ch[-1])) >= rate).astype(np.float32)
+    eng.set_inputs(x)
+    eng.set_noise(None, {'sp': m})
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True)
+    torch.cuda.synchronize()
+    xh = eng.br[0].xhat.cpu().numpy()
+    sgn = np.sign(xh.astype(np.float64) - x)
+    out, L, G = O.loss_and_grads(O.AES, P, x, masks={'z': m}, dropout_rate=rate, training=True, dtype=torch.float64, l1_sign=sgn)
+    assert _relerr(xh, out['x_hat'].numpy()) < TOL
+    assert _relerr(eng.br[0].zr.cpu().numpy(), out['z'].numpy()) < TOL
+    got = eng.losses()
+    assert abs(got['loss'] - float(L['loss'])) / abs(float(L['loss'])) < TOL
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    worst = max((_relerr(grads[k], G[k].numpy()), k) for k in P)
+    assert worst[0] < 5 * TOL, worst
+    # inference forward (dropout off) equals the oracle's
+    eng.set_noise(None, None)
+    eng.br[0].masks['sp'] = None
+    eng.forward(training=False, dropout_rate=0.0)
+    torch.cuda.synchronize()
+    out2 = O.forward(O.AES, P, x, training=False, dtype=torch.float64)
+    assert _relerr(eng.br[0].xhat.cpu().numpy(), out2['x_hat'].numpy()) < TOL
