@@ -157,8 +157,8 @@ def test_spatial_autoencoder_step_parity(S, B, mode):
     grads = eng.fp.to_numpy(eng.fp.grads)
     worst = max((_relerr(grads[k], G[k].numpy()), k) for k in P)
     assert worst[0] < 5 * TOL, worst
-    # inference forward (dropout off) equals the oracle's
-    eng.set_noise(None, None)
+    # inference forward (dropout off) equals the oracle's (reload the weights: train_step applied Adam)
+    eng.fp.load(P)
     eng.br[0].masks['sp'] = None
     eng.forward(training=False, dropout_rate=0.0)
     torch.cuda.synchronize()
