@@ -28,7 +28,8 @@ AE = 'autoencoder'
 VAE = 'variational_autoencoder'
 CEVAE = 'context_encoder_variational_autoencoder'
 AES = 'autoencoder_spatial'
-ARCHS = (AE, VAE, CEVAE, AES)
+CAE = 'constrained_autoencoder'
+ARCHS = (AE, VAE, CEVAE, AES, CAE)
 
 
 # --------------------------------------------------------------------------- layer plan
@@ -71,7 +72,7 @@ def init_params(arch: str, S: int, C: int = 1, zDim: int = 128, res: int = 8, se
         P['Bottleneck/conv2d_1/kernel'] = _glorot(rng, (1, 1, cb, cin), cb, cin)
         P['Bottleneck/conv2d_1/bias'] = np.zeros(cin, np.float32)
         flat = res * res * cb
-        heads = 1 if arch == AE else 2
+        heads = 1 if arch in (AE, CAE) else 2
         for h in range(heads):
             nm = 'dense' if h == 0 else f'dense_{h}'
             P[f'Bottleneck/{nm}/kernel'] = _glorot(rng, (flat, zDim), flat, zDim)
@@ -224,13 +225,22 @@ def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, tr
     res, cb = h.shape[2], h.shape[1]
     flat = _flatten_nhwc(h)
 
-    if arch == AE:
-        # autoencoder.py:29-30: dropout on z honours the flag; dropout on dec_dense(z) is called WITHOUT the flag -> identity
+    if arch in (AE, CAE):
+        # autoencoder.py:29-30: dropout on z honours the flag; dropout on dec_dense(z) is called WITHOUT the flag -> identity.
+        # constrained_autoencoder.py:29-30: both honour it (masks 'z', 'dec'), and x_hat is re-encoded by the SAME layers
+        # (:42-46) with a third, independent Dropout draw (mask 'z_rec').
         z = dropout(flat @ P['Bottleneck/dense/kernel'] + P['Bottleneck/dense/bias'], M('z'), dropout_rate, training)
         out['z'] = z
         d = z @ P['Bottleneck/dense_1/kernel'] + P['Bottleneck/dense_1/bias']
+        if arch == CAE:
+            d = dropout(d, M('dec'), dropout_rate, training)
         h = conv1x1(_unflatten_nhwc(d, res, cb), P['Bottleneck/conv2d_1/kernel'], P['Bottleneck/conv2d_1/bias'])
-        out['x_hat'] = decoder(P, h).permute(0, 2, 3, 1)
+        xh = decoder(P, h)
+        out['x_hat'] = xh.permute(0, 2, 3, 1)
+        if arch == CAE:
+            h2 = conv1x1(encoder(P, xh), P['Bottleneck/conv2d/kernel'], P['Bottleneck/conv2d/bias'])
+            out['z_rec'] = dropout(_flatten_nhwc(h2) @ P['Bottleneck/dense/kernel'] + P['Bottleneck/dense/bias'], M('z_rec'),
+                                   dropout_rate, training)
         return out
 
     mu = dropout(flat @ P['Bottleneck/dense/kernel'] + P['Bottleneck/dense/bias'], M('mu'), dropout_rate, training)
@@ -253,7 +263,7 @@ def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, tr
     return out
 
 
-def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_ce=None):
+def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_ce=None, rho=1.0):
     """trainers/AE.py:28-29, VAE.py:36-42, ceVAE.py:38-50.
 
     l1_sign / l1_sign_ce (test aid, default None = the literal |.|): evaluate |u| as u*sign with a CALLER-FIXED sign
@@ -264,6 +274,15 @@ def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_c
     L = {}
     l1 = (out['x_hat'] - xt).abs() if l1_sign is None else (out['x_hat'] - xt) * _t(l1_sign, dtype)
     rec = l1.sum(dim=(1, 2, 3))
+    if arch == CAE:
+        # trainers/ConstrainedAE.py:37-43 (tf.losses.mean_squared_error with Reduction.NONE = squared difference)
+        L['L1'] = l1
+        L['reconstructionLoss'] = rec.mean()
+        l2 = ((out['x_hat'] - xt) ** 2).mean(dim=(1, 2, 3))
+        rec_z = ((out['z'] - out['z_rec']) ** 2).mean(dim=1)
+        L['L2'], L['Rec_z'] = l2.mean(), rec_z.mean()
+        L['loss'] = (l2 + rho * rec_z).mean()
+        return L
     if arch in (AE, AES):
         L['L1'] = l1
         L['reconstructionLoss'] = L['loss'] = rec.mean()
@@ -290,12 +309,12 @@ def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_c
 
 
 def loss_and_grads(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, training=True, dtype=torch.float32,
-                   want_anomaly=False, l1_sign=None, l1_sign_ce=None):
+                   want_anomaly=False, l1_sign=None, l1_sign_ce=None, rho=1.0):
     """tf.gradients of losses['loss'] w.r.t. every trainable variable (DLMODEL.py:112-131); ceVAE 'anomaly' (ceVAE.py:51)."""
     Pt = OrderedDict((k, _t(v, dtype).clone().requires_grad_(True)) for k, v in P.items())
     xt = _t(x, dtype).clone().requires_grad_(want_anomaly)
     out = forward(arch, Pt, xt, x_ce=x_ce, eps=eps, masks=masks, dropout_rate=dropout_rate, training=training, dtype=dtype)
-    L = losses(arch, out, xt, x_ce=x_ce, dtype=dtype, l1_sign=l1_sign, l1_sign_ce=l1_sign_ce)
+    L = losses(arch, out, xt, x_ce=x_ce, dtype=dtype, l1_sign=l1_sign, l1_sign_ce=l1_sign_ce, rho=rho)
     names = list(Pt.keys())
     grads = torch.autograd.grad(L['loss'], [Pt[k] for k in names], retain_graph=want_anomaly, allow_unused=True)
     G = OrderedDict((k, (g if g is not None else torch.zeros_like(Pt[k])).detach()) for k, g in zip(names, grads))

@@ -164,3 +164,66 @@ def test_spatial_autoencoder_step_parity(S, B, mode):
     torch.cuda.synchronize()
     out2 = O.forward(O.AES, P, x, training=False, dtype=torch.float64)
     assert _relerr(eng.br[0].xhat.cpu().numpy(), out2['x_hat'].numpy()) < TOL
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('S,B,rho', [(64, 4, 1.0), (128, 2, 0.7)])
+def test_constrained_autoencoder_step_parity(S, B, rho, mode):
+    """models/constrained_autoencoder.py + trainers/ConstrainedAE.py:37-43: x -> z -> x_hat -> z_rec through shared layers,
+    loss = mean_b(L2 + rho*Rec_z).  Losses, x_hat, z, z_rec and every gradient (the Encoder's accumulate over both passes)
+    against the float64 oracle."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import CAE, ConvAutoencoderEngine
+    rate, lr = 0.2, 1e-3
+    P = O.perturb_params(O.init_params(O.CAE, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=31)
+    eng = ConvAutoencoderEngine(CAE, S, batch=B, math_mode=mode)
+    assert list(eng.specs.keys()) == list(P.keys())
+    eng.fp.load(P)
+    eng.rho = rho
+    rng = np.random.default_rng(8)
+
+    def mk(n):
+        return (rng.uniform(size=(B, n)) >= rate).astype(np.float32)
+
+    om = {'z': mk(128), 'dec': mk(eng.flat), 'z_rec': mk(128)}
+    eng.set_inputs(x)
+    eng.set_noise(None, {'mu': om['z'], 'dec': om['dec']}, {'mu': om['z_rec']})
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True)
+    torch.cuda.synchronize()
+    out, L, G = O.loss_and_grads(O.CAE, P, x, masks=om, dropout_rate=rate, training=True, dtype=torch.float64, rho=rho)
+    assert _relerr(eng.br[0].xhat.cpu().numpy(), out['x_hat'].numpy()) < TOL
+    assert _relerr(eng.br[0].mu.cpu().numpy(), out['z'].numpy()) < TOL
+    assert _relerr(eng.br[1].mu.cpu().numpy(), out['z_rec'].numpy()) < TOL
+    got = eng.losses()
+    for k in ('loss', 'L2', 'Rec_z', 'reconstructionLoss'):
+        assert abs(got[k] - float(L[k])) / abs(float(L[k])) < TOL, (k, got[k], float(L[k]))
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    worst = max((_relerr(grads[k], G[k].numpy()), k) for k in P)
+    assert worst[0] < 5 * TOL, worst          # smooth (squared) losses: no sub-gradient choice involved
+
+
+def test_constrained_ae_trainer_surface(tmp_path):
+    from unsupervised_anomaly_detection_brain_mri_b200.models.constrained_autoencoder import constrained_autoencoder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.ConstrainedAE import ConstrainedAE
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_datasets, get_options
+    assert ConstrainedAE.Config().rho == 1 and ConstrainedAE.Config().modelname == 'ConstrainedAE'
+    cfgjson = {'CHECKPOINTDIR': str(tmp_path / 'ckpt'), 'SAMPLEDIR': str(tmp_path / 'samples'), 'BRAINWEBDIR': ''}
+    options = get_options(batchsize=8, learningrate=1e-3, numEpochs=2, zDim=256, outputWidth=64, outputHeight=64, slices_start=20,
+                          slices_end=60, config=cfgjson)
+    options['data']['numPatients'] = 2
+    options['data']['numTestPatients'] = 1
+    hc, _ = get_datasets(options)
+    config = get_config(ConstrainedAE, options, 'ADAM', [16, 16], 0.1, hc)     # mains/main_constrainedAE.py uses res 16
+    config.useTensorboard = False
+    config.verbose = False
+    config.rho = 1
+    model = ConstrainedAE(None, config, network=constrained_autoencoder)
+    x = hc.next_batch(8, set='TRAIN')[0]
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.logger import Phase
+    first = model.run_batch(x, Phase.TRAIN)
+    model.train(hc)
+    last = model.run_batch(x, Phase.VAL)
+    assert set(('loss', 'L2', 'Rec_z', 'reconstructionLoss')) <= set(last)
+    assert np.isfinite(last['loss']) and last['loss'] < first['loss']
+    r = model.reconstruct(x)
+    assert r['reconstruction'].shape == x.shape and np.isfinite(r['l1err'])

@@ -160,3 +160,48 @@ def test_early_stopping_rule():
         best, last, stop = indicate_early_stopping(c, best, last)
         stops.append(stop)
     assert stops == [False, False, False, False, False, False, True]
+
+
+def test_sibling_models_and_trainers_keep_reference_protocol():
+    """models/autoencoder_spatial.py, models/constrained_autoencoder.py, trainers/ConstrainedAE.py, trainers/VAE_You.py:
+    names, output keys and Config defaults of the reference (looked up BY NAME from run.py:21-24)."""
+    import importlib
+    PKG = 'unsupervised_anomaly_detection_brain_mri_b200'
+
+    class C:
+        zDim, intermediateResolutions, outputWidth, numChannels = 128, [8, 8], 128, 1
+    x = Placeholder([None, 128, 128, 1])
+    for mname, keys in (('autoencoder_spatial', {'z', 'x_hat'}), ('constrained_autoencoder', {'z', 'x_hat', 'z_rec'})):
+        fn = getattr(importlib.import_module(f'{PKG}.models.{mname}'), mname)
+        assert fn.__name__ == mname
+        out = fn(x, 0.2, False, C)
+        assert set(out) == keys and out['x_hat'].graph.arch == mname
+    cae = getattr(importlib.import_module(f'{PKG}.trainers.ConstrainedAE'), 'ConstrainedAE')
+    assert cae.Config().rho == 1 and cae.Config().modelname == 'ConstrainedAE'          # ConstrainedAE.py:13-16
+    you = getattr(importlib.import_module(f'{PKG}.trainers.VAE_You'), 'VAE_You')
+    c = you.Config()
+    assert (c.modelname, c.restore_lr, c.restore_steps, c.tv_lambda) == ('VAE_You', 1e-3, 150, 1.8)   # VAE_You.py:13-18
+    # the constrained AE shares the dense AE's variables (the re-encoding pass reuses the layers)
+    assert list(E.param_specs(E.CAE, 128)) == list(E.param_specs(E.AE, 128))
+    assert not any(k.startswith('Bottleneck/') for k in E.param_specs(E.AES, 128))
+    for m in ('main_AE_spatial.py', 'main_constrainedAE.py', 'main_VAE_You.py'):
+        assert os.path.isfile(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'mains', m))
+
+
+def test_oracle_constrained_and_spatial_graphs_consistent():
+    """The oracle's sibling graphs reduce to compositions of its own pieces (no dropout): z_rec == Enc(x_hat), and the
+    spatial AE equals decoder(encoder(x))."""
+    P = O.perturb_params(O.init_params(O.CAE, 32, seed=4))
+    x = O.synthetic_slices(2, 32, seed=9)
+    out = O.forward(O.CAE, P, x, dtype=torch.float64)
+    again = O.forward(O.CAE, P, out['x_hat'].numpy(), dtype=torch.float64)
+    assert torch.allclose(out['z_rec'], again['z'], rtol=1e-12, atol=1e-12)
+    L = O.losses(O.CAE, out, x, dtype=torch.float64, rho=0.5)
+    l2 = ((out['x_hat'].numpy() - x) ** 2).mean(axis=(1, 2, 3))
+    rz = ((out['z'].numpy() - out['z_rec'].numpy()) ** 2).mean(axis=1)
+    assert np.isclose(float(L['loss']), float((l2 + 0.5 * rz).mean()))
+    Ps = O.perturb_params(O.init_params(O.AES, 32, seed=4))
+    outs = O.forward(O.AES, Ps, x, dtype=torch.float64)
+    Pt = {k: torch.from_numpy(v).double() for k, v in Ps.items()}
+    ref = O.decoder(Pt, O.encoder(Pt, torch.from_numpy(x).double().permute(0, 3, 1, 2))).permute(0, 2, 3, 1)
+    assert torch.allclose(outs['x_hat'], ref)

@@ -32,7 +32,29 @@ AE = 'autoencoder'
 VAE = 'variational_autoencoder'
 CEVAE = 'context_encoder_variational_autoencoder'
 AES = 'autoencoder_spatial'      # encoder -> Dropout -> decoder, no dense bottleneck (reference models/autoencoder_spatial.py)
-ARCHS = (AE, VAE, CEVAE, AES)
+CAE = 'constrained_autoencoder'  # dense AE whose reconstruction is re-encoded: z_rec = Enc(x_hat) (models/constrained_autoencoder.py)
+ARCHS = (AE, VAE, CEVAE, AES, CAE)
+
+
+import contextlib
+import gc
+
+
+@contextlib.contextmanager
+def graph_capture(graph):
+    """torch.cuda.graph with two guards.  (1) The cyclic GC is paused: a collection that runs inside the capture window can
+    finalise objects of earlier work (pinned staging buffers, events, other engines) whose destructors issue CUDA calls that
+    are illegal while a stream captures - observed as cudaErrorStreamCaptureInvalidated in the middle of a long test
+    session.  (2) capture_error_mode='thread_local': only this thread's calls are checked, so a data-loader or logging
+    thread of the host application cannot invalidate the capture either."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+            yield
+    finally:
+        if was:
+            gc.enable()
 
 
 def stack_plan(S, res=8):
@@ -65,7 +87,7 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
         sp['Bottleneck/conv2d_1/bias'] = (cin,)
         flat = res * res * cb
-        heads = 1 if arch == AE else 2
+        heads = 1 if arch in (AE, CAE) else 2
         for h in range(heads):
             nm = 'dense' if h == 0 else f'dense_{h}'
             sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
@@ -207,10 +229,10 @@ class ConvAutoencoderEngine:
     def _new(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.device)
 
-    def _alloc_branch(self):
+    def _alloc_branch(self, encoder_only=False, x=None):
         B, S = self.B, self.S
         br = _Branch()
-        br.x = self._new(B, S, S, 1)
+        br.x = self._new(B, S, S, 1) if x is None else x
         br.enc_z, br.enc_a = [], []
         s = S
         for co in self.enc_ch:
@@ -224,6 +246,10 @@ class ConvAutoencoderEngine:
         br.sigma = self._new(B, self.zDim)
         br.zv = self._new(B, self.zDim)
         br.kl = self._new(B)
+        br.masks = {k: None for k in ('mu', 'ls', 'dec', 'sp')}
+        br.mask_bufs = {'mu': self._new(B, self.zDim)}
+        if encoder_only:                                 # the re-encoding pass of the constrained AE: x_hat -> z_rec
+            return br
         br.d = self._new(B, self.flat)                   # dec_dense output (post-dropout)
         br.zr = self._new(B, r, r, self.enc_ch[-1])      # conv2d_1 output (pre decoder-BN)
         br.ar = self._new(B, r, r, self.enc_ch[-1])      # after decoder BN + ReLU
@@ -237,8 +263,7 @@ class ConvAutoencoderEngine:
         br.l1 = self._new(B, S, S, 1)
         br.rec = self._new(B)
         br.eps = self._new(B, self.zDim)
-        br.masks = {k: None for k in ('mu', 'ls', 'dec', 'sp')}
-        br.mask_bufs = {'mu': self._new(B, self.zDim), 'ls': self._new(B, self.zDim), 'dec': self._new(B, self.flat)}
+        br.mask_bufs.update(ls=self._new(B, self.zDim), dec=self._new(B, self.flat))
         if self.arch == AES:
             br.mask_bufs['sp'] = self._new(B, r, r, self.enc_ch[-1])      # Dropout on the spatial code z [B,res,res,C]
         return br
@@ -248,6 +273,11 @@ class ConvAutoencoderEngine:
         self.br = [self._alloc_branch()]
         if self.arch == CEVAE:
             self.br.append(self._alloc_branch())
+        if self.arch == CAE:
+            self.br.append(self._alloc_branch(encoder_only=True, x=self.br[0].xhat))
+            self.gxhat = self._new(B, S, S, 1)           # d loss / d x_hat: MSE term + the re-encoding pass
+            self.dzrec = self._new(B, self.zDim)
+            self.rho = 1.0                               # trainers/ConstrainedAE.py:16
         big = B * S * S * max(32, self.dec_ch[-1])
         self.gbuf = [self._new(big), self._new(big)]
         self.gx = self._new(B, S, S, 1)                  # d loss / d x (ceVAE anomaly)
@@ -337,6 +367,15 @@ class ConvAutoencoderEngine:
                 br.masks['sp'] = None
             call('uad_counter_add', ctr, 1 << 20, st)
             return
+        if self.arch == CAE:                             # three Dropout calls: z, dec_dense(z), z_rec (each its own draw)
+            on = bool(dropout) and rate > 0
+            for sid, (br, k) in enumerate(((self.br[0], 'mu'), (self.br[0], 'dec'), (self.br[1], 'mu'))):
+                if on:
+                    call('uad_dropout_mask', ptr(br.mask_bufs[k]), br.mask_bufs[k].numel(), float(rate), self.rng_seed,
+                         (sid + 1) << 40, ctr, st)
+                br.masks[k] = br.mask_bufs[k] if on else None
+            call('uad_counter_add', ctr, 1 << 20, st)
+            return
         for bi, br in enumerate(self.br):
             if self.arch != AE and bi == 0:
                 call('uad_randn', ptr(br.eps), br.eps.numel(), self.rng_seed, nb << 40, ctr, st)
@@ -380,11 +419,14 @@ class ConvAutoencoderEngine:
                  1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             if self.arch == AES:
                 pass
-            elif self.arch == AE:
-                # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity
+            elif self.arch in (AE, CAE):
+                # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity.
+                # constrained_autoencoder.py:29-30: BOTH dropout calls honour the flag.
                 self._op('bneck02', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
                      ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
-                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', None
+                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', (m['dec'] if self.arch == CAE else None)
+                if is_ce:                                # constrained AE, re-encoding pass: z_rec is all that is needed
+                    continue
             else:
                 self._op('bneck03', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
                      ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
@@ -418,7 +460,15 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES) else None, ptr(self.scalars), B, st)
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE) else None, ptr(self.scalars), B, st)
+        if self.arch == CAE and (branches is None or 1 in branches):
+            # trainers/ConstrainedAE.py:37-43: L2 = mean_hwc (x - x_hat)^2, Rec_z = mean_j (z - z_rec)^2 (per sample);
+            # loss = mean_b(L2 + rho * Rec_z).  The same calls leave d loss/d x_hat and d loss/d z_rec (d/dz = -d/dz_rec).
+            nx, nz = b0.x.numel(), B * self.zDim
+            self._op('bneck09', 'uad_mse', ptr(b0.xhat), ptr(b0.x), nx, 2.0 / nx, ptr(self.gxhat), 1.0 / nx, self.scalars[4:].data_ptr(),
+                     ws, wsb, st)
+            self._op('bneck09', 'uad_mse', ptr(self.br[1].mu), ptr(b0.mu), nz, 2.0 * self.rho / nz, ptr(self.dzrec), 1.0 / nz,
+                     self.scalars[5:].data_ptr(), ws, wsb, st)
         if self.arch == CEVAE and (branches is None or 1 in branches):
             self._op('bneck09', 'uad_loss_scalars', ptr(self.br[1].rec), None, ptr(self.scalars[3:]), B, st)
 
@@ -538,6 +588,100 @@ class ConvAutoencoderEngine:
 
     _keep = 1.0
 
+    # ------------------------------------------------------------------ constrained AE backward
+    def _encoder_backward(self, br, g, gn, acc, dx_out):
+        """Reverse of the encoder stack for one pass (BN/LeakyReLU backward, wgrad, dgrad per block); g holds the gradient
+        w.r.t. the last encoder activation.  dx_out (nullable): receives d/d(input image) (first layer dgrad, Cin = 1)."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsargs()
+        B = self.B
+        kp = self.keep_preact
+        act_blk = ACT_LEAKY if kp else (ACT_LEAKY | abi.ACT_FROM_OUTPUT)
+        s = self.res
+        for i in reversed(range(self.n)):
+            co = self.enc_ch[i]
+            ci = self.enc_ch[i - 1] if i > 0 else 1
+            pre = f'Encoder/enc_conv2D_{i}'
+            bnn = f'Encoder/{_bn(i)}'
+            self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(br.enc_z[i] if kp else br.enc_a[i]), ptr(fp.p(bnn + '/gamma')),
+                     ptr(fp.p(bnn + '/beta')), ptr(g), ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')),
+                     B * s * s, co, act_blk, LRELU_ALPHA, BN_C, acc, ws, wsb, st)
+            xin = br.enc_a[i - 1] if i > 0 else br.x
+            self._op(pre.split('/')[-1], 'uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE,
+                     acc, mm, ws, wsb, st)
+            if i > 0:
+                self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, 2 * s, 2 * s, ci, co, KSIZE,
+                         mm, ws, wsb, st)
+                g, gn = gn, g
+            elif dx_out is not None:
+                self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(dx_out), B, 2 * s, 2 * s, ci, co,
+                         KSIZE, mm, ws, wsb, st)
+            s *= 2
+
+    def backward_constrained(self):
+        """tf.gradients of loss = mean_b(L2 + rho*Rec_z) (trainers/ConstrainedAE.py:37-43) through
+        x -> Enc -> z -> Dec -> x_hat -> Enc -> z_rec (models/constrained_autoencoder.py:12-46, shared weights).
+        Order: the re-encoding pass first (it yields d/d x_hat), then decoder + bottleneck + first encoder pass, whose
+        Encoder / Bottleneck-dense gradients ACCUMULATE onto the re-encoding pass's."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsargs()
+        B, b0, b1, sm = self.B, self.br[0], self.br[1], self.small
+        r2 = self.res * self.res
+        ctop = self.enc_ch[-1]
+        keep = self._keep
+        kp = self.keep_preact
+        act_blk = ACT_LEAKY if kp else (ACT_LEAKY | abi.ACT_FROM_OUTPUT)
+        g, gn = self.gbuf
+        # ---- pass 2 (x_hat -> z_rec): seed dzrec = d loss / d z_rec (left by forward)
+        self._op('bneck20', 'uad_dense_bwd', ptr(b1.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(self.dzrec), ptr(b1.masks['mu']), keep,
+                 ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B, self.flat, self.zDim,
+                 0, ws, wsb, st)
+        self._op('bneck21', 'uad_dense_bwd', ptr(b1.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0, ptr(g),
+                 ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb, 0, ws, wsb, st)
+        self._encoder_backward(b1, g, gn, 0, self.gx)
+        # d loss / d x_hat = MSE term (in gxhat) + the path through the re-encoding pass (in gx)
+        self._op('bneck22', 'uad_axpby', 1.0, ptr(self.gx), 1.0, ptr(self.gxhat), b0.x.numel(), st)
+        # ---- decoder
+        g, gn = self.gbuf
+        cin = self.dec_ch[-1]
+        self._op('dec_Conv2D_final', 'uad_final1x1_bwd', ptr(b0.dec_a[-1]), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(self.gxhat),
+                 ptr(g), ptr(fp.g('Decoder/dec_Conv2D_final/kernel')), ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B, self.S * self.S,
+                 cin, 0, ws, wsb, st)
+        s = self.S
+        for i in reversed(range(self.n)):
+            co = self.dec_ch[i]
+            ci = self.dec_ch[i - 1] if i > 0 else ctop
+            pre = f'Decoder/dec_Conv2DT_{i}'
+            bnn = f'Decoder/{_bn(self.n + 1 + i)}'
+            self._op(pre.split('/')[-1], 'uad_act_bn_bwd', ptr(g), ptr(b0.dec_z[i] if kp else b0.dec_a[i]), ptr(fp.p(bnn + '/gamma')),
+                     ptr(fp.p(bnn + '/beta')), ptr(g), ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')),
+                     B * s * s, co, act_blk, LRELU_ALPHA, BN_C, 0, ws, wsb, st)
+            xin = b0.dec_a[i - 1] if i > 0 else b0.ar
+            self._op(pre.split('/')[-1], 'uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
+                     0, mm, ws, wsb, st)
+            self._op(pre.split('/')[-1], 'uad_convT2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, s // 2, s // 2, ci, co, KSIZE,
+                     mm, ws, wsb, st)
+            g, gn = gn, g
+            s //= 2
+        dbn = f'Decoder/{_bn(self.n)}'
+        self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(b0.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
+                 ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')), B * r2, ctop, ACT_RELU, 0.0,
+                 BN_C, 0, ws, wsb, st)
+        # ---- bottleneck: conv2d_1, dec_dense (dense_1, Dropout honoured), then z = Dropout(dense(...)) with the extra -dzrec
+        self._op('bneck10', 'uad_dense_bwd', ptr(b0.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, 0, ws, wsb, st)
+        self._op('bneck11', 'uad_dense_bwd', ptr(b0.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), ptr(b0.masks['dec']), keep,
+                 ptr(sm['dmu']), ptr(fp.g('Bottleneck/dense_1/kernel')), ptr(fp.g('Bottleneck/dense_1/bias')), B, self.zDim, self.flat,
+                 0, ws, wsb, st)
+        self._op('bneck23', 'uad_axpby', -1.0, ptr(self.dzrec), 1.0, ptr(sm['dmu']), B * self.zDim, st)     # d Rec_z / d z = -d/d z_rec
+        self._op('bneck12', 'uad_dense_bwd', ptr(b0.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(b0.masks['mu']), keep,
+                 ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B, self.flat, self.zDim,
+                 1, ws, wsb, st)
+        self._op('bneck18', 'uad_dense_bwd', ptr(b0.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0, ptr(g),
+                 ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb, 1, ws, wsb, st)
+        # ---- pass 1 encoder (accumulating)
+        self._encoder_backward(b0, g, gn, 1, None)
+
     # ------------------------------------------------------------------ gradient w.r.t. the input only (restoration)
     def backward_to_input(self, seed, kl_scale=1.0):
         """d/dx of  <seed, x_hat(x)> + kl_scale * sum_b kl_b(x)  through the x-branch: the dgrad-only chain (no weight
@@ -654,7 +798,7 @@ class ConvAutoencoderEngine:
             return
         if self._restore_graph is None and steps > done:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with graph_capture(g):
                 self.restore_step(restore_lr, tv_lambda, dropout, dropout_rate)
             self._restore_graph = g
         for _ in range(done, steps):
@@ -676,6 +820,9 @@ class ConvAutoencoderEngine:
         if not parity_noise:
             self.draw_noise(dropout, rate)
         self.forward(training=True, dropout_rate=rate)
+        if self.arch == CAE:
+            self.backward_constrained()
+            return
         self.backward(want_input_grad=want_anomaly)
         if want_anomaly and self.arch == CEVAE:
             self._finish_anomaly()
@@ -694,7 +841,7 @@ class ConvAutoencoderEngine:
             if self.graph is None:
                 g = torch.cuda.CUDAGraph()
                 t_save = self.t
-                with torch.cuda.graph(g):
+                with graph_capture(g):
                     self._fwd_bwd(rate, dropout, False, want_anomaly)
                     if allreduce is None:
                         self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
@@ -730,6 +877,9 @@ class ConvAutoencoderEngine:
         s = self.scalars.detach().cpu().numpy()
         if self.arch in (AE, AES):
             return {'reconstructionLoss': float(s[0]), 'loss': float(s[0])}
+        if self.arch == CAE:
+            return {'reconstructionLoss': float(s[0]), 'L2': float(s[4]), 'Rec_z': float(s[5]),
+                    'loss': float(s[4]) + self.rho * float(s[5])}
         if self.arch == VAE:
             return {'reconstructionLoss': float(s[0]), 'kl': float(s[1]), 'loss': float(s[2])}
         return {'Rec_vae': float(s[0]), 'kl': float(s[1]), 'loss_vae': float(s[2]), 'Rec_ce': float(s[3]),

@@ -18,7 +18,7 @@ import torch
 from . import abi
 from .abi import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, OP_CONV_DGRAD, OP_CONV_FWD, OP_CONV_WGRAD, OP_CONVT_DGRAD,
                   OP_CONVT_FWD, OP_CONVT_WGRAD, call, ptr)
-from .engine import BN_C, KSIZE, LRELU_ALPHA, FlatParams, glorot_init, stack_plan
+from .engine import BN_C, KSIZE, LRELU_ALPHA, FlatParams, glorot_init, graph_capture, stack_plan
 
 LN_EPS = 1e-3
 
@@ -503,7 +503,7 @@ class FanoganEngine:
         if g is None and self._warm.get(name) == key:
             t_save = dict(self.t)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with graph_capture(g):
                 body()
             self.t = t_save                       # capture does not execute: undo the host-side step bookkeeping
             self._graphs[k] = g
