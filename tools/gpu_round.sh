@@ -19,10 +19,12 @@ cat gpurun_out/${TAG}_restore.json
 timeout 300 python tools/config_times.py 20 > gpurun_out/${TAG}_configs.json 2> gpurun_out/${TAG}_configs.err
 cat gpurun_out/${TAG}_configs.json
 if [ "${2:-}" = "ncu" ]; then
-  # launch list of one eager step (second of two) and one --set full capture of every tcgen05 launch of that step
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 140 -c 160 --csv --log-file gpurun_out/${TAG}_launches.csv \
+  # launch list of one eager step (the second of two) and a --set full capture of the launches selected by $3 (regex)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 128 -c 128 --csv --log-file gpurun_out/${TAG}_launches.csv \
       python tools/profile_step.py 2 tc3 > gpurun_out/${TAG}_ncu1.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:gather_gemm_tc|wgrad_tc' -s 27 -c 27 \
+  KRE=${3:-gather_gemm_tc|wgrad_tc}
+  NK=${4:-27}
+  timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${KRE}" -s ${NK} -c ${NK} \
       -o gpurun_out/${TAG}_tc python tools/profile_step.py 2 tc3 > gpurun_out/${TAG}_ncu2.log 2>&1
   ncu -i gpurun_out/${TAG}_tc.ncu-rep --page raw --csv > gpurun_out/${TAG}_tc_raw.csv 2>/dev/null
   ls -la gpurun_out/ | tail -20
