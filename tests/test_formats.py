@@ -69,11 +69,11 @@ def test_example_encoding_matches_protobuf_runtime():
     assert ex.SerializeToString(deterministic=True) == mine           # ... and re-serialises them to the same bytes
     # and the hand-written decoder parses what the runtime writes (any field order, floats included)
     ex2 = Example()
-    ex2.features.feature['set'].bytes_list.value.append(b'\\x01\\x00\\x00\\x00')
+    ex2.features.feature['set'].bytes_list.value.append(b'\x01\x00\x00\x00')
     ex2.features.feature['w'].float_list.value.extend([1.5, -2.0])
     ex2.features.feature['n'].int64_list.value.extend([5, -1, 1 << 40])
     got = T.decode_example(ex2.SerializeToString())
-    assert got['set'] == ('bytes', [b'\\x01\\x00\\x00\\x00']) and got['w'] == ('float', [1.5, -2.0])
+    assert got['set'] == ('bytes', [b'\x01\x00\x00\x00']) and got['w'] == ('float', [1.5, -2.0])
     assert got['n'] == ('int64', [5, -1, 1 << 40])
 
 
@@ -103,3 +103,156 @@ def test_tfrecord_roundtrip_and_framing(tmp_path):
     open(fn, 'wb').write(bytes(bad))
     with pytest.raises(IOError):
         T.read_tf_record(fn)
+
+
+# ------------------------------------------------------------------------------------------------ tensor bundle (Saver V2)
+def _bundle_classes():
+    """tensorflow/core/protobuf/tensor_bundle.proto (+ the pieces of tensor_shape.proto / versions.proto it uses)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name='uad_test_bundle.proto', package='uadb', syntax='proto3')
+    F = descriptor_pb2.FieldDescriptorProto
+    ver = fd.message_type.add(name='VersionDef')
+    ver.field.add(name='producer', number=1, label=F.LABEL_OPTIONAL, type=F.TYPE_INT32)
+    ver.field.add(name='min_consumer', number=2, label=F.LABEL_OPTIONAL, type=F.TYPE_INT32)
+    shp = fd.message_type.add(name='TensorShapeProto')
+    dim = shp.nested_type.add(name='Dim')
+    dim.field.add(name='size', number=1, label=F.LABEL_OPTIONAL, type=F.TYPE_INT64)
+    dim.field.add(name='name', number=2, label=F.LABEL_OPTIONAL, type=F.TYPE_STRING)
+    shp.field.add(name='dim', number=2, label=F.LABEL_REPEATED, type=F.TYPE_MESSAGE, type_name='.uadb.TensorShapeProto.Dim')
+    shp.field.add(name='unknown_rank', number=3, label=F.LABEL_OPTIONAL, type=F.TYPE_BOOL)
+    hdr = fd.message_type.add(name='BundleHeaderProto')
+    hdr.field.add(name='num_shards', number=1, label=F.LABEL_OPTIONAL, type=F.TYPE_INT32)
+    hdr.field.add(name='endianness', number=2, label=F.LABEL_OPTIONAL, type=F.TYPE_INT32)       # enum LITTLE = 0, BIG = 1
+    hdr.field.add(name='version', number=3, label=F.LABEL_OPTIONAL, type=F.TYPE_MESSAGE, type_name='.uadb.VersionDef')
+    ent = fd.message_type.add(name='BundleEntryProto')
+    ent.field.add(name='dtype', number=1, label=F.LABEL_OPTIONAL, type=F.TYPE_INT32)            # enum DataType
+    ent.field.add(name='shape', number=2, label=F.LABEL_OPTIONAL, type=F.TYPE_MESSAGE, type_name='.uadb.TensorShapeProto')
+    ent.field.add(name='shard_id', number=3, label=F.LABEL_OPTIONAL, type=F.TYPE_INT32)
+    ent.field.add(name='offset', number=4, label=F.LABEL_OPTIONAL, type=F.TYPE_INT64)
+    ent.field.add(name='size', number=5, label=F.LABEL_OPTIONAL, type=F.TYPE_INT64)
+    ent.field.add(name='crc32c', number=6, label=F.LABEL_OPTIONAL, type=F.TYPE_FIXED32)
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName('uadb.' + n))   # noqa: E731
+    return get('BundleHeaderProto'), get('BundleEntryProto')
+
+
+def test_bundle_protos_match_protobuf_runtime():
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import tf_checkpoint as C
+    Header, Entry = _bundle_classes()
+    h = Header()
+    h.ParseFromString(C.encode_header(1))
+    assert (h.num_shards, h.endianness, h.version.producer) == (1, 0, 1)
+    assert h.SerializeToString(deterministic=True) == C.encode_header(1)
+    raw = C.encode_entry(np.float32, (5, 5, 32, 64), offset=1234567, size=204800, crc_masked=0xDEADBEEF)
+    e = Entry()
+    e.ParseFromString(raw)
+    assert (e.dtype, [d.size for d in e.shape.dim], e.shard_id, e.offset, e.size, e.crc32c) == (1, [5, 5, 32, 64], 0, 1234567, 204800, 0xDEADBEEF)
+    assert e.SerializeToString(deterministic=True) == raw
+    e2 = Entry(dtype=9, offset=0, size=8, crc32c=7)                  # scalar int64 (e.g. a global_step): no dims at all
+    d = C.decode_entry(e2.SerializeToString())
+    assert (d['dtype'], d['shape'], d['offset'], d['size'], d['crc32c']) == (9, [], 0, 8, 7)
+
+
+def test_bundle_roundtrip_table_structure(tmp_path):
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as E
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import tf_checkpoint as C
+    specs = E.param_specs(E.VAE, 256)
+    weights = E.glorot_init(specs, seed=3)
+    rng = np.random.default_rng(0)
+    m = {k: rng.standard_normal(v.shape).astype(np.float32) for k, v in weights.items()}
+    v = {k: rng.random(v.shape).astype(np.float32) for k, v in weights.items()}
+    variables = C.saver_variables(weights, m, v, step=10, beta1=0.5, beta2=0.999)
+    assert 'Encoder/batch_normalization/moving_mean' in variables and 'Decoder/dec_Conv2DT_4/kernel/Adam_1' in variables
+    prefix = str(tmp_path / 'VAE_dSYNTH' / 'VAE.model-3')
+    C.write_bundle(prefix, variables)
+    C.update_checkpoint_state(os.path.dirname(prefix), 'VAE.model-3')
+    assert C.latest_checkpoint(os.path.dirname(prefix)) == prefix
+    header, entries = C.list_bundle(prefix)
+    assert header == {'num_shards': 1, 'endianness': 0, 'producer': 1}
+    assert list(entries) == sorted(variables, key=lambda n: n.encode())              # bytewise key order
+    back = C.read_bundle(prefix)
+    assert all(np.array_equal(back[k], variables[k]) and back[k].shape == np.shape(variables[k]) for k in variables)
+    assert back['beta1_power'].shape == () and np.isclose(back['beta1_power'], 0.5 ** 11)
+    w2, m2, v2, frozen = C.split_saver_variables(back, list(weights))
+    assert frozen and all(np.array_equal(w2[k], weights[k]) and np.array_equal(m2[k], m[k]) for k in weights)
+    # structure of the index file: magic, several data blocks (> 4 KiB of entries), checksummed blocks, prefix compression
+    raw = open(prefix + '.index', 'rb').read()
+    assert struct.unpack('<Q', raw[-8:])[0] == 0xDB4775248B80FB57
+    items = C.parse_table(raw)
+    assert items[0][0] == b'' and len(items) == len(variables) + 1
+    assert len(raw) < sum(len(k) + len(val) for k, val in items) + 2048                # shared key prefixes were elided
+    footer = raw[-48:-8]
+    pos = 0
+    for _ in range(2):
+        _, pos = C._read_varint(footer, pos)
+    ioff, pos = C._read_varint(footer, pos)
+    isize, pos = C._read_varint(footer, pos)
+    assert len(C._read_block(raw, ioff, isize)) >= 2                                   # more than one data block
+    # data file = tensors back to back in key order
+    sizes = [entries[k]['size'] for k in entries]
+    assert [entries[k]['offset'] for k in entries] == list(np.cumsum([0] + sizes[:-1]))
+    assert os.path.getsize(prefix + '.data-00000-of-00001') == sum(sizes)
+    # corruption of a tensor and of an index block is detected
+    data = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+    data[100] ^= 1
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(data))
+    with pytest.raises(IOError):
+        C.read_bundle(prefix)
+    bad = bytearray(raw)
+    bad[10] ^= 1
+    with pytest.raises(IOError):
+        C.parse_table(bytes(bad))
+    # a bundle with non-trivial moving statistics is flagged (the kernels assume the reference's frozen 0 / 1)
+    back['Encoder/batch_normalization/moving_mean'] = np.full_like(back['Encoder/batch_normalization/moving_mean'], 0.1)
+    assert C.split_saver_variables(back, list(weights))[3] is False
+
+
+def test_trainer_tf_checkpoint_export_import_on_cpu(tmp_path):
+    """DLMODEL.export_tf_checkpoint / import_tf_checkpoint with a CPU-resident parameter buffer (no kernels involved)."""
+    import types
+
+    import torch
+
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as E
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.DLMODEL import DLMODEL
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import tf_checkpoint as C
+
+    class T(DLMODEL):
+        def train(self, dataset):
+            pass
+
+    def make(seed):
+        cfg = DLMODEL.Config()
+        cfg.modelname, cfg.dataset, cfg.description = 'VAE', 'SYNTHETIC', 'cpu-test'
+        t = T(None, cfg)
+        specs = E.param_specs(E.VAE, 64)
+        fp = E.FlatParams(specs, 'cpu')
+        fp.load(E.glorot_init(specs, seed))
+        t.engine = types.SimpleNamespace(fp=fp, specs=specs, t=0, step_dev=torch.zeros(1, dtype=torch.int64), adam_step=lambda *a, **k: None)
+        return t
+    a, b = make(1), make(2)
+    rng = np.random.default_rng(0)
+    a.engine.fp.load({k: rng.standard_normal(s).astype(np.float32) for k, s in a.engine.specs.items()}, buf=a.engine.fp.m)
+    a.engine.fp.load({k: rng.random(s).astype(np.float32) for k, s in a.engine.specs.items()}, buf=a.engine.fp.v)
+    a.engine.t = 37
+    # the reference's variable set: no optimiser slots
+    prefix = a.export_tf_checkpoint(str(tmp_path), 4)
+    assert os.path.basename(prefix) == 'VAE.model-4' and os.path.isfile(prefix + '.index')
+    names = list(C.list_bundle(prefix)[1])
+    assert not any(n.endswith('/Adam') for n in names) and 'Decoder/batch_normalization_6/moving_variance' in names
+    assert b.import_tf_checkpoint(os.path.dirname(prefix)) == 4                      # via the `checkpoint` state file
+    wa, wb = a._weights(), b._weights()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa) and b.engine.t == 0
+    # with optimiser state
+    prefix = a.export_tf_checkpoint(str(tmp_path), 5, with_optimizer=True)
+    c = make(3)
+    assert c.import_tf_checkpoint(prefix) == 5
+    assert c.engine.t == 37 and int(c.engine.step_dev) == 37
+    ma, mc = a.engine.fp.to_numpy(a.engine.fp.m), c.engine.fp.to_numpy(c.engine.fp.m)
+    assert all(np.array_equal(ma[k], mc[k]) for k in ma)
+    # a checkpoint of another architecture is refused with a clear error
+    ae = make(1)
+    ae.engine.specs = E.param_specs(E.CEVAE, 128)
+    with pytest.raises((KeyError, ValueError)):
+        ae.import_tf_checkpoint(prefix)

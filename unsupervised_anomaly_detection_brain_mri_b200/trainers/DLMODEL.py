@@ -3,7 +3,8 @@
 Checkpoints keep the reference's directory layout and side files (``<dir>/<model_dir>/<modelname>.model-<step>``,
 ``Config-<step>.json``, ``Curves.npy``, DLMODEL.py:63-84) but store the weights as ``.npz`` keyed by the TF variable
 names instead of a TF tensor bundle.  As in the reference, Adam moments are NOT checkpointed (the Saver is created
-before the optimiser there: AE.py:21 vs :32)."""
+before the optimiser there: AE.py:21 vs :32).  ``export_tf_checkpoint`` / ``import_tf_checkpoint`` additionally write /
+read the reference's own on-disk format (tf.train.Saver V2 tensor bundles, ``utils/tf_checkpoint.py``)."""
 import json
 import os
 import re
@@ -91,6 +92,65 @@ class DLMODEL(object):
             return True, counter
         print(" [*] Failed to find a checkpoint")
         return False, 0
+
+    # ------------------------------------------------------------------ TensorFlow checkpoint files (tf.train.Saver V2)
+    def export_tf_checkpoint(self, checkpoint_dir, step, with_optimizer=False):
+        """Writes `<checkpoint_dir>/<model_dir>/<modelname>.model-<step>.{index,data-00000-of-00001}` + the `checkpoint`
+        state file in the format the reference's `self.saver.save(...)` produces (trainers/DLMODEL.py:66-74), so a
+        TensorFlow installation of the reference can `load()` weights trained here.  Variables: the trainable ones and the
+        (frozen) BatchNormalization moving statistics - exactly the set the reference's Saver holds (it is created before
+        the optimiser, AE.py:21 vs :32, so the Adam slots are NOT in its files); with_optimizer=True adds
+        `<var>/Adam`, `<var>/Adam_1`, `beta1_power`, `beta2_power` as a Saver created after `minimize()` would."""
+        from ..utils import tf_checkpoint as tfc
+        eng = self.engine
+        weights = self._weights()
+        m = v = None
+        if with_optimizer and hasattr(eng, 'adam_step') and isinstance(getattr(eng, 't', None), int):
+            m, v = eng.fp.to_numpy(eng.fp.m), eng.fp.to_numpy(eng.fp.v)
+        variables = tfc.saver_variables(weights, m, v, step=int(getattr(eng, 't', 0)) if m is not None else 0,
+                                        beta1=float(getattr(self.config, 'beta1', 0.5)), beta2=0.999)
+        directory = os.path.join(checkpoint_dir, self.model_dir)
+        name = f'{self.config.modelname}.model-{step}'
+        tfc.write_bundle(os.path.join(directory, name), variables)
+        tfc.update_checkpoint_state(directory, name)
+        return os.path.join(directory, name)
+
+    def import_tf_checkpoint(self, prefix_or_dir, load_optimizer=True):
+        """Loads a TensorFlow checkpoint of the reference (a `...model-<step>` prefix, or a directory holding a `checkpoint`
+        state file) into the engine: weights by TF variable name, Adam moments when present.  Returns the step parsed
+        from the name (reference DLMODEL.load :104).  Raises if a variable is missing, a shape differs, or the file carries
+        BatchNormalization moving statistics other than the 0 / 1 the reference never updates."""
+        from ..utils import tf_checkpoint as tfc
+        prefix = prefix_or_dir
+        if os.path.isdir(prefix_or_dir):
+            prefix = tfc.latest_checkpoint(prefix_or_dir)
+            if prefix is None:
+                raise FileNotFoundError(f'no checkpoint state file in {prefix_or_dir}')
+        variables = tfc.read_bundle(prefix)
+        eng = self.engine
+        wanted = list(eng.specs.keys())
+        missing = [n for n in wanted if n not in variables]
+        if missing:
+            raise KeyError(f'{prefix}: variables missing from the checkpoint: {missing[:4]}{"..." if len(missing) > 4 else ""}')
+        for n in wanted:
+            if tuple(variables[n].shape) != tuple(eng.specs[n]):
+                raise ValueError(f'{prefix}: {n} has shape {variables[n].shape}, the graph needs {tuple(eng.specs[n])}')
+        weights, m, v, frozen = tfc.split_saver_variables(variables, wanted)
+        if not frozen:
+            raise ValueError(f'{prefix}: BatchNormalization moving statistics differ from 0 / 1 - the frozen-BN kernels '
+                             f'(SURVEY App. A.3) would not reproduce this checkpoint')
+        self._load_weights(weights)
+        if load_optimizer and m is not None and hasattr(eng, 'adam_step') and isinstance(getattr(eng, 't', None), int):
+            eng.fp.load(m, buf=eng.fp.m)
+            eng.fp.load(v, buf=eng.fp.v)
+            if 'beta1_power' in variables:                      # beta1_power = beta1^(t+1)  ->  t
+                import math
+                b1 = float(getattr(self.config, 'beta1', 0.5))
+                t = int(round(math.log(float(variables['beta1_power'])) / math.log(b1))) - 1 if 0 < b1 < 1 else 0
+                eng.t = max(t, 0)
+                eng.step_dev.fill_(eng.t)
+        mm = re.search(r'(\d+)(?!.*\d)', os.path.basename(prefix))
+        return int(mm.group(0)) if mm else 0
 
     @staticmethod
     def create_optimizer(loss=None, var_list=(), learningrate=0.001, type='ADAM', beta1=0.05, momentum=0.9, name='optimizer',
