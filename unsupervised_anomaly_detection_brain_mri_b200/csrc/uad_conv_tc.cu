@@ -1410,11 +1410,16 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
   const size_t stage_bytes = kABytes + 2u * N * 128u;
   {
     // ---- v2 role structure (two converter groups, two issuers for N <= 64); UAD_TC_V2=0 selects the first-generation kernel
-    // UAD_TC_V2 (bit mask, developer switch; default 5): 1 = N = 64 layers (dual issue on alternate k-blocks), 4 = N = 128
-    // layers (column-split dual issue; +8: single issuer - measured no faster than the first-generation kernel),
-    // 2 = N = 32 single-class layers (measured SLOWER than the two-CTA-per-SM N = 32 kernel, off by default); 0 = never.
+    // UAD_TC_V2 (bit mask, developer switch; default 1): 1 = N = 64 layers (dual issue on alternate k-blocks), 4 = N = 128
+    // layers (column-split dual issue, measured 13 % faster; +8: single issuer - no faster than the first generation),
+    // 2 = N = 32 single-class layers (measured SLOWER than the two-CTA-per-SM N = 32 kernel); 0 = never.
+    // Why N = 128 is NOT on by default: a role that handles every other k-block must own its stages statically, i.e. the
+    // stage ring must be EVEN (as the slot ring is) - with an odd ring successive uses of full[s] alternate between the
+    // two groups, each group waits with the parity of the use BEFORE the one it skipped and can pass while the skipped
+    // load is still in flight (tests/test_pipeline_protocol.py reproduces it).  N = 128 stages are 48 KB: 3 fit, 4 do not
+    // (yet), 2 would starve the pipe - so those layers stay on the first-generation kernel until the staging buffer shrinks.
     static int use_v2 = -1;
-    if (use_v2 < 0) { const char* e = getenv("UAD_TC_V2"); use_v2 = e ? atoi(e) : 5; }
+    if (use_v2 < 0) { const char* e = getenv("UAD_TC_V2"); use_v2 = e ? atoi(e) : 1; }
     if ((N == 64 && (use_v2 & 1)) || (N == 32 && nclasses == 1 && (use_v2 & 2)) || (N == 128 && (use_v2 & 4))) {
       p.split_n = (N == 128 && !(use_v2 & 8)) ? 1 : 0;
       p.n_issuers = (N <= 64 || p.split_n) ? 2 : 1;
@@ -1427,6 +1432,7 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
       const size_t tail2 = 256 + 3 * N * sizeof(float) + 8 * 32 * 36 * sizeof(float) + 64;
       p.stages = (int)((226 * 1024 - 1024 - tail2) / stage_bytes);
       if (p.stages > 8) p.stages = 8;
+      p.stages &= ~1;                                      // EVEN ring: static stage ownership per converter group / issuer
       UAD_REQUIRE(p.stages >= 2, "gather_gemm_tc2: shared-memory budget exceeded");
       const size_t smem2 = 1024 + p.stages * stage_bytes + tail2;
       static bool attr2 = false;
