@@ -49,7 +49,7 @@ for name, (op, H, Cin, Cout) in cases.items():
         elif op == 'convT_wgrad': call('uad_convT2d_wgrad', x.data_ptr(), y.data_ptr(), dw.data_ptr(), B, H, H, Cin, Cout, 5, 0, 1, ws.data_ptr(), wsb, st())
     res = []
     var = 'UAD_WGRAD_DEBUG' if 'wgrad' in op else 'UAD_TC_DEBUG'
-    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0']
+    modes = ['0', '2', '4', '6'] if 'wgrad' in op else ['0', '1', '2', '3', '96', '99']
     for dbg in modes:
         os.environ[var] = dbg
         res.append(f'{dbg}:{timeit(run):.3f}ms')
