@@ -415,8 +415,8 @@ class ConvAutoencoderEngine:
                 self._op('bneck01', 'uad_mask_bn_act_fwd', ptr(h), ptr(m['sp']), keep, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')),
                          BN_C, ACT_RELU, 0.0, ptr(br.zr), ptr(br.ar), B * r2, cin, st)
             else:
-              self._op('bneck01', 'uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
-                 1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+                self._op('bneck01', 'uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
+                   1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             if self.arch == AES:
                 pass
             elif self.arch in (AE, CAE):
@@ -441,12 +441,12 @@ class ConvAutoencoderEngine:
                     zsrc = br.mu      # ce branch decodes z_mu_ce without sampling (ceVAE model :37,43)
                 dd_name, dec_mask = 'Bottleneck/dense_2', m['dec']
             if self.arch != AES:
-              self._op('bneck06', 'uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
-                 keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, ws, wsb, st)
-              dbn = f'Decoder/{_bn(self.n)}'
-              self._op('bneck07', 'uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
-                 None, 1.0, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(br.zr) if training else None,
-                 ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, ws, wsb, st)
+                self._op('bneck06', 'uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
+                   keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+                dbn = f'Decoder/{_bn(self.n)}'
+                self._op('bneck07', 'uad_dense_fwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(fp.p('Bottleneck/conv2d_1/bias')),
+                   None, 1.0, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(br.zr) if training else None,
+                   ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, ws, wsb, st)
             h, s = br.ar, self.res
             for i, co in enumerate(self.dec_ch):
                 pre = f'Decoder/dec_Conv2DT_{i}'
@@ -530,8 +530,8 @@ class ConvAutoencoderEngine:
                 if m['sp'] is not None:
                     self._op('bneck10', 'uad_mask_scale', ptr(g), ptr(m['sp']), keep, ptr(g), B * r2 * ctop, st)
             else:
-              self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
-                 ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
+                self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
+                   ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
             if self.arch == AES:
                 pass
             elif self.arch == AE:
@@ -562,9 +562,9 @@ class ConvAutoencoderEngine:
                     self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
             # bottleneck 1x1 conv backward -> gradient w.r.t. the last encoder activation
             if self.arch != AES:
-              self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
-                 ptr(g), ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb,
-                 acc, ws, wsb, st)
+                self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
+                   ptr(g), ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb,
+                   acc, ws, wsb, st)
             s = self.res
             for i in reversed(range(self.n)):
                 co = self.enc_ch[i]
