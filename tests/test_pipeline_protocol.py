@@ -29,8 +29,11 @@ class MBar:
 
 
 class Sim:
-    def __init__(self, items, S, NS, n_iss, split_n, seed, instant_mma=False):
+    def __init__(self, items, S, NS, n_iss, split_n, seed, instant_mma=False, acc_bufs=1, ded_epi=False):
         self.items, self.S, self.NS, self.n_iss, self.split = items, S, NS, n_iss, split_n
+        # acc_bufs = 2 + ded_epi: the round-2 candidate `gather_gemm_tc3` (N = 32): a dedicated epilogue warpgroup drains
+        # accumulator set b while the issuers already work on the next item in set b ^ 1
+        self.acc_bufs, self.ded_epi = acc_bufs, ded_epi
         self.rng = random.Random(seed)
         self.instant = instant_mma
         n_rel = 2 if split_n else 1
@@ -38,11 +41,13 @@ class Sim:
         self.empty = [MBar(n_rel) for _ in range(S)]
         self.afull = [MBar(128) for _ in range(NS)]
         self.aempty = [MBar(n_rel) for _ in range(NS)]
-        self.accfull, self.accempty = MBar(n_iss), MBar(256)
+        self.accfull = [MBar(n_iss) for _ in range(2)]
+        self.accempty = [MBar(256) for _ in range(2)]
         self.stage = [None] * S            # k-block id whose operands are in the stage (None while a load is in flight)
         self.slot = [None] * NS            # k-block id converted into the TMEM slot
         self.acc = {}                      # item -> set of (k-block, half) accumulated
         self.acc_read = -1                 # last item whose accumulators the epilogue has read
+        self.buf_owner = [None, None]      # item currently accumulated in each accumulator set
         self.tma = []                      # in-flight loads: (stage, kc)
         self.mmaq = [[] for _ in range(2)]  # per issuer: issued, not yet executed ops ('mma', ...) / ('commit', bar)
         self.written = []
@@ -67,18 +72,19 @@ class Sim:
             for i in range(nkb):
                 mine = self.n_iss == 1 or self.split or (kc & 1) == me
                 if mine:
+                    buf, use = il % self.acc_bufs, il // self.acc_bufs
                     if not have_acc:
-                        yield ('wait', self.accempty, (il & 1) ^ 1)
+                        yield ('wait', self.accempty[buf], (use & 1) ^ 1)
                         have_acc = True
                     yield ('wait', self.full[s], ph)
                     yield ('wait', self.afull[t], pht)
                     last = (i == nkb - 1) if (self.n_iss == 1 or self.split) else (i >= nkb - 2)
                     q = self.mmaq[me]
-                    q.append(('mma', il, kc, s, t, me if self.split else 0))
+                    q.append(('mma', il, kc, s, t, me if self.split else 0, buf))
                     q.append(('commit', self.empty[s]))
                     q.append(('commit', self.aempty[t]))
                     if last:
-                        q.append(('commit', self.accfull))
+                        q.append(('commit', self.accfull[buf]))
                 kc += 1
                 s += 1
                 if s == self.S:
@@ -106,14 +112,26 @@ class Sim:
                 t += 1
                 if t == self.NS:
                     t, pht = 0, pht ^ 1
-            yield ('wait', self.accfull, il & 1)
-            halves = (0, 1) if self.split else (0,)
-            want = {(k, h) for k in range(first_kc, first_kc + nkb) for h in halves}
-            assert self.acc.get(il, set()) == want, ('epilogue read incomplete / foreign accumulators', il)
-            if grp == 0 and thread == 0:
-                self.acc_read = il
-                self.written.append(il)
-            self.accempty.arrive()
+            if not self.ded_epi:
+                yield from self.epilogue_item(il, first_kc, nkb, grp == 0 and thread == 0)
+
+    def epilogue_item(self, il, first_kc, nkb, leader):
+        buf, use = il % self.acc_bufs, il // self.acc_bufs
+        yield ('wait', self.accfull[buf], use & 1)
+        halves = (0, 1) if self.split else (0,)
+        want = {(k, h) for k in range(first_kc, first_kc + nkb) for h in halves}
+        assert self.acc.get(il, set()) == want, ('epilogue read incomplete / foreign accumulators', il)
+        assert self.buf_owner[buf] == il, ('epilogue read an accumulator set that holds another item', il, self.buf_owner)
+        if leader:
+            self.acc_read = il
+            self.written.append(il)
+        self.accempty[buf].arrive()
+
+    def epilogue_group(self, thread):
+        kc = 0
+        for il, nkb in enumerate(self.items):
+            yield from self.epilogue_item(il, kc, nkb, thread == 0)
+            kc += nkb
 
     # ---- asynchronous hardware
     def hw_steps(self):
@@ -135,10 +153,11 @@ class Sim:
         if op[0] == 'commit':
             op[1].arrive()
             return
-        _, il, kc, s, t, half = op
+        _, il, kc, s, t, half, buf = op
         assert self.stage[s] == kc, ('MMA executed on a refilled stage', self.stage[s], kc)
         assert self.slot[t] == kc, ('MMA executed on a refilled A slot', self.slot[t], kc)
-        assert self.acc_read >= il - 1, ('MMA overwrote accumulators the epilogue has not read', il, self.acc_read)
+        assert self.acc_read >= il - self.acc_bufs, ('MMA overwrote accumulators the epilogue has not read', il, self.acc_read)
+        self.buf_owner[buf] = il
         self.acc.setdefault(il, set()).add((kc, half))
 
     def run(self):
@@ -146,9 +165,12 @@ class Sim:
         # 128 threads per converter group arrive on afull / accempty: model 2 representative threads with weight 64 each
         conv = [(g, th) for g in range(2) for th in range(2)]
         actors += [self.converter(g, th) for g, th in conv]
+        if self.ded_epi:
+            actors += [self.epilogue_group(th) for th in range(2)]
         for b in self.afull:
             b.count = b.pending = 2
-        self.accempty.count = self.accempty.pending = 4
+        for b in self.accempty:
+            b.count = b.pending = 2 if self.ded_epi else 4
         blocked = [None] * len(actors)
         alive = [True] * len(actors)
 
@@ -211,6 +233,16 @@ def test_odd_stage_ring_aliases_parity_waits():
             except AssertionError:
                 hit += 1
         assert hit > 0, cfg
+
+
+@pytest.mark.parametrize('items', ITEMS)
+@pytest.mark.parametrize('S,NS', [(8, 4), (4, 4), (2, 2)])
+def test_v3_protocol_dedicated_epilogue_two_accumulator_sets(items, S, NS):
+    """Round-2 candidate for the N = 32 layers (`gather_gemm_tc3`, opt-in): as v2 plus a dedicated epilogue warpgroup and
+    two accumulator sets, so the epilogue of item k overlaps the MMAs of item k+1."""
+    for seed in range(10):
+        Sim(items, S, NS, 2, False, seed, acc_bufs=2, ded_epi=True).run()
+        Sim(items, S, NS, 2, False, seed, instant_mma=(seed % 2 == 0), acc_bufs=2, ded_epi=True).run()
 
 
 @pytest.mark.parametrize('S,NS,n_iss,split', [(4, 4, 2, False), (2, 2, 2, True)])

@@ -1017,6 +1017,307 @@ gather_gemm_tc2(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------ the kernel, v3 (CANDIDATE)
+// Round-2 candidate for the N = 32 layers (1.5 ms of the VAE-256 step), written at the end of round 1 AFTER the GPU budget
+// was spent: it compiles, its barrier protocol passes the random-schedule model (tests/test_pipeline_protocol.py), but it
+// has NOT run on hardware yet - opt-in only (UAD_TC_V3=1), never selected by default.
+// = gather_gemm_tc2 (two converter groups, two issuers on alternate k-blocks, even rings) plus what the N = 32 shapes need:
+// items there are short (4-9 k-blocks per output-parity class), so the serial epilogue of v2 would dominate; here a
+// DEDICATED epilogue warpgroup (warps 12-15) drains accumulator set b while the issuers already fill set b ^ 1
+// (two sets of 4 x 32 columns + four A slots = 512 TMEM columns).
+// 16 warps: 0 TMA producer | 1 issuer A | 2 TMEM alloc, issuer B | 3 constants | 4-7, 8-11 converter groups | 12-15 epilogue.
+__global__ void __launch_bounds__(512, 1)
+gather_gemm_tc3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int N = p.N;
+  const uint32_t b_bytes = 2u * N * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  const int S = p.stages;
+  const int NS = p.nslots;                              // even: slot parity == k-block parity == converter group
+  const uint32_t misc = smem_base + S * stage_bytes;
+  const uint32_t bar_full = misc;                       // S x 8   (S <= 8)
+  const uint32_t bar_empty = misc + 64;                 // S x 8
+  const uint32_t bar_afull = misc + 128;                // NS x 8  (NS <= 6)
+  const uint32_t bar_aempty = misc + 176;               // NS x 8
+  const uint32_t bar_accfull = misc + 224;              // 2 x 8 (one per accumulator set)
+  const uint32_t bar_accempty = misc + 240;             // 2 x 8
+  const uint32_t tmem_slot = misc + 256;
+  float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 320);               // bias[N], scale[N], shift[N]
+  float* stg_base = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 320 + 3 * N * 4);   // 4 warps x 32 x 36 staging
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t acc_cols = p.nacc * N;                 // columns of one accumulator set
+  const uint32_t aoff = 2 * acc_cols;                   // first A slot column (after the two accumulator sets)
+  const int nclasses = p.nclasses;
+  const int n_iss = p.n_issuers;
+
+  if (threadIdx.x == 0) {
+    const int n_rel = p.split_n ? 2 : 1;                // column-split mode: BOTH issuers consume every stage / slot
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, n_rel); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, n_rel); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, n_iss); mbar_init(bar_accempty + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {
+    for (int n = lane; n < N; n += 32) {
+      epi[n] = p.bias ? p.bias[n] : 0.f;
+      epi[N + n] = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
+      epi[2 * N + n] = p.beta ? p.beta[n] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (as gather_gemm_tc)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int cls = item % nclasses, tile = item / nclasses;
+        const TapSet& ts = p.taps[cls];
+        const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tbi = tile / (p.tiles_w * p.tiles_h);
+        const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+        const int nkb = ts.n * p.Cblks;
+        int tap = 0, cb = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, ((p.debug & 32) ? 0u : (uint32_t)kABytes) + ((p.debug & 64) ? 0u : b_bytes));
+          const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
+          const uint32_t a_dst = smem_base + s * stage_bytes;
+          if (p.debug & 32) {
+          } else if (p.stride2)
+            tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
+          else
+            tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
+          const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
+          if (!(p.debug & 64)) bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+          if (++cb == p.Cblks) { cb = 0; ++tap; }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 || warp == 2) {
+    // ===================================================================== MMA issuers (whole warp converged, one elected lane issues)
+    const int me = warp - 1;
+    if (me < n_iss) {
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
+      const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
+      const uint64_t bdesc0 = make_sw128_desc(smem_base + kABytes);
+      const uint32_t stage_units = stage_bytes >> 4, lo_units = (uint32_t)(N * 128) >> 4;
+      const bool paired = (N <= 64);
+      int s = 0, t = 0;
+      uint32_t ph = 0, pht = 0, kc = 0, il = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++il) {
+        const int nkb = p.taps[item % nclasses].n * p.Cblks;
+        bool have_acc = false;
+        int g = 0;                                               // single-issuer mode: round robin over the G main accumulators
+        for (int i = 0; i < nkb; ++i, ++kc) {
+          const bool mine = (n_iss == 1) || p.split_n || ((int)(kc & 1u) == me);
+          if (mine) {
+            const uint32_t buf = il & 1u, use = il >> 1;         // accumulator set and how often it has been used
+            if (!have_acc) {                                     // the epilogue group has drained this set's previous item
+              mbar_wait(bar_accempty + 8 * buf, (use & 1u) ^ 1u);
+              have_acc = true;
+            }
+            const uint32_t acc0 = tmem_base + buf * acc_cols;
+            mbar_wait(bar_full + 8 * s, ph);                     // weight image landed (async proxy -> visible to this thread's MMAs)
+            mbar_wait(bar_afull + 8 * t, pht);                   // converters filled TMEM A slot t
+            tc_fence_after();
+            const uint64_t dhi0 = bdesc0 + (uint64_t)(s * stage_units);
+            const uint32_t a_hi = tmem_base + aoff + t * 64;
+            const uint32_t a_lo = a_hi + 32;
+            const bool last_mine = (n_iss == 1 || p.split_n) ? (i == nkb - 1) : (i >= nkb - 2);
+            if (elect_one()) {
+              if (p.debug & 2) {
+              } else if (p.split_n) {
+                // N = 128, column-split dual issue: this warp owns output columns [64*me, 64*me + 64) of EVERY k-block:
+                // B rows 64*me.. of the hi / lo images, accumulators [main_0 | main_1 | corr] of 64 columns at 192*me
+                const uint32_t first = (i >= p.G) ? 1u : 0u;
+                const uint32_t accb = acc0 + me * 192;
+                const uint32_t d_main = accb + g * 64;
+                const uint32_t d_corr = accb + 128;
+                const uint64_t dh = dhi0 + (uint64_t)(me * ((64 * 128) >> 4));
+                const uint32_t idesc64 = idesc_base | ((uint32_t)(64 >> 3) << 17);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  mma_tf32_ts(d_corr, a_lo + j * 8, dh + 2 * j, idesc64, (i | j) != 0);
+                  mma_tf32_ts(d_corr, a_hi + j * 8, dh + lo_units + 2 * j, idesc64, 1u);
+                  mma_tf32_ts(d_main, a_hi + j * 8, dh + 2 * j, idesc64, first | (j != 0));
+                }
+              } else if (paired) {
+                const int gi = (n_iss == 2) ? (i & 1) : g;       // dual issue: the pair is owned by the k-block parity
+                const uint32_t first = (i >= p.G) ? 1u : 0u;
+                const uint32_t d_pair = acc0 + gi * 2 * N;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  mma_tf32_ts(d_pair, a_hi + j * 8, dhi0 + 2 * j, idesc2N, first | (j != 0));
+                  mma_tf32_ts(d_pair + N, a_lo + j * 8, dhi0 + 2 * j, idescN, 1u);
+                }
+              } else {
+                const uint32_t first = (i >= p.G) ? 1u : 0u;
+                const uint32_t d_main = acc0 + g * N;
+                const uint32_t d_corr = acc0 + p.G * N;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  mma_tf32_ts(d_corr, a_lo + j * 8, dhi0 + 2 * j, idescN, (i | j) != 0);
+                  mma_tf32_ts(d_corr, a_hi + j * 8, dhi0 + lo_units + 2 * j, idescN, 1u);
+                  mma_tf32_ts(d_main, a_hi + j * 8, dhi0 + 2 * j, idescN, first | (j != 0));
+                }
+              }
+              tc_commit(bar_empty + 8 * s);
+              tc_commit(bar_aempty + 8 * t);
+              if (last_mine) tc_commit(bar_accfull + 8 * buf);
+            }
+            __syncwarp();
+          }
+          if (++s == S) { s = 0; ph ^= 1; }
+          if (++t == NS) { t = 0; pht ^= 1; }
+          if (++g == p.G) g = 0;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================================== converter groups (conversion only)
+    const int grp = (warp - 4) >> 2;
+    const int row = (threadIdx.x - 128) & 127;                  // tile row == TMEM lane
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t swz = (uint32_t)(row & 7);
+    int s = 0, t = 0;
+    uint32_t ph = 0, pht = 0, kc = 0, il = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++il) {
+      const int nkb = p.taps[item % nclasses].n * p.Cblks;
+      for (int i = 0; i < nkb; ++i, ++kc) {
+        if ((int)(kc & 1u) == grp) {
+          mbar_wait(bar_full + 8 * s, ph);
+          if (p.debug & 1) {
+            mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+            mbar_arrive(bar_afull + 8 * t);
+          } else {
+            const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                       // 16-byte chunk j of this row sits at (j ^ (row & 7))
+              const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
+              const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t h = __float_as_uint(f[e]) & 0xffffe000u;
+                hi[4 * j + e] = h;
+                lo[4 * j + e] = __float_as_uint(f[e] - __uint_as_float(h));
+              }
+            }
+            mbar_wait(bar_aempty + 8 * t, pht ^ 1);
+            tc_fence_after();
+            const uint32_t a_slot = lane_base + aoff + t * 64;
+            tmem_st32(a_slot, hi);
+            tmem_st32(a_slot + 32, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_afull + 8 * t);
+          }
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++t == NS) { t = 0; pht ^= 1; }
+      }
+    }
+  } else if (warp >= 12) {
+    // ===================================================================== dedicated epilogue group
+    const int row = threadIdx.x - 384;                          // tile row == TMEM lane
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* stg = stg_base + (size_t)q * 32 * 36;                // this warp's 32 x (32+4) staging rows
+    const int nchunks = N >> 5;
+    uint32_t il = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++il) {
+      const int cls = item % nclasses, tile = item / nclasses;
+      const TapSet& ts = p.taps[cls];
+      const uint32_t buf = il & 1u, use = il >> 1;
+      const uint32_t acc_base = lane_base + buf * acc_cols;
+      const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tbi = tile / (p.tiles_w * p.tiles_h);
+      const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+      const int tw = row & (p.TW - 1);
+      const int th = (row >> p.lgTW) & (p.TH - 1);
+      const int tb = row >> (p.lgTW + p.lgTH);
+      const int b = b0 + tb;
+      const long long my_off = (b < p.B)
+          ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
+          : -1;
+      mbar_wait(bar_accfull + 8 * buf, use & 1u);
+      tc_fence_after();
+      long long offs[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + (lane >> 3));
+      const int cq = (lane & 7) * 4;
+      for (int c = 0; c < nchunks; ++c) {
+        const int c0 = c * 32;
+        uint32_t v[32], u[32];
+        // accumulator k of output columns c0..c0+31: k * N + c0, or (column-split) 192 * half + 64 * k + (c0 % 64)
+        const uint32_t acc_c0 = p.split_n ? (uint32_t)((c0 >> 6) * 192 + (c0 & 63)) : (uint32_t)c0;
+        const uint32_t acc_stride = p.split_n ? 64u : (uint32_t)N;
+        tmem_ld32(acc_base + acc_c0, v);
+        for (int k = 1; k < p.nacc; ++k) {
+          tmem_ld32(acc_base + k * acc_stride + acc_c0, u);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
+        tmem_wait_ld();
+        if (c + 1 == nchunks) {                                 // last TMEM read of this thread for the item: hand the set back
+          tc_fence_before();
+          mbar_arrive(bar_accempty + 8 * buf);
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {                  // z then a from the SAME registers
+          float* out = pass == 0 ? p.z_out : p.a_out;
+          if (!out) continue;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = c0 + j + e;
+              const float z = __uint_as_float(v[j + e]) + epi[n];
+              o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], p.act, p.alpha);
+            }
+            *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          __syncwarp();
+          float4 vals[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) vals[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * 36 + cq);
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (offs[it] >= 0) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = vals[it];
+          __syncwarp();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------ weight images
 // raw weights -> per (tap, 32-channel block): {hi, lo} images of [N rows][32 k] fp32 in the SWIZZLE_128B byte order the
 // UMMA descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n]; true: raw[t][n][c].
@@ -1447,6 +1748,34 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
     }
   }
   if (N == 32) {
+    {
+      // ---- UAD_TC_V3=1 (developer switch, default 0): the round-2 CANDIDATE kernel gather_gemm_tc3 - not yet run on hardware
+      static int use_v3 = -1;
+      if (use_v3 < 0) { const char* e = getenv("UAD_TC_V3"); use_v3 = e ? atoi(e) : 0; }
+      if (use_v3) {
+        p.split_n = 0;
+        p.n_issuers = 2;
+        p.G = 2;                                           // each issuer owns one accumulator pair
+        p.nacc = 4;
+        p.acc_bufs = 2;
+        p.nslots = ((512 - 2 * p.nacc * N) / 64) & ~1;     // 4
+        const size_t tail3 = 320 + 3 * N * sizeof(float) + 4 * 32 * 36 * sizeof(float) + 64;
+        p.stages = (int)((226 * 1024 - 1024 - tail3) / stage_bytes);
+        if (p.stages > 8) p.stages = 8;
+        p.stages &= ~1;                                    // even ring: static stage ownership (see gather_gemm_tc2)
+        UAD_REQUIRE(p.nslots >= 2 && p.stages >= 2, "gather_gemm_tc3: TMEM / shared-memory budget exceeded");
+        const size_t smem3 = 1024 + p.stages * stage_bytes + tail3;
+        static bool attr3 = false;
+        if (!attr3) {
+          UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc3, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          attr3 = true;
+        }
+        const int grid3 = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
+        gather_gemm_tc3<<<grid3, 512, smem3, st>>>(tmap, p);
+        UAD_LAUNCH_CHECK("gather_gemm_tc3");
+        return 0;
+      }
+    }
     // ---- N = 32 variant: one tile (all classes) per CTA, TMEM / smem sized for 2 CTAs per SM where possible
     p.acc_bufs = 1;
     const int acc_cols = p.nacc * N;
