@@ -402,3 +402,36 @@ def test_minc1_values_outside_valid_range_are_clamped(tmp_path):
     data, _, _ = read_minc1(p)
     expect = (np.clip(raw.astype(np.float64), 5, 200) - 5) / 195.0 * 2.0 + 1.0
     np.testing.assert_allclose(data, expect.transpose(2, 1, 0), atol=1e-12)
+
+
+def test_get_datasets_routes_brainweb_directories_to_the_loader(tmp_path):
+    """default_config_setup.get_datasets: a BrainWeb tree on disk -> (healthy T2 NORMAL 0.7/0.3/0, SEVEREMS test set), configured
+    as the reference does (default_config_setup.py:200-242); no data on disk -> the synthetic generator."""
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import default_config_setup as cfg
+    root, labels, ms, _ = _dataset_dir(tmp_path, n_normal=4, n_ms=0)
+    rng = np.random.default_rng(11)
+    write_minc1(os.path.join(root, 'groundtruth', 'severe_lesions.mnc.gz'), ms, 0.0, 10.0, (0, 10), 'unsigned')
+    for i in range(2):
+        v = ((ms.astype(np.float64) * 20 + rng.integers(0, 20, ms.shape)) * (ms > 0)).astype(np.uint8)
+        write_minc1(os.path.join(root, 'lesions', 'severe', f't2_s{i}.mnc.gz'), v, np.zeros(Z), np.full(Z, 255.0), (0, 255), 'unsigned')
+    options = cfg.get_options(batchsize=4, learningrate=1e-4, numEpochs=1, zDim=16, outputWidth=32, outputHeight=32,
+                              slices_start=1, slices_end=10, config={'CHECKPOINTDIR': str(tmp_path / 'c'), 'SAMPLEDIR': str(tmp_path / 's'),
+                                                                     'BRAINWEBDIR': root})
+    options['data']['dir'] = options['globals'][cfg.Dataset.BRAINWEB.value]
+    np.random.seed(5)
+    hc, pc = cfg.get_datasets(options, cfg.Dataset.BRAINWEB)
+    assert isinstance(hc, BRAINWEB) and isinstance(pc, BRAINWEB)
+    assert [p['type'] for p in hc.patients] == ['NORMAL'] * 4 and [p['type'] for p in pc.patients] == ['SEVEREMS'] * 2
+    assert [len(hc.patients_split[s]) for s in BRAINWEB.SET_TYPES] == [2, 1, 0]         # floor(.7*4), floor(.3*4), 0
+    assert [len(pc.patients_split[s]) for s in BRAINWEB.SET_TYPES] == [0, 0, 2]
+    assert hc.images.shape == (3 * 9, 32, 32, 1) and pc.images.shape == (2 * 9, 32, 32, 1)
+    assert not hc.labels.any() and pc.labels.any()
+    assert hc.options.skullRemoval and hc.options.backgroundRemoval and hc.options.cache and os.path.isfile(hc.tfrecord_name())
+    assert float(hc.images.min()) == 0.0 and float(hc.images.max()) <= 1.0 + 1e-6
+    assert len(pc.get_patient_idx('TEST')) == 2
+    vol, seg, skull = pc.load_volume_and_groundtruth(pc.patients[0]['filtered_files'], pc.patients[0])
+    assert vol.num_slices_along_axis(pc.options.axis) == Z and seg.data.any()
+    options['data']['dir'] = str(tmp_path / 'nothing-here')
+    hs, ps = cfg.get_datasets(options, cfg.Dataset.BRAINWEB)
+    assert isinstance(hs, SYNTHETIC) and isinstance(ps, SYNTHETIC)

@@ -3,6 +3,7 @@ import json
 import os
 from enum import Enum
 
+from ..dataloaders.BRAINWEB import BRAINWEB
 from ..dataloaders.SYNTHETIC import SYNTHETIC
 
 base_path = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -73,14 +74,65 @@ def get_synthetic_dataset_options(options, lesions, num_patients=None):
 
 
 def get_datasets(options, dataset: Dataset = Dataset.BRAINWEB):
-    """(healthy train/val set, lesion test set).  The real MINC / NIfTI loaders are out of scope: every Dataset member maps
-    to the synthetic BrainWeb-shaped generator (healthy slices for training, slices with lesions + labels for testing)."""
+    """(healthy train/val set, lesion test set) - reference default_config_setup.py:60-72.
+    BRAINWEB with a real data directory (``<dir>/normal/*.mnc.gz`` present) goes through the BrainWeb loader exactly as the
+    reference configures it (:200-242).  Everything else - no data on disk, or the MSSEG2008 / MSISBI2015 / MSLUB members whose
+    loaders are not carried over - maps to the synthetic BrainWeb-shaped generator (healthy slices for training, slices with
+    lesions + labels for testing), which is also what the metric is defined on."""
+    if dataset in (Dataset.BRAINWEB, Dataset.Brainweb) and has_brainweb_data(options.get('data', {}).get('dir')):
+        return get_Brainweb_healthy_dataset(options), get_Brainweb_lesion_dataset(options)
     hc = get_synthetic_dataset_options(options, lesions=False)
     hc.partition = {'TRAIN': 0.7, 'VAL': 0.3, 'TEST': 0.0}
     pc = get_synthetic_dataset_options(options, lesions=True, num_patients=options.get('data', {}).get('numTestPatients', 2))
     pc.partition = {'TRAIN': 0.0, 'VAL': 0.0, 'TEST': 1.0}
     pc.seed = 4321
     return SYNTHETIC(hc), SYNTHETIC(pc)
+
+
+def has_brainweb_data(directory):
+    import glob
+    return bool(directory) and bool(glob.glob(os.path.join(directory, BRAINWEB.Options().folderNormal, '*.mnc.gz')))
+
+
+def get_Brainweb_healthy_dataset(options):
+    return BRAINWEB(get_Brainweb_dataset_options(options))
+
+
+def get_Brainweb_lesion_dataset(options):
+    dataset_options = get_Brainweb_dataset_options(options)
+    dataset_options.partition = {'TRAIN': 0.0, 'VAL': 0.0, 'TEST': 1.0}      # patients with lesions: only for testing
+    dataset_options.filterType = 'SEVEREMS'
+    dataset_options.rotations = [0]
+    return BRAINWEB(dataset_options)
+
+
+def get_Brainweb_dataset_options(options):
+    """reference default_config_setup.py:217-242, field for field."""
+    o = BRAINWEB.Options()
+    o.description = ""
+    o.debug = options['debug']
+    o.dir = options['data']['dir']
+    o.useCrops = False
+    o.cropType = 'center'
+    o.cropWidth = options['train']['outputWidth']
+    o.cropHeight = options['train']['outputHeight']
+    o.numRandomCropsPerSlice = 5
+    o.rotations = [0]
+    o.partition = {'TRAIN': 0.7, 'VAL': 0.3, 'TEST': 0.0}
+    o.sliceResolution = [options['train']['outputHeight'], options['train']['outputWidth']]
+    o.cache = True
+    o.numSamples = -1
+    o.addInstanceNoise = False
+    o.axis = 'axial'
+    o.filterType = 'NORMAL'
+    o.filterProtocol = 'T2'
+    o.normalizationMethod = 'scaling'
+    o.skullRemoval = True
+    o.sliceStart = options['sliceStart']
+    o.sliceEnd = options['sliceEnd']
+    o.backgroundRemoval = True
+    o.registerTo = None
+    return o
 
 
 def get_config(trainer, options, optimizer, intermediateResolutions, dropout_rate, dataset):
