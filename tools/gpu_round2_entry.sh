@@ -1,0 +1,23 @@
+#!/bin/bash
+# FIRST GPU call of round 2 (cheap, ~3 GPU-minutes): answers the open hardware questions left at the end of round 1, which
+# had no GPU minutes left when the candidates were written.  usage: gpurun --timeout 900 -- 'bash tools/gpu_round2_entry.sh'
+#   1. the shipped defaults (even stage ring at N = 64, N = 128 on the first-generation kernel) were derived on CPU from the
+#      barrier-protocol model - confirm the GPU suite and re-measure the headline;
+#   2. tools/ubench/operand_probe.cu: tf32 operand forms the Form-W redesign needs (MN-major SWIZZLE_128B_BASE32B operands,
+#      row-shifted descriptors, truncation of raw fp32 words);
+#   3. the N = 32 candidate kernel gather_gemm_tc3 (UAD_TC_V3=1): correctness, then time against the shipped kernel.
+TAG=${1:-r2a}
+mkdir -p gpurun_out build
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/operand_probe tools/ubench/operand_probe.cu \
+  && timeout 120 build/operand_probe > gpurun_out/${TAG}_operand_probe.txt 2>&1
+cat gpurun_out/${TAG}_operand_probe.txt
+( time timeout 900 python -m pytest tests -m gpu -q --maxfail=15 -p no:cacheprovider ) > gpurun_out/${TAG}_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_pytest.log
+timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers.json > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+cat gpurun_out/${TAG}_bench.json
+UAD_TC_V3=1 timeout 300 python -m pytest tests/test_gpu_v3_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_v3_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_v3_pytest.log
+timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_shipped.txt 2>&1
+UAD_TC_V3=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v3.txt 2>&1
+tail -12 gpurun_out/${TAG}_time_tc_shipped.txt gpurun_out/${TAG}_time_tc_v3.txt
