@@ -1,0 +1,407 @@
+"""CPU emulation of the C ABI (include/uad_b200.h) for HOST-SIDE COMPOSITION tests - test infrastructure only.
+
+What it is for: the engines (fanogan_engine, anovaegan_engine, ...) are sequences of ABI calls on caller-owned buffers.  Each
+kernel is parity-tested on the GPU on its own (tests/test_gpu_ops.py, test_gpu_fanogan.py); whether a NEW sequence of calls
+computes the right gradients is a property of the host code and can be checked without a GPU if every entry point is replaced
+by a float64 torch-CPU function with the semantics the header documents.  `install(monkeypatch, module, ...)` swaps the
+module-level `call` / `ptr` of an engine module for the emulated ones (``ptr`` then hands the tensor itself through) and
+makes the engine allocate on the CPU.  The emulator is validated the other way round: the f-AnoGAN engine, whose real-kernel
+runs match the oracle on the B200, must also match the oracle through the emulator (tests/test_engine_emulated.py).
+
+The product never imports this file; nothing here is a fallback path."""
+import math
+
+import numpy as np
+import torch
+
+from oracle.tf_graph_cpu import conv2d_same_s2, conv2dT_same_s2
+
+ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+D = torch.float64
+
+_registry = []          # tensors whose raw data_ptr() the engines pass (scalars, counters)
+
+
+def register(*tensors):
+    _registry.extend(tensors)
+
+
+def _resolve(p):
+    """raw int pointer -> flat view starting there (only for registered tensors)."""
+    if p is None or isinstance(p, torch.Tensor):
+        return None if p is None else p.reshape(-1)
+    for t in _registry:
+        base, size = t.data_ptr(), t.numel() * t.element_size()
+        if base <= p < base + size:
+            return t.reshape(-1)[(p - base) // t.element_size():]
+    raise KeyError(f'pointer {p:#x} is not inside a registered tensor')
+
+
+def _v(t, *shape):
+    """float64 copy of the first prod(shape) elements behind a pointer, shaped."""
+    n = int(np.prod(shape))
+    return _resolve(t)[:n].to(D).reshape(*shape)
+
+
+def _w(t, value):
+    """write value (any shape) to the first numel elements behind a pointer."""
+    if t is None:
+        return
+    flat = _resolve(t)
+    flat[:value.numel()].copy_(value.reshape(-1).to(flat.dtype))
+
+
+def _acc(t, value, accumulate):
+    if t is None:
+        return
+    if accumulate:
+        value = value + _v(t, *value.shape)
+    _w(t, value)
+
+
+def _act(n, act, alpha):
+    act &= 0xff
+    if act == ACT_NONE:
+        return n
+    if act == ACT_LEAKY:
+        return torch.where(n > 0, n, alpha * n)
+    if act == ACT_RELU:
+        return torch.where(n > 0, n, torch.zeros_like(n))
+    if act == ACT_SIGMOID:
+        return torch.sigmoid(n)
+    if act == ACT_TANH:
+        return torch.tanh(n)
+    raise ValueError(act)
+
+
+def _dact(n, act, alpha):
+    act &= 0xff
+    if act == ACT_NONE:
+        return torch.ones_like(n)
+    if act == ACT_LEAKY:
+        return torch.where(n > 0, torch.ones_like(n), torch.full_like(n, alpha))
+    if act == ACT_RELU:
+        return (n > 0).to(n.dtype)
+    if act == ACT_SIGMOID:
+        s = torch.sigmoid(n)
+        return s * (1 - s)
+    if act == ACT_TANH:
+        return 1 - torch.tanh(n) ** 2
+    raise ValueError(act)
+
+
+def _nchw(t, B, H, W, C):
+    return _v(t, B, H, W, C).permute(0, 3, 1, 2)
+
+
+def _affine(z_nhwc, gamma, beta, C, bn_c):
+    if gamma is None:
+        return z_nhwc
+    return z_nhwc * (_v(gamma, C) * bn_c) + _v(beta, C)
+
+
+# ------------------------------------------------------------------------------------------------ conv family
+def uad_conv2d_fwd(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cin, Cout, k, act, alpha, bn_c, mm, ws, wsb, st):
+    b = _v(bias, Cout) if bias is not None else torch.zeros(Cout, dtype=D)
+    z = conv2d_same_s2(_nchw(x, B, H, W, Cin), _v(w, k, k, Cin, Cout), b).permute(0, 2, 3, 1)
+    _w(z_out, z)
+    _w(a_out, _act(_affine(z, gamma, beta, Cout, bn_c), act, alpha))
+
+
+def uad_conv2d_dgrad(dz, w, dx, B, H, W, Cin, Cout, k, mm, ws, wsb, st):
+    x = torch.zeros(B, Cin, H, W, dtype=D, requires_grad=True)
+    y = conv2d_same_s2(x, _v(w, k, k, Cin, Cout), torch.zeros(Cout, dtype=D))
+    g, = torch.autograd.grad(y, x, _nchw(dz, B, H // 2, W // 2, Cout))
+    _w(dx, g.permute(0, 2, 3, 1))
+
+
+def uad_conv2d_wgrad(x, dz, dw, B, H, W, Cin, Cout, k, accumulate, mm, ws, wsb, st):
+    wt = torch.zeros(k, k, Cin, Cout, dtype=D, requires_grad=True)
+    y = conv2d_same_s2(_nchw(x, B, H, W, Cin), wt, torch.zeros(Cout, dtype=D))
+    g, = torch.autograd.grad(y, wt, _nchw(dz, B, H // 2, W // 2, Cout))
+    _acc(dw, g, accumulate)
+
+
+def uad_convT2d_fwd(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cin, Cout, k, act, alpha, bn_c, mm, ws, wsb, st):
+    b = _v(bias, Cout) if bias is not None else torch.zeros(Cout, dtype=D)
+    z = conv2dT_same_s2(_nchw(x, B, H, W, Cin), _v(w, k, k, Cout, Cin), b).permute(0, 2, 3, 1)
+    _w(z_out, z)
+    _w(a_out, _act(_affine(z, gamma, beta, Cout, bn_c), act, alpha))
+
+
+def uad_convT2d_dgrad(dz, w, dx, B, H, W, Cin, Cout, k, mm, ws, wsb, st):
+    x = torch.zeros(B, Cin, H, W, dtype=D, requires_grad=True)
+    y = conv2dT_same_s2(x, _v(w, k, k, Cout, Cin), torch.zeros(Cout, dtype=D))
+    g, = torch.autograd.grad(y, x, _nchw(dz, B, 2 * H, 2 * W, Cout))
+    _w(dx, g.permute(0, 2, 3, 1))
+
+
+def uad_convT2d_wgrad(x, dz, dw, B, H, W, Cin, Cout, k, accumulate, mm, ws, wsb, st):
+    wt = torch.zeros(k, k, Cout, Cin, dtype=D, requires_grad=True)
+    y = conv2dT_same_s2(_nchw(x, B, H, W, Cin), wt, torch.zeros(Cout, dtype=D))
+    g, = torch.autograd.grad(y, wt, _nchw(dz, B, 2 * H, 2 * W, Cout))
+    _acc(dw, g, accumulate)
+
+
+def uad_act_bn_bwd(da, z, gamma, beta, dz, dgamma, dbeta, dbias, rows, C, act, alpha, bn_c, accumulate, ws, wsb, st):
+    assert not (act & 0x100), 'emulator: UAD_ACT_FROM_OUTPUT is not modelled'
+    zt, dat = _v(z, rows, C), _v(da, rows, C)
+    if gamma is None:
+        du = dat * _dact(zt, act, alpha)
+        dzt = du
+    else:
+        g, b = _v(gamma, C), _v(beta, C)
+        du = dat * _dact(g * bn_c * zt + b, act, alpha)
+        dzt = g * bn_c * du
+        _acc(dgamma, bn_c * (du * zt).sum(0), accumulate)
+        _acc(dbeta, du.sum(0), accumulate)
+    _acc(dbias, dzt.sum(0), accumulate)
+    _w(dz, dzt)
+
+
+# ------------------------------------------------------------------------------------------------ dense / bottleneck
+def uad_dense_fwd(x, w, bias, mask, mask_scale, gamma, beta, z_out, a_out, M, K, N, act, alpha, bn_c, ws, wsb, st):
+    z = _v(x, M, K) @ _v(w, K, N)
+    if bias is not None:
+        z = z + _v(bias, N)
+    if mask is not None:
+        z = z * _v(mask, M, N) * mask_scale
+    _w(z_out, z)
+    _w(a_out, _act(_affine(z, gamma, beta, N, bn_c), act, alpha))
+
+
+def uad_dense_bwd(x, w, dz, mask, mask_scale, dx, dw, dbias, M, K, N, accumulate, ws, wsb, st):
+    d = _v(dz, M, N)
+    if mask is not None:
+        d = d * _v(mask, M, N) * mask_scale
+    if dx is not None:
+        _w(dx, d @ _v(w, K, N).t())
+    _acc(dw, _v(x, M, K).t() @ d, accumulate)
+    _acc(dbias, d.sum(0), accumulate)
+
+
+def uad_reparam_kl_fwd(mu, ls, eps, sigma, z, kl, B, Z, st):
+    m, l = _v(mu, B, Z), _v(ls, B, Z)
+    s = torch.exp(l)
+    _w(sigma, s)
+    _w(z, m if eps is None else m + _v(eps, B, Z) * s)
+    _w(kl, 0.5 * (m * m + s * s - torch.log(s * s) - 1).sum(1))
+
+
+def uad_reparam_kl_bwd(mu, ls, eps, dz, kl_scale, dmu, dls, B, Z, st):
+    m, l, d = _v(mu, B, Z), _v(ls, B, Z), _v(dz, B, Z)
+    s = torch.exp(l)
+    _w(dmu, d + kl_scale * m)
+    _w(dls, d * _v(eps, B, Z) * s + kl_scale * (s * s - 1))
+
+
+def uad_final1x1_l1_fwd(a, w, bias, x, xhat, l1, rec, B, HW, Cin, ws, wsb, st):
+    y = _v(a, B * HW, Cin) @ _v(w, Cin) + _v(bias, 1)
+    _w(xhat, y)
+    if l1 is not None or rec is not None:
+        r = (y - _v(x, B * HW)).abs()
+        _w(l1, r)
+        _w(rec, r.reshape(B, HW).sum(1))
+
+
+def _final_bwd(a, w, dxh, da, dw, dbias, B, HW, Cin, accumulate):
+    _w(da, dxh[:, None] * _v(w, Cin)[None, :])
+    _acc(dw, _v(a, B * HW, Cin).t() @ dxh, accumulate)
+    _acc(dbias, dxh.sum().reshape(1), accumulate)
+
+
+def uad_final1x1_l1_bwd(a, w, x, xhat, scale, da, dw, dbias, B, HW, Cin, accumulate, ws, wsb, st):
+    _final_bwd(a, w, torch.sign(_v(xhat, B * HW) - _v(x, B * HW)) * scale, da, dw, dbias, B, HW, Cin, accumulate)
+
+
+def uad_final1x1_bwd(a, w, dxhat, da, dw, dbias, B, HW, Cin, accumulate, ws, wsb, st):
+    _final_bwd(a, w, _v(dxhat, B * HW), da, dw, dbias, B, HW, Cin, accumulate)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNormalization([1,2])
+def _ln_parts(x, stats, gamma, beta, B, HW, C):
+    xt = _v(x, B, HW, C)
+    st_ = _v(stats, 2, B, C)
+    xh = (xt - st_[0][:, None, :]) * st_[1][:, None, :]
+    g, b = _v(gamma, HW)[None, :, None], _v(beta, HW)[None, :, None]
+    return xt, xh, st_[1][:, None, :], g, b
+
+
+def uad_layernorm_hw_fwd_train(x, gamma, beta, y, stats, B, HW, C, eps, act, alpha, ws, wsb, st):
+    xt = _v(x, B, HW, C)
+    mean = xt.mean(1)
+    rstd = 1.0 / torch.sqrt(xt.var(1, unbiased=False) + eps)
+    _w(stats, torch.stack([mean, rstd]))
+    n = (xt - mean[:, None, :]) * rstd[:, None, :] * _v(gamma, HW)[None, :, None] + _v(beta, HW)[None, :, None]
+    _w(y, _act(n, act, alpha))
+
+
+def uad_layernorm_hw_fwd(x, gamma, beta, y, B, HW, C, eps, act, alpha, ws, wsb, st):
+    uad_layernorm_hw_fwd_train(x, gamma, beta, y, None, B, HW, C, eps, act, alpha, ws, wsb, st)
+
+
+def _ln_reverse(dn, xh, r, g):
+    """adjoint of x through xhat = (x - mean) * rstd given dn = adjoint of gamma*xhat+beta."""
+    dxh = dn * g
+    return r * (dxh - dxh.mean(1, keepdim=True) - xh * (dxh * xh).mean(1, keepdim=True))
+
+
+def uad_layernorm_hw_bwd(dy, x, stats, gamma, beta, dx, dgamma, dbeta, B, HW, C, act, alpha, accumulate, ws, wsb, st):
+    xt, xh, r, g, b = _ln_parts(x, stats, gamma, beta, B, HW, C)
+    dn = _v(dy, B, HW, C) * _dact(g * xh + b, act, alpha)
+    _acc(dgamma, (dn * xh).sum((0, 2)), accumulate)
+    _acc(dbeta, dn.sum((0, 2)), accumulate)
+    _w(dx, _ln_reverse(dn, xh, r, g))
+
+
+def _ln_tangent(xd, xh, r):
+    return r * (xd - xd.mean(1, keepdim=True) - xh * (xd * xh).mean(1, keepdim=True))
+
+
+def uad_layernorm_hw_jvp(xdot, x, stats, gamma, beta, ydot, jstats, B, HW, C, act, alpha, ws, wsb, st):
+    xt, xh, r, g, b = _ln_parts(x, stats, gamma, beta, B, HW, C)
+    xd = _v(xdot, B, HW, C)
+    _w(jstats, torch.stack([xd.mean(1), (xd * xh).mean(1)]))
+    _w(ydot, _dact(g * xh + b, act, alpha) * g * _ln_tangent(xd, xh, r))
+
+
+def uad_layernorm_hw_bwd2(dydot, dy, x, xdot, stats, jstats, gamma, beta, dxdot, dx, dgamma, dbeta, B, HW, C, act, alpha,
+                          accumulate, ws, wsb, st):
+    """Reverse of (y, ydot) = (act(LN(x)), d/de act(LN(x + e xdot))) by autograd on the closed forms (the activation's
+    derivative is piecewise constant, so its own derivative contributes nothing - exactly what the kernel assumes)."""
+    xt = _v(x, B, HW, C).clone().requires_grad_(True)
+    xd = _v(xdot, B, HW, C).clone().requires_grad_(True)
+    g0 = _v(gamma, HW).clone().requires_grad_(True)
+    b0 = _v(beta, HW).clone().requires_grad_(True)
+    # the forward's epsilon is not an argument: recover var + eps from the saved rstd so autograd sees rstd as a function of x
+    rs = _v(stats, 2, B, C)[1][:, None, :]
+    eps_t = (1.0 / (rs * rs) - _v(x, B, HW, C).var(1, unbiased=False, keepdim=True)).detach()
+    mean = xt.mean(1, keepdim=True)
+    r = 1.0 / torch.sqrt(xt.var(1, unbiased=False, keepdim=True) + eps_t)
+    xh = (xt - mean) * r
+    g, b = g0[None, :, None], b0[None, :, None]
+    n = g * xh + b
+    da = _dact(n.detach(), act, alpha)
+    y = torch.where(n > 0, n, alpha * n) if (act & 0xff) == ACT_LEAKY else (torch.relu(n) if (act & 0xff) == ACT_RELU else n)
+    ydot = da * g * _ln_tangent(xd, xh, r)
+    total = (ydot * _v(dydot, B, HW, C)).sum()
+    if dy is not None:
+        total = total + (y * _v(dy, B, HW, C)).sum()
+    gx, gxd, gg, gb = torch.autograd.grad(total, (xt, xd, g0, b0), allow_unused=True)
+    _w(dxdot, gxd)
+    _w(dx, gx)
+    _acc(dgamma, gg, accumulate)
+    _acc(dbeta, torch.zeros(HW, dtype=D) if gb is None else gb, accumulate)
+
+
+# ------------------------------------------------------------------------------------------------ element-wise / reductions
+def uad_activation(x, y, n, act, alpha, st):
+    _w(y, _act(_v(x, n), act, alpha))
+
+
+def uad_activation_bwd(dy, u, dx, n, act, alpha, st):
+    _w(dx, _v(dy, n) * _dact(_v(u, n), act, alpha))
+
+
+def uad_fill(y, v, n, st):
+    _w(y, torch.full((n,), float(v), dtype=D))
+
+
+def uad_axpby(a, x, b, y, n, st):
+    _w(y, a * _v(x, n) + b * _v(y, n))
+
+
+def uad_sum_scaled(x, n, scale, out, ws, wsb, st):
+    _w(out, (_v(x, n).sum() * scale).reshape(1))
+
+
+def uad_mse(a, b, n, grad_scale, grad_a, loss_scale, loss_out, ws, wsb, st):
+    d = _v(a, n) - _v(b, n)
+    _w(grad_a, grad_scale * d)
+    _w(loss_out, (loss_scale * (d * d).sum()).reshape(1))
+
+
+def uad_gradient_penalty(ddx, B, H, WC, scale, u_out, gp_out, ws, wsb, st):
+    t = _v(ddx, B, H, WC).clone().requires_grad_(True)
+    gp = ((torch.sqrt((t * t).sum(1)) - 1.0) ** 2).mean() * scale
+    u, = torch.autograd.grad(gp, t)
+    _w(u_out, u)
+    _w(gp_out, gp.detach().reshape(1))
+
+
+def uad_interpolate(x, x_gen, alpha, out, B, per_sample, st):
+    xt, xg = _v(x, B, per_sample), _v(x_gen, B, per_sample)
+    _w(out, xt + _v(alpha, B)[:, None] * (xg - xt))
+
+
+def uad_l1_map(x, xhat, l1, rec, B, HW, st):
+    r = (_v(xhat, B, HW) - _v(x, B, HW)).abs()
+    _w(l1, r)
+    _w(rec, r.sum(1))
+
+
+def uad_counter_add(counter, inc, st):
+    c = _resolve(counter)
+    c[0] += int(inc)
+
+
+def uad_adam_tf_step(params, grads, m, v, n, lr, b1, b2, eps, grad_scale, step_dev, st):
+    lr_t = lr
+    if step_dev is not None:
+        t = int(_resolve(step_dev)[0])
+        lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+    g = _v(grads, n) * grad_scale
+    mn = b1 * _v(m, n) + (1 - b1) * g
+    vn = b2 * _v(v, n) + (1 - b2) * g * g
+    _w(m, mn)
+    _w(v, vn)
+    _w(params, _v(params, n) - lr_t * mn / (vn.sqrt() + eps))
+
+
+_rng = np.random.default_rng(1234)
+
+
+def uad_randn(out, n, seed, offset, offset_dev, st):
+    _w(out, torch.from_numpy(_rng.standard_normal(n)))
+
+
+def uad_uniform(out, n, seed, offset, offset_dev, st):
+    _w(out, torch.from_numpy(_rng.random(n)))
+
+
+def uad_dropout_mask(mask, n, rate, seed, offset, offset_dev, st):
+    _w(mask, torch.from_numpy((_rng.random(n) >= rate).astype(np.float64)))
+
+
+calls = []
+
+
+def call(name, *args):
+    fn = globals().get(name)
+    if fn is None:
+        raise NotImplementedError(f'abi_emulator: {name} is not modelled')
+    calls.append(name)
+    with torch.enable_grad():
+        fn(*args)
+    return 0
+
+
+def ptr(t):
+    return t
+
+
+def install(monkeypatch, *modules):
+    """Route the given engine modules' ABI calls through the emulator and make their engines live on the CPU."""
+    from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
+    for mod in modules:
+        monkeypatch.setattr(mod, 'call', call)
+        monkeypatch.setattr(mod, 'ptr', ptr)
+    monkeypatch.setattr(FanoganEngine, '_st', lambda self: 0)
+    del _registry[:]
+    del calls[:]
+
+
+def adopt(engine):
+    """Register the buffers an engine passes as raw pointers (loss scalars, step counters, the Philox counter)."""
+    register(engine.sc, engine.rng_ctr, *engine.steps.values())
+    return engine

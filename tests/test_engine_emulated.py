@@ -1,0 +1,275 @@
+"""Host-side composition checks WITHOUT a GPU (tests/abi_emulator.py replaces every ABI entry point by a float64 torch-CPU
+function with the header's semantics).
+
+1. Calibration: the f-AnoGAN engine's three train ops, whose real-kernel runs match the oracle on the B200
+   (tests/test_gpu_fanogan.py), must match the same oracle through the emulator - this pins the emulator's reading of the ABI.
+2. New compositions that have not run on hardware yet (AnoVAEGAN) are then checked the same way against their own oracle:
+   every gradient, every loss scalar, the Adam slot ownership of the three optimisers.
+What this does NOT cover: the kernels themselves (GPU parity tests), CUDA-graph capture, device RNG streams."""
+import numpy as np
+import pytest
+import torch
+
+import abi_emulator as E
+from oracle import anovaegan_cpu as AO
+from oracle import fanogan_cpu as FO
+from oracle import tf_graph_cpu as O
+from unsupervised_anomaly_detection_brain_mri_b200 import anovaegan_engine, fanogan_engine
+
+TOL = 1e-5
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+def _pat(ts):
+    return [(t > 0).numpy() for t in ts]
+
+
+def _compare_grads(eng, G, tol=TOL):
+    got = eng.fp.to_numpy(eng.fp.grads)
+    gmax = max(float(v.abs().max()) for v in G.values())
+    for k, v in G.items():
+        ref = v.numpy()
+        if k.endswith('/bias') and float(np.abs(ref).max()) < 1e-9 * gmax:
+            assert float(np.abs(got[k]).max()) <= 1e-9 * gmax, k       # bias feeding a LayerNorm over (H,W): exactly 0
+            continue
+        assert _rel(got[k], ref) < tol, (k, _rel(got[k], ref))
+
+
+def _check_update(after, before, ref_P, G, scopes, lr):
+    """The Adam update touched exactly the op's variables and equals tf.train.AdamOptimizer's.  The first step is ~lr*sign(g), so
+    it is compared where the sign is determined (the engine's gradient buffer is float32, the oracle's float64)."""
+    gmax = max(float(v.abs().max()) for v in G.values())
+    tot = bad = 0
+    for k in after:
+        if k.split('/')[0] not in scopes:
+            assert np.array_equal(after[k], before[k]), k
+            continue
+        ref, g = ref_P[k].numpy(), G[k].numpy()
+        sel = np.abs(g) > 1e-3 * gmax
+        tot += int(sel.sum())
+        bad += int((np.abs(after[k].reshape(ref.shape) - ref)[sel] > 0.02 * lr).sum())
+    assert tot > 0 and bad == 0, (bad, tot)
+
+
+def _feed(S, B, rate, flat, zDim=128, seed=21):
+    rng = np.random.default_rng(seed)
+    x = O.synthetic_slices(B, S, seed=seed)
+    z = rng.standard_normal((B, zDim)).astype(np.float32)
+    alpha = rng.random((B, 1), dtype=np.float32)
+    m_z = [(rng.uniform(size=(B, zDim)) >= rate).astype(np.float32) for _ in range(2)]
+    m_gen = (rng.uniform(size=(B, flat)) >= rate).astype(np.float32)
+    return x, z, alpha, m_z, m_gen
+
+
+# ------------------------------------------------------------------------------------------------ 1. calibration on f-AnoGAN
+def _fanogan_signs(eng, which, keep):
+    def critic(x_dev):
+        eng._critic_forward(eng.pass1, x_dev, critic=False)
+        return _pat(eng.pass1.a)
+    sg = {}
+    if which in ('gen', 'disc'):
+        eng.generate(eng.z_in, eng.mask_gen, keep, out=eng.x_gen)
+        sg['gen_z'] = _pat([eng.ar] + eng.gen_a)
+        sg['d_fake'] = critic(eng.x_gen)
+    if which == 'disc':
+        sg['d_real'] = critic(eng.x)
+        E.call('uad_interpolate', eng.x, eng.x_gen, eng.alpha, eng.x_hat, eng.B, eng.S * eng.S, 0)
+        sg['d_hat'] = critic(eng.x_hat)
+    if which == 'enc':
+        z_enc = eng.encode(eng.mask_enc, keep)
+        sg['enc'] = _pat(eng.enc_a)
+        x_enc = eng.generate(z_enc, eng.mask_gen, keep, out=eng.x_enc)
+        sg['gen_enc'] = _pat([eng.ar] + eng.gen_a)
+        sg['d_enc'] = critic(x_enc)
+        sg['d_real'] = critic(eng.x)
+    return sg
+
+
+@pytest.mark.parametrize('which', ['gen', 'disc', 'enc'])
+def test_emulator_reproduces_the_gpu_verified_fanogan_ops(which, monkeypatch):
+    E.install(monkeypatch, fanogan_engine)
+    S, B, rate, lr = 32, 2, 0.2, 1e-3
+    P = FO.perturb(FO.init_params(S, seed=1))
+    eng = fanogan_engine.FanoganEngine(S, batch=B, device='cpu', math_mode=0, kappa=1.0, scale=10.0)
+    x, z, alpha, m_z, m_gen = _feed(S, B, rate, eng.flat)
+    eng.fp.load(P)
+    eng.enable_training()
+    E.adopt(eng)
+    eng.set_inputs(x)
+    eng.set_latent(z)
+    eng.alpha.copy_(torch.from_numpy(alpha.reshape(-1)))
+    eng.mask_enc.copy_(torch.from_numpy(m_z[0]))
+    eng.mask_gen.copy_(torch.from_numpy(m_gen))
+    tr = FO.WganTrainer(P, lr=lr, dropout_rate=rate, scale=10.0, kappa=1.0, dtype=torch.float64)
+    out, G = tr.step(which, x, z, alpha, mask_enc=m_z[0], mask_gen=m_gen, signs=_fanogan_signs(eng, which, 1.0 / (1.0 - rate)))
+    step = {'gen': eng.step_gen, 'disc': eng.step_disc, 'enc': eng.step_enc}[which]
+    before = eng.fp.to_numpy()
+    res = step(lr, dropout_rate=rate, dropout=True, parity_noise=True)
+    for k, v in res.items():
+        if k in out:
+            assert abs(v - float(out[k])) <= 1e-5 * max(abs(float(out[k])), 1e-3), (k, v, float(out[k]))
+    if which == 'disc':
+        assert _rel(eng.ddx.numpy(), out['ddx'].numpy()) < TOL
+    _compare_grads(eng, G)
+    scope = {'gen': 'Generator', 'disc': 'Discriminator', 'enc': 'Encoder'}[which]
+    _check_update(eng.fp.to_numpy(), before, tr.P, G, (scope,), lr)
+
+
+# ------------------------------------------------------------------------------------------------ 2. AnoVAEGAN
+def _anovaegan_signs(eng, which, on, keep):
+    def critic(x_dev):
+        eng._critic_forward(eng.pass1, x_dev, critic=False)
+        return _pat(eng.pass1.a)
+    out = eng._forward_out(on, keep)
+    sg = {'enc': _pat(eng.enc_a), 'gen': _pat([eng.ar] + eng.gen_a)}
+    l1_sign = np.sign(out.numpy() - eng.x.numpy())
+    if which in ('gen', 'disc'):
+        sg['d_fake'] = critic(out)
+    if which == 'disc':
+        sg['d_real'] = critic(eng.x)
+        E.call('uad_interpolate', eng.x, out, eng.alpha, eng.x_hat, eng.B, eng.S * eng.S, 0)
+        sg['d_hat'] = critic(eng.x_hat)
+    return sg, l1_sign
+
+
+def _anovaegan(monkeypatch, S=32, B=2, rate=0.2, zDim=128, kl_weight=1.0):
+    E.install(monkeypatch, fanogan_engine, anovaegan_engine)
+    P = FO.perturb(AO.init_params(S, zDim=zDim, seed=1))
+    eng = anovaegan_engine.AnoVaeGanEngine(S, zDim=zDim, batch=B, device='cpu', math_mode=0, kl_weight=kl_weight, scale=10.0)
+    assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
+    x, eps, alpha, m_z, m_gen = _feed(S, B, rate, eng.flat, zDim)
+    eng.fp.load(P)
+    eng.enable_training()
+    E.adopt(eng)
+    eng.set_inputs(x)
+    eng.set_noise(eps)
+    eng.alpha.copy_(torch.from_numpy(alpha.reshape(-1)))
+    eng.mask_mu.copy_(torch.from_numpy(m_z[0]))
+    eng.mask_ls.copy_(torch.from_numpy(m_z[1]))
+    eng.mask_gen.copy_(torch.from_numpy(m_gen))
+    masks = {'mu': m_z[0], 'ls': m_z[1], 'dec': m_gen}
+    return eng, P, x, eps, alpha, masks
+
+
+@pytest.mark.parametrize('kl_weight', [1.0, 0.25])
+@pytest.mark.parametrize('which', ['vae', 'gen', 'disc'])
+def test_anovaegan_train_ops_match_oracle(which, kl_weight, monkeypatch):
+    rate, lr = 0.2, 1e-3
+    eng, P, x, eps, alpha, masks = _anovaegan(monkeypatch, rate=rate, kl_weight=kl_weight)
+    tr = AO.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, kl_weight=kl_weight, dtype=torch.float64)
+    sg, l1_sign = _anovaegan_signs(eng, which, True, 1.0 / (1.0 - rate))
+    out, G = tr.step(which, x, eps, alpha, masks, signs=sg, l1_sign=l1_sign)
+    step = {'vae': eng.step_vae, 'gen': eng.step_gen, 'disc': eng.step_disc}[which]
+    before = eng.fp.to_numpy()
+    res = step(lr, dropout_rate=rate, dropout=True, parity_noise=True)
+    for k, v in res.items():
+        if k in out:
+            assert abs(v - float(out[k])) <= 1e-5 * max(abs(float(out[k])), 1e-3), (k, v, float(out[k]))
+    assert _rel(eng.x_gen.numpy(), out['out'].numpy()) < TOL
+    assert _rel(eng.mu.numpy(), out['z_mu'].numpy()) < TOL and _rel(eng.sigma.numpy(), out['z_sigma'].numpy()) < TOL
+    if which == 'vae':
+        assert _rel(eng.l1.numpy(), out['L1'].numpy()) < TOL
+    if which == 'disc':
+        assert _rel(eng.ddx.numpy(), out['ddx'].numpy()) < TOL
+    _compare_grads(eng, G)
+    _check_update(eng.fp.to_numpy(), before, tr.P, G, anovaegan_engine.OPS[which], lr)
+
+
+def test_anovaegan_optimisers_own_their_adam_slots(monkeypatch):
+    """One mini-batch of AnoVAEGAN.train (optim_vae, optim_gen, 2 x optim_dis), twice: weights track the oracle trainer, whose
+    optim_gen keeps Adam moments for the Generator separate from optim_vae's (TensorFlow creates slots per optimizer)."""
+    rate, lr = 0.0, 1e-3
+    eng, P, x, eps, alpha, masks = _anovaegan(monkeypatch, rate=rate, zDim=32)
+    tr = AO.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, dtype=torch.float64)
+    for it in range(2):
+        for which in ('vae', 'gen', 'disc', 'disc'):
+            sg, l1_sign = _anovaegan_signs(eng, which, False, 1.0)
+            tr.step(which, x, eps, alpha, None, signs=sg, l1_sign=l1_sign)
+            {'vae': eng.step_vae, 'gen': eng.step_gen, 'disc': eng.step_disc}[which](lr, dropout_rate=rate, dropout=True,
+                                                                                     parity_noise=True)
+    assert eng.t == {'vae': 2, 'gen': 2, 'disc': 4}
+    assert [int(eng.steps[k][0]) for k in ('vae', 'gen', 'disc')] == [2, 2, 4]
+    after = eng.fp.to_numpy()
+    off = tot = 0
+    for k in after:                     # Adam steps are ~lr*sign(g) early on: elements whose float32 gradient is round-off may differ by O(lr)
+        d = np.abs(after[k] - tr.P[k].numpy().reshape(after[k].shape))
+        assert float(d.max()) < 4.5 * lr, (k, float(d.max()))
+        off += int((d > 0.05 * lr).sum())
+        tot += d.size
+    assert off < 2e-3 * tot, (off, tot)
+    lo, hi = eng.op_range('gen')
+    m_vae = eng.fp.m[lo:hi]
+    assert float(eng.m_gen.abs().max()) > 0 and not torch.equal(eng.m_gen, m_vae)
+    m_ref = tr.slots['gen']['m']
+    got = eng.fp.to_numpy(torch.cat([torch.zeros(lo), eng.m_gen, torch.zeros(eng.fp.numel - hi)]))
+    mmax = max(float(v.abs().max()) for v in m_ref.values())
+    for k, v in m_ref.items():
+        if float(v.abs().max()) < 1e-9 * mmax:          # biases feeding a LayerNorm: exactly 0 here, round-off in the oracle
+            assert float(np.abs(got[k]).max()) == 0.0, k
+            continue
+        assert _rel(got[k], v.numpy()) < 5e-2, k    # (trajectories drift by O(lr) elements; shared slots would be off by orders of magnitude)
+
+
+def test_anovaegan_validation_fetch_and_noise(monkeypatch):
+    """train=False evaluates the validation fetches without touching weights; perf-mode noise draws eps / masks / alpha."""
+    eng, P, x, eps, alpha, masks = _anovaegan(monkeypatch, rate=0.2)
+    before = eng.fp.to_numpy()
+    res = eng.step_vae(1e-3, dropout_rate=0.2, dropout=False, train=False, parity_noise=True)
+    o = {k: v.detach() for k, v in AO.graph(AO.as_leaves(P, torch.float64), x, eps, dropout_rate=0.2, training=False,
+                                            dtype=torch.float64, want=("vae",)).items()}
+    assert abs(res['reconstructionLoss'] - float(o['reconstructionLoss'])) < 1e-5 * float(o['reconstructionLoss'])
+    assert abs(res['kl'] - float(o['kl'])) < 1e-5 * float(o['kl'])
+    assert all(np.array_equal(before[k], v) for k, v in eng.fp.to_numpy().items())
+    e0, m0, a0 = eng.eps.clone(), eng.mask_gen.clone(), eng.alpha.clone()
+    eng.step_disc(1e-3, dropout_rate=0.2, dropout=True)
+    assert not torch.equal(e0, eng.eps) and not torch.equal(m0, eng.mask_gen) and not torch.equal(a0, eng.alpha)
+    assert int(eng.rng_ctr[0]) == 1 << 20
+    with pytest.raises(NotImplementedError):
+        eng.step_enc(1e-3)
+
+
+def test_anovaegan_trainer_loop(monkeypatch, tmp_path):
+    """trainers/AnoVAEGAN.train on the synthetic dataset, engine on the emulator: per mini-batch 1 optim_vae + 1 optim_gen +
+    5 optim_dis, validation pass, checkpoint written; the model / trainer keep the reference's protocol."""
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.anovaegan import anovaegan
+    from unsupervised_anomaly_detection_brain_mri_b200.models.customlayers import Placeholder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.AnoVAEGAN import AnoVAEGAN
+    E.install(monkeypatch, fanogan_engine, anovaegan_engine)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    config = AnoVAEGAN.Config()
+    assert (config.modelname, config.scale, config.kappa, config.kl_weight) == ('AnoVAEGAN', 10.0, 1.0, 1.0)
+    config.outputHeight = config.outputWidth = 32
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 16, 1
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate = 0.1, 1e-4
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.useCudaGraph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    outs = anovaegan(Placeholder([None, 32, 32, 1]), 0.1, False, config)
+    assert set(outs) == {'z_mu', 'z_log_sigma', 'z_sigma', 'out', 'd_fake_features', 'd_', 'd_features', 'd', 'x_hat', 'd_hat_features',
+                         'd_hat'}
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (32, 32)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 20, 28
+    ds = SYNTHETIC(opts)
+    model = AnoVAEGAN(None, config, network=anovaegan)
+    assert model.network.__name__ == 'anovaegan' and 'AnoVAEGAN' in model.model_dir
+    model.engine.enable_training()
+    E.adopt(model.engine)
+    w0 = model.engine.fp.to_numpy()
+    model.train(ds)
+    w1 = model.engine.fp.to_numpy()
+    for scope in ('Encoder', 'Generator', 'Discriminator'):
+        assert any(not np.array_equal(w0[k], w1[k]) for k in w0 if k.startswith(scope + '/')), scope
+    assert all(np.isfinite(v).all() for v in w1.values())
+    t = model.engine.t
+    assert t['vae'] == t['gen'] > 0 and t['disc'] == 5 * t['gen']
+    assert E.calls.count('uad_randn') == t['vae'] + t['gen'] + t['disc'] + ds.num_batches(2, set='VAL')
+    ok, step = model.load(model.checkpointDir)
+    assert ok and step == 1

@@ -141,3 +141,38 @@ def test_restore_gradient_finite_difference():
         if abs(fd - g[b, i, j, 0]) < 1e-4 * max(1.0, abs(fd)):
             checked += 1
     assert checked >= 10          # the remaining probes may straddle a kink of |.|
+
+
+def test_anovaegan_oracle_gradients_by_central_differences():
+    """oracle/anovaegan_cpu: autograd gradients of the three op losses (incl. the second-order gradient-penalty term) against
+    central differences in float64, on one entry per scope."""
+    from oracle import anovaegan_cpu as AO
+    from oracle.fanogan_cpu import perturb
+    S, B, Z = 32, 2, 16
+    P = perturb(AO.init_params(S, zDim=Z, seed=3))
+    rng = np.random.default_rng(0)
+    x = rng.uniform(size=(B, S, S, 1)).astype(np.float32)
+    eps = rng.standard_normal((B, Z)).astype(np.float32)
+    alpha = rng.uniform(size=(B, 1)).astype(np.float32)
+
+    def loss(Pv, which):
+        o = AO.graph(AO.as_leaves(Pv, torch.float64), x, eps, alpha, None, 0.0, True, 10.0, 0.5, torch.float64, want=(which,))
+        return o[{'vae': 'enc_loss', 'gen': 'gen_loss', 'disc': 'disc_loss'}[which]]
+
+    probes = {'vae': ['Encoder/dense_1/kernel', 'Generator/dec_Conv2DT_0/kernel', 'Encoder/batch_normalization/gamma'],
+              'gen': ['Generator/dense_2/kernel', 'Generator/layer_normalization_1/gamma'],
+              'disc': ['Discriminator/enc_conv2D_1/kernel', 'Discriminator/dense_3/kernel']}
+    for which, names in probes.items():
+        L = AO.as_leaves(P, torch.float64)
+        o = AO.graph(L, x, eps, alpha, None, 0.0, True, 10.0, 0.5, torch.float64, want=(which,))
+        g = torch.autograd.grad(o[{'vae': 'enc_loss', 'gen': 'gen_loss', 'disc': 'disc_loss'}[which]], [L[n] for n in names])
+        for n, gn in zip(names, g):
+            idx = np.unravel_index(int(np.argmax(np.abs(gn.numpy()))), gn.shape)
+            h = 1e-5
+            Pp, Pm = dict(P), dict(P)
+            Pp[n] = P[n].astype(np.float64).copy()
+            Pm[n] = P[n].astype(np.float64).copy()
+            Pp[n][idx] += h
+            Pm[n][idx] -= h
+            fd = (float(loss(Pp, which).detach()) - float(loss(Pm, which).detach())) / (2 * h)
+            assert abs(fd - float(gn[idx])) <= 1e-5 * max(abs(fd), 1e-6), (which, n, fd, float(gn[idx]))

@@ -97,6 +97,15 @@ class _CriticPass:
 
 class FanoganEngine:
     SC = dict(disc_fake=0, disc_real=1, gp=2, loss_img=3, loss_fts=4, reconstructionLoss=5)
+    # what a sibling graph on the same stacks overrides (anovaegan_engine.AnoVaeGanEngine): TF names of the Dense layers (the
+    # tf.layers name counter runs over the whole graph) and the generator's output non-linearity
+    GEN_DENSE = 'Generator/dense_1'
+    DISC_DENSE = 'Discriminator/dense_2'
+    FINAL_ACT = ACT_SIGMOID
+
+    @staticmethod
+    def _param_specs(S, C, zDim, res):
+        return param_specs(S, C, zDim, res)
 
     def __init__(self, S, C=1, zDim=128, res=8, batch=8, device='cuda:0', math_mode=abi.MATH_TC_3XTF32, seed=1, kappa=1.0,
                  scale=10.0):
@@ -110,7 +119,7 @@ class FanoganEngine:
         self.n, self.enc_ch, self.dec_ch = stack_plan(S, res)
         self.cb = self.enc_ch[-1] // 8
         self.flat = res * res * self.cb
-        self.specs = param_specs(S, C, zDim, res)
+        self.specs = self._param_specs(S, C, zDim, res)
         self.fp = FlatParams(self.specs, self.device)
         init = glorot_init(self.specs, seed)
         self.fp.load(init)
@@ -255,7 +264,7 @@ class FanoganEngine:
         ctop = self.enc_ch[-1]
         out = self.x_enc if out is None else out
         self._g_in, self._g_mask, self._g_keep = z, mask, keep
-        call('uad_dense_fwd', ptr(z), ptr(fp.p('Generator/dense_1/kernel')), ptr(fp.p('Generator/dense_1/bias')), ptr(mask), keep,
+        call('uad_dense_fwd', ptr(z), ptr(fp.p(self.GEN_DENSE + '/kernel')), ptr(fp.p(self.GEN_DENSE + '/bias')), ptr(mask), keep,
              None, None, ptr(self.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, ws, wsb, st)
         call('uad_dense_fwd', ptr(self.d), ptr(fp.p('Generator/conv2d_1/kernel')), ptr(fp.p('Generator/conv2d_1/bias')), None, 1.0,
              None, None, ptr(self.zr), None, B * r2, self.cb, ctop, ACT_NONE, 0.0, 1.0, ws, wsb, st)
@@ -276,9 +285,11 @@ class FanoganEngine:
             ln += 1
             h, cin = self.gen_a[i], co
         # final 1x1 conv (Cin -> 1), then sigmoid (fanogan.py:41)
+        head = self.g_pre if self.FINAL_ACT != ACT_NONE else out
         call('uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Generator/dec_Conv2D_final/kernel')), ptr(fp.p('Generator/dec_Conv2D_final/bias')),
-             ptr(self.x), ptr(self.g_pre), None, None, B, self.S * self.S, cin, ws, wsb, st)
-        call('uad_activation', ptr(self.g_pre), ptr(out), self.g_pre.numel(), ACT_SIGMOID, 0.0, st)
+             ptr(self.x), ptr(head), None, None, B, self.S * self.S, cin, ws, wsb, st)
+        if self.FINAL_ACT != ACT_NONE:
+            call('uad_activation', ptr(self.g_pre), ptr(out), self.g_pre.numel(), self.FINAL_ACT, 0.0, st)
         return out
 
     def _critic_forward(self, cp, x_dev, critic=True):
@@ -299,7 +310,7 @@ class FanoganEngine:
             h, cin = cp.a[i], co
         if critic:
             r2 = self.res * self.res
-            call('uad_dense_fwd', ptr(h), ptr(fp.p('Discriminator/dense_2/kernel')), ptr(fp.p('Discriminator/dense_2/bias')), None,
+            call('uad_dense_fwd', ptr(h), ptr(fp.p(self.DISC_DENSE + '/kernel')), ptr(fp.p(self.DISC_DENSE + '/bias')), None,
                  1.0, None, None, ptr(cp.d), None, B * r2, cin, 1, ACT_NONE, 0.0, 1.0, ws, wsb, st)
         return h, cp.d
 
@@ -319,9 +330,9 @@ class FanoganEngine:
         r2 = self.res * self.res
         ctop = self.enc_ch[-1]
         call('uad_fill', ptr(self.ones), float(coef), self.ones.numel(), st)
-        call('uad_dense_bwd', ptr(cp.a[-1]), ptr(fp.p('Discriminator/dense_2/kernel')), ptr(self.ones), None, 1.0,
-             ptr(self.dis_g1[-1]), ptr(fp.g('Discriminator/dense_2/kernel')) if params else None,
-             ptr(fp.g('Discriminator/dense_2/bias')) if params else None, self.B * r2, ctop, 1, 1, ws, wsb, st)
+        call('uad_dense_bwd', ptr(cp.a[-1]), ptr(fp.p(self.DISC_DENSE + '/kernel')), ptr(self.ones), None, 1.0,
+             ptr(self.dis_g1[-1]), ptr(fp.g(self.DISC_DENSE + '/kernel')) if params else None,
+             ptr(fp.g(self.DISC_DENSE + '/bias')) if params else None, self.B * r2, ctop, 1, 1, ws, wsb, st)
         return self.dis_g1[-1]
 
     def _critic_backward(self, cp, x_in, params, dx_out):
@@ -362,7 +373,7 @@ class FanoganEngine:
         sizes = [S >> k for k in range(n + 1)]
         r2 = self.res * self.res
         ctop = self.enc_ch[-1]
-        wd = fp.p('Discriminator/dense_2/kernel')
+        wd = fp.p(self.DISC_DENSE + '/kernel')
         # (1) ddx = d sum(d_hat) / d x_hat
         self._critic_top(cp, 1.0, params=False)
         self._critic_backward(cp, x_hat, params=False, dx_out=self.ddx)
@@ -383,7 +394,7 @@ class FanoganEngine:
         # (4) joint reverse of s_dot = sum(hd_top . w_d): adjoint of hd_top = w_d, of h_top = 0; d/dw_d = sum hd_top
         call('uad_fill', ptr(self.ones), 1.0, self.ones.numel(), st)
         call('uad_dense_bwd', ptr(self.dis_hd[-1]), ptr(wd), ptr(self.ones), None, 1.0, ptr(self.dis_g1[-1]),
-             ptr(fp.g('Discriminator/dense_2/kernel')), None, B * r2, ctop, 1, 1, ws, wsb, st)
+             ptr(fp.g(self.DISC_DENSE + '/kernel')), None, B * r2, ctop, 1, 1, ws, wsb, st)
         have_dh = False
         for i in reversed(range(n)):
             co = self.enc_ch[i]
@@ -407,9 +418,10 @@ class FanoganEngine:
                      mm, ws, wsb, st)
                 have_dh = True
 
-    def _generator_backward(self, dx_out, params, dz_out=None):
-        """Reverse pass of the last generate() call from d/d(sigmoid output).  params: Generator gradients (overwritten);
-        dz_out: gradient w.r.t. the latent input."""
+    def _generator_backward(self, dx_out, params, dz_out=None, head=True):
+        """Reverse pass of the last generate() call from d/d(output).  params: Generator gradients (overwritten);
+        dz_out: gradient w.r.t. the latent input.  head=False: the caller has already taken the final 1x1 conv's backward
+        (gradient w.r.t. the last block's activation in gen_g[-1], its parameter gradients written)."""
         fp, st, mm = self.fp, self._st(), self.math_mode
         ws, wsb = self._wsp()
         B, r = self.B, self.res
@@ -417,11 +429,14 @@ class FanoganEngine:
         ctop = self.enc_ch[-1]
         nd = len(self.dec_ch)
         G = (lambda name: ptr(fp.g(name))) if params else (lambda name: None)
-        call('uad_activation_bwd', ptr(dx_out), ptr(self.g_pre), ptr(self.dxi2), self.g_pre.numel(), ACT_SIGMOID, 0.0, st)
-        cin = self.dec_ch[-1]
-        g = self.gen_g[-1]
-        call('uad_final1x1_bwd', ptr(self.gen_a[-1]), ptr(fp.p('Generator/dec_Conv2D_final/kernel')), ptr(self.dxi2), ptr(g),
-             G('Generator/dec_Conv2D_final/kernel'), G('Generator/dec_Conv2D_final/bias'), B, self.S * self.S, cin, 0, ws, wsb, st)
+        if head:
+            seed = dx_out
+            if self.FINAL_ACT != ACT_NONE:
+                call('uad_activation_bwd', ptr(dx_out), ptr(self.g_pre), ptr(self.dxi2), self.g_pre.numel(), self.FINAL_ACT, 0.0, st)
+                seed = self.dxi2
+            call('uad_final1x1_bwd', ptr(self.gen_a[-1]), ptr(fp.p('Generator/dec_Conv2D_final/kernel')), ptr(seed), ptr(self.gen_g[-1]),
+                 G('Generator/dec_Conv2D_final/kernel'), G('Generator/dec_Conv2D_final/bias'), B, self.S * self.S, self.dec_ch[-1], 0,
+                 ws, wsb, st)
         s = self.S
         for i in reversed(range(nd)):
             co = self.dec_ch[i]
@@ -443,8 +458,8 @@ class FanoganEngine:
              ptr(self.dzr), G(gam), G(bet), B, r2, ctop, ACT_RELU, 0.0, 0, ws, wsb, st)
         call('uad_dense_bwd', ptr(self.d), ptr(fp.p('Generator/conv2d_1/kernel')), ptr(self.dzr), None, 1.0, ptr(self.dd),
              G('Generator/conv2d_1/kernel'), None, B * r2, self.cb, ctop, 0, ws, wsb, st)
-        call('uad_dense_bwd', ptr(self._g_in), ptr(fp.p('Generator/dense_1/kernel')), ptr(self.dd), ptr(self._g_mask), self._g_keep,
-             ptr(dz_out), G('Generator/dense_1/kernel'), G('Generator/dense_1/bias'), B, self.zDim, self.flat, 0, ws, wsb, st)
+        call('uad_dense_bwd', ptr(self._g_in), ptr(fp.p(self.GEN_DENSE + '/kernel')), ptr(self.dd), ptr(self._g_mask), self._g_keep,
+             ptr(dz_out), G(self.GEN_DENSE + '/kernel'), G(self.GEN_DENSE + '/bias'), B, self.zDim, self.flat, 0, ws, wsb, st)
 
     def _encoder_backward(self, dz_enc):
         fp, st, mm = self.fp, self._st(), self.math_mode
@@ -455,6 +470,15 @@ class FanoganEngine:
         call('uad_activation_bwd', ptr(dz_enc), ptr(self.z_pre), ptr(dz_enc), dz_enc.numel(), ACT_TANH, 0.0, st)
         call('uad_dense_bwd', ptr(self.zb), ptr(fp.p('Encoder/dense/kernel')), ptr(dz_enc), ptr(self._e_mask), self._e_keep,
              ptr(self.dzb), ptr(fp.g('Encoder/dense/kernel')), ptr(fp.g('Encoder/dense/bias')), B, self.flat, self.zDim, 0, ws, wsb, st)
+        self._encoder_stack_backward()
+
+    def _encoder_stack_backward(self):
+        """From dzb (gradient w.r.t. the 1x1 bottleneck conv's output) down through the frozen-BN conv blocks."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsp()
+        B, r = self.B, self.res
+        r2 = r * r
+        ctop = self.enc_ch[-1]
         call('uad_dense_bwd', ptr(self.enc_a[-1]), ptr(fp.p('Encoder/conv2d/kernel')), ptr(self.dzb), None, 1.0, ptr(self.enc_g[-1]),
              ptr(fp.g('Encoder/conv2d/kernel')), ptr(fp.g('Encoder/conv2d/bias')), B * r2, ctop, self.cb, 0, ws, wsb, st)
         n = len(self.enc_ch)

@@ -25,6 +25,15 @@ class fAnoGAN(DLMODEL):
             self.kappa = 1.0
             self.scale = 10.0
 
+    ENGINE = FanoganEngine          # what a sibling trainer on the same stacks overrides (trainers/AnoVAEGAN.py)
+    REC_KEY = 'x_enc'
+
+    def _network_outputs(self):
+        return self.network(self.z, self.x, dropout_rate=self.dropout_rate, dropout=self.dropout, config=self.config)
+
+    def _engine_kwargs(self):
+        return dict(kappa=float(self.config.kappa), scale=float(self.config.scale))
+
     def __init__(self, sess, config=None, network=None):
         super().__init__(sess, config if config is not None else self.Config())
         self.losses = {}
@@ -34,9 +43,9 @@ class fAnoGAN(DLMODEL):
         self.z = Placeholder([None, cfg.zDim], 'z')
         self.dropout = Placeholder([], 'dropout')
         self.dropout_rate = Placeholder([], 'dropout_rate')
-        self.outputs = self.network(self.z, self.x, dropout_rate=self.dropout_rate, dropout=self.dropout, config=cfg)
-        self.reconstruction = self.outputs['x_enc']
-        self.generated = self.outputs['x_']
+        self.outputs = self._network_outputs()
+        self.reconstruction = self.outputs[self.REC_KEY]
+        self.generated = self.outputs.get('x_')
         self.graph = self.reconstruction.graph
         self.checkpointDir = os.path.join(cfg.checkpointDir or 'checkpoints', self.network.__name__)
         self.logDir = os.path.join(os.getcwd(), 'logs', self.network.__name__, self.model_dir, datetime.now().strftime('%Y%m%d_%H%M%S'))
@@ -44,8 +53,8 @@ class fAnoGAN(DLMODEL):
         self.math_mode = int(getattr(cfg, 'math_mode', abi.MATH_TC_3XTF32))
         torch.cuda.set_device(self.device)
         g = self.graph
-        self.engine = FanoganEngine(g.S, g.C, g.zDim, g.res, batch=cfg.batchsize, device=self.device, math_mode=self.math_mode,
-                                    seed=int(getattr(cfg, 'seed', 1)), kappa=float(cfg.kappa), scale=float(cfg.scale))
+        self.engine = self.ENGINE(g.S, g.C, g.zDim, g.res, batch=cfg.batchsize, device=self.device, math_mode=self.math_mode,
+                                  seed=int(getattr(cfg, 'seed', 1)), **self._engine_kwargs())
         self._eval = {}
         self.world, self._allreduce = 1, None
         self.logger = Logger(self.sess, self.logDir, enabled=bool(getattr(cfg, 'useTensorboard', False)))
@@ -166,7 +175,7 @@ class fAnoGAN(DLMODEL):
     def _engine_for(self, n):
         if n not in self._eval:
             g = self.graph
-            e = FanoganEngine(g.S, g.C, g.zDim, g.res, batch=n, device=self.device, math_mode=self.math_mode)
+            e = self.ENGINE(g.S, g.C, g.zDim, g.res, batch=n, device=self.device, math_mode=self.math_mode)
             e.fp = self.engine.fp            # share the weights
             self._eval[n] = e
         return self._eval[n]
