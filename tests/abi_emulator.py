@@ -144,19 +144,52 @@ def uad_convT2d_wgrad(x, dz, dw, B, H, W, Cin, Cout, k, accumulate, mm, ws, wsb,
 
 
 def uad_act_bn_bwd(da, z, gamma, beta, dz, dgamma, dbeta, dbias, rows, C, act, alpha, bn_c, accumulate, ws, wsb, st):
-    assert not (act & 0x100), 'emulator: UAD_ACT_FROM_OUTPUT is not modelled'
     zt, dat = _v(z, rows, C), _v(da, rows, C)
-    if gamma is None:
-        du = dat * _dact(zt, act, alpha)
-        dzt = du
+    g = _v(gamma, C) if gamma is not None else torch.ones(C, dtype=D)
+    b = _v(beta, C) if gamma is not None else torch.zeros(C, dtype=D)
+    c = bn_c if gamma is not None else 1.0
+    if act & 0x100:                 # UAD_ACT_FROM_OUTPUT: `z` holds a = act(u), u = gamma*bn_c*z + beta (piecewise-linear act only)
+        a = zt
+        u = torch.where(a > 0, a, a / alpha) if (act & 0xff) == ACT_LEAKY else a
+        zt = (u - b) / (g * c)
     else:
-        g, b = _v(gamma, C), _v(beta, C)
-        du = dat * _dact(g * bn_c * zt + b, act, alpha)
-        dzt = g * bn_c * du
-        _acc(dgamma, bn_c * (du * zt).sum(0), accumulate)
+        u = g * c * zt + b
+    du = dat * _dact(u, act, alpha)
+    dzt = g * c * du
+    if gamma is not None:
+        _acc(dgamma, c * (du * zt).sum(0), accumulate)
         _acc(dbeta, du.sum(0), accumulate)
     _acc(dbias, dzt.sum(0), accumulate)
     _w(dz, dzt)
+
+
+def uad_final1x1_l1_bwd_fused(z, gamma, beta, w, x, xhat, scale, dz, dgamma, dbeta, dbias_prev, dw, dbias, B, HW, Cin, act, alpha, bn_c,
+                              accumulate, ws, wsb, st):
+    """= uad_final1x1_l1_bwd followed by uad_act_bn_bwd of the preceding block, without materialising da."""
+    rows = B * HW
+    g, b = _v(gamma, Cin), _v(beta, Cin)
+    zt = _v(z, rows, Cin)
+    if act & 0x100:
+        a = zt
+        zt = ((torch.where(a > 0, a, a / alpha) if (act & 0xff) == ACT_LEAKY else a) - b) / (g * bn_c)
+    else:
+        a = _act(g * bn_c * zt + b, act, alpha)
+    dxh = torch.sign(_v(xhat, rows) - _v(x, rows)) * scale
+    _acc(dw, a.t() @ dxh, accumulate)
+    _acc(dbias, dxh.sum().reshape(1), accumulate)
+    da = dxh[:, None] * _v(w, Cin)[None, :]
+    du = da * _dact(g * bn_c * zt + b, act, alpha)
+    dzt = g * bn_c * du
+    _acc(dgamma, bn_c * (du * zt).sum(0), accumulate)
+    _acc(dbeta, du.sum(0), accumulate)
+    _acc(dbias_prev, dzt.sum(0), accumulate)
+    _w(dz, dzt)
+
+
+def uad_loss_scalars(rec, kl, out3, B, st):
+    r = _v(rec, B)
+    k = _v(kl, B) if kl is not None else torch.zeros(B, dtype=D)
+    _w(out3, torch.stack([r.mean(), k.mean(), (r + k).mean()]))
 
 
 # ------------------------------------------------------------------------------------------------ dense / bottleneck
@@ -392,16 +425,23 @@ def ptr(t):
 
 def install(monkeypatch, *modules):
     """Route the given engine modules' ABI calls through the emulator and make their engines live on the CPU."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
     from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
     for mod in modules:
         monkeypatch.setattr(mod, 'call', call)
         monkeypatch.setattr(mod, 'ptr', ptr)
     monkeypatch.setattr(FanoganEngine, '_st', lambda self: 0)
+    monkeypatch.setattr(ConvAutoencoderEngine, '_st', lambda self: 0)
     del _registry[:]
     del calls[:]
 
 
 def adopt(engine):
     """Register the buffers an engine passes as raw pointers (loss scalars, step counters, the Philox counter)."""
-    register(engine.sc, engine.rng_ctr, *engine.steps.values())
+    for name in ('sc', 'scalars', 'rng_ctr', 'step_dev'):
+        if hasattr(engine, name):
+            register(getattr(engine, name))
+    for name in ('steps', 'op_steps'):
+        if hasattr(engine, name):
+            register(*getattr(engine, name).values())
     return engine

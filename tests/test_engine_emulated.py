@@ -273,3 +273,42 @@ def test_anovaegan_trainer_loop(monkeypatch, tmp_path):
     assert E.calls.count('uad_randn') == t['vae'] + t['gen'] + t['disc'] + ds.num_batches(2, set='VAL')
     ok, step = model.load(model.checkpointDir)
     assert ok and step == 1
+
+
+# ------------------------------------------------------------------------------------------------ 3. the AE-family engine
+@pytest.mark.parametrize('keep_preact', [False, True])
+@pytest.mark.parametrize('arch', [O.VAE, O.CAE])
+def test_emulator_reproduces_the_gpu_verified_autoencoder_steps(arch, keep_preact, monkeypatch):
+    """Calibration on engine.ConvAutoencoderEngine (VAE: fused final-1x1 backward, reparameterisation; constrained AE: the split
+    backward_constrained -> backward_from_gxhat), both backward variants (from z, from the block output)."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod)
+    S, B, rate, lr = 32, 2, 0.2, 1e-3
+    P = O.perturb_params(O.init_params(arch, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=31)
+    eng = eng_mod.ConvAutoencoderEngine(arch, S, batch=B, device='cpu', math_mode=0, keep_preact=keep_preact)
+    E.adopt(eng)
+    eng.fp.load(P)
+    rng = np.random.default_rng(8)
+    mk = lambda n: (rng.uniform(size=(B, n)) >= rate).astype(np.float32)   # noqa: E731
+    eng.set_inputs(x)
+    if arch == O.CAE:
+        om = {'z': mk(128), 'dec': mk(eng.flat), 'z_rec': mk(128)}
+        eng.set_noise(None, {'mu': om['z'], 'dec': om['dec']}, {'mu': om['z_rec']})
+        kw = dict(masks=om, rho=1.0)
+    else:
+        om = {'mu': mk(128), 'ls': mk(128), 'dec': mk(eng.flat)}
+        eps = rng.standard_normal((B, 128)).astype(np.float32)
+        eng.set_noise(eps, om)
+        eng._keep = 1.0 / (1.0 - rate)
+        eng.forward(training=True, dropout_rate=rate)
+        kw = dict(masks={'mu': om['mu'], 'log_sigma': om['ls'], 'dec': om['dec']}, eps=eps, l1_sign=np.sign(eng.br[0].xhat.numpy() - x))
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True)
+    out, L, G = O.loss_and_grads(arch, P, x, dropout_rate=rate, training=True, dtype=torch.float64, **kw)
+    assert _rel(eng.br[0].xhat.numpy(), out['x_hat'].numpy()) < TOL
+    got = eng.losses()
+    for k in got:
+        assert abs(got[k] - float(L[k])) <= 1e-5 * abs(float(L[k])), (k, got[k], float(L[k]))
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    for k in P:
+        assert _rel(grads[k], G[k].numpy()) < 2e-5, (k, _rel(grads[k], G[k].numpy()))

@@ -33,7 +33,9 @@ VAE = 'variational_autoencoder'
 CEVAE = 'context_encoder_variational_autoencoder'
 AES = 'autoencoder_spatial'      # encoder -> Dropout -> decoder, no dense bottleneck (reference models/autoencoder_spatial.py)
 CAE = 'constrained_autoencoder'  # dense AE whose reconstruction is re-encoded: z_rec = Enc(x_hat) (models/constrained_autoencoder.py)
-ARCHS = (AE, VAE, CEVAE, AES, CAE)
+AAE = 'adversarial_autoencoder'  # dense AE (both bottleneck Dropouts honour the flag, MSE loss) + latent MLP critic (aae_engine.py)
+ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE)
+AAE_CRITIC = (50, 50, 1)         # Dense widths of the latent critic (models/adversarial_autoencoder.py:44-48)
 
 
 import contextlib
@@ -87,7 +89,7 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
         sp['Bottleneck/conv2d_1/bias'] = (cin,)
         flat = res * res * cb
-        heads = 1 if arch in (AE, CAE) else 2
+        heads = 1 if arch in (AE, CAE, AAE) else 2
         for h in range(heads):
             nm = 'dense' if h == 0 else f'dense_{h}'
             sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
@@ -106,6 +108,12 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         cin = co
     sp['Decoder/dec_Conv2D_final/kernel'] = (1, 1, cin, C)
     sp['Decoder/dec_Conv2D_final/bias'] = (C,)
+    if arch == AAE:                  # the tf.layers Dense counter runs on: Bottleneck/{dense, dense_1}, Discriminator/dense_{2,3,4}
+        k = zDim
+        for j, width in enumerate(AAE_CRITIC):
+            sp[f'Discriminator/dense_{2 + j}/kernel'] = (k, width)
+            sp[f'Discriminator/dense_{2 + j}/bias'] = (width,)
+            k = width
     return sp
 
 
@@ -278,6 +286,8 @@ class ConvAutoencoderEngine:
             self.gxhat = self._new(B, S, S, 1)           # d loss / d x_hat: MSE term + the re-encoding pass
             self.dzrec = self._new(B, self.zDim)
             self.rho = 1.0                               # trainers/ConstrainedAE.py:16
+        if self.arch == AAE:
+            self.gxhat = self._new(B, S, S, 1)           # d loss / d x_hat of the MSE loss (trainers/AAE.py:55-57)
         big = B * S * S * max(32, self.dec_ch[-1])
         self.gbuf = [self._new(big), self._new(big)]
         self.gx = self._new(B, S, S, 1)                  # d loss / d x (ceVAE anomaly)
@@ -367,9 +377,10 @@ class ConvAutoencoderEngine:
                 br.masks['sp'] = None
             call('uad_counter_add', ctr, 1 << 20, st)
             return
-        if self.arch == CAE:                             # three Dropout calls: z, dec_dense(z), z_rec (each its own draw)
+        if self.arch in (CAE, AAE):                      # Dropout calls: z, dec_dense(z) [, z_rec] (each its own draw)
             on = bool(dropout) and rate > 0
-            for sid, (br, k) in enumerate(((self.br[0], 'mu'), (self.br[0], 'dec'), (self.br[1], 'mu'))):
+            sites = ((self.br[0], 'mu'), (self.br[0], 'dec')) + (((self.br[1], 'mu'),) if self.arch == CAE else ())
+            for sid, (br, k) in enumerate(sites):
                 if on:
                     call('uad_dropout_mask', ptr(br.mask_bufs[k]), br.mask_bufs[k].numel(), float(rate), self.rng_seed,
                          (sid + 1) << 40, ctr, st)
@@ -419,12 +430,12 @@ class ConvAutoencoderEngine:
                    1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             if self.arch == AES:
                 pass
-            elif self.arch in (AE, CAE):
+            elif self.arch in (AE, CAE, AAE):
                 # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity.
-                # constrained_autoencoder.py:29-30: BOTH dropout calls honour the flag.
+                # constrained_autoencoder.py:29-30, adversarial_autoencoder.py:30-31: BOTH dropout calls honour the flag.
                 self._op('bneck02', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
                      ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
-                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', (m['dec'] if self.arch == CAE else None)
+                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', (m['dec'] if self.arch in (CAE, AAE) else None)
                 if is_ce:                                # constrained AE, re-encoding pass: z_rec is all that is needed
                     continue
             else:
@@ -460,7 +471,7 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE) else None, ptr(self.scalars), B, st)
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE) else None, ptr(self.scalars), B, st)
         if self.arch == CAE and (branches is None or 1 in branches):
             # trainers/ConstrainedAE.py:37-43: L2 = mean_hwc (x - x_hat)^2, Rec_z = mean_j (z - z_rec)^2 (per sample);
             # loss = mean_b(L2 + rho * Rec_z).  The same calls leave d loss/d x_hat and d loss/d z_rec (d/dz = -d/dz_rec).
@@ -471,6 +482,10 @@ class ConvAutoencoderEngine:
                      self.scalars[5:].data_ptr(), ws, wsb, st)
         if self.arch == CEVAE and (branches is None or 1 in branches):
             self._op('bneck09', 'uad_loss_scalars', ptr(self.br[1].rec), None, ptr(self.scalars[3:]), B, st)
+        if self.arch == AAE:         # trainers/AAE.py:55-57: loss = mean_b mean_hwc (x - x_hat)^2; leaves d loss / d x_hat in gxhat
+            nx = b0.x.numel()
+            self._op('bneck09', 'uad_mse', ptr(b0.xhat), ptr(b0.x), nx, 2.0 / nx, ptr(self.gxhat), 1.0 / nx, self.scalars[4:].data_ptr(),
+                     ws, wsb, st)
 
     # ------------------------------------------------------------------ backward
     def backward(self, want_input_grad=False):
@@ -641,6 +656,21 @@ class ConvAutoencoderEngine:
         self._encoder_backward(b1, g, gn, 0, self.gx)
         # d loss / d x_hat = MSE term (in gxhat) + the path through the re-encoding pass (in gx)
         self._op('bneck22', 'uad_axpby', 1.0, ptr(self.gx), 1.0, ptr(self.gxhat), b0.x.numel(), st)
+        self.backward_from_gxhat(acc=1, dzrec=self.dzrec)
+
+    def backward_from_gxhat(self, acc=0, dzrec=None):
+        """Decoder + bottleneck + encoder reverse pass of the dense AE whose BOTH bottleneck Dropouts honour the flag, seeded
+        with d loss / d x_hat in ``gxhat``.  acc: the Encoder / Bottleneck-dense gradients accumulate onto what a preceding pass
+        left (constrained AE); dzrec: an extra -dzrec on d/dz (constrained AE).  With acc=0, dzrec=None this is the whole
+        backward of the adversarial AE's reconstruction loss (trainers/AAE.py:55-57,67)."""
+        fp, st, mm = self.fp, self._st(), self.math_mode
+        ws, wsb = self._wsargs()
+        B, b0, sm = self.B, self.br[0], self.small
+        r2 = self.res * self.res
+        ctop = self.enc_ch[-1]
+        keep = self._keep
+        kp = self.keep_preact
+        act_blk = ACT_LEAKY if kp else (ACT_LEAKY | abi.ACT_FROM_OUTPUT)
         # ---- decoder
         g, gn = self.gbuf
         cin = self.dec_ch[-1]
@@ -673,14 +703,15 @@ class ConvAutoencoderEngine:
         self._op('bneck11', 'uad_dense_bwd', ptr(b0.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), ptr(b0.masks['dec']), keep,
                  ptr(sm['dmu']), ptr(fp.g('Bottleneck/dense_1/kernel')), ptr(fp.g('Bottleneck/dense_1/bias')), B, self.zDim, self.flat,
                  0, ws, wsb, st)
-        self._op('bneck23', 'uad_axpby', -1.0, ptr(self.dzrec), 1.0, ptr(sm['dmu']), B * self.zDim, st)     # d Rec_z / d z = -d/d z_rec
+        if dzrec is not None:
+            self._op('bneck23', 'uad_axpby', -1.0, ptr(dzrec), 1.0, ptr(sm['dmu']), B * self.zDim, st)     # d Rec_z / d z = -d/d z_rec
         self._op('bneck12', 'uad_dense_bwd', ptr(b0.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(sm['dmu']), ptr(b0.masks['mu']), keep,
                  ptr(sm['dflat']), ptr(fp.g('Bottleneck/dense/kernel')), ptr(fp.g('Bottleneck/dense/bias')), B, self.flat, self.zDim,
-                 1, ws, wsb, st)
+                 acc, ws, wsb, st)
         self._op('bneck18', 'uad_dense_bwd', ptr(b0.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0, ptr(g),
-                 ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb, 1, ws, wsb, st)
-        # ---- pass 1 encoder (accumulating)
-        self._encoder_backward(b0, g, gn, 1, None)
+                 ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb, acc, ws, wsb, st)
+        # ---- pass 1 encoder (accumulating onto the re-encoding pass when acc = 1)
+        self._encoder_backward(b0, g, gn, acc, None)
 
     # ------------------------------------------------------------------ gradient w.r.t. the input only (restoration)
     def backward_to_input(self, seed, kl_scale=1.0):
@@ -823,6 +854,9 @@ class ConvAutoencoderEngine:
         if self.arch == CAE:
             self.backward_constrained()
             return
+        if self.arch == AAE:
+            self.backward_from_gxhat()
+            return
         self.backward(want_input_grad=want_anomaly)
         if want_anomaly and self.arch == CEVAE:
             self._finish_anomaly()
@@ -880,6 +914,8 @@ class ConvAutoencoderEngine:
         if self.arch == CAE:
             return {'reconstructionLoss': float(s[0]), 'L2': float(s[4]), 'Rec_z': float(s[5]),
                     'loss': float(s[4]) + self.rho * float(s[5])}
+        if self.arch == AAE:
+            return {'reconstructionLoss': float(s[0]), 'L2': float(s[4]), 'loss': float(s[4])}
         if self.arch == VAE:
             return {'reconstructionLoss': float(s[0]), 'kl': float(s[1]), 'loss': float(s[2])}
         return {'Rec_vae': float(s[0]), 'kl': float(s[1]), 'loss_vae': float(s[2]), 'Rec_ce': float(s[3]),
