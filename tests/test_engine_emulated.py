@@ -312,3 +312,140 @@ def test_emulator_reproduces_the_gpu_verified_autoencoder_steps(arch, keep_preac
     grads = eng.fp.to_numpy(eng.fp.grads)
     for k in P:
         assert _rel(grads[k], G[k].numpy()) < 2e-5, (k, _rel(grads[k], G[k].numpy()))
+
+
+# ------------------------------------------------------------------------------------------------ 4. adversarial autoencoder
+def _aae(monkeypatch, S=32, B=2, rate=0.2, zDim=32):
+    from oracle import aae_cpu as AA
+    from unsupervised_anomaly_detection_brain_mri_b200 import aae_engine
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod, aae_engine)
+    P = AA.perturb(AA.init_params(S, zDim=zDim, seed=1))
+    eng = aae_engine.AdversarialAEEngine(S, zDim=zDim, batch=B, device='cpu', math_mode=0, scale=10.0)
+    E.adopt(eng)
+    assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
+    eng.fp.load(P)
+    rng = np.random.default_rng(5)
+    x = O.synthetic_slices(B, S, seed=31)
+    z = rng.standard_normal((B, zDim)).astype(np.float32)
+    epsilon = rng.random((B, 1), dtype=np.float32)
+    masks = {'z': (rng.uniform(size=(B, zDim)) >= rate).astype(np.float32), 'dec': (rng.uniform(size=(B, eng.flat)) >= rate).astype(np.float32)}
+    eng.set_inputs(x)
+    eng.set_latent(z)
+    eng.set_epsilon(epsilon)
+    eng.set_noise(None, {'mu': masks['z'], 'dec': masks['dec']})
+    return AA, eng, P, x, z, epsilon, masks
+
+
+def _aae_signs(eng, which, rate):
+    eng._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+    z_ = eng.encode_latent()
+    sg = {}
+    if which in ('gen', 'disc'):
+        eng.critic_forward(z_)
+        sg['d_fake'] = _pat(eng.cp.pre)
+    if which == 'disc':
+        eng.critic_forward(eng.z_real)
+        sg['d_real'] = _pat(eng.cp.pre)
+        E.call('uad_interpolate', eng.z_real, z_, eng.epsilon, eng.z_hat, eng.B, eng.zDim, 0)
+        eng.critic_forward(eng.z_hat)
+        sg['d_hat'] = _pat(eng.cp.pre)
+    return sg
+
+
+@pytest.mark.parametrize('which', ['ae', 'disc', 'gen'])
+def test_aae_train_ops_match_oracle(which, monkeypatch):
+    rate, lr = 0.2, 1e-3
+    AA, eng, P, x, z, epsilon, masks = _aae(monkeypatch, rate=rate)
+    tr = AA.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, dtype=torch.float64)
+    out, G = tr.step(which, x, z, epsilon, masks, signs=_aae_signs(eng, which, rate))
+    before = eng.fp.to_numpy()
+    res = {'ae': eng.step_ae, 'disc': eng.step_disc, 'gen': eng.step_gen}[which](lr, dropout_rate=rate, dropout=True, parity_noise=True)
+    for k, v in res.items():
+        if k in out and out[k].ndim == 0:
+            assert abs(v - float(out[k])) <= 1e-5 * max(abs(float(out[k])), 1e-3), (k, v, float(out[k]))
+    assert _rel(eng.br[0].mu.numpy(), out['z_'].numpy()) < TOL
+    if which == 'ae':
+        assert _rel(eng.br[0].xhat.numpy(), out['x_hat'].numpy()) < TOL
+    if which == 'disc':
+        assert _rel(eng.z_hat.numpy(), out['z_hat'].detach().numpy()) < TOL
+        assert _rel(eng.ddz.numpy(), out['ddz'].numpy()) < TOL
+    got = eng.fp.to_numpy(eng.fp.grads)
+    for k, v in G.items():
+        assert _rel(got[k], v.numpy()) < 2e-5, (k, _rel(got[k], v.numpy()))
+    _check_update(eng.fp.to_numpy(), before, tr.P, G, {'ae': ('Encoder', 'Bottleneck', 'Decoder'), 'disc': ('Discriminator',),
+                                                       'gen': ('Encoder',)}[which], lr)
+
+
+def test_aae_optimisers_and_validation(monkeypatch):
+    """A few rounds of (optim_ae, 2 x optim_dis, optim_gen) track the oracle trainer: optim_gen's Adam moments for the Encoder are
+    its own; the validation fetch changes nothing; perf-mode noise refreshes masks and epsilon."""
+    lr = 1e-3
+    AA, eng, P, x, z, epsilon, masks = _aae(monkeypatch, rate=0.0)
+    tr = AA.Trainer(P, lr=lr, dropout_rate=0.0, scale=10.0, dtype=torch.float64)
+    for it in range(2):
+        for which in ('ae', 'disc', 'disc', 'gen'):
+            tr.step(which, x, z, epsilon, None, signs=_aae_signs(eng, which, 0.0))
+            {'ae': eng.step_ae, 'disc': eng.step_disc, 'gen': eng.step_gen}[which](lr, dropout_rate=0.0, dropout=True, parity_noise=True)
+    assert eng.op_t == {'ae': 2, 'disc': 4, 'gen': 2}
+    after = eng.fp.to_numpy()
+    off = tot = 0
+    for k in after:
+        d = np.abs(after[k] - tr.P[k].numpy().reshape(after[k].shape))
+        assert float(d.max()) < 4.5 * lr, (k, float(d.max()))
+        off += int((d > 0.05 * lr).sum())
+        tot += d.size
+    assert off < 2e-3 * tot, (off, tot)
+    lo, hi = eng.rng['gen']
+    assert float(eng.m_gen.abs().max()) > 0 and not torch.equal(eng.m_gen, eng.fp.m[lo:hi])
+    got = eng.fp.to_numpy(torch.cat([torch.zeros(lo), eng.m_gen, torch.zeros(eng.fp.numel - hi)]))
+    for k, v in tr.slots['gen']['m'].items():
+        assert _rel(got[k], v.numpy()) < 5e-2, k
+    before = eng.fp.to_numpy()
+    res = eng.step_ae(lr, dropout_rate=0.2, dropout=False, train=False)
+    assert all(np.array_equal(before[k], v) for k, v in eng.fp.to_numpy().items()) and res['loss'] > 0
+    e0 = eng.epsilon.clone()
+    eng.step_disc(lr, dropout_rate=0.2, dropout=True)
+    assert not torch.equal(e0, eng.epsilon) and float(eng.epsilon.max()) <= 0.0 and eng.br[0].masks['mu'] is not None
+
+
+def test_aae_trainer_loop(monkeypatch, tmp_path):
+    """trainers/AAE.train on the synthetic dataset through the emulator: d_iters optim_ae + d_iters optim_dis + 1 optim_gen per
+    mini-batch (epoch <= 5), validation with all losses, checkpoint; model / trainer protocol of the reference."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import aae_engine
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.adversarial_autoencoder import adversarial_autoencoder
+    from unsupervised_anomaly_detection_brain_mri_b200.models.customlayers import Placeholder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.AAE import AAE
+    E.install(monkeypatch, eng_mod, aae_engine)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    config = AAE.Config()
+    assert (config.modelname, config.scale) == ('AAE', 10.0)
+    config.outputHeight = config.outputWidth = 32
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 16, 1
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate, config.d_iters = 0.1, 1e-4, 3
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.useCudaGraph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    outs = adversarial_autoencoder(Placeholder([None, 16]), Placeholder([None, 32, 32, 1]), 0.1, False, config)
+    assert set(outs) == {'z_', 'x_hat', 'd_', 'd', 'z_hat', 'd_hat'}
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (32, 32)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 20, 28
+    ds = SYNTHETIC(opts)
+    np.random.seed(0)
+    model = AAE(None, config, network=adversarial_autoencoder)
+    E.adopt(model.engine)
+    w0 = model.engine.fp.to_numpy()
+    model.train(ds)
+    w1 = model.engine.fp.to_numpy()
+    for scope in ('Encoder', 'Bottleneck', 'Decoder', 'Discriminator'):
+        assert any(not np.array_equal(w0[k], w1[k]) for k in w0 if k.startswith(scope + '/')), scope
+    assert all(np.isfinite(v).all() for v in w1.values())
+    t = model.engine.op_t
+    assert t['gen'] > 0 and t['ae'] == 3 * t['gen'] and t['disc'] == 3 * t['gen']
+    ok, step = model.load(model.checkpointDir)
+    assert ok and step == 1
