@@ -449,3 +449,80 @@ def test_aae_trainer_loop(monkeypatch, tmp_path):
     assert t['gen'] > 0 and t['ae'] == 3 * t['gen'] and t['disc'] == 3 * t['gen']
     ok, step = model.load(model.checkpointDir)
     assert ok and step == 1
+
+
+# ------------------------------------------------------------------------------------------------ 5. context encoder (CE)
+def test_context_encoder_step_scores_against_the_plain_batch(monkeypatch):
+    """trainers/CE.py:21,34: the AE graph runs on the masked batch, the L1 loss is taken against the plain batch - the engine's
+    reconstruction target decoupled from its input.  Loss and every gradient vs the oracle; set_target(None) restores target == input."""
+    from collections import OrderedDict
+
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod)
+    S, B, rate, lr = 32, 2, 0.2, 1e-3
+    P = O.perturb_params(O.init_params(O.AE, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=31)
+    x_ce = x.copy()
+    x_ce[:, 8:20, 10:22] = 0
+    eng = eng_mod.ConvAutoencoderEngine(O.AE, S, batch=B, device='cpu', math_mode=0)
+    E.adopt(eng)
+    eng.fp.load(P)
+    mz = (np.random.default_rng(8).uniform(size=(B, 128)) >= rate).astype(np.float32)
+    eng.set_inputs(x_ce)
+    eng.set_target(x)
+    eng.set_noise(None, {'mu': mz})
+    eng._keep = 1.0 / (1.0 - rate)
+    eng.forward(training=True, dropout_rate=rate)
+    l1_sign = np.sign(eng.br[0].xhat.numpy() - x)
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True)
+    Pt = OrderedDict((k, torch.from_numpy(v).double().requires_grad_(True)) for k, v in P.items())
+    out = O.forward(O.AE, Pt, x_ce, masks={'z': mz}, dropout_rate=rate, training=True, dtype=torch.float64)
+    L = O.losses(O.AE, out, x, dtype=torch.float64, l1_sign=l1_sign)
+    G = torch.autograd.grad(L['loss'], list(Pt.values()))
+    assert abs(eng.losses()['loss'] - float(L['loss'].detach())) < 1e-5 * float(L['loss'].detach())
+    assert _rel(eng.br[0].l1.numpy(), (out['x_hat'].detach() - torch.from_numpy(x).double()).abs().numpy()) < TOL
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    for k, g in zip(Pt, G):
+        assert _rel(grads[k], g.numpy()) < 2e-5, k
+    eng.set_target(None)
+    eng.forward(training=False)
+    assert _rel(eng.br[0].l1.numpy(), np.abs(eng.br[0].xhat.numpy() - x_ce)) < 1e-6
+
+
+def test_context_encoder_trainer_loop(monkeypatch, tmp_path):
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.autoencoder import autoencoder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.AEMODEL import AEMODEL
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.CE import CE
+    E.install(monkeypatch, eng_mod)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(AEMODEL, '_stage', lambda self, key, arr: torch.from_numpy(np.ascontiguousarray(arr, np.float32)))
+    config = CE.Config()
+    assert config.modelname == 'CE'
+    config.outputHeight = config.outputWidth = 64
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 16, 1
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate, config.optimizer = 0.1, 1e-4, 'ADAM'
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.use_cuda_graph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (64, 64)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 40, 48
+    ds = SYNTHETIC(opts)
+    model = CE(None, config, network=autoencoder)
+    E.adopt(model.engine)
+    seen = []
+    orig = model.engine.set_inputs
+    monkeypatch.setattr(model.engine, 'set_inputs', lambda x, x_ce=None: (seen.append(x.clone()), orig(x, x_ce))[1])
+    w0 = model.engine.fp.to_numpy()
+    import random
+    random.seed(0)
+    model.train(ds)
+    assert any(not np.array_equal(w0[k], v) for k, v in model.engine.fp.to_numpy().items())
+    assert model.engine.br[0].target is not None and model.engine.t == ds.num_batches(2, set='TRAIN')
+    # TRAIN batches went in masked (exact zeros inside the brain), the target stayed the plain batch
+    n_train = ds.num_batches(2, set='TRAIN')
+    assert any(float((s == 0).float().mean()) > float((model.engine.br[0].target == 0).float().mean()) for s in seen[:n_train])

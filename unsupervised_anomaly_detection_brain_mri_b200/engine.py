@@ -241,6 +241,7 @@ class ConvAutoencoderEngine:
         B, S = self.B, self.S
         br = _Branch()
         br.x = self._new(B, S, S, 1) if x is None else x
+        br.target = None                                 # reconstruction target when it is not the input (context encoder, set_target)
         br.enc_z, br.enc_a = [], []
         s = S
         for co in self.enc_ch:
@@ -351,6 +352,20 @@ class ConvAutoencoderEngine:
             if isinstance(v, np.ndarray):
                 v = torch.from_numpy(np.ascontiguousarray(v, np.float32))
             br.x.copy_(v.reshape(br.x.shape), non_blocking=True)
+
+    def set_target(self, x):
+        """Reconstruction target of branch 0 when it differs from the input: the context-encoder trainer feeds the masked
+        batch and scores against the plain one (reference trainers/CE.py:21,34,87-88).  None: back to target == input."""
+        br = self.br[0]
+        if x is None:
+            if br.target is not None:
+                br.target, self.graph = None, None       # a captured step holds the old target pointer
+            return
+        if br.target is None:
+            br.target, self.graph = self._new(*br.x.shape), None
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, np.float32))
+        br.target.copy_(x.reshape(br.target.shape), non_blocking=True)
 
     def set_noise(self, eps=None, masks=None, masks_ce=None):
         """Parity mode: caller-supplied eps / dropout masks ({0,1} arrays keyed 'mu','ls','dec'; AE uses 'mu' for z)."""
@@ -467,7 +482,8 @@ class ConvAutoencoderEngine:
                      ptr(br.dec_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.dec_a[i], s * 2, co
             self._op('dec_Conv2D_final', 'uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
-                 ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.x), ptr(br.xhat), ptr(br.l1) if need_l1 else None,
+                 ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.x if br.target is None else br.target), ptr(br.xhat),
+                 ptr(br.l1) if need_l1 else None,
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
@@ -510,7 +526,8 @@ class ConvAutoencoderEngine:
             lbn = f'Decoder/{_bn(self.n + 1 + last)}'
             # fused: final 1x1 + L1 backward AND the BN/LeakyReLU backward of the last transposed-conv block
             self._op('dec_Conv2D_final', 'uad_final1x1_l1_bwd_fused', ptr(br.dec_z[last] if kp else br.dec_a[last]), ptr(fp.p(lbn + '/gamma')),
-                     ptr(fp.p(lbn + '/beta')), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x), ptr(br.xhat), scale,
+                     ptr(fp.p(lbn + '/beta')), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(br.x if br.target is None else br.target),
+                     ptr(br.xhat), scale,
                      ptr(g), ptr(fp.g(lbn + '/gamma')), ptr(fp.g(lbn + '/beta')), ptr(fp.g(lpre + '/bias')),
                      ptr(fp.g('Decoder/dec_Conv2D_final/kernel')), ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B,
                      self.S * self.S, cin, act_blk, LRELU_ALPHA, BN_C, acc, ws, wsb, st)

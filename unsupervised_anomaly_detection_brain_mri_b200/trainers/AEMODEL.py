@@ -30,6 +30,7 @@ class AEMODEL(DLMODEL, ABC):
             self.zDim = 128
 
     TWO_INPUTS = False          # ceVAE feeds (x, x_ce)
+    MASKED_INPUT = False        # CE feeds the patch-masked batch and scores against the plain one (one-input graph)
     LOSS_KEYS = ('loss',)
 
     def __init__(self, sess, config=None, network=None):
@@ -227,7 +228,7 @@ class AEMODEL(DLMODEL, ABC):
         every = int(getattr(self.config, 'fetchMapsEvery', 0))      # the reference fetches the full maps EVERY step
         verbose = bool(getattr(self.config, 'verbose', True))
         def fetch():
-            if self.TWO_INPUTS:
+            if self.TWO_INPUTS or self.MASKED_INPUT:
                 b, _, masks = dataset.next_batch(self.config.batchsize, return_brainmask=True, set=phase.value)
                 return b, self._make_ce_batch(b, masks, phase)
             b, _, _ = dataset.next_batch(self.config.batchsize, set=phase.value)
