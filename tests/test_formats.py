@@ -256,3 +256,58 @@ def test_trainer_tf_checkpoint_export_import_on_cpu(tmp_path):
     ae.engine.specs = E.param_specs(E.CEVAE, 128)
     with pytest.raises((KeyError, ValueError)):
         ae.import_tf_checkpoint(prefix)
+
+
+def test_tf_checkpoint_import_pairs_layers_whose_automatic_suffixes_differ(tmp_path):
+    """A bundle whose un-named layers are numbered PER VARIABLE SCOPE (tf.layers makes the layer scope unique when the layer is
+    first called: the Decoder's first BatchNormalization is 'Decoder/batch_normalization') instead of over the whole graph (the
+    convention of engine.param_specs: 'Decoder/batch_normalization_3') imports into the same variables, slots and moving
+    statistics included; a bundle with a different number of layers is refused."""
+    import re
+    import types
+
+    import torch
+
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as E
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.DLMODEL import DLMODEL
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import tf_checkpoint as C
+
+    class T(DLMODEL):
+        def train(self, dataset):
+            pass
+
+    specs = E.param_specs(E.VAE, 64)
+    rng = np.random.default_rng(3)
+    weights = {k: rng.standard_normal(s).astype(np.float32) for k, s in specs.items()}
+    m = {k: rng.standard_normal(s).astype(np.float32) for k, s in specs.items()}
+    v = {k: rng.random(s).astype(np.float32) for k, s in specs.items()}
+    saved = C.saver_variables(weights, m, v, step=9)
+    n_enc = sum(1 for k in specs if re.match(r'Encoder/batch_normalization(_\d+)?/gamma', k))
+
+    def per_scope(name):                      # Decoder/batch_normalization_{n_enc + j} -> Decoder/batch_normalization[_j]
+        mm = re.match(r'^Decoder/batch_normalization_(\d+)(/.*)$', name)
+        if not mm:
+            return name
+        j = int(mm.group(1)) - n_enc
+        return f'Decoder/batch_normalization{"" if j == 0 else "_" + str(j)}{mm.group(2)}'
+
+    renamed = {per_scope(k): a for k, a in saved.items()}
+    assert 'Decoder/batch_normalization/gamma' in renamed and f'Decoder/batch_normalization_{2 * n_enc}/gamma' not in renamed
+    mapping = C.resolve_layer_names(list(specs), renamed.keys())
+    assert mapping[f'Decoder/batch_normalization_{n_enc}'] == 'Decoder/batch_normalization'
+    assert mapping['Bottleneck/dense_2'] == 'Bottleneck/dense_2' and mapping['Encoder/batch_normalization_1'] == 'Encoder/batch_normalization_1'
+    prefix = str(tmp_path / 'VAE.model-7')
+    C.write_bundle(prefix, renamed)
+    cfg = DLMODEL.Config()
+    cfg.modelname = 'VAE'
+    t = T(None, cfg)
+    fp = E.FlatParams(specs, 'cpu')
+    t.engine = types.SimpleNamespace(fp=fp, specs=specs, t=0, step_dev=torch.zeros(1, dtype=torch.int64), adam_step=lambda *a, **k: None)
+    assert t.import_tf_checkpoint(prefix) == 7
+    got, gm = t._weights(), fp.to_numpy(fp.m)
+    assert all(np.array_equal(got[k], weights[k]) for k in specs) and all(np.array_equal(gm[k], m[k]) for k in specs)
+    assert t.engine.t == 9
+    fewer = {k: a for k, a in renamed.items() if not k.startswith('Decoder/batch_normalization_2/')}
+    C.write_bundle(str(tmp_path / 'VAE.model-8'), fewer)
+    with pytest.raises(KeyError, match='batch_normalization'):
+        t.import_tf_checkpoint(str(tmp_path / 'VAE.model-8'))

@@ -129,6 +129,9 @@ class DLMODEL(object):
         variables = tfc.read_bundle(prefix)
         eng = self.engine
         wanted = list(eng.specs.keys())
+        if any(n not in variables for n in wanted):
+            # same layers, other automatic suffixes (per-scope vs whole-graph counters): pair them by creation order
+            variables = tfc.rename_layers(variables, tfc.resolve_layer_names(wanted, variables.keys()))
         missing = [n for n in wanted if n not in variables]
         if missing:
             raise KeyError(f'{prefix}: variables missing from the checkpoint: {missing[:4]}{"..." if len(missing) > 4 else ""}')

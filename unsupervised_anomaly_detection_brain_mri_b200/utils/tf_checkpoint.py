@@ -319,3 +319,67 @@ def split_saver_variables(variables, wanted):
         if n.endswith('/moving_variance') and np.any(a != 1):
             ok = False
     return weights, m, v, ok
+
+
+# ---------------------------------------------------------------------------------------------- auto-suffix tolerant names
+_SUFFIX = None
+
+
+def _split_layer(prefix):
+    """'Decoder/batch_normalization_7' -> ('Decoder', 'batch_normalization', 7); names without a numeric suffix -> index 0 ...
+    unless the whole last component is an explicit layer name such as 'enc_conv2D_3' (kept verbatim, index None)."""
+    import re
+    global _SUFFIX
+    if _SUFFIX is None:
+        _SUFFIX = re.compile(r'^(batch_normalization|layer_normalization|dense|conv2d|conv2d_transpose)(?:_(\d+))?$')
+    scope, _, layer = prefix.rpartition('/')
+    m = _SUFFIX.match(layer)
+    if not m:
+        return scope, layer, None
+    return scope, m.group(1), int(m.group(2) or 0)
+
+
+def resolve_layer_names(wanted, available):
+    """Map the layer prefixes this code uses onto the ones a checkpoint holds when only the AUTOMATIC numeric suffixes differ.
+
+    TensorFlow numbers un-named layers automatically ('dense', 'dense_1', ...; 'batch_normalization_4', ...), and whether the
+    counter runs per variable scope (tf.layers: the scope is made unique when the layer is first called) or over the whole
+    graph (Keras object names) depends on the layer class and TF version - SURVEY App. A.10 could not confirm the suffixes
+    without a TensorFlow runtime.  What IS determined by the model code is, per (scope, layer kind), the ORDER in which the
+    layers are created; so within each (scope, kind) the wanted layers, sorted by suffix, are paired with the available ones,
+    sorted by suffix.  wanted / available: iterables of variable names.  Returns {wanted_prefix: available_prefix}; raises
+    KeyError when a (scope, kind) group has a different number of layers on the two sides."""
+    def groups(names):
+        g = OrderedDict()
+        for n in names:
+            prefix = n.rpartition('/')[0]
+            scope, kind, idx = _split_layer(prefix)
+            if idx is None:
+                continue
+            g.setdefault((scope, kind), {})[idx] = prefix
+        return g
+    leaves = ('/kernel', '/bias', '/gamma', '/beta')
+    gw = groups(n for n in wanted if n.endswith(leaves))
+    ga = groups(n for n in available if n.endswith(leaves))
+    mapping = {}
+    for key, layers in gw.items():
+        have = ga.get(key, {})
+        if len(have) != len(layers):
+            raise KeyError(f'checkpoint holds {len(have)} {key[1]} layers in scope {key[0]!r}, the graph needs {len(layers)}')
+        for w_idx, a_idx in zip(sorted(layers), sorted(have)):
+            mapping[layers[w_idx]] = have[a_idx]
+    return mapping
+
+
+def rename_layers(variables, mapping):
+    """Checkpoint variables re-keyed to this code's layer prefixes (inverse of ``mapping``'s direction); slot variables and
+    moving statistics follow their layer."""
+    inverse = {a: w for w, a in mapping.items()}
+    out = OrderedDict()
+    for name, value in variables.items():
+        hit = None
+        for a in inverse:
+            if name.startswith(a + '/') and (hit is None or len(a) > len(hit)):
+                hit = a
+        out[name if hit is None else inverse[hit] + name[len(hit):]] = value
+    return out
