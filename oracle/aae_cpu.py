@@ -10,7 +10,13 @@ z_hat = z + epsilon * (z - z_) (:64-65, as written) - and trainers/AAE.py:41-69:
     optim_dis  minimises  mean(D(z_)) - mean(D(z)) + mean((|dD(z_hat)/dz_hat|_2 - 1)^2 * scale)     over Discriminator variables
     optim_gen  minimises  -mean(D(z_))                                          over ENCODER-scope variables only (:64; the
                Bottleneck layers between the encoder and z_ carry the gradient but are not updated)
-each its own tf.train.AdamOptimizer(lr, beta1=0.5, beta2=0.9)."""
+each its own tf.train.AdamOptimizer(lr, beta1=0.5, beta2=0.9).
+
+``constrained=True`` restates models/constrained_adversarial_autoencoder.py:10-79 + trainers/ConstrainedAAE.py:44-72: x_hat is
+re-encoded by the same layers (z_rec), loss = mean_b(L2 + rho * mean_j (z_rec - z_)^2), the Dropout calls on dec_dense(z_) and on
+z_rec carry no flag (identity), the critic is 100-50-1, and the 'Encoder' scope that optim_gen selects by substring also holds the
+1x1 bottleneck conv, the latent Dense and dec_dense (which receives no gradient from gen_loss) - variable names here stay the
+canonical Encoder/ | Bottleneck/ | Decoder/ ones of the dense AE."""
 from __future__ import annotations
 
 from collections import OrderedDict
@@ -23,14 +29,15 @@ from .tf_graph_cpu import AE, _glorot, _t, adam_tf, conv1x1, decoder, dropout, e
 from .tf_graph_cpu import _flatten_nhwc, _unflatten_nhwc
 
 CRITIC = (50, 50, 1)
+CRITIC_CONSTRAINED = (100, 50, 1)
 CRITIC_ALPHA = 0.2
 
 
-def init_params(S, C=1, zDim=128, res=8, seed=1):
+def init_params(S, C=1, zDim=128, res=8, seed=1, constrained=False):
     P = ae_init_params(AE, S, C, zDim, res, seed)                  # same variables / names as the dense AE
     rng = np.random.default_rng(seed + 1000)
     k = zDim
-    for j, width in enumerate(CRITIC):
+    for j, width in enumerate(CRITIC_CONSTRAINED if constrained else CRITIC):
         P[f'Discriminator/dense_{2 + j}/kernel'] = _glorot(rng, (k, width), k, width)
         P[f'Discriminator/dense_{2 + j}/bias'] = np.zeros(width, np.float32)
         k = width
@@ -66,9 +73,10 @@ def critic(P, z, signs=None):
     """[B, zDim] -> [B, 1].  signs (optional): per hidden layer the {0,1} pattern "pre-activation > 0" that pins the
     leaky-ReLU branch (see fanogan_cpu._act)."""
     h = z
-    for j in range(len(CRITIC)):
+    n_layers = sum(1 for k in P if k.startswith('Discriminator/') and k.endswith('/kernel'))
+    for j in range(n_layers):
         h = h @ P[f'Discriminator/dense_{2 + j}/kernel'] + P[f'Discriminator/dense_{2 + j}/bias']
-        if j < len(CRITIC) - 1:
+        if j < n_layers - 1:
             if signs is None:
                 h = F.leaky_relu(h, CRITIC_ALPHA)
             else:
@@ -77,7 +85,7 @@ def critic(P, z, signs=None):
 
 
 def graph(P, x, z, epsilon=None, masks=None, dropout_rate=0.0, training=True, scale=10.0, dtype=torch.float32,
-          want=('ae', 'gen', 'disc'), signs=None):
+          want=('ae', 'gen', 'disc'), signs=None, constrained=False, rho=1.0):
     """All losses of AAE.train (AAE.py:41-57) on one feed.  P: as_leaves(...).  masks: {'z','dec'}; epsilon [B,1]: the
     tf.random_uniform draw of adversarial_autoencoder.py:64; signs: {'d_fake','d_real','d_hat'} -> critic sign patterns."""
     x, z = _t(x, dtype), _t(z, dtype)
@@ -87,12 +95,16 @@ def graph(P, x, z, epsilon=None, masks=None, dropout_rate=0.0, training=True, sc
     z_, geom = encode(P, x, mk('z'), dropout_rate, training, dtype)
     o['z_'] = z_
     if 'ae' in want:
-        x_hat = decode(P, z_, geom, mk('dec'), dropout_rate, training, dtype)
+        x_hat = decode(P, z_, geom, None if constrained else mk('dec'), dropout_rate, training, dtype)
         o['x_hat'] = x_hat
         o['L1'] = (x_hat - x).abs()
         o['reconstructionLoss'] = o['L1'].sum(dim=(1, 2, 3)).mean()
         o['L2'] = ((x - x_hat) ** 2).mean(dim=(1, 2, 3))
         o['loss'] = o['L2'].mean()
+        if constrained:
+            o['z_rec'], _ = encode(P, x_hat, None, dropout_rate, training, dtype)
+            o['Rec_z'] = ((o['z_rec'] - z_) ** 2).mean(dim=1)
+            o['loss'] = (o['L2'] + rho * o['Rec_z']).mean()
     if 'gen' in want or 'disc' in want:
         o['disc_fake'] = critic(P, z_, sg('d_fake')).mean()
         o['gen_loss'] = -o['disc_fake']
@@ -114,18 +126,22 @@ class Trainer:
     OPS = {'ae': ('Encoder', 'Bottleneck', 'Decoder', 'Discriminator'), 'disc': ('Discriminator',), 'gen': ('Encoder',)}
     LOSS = {'ae': 'loss', 'disc': 'disc_loss', 'gen': 'gen_loss'}
 
-    def __init__(self, P, lr=1e-4, dropout_rate=0.0, scale=10.0, dtype=torch.float32):
-        self.dtype, self.lr, self.rate, self.scale = dtype, lr, dropout_rate, scale
+    def __init__(self, P, lr=1e-4, dropout_rate=0.0, scale=10.0, dtype=torch.float32, constrained=False, rho=1.0):
+        self.dtype, self.lr, self.rate, self.scale, self.constrained, self.rho = dtype, lr, dropout_rate, scale, constrained, rho
         self.P = OrderedDict((k, _t(v, dtype).clone()) for k, v in P.items())
         self.slots = {}
         for op, scopes in self.OPS.items():
             names = [k for k in self.P if k.split('/')[0] in scopes]
+            if constrained and op == 'gen':      # the reference's 'Encoder' scope: + conv2d, dense (z_layer), dense_1 (dec_dense)
+                names = [k for k in self.P if k.split('/')[0] == 'Encoder' or k.rsplit('/', 1)[0] in
+                         ('Bottleneck/conv2d', 'Bottleneck/dense', 'Bottleneck/dense_1')]
             self.slots[op] = dict(names=names, m=OrderedDict((k, torch.zeros_like(self.P[k])) for k in names),
                                   v=OrderedDict((k, torch.zeros_like(self.P[k])) for k in names), t=0)
 
     def step(self, which, x, z, epsilon=None, masks=None, training=True, signs=None):
         L = as_leaves(self.P, self.dtype)
-        o = graph(L, x, z, epsilon, masks, self.rate, training, self.scale, self.dtype, want=(which,), signs=signs)
+        o = graph(L, x, z, epsilon, masks, self.rate, training, self.scale, self.dtype, want=(which,), signs=signs,
+                  constrained=self.constrained, rho=self.rho)
         sl = self.slots[which]
         gs = torch.autograd.grad(o[self.LOSS[which]], [L[k] for k in sl['names']], allow_unused=True)
         used = [k for k, g in zip(sl['names'], gs) if g is not None]      # compute_gradients drops (None, var) pairs

@@ -315,13 +315,13 @@ def test_emulator_reproduces_the_gpu_verified_autoencoder_steps(arch, keep_preac
 
 
 # ------------------------------------------------------------------------------------------------ 4. adversarial autoencoder
-def _aae(monkeypatch, S=32, B=2, rate=0.2, zDim=32):
+def _aae(monkeypatch, S=32, B=2, rate=0.2, zDim=32, constrained=False, rho=1.0):
     from oracle import aae_cpu as AA
     from unsupervised_anomaly_detection_brain_mri_b200 import aae_engine
     from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
     E.install(monkeypatch, eng_mod, aae_engine)
-    P = AA.perturb(AA.init_params(S, zDim=zDim, seed=1))
-    eng = aae_engine.AdversarialAEEngine(S, zDim=zDim, batch=B, device='cpu', math_mode=0, scale=10.0)
+    P = AA.perturb(AA.init_params(S, zDim=zDim, seed=1, constrained=constrained))
+    eng = aae_engine.AdversarialAEEngine(S, zDim=zDim, batch=B, device='cpu', math_mode=0, scale=10.0, constrained=constrained, rho=rho)
     E.adopt(eng)
     assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
     eng.fp.load(P)
@@ -333,7 +333,7 @@ def _aae(monkeypatch, S=32, B=2, rate=0.2, zDim=32):
     eng.set_inputs(x)
     eng.set_latent(z)
     eng.set_epsilon(epsilon)
-    eng.set_noise(None, {'mu': masks['z'], 'dec': masks['dec']})
+    eng.set_noise(None, {'mu': masks['z']} if constrained else {'mu': masks['z'], 'dec': masks['dec']})
     return AA, eng, P, x, z, epsilon, masks
 
 
@@ -353,11 +353,14 @@ def _aae_signs(eng, which, rate):
     return sg
 
 
+@pytest.mark.parametrize('constrained', [False, True])
 @pytest.mark.parametrize('which', ['ae', 'disc', 'gen'])
-def test_aae_train_ops_match_oracle(which, monkeypatch):
-    rate, lr = 0.2, 1e-3
-    AA, eng, P, x, z, epsilon, masks = _aae(monkeypatch, rate=rate)
-    tr = AA.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, dtype=torch.float64)
+def test_aae_train_ops_match_oracle(which, constrained, monkeypatch):
+    """constrained=True: models/constrained_adversarial_autoencoder.py + trainers/ConstrainedAAE.py (two-pass graph, rho * Rec_z,
+    100-50-1 critic, optim_gen over Encoder/* + the 1x1 bottleneck conv + the latent Dense)."""
+    rate, lr, rho = 0.2, 1e-3, 0.7
+    AA, eng, P, x, z, epsilon, masks = _aae(monkeypatch, rate=rate, constrained=constrained, rho=rho)
+    tr = AA.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, dtype=torch.float64, constrained=constrained, rho=rho)
     out, G = tr.step(which, x, z, epsilon, masks, signs=_aae_signs(eng, which, rate))
     before = eng.fp.to_numpy()
     res = {'ae': eng.step_ae, 'disc': eng.step_disc, 'gen': eng.step_gen}[which](lr, dropout_rate=rate, dropout=True, parity_noise=True)
@@ -367,14 +370,28 @@ def test_aae_train_ops_match_oracle(which, monkeypatch):
     assert _rel(eng.br[0].mu.numpy(), out['z_'].numpy()) < TOL
     if which == 'ae':
         assert _rel(eng.br[0].xhat.numpy(), out['x_hat'].numpy()) < TOL
+        if constrained:
+            assert _rel(eng.br[1].mu.numpy(), out['z_rec'].numpy()) < TOL and 'Rec_z' in res
     if which == 'disc':
         assert _rel(eng.z_hat.numpy(), out['z_hat'].detach().numpy()) < TOL
         assert _rel(eng.ddz.numpy(), out['ddz'].numpy()) < TOL
     got = eng.fp.to_numpy(eng.fp.grads)
     for k, v in G.items():
         assert _rel(got[k], v.numpy()) < 2e-5, (k, _rel(got[k], v.numpy()))
-    _check_update(eng.fp.to_numpy(), before, tr.P, G, {'ae': ('Encoder', 'Bottleneck', 'Decoder'), 'disc': ('Discriminator',),
-                                                       'gen': ('Encoder',)}[which], lr)
+    if constrained and which == 'gen':            # updated: Encoder/* + Bottleneck/conv2d + Bottleneck/dense, nothing else
+        assert set(G) == {k for k in P if k.startswith('Encoder/') or k.rsplit('/', 1)[0] in ('Bottleneck/conv2d', 'Bottleneck/dense')}
+        after = eng.fp.to_numpy()
+        gmax = max(float(v.abs().max()) for v in G.values())
+        for k in after:
+            if k not in G:
+                assert np.array_equal(after[k], before[k]), k
+            else:
+                sel = np.abs(G[k].numpy()) > 1e-3 * gmax
+                assert (np.abs(after[k] - tr.P[k].numpy().reshape(after[k].shape))[sel] <= 0.02 * lr).all(), k
+                assert not np.array_equal(after[k], before[k]), k
+    else:
+        _check_update(eng.fp.to_numpy(), before, tr.P, G, {'ae': ('Encoder', 'Bottleneck', 'Decoder'), 'disc': ('Discriminator',),
+                                                           'gen': ('Encoder',)}[which], lr)
 
 
 def test_aae_optimisers_and_validation(monkeypatch):
@@ -526,3 +543,44 @@ def test_context_encoder_trainer_loop(monkeypatch, tmp_path):
     # TRAIN batches went in masked (exact zeros inside the brain), the target stayed the plain batch
     n_train = ds.num_batches(2, set='TRAIN')
     assert any(float((s == 0).float().mean()) > float((model.engine.br[0].target == 0).float().mean()) for s in seen[:n_train])
+
+
+def test_constrained_aae_trainer_loop(monkeypatch, tmp_path):
+    from unsupervised_anomaly_detection_brain_mri_b200 import aae_engine
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.constrained_adversarial_autoencoder import constrained_adversarial_autoencoder
+    from unsupervised_anomaly_detection_brain_mri_b200.models.customlayers import Placeholder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.ConstrainedAAE import ConstrainedAAE
+    E.install(monkeypatch, eng_mod, aae_engine)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    config = ConstrainedAAE.Config()
+    assert (config.modelname, config.rho) == ('ConstrainedAAE', 1)
+    config.outputHeight = config.outputWidth = 32
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 16, 1
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate, config.d_iters, config.rho, config.scale = 0.1, 1e-4, 2, 0.5, 1
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.useCudaGraph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    outs = constrained_adversarial_autoencoder(Placeholder([None, 16]), Placeholder([None, 32, 32, 1]), 0.1, False, config)
+    assert set(outs) == {'z_', 'x_hat', 'z_rec', 'd_', 'd', 'z_hat', 'd_hat'}
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (32, 32)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 20, 28
+    ds = SYNTHETIC(opts)
+    np.random.seed(0)
+    model = ConstrainedAAE(None, config, network=constrained_adversarial_autoencoder)
+    eng = model.engine
+    assert eng.constrained and eng.rho == 0.5 and eng.scale == 1.0 and eng.widths == (100, 50, 1)
+    assert eng.specs['Discriminator/dense_2/kernel'] == (16, 100)
+    E.adopt(eng)
+    w0 = eng.fp.to_numpy()
+    model.train(ds)
+    w1 = eng.fp.to_numpy()
+    for scope in ('Encoder', 'Bottleneck', 'Decoder', 'Discriminator'):
+        assert any(not np.array_equal(w0[k], w1[k]) for k in w0 if k.startswith(scope + '/')), scope
+    assert all(np.isfinite(v).all() for v in w1.values())
+    assert eng.op_t['gen'] > 0 and eng.op_t['ae'] == 2 * eng.op_t['gen'] == eng.op_t['disc']
+    assert eng.br[1].masks['mu'] is None and eng.br[0].masks['dec'] is None          # the two Dropout calls without the flag

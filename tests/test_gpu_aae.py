@@ -21,10 +21,10 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
 
 
-def _setup(S, B, rate, mode, zDim=128):
+def _setup(S, B, rate, mode, zDim=128, constrained=False, rho=0.7):
     from unsupervised_anomaly_detection_brain_mri_b200.aae_engine import AdversarialAEEngine
-    P = AA.perturb(AA.init_params(S, zDim=zDim, seed=1))
-    eng = AdversarialAEEngine(S, zDim=zDim, batch=B, math_mode=mode, scale=10.0)
+    P = AA.perturb(AA.init_params(S, zDim=zDim, seed=1, constrained=constrained))
+    eng = AdversarialAEEngine(S, zDim=zDim, batch=B, math_mode=mode, scale=10.0, constrained=constrained, rho=rho)
     eng.fp.load(P)
     rng = np.random.default_rng(5)
     x = O.synthetic_slices(B, S, seed=31)
@@ -34,7 +34,7 @@ def _setup(S, B, rate, mode, zDim=128):
     eng.set_inputs(x)
     eng.set_latent(z)
     eng.set_epsilon(epsilon)
-    eng.set_noise(None, {'mu': masks['z'], 'dec': masks['dec']})
+    eng.set_noise(None, {'mu': masks['z']} if constrained else {'mu': masks['z'], 'dec': masks['dec']})
     return eng, P, x, z, epsilon, masks
 
 
@@ -61,13 +61,14 @@ def _signs(eng, which, rate):
     return sg
 
 
+@pytest.mark.parametrize('constrained', [False, True])
 @pytest.mark.parametrize('mode', [0, 1])
 @pytest.mark.parametrize('S,B', [(32, 4), (64, 2)])
 @pytest.mark.parametrize('which', ['ae', 'disc', 'gen'])
-def test_aae_train_ops_match_oracle(which, S, B, mode):
+def test_aae_train_ops_match_oracle(which, S, B, mode, constrained):
     rate, lr = 0.2, 1e-3
-    eng, P, x, z, epsilon, masks = _setup(S, B, rate, mode)
-    tr = AA.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, dtype=torch.float64)
+    eng, P, x, z, epsilon, masks = _setup(S, B, rate, mode, constrained=constrained)
+    tr = AA.Trainer(P, lr=lr, dropout_rate=rate, scale=10.0, dtype=torch.float64, constrained=constrained, rho=0.7)
     out, G = tr.step(which, x, z, epsilon, masks, signs=_signs(eng, which, rate))
     res = {'ae': eng.step_ae, 'disc': eng.step_disc, 'gen': eng.step_gen}[which](lr, dropout_rate=rate, dropout=True, parity_noise=True)
     torch.cuda.synchronize()

@@ -10,6 +10,12 @@ taken without a tape: with u = d gp / d(ddz) fixed, grad_theta gp = grad_theta <
 MLP along u (Dense without bias, then * leaky'(pre-activation)) and its reverse pass.  The leaky ReLU is piecewise linear, so
 the primal activations enter only through their sign patterns.
 
+``constrained=True`` is the constrained adversarial AE (reference models/constrained_adversarial_autoencoder.py,
+trainers/ConstrainedAAE.py:44-72): the constrained AE's two-pass graph and loss mean_b(L2 + rho * Rec_z) for optim_ae (the Dropout
+calls on dec_dense(z_) and on z_rec carry no flag there: identity), a 100-50-1 critic, and an optim_gen whose 'Encoder' scope also
+holds the 1x1 bottleneck conv and the latent Dense (the reference builds them inside that scope, :13-29) - so step_gen updates
+Encoder/* + Bottleneck/conv2d + Bottleneck/dense (this repo's canonical names; two Adam ranges, one step counter).
+
 STATUS: written after round 1's GPU budget was spent; the call sequences are verified on CPU against oracle/aae_cpu.py through
 the ABI emulator (tests/test_engine_emulated.py); tests/test_gpu_aae.py is opt-in (UAD_UNVERIFIED=1) until its first hardware run."""
 from __future__ import annotations
@@ -19,7 +25,7 @@ import torch
 
 from . import abi
 from .abi import ACT_LEAKY, ACT_NONE, call, ptr
-from .engine import AAE, AAE_CRITIC, BN_C, KSIZE, LRELU_ALPHA, ConvAutoencoderEngine, FlatParams, _bn, glorot_init, graph_capture, param_specs
+from .engine import AAE, BN_C, CAAE, CRITIC_WIDTHS, KSIZE, LRELU_ALPHA, ConvAutoencoderEngine, FlatParams, _bn, glorot_init, graph_capture, param_specs
 
 CRITIC_ALPHA = 0.2          # tf.nn.leaky_relu default (adversarial_autoencoder.py:4,45-46)
 
@@ -28,9 +34,9 @@ class _CriticPass:
     """Pre-activations / activations of one pass through the latent critic."""
 
     def __init__(self, eng):
-        self.pre = [eng._new(eng.B, w) for w in AAE_CRITIC[:-1]]
-        self.act = [eng._new(eng.B, w) for w in AAE_CRITIC[:-1]]
-        self.d = eng._new(eng.B, AAE_CRITIC[-1])
+        self.pre = [eng._new(eng.B, w) for w in eng.widths[:-1]]
+        self.act = [eng._new(eng.B, w) for w in eng.widths[:-1]]
+        self.d = eng._new(eng.B, eng.widths[-1])
 
 
 class AdversarialAEEngine(ConvAutoencoderEngine):
@@ -38,8 +44,12 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
     OPS = ('ae', 'disc', 'gen')
 
     def __init__(self, S, C=1, zDim=128, res=8, batch=8, device='cuda:0', math_mode=abi.MATH_TC_3XTF32, seed=1, scale=10.0,
-                 share_params=None):
-        super().__init__(AAE, S, C, zDim, res, batch, device, math_mode, seed, share_params=share_params)
+                 share_params=None, constrained=False, rho=1.0):
+        super().__init__(CAAE if constrained else AAE, S, C, zDim, res, batch, device, math_mode, seed, share_params=share_params)
+        self.constrained = bool(constrained)
+        if constrained:
+            self.rho = float(rho)
+        self.widths = CRITIC_WIDTHS[self.arch]
         self.scale = float(scale)
         B = self.B
         self.scalars = torch.zeros(16, dtype=torch.float32, device=self.device)
@@ -47,9 +57,9 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
         self.epsilon = self._new(B)                      # tf.random_uniform of adversarial_autoencoder.py:64 (stored NEGATED, see step_disc)
         self.z_hat = self._new(B, zDim)
         self.cp = _CriticPass(self)
-        self.tan = [self._new(B, w) for w in AAE_CRITIC[:-1]]      # tangent activations of the gradient-penalty pass
-        self.tpre = [self._new(B, w) for w in AAE_CRITIC[:-1]]
-        self.gh = [self._new(B, w) for w in AAE_CRITIC[:-1]]       # gradient scratch per hidden layer
+        self.tan = [self._new(B, w) for w in self.widths[:-1]]     # tangent activations of the gradient-penalty pass
+        self.tpre = [self._new(B, w) for w in self.widths[:-1]]
+        self.gh = [self._new(B, w) for w in self.widths[:-1]]      # gradient scratch per hidden layer
         self.dd = self._new(B, 1)
         self.ddz = self._new(B, zDim)
         self.u = self._new(B, zDim)
@@ -57,6 +67,10 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
         fp = self.fp
         self.rng = {op: fp.subset_ranges(p) for op, p in (('disc', 'Discriminator/'), ('gen', 'Encoder/'))}
         self.rng['ae'] = (0, self.rng['disc'][0])        # Encoder | Bottleneck | Decoder precede the critic in the layout
+        self.rngs = {op: [r] for op, r in self.rng.items()}                # the slices an op's Adam touches (ascending)
+        if constrained:                                  # optim_gen: Encoder/* + the 1x1 bottleneck conv + the latent Dense
+            self.rngs['gen'] += [fp.subset_ranges('Bottleneck/conv2d/'), fp.subset_ranges('Bottleneck/dense/')]
+            self.rng['gen'] = (self.rngs['gen'][0][0], self.rngs['gen'][-1][1])
         lo, hi = self.rng['gen']
         self.m_gen = torch.zeros(hi - lo, dtype=torch.float32, device=self.device)    # optim_gen's own Adam slots
         self.v_gen = torch.zeros(hi - lo, dtype=torch.float32, device=self.device)
@@ -71,13 +85,13 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
 
     def _critic_dims(self):
         k, dims = self.zDim, []
-        for w in AAE_CRITIC:
+        for w in self.widths:
             dims.append((k, w))
             k = w
         return dims
 
     def _critic_names(self):
-        return [f'Discriminator/dense_{2 + j}' for j in range(len(AAE_CRITIC))]
+        return [f'Discriminator/dense_{2 + j}' for j in range(len(self.widths))]
 
     def set_latent(self, z):
         if isinstance(z, np.ndarray):
@@ -180,14 +194,15 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
 
     def _adam(self, op, lr, allreduce, world):
         fp, st = self.fp, self._st()
-        lo, hi = self.rng[op]
-        if allreduce is not None and world > 1:
-            allreduce(fp.grads[lo:hi])
+        base = self.rng[op][0]
         self.op_t[op] += 1
         call('uad_counter_add', self.op_steps[op].data_ptr(), 1, st)
-        m, v = (self.m_gen, self.v_gen) if op == 'gen' else (fp.m[lo:], fp.v[lo:])
-        call('uad_adam_tf_step', ptr(fp.params[lo:]), ptr(fp.grads[lo:]), ptr(m), ptr(v), hi - lo, float(lr), 0.5, 0.9, 1e-8, 1.0 / world,
-             self.op_steps[op].data_ptr(), st)
+        for lo, hi in self.rngs[op]:
+            if allreduce is not None and world > 1:
+                allreduce(fp.grads[lo:hi])
+            m, v = (self.m_gen[lo - base:], self.v_gen[lo - base:]) if op == 'gen' else (fp.m[lo:], fp.v[lo:])
+            call('uad_adam_tf_step', ptr(fp.params[lo:]), ptr(fp.grads[lo:]), ptr(m), ptr(v), hi - lo, float(lr), 0.5, 0.9, 1e-8, 1.0 / world,
+                 self.op_steps[op].data_ptr(), st)
 
     def _launch(self, op, key, body, use_graph, in_graph_adam):
         """Eager, or (use_graph) eager once, then captured into a CUDA graph and replayed - as fanogan_engine._run."""
@@ -232,7 +247,10 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
             self._noise(dropout, rate, parity_noise)
             self.forward(training=train, dropout_rate=rate)
             if train:
-                self.backward_from_gxhat()
+                if self.constrained:
+                    self.backward_constrained()
+                else:
+                    self.backward_from_gxhat()
                 if apply and allreduce is None:
                     self._adam('ae', lr, None, world)
 
@@ -242,6 +260,9 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
             self._adam('ae', lr, allreduce, world)
         s = self._sc(['reconstructionLoss', 'L2'])
         s['loss'] = s['L2']
+        if self.constrained:
+            s['Rec_z'] = float(self.scalars[5])
+            s['loss'] = s['L2'] + self.rho * s['Rec_z']
         return s
 
     def step_disc(self, lr, dropout_rate=0.0, dropout=True, parity_noise=False, allreduce=None, world=1, apply=True, use_graph=False):
@@ -293,10 +314,11 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
             call('uad_sum_scaled', ptr(d), B, 1.0 / B, self.scalars[8:].data_ptr(), ws, wsb, st)
             self.critic_backward(z_, -1.0 / B, params=False, dz_out=self.dz_lat)
             g, gn = self.gbuf
+            G = (lambda n: ptr(fp.g(n))) if self.constrained else (lambda n: None)      # constrained: these two layers are updated too
             call('uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(self.dz_lat), ptr(br.masks['mu']), self._keep,
-                 ptr(sm['dflat']), None, None, B, self.flat, self.zDim, 0, ws, wsb, st)
-            call('uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0, ptr(g), None, None,
-                 B * self.res * self.res, self.enc_ch[-1], self.cb, 0, ws, wsb, st)
+                 ptr(sm['dflat']), G('Bottleneck/dense/kernel'), G('Bottleneck/dense/bias'), B, self.flat, self.zDim, 0, ws, wsb, st)
+            call('uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0, ptr(g),
+                 G('Bottleneck/conv2d/kernel'), G('Bottleneck/conv2d/bias'), B * self.res * self.res, self.enc_ch[-1], self.cb, 0, ws, wsb, st)
             self._encoder_backward(br, g, gn, 0, None)
             if apply and allreduce is None:
                 self._adam('gen', lr, None, world)
@@ -309,9 +331,9 @@ class AdversarialAEEngine(ConvAutoencoderEngine):
         return {'gen_loss': -s['disc_fake'], 'disc_fake': s['disc_fake']}
 
 
-def make_params(S, C=1, zDim=128, res=8, device='cuda:0', seed=1):
-    """A FlatParams for the AAE variable set (what share_params expects), Glorot-initialised."""
-    specs = param_specs(AAE, S, C, zDim, res)
+def make_params(S, C=1, zDim=128, res=8, device='cuda:0', seed=1, constrained=False):
+    """A FlatParams for the (constrained) AAE variable set (what share_params expects), Glorot-initialised."""
+    specs = param_specs(CAAE if constrained else AAE, S, C, zDim, res)
     fp = FlatParams(specs, torch.device(device))
     fp.load(glorot_init(specs, seed))
     return fp

@@ -34,8 +34,14 @@ CEVAE = 'context_encoder_variational_autoencoder'
 AES = 'autoencoder_spatial'      # encoder -> Dropout -> decoder, no dense bottleneck (reference models/autoencoder_spatial.py)
 CAE = 'constrained_autoencoder'  # dense AE whose reconstruction is re-encoded: z_rec = Enc(x_hat) (models/constrained_autoencoder.py)
 AAE = 'adversarial_autoencoder'  # dense AE (both bottleneck Dropouts honour the flag, MSE loss) + latent MLP critic (aae_engine.py)
-ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE)
-AAE_CRITIC = (50, 50, 1)         # Dense widths of the latent critic (models/adversarial_autoencoder.py:44-48)
+# constrained AE + the latent critic.  The reference scopes its layers differently there (Encoder/{conv2d, dense, dense_1},
+# Decoder/conv2d_1: models/constrained_adversarial_autoencoder.py:13-36); the engine keeps ONE canonical naming for the shared
+# bottleneck layers (Bottleneck/...), what differs in behaviour - which variables optim_gen updates - is handled by aae_engine.
+CAAE = 'constrained_adversarial_autoencoder'
+ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE, CAAE)
+# Dense widths of the latent critic (models/adversarial_autoencoder.py:44-48, constrained_adversarial_autoencoder.py:52-56)
+CRITIC_WIDTHS = {AAE: (50, 50, 1), CAAE: (100, 50, 1)}
+AAE_CRITIC = CRITIC_WIDTHS[AAE]
 
 
 import contextlib
@@ -89,7 +95,7 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
         sp['Bottleneck/conv2d_1/bias'] = (cin,)
         flat = res * res * cb
-        heads = 1 if arch in (AE, CAE, AAE) else 2
+        heads = 1 if arch in (AE, CAE, AAE, CAAE) else 2
         for h in range(heads):
             nm = 'dense' if h == 0 else f'dense_{h}'
             sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
@@ -108,9 +114,9 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         cin = co
     sp['Decoder/dec_Conv2D_final/kernel'] = (1, 1, cin, C)
     sp['Decoder/dec_Conv2D_final/bias'] = (C,)
-    if arch == AAE:                  # the tf.layers Dense counter runs on: Bottleneck/{dense, dense_1}, Discriminator/dense_{2,3,4}
+    if arch in CRITIC_WIDTHS:        # the tf.layers Dense counter runs on: Bottleneck/{dense, dense_1}, Discriminator/dense_{2,3,4}
         k = zDim
-        for j, width in enumerate(AAE_CRITIC):
+        for j, width in enumerate(CRITIC_WIDTHS[arch]):
             sp[f'Discriminator/dense_{2 + j}/kernel'] = (k, width)
             sp[f'Discriminator/dense_{2 + j}/bias'] = (width,)
             k = width
@@ -282,7 +288,7 @@ class ConvAutoencoderEngine:
         self.br = [self._alloc_branch()]
         if self.arch == CEVAE:
             self.br.append(self._alloc_branch())
-        if self.arch == CAE:
+        if self.arch in (CAE, CAAE):
             self.br.append(self._alloc_branch(encoder_only=True, x=self.br[0].xhat))
             self.gxhat = self._new(B, S, S, 1)           # d loss / d x_hat: MSE term + the re-encoding pass
             self.dzrec = self._new(B, self.zDim)
@@ -392,9 +398,11 @@ class ConvAutoencoderEngine:
                 br.masks['sp'] = None
             call('uad_counter_add', ctr, 1 << 20, st)
             return
-        if self.arch in (CAE, AAE):                      # Dropout calls: z, dec_dense(z) [, z_rec] (each its own draw)
+        if self.arch in (CAE, AAE, CAAE):                # Dropout calls: z, dec_dense(z) [, z_rec] (each its own draw)
             on = bool(dropout) and rate > 0
-            sites = ((self.br[0], 'mu'), (self.br[0], 'dec')) + (((self.br[1], 'mu'),) if self.arch == CAE else ())
+            # constrained_adversarial_autoencoder.py:35,48 call Dropout on dec_dense(z_) and on z_rec WITHOUT the flag: identity
+            sites = ((self.br[0], 'mu'),) + (((self.br[0], 'dec'),) if self.arch != CAAE else ()) + \
+                    (((self.br[1], 'mu'),) if self.arch == CAE else ())
             for sid, (br, k) in enumerate(sites):
                 if on:
                     call('uad_dropout_mask', ptr(br.mask_bufs[k]), br.mask_bufs[k].numel(), float(rate), self.rng_seed,
@@ -445,12 +453,12 @@ class ConvAutoencoderEngine:
                    1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
             if self.arch == AES:
                 pass
-            elif self.arch in (AE, CAE, AAE):
+            elif self.arch in (AE, CAE, AAE, CAAE):
                 # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity.
                 # constrained_autoencoder.py:29-30, adversarial_autoencoder.py:30-31: BOTH dropout calls honour the flag.
                 self._op('bneck02', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
                      ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
-                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', (m['dec'] if self.arch in (CAE, AAE) else None)
+                zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', (m['dec'] if self.arch in (CAE, AAE, CAAE) else None)
                 if is_ce:                                # constrained AE, re-encoding pass: z_rec is all that is needed
                     continue
             else:
@@ -487,8 +495,8 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE) else None, ptr(self.scalars), B, st)
-        if self.arch == CAE and (branches is None or 1 in branches):
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE, CAAE) else None, ptr(self.scalars), B, st)
+        if self.arch in (CAE, CAAE) and (branches is None or 1 in branches):
             # trainers/ConstrainedAE.py:37-43: L2 = mean_hwc (x - x_hat)^2, Rec_z = mean_j (z - z_rec)^2 (per sample);
             # loss = mean_b(L2 + rho * Rec_z).  The same calls leave d loss/d x_hat and d loss/d z_rec (d/dz = -d/dz_rec).
             nx, nz = b0.x.numel(), B * self.zDim
@@ -868,7 +876,7 @@ class ConvAutoencoderEngine:
         if not parity_noise:
             self.draw_noise(dropout, rate)
         self.forward(training=True, dropout_rate=rate)
-        if self.arch == CAE:
+        if self.arch in (CAE, CAAE):
             self.backward_constrained()
             return
         if self.arch == AAE:
@@ -928,7 +936,7 @@ class ConvAutoencoderEngine:
         s = self.scalars.detach().cpu().numpy()
         if self.arch in (AE, AES):
             return {'reconstructionLoss': float(s[0]), 'loss': float(s[0])}
-        if self.arch == CAE:
+        if self.arch in (CAE, CAAE):
             return {'reconstructionLoss': float(s[0]), 'L2': float(s[4]), 'Rec_z': float(s[5]),
                     'loss': float(s[4]) + self.rho * float(s[5])}
         if self.arch == AAE:

@@ -111,7 +111,7 @@ class AAE(fAnoGAN):
                 xb = np.concatenate([xb, np.zeros((chunk - n,) + xb.shape[1:], np.float32)], 0)
             eng.set_inputs(xb)
             eng.draw_noise(rate > 0, rate)                 # MC-dropout: both bottleneck Dropout sites are live
-            eng.forward(training=False, dropout_rate=rate, need_l1=False)
+            eng.forward(training=False, dropout_rate=rate, branches=[0], need_l1=False)
             rec[i:i + n] = eng.br[0].xhat.cpu().numpy()[:n]
         results = {'reconstruction': rec}
         results['l1err'] = np.sum(np.abs(x - rec))

@@ -175,7 +175,7 @@ class fAnoGAN(DLMODEL):
     def _engine_for(self, n):
         if n not in self._eval:
             g = self.graph
-            e = self.ENGINE(g.S, g.C, g.zDim, g.res, batch=n, device=self.device, math_mode=self.math_mode)
+            e = self.ENGINE(g.S, g.C, g.zDim, g.res, batch=n, device=self.device, math_mode=self.math_mode, **self._engine_kwargs())
             e.fp = self.engine.fp            # share the weights
             self._eval[n] = e
         return self._eval[n]
