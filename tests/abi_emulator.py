@@ -186,6 +186,26 @@ def uad_final1x1_l1_bwd_fused(z, gamma, beta, w, x, xhat, scale, dz, dgamma, dbe
     _w(dz, dzt)
 
 
+def uad_mask_bn_act_fwd(x, mask, keep, gamma, beta, bn_c, act, alpha, z_out, a_out, rows, C, st):
+    z = _v(x, rows, C)
+    if mask is not None:
+        z = z * _v(mask, rows, C) * keep
+    _w(z_out, z)
+    _w(a_out, _act(_affine(z, gamma, beta, C, bn_c), act, alpha))
+
+
+def uad_mask_scale(g, mask, keep, out, n, st):
+    _w(out, _v(g, n) * _v(mask, n) * keep)
+
+
+def uad_l1_direct_term(x, xhat, scale, gx, n, st):
+    _w(gx, _v(gx, n) - torch.sign(_v(xhat, n) - _v(x, n)) * scale)
+
+
+def uad_mul_abs(l1, gx, out, n, st):
+    _w(out, _v(l1, n) * _v(gx, n).abs())
+
+
 def uad_loss_scalars(rec, kl, out3, B, st):
     r = _v(rec, B)
     k = _v(kl, B) if kl is not None else torch.zeros(B, dtype=D)

@@ -584,3 +584,61 @@ def test_constrained_aae_trainer_loop(monkeypatch, tmp_path):
     assert all(np.isfinite(v).all() for v in w1.values())
     assert eng.op_t['gen'] > 0 and eng.op_t['ae'] == 2 * eng.op_t['gen'] == eng.op_t['disc']
     assert eng.br[1].masks['mu'] is None and eng.br[0].masks['dec'] is None          # the two Dropout calls without the flag
+
+
+@pytest.mark.parametrize('arch', [O.AE, O.AES, O.CEVAE])
+def test_emulator_reproduces_the_other_gpu_verified_steps(arch, monkeypatch):
+    """Calibration / regression guard for the remaining AE-family graphs (dense AE, spatial AE, ceVAE with the input-gradient
+    anomaly map): engine.py was edited after its last GPU run (new archs, backward split, decoupled target) - the call sequences
+    the GPU suite verified must still reproduce the oracle."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod)
+    S, B, rate, lr = 32, 2, 0.2, 1e-3
+    P = O.perturb_params(O.init_params(arch, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=1234)
+    x_ce = x.copy()
+    x_ce[:, 8:20, 10:22] = 0
+    eng = eng_mod.ConvAutoencoderEngine(arch, S, batch=B, device='cpu', math_mode=0)
+    E.adopt(eng)
+    assert list(eng.specs.keys()) == list(P.keys())
+    eng.fp.load(P)
+    rng = np.random.default_rng(3)
+    eps = rng.standard_normal((B, 128)).astype(np.float32)
+    mk = lambda *n: (rng.uniform(size=(B,) + n) >= rate).astype(np.float32)   # noqa: E731
+    emc = None
+    if arch == O.AE:
+        om = {'z': mk(128)}
+        em = {'mu': om['z']}
+    elif arch == O.AES:
+        om = {'z': mk(8, 8, eng.enc_ch[-1])}
+        em = {'sp': om['z']}
+    else:
+        om = {'mu': mk(128), 'log_sigma': mk(128), 'dec': mk(eng.flat), 'mu_ce': mk(128), 'dec_ce': mk(eng.flat)}
+        em, emc = {'mu': om['mu'], 'ls': om['log_sigma'], 'dec': om['dec']}, {'mu': om['mu_ce'], 'dec': om['dec_ce']}
+    ce = arch == O.CEVAE
+    eng.set_inputs(x, x_ce if ce else None)
+    eng.set_noise(eps, em, emc)
+    eng._keep = 1.0 / (1.0 - rate)
+    eng.forward(training=True, dropout_rate=rate)
+    sgn = np.sign(eng.br[0].xhat.numpy().astype(np.float64) - x)
+    sgn_ce = np.sign(eng.br[1].xhat.numpy().astype(np.float64) - x_ce) if ce else None
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True, want_anomaly=ce)
+    out, L, G = O.loss_and_grads(arch, P, x, x_ce=x_ce, eps=eps, masks=om, dropout_rate=rate, training=True, dtype=torch.float64,
+                                 want_anomaly=ce, l1_sign=sgn, l1_sign_ce=sgn_ce)
+    assert _rel(eng.br[0].xhat.numpy(), out['x_hat'].numpy()) < TOL
+    got = eng.losses()
+    for k in got:
+        assert abs(got[k] - float(L[k])) <= 1e-5 * abs(float(L[k])), (k, got[k], float(L[k]))
+    if ce:
+        assert _rel(eng.br[1].xhat.numpy(), out['x_hat_ce'].numpy()) < TOL
+        assert _rel(eng.anomaly.numpy(), L['anomaly'].numpy()) < 2e-5
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    for k in P:
+        assert _rel(grads[k], G[k].numpy()) < 2e-5, (k, _rel(grads[k], G[k].numpy()))
+    # inference forward, dropout off (what reconstruct() runs)
+    eng.fp.load(P)
+    for br in eng.br:
+        br.masks = {k: None for k in br.masks}
+    eng.forward(training=False, dropout_rate=0.0, branches=[0], need_l1=False)
+    out2 = O.forward(arch, P, x, x_ce=x_ce, eps=eps, training=False, dtype=torch.float64)
+    assert _rel(eng.br[0].xhat.numpy(), out2['x_hat'].numpy()) < TOL
