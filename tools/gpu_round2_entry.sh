@@ -1,11 +1,13 @@
 #!/bin/bash
-# FIRST GPU call of round 2 (cheap, ~3 GPU-minutes): answers the open hardware questions left at the end of round 1, which
+# FIRST GPU call of round 2 (~6 GPU-minutes): answers the open hardware questions left at the end of round 1, which
 # had no GPU minutes left when the candidates were written.  usage: gpurun --timeout 900 -- 'bash tools/gpu_round2_entry.sh'
 #   1. the shipped defaults (even stage ring at N = 64, N = 128 on the first-generation kernel) were derived on CPU from the
 #      barrier-protocol model - confirm the GPU suite and re-measure the headline;
 #   2. tools/ubench/operand_probe.cu: tf32 operand forms the Form-W redesign needs (MN-major SWIZZLE_128B_BASE32B operands,
 #      row-shifted descriptors, truncation of raw fp32 words);
-#   3. the N = 32 candidate kernel gather_gemm_tc3 (UAD_TC_V3=1): correctness, then time against the shipped kernel.
+#   3. the N = 32 candidate kernel gather_gemm_tc3 (UAD_TC_V3=1): correctness, then time against the shipped kernel;
+#   4. the compositions that so far only ran through the CPU emulation of the ABI (AnoVAEGAN, AAE / constrained AAE, CE):
+#      real-kernel parity, CUDA-graph replay, trainers (UAD_UNVERIFIED=1) - drop the skip markers of the files that pass.
 TAG=${1:-r2a}
 mkdir -p gpurun_out build
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
@@ -21,3 +23,9 @@ tail -5 gpurun_out/${TAG}_v3_pytest.log
 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_shipped.txt 2>&1
 UAD_TC_V3=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v3.txt 2>&1
 tail -12 gpurun_out/${TAG}_time_tc_shipped.txt gpurun_out/${TAG}_time_tc_v3.txt
+UAD_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_anovaegan.py tests/test_gpu_aae.py tests/test_gpu_ce.py -m gpu -q --maxfail=20 \
+  -p no:cacheprovider > gpurun_out/${TAG}_unverified_pytest.log 2>&1
+tail -15 gpurun_out/${TAG}_unverified_pytest.log
+UAD_TC_V2=5 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_5.txt 2>&1      # N = 128 column-split (odd ring: timing only)
+UAD_TC_V2=0 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v1.txt 2>&1        # first-generation kernel everywhere
+tail -6 gpurun_out/${TAG}_time_tc_v2_5.txt gpurun_out/${TAG}_time_tc_v1.txt
