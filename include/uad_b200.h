@@ -247,6 +247,18 @@ int uad_tv_restore_seed(const float* x, const float* xhat, float tv_lambda, floa
  * grads_out (nullable) receives gx - g, the tensor the reference fetches as losses['grads'] (VAE_You.py:54). */
 int uad_restore_update(float* x, const float* gx, const float* g, float lr, float* grads_out, size_t n, void* stream);
 
+/* ================= GMVAE latent block (models/gaussian_mixture_variational_autoencoder.py:64-71; trainers/GMVAE.py:66-88) =========
+ * per sample: logit_c = sum_j(-0.5 (z_s_j - M_jc)^2 e^{S_jc} - S_jc + log pi), pc = softmax(logit) [B,dc] (nullable output);
+ * con[b] = sum_c pc_c sum_j kl_jc with kl_jc = 0.5((e^{z_ls_j} + (z_mu_j - M_jc)^2)(e^{S_jc} + 1e-6) - S_jc - z_ls_j - 1)
+ * (conditional_prior_loss); closs[b] = max(sum_c pc_c log(pc_c dc + 1e-8), c_lambda) (c_prior_loss).
+ * z_mu, z_ls, z_s: [B,dz]; M = z_wc_mus, S = z_wc_log_sigma_invs: [B,dz,dc]; dc <= 32. */
+int uad_gmvae_latent_fwd(const float* z_mu, const float* z_ls, const float* z_s, const float* M, const float* S, float* pc,
+                         float* con, float* closs, int B, int dz, int dc, float c_lambda, void* stream);
+/* gradients of scale*(con[b] + closs[b]) w.r.t. the five inputs (z_s as an independent input) */
+int uad_gmvae_latent_bwd(const float* z_mu, const float* z_ls, const float* z_s, const float* M, const float* S, float scale,
+                         float* dz_mu, float* dz_ls, float* dz_s, float* dM, float* dS, int B, int dz, int dc, float c_lambda,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

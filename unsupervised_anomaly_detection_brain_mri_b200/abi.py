@@ -78,6 +78,8 @@ SIGNATURES = {
     'uad_tv_restore_workspace_bytes': (_Z, [_I, _I, _I]),
     'uad_tv_restore_seed': (_I, [_P, _P, _F, _P, _P, _I, _I, _I, _P, _Z, _P]),
     'uad_restore_update': (_I, [_P, _P, _P, _F, _P, _Z, _P]),
+    'uad_gmvae_latent_fwd': (_I, [_P] * 8 + [_I, _I, _I, _F, _P]),
+    'uad_gmvae_latent_bwd': (_I, [_P] * 5 + [_F] + [_P] * 5 + [_I, _I, _I, _F, _P]),
 }
 
 
