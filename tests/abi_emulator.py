@@ -411,6 +411,47 @@ def uad_adam_tf_step(params, grads, m, v, n, lr, b1, b2, eps, grad_scale, step_d
     _w(params, _v(params, n) - lr_t * mn / (vn.sqrt() + eps))
 
 
+# ------------------------------------------------------------------------------------------------ GMVAE latent block, restoration
+def _gmvae_terms(z_mu, z_ls, z_s, M, S, dc, c_lambda):
+    """The reference's graph nodes (models/gaussian_mixture_variational_autoencoder.py:64-71, trainers/GMVAE.py:66-88) - an
+    implementation independent of csrc/uad_gmvae_latent.h (that header is checked against the same formulas in test_gmvae_latent.py)."""
+    zs = z_s.unsqueeze(-1)
+    pc = torch.softmax((-0.5 * (zs - M) ** 2 * torch.exp(S) - S + math.log(math.pi)).sum(1), dim=-1)
+    kl = 0.5 * ((torch.exp(z_ls).unsqueeze(-1) + (z_mu.unsqueeze(-1) - M) ** 2) * (torch.exp(S) + 1e-6) - S - z_ls.unsqueeze(-1) - 1)
+    con = (kl * pc.unsqueeze(1)).sum((1, 2))
+    closs1 = (pc * torch.log(pc * dc + 1e-8)).sum(1)
+    return pc, con, torch.maximum(closs1, torch.full_like(closs1, c_lambda))
+
+
+def uad_gmvae_latent_fwd(z_mu, z_ls, z_s, M, S, pc, con, closs, B, dz, dc, c_lambda, st):
+    p, c, cl = _gmvae_terms(_v(z_mu, B, dz), _v(z_ls, B, dz), _v(z_s, B, dz), _v(M, B, dz, dc), _v(S, B, dz, dc), dc, c_lambda)
+    _w(pc, p)
+    _w(con, c)
+    _w(closs, cl)
+
+
+def uad_gmvae_latent_bwd(z_mu, z_ls, z_s, M, S, scale, dz_mu, dz_ls, dz_s, dM, dS, B, dz, dc, c_lambda, st):
+    t = [a.clone().requires_grad_(True) for a in (_v(z_mu, B, dz), _v(z_ls, B, dz), _v(z_s, B, dz), _v(M, B, dz, dc), _v(S, B, dz, dc))]
+    _, c, cl = _gmvae_terms(*t, dc, c_lambda)
+    for dst, g in zip((dz_mu, dz_ls, dz_s, dM, dS), torch.autograd.grad(scale * (c + cl).sum(), t)):
+        _w(dst, g)
+
+
+def uad_tv_restore_seed(x, xhat, tv_lambda, g, tv, B, H, W, ws, wsb, st):
+    xt, xh = _v(x, B, H, W), _v(xhat, B, H, W)
+    d = (xt - xh).clone().requires_grad_(True)
+    t = (d[:, 1:] - d[:, :-1]).abs().sum((1, 2)) + (d[:, :, 1:] - d[:, :, :-1]).abs().sum((1, 2))
+    T, = torch.autograd.grad(t.sum(), d)
+    _w(g, torch.sign(xh - xt) - tv_lambda * T)
+    _w(tv, t.detach())
+
+
+def uad_restore_update(x, gx, g, lr, grads_out, n, st):
+    gr = _v(gx, n) - _v(g, n)
+    _w(grads_out, gr)
+    _w(x, _v(x, n) - lr * gr)
+
+
 _rng = np.random.default_rng(1234)
 
 

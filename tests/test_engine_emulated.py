@@ -642,3 +642,75 @@ def test_emulator_reproduces_the_other_gpu_verified_steps(arch, monkeypatch):
     eng.forward(training=False, dropout_rate=0.0, branches=[0], need_l1=False)
     out2 = O.forward(arch, P, x, x_ce=x_ce, eps=eps, training=False, dtype=torch.float64)
     assert _rel(eng.br[0].xhat.numpy(), out2['x_hat'].numpy()) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ 6. Gaussian-mixture VAE
+def _gmvae(monkeypatch, S=32, B=2, rate=0.2, dz=16, dw=2, dc=5, c_lambda=0.01):
+    from oracle import gmvae_cpu as GO
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod)
+    P = GO.perturb(GO.init_params(S, dim_z=dz, dim_w=dw, dim_c=dc, seed=1))
+    eng = eng_mod.ConvAutoencoderEngine(eng_mod.GMVAE, S, zDim=dz, batch=B, device='cpu', math_mode=0, dim_w=dw, dim_c=dc, c_lambda=c_lambda)
+    E.adopt(eng)
+    assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
+    eng.fp.load(P)
+    rng = np.random.default_rng(9)
+    x = O.synthetic_slices(B, S, seed=31)
+    eps_w, eps_z = rng.standard_normal((B, dw)).astype(np.float32), rng.standard_normal((B, dz)).astype(np.float32)
+    mk = lambda n: (rng.uniform(size=(B, n)) >= rate).astype(np.float32)   # noqa: E731
+    masks = {'w_mu': mk(dw), 'w_ls': mk(dw), 'z_mu': mk(dz), 'dec': mk(eng.flat)}
+    eng.set_inputs(x)
+    eng.br[0].eps_w.copy_(torch.from_numpy(eps_w))
+    eng.set_noise(eps_z, {'wmu': masks['w_mu'], 'wls': masks['w_ls'], 'mu': masks['z_mu'], 'dec': masks['dec']})
+    return GO, eng, P, x, eps_w, eps_z, masks
+
+
+@pytest.mark.parametrize('c_lambda', [0.01, 100.0])
+def test_gmvae_train_step_matches_oracle(c_lambda, monkeypatch):
+    """models/gaussian_mixture_variational_autoencoder.py + trainers/GMVAE.py:58-88: forward tensors, the four loss terms and every
+    gradient (both sides of the tf.maximum gate of the cluster prior)."""
+    rate, lr, dc = 0.2, 1e-3, 5
+    GO, eng, P, x, eps_w, eps_z, masks = _gmvae(monkeypatch, rate=rate, dc=dc, c_lambda=c_lambda)
+    eng._keep = 1.0 / (1.0 - rate)
+    eng.forward(training=True, dropout_rate=rate)
+    sgn = np.sign(eng.br[0].xhat.numpy().astype(np.float64) - x)
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True)
+    o, L, G = GO.loss_and_grads(P, x, eps_w, eps_z, masks, rate, True, dc, c_lambda, torch.float64, l1_sign=sgn)
+    br = eng.br[0]
+    for got, key in ((br.xhat, 'xz_mu'), (br.mu, 'z_mu'), (br.ls, 'z_log_sigma'), (br.zv, 'z_sampled'), (br.w_s, 'w_sampled'), (br.pc, 'pc')):
+        assert _rel(got.numpy().reshape(o[key].shape), o[key].numpy()) < TOL, key
+    assert _rel(br.Mz.numpy().reshape(o['z_wc_mus'].shape), o['z_wc_mus'].numpy()) < TOL
+    assert _rel(br.Sz.numpy().reshape(o['z_wc_log_sigma_invs'].shape), o['z_wc_log_sigma_invs'].numpy()) < TOL
+    got = eng.losses()
+    for k in got:
+        assert abs(got[k] - float(L[k])) <= 1e-5 * max(abs(float(L[k])), 1e-6), (k, got[k], float(L[k]))
+    assert (float(L['c_prior_loss']) == c_lambda) == (c_lambda == 100.0)
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    gmax = max(float(v.abs().max()) for v in G.values())
+    for k in P:
+        ref = G[k].numpy()
+        if float(np.abs(ref).max()) < 1e-12 * gmax:
+            assert float(np.abs(grads[k]).max()) < 1e-9 * gmax, k
+            continue
+        assert _rel(grads[k], ref) < 2e-5, (k, _rel(grads[k], ref))
+    assert np.array_equal(grads['Variable'], grads['dense_6/bias'])
+
+
+def test_gmvae_restoration_step_matches_oracle(monkeypatch):
+    """GMVAE.reconstruct (trainers/GMVAE.py:166-197): one MAP-restoration iteration, grads = d/dx sum_b [loss + tv_lambda TV(x - xz_mu)]
+    with the batch mean of `loss` multiplied back by B (a scalar broadcast over the per-image TV vector)."""
+    tv_lambda, lr, dc, c_lambda = 1.3, 1e-3, 5, 0.01
+    GO, eng, P, x, eps_w, eps_z, masks = _gmvae(monkeypatch, rate=0.0, dc=dc, c_lambda=c_lambda)
+    for br in eng.br:
+        br.masks = {k: None for k in br.masks}
+    eng.forward(training=False, dropout_rate=0.0, branches=[0], need_l1=False)
+    xh = eng.br[0].xhat.numpy().astype(np.float64)
+    d = x.astype(np.float64) - xh
+    tv_sign = (np.sign(d[:, 1:] - d[:, :-1]), np.sign(d[:, :, 1:] - d[:, :, :-1]))
+    # (oracle.restore_gradient sums `loss + tv_lambda * tv` over the batch exactly as tf.gradients does: the scalar batch-mean loss is
+    #  broadcast over the per-image TV vector, i.e. multiplied back by B)
+    want, o = GO.restore_gradient(P, x, eps_w, eps_z, tv_lambda, dc, c_lambda, torch.float64, l1_sign=np.sign(xh - x), tv_sign=tv_sign)
+    x0 = eng.br[0].x.clone()
+    eng.restore_step(lr, tv_lambda, parity_noise=True, keep_grads=True)
+    assert _rel(eng.restore_grads.numpy(), want.numpy()) < 2e-5
+    assert _rel((x0 - eng.br[0].x).numpy(), lr * want.numpy()) < 1e-4

@@ -38,7 +38,10 @@ AAE = 'adversarial_autoencoder'  # dense AE (both bottleneck Dropouts honour the
 # Decoder/conv2d_1: models/constrained_adversarial_autoencoder.py:13-36); the engine keeps ONE canonical naming for the shared
 # bottleneck layers (Bottleneck/...), what differs in behaviour - which variables optim_gen updates - is handled by aae_engine.
 CAAE = 'constrained_adversarial_autoencoder'
-ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE, CAAE)
+# Gaussian-mixture VAE (models/gaussian_mixture_variational_autoencoder.py): four Dense heads (w_mu, w_log_sigma, z_mu, z_log_sigma),
+# z and w reparameterised with exp(0.5 * log-variance), p(z|w,c) heads on w and the mixture latent block (uad_gmvae_latent_*)
+GMVAE = 'gaussian_mixture_variational_autoencoder'
+ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE, CAAE, GMVAE)
 # Dense widths of the latent critic (models/adversarial_autoencoder.py:44-48, constrained_adversarial_autoencoder.py:52-56)
 CRITIC_WIDTHS = {AAE: (50, 50, 1), CAAE: (100, 50, 1)}
 AAE_CRITIC = CRITIC_WIDTHS[AAE]
@@ -75,7 +78,7 @@ def _bn(k):
     return 'batch_normalization' if k == 0 else f'batch_normalization_{k}'
 
 
-def param_specs(arch, S, C=1, zDim=128, res=8):
+def param_specs(arch, S, C=1, zDim=128, res=8, dim_w=1, dim_c=9):
     """TF variable names -> shapes, in creation order."""
     assert arch in ARCHS, arch
     n, enc, dec = stack_plan(S, res)
@@ -95,11 +98,12 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
         sp['Bottleneck/conv2d_1/bias'] = (cin,)
         flat = res * res * cb
-        heads = 1 if arch in (AE, CAE, AAE, CAAE) else 2
+        heads = 1 if arch in (AE, CAE, AAE, CAAE) else (4 if arch == GMVAE else 2)
         for h in range(heads):
             nm = 'dense' if h == 0 else f'dense_{h}'
-            sp[f'Bottleneck/{nm}/kernel'] = (flat, zDim)
-            sp[f'Bottleneck/{nm}/bias'] = (zDim,)
+            width = dim_w if (arch == GMVAE and h < 2) else zDim         # GMVAE: w_mu, w_log_sigma, z_mu, z_log_sigma
+            sp[f'Bottleneck/{nm}/kernel'] = (flat, width)
+            sp[f'Bottleneck/{nm}/bias'] = (width,)
         sp[f'Bottleneck/dense_{heads}/kernel'] = (zDim, flat)
         sp[f'Bottleneck/dense_{heads}/bias'] = (flat,)
     sp[f'Decoder/{_bn(bn)}/gamma'] = (cin,)
@@ -114,6 +118,11 @@ def param_specs(arch, S, C=1, zDim=128, res=8):
         cin = co
     sp['Decoder/dec_Conv2D_final/kernel'] = (1, 1, cin, C)
     sp['Decoder/dec_Conv2D_final/bias'] = (C,)
+    if arch == GMVAE:                # p(z|w,c): the two un-scoped Dense layers on w and the trainable 0.1 bias (model :46-51)
+        for nm in ('dense_5', 'dense_6'):
+            sp[nm + '/kernel'] = (dim_w, zDim * dim_c)
+            sp[nm + '/bias'] = (zDim * dim_c,)
+        sp['Variable'] = (zDim * dim_c,)
     if arch in CRITIC_WIDTHS:        # the tf.layers Dense counter runs on: Bottleneck/{dense, dense_1}, Discriminator/dense_{2,3,4}
         k = zDim
         for j, width in enumerate(CRITIC_WIDTHS[arch]):
@@ -138,6 +147,8 @@ def glorot_init(specs, seed=1):
             out[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
         elif name.endswith('/gamma'):
             out[name] = np.ones(shape, np.float32)
+        elif name == 'Variable':                         # GMVAE: tf.constant(0.1) bias of z_wc_log_sigma_inv
+            out[name] = np.full(shape, 0.1, np.float32)
         else:
             out[name] = np.zeros(shape, np.float32)
     return out
@@ -210,7 +221,7 @@ class ConvAutoencoderEngine:
     """
 
     def __init__(self, arch, S, C=1, zDim=128, res=8, batch=8, device='cuda:0', math_mode=abi.MATH_FP32_SIMT, seed=1,
-                 rng_seed=0x5eed, share_params=None, keep_preact=False):
+                 rng_seed=0x5eed, share_params=None, keep_preact=False, dim_w=1, dim_c=9, c_lambda=1.0):
         if arch not in ARCHS:
             raise ValueError(f'unsupported architecture {arch!r}; supported: {ARCHS}')
         if C != 1:
@@ -223,7 +234,8 @@ class ConvAutoencoderEngine:
         self.n, self.enc_ch, self.dec_ch = stack_plan(S, res)
         self.cb = self.enc_ch[-1] // 8
         self.flat = res * res * self.cb
-        self.specs = param_specs(arch, S, C, zDim, res)
+        self.dim_w, self.dim_c, self.c_lambda = int(dim_w), int(dim_c), float(c_lambda)      # GMVAE only
+        self.specs = param_specs(arch, S, C, zDim, res, dim_w, dim_c)
         if share_params is not None:      # e.g. an evaluation engine with another batch size on the same weights
             self.fp = share_params
         else:
@@ -281,6 +293,19 @@ class ConvAutoencoderEngine:
         br.mask_bufs.update(ls=self._new(B, self.zDim), dec=self._new(B, self.flat))
         if self.arch == AES:
             br.mask_bufs['sp'] = self._new(B, r, r, self.enc_ch[-1])      # Dropout on the spatial code z [B,res,res,C]
+        if self.arch == GMVAE:
+            dw, n = self.dim_w, self.zDim * self.dim_c
+            for k in ('w_mu', 'w_ls', 'w_lsh', 'w_sigma', 'w_s', 'eps_w', 'dws', 'dws2', 'dwmu', 'dwlsh'):
+                setattr(br, k, self._new(B, dw))
+            for k in ('z_lsh', 'gzmu', 'gzls', 'gzs', 'dlsh'):
+                setattr(br, k, self._new(B, self.zDim))
+            for k in ('Mz', 'S0', 'Sz', 'dM', 'dS'):
+                setattr(br, k, self._new(B, n))
+            br.kl_w, br.kl_unused, br.con, br.closs = (self._new(B) for _ in range(4))
+            br.pc = self._new(B, self.dim_c)
+            br.ones_n = torch.ones(n, dtype=torch.float32, device=self.device)
+            br.masks.update(wmu=None, wls=None)
+            br.mask_bufs.update(wmu=self._new(B, dw), wls=self._new(B, dw))
         return br
 
     def _alloc(self):
@@ -410,6 +435,19 @@ class ConvAutoencoderEngine:
                 br.masks[k] = br.mask_bufs[k] if on else None
             call('uad_counter_add', ctr, 1 << 20, st)
             return
+        if self.arch == GMVAE:           # eps_z, eps_w; Dropout with the flag on w_mu, w_log_sigma, z_mu, dec_dense(z) (z_log_sigma: none)
+            br = self.br[0]
+            on = bool(dropout) and rate > 0
+            call('uad_randn', ptr(br.eps), br.eps.numel(), self.rng_seed, 0 << 40, ctr, st)
+            call('uad_randn', ptr(br.eps_w), br.eps_w.numel(), self.rng_seed, 1 << 40, ctr, st)
+            for sid, k in enumerate(('wmu', 'wls', 'mu', 'dec')):
+                if on:
+                    call('uad_dropout_mask', ptr(br.mask_bufs[k]), br.mask_bufs[k].numel(), float(rate), self.rng_seed, (sid + 2) << 40,
+                         ctr, st)
+                br.masks[k] = br.mask_bufs[k] if on else None
+            br.masks['ls'] = None
+            call('uad_counter_add', ctr, 1 << 20, st)
+            return
         for bi, br in enumerate(self.br):
             if self.arch != AE and bi == 0:
                 call('uad_randn', ptr(br.eps), br.eps.numel(), self.rng_seed, nb << 40, ctr, st)
@@ -461,6 +499,8 @@ class ConvAutoencoderEngine:
                 zsrc, dd_name, dec_mask = br.mu, 'Bottleneck/dense_1', (m['dec'] if self.arch in (CAE, AAE, CAAE) else None)
                 if is_ce:                                # constrained AE, re-encoding pass: z_rec is all that is needed
                     continue
+            elif self.arch == GMVAE:
+                zsrc, dd_name, dec_mask = self._gmvae_bottleneck_fwd(br, keep)
             else:
                 self._op('bneck03', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense/kernel')), ptr(fp.p('Bottleneck/dense/bias')),
                      ptr(m['mu']), keep, None, None, ptr(br.mu), None, B, self.flat, self.zDim, ACT_NONE, 0.0, 1.0, ws, wsb, st)
@@ -495,7 +535,7 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE, CAAE) else None, ptr(self.scalars), B, st)
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE, CAAE, GMVAE) else None, ptr(self.scalars), B, st)
         if self.arch in (CAE, CAAE) and (branches is None or 1 in branches):
             # trainers/ConstrainedAE.py:37-43: L2 = mean_hwc (x - x_hat)^2, Rec_z = mean_j (z - z_rec)^2 (per sample);
             # loss = mean_b(L2 + rho * Rec_z).  The same calls leave d loss/d x_hat and d loss/d z_rec (d/dz = -d/dz_rec).
@@ -510,6 +550,72 @@ class ConvAutoencoderEngine:
             nx = b0.x.numel()
             self._op('bneck09', 'uad_mse', ptr(b0.xhat), ptr(b0.x), nx, 2.0 / nx, ptr(self.gxhat), 1.0 / nx, self.scalars[4:].data_ptr(),
                      ws, wsb, st)
+
+    # ------------------------------------------------------------------ GMVAE bottleneck (models/gaussian_mixture_variational_autoencoder.py:21-71)
+    def _gmvae_bottleneck_fwd(self, br, keep):
+        """zb -> w_mu, w_log_sigma, z_mu, z_log_sigma -> w, z (std = exp(0.5 * log-variance): uad_reparam_kl_fwd on the halved
+        log-variance, whose KL output for w IS w_prior_loss) -> p(z|w,c) heads -> responsibilities, conditional-prior and
+        cluster-prior losses per sample.  Returns what the shared decoder entry needs (source, Dense name, mask)."""
+        fp, st = self.fp, self._st()
+        ws, wsb = self._wsargs()
+        B, dz, dw, n, m = self.B, self.zDim, self.dim_w, self.zDim * self.dim_c, br.masks
+        for name, out, mask, width in (('dense', br.w_mu, m['wmu'], dw), ('dense_1', br.w_ls, m['wls'], dw), ('dense_2', br.mu, m['mu'], dz),
+                                       ('dense_3', br.ls, None, dz)):
+            self._op('bneck03', 'uad_dense_fwd', ptr(br.zb), ptr(fp.p(f'Bottleneck/{name}/kernel')), ptr(fp.p(f'Bottleneck/{name}/bias')),
+                     ptr(mask), keep, None, None, ptr(out), None, B, self.flat, width, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+        self._op('bneck05', 'uad_axpby', 0.5, ptr(br.w_ls), 0.0, ptr(br.w_lsh), B * dw, st)
+        self._op('bneck05', 'uad_axpby', 0.5, ptr(br.ls), 0.0, ptr(br.z_lsh), B * dz, st)
+        self._op('bneck05', 'uad_reparam_kl_fwd', ptr(br.w_mu), ptr(br.w_lsh), ptr(br.eps_w), ptr(br.w_sigma), ptr(br.w_s), ptr(br.kl_w), B, dw, st)
+        self._op('bneck05', 'uad_reparam_kl_fwd', ptr(br.mu), ptr(br.z_lsh), ptr(br.eps), ptr(br.sigma), ptr(br.zv), ptr(br.kl_unused), B, dz, st)
+        self._op('bneck05', 'uad_dense_fwd', ptr(br.w_s), ptr(fp.p('dense_5/kernel')), ptr(fp.p('dense_5/bias')), None, 1.0, None, None,
+                 ptr(br.Mz), None, B, dw, n, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+        # z_wc_log_sigma_inv = Dense(w) + Variable: the extra trainable bias rides the affine slot (gamma = 1, beta = Variable)
+        self._op('bneck05', 'uad_dense_fwd', ptr(br.w_s), ptr(fp.p('dense_6/kernel')), ptr(fp.p('dense_6/bias')), None, 1.0, ptr(br.ones_n),
+                 ptr(fp.p('Variable')), ptr(br.S0), ptr(br.Sz), B, dw, n, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+        self._op('bneck05', 'uad_gmvae_latent_fwd', ptr(br.mu), ptr(br.ls), ptr(br.zv), ptr(br.Mz), ptr(br.Sz), ptr(br.pc), ptr(br.con),
+                 ptr(br.closs), B, dz, self.dim_c, self.c_lambda, st)
+        for buf, slot in ((br.con, 5), (br.kl_w, 6), (br.closs, 7)):     # batch means: conditional_prior / w_prior / c_prior loss
+            self._op('bneck08', 'uad_sum_scaled', ptr(buf), B, 1.0 / B, self.scalars[slot:].data_ptr(), ws, wsb, st)
+        return br.zv, 'Bottleneck/dense_4', m['dec']
+
+    def _gmvae_bottleneck_bwd(self, br, params, scale, acc):
+        """From sm['dd'] (gradient w.r.t. dec_dense's post-dropout output) to sm['dflat'] (w.r.t. the flattened 1x1-conv output):
+        the reconstruction path through z plus scale * d(con + w_loss + c_loss)_b.  params=False forms no weight gradient
+        (restoration, tf.gradients(..., x)); scale = 1/B for the batch-mean training loss, 1 for the per-sample sums of GMVAE.py:89-90."""
+        fp, st = self.fp, self._st()
+        ws, wsb = self._wsargs()
+        B, dz, dw, n, m, sm, keep = self.B, self.zDim, self.dim_w, self.zDim * self.dim_c, br.masks, self.small, self._keep
+        G = (lambda name: ptr(fp.g(name))) if params else (lambda name: None)
+        self._op('bneck13', 'uad_dense_bwd', ptr(br.zv), ptr(fp.p('Bottleneck/dense_4/kernel')), ptr(sm['dd']), ptr(m['dec']), keep,
+                 ptr(sm['dzv']), G('Bottleneck/dense_4/kernel'), G('Bottleneck/dense_4/bias'), B, dz, self.flat, acc, ws, wsb, st)
+        self._op('bneck14', 'uad_gmvae_latent_bwd', ptr(br.mu), ptr(br.ls), ptr(br.zv), ptr(br.Mz), ptr(br.Sz), float(scale), ptr(br.gzmu),
+                 ptr(br.gzls), ptr(br.gzs), ptr(br.dM), ptr(br.dS), B, dz, self.dim_c, self.c_lambda, st)
+        self._op('bneck14', 'uad_axpby', 1.0, ptr(br.gzs), 1.0, ptr(sm['dzv']), B * dz, st)                  # d/dz_sampled, both paths
+        self._op('bneck14', 'uad_reparam_kl_bwd', ptr(br.mu), ptr(br.z_lsh), ptr(br.eps), ptr(sm['dzv']), 0.0, ptr(sm['dmu']), ptr(br.dlsh),
+                 B, dz, st)
+        self._op('bneck14', 'uad_axpby', 1.0, ptr(br.gzmu), 1.0, ptr(sm['dmu']), B * dz, st)                 # d/dz_mu
+        self._op('bneck14', 'uad_axpby', 0.5, ptr(br.dlsh), 1.0, ptr(br.gzls), B * dz, st)                   # d/dz_log_sigma (in gzls)
+        # p(z|w,c) heads -> d/dw_sampled; the 0.1 bias Variable shares dense_6's bias gradient
+        self._op('bneck14', 'uad_dense_bwd', ptr(br.w_s), ptr(fp.p('dense_5/kernel')), ptr(br.dM), None, 1.0, ptr(br.dws),
+                 G('dense_5/kernel'), G('dense_5/bias'), B, dw, n, acc, ws, wsb, st)
+        self._op('bneck14', 'uad_dense_bwd', ptr(br.w_s), ptr(fp.p('dense_6/kernel')), ptr(br.dS), None, 1.0, ptr(br.dws2),
+                 G('dense_6/kernel'), G('dense_6/bias'), B, dw, n, acc, ws, wsb, st)
+        if params:
+            self._op('bneck14', 'uad_axpby', 1.0, ptr(fp.g('dense_6/bias')), 0.0, ptr(fp.g('Variable')), n, st)
+        self._op('bneck14', 'uad_axpby', 1.0, ptr(br.dws2), 1.0, ptr(br.dws), B * dw, st)
+        self._op('bneck14', 'uad_reparam_kl_bwd', ptr(br.w_mu), ptr(br.w_lsh), ptr(br.eps_w), ptr(br.dws), float(scale), ptr(br.dwmu),
+                 ptr(br.dwlsh), B, dw, st)
+        self._op('bneck14', 'uad_axpby', 0.5, ptr(br.dwlsh), 0.0, ptr(br.dwlsh), B * dw, st)                 # d/dw_log_sigma
+        # the four heads back to the flattened bottleneck
+        first = True
+        for name, g_in, mask, width in (('dense_2', sm['dmu'], m['mu'], dz), ('dense_3', br.gzls, None, dz), ('dense', br.dwmu, m['wmu'], dw),
+                                        ('dense_1', br.dwlsh, m['wls'], dw)):
+            dst = sm['dflat'] if first else sm['dflat2']
+            self._op('bneck15', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p(f'Bottleneck/{name}/kernel')), ptr(g_in), ptr(mask), keep, ptr(dst),
+                     G(f'Bottleneck/{name}/kernel'), G(f'Bottleneck/{name}/bias'), B, self.flat, width, acc, ws, wsb, st)
+            if not first:
+                self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
+            first = False
 
     # ------------------------------------------------------------------ backward
     def backward(self, want_input_grad=False):
@@ -574,6 +680,8 @@ class ConvAutoencoderEngine:
                    ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
             if self.arch == AES:
                 pass
+            elif self.arch == GMVAE:
+                self._gmvae_bottleneck_bwd(br, True, scale, acc)
             elif self.arch == AE:
                 self._op('bneck11', 'uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
                      ptr(sm['dmu']), ptr(fp.g('Bottleneck/dense_1/kernel')), ptr(fp.g('Bottleneck/dense_1/bias')), B,
@@ -778,6 +886,8 @@ class ConvAutoencoderEngine:
                      None, None, B * r2, self.cb, ctop, 0, ws, wsb, st)
         if self.arch == AES:
             pass
+        elif self.arch == GMVAE:
+            self._gmvae_bottleneck_bwd(br, False, float(kl_scale), 0)
         elif self.arch == AE:
             self._op('bneck11', 'uad_dense_bwd', ptr(br.mu), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dd']), None, 1.0,
                      ptr(sm['dmu']), None, None, B, self.zDim, self.flat, 0, ws, wsb, st)
@@ -943,5 +1053,8 @@ class ConvAutoencoderEngine:
             return {'reconstructionLoss': float(s[0]), 'L2': float(s[4]), 'loss': float(s[4])}
         if self.arch == VAE:
             return {'reconstructionLoss': float(s[0]), 'kl': float(s[1]), 'loss': float(s[2])}
+        if self.arch == GMVAE:
+            return {'reconstructionLoss': float(s[0]), 'mean_p_loss': float(s[0]), 'conditional_prior_loss': float(s[5]),
+                    'w_prior_loss': float(s[6]), 'c_prior_loss': float(s[7]), 'loss': float(s[0]) + float(s[5]) + float(s[6]) + float(s[7])}
         return {'Rec_vae': float(s[0]), 'kl': float(s[1]), 'loss_vae': float(s[2]), 'Rec_ce': float(s[3]),
                 'reconstructionLoss': 0.5 * float(s[0] + s[3]), 'loss': float(s[2] + s[3])}
