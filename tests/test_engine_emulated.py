@@ -714,3 +714,55 @@ def test_gmvae_restoration_step_matches_oracle(monkeypatch):
     eng.restore_step(lr, tv_lambda, parity_noise=True, keep_grads=True)
     assert _rel(eng.restore_grads.numpy(), want.numpy()) < 2e-5
     assert _rel((x0 - eng.br[0].x).numpy(), lr * want.numpy()) < 1e-4
+
+
+def test_gmvae_trainer_loop_and_restoration(monkeypatch, tmp_path):
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.customlayers import Placeholder
+    from unsupervised_anomaly_detection_brain_mri_b200.models.gaussian_mixture_variational_autoencoder import gaussian_mixture_variational_autoencoder
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.AEMODEL import AEMODEL
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.GMVAE import GMVAE
+    E.install(monkeypatch, eng_mod)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(AEMODEL, '_stage', lambda self, key, arr: torch.from_numpy(np.ascontiguousarray(arr, np.float32)))
+    monkeypatch.setattr(AEMODEL, '_prefetch', lambda self, key, arr: None)
+    config = GMVAE.Config()
+    assert (config.modelname, config.dim_c, config.dim_z, config.dim_w, config.c_lambda, config.restore_steps) == ('GMVAE', 6, 1, 1, 1, 150)
+    config.outputHeight = config.outputWidth = 32
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 128, 1
+    config.dim_c, config.dim_z, config.dim_w, config.c_lambda = 4, 8, 1, 0.5
+    config.restore_steps, config.restore_lr, config.tv_lambda = 2, 1e-3, 1.2
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate, config.optimizer = 0.1, 1e-4, 'ADAM'
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.use_cuda_graph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    outs = gaussian_mixture_variational_autoencoder(Placeholder([None, 32, 32, 1]), 0.1, False, config)
+    assert {'w_mu', 'z_mu', 'z_wc_mus', 'xz_mu', 'pc'} <= set(outs) and outs['xz_mu'].graph.zDim == 8
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (32, 32)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 20, 28
+    ds = SYNTHETIC(opts)
+    model = GMVAE(None, config, network=gaussian_mixture_variational_autoencoder)
+    eng = model.engine
+    assert (eng.arch, eng.zDim, eng.dim_w, eng.dim_c, eng.c_lambda) == (eng_mod.GMVAE, 8, 1, 4, 0.5)
+    E.adopt(eng)
+    w0 = eng.fp.to_numpy()
+    model.train(ds)
+    w1 = eng.fp.to_numpy()
+    assert all(np.isfinite(v).all() for v in w1.values())
+    for name in ('Encoder/enc_conv2D_0/kernel', 'Bottleneck/dense/kernel', 'Bottleneck/dense_3/kernel', 'dense_5/kernel', 'dense_6/kernel',
+                 'Variable', 'Decoder/dec_Conv2D_final/kernel'):
+        assert not np.array_equal(w0[name], w1[name]), name
+    assert eng.t == ds.num_batches(2, set='TRAIN')
+    x = ds.next_batch(2, set='VAL')[0]
+    orig_eval = model._eval_engine
+    monkeypatch.setattr(model, '_eval_engine', lambda n: E.adopt(orig_eval(n)))
+    rec = model.reconstruct(x)                       # restored input after 2 iterations
+    assert rec['reconstruction'].shape == x.shape and np.isfinite(rec['l1err'])
+    assert 0 < np.abs(rec['reconstruction'] - x).max() < 0.1
+    model.restore_steps = 0                          # GMVAE.py:170-177: plain reconstruction
+    rec0 = model.reconstruct(x)
+    assert np.abs(rec0['reconstruction'] - x).max() > np.abs(rec['reconstruction'] - x).max()

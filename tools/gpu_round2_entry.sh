@@ -6,7 +6,7 @@
 #   2. tools/ubench/operand_probe.cu: tf32 operand forms the Form-W redesign needs (MN-major SWIZZLE_128B_BASE32B operands,
 #      row-shifted descriptors, truncation of raw fp32 words);
 #   3. the N = 32 candidate kernel gather_gemm_tc3 (UAD_TC_V3=1): correctness, then time against the shipped kernel;
-#   4. the compositions that so far only ran through the CPU emulation of the ABI (AnoVAEGAN, AAE / constrained AAE, CE):
+#   4. the compositions that so far only ran through the CPU emulation of the ABI (AnoVAEGAN, AAE / constrained AAE, CE, GMVAE incl. its latent kernel pair):
 #      real-kernel parity, CUDA-graph replay, trainers (UAD_UNVERIFIED=1) - drop the skip markers of the files that pass.
 TAG=${1:-r2a}
 mkdir -p gpurun_out build
@@ -23,7 +23,7 @@ tail -5 gpurun_out/${TAG}_v3_pytest.log
 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_shipped.txt 2>&1
 UAD_TC_V3=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v3.txt 2>&1
 tail -12 gpurun_out/${TAG}_time_tc_shipped.txt gpurun_out/${TAG}_time_tc_v3.txt
-UAD_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_anovaegan.py tests/test_gpu_aae.py tests/test_gpu_ce.py -m gpu -q --maxfail=20 \
+UAD_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_anovaegan.py tests/test_gpu_aae.py tests/test_gpu_ce.py tests/test_gpu_gmvae.py -m gpu -q --maxfail=20 \
   -p no:cacheprovider > gpurun_out/${TAG}_unverified_pytest.log 2>&1
 tail -15 gpurun_out/${TAG}_unverified_pytest.log
 UAD_TC_V2=5 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_5.txt 2>&1      # N = 128 column-split (odd ring: timing only)

@@ -30,6 +30,7 @@ class AEMODEL(DLMODEL, ABC):
             self.zDim = 128
 
     TWO_INPUTS = False          # ceVAE feeds (x, x_ce)
+    REC_KEY = 'x_hat'           # output key of the reconstruction (GMVAE: 'xz_mu')
     MASKED_INPUT = False        # CE feeds the patch-masked batch and scores against the plain one (one-input graph)
     LOSS_KEYS = ('loss',)
 
@@ -49,7 +50,7 @@ class AEMODEL(DLMODEL, ABC):
             self.outputs = self.network(self.x, self.x_ce, dropout_rate=self.dropout_rate, dropout=self.dropout, config=cfg)
         else:
             self.outputs = self.network(self.x, dropout_rate=self.dropout_rate, dropout=self.dropout, config=cfg)
-        self.reconstruction = self.outputs['x_hat']
+        self.reconstruction = self.outputs[self.REC_KEY]
         self.graph = self.reconstruction.graph
         # device / data-parallel context (one process per GPU; world > 1 when launched under torchrun)
         self.device = getattr(cfg, 'device', None) or f'cuda:{int(os.environ.get("LOCAL_RANK", 0))}'
@@ -60,11 +61,15 @@ class AEMODEL(DLMODEL, ABC):
         self.engine = ConvAutoencoderEngine(self.graph.arch, self.graph.S, self.graph.C, self.graph.zDim, self.graph.res,
                                             batch=cfg.batchsize, device=self.device, math_mode=self.math_mode,
                                             seed=int(getattr(cfg, 'seed', 1)),
-                                            keep_preact=bool(getattr(cfg, 'keep_preact', False)))
+                                            keep_preact=bool(getattr(cfg, 'keep_preact', False)), **self._engine_extra())
         self._eval_engines = {}
         self._pinned = {}
         self.get_number_of_trainable_params()
         self.saver = self           # reference attribute; save/load live on the trainer itself
+
+    def _engine_extra(self):
+        """Architecture-specific engine arguments (GMVAE: dim_w, dim_c, c_lambda)."""
+        return {}
 
     # ------------------------------------------------------------------ data parallel
     def enable_data_parallel(self):
@@ -172,7 +177,7 @@ class AEMODEL(DLMODEL, ABC):
         if n not in self._eval_engines:
             g = self.graph
             self._eval_engines[n] = ConvAutoencoderEngine(g.arch, g.S, g.C, g.zDim, g.res, batch=n, device=self.device,
-                                                          math_mode=self.math_mode, share_params=self.engine.fp)
+                                                          math_mode=self.math_mode, share_params=self.engine.fp, **self._engine_extra())
         return self._eval_engines[n]
 
     def reconstruct(self, x, dropout=False):
