@@ -766,3 +766,40 @@ def test_gmvae_trainer_loop_and_restoration(monkeypatch, tmp_path):
     model.restore_steps = 0                          # GMVAE.py:170-177: plain reconstruction
     rec0 = model.reconstruct(x)
     assert np.abs(rec0['reconstruction'] - x).max() > np.abs(rec['reconstruction'] - x).max()
+
+
+def test_fanogan_trainer_loop_after_the_trainer_refactor(monkeypatch, tmp_path):
+    """trainers/fAnoGAN.train through the emulator (the trainer grew override hooks for AnoVAEGAN / AAE after its last GPU run):
+    WGAN phase (1 generator + 5 critic steps per batch), encoder phase with validation, checkpoints."""
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.fanogan import fanogan
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.fAnoGAN import fAnoGAN
+    E.install(monkeypatch, fanogan_engine)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    config = fAnoGAN.Config()
+    config.outputHeight = config.outputWidth = 32
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 16, 1
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate = 0.1, 1e-4
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.useCudaGraph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (32, 32)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 20, 28
+    ds = SYNTHETIC(opts)
+    np.random.seed(0)
+    model = fAnoGAN(None, config, network=fanogan)
+    assert model.reconstruction.key == 'x_enc' and model.generated.key == 'x_'
+    model.engine.enable_training()
+    E.adopt(model.engine)
+    w0 = model.engine.fp.to_numpy()
+    model.train(ds)
+    w1 = model.engine.fp.to_numpy()
+    for scope in ('Encoder', 'Generator', 'Discriminator'):
+        assert any(not np.array_equal(w0[k], w1[k]) for k in w0 if k.startswith(scope + '/')), scope
+    t = model.engine.t
+    assert t['Generator'] > 0 and t['Discriminator'] == 5 * t['Generator'] and t['Encoder'] > 0
+    e2 = model._engine_for(2)
+    assert e2.kappa == model.engine.kappa and e2.fp is model.engine.fp
