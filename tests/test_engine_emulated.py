@@ -803,3 +803,24 @@ def test_fanogan_trainer_loop_after_the_trainer_refactor(monkeypatch, tmp_path):
     assert t['Generator'] > 0 and t['Discriminator'] == 5 * t['Generator'] and t['Encoder'] > 0
     e2 = model._engine_for(2)
     assert e2.kappa == model.engine.kappa and e2.fp is model.engine.fp
+
+
+@pytest.mark.parametrize('arch', [O.VAE, O.AE])
+def test_emulator_reproduces_the_gpu_verified_restoration_step(arch, monkeypatch):
+    """VAE_You restoration iteration (engine.restore_step -> backward_to_input, edited for the GMVAE branch after its last GPU run)."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod)
+    S, B, lam, lr = 32, 2, 1.8, 1e-3
+    P = O.perturb_params(O.init_params(arch, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=11)
+    eps = np.random.default_rng(4).standard_normal((B, 128)).astype(np.float32)
+    eng = eng_mod.ConvAutoencoderEngine(arch, S, batch=B, device='cpu', math_mode=0)
+    E.adopt(eng)
+    eng.fp.load(P)
+    eng.set_inputs(x)
+    eng.set_noise(eps)
+    eng.restore_step(lr, lam, parity_noise=True, keep_grads=True)
+    xh = eng.br[0].xhat.numpy()
+    g_ref, out, tv_ref = O.restore_gradient(arch, P, x, eps=eps, tv_lambda=lam, dtype=torch.float64, sign_from=xh)
+    assert _rel(xh, out['x_hat'].numpy()) < TOL and _rel(eng.tv.numpy(), tv_ref.numpy()) < TOL
+    assert _rel(eng.restore_grads.numpy(), g_ref.numpy()) < 2e-5
