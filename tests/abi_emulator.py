@@ -361,7 +361,7 @@ def uad_fill(y, v, n, st):
 
 
 def uad_axpby(a, x, b, y, n, st):
-    _w(y, a * _v(x, n) + b * _v(y, n))
+    _w(y, a * _v(x, n) + (b * _v(y, n) if b != 0 else 0.0))         # b == 0: y is write-only (the kernel does not read it)
 
 
 def uad_sum_scaled(x, n, scale, out, ws, wsb, st):
@@ -506,3 +506,33 @@ def adopt(engine):
         if hasattr(engine, name):
             register(*getattr(engine, name).values())
     return engine
+
+
+def poison(engine):
+    """Fill every float32 work buffer of an engine with NaN (parameters, gradient / Adam buffers, loss scalars and constant
+    vectors excepted): any ABI call that READS a buffer no earlier call wrote then shows up as NaN in the results - on the GPU
+    such a read would see whatever the allocator left there.  Call it after the engine is built, before inputs / noise are staged."""
+    skip = {id(t) for t in (getattr(engine, 'scalars', None), getattr(engine, 'sc', None)) if t is not None}
+    seen = 0
+
+    def visit(o, name=''):
+        nonlocal seen
+        if isinstance(o, torch.Tensor):
+            if o.dtype == torch.float32 and id(o) not in skip and 'ones' not in name:
+                o.fill_(float('nan'))
+                seen += 1
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                visit(v, name)
+        elif isinstance(o, dict):
+            for k, v in o.items():
+                visit(v, f'{name}.{k}')
+        elif type(o).__name__ in ('_Branch', '_CriticPass'):
+            for k, v in vars(o).items():
+                visit(v, k)
+
+    for k, v in vars(engine).items():
+        if k in ('fp', 'm_gen', 'v_gen', 'ws'):
+            continue
+        visit(v, k)
+    return seen

@@ -99,6 +99,7 @@ def test_emulator_reproduces_the_gpu_verified_fanogan_ops(which, monkeypatch):
     eng.fp.load(P)
     eng.enable_training()
     E.adopt(eng)
+    assert E.poison(eng) > 40           # NaN in every work buffer: a read of a never-written buffer would surface in the results
     eng.set_inputs(x)
     eng.set_latent(z)
     eng.alpha.copy_(torch.from_numpy(alpha.reshape(-1)))
@@ -145,6 +146,7 @@ def _anovaegan(monkeypatch, S=32, B=2, rate=0.2, zDim=128, kl_weight=1.0):
     eng.fp.load(P)
     eng.enable_training()
     E.adopt(eng)
+    E.poison(eng)
     eng.set_inputs(x)
     eng.set_noise(eps)
     eng.alpha.copy_(torch.from_numpy(alpha.reshape(-1)))
@@ -289,6 +291,7 @@ def test_emulator_reproduces_the_gpu_verified_autoencoder_steps(arch, keep_preac
     eng = eng_mod.ConvAutoencoderEngine(arch, S, batch=B, device='cpu', math_mode=0, keep_preact=keep_preact)
     E.adopt(eng)
     eng.fp.load(P)
+    E.poison(eng)
     rng = np.random.default_rng(8)
     mk = lambda n: (rng.uniform(size=(B, n)) >= rate).astype(np.float32)   # noqa: E731
     eng.set_inputs(x)
@@ -325,6 +328,7 @@ def _aae(monkeypatch, S=32, B=2, rate=0.2, zDim=32, constrained=False, rho=1.0):
     E.adopt(eng)
     assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
     eng.fp.load(P)
+    E.poison(eng)
     rng = np.random.default_rng(5)
     x = O.synthetic_slices(B, S, seed=31)
     z = rng.standard_normal((B, zDim)).astype(np.float32)
@@ -484,6 +488,7 @@ def test_context_encoder_step_scores_against_the_plain_batch(monkeypatch):
     eng = eng_mod.ConvAutoencoderEngine(O.AE, S, batch=B, device='cpu', math_mode=0)
     E.adopt(eng)
     eng.fp.load(P)
+    E.poison(eng)
     mz = (np.random.default_rng(8).uniform(size=(B, 128)) >= rate).astype(np.float32)
     eng.set_inputs(x_ce)
     eng.set_target(x)
@@ -602,6 +607,7 @@ def test_emulator_reproduces_the_other_gpu_verified_steps(arch, monkeypatch):
     E.adopt(eng)
     assert list(eng.specs.keys()) == list(P.keys())
     eng.fp.load(P)
+    E.poison(eng)
     rng = np.random.default_rng(3)
     eps = rng.standard_normal((B, 128)).astype(np.float32)
     mk = lambda *n: (rng.uniform(size=(B,) + n) >= rate).astype(np.float32)   # noqa: E731
@@ -654,6 +660,7 @@ def _gmvae(monkeypatch, S=32, B=2, rate=0.2, dz=16, dw=2, dc=5, c_lambda=0.01):
     E.adopt(eng)
     assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
     eng.fp.load(P)
+    E.poison(eng)
     rng = np.random.default_rng(9)
     x = O.synthetic_slices(B, S, seed=31)
     eps_w, eps_z = rng.standard_normal((B, dw)).astype(np.float32), rng.standard_normal((B, dz)).astype(np.float32)
@@ -817,6 +824,7 @@ def test_emulator_reproduces_the_gpu_verified_restoration_step(arch, monkeypatch
     eng = eng_mod.ConvAutoencoderEngine(arch, S, batch=B, device='cpu', math_mode=0)
     E.adopt(eng)
     eng.fp.load(P)
+    E.poison(eng)
     eng.set_inputs(x)
     eng.set_noise(eps)
     eng.restore_step(lr, lam, parity_noise=True, keep_grads=True)
