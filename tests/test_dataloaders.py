@@ -435,3 +435,28 @@ def test_get_datasets_routes_brainweb_directories_to_the_loader(tmp_path):
     options['data']['dir'] = str(tmp_path / 'nothing-here')
     hs, ps = cfg.get_datasets(options, cfg.Dataset.BRAINWEB)
     assert isinstance(hs, SYNTHETIC) and isinstance(ps, SYNTHETIC)
+
+
+def test_export_patient_volume_writes_nifti_in_native_geometry(tmp_path):
+    """options['exportVolumes'] (reference utils/Evaluation.py:323-334): the [slices, H, W] residual sub-volume is resampled back to
+    the native in-plane size and written into the patient's volume geometry, plus a binary volume for a numeric threshold."""
+    import types
+
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation as Ev
+    NII.set_view_mapping({'saggital': 2, 'coronal': 1, 'axial': 0})          # [z, y, x] volumes (the MSLUB-style mapping)
+    try:
+        vol = NII(data=np.zeros((12, 20, 24)))
+        vol.origin, vol.spacing = (1.0, 2.0, 3.0), (1.0, 1.0, 2.0)
+        sub = np.zeros((6, 10, 12), np.float64)                              # slices 3..8 at half resolution
+        sub[2, 4:6, 5:8] = 0.5
+        opts = types.SimpleNamespace(sliceStart=3, sliceEnd=9, axis='axial')
+        paths = Ev.export_patient_volume(vol, sub, (0.5, 0.5), opts, {'threshold': 0.25}, str(tmp_path), 'patient7')
+        assert [os.path.basename(p) for p in paths] == ['patient7.nii.gz', 'patient7.binary.nii.gz']
+        cont, binary = NII(paths[0]), NII(paths[1])
+        assert cont.data.shape == (12, 20, 24) and cont.origin == (1.0, 2.0, 3.0)
+        assert not cont.data[:3].any() and not cont.data[9:].any() and cont.data[5].max() > 0.3
+        assert set(np.unique(binary.data)) == {0.0, 1.0} and binary.data[5, 8:12, 10:16].all()
+        only = Ev.export_patient_volume(NII(data=np.zeros((12, 20, 24))), sub, (0.5, 0.5), opts, {'threshold': 'bestdice'}, str(tmp_path), 'q')
+        assert len(only) == 1
+    finally:
+        NII.set_view_mapping({'saggital': 0, 'coronal': 1, 'axial': 2})

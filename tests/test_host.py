@@ -205,3 +205,113 @@ def test_oracle_constrained_and_spatial_graphs_consistent():
     Pt = {k: torch.from_numpy(v).double() for k, v in Ps.items()}
     ref = O.decoder(Pt, O.encoder(Pt, torch.from_numpy(x).double().permute(0, 3, 1, 2))).permute(0, 2, 3, 1)
     assert torch.allclose(outs['x_hat'], ref)
+
+
+def test_lesion_wise_detection_rate_and_summary():
+    """utils/Evaluation.compute_detection_rate / summarize_predictions (reference Evaluation.py:130-172, 463-500; skimage label /
+    regionprops restated on scipy.ndimage): hand-built volumes with known lesion counts."""
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation as Ev
+    gt = np.zeros((25, 16, 16), bool)
+    pred = np.zeros_like(gt)
+    gt[2:5, 2:5, 2:5] = True             # lesion A: detected
+    pred[3:6, 3:6, 3:6] = True
+    gt[10:12, 8:11, 8:11] = True         # lesion B: missed
+    pred[8:10, 1:4, 12:15] = True        # 18-voxel false positive
+    pred[14, 14, 14] = True              # 1-voxel false positive: dropped (< 8 voxels)
+    gt[21:24, 4:8, 4:8] = True           # lesion C (second block of 20 slices): detected
+    pred[22:24, 5:9, 5:9] = True
+    pred[0, 0, 0] = pred[1, 1, 1] = True  # 26-connected with nothing else of size: a 2-voxel component, dropped
+    assert Ev.compute_detection_rate(pred, gt) == (2, 1, 1)
+    # a lesion straddling the block boundary is seen once per block, as in the reference's per-block labelling
+    gt2 = np.zeros((25, 8, 8), bool)
+    gt2[18:22, 2:5, 2:5] = True
+    assert Ev.compute_detection_rate(gt2.copy(), gt2) == (2, 0, 0)
+    assert Ev.compute_detection_rate(np.zeros_like(gt2), gt2) == (0, 0, 2)
+    # summary over two "patients" stacked along the slice axis
+    preds, gts = np.concatenate([pred, np.zeros_like(pred)]), np.concatenate([gt, gt])
+    ev = Ev.summarize_predictions({}, gts.astype(np.uint8), preds, preds, 2, 25, 'bestdice')
+    assert ev['thresholdType'] == 'bestdice' and (ev['TPCC'], ev['FPCC'], ev['FNCC']) == (2, 1, 1 + 3)
+    assert ev['TPRCC'] == 2 / 6 and ev['PrecisionCC'] == 2 / 3
+    tp = int((preds & gts).sum())
+    assert (ev['TP'], ev['FP'], ev['FN'], ev['TN']) == (tp, int(preds.sum()) - tp, int(gts.sum()) - tp, gts.size - int((preds | gts).sum()))
+    assert ev['DiceScore'] == pytest.approx(2 * tp / (preds.sum() + gts.sum()))
+    assert ev['DiceScorePerPatient'][0] == pytest.approx(2 * tp / (pred.sum() + gt.sum())) and ev['DiceScorePerPatient'][1] == 0
+    assert ev['RecallPerPatient'] == [pytest.approx(tp / gt.sum()), 0.0] and np.isnan(ev['PrecisionPerPatient'][1])
+    assert ev['TPR'] == ev['FPR'] == pytest.approx(tp / gts.sum())            # (sic) the reference's FPR is Metrics.tpr
+    assert ev['VD'] == pytest.approx((gts.sum() - tp) / gts.sum())
+    assert ev['DiceScorePerPatientMean'] == pytest.approx(np.mean(ev['DiceScorePerPatient']))
+
+
+def test_evaluate_orchestration_keys_and_files(tmp_path, monkeypatch):
+    """utils/Evaluation.evaluate with the device pieces replaced by numpy stand-ins (a scorer that answers `diffs > t` counts, a
+    canned _evaluate): the result carries the reference's evalPC keys (Evaluation.py:440-526), the files land in the reference's
+    eval-<epoch>-<timestamp>-<description> directory, and the numbers agree with a direct numpy evaluation."""
+    import types
+
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation as Ev
+    rng = np.random.default_rng(0)
+    n_pat, Z, S = 2, 20, 24
+    labels = np.zeros((n_pat * Z, S, S), np.uint8)
+    labels[3:7, 5:10, 5:10] = 1
+    labels[Z + 8:Z + 12, 12:18, 10:15] = 1
+    diffs = (0.02 * rng.random((n_pat * Z, S, S))).astype(np.float32)
+    diffs[labels > 0] += (0.05 + 0.1 * rng.random(int(labels.sum()))).astype(np.float32)
+    diffs[Z + 2:Z + 4, 2:5, 2:5] = 0.2                                   # a false-positive blob
+    diffs64 = diffs.astype(np.float64)
+
+    class NumpyScorer:
+        def __init__(self, predictions, lab, device=None, allreduce=None):
+            self.d, self.l = np.asarray(predictions, np.float64).reshape(-1), np.asarray(lab).reshape(-1) != 0
+
+        def dice_scores(self, thresholds):
+            out = []
+            for t in thresholds:
+                p = self.d > t
+                with np.errstate(divide='ignore', invalid='ignore'):
+                    out.append(np.float64(2 * np.sum(p & self.l)) / np.float64(p.sum() + self.l.sum()))
+            return out
+
+        def threshold_mask(self, t):
+            import torch
+            return torch.from_numpy((self.d > t).astype(np.uint8))
+
+    def fake_evaluate(datasetObj, modelObj, sampleDir, options, split='TEST', shard=None):
+        ev = Ev.get_eval_dictionary()
+        ev.update(x=diffs64 * 0, reconstructions=diffs64 * 0, diffs=diffs64, labelmaps=labels, l1reconstructionErrorMean=1.0,
+                  reconstructionTimes=0.001)
+        return ev, [{'name': 'p0'}, {'name': 'p1'}]
+
+    monkeypatch.setattr(Ev, '_evaluate', fake_evaluate)
+    monkeypatch.setattr(Ev.Metrics, 'DeviceScorer', NumpyScorer)
+    model = types.SimpleNamespace(network=types.SimpleNamespace(__name__='variational_autoencoder'), model_dir='VAE_test', device='cpu', world=1)
+    options = {'train': {'samplesDir': str(tmp_path)}, 'threshold': 'bestdice', 'exportROC': True, 'exportPRC': True,
+               'sliceStart': 20, 'sliceEnd': 40}
+    ev = Ev.evaluate(None, model, options, epoch='3', description='SYNTHETIC-bestdice')
+    ref_keys = {'diff_AUC', 'diff_AUPRC', 'bestDiceScore', 'bestThreshold', 'thresholdType', 'DiceScore', 'DiceScorePerPatient',
+                'PrecisionPerPatient', 'RecallPerPatient', 'DiceScorePerPatientMean', 'DiceScorePerPatientStd', 'PrecisionPerPatientMean',
+                'PrecisionPerPatientStd', 'RecallPerPatientMean', 'RecallPerPatientStd', 'TP', 'FP', 'TN', 'FN', 'TPR', 'FPR', 'VD', 'TPCC',
+                'FPCC', 'FNCC', 'TPRCC', 'PrecisionCC'}
+    assert ref_keys <= set(ev), ref_keys - set(ev)
+    d = ev['evalDir']
+    assert os.path.basename(d).startswith('eval-3-') and d.endswith('-SYNTHETIC-bestdice')
+    assert os.path.dirname(d) == os.path.join(str(tmp_path), 'variational_autoencoder', 'VAE_test')
+    for f in ('rocPC.npy', 'prcPC.npy', 'evalPC.npy', 'evalPC.txt'):
+        assert os.path.isfile(os.path.join(d, f)), f
+    assert os.path.isdir(os.path.join(d, 'samples_test_PC'))
+    stored = np.load(os.path.join(d, 'evalPC.npy'), allow_pickle=True).item()
+    assert ref_keys <= set(stored) and 'diffs' not in stored and 'x' not in stored
+    roc = np.load(os.path.join(d, 'rocPC.npy'), allow_pickle=True).item()
+    assert set(roc) == {'fpr', 'tpr', 'threshs'}
+    # numbers: the best-Dice threshold separates lesions (> 0.05) from background (< 0.02) and the blob (0.2) is a false positive
+    assert 0.02 <= ev['bestThreshold'] < 0.05 and ev['thresholdType'] == 'bestdice'
+    mask = Ev.filter_3d_connected_components((diffs64 > ev['bestThreshold']).copy())
+    tp = int((mask & (labels > 0)).sum())
+    assert ev['TP'] == tp and ev['FN'] == int(labels.sum()) - tp and ev['FP'] == 18
+    assert ev['DiceScore'] == pytest.approx(2 * tp / (mask.sum() + labels.sum())) == ev['DICE']
+    assert (ev['TPCC'], ev['FNCC']) == (2, 0) and ev['TPRCC'] == 1.0
+    assert ev['diff_AUC'] > 0.99 and ev['AUC'] == ev['diff_AUC']
+    # a fixed threshold: thresholdType records it and the lesion-wise rate is taken at that operating point
+    options['threshold'] = 0.1
+    ev2 = Ev.evaluate(None, model, options, epoch='3')
+    assert ev2['thresholdType'] == 0.1 and ev2['threshold'] == 0.1 and not ev2['evalDir'].endswith('bestdice')
+    assert ev2['FPCC'] == 1

@@ -5,9 +5,11 @@ Device side (hand-written kernels through the C ABI):
     per slice with batch 1: Evaluation.py:246-250),
   * the residual / brain-mask / hyper-intensity-prior arithmetic (:282-291) -> ``uad_residual_score``,
   * ``diffs > t`` + Dice counts for every candidate threshold (:444-457, Metrics.py:138-162) -> ``uad_threshold_counts``.
-Host side (kept in scipy / sklearn exactly like the reference): brain-mask erosion (:84-89), 5x5x5 median filter
-(:108-110), connected-component filter (:113-127, scipy.ndimage.label because skimage is absent), ROC / PRC.
-PNG / NIfTI export and plots are out of scope (SURVEY 2 #17)."""
+Host side (scipy / sklearn like the reference; skimage's label / regionprops restated on scipy.ndimage): connected-component
+filter (:113-127), lesion-wise detection rate (:130-172), ROC / PRC and their .npy exports, the per-patient Dice / precision /
+recall, confusion counts and the evalPC.npy / evalPC.txt summary with the reference's keys (:440-526).  PNG exports and
+matplotlib plots are not reproduced."""
+import math
 import os
 import time
 
@@ -60,6 +62,96 @@ def filter_3d_connected_components(volume):
     if sz is not None:
         volume = np.reshape(volume, sz)
     return volume
+
+
+def is_float(s):
+    try:
+        float(s)
+        return True
+    except (TypeError, ValueError):
+        return False
+
+
+def export_patient_volume(nii_seg, subvolume, zoom_factor, dataset_options, options, sample_dir, patient_name):
+    """options['exportVolumes'] (Evaluation.py:323-334): the residual sub-volume, resampled back to the native slice resolution,
+    written into a copy of the patient's volume geometry as <name>.nii.gz (+ <name>.binary.nii.gz for a numeric threshold).
+    Needs a volume object with the NII interface (utils/NII.py); returns the paths written."""
+    dezoom = (1,) + tuple(1 / np.asarray(zoom_factor, np.float64)) if zoom_factor is not None else (1, 1, 1)
+    restored = scipy.ndimage.zoom(subvolume, dezoom)
+    nii_seg.set_to_zero()
+    nii_seg.cast_to_float()
+    end = min(dataset_options.sliceEnd, dataset_options.sliceStart + restored.shape[0])
+    nii_seg.set_subvolume(dataset_options.sliceStart, end, restored, axis=dataset_options.axis)
+    paths = [os.path.join(sample_dir, '{}.nii.gz'.format(patient_name))]
+    nii_seg.save(paths[0])
+    if options.get('threshold') and is_float(options['threshold']):
+        nii_seg.data = np.asarray(nii_seg.data > float(options['threshold'])).astype(np.float32)
+        paths.append(os.path.join(sample_dir, '{}.binary.nii.gz'.format(patient_name)))
+        nii_seg.save(paths[1])
+    return paths
+
+
+def compute_detection_rate(predicted_volume, groundtruth_volume):
+    """Lesion-wise true / false positives and false negatives (Evaluation.py:130-172), in blocks of 20 slices: connected
+    components (skimage.measure.label's default = full connectivity) of prediction AND ground truth are the true positives;
+    predicted components of fewer than 8 voxels are dropped; every component touched by a true positive is removed from the
+    prediction / ground truth, what remains are the false positives / false negatives."""
+    full = np.ones((3, 3, 3))
+    tps = fns = fps = 0
+    pred = np.asarray(predicted_volume).astype(bool)
+    gt = np.asarray(groundtruth_volume).astype(bool)
+    num_slices = gt.shape[0]
+    inter = pred & gt
+    for s in range(int(math.ceil(num_slices / 20))):
+        sl = slice(s * 20, min((s + 1) * 20, num_slices))
+        cc_i, n_i = scipy.ndimage.label(inter[sl], structure=full)
+        cc_p, n_p = scipy.ndimage.label(pred[sl], structure=full)
+        cc_g, _ = scipy.ndimage.label(gt[sl], structure=full)
+        if n_p:
+            areas = np.bincount(cc_p.ravel(), minlength=n_p + 1)
+            small = np.flatnonzero(areas < 8)
+            cc_p[np.isin(cc_p, small[small > 0])] = 0
+        for lab in range(1, n_i + 1):
+            first = np.argwhere(cc_i == lab)[0]                       # regionprops' coords[0]: first voxel in row-major order
+            lp = cc_p[tuple(first)]
+            cc_p[cc_p == lp] = 0                                      # (lp == 0, a dropped small component, clears nothing new)
+            lg = cc_g[tuple(first)]
+            cc_g[cc_g == lg] = 0
+        tps += n_i
+        fns += len(np.unique(cc_g)) - (1 if (cc_g == 0).any() else 0)
+        fps += len(np.unique(cc_p)) - (1 if (cc_p == 0).any() else 0)
+    return tps, fps, fns
+
+
+def summarize_predictions(eval_pc, labelmaps, diffs_thresholded, diffs_thresholded_at_precision70, num_patients, num_slices,
+                          threshold_type):
+    """The per-patient / lesion-wise / confusion statistics of the reference's evaluate() (Evaluation.py:463-500), same keys."""
+    labels = np.asarray(labelmaps).astype(bool)
+    eval_pc['thresholdType'] = threshold_type
+    eval_pc['DiceScore'] = Metrics.dice(diffs_thresholded, labelmaps)
+    eval_pc['DiceScorePerPatient'], eval_pc['PrecisionPerPatient'], eval_pc['RecallPerPatient'] = [], [], []
+    eval_pc['TPCC'] = eval_pc['FPCC'] = eval_pc['FNCC'] = 0
+    with np.errstate(divide='ignore', invalid='ignore'):
+        for p in range(num_patients):
+            sl = slice(p * num_slices, (p + 1) * num_slices)
+            pred, gt = diffs_thresholded[sl], labels[sl]
+            eval_pc['DiceScorePerPatient'] += [Metrics.dice(pred, gt)]
+            eval_pc['PrecisionPerPatient'] += [Metrics.precision(pred, gt)]
+            eval_pc['RecallPerPatient'] += [Metrics.recall(pred, gt)]
+            tps, fps, fns = compute_detection_rate(np.squeeze(diffs_thresholded_at_precision70[sl]), np.squeeze(gt))
+            eval_pc['TPCC'] += tps
+            eval_pc['FPCC'] += fps
+            eval_pc['FNCC'] += fns
+        for key in ('DiceScore', 'Precision', 'Recall'):
+            vals = np.array(eval_pc[key + 'PerPatient'])
+            eval_pc[key + 'PerPatientMean'], eval_pc[key + 'PerPatientStd'] = np.mean(vals), np.std(vals)
+        eval_pc['TP'], eval_pc['FP'], eval_pc['TN'], eval_pc['FN'] = Metrics.confusion_matrix(diffs_thresholded, labels)
+        eval_pc['TPR'] = Metrics.tpr(diffs_thresholded, labels)
+        eval_pc['FPR'] = Metrics.tpr(diffs_thresholded, labels)      # sic: the reference computes FPR with Metrics.tpr (:490)
+        eval_pc['VD'] = Metrics.vd(diffs_thresholded, labels)
+    eval_pc['TPRCC'] = eval_pc['TPCC'] / (eval_pc['TPCC'] + eval_pc['FNCC']) if eval_pc['TPCC'] + eval_pc['FNCC'] > 0 else 0.0
+    eval_pc['PrecisionCC'] = eval_pc['TPCC'] / (eval_pc['TPCC'] + eval_pc['FPCC']) if eval_pc['TPCC'] + eval_pc['FPCC'] > 0 else 0.0
+    return eval_pc
 
 
 def residual_on_device(x, x_rec, mask, prior_quantile, keep_positive, apply_prior, device):
@@ -119,6 +211,7 @@ def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST", shard=None
             slice_start = datasetObj.options.sliceStart or 0
             slice_end = min(datasetObj.options.sliceEnd, nii.num_slices_along_axis(datasetObj.options.axis))
             xs, segs, skulls = [], [], []
+            zoom_factor = None
             for s in range(slice_start, slice_end):
                 slice_data = nii.get_slice(s, datasetObj.options.axis)
                 slice_seg = nii_seg.get_slice(s, datasetObj.options.axis).astype(int)
@@ -155,6 +248,8 @@ def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST", shard=None
                 eval_dict['l1reconstructionErrors'] += [np.sum(np.abs(x[i] - x_rec[i]))]
                 eval_dict['l2reconstructionErrors'] += [np.sum(np.sqrt((x[i] - x_rec[i]) ** 2))]
             eval_dict['diffs'] += [subvolume]
+            if should(options, 'exportVolumes') and hasattr(nii_seg, 'set_subvolume'):
+                export_patient_volume(nii_seg, subvolume, zoom_factor, datasetObj.options, options, sampleDir, patient['name'])
             done = True
     eval_dict['x'] = np.squeeze(np.array(eval_dict['x']))
     eval_dict['reconstructions'] = np.squeeze(np.array(eval_dict['reconstructions']))
@@ -181,9 +276,17 @@ def _dp_context(model):
 
 
 def evaluate(datasetPC, gan, options, epoch='last', description=None):
-    """Evaluation.py:372-526 minus file export / plots: returns the evalPC dictionary (also saved as evalPC.npy)."""
+    """Evaluation.py:372-526 minus PNG export / plots: returns the evalPC dictionary with the reference's keys (plus the short
+    aliases DICE / AUC / AUPRC / Precision used by run.py) and writes rocPC.npy, prcPC.npy, evalPC.npy, evalPC.txt into the
+    reference's directory layout <samplesDir>/<network>/<model_dir>/eval-<epoch>-<timestamp>[-<description>]/."""
     model = gan
-    sample_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir, str(description or ''))
+    _time = {'evaluation': time.time()}
+    histogram_range = (0.01, 0.075)
+    eval_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir,
+                            'eval-' + str(epoch) + '-' + time.strftime('%Y-%m-%d %H-%M-%S'))
+    if description is not None:
+        eval_dir += '-' + str(description)
+    sample_dir = os.path.join(eval_dir, 'samples_test_PC')
     os.makedirs(sample_dir, exist_ok=True)
     shard, reduce_ = _dp_context(model)
     eval_pc, patients = _evaluate(datasetPC, model, sample_dir, options, "TEST", shard=shard)
@@ -191,41 +294,59 @@ def evaluate(datasetPC, gan, options, epoch='last', description=None):
     labels = (eval_pc['labelmaps'] > 0)
     scorer = Metrics.DeviceScorer(diffs, labels, device=model.device, allreduce=reduce_)
     flat_d, flat_l = diffs.flatten(), labels.flatten().astype(int)
+    eval_pc['diffHistogram'], _ = np.histogram(diffs, bins='auto', range=histogram_range)
+    if len(eval_pc.get('epistemic_variance', [])) > 0:
+        ev = np.asarray(eval_pc['epistemic_variance'])
+        eval_pc['uncertaintyHistogram'], _ = np.histogram(ev, bins=50, range=(1e-5, np.percentile(ev[ev >= 0], 99.8)))
+    t0 = time.time()
+    eval_pc['diff_AUC'], _fpr, _tpr, _roc_threshs = Metrics.compute_roc(flat_d, flat_l)
+    _time['ROC'] = time.time() - t0
     if should(options, 'exportROC'):
-        eval_pc['AUC'], _fpr, _tpr, _ = Metrics.compute_roc(flat_d, flat_l)
+        np.save(os.path.join(eval_dir, 'rocPC.npy'), {'fpr': _fpr, 'tpr': _tpr, 'threshs': _roc_threshs}, allow_pickle=True)
+    t0 = time.time()
+    eval_pc['diff_AUPRC'], _precisions, _recalls, _threshs = Metrics.compute_prc(flat_d, flat_l)
+    _time['PRC'] = time.time() - t0
     if should(options, 'exportPRC'):
-        eval_pc['AUPRC'], _p, _r, _ = Metrics.compute_prc(flat_d, flat_l)
+        np.save(os.path.join(eval_dir, 'prcPC.npy'), {'precisions': _precisions, 'recalls': _recalls, 'threshs': _threshs}, allow_pickle=True)
+    eval_pc['AUC'], eval_pc['AUPRC'] = eval_pc['diff_AUC'], eval_pc['diff_AUPRC']
+    # operating point at (at most) 70 % precision for the lesion-wise detection rate (:438-440)
+    idx_precision70 = min(int(np.argmax(_precisions <= 0.7)), len(_threshs) - 1)
+    mask70 = filter_3d_connected_components(np.squeeze(diffs > _threshs[idx_precision70]).copy())
     t0 = time.time()
     best_dice, best_thresh = Metrics.compute_dice_curve_recursive(diffs, labels, granularity=10, scorer=scorer)
-    eval_pc['diceSearchTime'] = time.time() - t0
+    eval_pc['diceSearchTime'] = _time['DiceCurve'] = time.time() - t0
     eval_pc['bestDiceScore'], eval_pc['bestThreshold'] = best_dice, best_thresh
     threshold = best_thresh if options['threshold'] == 'bestdice' else float(options['threshold'])
     eval_pc['threshold'] = threshold
     mask = scorer.threshold_mask(threshold).cpu().numpy().astype(bool).reshape(diffs.shape)     # == diffs > threshold, bit-exact
-    mask = filter_3d_connected_components(mask.copy())
+    if options['threshold'] != 'bestdice':
+        mask70 = mask
+    mask = filter_3d_connected_components(np.squeeze(mask).copy())
     eval_pc['thresholded'] = mask
-    if reduce_ is None:
-        eval_pc['DICE'] = Metrics.dice(mask, labels)
-        eval_pc['TPR'] = Metrics.tpr(mask, labels)
-        eval_pc['FPR'] = Metrics.tpr(mask, labels)      # sic: the reference computes FPR with Metrics.tpr (Evaluation.py:490)
+    n_per = diffs.shape[0] // max(len(patients), 1)
+    summarize_predictions(eval_pc, eval_pc['labelmaps'], mask, mask70, len(patients), n_per, options['threshold'])
+    eval_pc['DICE'], eval_pc['perPatientDice'] = eval_pc['DiceScore'], list(eval_pc['DiceScorePerPatient'])
+    with np.errstate(divide='ignore', invalid='ignore'):
         eval_pc['Precision'] = Metrics.precision(mask, labels)
-    else:                                               # same formulas on the rank-summed integer counts
-        tp, fp, tn, fn = (int(v) for v in Metrics.confusion_matrix(mask, labels))
-        c = torch.tensor([tp, fp, tn, fn], dtype=torch.int64, device=model.device)
+    if reduce_ is not None:                             # data-parallel scoring: the pooled figures from the rank-summed integer counts
+        c = torch.tensor([int(eval_pc[k]) for k in ('TP', 'FP', 'TN', 'FN', 'TPCC', 'FPCC', 'FNCC')], dtype=torch.int64, device=model.device)
         reduce_(c)
-        tp, fp, tn, fn = (np.int64(v) for v in c.cpu().numpy())
+        tp, fp, tn, fn, tpcc, fpcc, fncc = (np.int64(v) for v in c.cpu().numpy())
+        eval_pc.update(TP=tp, FP=fp, TN=tn, FN=fn, TPCC=int(tpcc), FPCC=int(fpcc), FNCC=int(fncc))
         with np.errstate(divide='ignore', invalid='ignore'):
-            eval_pc['DICE'] = (2 * tp) / ((tp + fp) + (tp + fn))
+            eval_pc['DICE'] = eval_pc['DiceScore'] = (2 * tp) / ((tp + fp) + (tp + fn))
             eval_pc['TPR'] = eval_pc['FPR'] = tp / (tp + fn)
             eval_pc['Precision'] = tp / (tp + fp)
-    n_per = diffs.shape[0] // max(len(patients), 1)
-    eval_pc['perPatientDice'] = [Metrics.dice(mask[i * n_per:(i + 1) * n_per], labels[i * n_per:(i + 1) * n_per])
-                                 for i in range(len(patients))]
-    np.save(os.path.join(sample_dir, 'evalPC.npy'), {k: v for k, v in eval_pc.items() if np.ndim(v) == 0})
-    with open(os.path.join(sample_dir, 'evalPC.txt'), 'w') as f:
-        for k, v in eval_pc.items():
-            if np.ndim(v) == 0:
-                f.write(f'{k}: {v}\n')
+        eval_pc['TPRCC'] = tpcc / (tpcc + fncc) if tpcc + fncc > 0 else 0.0
+        eval_pc['PrecisionCC'] = tpcc / (tpcc + fpcc) if tpcc + fpcc > 0 else 0.0
+    _time['evaluation'] = time.time() - _time['evaluation']
+    eval_pc['evalDir'] = eval_dir
+    big = ('x', 'diffs', 'labelmaps', 'l1reconstructionErrors', 'l2reconstructionErrors', 'reconstructions', 'diffHistogram', 'thresholded',
+           'epistemic_variance')
+    stored = {k: v for k, v in eval_pc.items() if k not in big}
+    np.save(os.path.join(eval_dir, 'evalPC.npy'), stored)
+    with open(os.path.join(eval_dir, 'evalPC.txt'), 'w') as f:
+        f.write(str(stored))
     return eval_pc
 
 
