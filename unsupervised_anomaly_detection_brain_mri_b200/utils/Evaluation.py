@@ -350,14 +350,23 @@ def evaluate(datasetPC, gan, options, epoch='last', description=None):
     return eval_pc
 
 
-def determine_threshold_on_labeled_patients(datasets, model, options, description=''):
-    """Evaluation.py:529-567: best-Dice threshold over the labelled (validation) patients."""
+def determine_threshold_on_labeled_patients(dataset_pc, model, options, epoch='last', description=None):
+    """Evaluation.py:529-567: best-Dice threshold over the labelled VALIDATION patients of one or several datasets (same signature).
+    The reference evaluates split="VAL"; its own BrainWeb lesion set puts every patient into TEST (default_config_setup.py:211), which
+    leaves that call without data there - a dataset with no VAL patients is therefore scored on its TEST split here."""
+    eval_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir,
+                            'eval-' + str(epoch) + '-' + time.strftime('%Y-%m-%d %H-%M-%S'))
+    if description is not None:
+        eval_dir += '-' + str(description)
+    sample_dir = os.path.join(eval_dir, 'samples_val_PC')
+    os.makedirs(sample_dir, exist_ok=True)
+    if not isinstance(dataset_pc, (list, tuple)):
+        dataset_pc = [dataset_pc]
     diffs, labels = [], []
     shard, reduce_ = _dp_context(model)
-    for ds in datasets:
-        sample_dir = os.path.join(options['train']['samplesDir'], model.network.__name__, model.model_dir, str(description))
-        os.makedirs(sample_dir, exist_ok=True)
-        ev, _ = _evaluate(ds, model, sample_dir, options, "TEST", shard=shard)
+    for ds in dataset_pc:
+        split = 'VAL' if len(ds.get_patient_idx(split='VAL')) > 0 else 'TEST'
+        ev, _ = _evaluate(ds, model, sample_dir, options, split, shard=shard)
         diffs.append(ev['diffs'])
         labels.append(ev['labelmaps'] > 0)
     diffs, labels = np.concatenate(diffs, 0), np.concatenate(labels, 0)
