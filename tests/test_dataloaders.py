@@ -153,8 +153,8 @@ def test_nii_wrapper_semantics(tmp_path):
     r.data[:] = 3
     r.set_to_zero()
     assert not r.get_data().any()
-    with pytest.raises(NotImplementedError):
-        r.denoise()
+    r.denoise()                                                               # constant volume: a fixed point of the curvature flow
+    assert not r.get_data().any()
 
 
 # ---------------------------------------------------------------------------------------------------- MINC-1
@@ -458,5 +458,114 @@ def test_export_patient_volume_writes_nifti_in_native_geometry(tmp_path):
         assert set(np.unique(binary.data)) == {0.0, 1.0} and binary.data[5, 8:12, 10:16].all()
         only = Ev.export_patient_volume(NII(data=np.zeros((12, 20, 24))), sub, (0.5, 0.5), opts, {'threshold': 'bestdice'}, str(tmp_path), 'q')
         assert len(only) == 1
+    finally:
+        NII.set_view_mapping({'saggital': 0, 'coronal': 1, 'axial': 2})
+
+
+# ---------------------------------------------------------------------------------------------------- NIfTI lesion datasets
+def test_curvature_flow_is_mean_curvature_motion():
+    """NII.denoise restates SimpleITK's CurvatureFlow (I_t = kappa |grad I|): on a radially symmetric bump f(r) the exact rate is
+    (n - 1) f'(r) / r; flat regions and constants are fixed points; spacing rescales the derivatives."""
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.NII import curvature_flow
+    n = 97
+    y, x = np.mgrid[0:n, 0:n] - 48.0
+    r = np.hypot(x, y)
+    img = np.exp(-r ** 2 / (2 * 12.0 ** 2))
+    out = curvature_flow(img, None, 0.125, 1)
+    rate = -r / 144.0 * img / np.maximum(r, 1e-9)
+    ring = (r > 5) & (r < 30)
+    assert np.abs((out - img)[ring] / 0.125 - rate[ring]).max() < 0.01 * np.abs(rate[ring]).max()
+    z, y, x = np.mgrid[0:41, 0:41, 0:41] - 20.0
+    r3 = np.sqrt(x * x + y * y + z * z)
+    vol = np.exp(-r3 ** 2 / (2 * 7.0 ** 2))
+    out3 = curvature_flow(vol, None, 0.125, 1)
+    rate3 = 2 * (-r3 / 49.0 * vol) / np.maximum(r3, 1e-9)
+    shell = (r3 > 3) & (r3 < 14)
+    assert np.abs((out3 - vol)[shell] / 0.125 - rate3[shell]).max() < 0.02 * np.abs(rate3[shell]).max()
+    assert np.array_equal(curvature_flow(np.full((5, 6, 7), 3.0)), np.full((5, 6, 7), 3.0))
+    ramp = np.tile(np.arange(16.0), (16, 1))                                     # straight level lines: zero curvature
+    assert np.abs(curvature_flow(ramp, None, 0.125, 3) - ramp).max() < 1e-12
+    half = curvature_flow(img, (2.0, 2.0), 0.125, 1)                              # doubled spacing: every derivative term scales by 1/4
+    assert np.abs((half - img)[ring] * 4 - (out - img)[ring]).max() < 1e-12
+    v = NII(data=vol)
+    v.denoise()
+    assert v.data.shape == vol.shape and 0 < np.abs(v.data - vol).max() < 0.05
+
+
+def _lesion_tree(tmp_path, kind):
+    rng = np.random.default_rng(5)
+    Zs, Ys, Xs = 10, 20, 24                                                      # [k, j, i] = axial slices first
+    names = []
+
+    def volume():
+        zz, yy, xx = np.mgrid[0:Zs, 0:Ys, 0:Xs]
+        brain = (((yy - Ys / 2) / (Ys / 2 - 1)) ** 2 + ((xx - Xs / 2) / (Xs / 2 - 1)) ** 2) < 1
+        brain[0] = False
+        img = (100 + 40 * rng.random((Zs, Ys, Xs))) * brain + 5 * rng.random((Zs, Ys, Xs))
+        gt = np.zeros((Zs, Ys, Xs), np.float32)
+        gt[4:6, 8:12, 10:14] = 1
+        return img.astype(np.float32), gt, brain.astype(np.float32)
+
+    root = tmp_path / kind
+    for p in range(4):
+        img, gt, brain = volume()
+        if kind == 'MSLUB':
+            d = root / 'data' / f'patient{p:02d}'
+            files = {f'patient{p:02d}_FLAIR.aligned.nii.gz': img, f'patient{p:02d}_T1W.aligned.nii.gz': img * 0.5,
+                     f'patient{p:02d}_T1WKS.aligned.nii.gz': img, f'patient{p:02d}_T2W.aligned.nii.gz': img,
+                     f'patient{p:02d}_consensus_gt.aligned.nii.gz': gt, f'patient{p:02d}_brainmask.aligned.nii.gz': brain}
+        elif kind == 'MSISBI2015':
+            folder = f'training0{p + 1}'
+            d = root / folder / 'preprocessed'
+            nm = f'{folder}_01'
+            files = {f'{nm}_flair_pp.nii': img, f'{nm}_flair.aligned.nii.gz': img, f'{nm}_mask1.aligned.nii.gz': gt,
+                     f'{nm}_skullmap.aligned.nii.gz': brain}
+        else:
+            d = root / ('UNC_train' if p < 3 else 'CHB_train') / f'case{p:02d}'
+            nm = f'case{p:02d}'
+            files = {f'{nm}_FLAIR.aligned.nii.gz': img, f'{nm}_T1.aligned.nii.gz': img, f'{nm}_T2.aligned.nii.gz': img,
+                     f'{nm}_lesion.aligned.nii.gz': gt, f'{nm}_skullmap.nii.gz': brain}
+        os.makedirs(d)
+        for fn, arr in files.items():
+            write_nifti(str(d / fn), arr)
+        names.append(d)
+    return str(root)
+
+
+@pytest.mark.parametrize('kind', ['MSLUB', 'MSISBI2015', 'MSSEG2008'])
+def test_lesion_datasets_through_get_datasets(tmp_path, kind):
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import default_config_setup as cfg
+    root = _lesion_tree(tmp_path, kind)
+    globals_ = {'CHECKPOINTDIR': str(tmp_path / 'c'), 'SAMPLEDIR': str(tmp_path / 's'), 'MSLUBDIR': '', 'MSISBI2015DIR': '', 'MSSEG2008DIR': '',
+                'BRAINWEBDIR': ''}
+    globals_[kind + 'DIR'] = root
+    options = cfg.get_options(batchsize=2, learningrate=1e-4, numEpochs=1, zDim=16, outputWidth=32, outputHeight=32, slices_start=1,
+                              slices_end=9, config=globals_)
+    member = {'MSLUB': cfg.Dataset.MSLUB, 'MSISBI2015': cfg.Dataset.MSISBI2015, 'MSSEG2008': cfg.Dataset.MSSEG2008_UNC}[kind]
+    np.random.seed(3)
+    try:
+        hc, pc = cfg.get_datasets(options, member)
+        assert hc is None and type(pc).__name__ == kind
+        n_pat = 3 if kind == 'MSSEG2008' else 4
+        assert len(pc.patients) == n_pat and all(len(p['filtered_files']) == 1 for p in pc.patients)       # FLAIR only
+        val, test = list(pc.get_patient_idx('VAL')), list(pc.get_patient_idx('TEST'))
+        assert len(pc.get_patient_idx('TRAIN')) == 0 and len(val) + len(test) == n_pat and not set(val) & set(test)
+        assert pc.images.shape[1:] == (32, 32, 1) and pc.images.dtype == np.float32 and pc.num_channels == 1
+        assert pc.images.shape[0] == n_pat * 8 and set(np.unique(pc.labels)) <= {0.0, 1.0} and pc.labels.any()
+        assert float(pc.images.max()) <= 1.0 + 1e-6 and float(pc.images.min()) == 0.0          # skull-stripped, scaled
+        assert os.path.isfile(pc.tfrecord_name()) and pc.name().endswith('_res32x32_aligned')
+        again = cfg.get_datasets(options, member)[1]                                  # second construction: cached TFRecord + stored split
+        np.testing.assert_array_equal(again.images, pc.images)
+        assert [list(again.get_patient_idx(s)) for s in pc.SET_TYPES] == [list(pc.get_patient_idx(s)) for s in pc.SET_TYPES]
+        x, y, m = pc.next_batch(4, set='TEST' if len(test) else 'VAL')                # (shuffles the set in place on its first call)
+        assert x.shape == (4, 32, 32, 1) and m.dtype == bool and m.shape == x.shape
+        # the evaluation protocol (utils/Evaluation._evaluate): axial slices of the [z, y, x] volume, binary ground truth, brain mask
+        patient = pc.patients[int(pc.get_patient_idx('TEST' if len(test) else 'VAL')[0])]
+        vol, seg, skull = pc.load_volume_and_groundtruth(patient['filtered_files'][0], patient)
+        assert vol.num_slices_along_axis('axial') == 10 and vol.get_slice(3, 'axial').shape == (20, 24)
+        assert set(np.unique(seg.data)) == {0.0, 1.0} and skull is not None and not vol.data[0].any()
+        options['globals'][kind + 'DIR'] = str(tmp_path / 'absent')
+        assert isinstance(cfg.get_datasets(options, member)[1], SYNTHETIC)
     finally:
         NII.set_view_mapping({'saggital': 0, 'coronal': 1, 'axial': 2})

@@ -7,8 +7,7 @@ reference (NII.py:23) - so VIEW_MAPPING {'saggital': 0, 'coronal': 1, 'axial': 2
 
 NIfTI-1 header fields used (nifti1.h): sizeof_hdr@0 (348; byte-swapped 348 => big-endian file), dim@40 (8 x int16),
 datatype@70, bitpix@72, pixdim@76 (8 x float32), vox_offset@108, scl_slope@112, scl_inter@116, qoffset_x/y/z@268,
-srow_x/y/z@280, magic@344 ('n+1\\0' single file).  Not implemented (the reference pipeline does not need them):
-denoise() (SimpleITK CurvatureFlow), visualize() (matplotlib)."""
+srow_x/y/z@280, magic@344 ('n+1\\0' single file).  denoise() restates SimpleITK's CurvatureFlow (see curvature_flow); visualize() (matplotlib) is not reproduced."""
 import copy
 import gzip
 import struct
@@ -82,6 +81,48 @@ def write_nifti(filename, data, origin=(0.0, 0.0, 0.0), spacing=(1.0, 1.0, 1.0))
     hdr[344:348] = b'n+1\x00'
     with _open(filename, 'wb') as f:
         f.write(bytes(hdr) + b'\x00' * 4 + a.tobytes())
+
+
+def curvature_flow(image, spacing=None, time_step=0.125, iterations=3):
+    """itk::CurvatureFlowImageFilter (N-D): per iteration, for every voxel
+        update = [ sum_i Ixx_i * sum_{j != i} Ix_j^2  -  2 sum_{i<j} Ix_i Ix_j Ixy_ij ] / |grad I|^2     (0 where |grad I|^2 < 1e-9)
+        I     <- I + time_step * update
+    first derivatives 0.5 (I[+1] - I[-1]) / h, second (I[+1] - 2 I + I[-1]) / h^2, cross 0.25 (I[--] - I[-+] - I[+-] + I[++]) / (h_i h_j);
+    neighbours outside the image replicate the edge voxel (ZeroFluxNeumannBoundaryCondition)."""
+    img = np.array(image, dtype=np.float64, copy=True)
+    nd = img.ndim
+    h = [1.0] * nd if spacing is None else [float(s) for s in spacing]
+
+    def shifted(p, offsets):
+        sl = tuple(slice(1 + o, p.shape[a] - 1 + o) for a, o in enumerate(offsets))
+        return p[sl]
+
+    for _ in range(int(iterations)):
+        p = np.pad(img, 1, mode='edge')
+        zero = [0] * nd
+        first, second = [], []
+        for i in range(nd):
+            plus, minus = list(zero), list(zero)
+            plus[i], minus[i] = 1, -1
+            first.append(0.5 * (shifted(p, plus) - shifted(p, minus)) / h[i])
+            second.append((shifted(p, plus) - 2.0 * img + shifted(p, minus)) / (h[i] * h[i]))
+        mag = sum(f * f for f in first)
+        update = np.zeros_like(img)
+        for i in range(nd):
+            update += second[i] * (mag - first[i] * first[i])
+        for i in range(nd):
+            for j in range(i + 1, nd):
+                o = [list(zero) for _ in range(4)]
+                o[0][i], o[0][j] = -1, -1
+                o[1][i], o[1][j] = -1, 1
+                o[2][i], o[2][j] = 1, -1
+                o[3][i], o[3][j] = 1, 1
+                cross = 0.25 * (shifted(p, o[0]) - shifted(p, o[1]) - shifted(p, o[2]) + shifted(p, o[3])) / (h[i] * h[j])
+                update -= 2.0 * first[i] * first[j] * cross
+        ok = mag >= 1e-9
+        update = np.where(ok, update / np.where(ok, mag, 1.0), 0.0)
+        img = img + time_step * update
+    return img
 
 
 class NII:
@@ -170,8 +211,17 @@ class NII:
     def set_to_zero(self):
         self.data.fill(0.0)
 
-    def denoise(self):
-        raise NotImplementedError('denoise() is SimpleITK.CurvatureFlow in the reference; not needed by the training / evaluation path')
+    def denoise(self, time_step=0.125, iterations=3):
+        """reference NII.py:82-84: sitk.CurvatureFlow(timeStep=0.125, numberOfIterations=3) - restated, not linked (SimpleITK 1.2.x is
+        a third-party dependency that is not installable here; this follows ITK's published itkCurvatureFlowFunction: explicit Euler
+        steps of  I_t = kappa |grad I|  with central differences scaled by 1 / spacing, zero-flux (edge-replicating) boundaries and
+        a zero update where |grad I|^2 < 1e-9).  NOT validated against ITK itself (none available): stated in DESIGN.md."""
+        self.data = curvature_flow(np.asarray(self.data, np.float64), self.spacing_of_axes(), time_step, iterations)
+
+    def spacing_of_axes(self):
+        """Voxel spacing per ARRAY axis: data is [k, j, i] for NIfTI voxel (i, j, k) whose pixdim is (di, dj, dk)."""
+        sp = tuple(float(v) if v else 1.0 for v in self.spacing)
+        return sp[::-1] if self.data.ndim == len(sp) else (1.0,) * self.data.ndim
 
     def copy(self):
         return copy.deepcopy(self)

@@ -4,6 +4,9 @@ import os
 from enum import Enum
 
 from ..dataloaders.BRAINWEB import BRAINWEB
+from ..dataloaders.MSISBI2015 import MSISBI2015
+from ..dataloaders.MSLUB import MSLUB
+from ..dataloaders.MSSEG2008 import MSSEG2008
 from ..dataloaders.SYNTHETIC import SYNTHETIC
 
 base_path = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -76,11 +79,18 @@ def get_synthetic_dataset_options(options, lesions, num_patients=None):
 def get_datasets(options, dataset: Dataset = Dataset.BRAINWEB):
     """(healthy train/val set, lesion test set) - reference default_config_setup.py:60-72.
     BRAINWEB with a real data directory (``<dir>/normal/*.mnc.gz`` present) goes through the BrainWeb loader exactly as the
-    reference configures it (:200-242).  Everything else - no data on disk, or the MSSEG2008 / MSISBI2015 / MSLUB members whose
-    loaders are not carried over - maps to the synthetic BrainWeb-shaped generator (healthy slices for training, slices with
-    lesions + labels for testing), which is also what the metric is defined on."""
+    reference configures it (:200-242); MSLUB / MSISBI2015 / MSSEG2008 with data on disk return (None, lesion set) as there
+    (:63-70, :78-194).  Without data on disk every member maps to the synthetic BrainWeb-shaped generator (healthy slices for
+    training, slices with lesions + labels for testing), which is also what the metric is defined on."""
     if dataset in (Dataset.BRAINWEB, Dataset.Brainweb) and has_brainweb_data(options.get('data', {}).get('dir')):
         return get_Brainweb_healthy_dataset(options), get_Brainweb_lesion_dataset(options)
+    g = options.get('globals', {})
+    if dataset == Dataset.MSLUB and os.path.isdir(os.path.join(g.get('MSLUBDIR', ''), 'data')):
+        return None, get_MSLUB_dataset(options)
+    if dataset == Dataset.MSISBI2015 and os.path.isdir(os.path.join(g.get('MSISBI2015DIR', ''), 'training01')):
+        return None, get_MSISBI2015_dataset(options)
+    if dataset.name.startswith('MSSEG2008') and os.path.isdir(os.path.join(g.get('MSSEG2008DIR', ''), dataset.name[-3:] + '_train')):
+        return None, get_MSSEG2008_dataset(options, dataset.name[-3:])
     hc = get_synthetic_dataset_options(options, lesions=False)
     hc.partition = {'TRAIN': 0.7, 'VAL': 0.3, 'TEST': 0.0}
     pc = get_synthetic_dataset_options(options, lesions=True, num_patients=options.get('data', {}).get('numTestPatients', 2))
@@ -92,6 +102,62 @@ def get_datasets(options, dataset: Dataset = Dataset.BRAINWEB):
 def has_brainweb_data(directory):
     import glob
     return bool(directory) and bool(glob.glob(os.path.join(directory, BRAINWEB.Options().folderNormal, '*.mnc.gz')))
+
+
+def _lesion_options(cls, options, directory, partition):
+    """The option block the reference repeats for its three NIfTI lesion sets (default_config_setup.py:87-114, 129-155, 169-194)."""
+    o = cls.Options()
+    o.description = ''
+    o.debug = options['debug']
+    o.dir = directory
+    o.useCrops = False
+    o.cropType = 'center'
+    o.cropWidth = options['train']['outputWidth']
+    o.cropHeight = options['train']['outputHeight']
+    o.numRandomCropsPerSlice = 5
+    o.rotations = [0]
+    o.partition = partition
+    o.sliceResolution = [options['train']['outputHeight'], options['train']['outputWidth']]
+    o.cache = True
+    o.numSamples = -1
+    o.addInstanceNoise = False
+    o.axis = 'axial'
+    o.filterProtocols = ['FLAIR']
+    o.normalizationMethod = 'scaling'
+    o.skullStripping = True
+    o.sliceStart = options['sliceStart']
+    o.sliceEnd = options['sliceEnd']
+    o.format = 'aligned'
+    return o
+
+
+def get_MSLUB_dataset_options(options):
+    return _lesion_options(MSLUB, options, options['globals']['MSLUBDIR'], {'TRAIN': 0, 'VAL': 5, 'TEST': 25})
+
+
+def get_MSLUB_dataset(options):
+    return MSLUB(get_MSLUB_dataset_options(options))
+
+
+def get_MSISBI2015_dataset_options(options):
+    o = _lesion_options(MSISBI2015, options, options['globals']['MSISBI2015DIR'], {'TRAIN': 0, 'VAL': 5, 'TEST': 15})
+    o.filterType = 'train'
+    return o
+
+
+def get_MSISBI2015_dataset(options):
+    return MSISBI2015(get_MSISBI2015_dataset_options(options))
+
+
+def get_MSSEG2008_dataset_options(options, filter_sanner):
+    o = _lesion_options(MSSEG2008, options, options['globals']['MSSEG2008DIR'], {'TRAIN': 0, 'VAL': 2, 'TEST': 8})
+    o.filterScanner = filter_sanner          # 'UNC' or 'CHB'
+    o.filterType = 'train'
+    return o
+
+
+def get_MSSEG2008_dataset(options, filter_sanner):
+    return MSSEG2008(get_MSSEG2008_dataset_options(options, filter_sanner))
 
 
 def get_Brainweb_healthy_dataset(options):
