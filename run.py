@@ -105,5 +105,10 @@ if __name__ == '__main__':
     args.add_argument('-T', '--tv_lambda', default=-1.0, type=float, help='only for VAE_You / GMVAE')
     args.add_argument('-K', '--kappa', default=1.0, type=float, help='only for GANs')
     args.add_argument('-M', '--scale', default=10.0, type=float, help='only for GANs')
+    args.add_argument('-R', '--rho', default=1.0, type=float, help='only for ConstrainedAAE')
+    args.add_argument('-C', '--dim_c', default=9, type=int, help='only for GMVAE')
+    args.add_argument('-Z', '--dim_z', default=128, type=int, help='only for GMVAE')
+    args.add_argument('-W', '--dim_w', default=1, type=int, help='only for GMVAE')
+    args.add_argument('-A', '--c_lambda', default=1, type=int, help='only for GMVAE')
     args.add_argument('--numPatients', default=0, type=int, help='synthetic dataset size (patients x 110 slices)')
     main(args.parse_args())

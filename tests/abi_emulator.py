@@ -470,10 +470,31 @@ def uad_dropout_mask(mask, n, rate, seed, offset, offset_dev, st):
 calls = []
 
 
+def check_signature(name, args):
+    """What ctypes would enforce on the GPU box: the argument COUNT and Python types of a call against abi.SIGNATURES (the
+    emulator bypasses ctypes, so a float where the ABI takes an int, a numpy scalar ctypes rejects, or a missing argument would
+    otherwise only surface on hardware)."""
+    import ctypes as C
+
+    from unsupervised_anomaly_detection_brain_mri_b200.abi import SIGNATURES
+    assert name in SIGNATURES, f'{name} has no ctypes signature in abi.SIGNATURES'
+    argtypes = SIGNATURES[name][1]
+    assert len(args) == len(argtypes), f'{name}: {len(args)} arguments, the ABI takes {len(argtypes)}'
+    for i, (a, t) in enumerate(zip(args, argtypes)):
+        if t is C.c_void_p:
+            ok = a is None or isinstance(a, torch.Tensor) or type(a) is int
+        elif t in (C.c_float, C.c_double):
+            ok = type(a) in (int, float) or isinstance(a, float)
+        else:                                                    # c_int, c_longlong, c_size_t, c_uint64
+            ok = type(a) is int and (a >= 0 or t in (C.c_int, C.c_longlong))
+        assert ok, f'{name}: argument {i} = {a!r} ({type(a).__name__}) does not fit {t.__name__}'
+
+
 def call(name, *args):
     fn = globals().get(name)
     if fn is None:
         raise NotImplementedError(f'abi_emulator: {name} is not modelled')
+    check_signature(name, args)
     calls.append(name)
     with torch.enable_grad():
         fn(*args)
