@@ -832,3 +832,35 @@ def test_emulator_reproduces_the_gpu_verified_restoration_step(arch, monkeypatch
     g_ref, out, tv_ref = O.restore_gradient(arch, P, x, eps=eps, tv_lambda=lam, dtype=torch.float64, sign_from=xh)
     assert _rel(xh, out['x_hat'].numpy()) < TOL and _rel(eng.tv.numpy(), tv_ref.numpy()) < TOL
     assert _rel(eng.restore_grads.numpy(), g_ref.numpy()) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ 7. data-parallel plumbing of the new engines
+@pytest.mark.parametrize('family', ['anovaegan', 'aae', 'caae'])
+def test_new_engines_data_parallel_equivalence(family, monkeypatch):
+    """Two identical ranks: the sum all-reduce of an op's gradient slices (here: x2) with grad_scale = 1 / world must leave exactly
+    the single-rank update - on every slice the op's Adam touches (three for the constrained AAE's optim_gen) and nowhere else."""
+    lr, rate = 1e-3, 0.2
+    results = []
+    for world in (1, 2):
+        if family == 'anovaegan':
+            eng, P, x, eps, alpha, masks = _anovaegan(monkeypatch, rate=rate, zDim=32)
+            ops = [('vae', eng.step_vae), ('gen', eng.step_gen), ('disc', eng.step_disc)]
+        else:
+            AA, eng, P, x, z, epsilon, masks = _aae(monkeypatch, rate=rate, constrained=family == 'caae')
+            ops = [('ae', eng.step_ae), ('disc', eng.step_disc), ('gen', eng.step_gen)]
+        reduced = []
+
+        def allreduce(t, _log=reduced):
+            _log.append(int(t.numel()))
+            t.mul_(2.0)
+        for name, step in ops:
+            step(lr, dropout_rate=rate, dropout=True, parity_noise=True, allreduce=allreduce if world == 2 else None, world=world)
+        results.append((eng.fp.to_numpy(), reduced, eng))
+    (w1, _, _), (w2, reduced, eng) = results
+    for k in w1:
+        assert np.allclose(w1[k], w2[k], rtol=0, atol=1e-9), k
+    if family == 'anovaegan':
+        assert reduced == [hi - lo for lo, hi in (eng.op_range('vae'), eng.op_range('gen'), eng.op_range('disc'))]
+    else:
+        want = [hi - lo for op in ('ae', 'disc', 'gen') for lo, hi in eng.rngs[op]]
+        assert reduced == want and len(want) == (5 if family == 'caae' else 3)
