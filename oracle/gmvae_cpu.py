@@ -120,3 +120,88 @@ def restore_gradient(P, x, eps_w, eps_z, tv_lambda, dim_c=9, c_lambda=1.0, dtype
         tv = ((d[:, 1:] - d[:, :-1]) * sv).sum(dim=(1, 2, 3)) + ((d[:, :, 1:] - d[:, :, :-1]) * sh).sum(dim=(1, 2, 3))
     total = (L['loss'] + tv_lambda * tv).sum()
     return torch.autograd.grad(total, xt)[0].detach(), {k: v.detach() for k, v in o.items()}
+
+
+# --------------------------------------------------------------------------- spatial variant
+def init_params_spatial(S, C=1, dim_z=1, dim_w=1, dim_c=9, res=8, seed=1):
+    """models/gaussian_mixture_variational_autoencoder_spatial.py:10-67.  The model opens no variable scope; the conv stacks keep this
+    repo's canonical Encoder/ | Decoder/ names, the explicitly named 1x1 heads keep the reference's (q_wz_x/..., p_z_wc/...)."""
+    from .tf_graph_cpu import AES
+    base = ae_init_params(AES, S, C, 128, res, seed)
+    rng = np.random.default_rng(seed + 3000)
+    ctop = [v.shape[3] for k, v in base.items() if k.startswith('Encoder/enc_conv2D_') and k.endswith('/kernel')][-1]
+    P = OrderedDict(base)
+    n = dim_z * dim_c
+    for name, cin, cout in (('q_wz_x/w_mu', ctop, dim_w), ('q_wz_x/w_log_sigma', ctop, dim_w), ('q_wz_x/z_mu', ctop, dim_z),
+                            ('q_wz_x/z_log_sigma', ctop, dim_z), ('p_z_wc/1x1convlayer', dim_w, 64), ('p_z_wc/z_wc_mu', 64, n),
+                            ('p_z_wc/z_wc_log_sigma', 64, n)):
+        P[name + '/kernel'] = _glorot(rng, (1, 1, cin, cout), cin, cout)
+        P[name + '/bias'] = np.zeros(cout, np.float32)
+    P['Variable'] = np.full(n, 0.1, np.float32)
+    return P
+
+
+def forward_spatial(P, x, eps_w, eps_z, dim_c=9, dtype=torch.float32):
+    """eps_w [B,r,r,dim_w], eps_z [B,r,r,dim_z] (NHWC).  No Dropout in this graph; the DECODER runs on the encoder output itself
+    (temp_out is never reassigned between the encoder and the decoder, :22-55): z only enters through the prior terms."""
+    P = {k: _t(v, dtype) for k, v in P.items()}
+    h = encoder(P, _t(x, dtype).permute(0, 3, 1, 2))
+    hn = h.permute(0, 2, 3, 1)                                            # NHWC: a 1x1 conv is a matmul on the channel axis
+
+    def c1(t, name):
+        return t @ P[name + '/kernel'][0, 0] + P[name + '/bias']
+    o = {}
+    o['w_mu'], o['w_log_sigma'] = c1(hn, 'q_wz_x/w_mu'), c1(hn, 'q_wz_x/w_log_sigma')
+    o['w_sampled'] = o['w_mu'] + _t(eps_w, dtype) * torch.exp(0.5 * o['w_log_sigma'])
+    o['z_mu'], o['z_log_sigma'] = c1(hn, 'q_wz_x/z_mu'), c1(hn, 'q_wz_x/z_log_sigma')
+    o['z_sampled'] = o['z_mu'] + _t(eps_z, dtype) * torch.exp(0.5 * o['z_log_sigma'])
+    mid = torch.relu(c1(o['w_sampled'], 'p_z_wc/1x1convlayer'))
+    B, r, dz = hn.shape[0], hn.shape[1], o['z_mu'].shape[3]
+    o['z_wc_mus'] = c1(mid, 'p_z_wc/z_wc_mu').reshape(B, r, r, dz, dim_c)
+    o['z_wc_log_sigma_invs'] = (c1(mid, 'p_z_wc/z_wc_log_sigma') + P['Variable']).reshape(B, r, r, dz, dim_c)
+    o['xz_mu'] = decoder(P, h).permute(0, 2, 3, 1)
+    zs = o['z_sampled'].unsqueeze(-1)
+    loglh = -0.5 * ((zs - o['z_wc_mus']) ** 2 * torch.exp(o['z_wc_log_sigma_invs'])) - o['z_wc_log_sigma_invs'] + np.log(np.pi)
+    o['pc_logit'] = loglh.sum(3)
+    o['pc'] = torch.softmax(o['pc_logit'], dim=-1)
+    return o
+
+
+def losses_spatial(o, x, dim_c=9, c_lambda=1.0, dtype=torch.float32, l1_sign=None):
+    """trainers/GMVAE_spatial.py:58-92: the GMVAE terms per spatial position, summed over the positions, batch means."""
+    xt = _t(x, dtype)
+    L = {}
+    diff = o['xz_mu'] - xt
+    L['L1'] = diff.abs() if l1_sign is None else diff * _t(l1_sign, dtype)
+    L['reconstructionLoss'] = L['mean_p_loss'] = L['L1'].sum(dim=(1, 2, 3)).mean()
+    zmu, zlv = o['z_mu'].unsqueeze(-1), o['z_log_sigma'].unsqueeze(-1)
+    d_var = (torch.exp(zlv) + (zmu - o['z_wc_mus']) ** 2) * (torch.exp(o['z_wc_log_sigma_invs']) + 1e-6)
+    kl = (d_var - (o['z_wc_log_sigma_invs'] + zlv) - 1) * 0.5
+    L['conditional_prior_loss'] = torch.matmul(kl, o['pc'].unsqueeze(-1)).squeeze(-1).sum(dim=(1, 2, 3)).mean()
+    L['w_prior_loss'] = (0.5 * (o['w_mu'] ** 2 + torch.exp(o['w_log_sigma']) - o['w_log_sigma'] - 1).sum(dim=(1, 2, 3))).mean()
+    closs1 = (o['pc'] * torch.log(o['pc'] * dim_c + 1e-8)).sum(3)
+    L['c_prior_loss'] = torch.maximum(closs1, torch.full_like(closs1, c_lambda)).sum(dim=(1, 2)).mean()
+    L['loss'] = L['mean_p_loss'] + L['conditional_prior_loss'] + L['w_prior_loss'] + L['c_prior_loss']
+    return L
+
+
+def loss_and_grads_spatial(P, x, eps_w, eps_z, dim_c=9, c_lambda=1.0, dtype=torch.float32, l1_sign=None):
+    Pt = OrderedDict((k, _t(v, dtype).clone().requires_grad_(True)) for k, v in P.items())
+    o = forward_spatial(Pt, x, eps_w, eps_z, dim_c, dtype)
+    L = losses_spatial(o, x, dim_c, c_lambda, dtype, l1_sign)
+    gs = torch.autograd.grad(L['loss'], list(Pt.values()))
+    return ({k: v.detach() for k, v in o.items()}, {k: v.detach() for k, v in L.items()},
+            OrderedDict((k, g.detach()) for k, g in zip(Pt, gs)))
+
+
+def restore_gradient_spatial(P, x, eps_w, eps_z, tv_lambda, dim_c=9, c_lambda=1.0, dtype=torch.float64, l1_sign=None, tv_sign=None):
+    xt = _t(x, dtype).clone().requires_grad_(True)
+    o = forward_spatial(P, xt, eps_w, eps_z, dim_c, dtype)
+    L = losses_spatial(o, xt, dim_c, c_lambda, dtype, l1_sign)
+    d = xt - o['xz_mu']
+    if tv_sign is None:
+        tv = total_variation(d)
+    else:
+        sv, sh = (_t(s, dtype) for s in tv_sign)
+        tv = ((d[:, 1:] - d[:, :-1]) * sv).sum(dim=(1, 2, 3)) + ((d[:, :, 1:] - d[:, :, :-1]) * sh).sum(dim=(1, 2, 3))
+    return torch.autograd.grad((L['loss'] + tv_lambda * tv).sum(), xt)[0].detach(), {k: v.detach() for k, v in o.items()}

@@ -864,3 +864,103 @@ def test_new_engines_data_parallel_equivalence(family, monkeypatch):
     else:
         want = [hi - lo for op in ('ae', 'disc', 'gen') for lo, hi in eng.rngs[op]]
         assert reduced == want and len(want) == (5 if family == 'caae' else 3)
+
+
+# ------------------------------------------------------------------------------------------------ 8. spatial GMVAE
+def _gmvaes(monkeypatch, S=32, B=2, dz=2, dw=1, dc=5, c_lambda=0.01):
+    from oracle import gmvae_cpu as GO
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    E.install(monkeypatch, eng_mod)
+    P = GO.perturb(GO.init_params_spatial(S, dim_z=dz, dim_w=dw, dim_c=dc, seed=1))
+    eng = eng_mod.ConvAutoencoderEngine(eng_mod.GMVAES, S, zDim=dz, batch=B, device='cpu', math_mode=0, dim_w=dw, dim_c=dc, c_lambda=c_lambda)
+    E.adopt(eng)
+    assert list(eng.specs) == list(P) and all(tuple(eng.specs[k]) == P[k].shape for k in P)
+    eng.fp.load(P)
+    E.poison(eng)
+    rng = np.random.default_rng(9)
+    x = O.synthetic_slices(B, S, seed=31)
+    eps_w, eps_z = rng.standard_normal((B, 8, 8, dw)).astype(np.float32), rng.standard_normal((B, 8, 8, dz)).astype(np.float32)
+    eng.set_inputs(x)
+    eng.br[0].eps_w.copy_(torch.from_numpy(eps_w.reshape(-1, dw)))
+    eng.br[0].eps.copy_(torch.from_numpy(eps_z.reshape(-1, dz)))
+    return GO, eng, P, x, eps_w, eps_z
+
+
+@pytest.mark.parametrize('c_lambda', [0.01, 100.0])
+def test_gmvae_spatial_train_step_matches_oracle(c_lambda, monkeypatch):
+    """models/gaussian_mixture_variational_autoencoder_spatial.py + trainers/GMVAE_spatial.py:58-92 (the decoder runs on the encoder
+    output; the prior terms act on the encoder through the 1x1 heads only)."""
+    lr, dc = 1e-3, 5
+    GO, eng, P, x, eps_w, eps_z = _gmvaes(monkeypatch, dc=dc, c_lambda=c_lambda)
+    eng._keep = 1.0
+    eng.forward(training=True, dropout_rate=0.0)
+    sgn = np.sign(eng.br[0].xhat.numpy().astype(np.float64) - x)
+    eng.train_step(lr, beta1=0.5, dropout_rate=0.0, dropout=False, parity_noise=True)
+    o, L, G = GO.loss_and_grads_spatial(P, x, eps_w, eps_z, dc, c_lambda, torch.float64, l1_sign=sgn)
+    br = eng.br[0]
+    for got, key in ((br.xhat, 'xz_mu'), (br.mu, 'z_mu'), (br.zv, 'z_sampled'), (br.w_s, 'w_sampled'), (br.pc, 'pc'), (br.Mz, 'z_wc_mus'),
+                     (br.Sz, 'z_wc_log_sigma_invs')):
+        assert _rel(got.numpy().reshape(o[key].shape), o[key].numpy()) < TOL, key
+    got = eng.losses()
+    for k in got:
+        assert abs(got[k] - float(L[k])) <= 1e-5 * max(abs(float(L[k])), 1e-6), (k, got[k], float(L[k]))
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    for k in P:
+        assert _rel(grads[k], G[k].numpy()) < 2e-5, (k, _rel(grads[k], G[k].numpy()))
+
+
+def test_gmvae_spatial_restoration_step_matches_oracle(monkeypatch):
+    tv_lambda, lr, dc, c_lambda = 1.3, 1e-3, 5, 0.01
+    GO, eng, P, x, eps_w, eps_z = _gmvaes(monkeypatch, dc=dc, c_lambda=c_lambda)
+    eng.forward(training=False, dropout_rate=0.0, branches=[0], need_l1=False)
+    xh = eng.br[0].xhat.numpy().astype(np.float64)
+    d = x.astype(np.float64) - xh
+    tv_sign = (np.sign(d[:, 1:] - d[:, :-1]), np.sign(d[:, :, 1:] - d[:, :, :-1]))
+    want, _ = GO.restore_gradient_spatial(P, x, eps_w, eps_z, tv_lambda, dc, c_lambda, torch.float64, l1_sign=np.sign(xh - x), tv_sign=tv_sign)
+    eng.restore_step(lr, tv_lambda, parity_noise=True, keep_grads=True)
+    assert _rel(eng.restore_grads.numpy(), want.numpy()) < 2e-5
+
+
+def test_gmvae_spatial_trainer_loop(monkeypatch, tmp_path):
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import SYNTHETIC
+    from unsupervised_anomaly_detection_brain_mri_b200.models.gaussian_mixture_variational_autoencoder_spatial import \
+        gaussian_mixture_variational_autoencoder_spatial as net
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.AEMODEL import AEMODEL
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.GMVAE_spatial import GMVAE_spatial
+    E.install(monkeypatch, eng_mod)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(AEMODEL, '_stage', lambda self, key, arr: torch.from_numpy(np.ascontiguousarray(arr, np.float32)))
+    monkeypatch.setattr(AEMODEL, '_prefetch', lambda self, key, arr: None)
+    config = GMVAE_spatial.Config()
+    assert config.modelname == 'GMVAE_spatial'
+    config.outputHeight = config.outputWidth = 32
+    config.batchsize, config.numEpochs, config.zDim, config.numChannels = 2, 1, 128, 1
+    config.dim_c, config.dim_z, config.dim_w, config.c_lambda = 4, 1, 1, 0.5
+    config.restore_steps, config.restore_lr, config.tv_lambda = 2, 1e-3, 1.2
+    config.intermediateResolutions = [8, 8]
+    config.dropout_rate, config.learningrate, config.optimizer = 0.1, 1e-4, 'ADAM'
+    config.checkpointDir = str(tmp_path / 'ckpt')
+    config.description, config.dataset = 'emulated', 'SYNTHETIC'
+    config.device, config.math_mode, config.use_cuda_graph, config.useTensorboard, config.verbose = 'cpu', 0, False, False, False
+    opts = SYNTHETIC.Options()
+    opts.sliceResolution = (32, 32)
+    opts.numPatients = 1
+    opts.sliceStart, opts.sliceEnd = 20, 28
+    ds = SYNTHETIC(opts)
+    model = GMVAE_spatial(None, config, network=net)
+    eng = model.engine
+    assert (eng.arch, eng.zDim, eng.dim_c) == (eng_mod.GMVAES, 1, 4) and model.network.__name__.endswith('_spatial')
+    E.adopt(eng)
+    w0 = eng.fp.to_numpy()
+    model.train(ds)
+    w1 = eng.fp.to_numpy()
+    assert all(np.isfinite(v).all() for v in w1.values())
+    for name in ('Encoder/enc_conv2D_0/kernel', 'q_wz_x/w_mu/kernel', 'q_wz_x/z_log_sigma/kernel', 'p_z_wc/1x1convlayer/kernel',
+                 'p_z_wc/z_wc_mu/kernel', 'Variable', 'Decoder/dec_Conv2D_final/kernel'):
+        assert not np.array_equal(w0[name], w1[name]), name
+    x = ds.next_batch(2, set='VAL')[0]
+    orig_eval = model._eval_engine
+    monkeypatch.setattr(model, '_eval_engine', lambda n: E.adopt(orig_eval(n)))
+    rec = model.reconstruct(x)
+    assert rec['reconstruction'].shape == x.shape and 0 < np.abs(rec['reconstruction'] - x).max() < 0.1

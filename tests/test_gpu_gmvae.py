@@ -88,3 +88,31 @@ def test_gmvae_restoration_graph_equals_eager():
         torch.cuda.synchronize()
         outs.append(eng.br[0].x.cpu().numpy().copy())
     assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_gmvae_spatial_train_step(mode):
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import GMVAES, ConvAutoencoderEngine
+    S, B, dz, dw, dc, c_lambda, lr = 64, 4, 1, 1, 9, 0.01, 1e-3
+    P = GO.perturb(GO.init_params_spatial(S, dim_z=dz, dim_w=dw, dim_c=dc, seed=1))
+    eng = ConvAutoencoderEngine(GMVAES, S, zDim=dz, batch=B, math_mode=mode, dim_w=dw, dim_c=dc, c_lambda=c_lambda)
+    eng.fp.load(P)
+    rng = np.random.default_rng(9)
+    x = O.synthetic_slices(B, S, seed=31)
+    eps_w, eps_z = rng.standard_normal((B, 8, 8, dw)).astype(np.float32), rng.standard_normal((B, 8, 8, dz)).astype(np.float32)
+    eng.set_inputs(x)
+    eng.br[0].eps_w.copy_(torch.from_numpy(eps_w.reshape(-1, dw)))
+    eng.br[0].eps.copy_(torch.from_numpy(eps_z.reshape(-1, dz)))
+    eng._keep = 1.0
+    eng.forward(training=True, dropout_rate=0.0)
+    sgn = np.sign(eng.br[0].xhat.cpu().numpy().astype(np.float64) - x)
+    eng.train_step(lr, beta1=0.5, dropout_rate=0.0, dropout=False, parity_noise=True)
+    torch.cuda.synchronize()
+    o, L, G = GO.loss_and_grads_spatial(P, x, eps_w, eps_z, dc, c_lambda, torch.float64, l1_sign=sgn)
+    assert _rel(eng.br[0].xhat.cpu().numpy(), o['xz_mu'].numpy()) < 1e-4
+    got = eng.losses()
+    for k in got:
+        assert abs(got[k] - float(L[k])) <= 1e-4 * max(abs(float(L[k])), 1e-6), (k, got[k], float(L[k]))
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    for k in P:
+        assert _rel(grads[k], G[k].numpy()) < 5e-4, (k, _rel(grads[k], G[k].numpy()))

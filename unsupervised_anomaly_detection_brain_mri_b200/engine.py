@@ -41,7 +41,12 @@ CAAE = 'constrained_adversarial_autoencoder'
 # Gaussian-mixture VAE (models/gaussian_mixture_variational_autoencoder.py): four Dense heads (w_mu, w_log_sigma, z_mu, z_log_sigma),
 # z and w reparameterised with exp(0.5 * log-variance), p(z|w,c) heads on w and the mixture latent block (uad_gmvae_latent_*)
 GMVAE = 'gaussian_mixture_variational_autoencoder'
-ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE, CAAE, GMVAE)
+# spatial GMVAE (models/gaussian_mixture_variational_autoencoder_spatial.py): the spatial AE's conv stacks (no Dropout; the decoder
+# runs on the encoder output itself), 1x1-conv latent heads on the spatial code and the mixture block at every spatial position
+GMVAES = 'gaussian_mixture_variational_autoencoder_spatial'
+ARCHS = (AE, VAE, CEVAE, AES, CAE, AAE, CAAE, GMVAE, GMVAES)
+SPATIAL = (AES, GMVAES)          # graphs without the dense bottleneck
+GMVAES_MID = 64                  # filters of p_z_wc/1x1convlayer (model :37)
 # Dense widths of the latent critic (models/adversarial_autoencoder.py:44-48, constrained_adversarial_autoencoder.py:52-56)
 CRITIC_WIDTHS = {AAE: (50, 50, 1), CAAE: (100, 50, 1)}
 AAE_CRITIC = CRITIC_WIDTHS[AAE]
@@ -92,7 +97,7 @@ def param_specs(arch, S, C=1, zDim=128, res=8, dim_w=1, dim_c=9):
         bn += 1
         cin = co
     cb = cin // 8
-    if arch != AES:
+    if arch not in SPATIAL:
         sp['Bottleneck/conv2d/kernel'] = (1, 1, cin, cb)
         sp['Bottleneck/conv2d/bias'] = (cb,)
         sp['Bottleneck/conv2d_1/kernel'] = (1, 1, cb, cin)
@@ -118,6 +123,14 @@ def param_specs(arch, S, C=1, zDim=128, res=8, dim_w=1, dim_c=9):
         cin = co
     sp['Decoder/dec_Conv2D_final/kernel'] = (1, 1, cin, C)
     sp['Decoder/dec_Conv2D_final/bias'] = (C,)
+    if arch == GMVAES:               # the explicitly named 1x1-conv heads (model :15-39) and the trainable 0.1 bias
+        ctop = enc[-1]
+        for nm, ci, co in (('q_wz_x/w_mu', ctop, dim_w), ('q_wz_x/w_log_sigma', ctop, dim_w), ('q_wz_x/z_mu', ctop, zDim),
+                           ('q_wz_x/z_log_sigma', ctop, zDim), ('p_z_wc/1x1convlayer', dim_w, GMVAES_MID),
+                           ('p_z_wc/z_wc_mu', GMVAES_MID, zDim * dim_c), ('p_z_wc/z_wc_log_sigma', GMVAES_MID, zDim * dim_c)):
+            sp[nm + '/kernel'] = (1, 1, ci, co)
+            sp[nm + '/bias'] = (co,)
+        sp['Variable'] = (zDim * dim_c,)
     if arch == GMVAE:                # p(z|w,c): the two un-scoped Dense layers on w and the trainable 0.1 bias (model :46-51)
         for nm in ('dense_5', 'dense_6'):
             sp[nm + '/kernel'] = (dim_w, zDim * dim_c)
@@ -293,6 +306,16 @@ class ConvAutoencoderEngine:
         br.mask_bufs.update(ls=self._new(B, self.zDim), dec=self._new(B, self.flat))
         if self.arch == AES:
             br.mask_bufs['sp'] = self._new(B, r, r, self.enc_ch[-1])      # Dropout on the spatial code z [B,res,res,C]
+        if self.arch == GMVAES:
+            R, dw, dz, n, ct = B * r * r, self.dim_w, self.zDim, self.zDim * self.dim_c, self.enc_ch[-1]
+            for k, width in (('w_mu', dw), ('w_ls', dw), ('w_lsh', dw), ('w_sigma', dw), ('w_s', dw), ('eps_w', dw), ('dws', dw), ('dwmu', dw),
+                             ('dwlsh', dw), ('mu', dz), ('ls', dz), ('z_lsh', dz), ('sigma', dz), ('zv', dz), ('eps', dz), ('gzmu', dz),
+                             ('gzls', dz), ('gzs', dz), ('dmu', dz), ('dlsh', dz), ('mid_pre', GMVAES_MID), ('mid', GMVAES_MID),
+                             ('dmid', GMVAES_MID), ('dmid2', GMVAES_MID), ('Mz', n), ('S0', n), ('Sz', n), ('dM', n), ('dS', n), ('dh', ct)):
+                setattr(br, k, self._new(R, width))
+            br.kl_w, br.kl_unused, br.con, br.closs = (self._new(R) for _ in range(4))
+            br.pc = self._new(R, self.dim_c)
+            br.ones_n = torch.ones(n, dtype=torch.float32, device=self.device)
         if self.arch == GMVAE:
             dw, n = self.dim_w, self.zDim * self.dim_c
             for k in ('w_mu', 'w_ls', 'w_lsh', 'w_sigma', 'w_s', 'eps_w', 'dws', 'dws2', 'dwmu', 'dwlsh'):
@@ -414,6 +437,13 @@ class ConvAutoencoderEngine:
         st = self._st()
         ctr = self.rng_ctr.data_ptr()
         nb = 0
+        if self.arch == GMVAES:          # no Dropout in this graph; eps_z, eps_w per spatial position
+            br = self.br[0]
+            call('uad_randn', ptr(br.eps), br.eps.numel(), self.rng_seed, 0 << 40, ctr, st)
+            call('uad_randn', ptr(br.eps_w), br.eps_w.numel(), self.rng_seed, 1 << 40, ctr, st)
+            br.masks['sp'] = None
+            call('uad_counter_add', ctr, 1 << 20, st)
+            return
         if self.arch == AES:
             br = self.br[0]
             if dropout and rate > 0:
@@ -481,15 +511,17 @@ class ConvAutoencoderEngine:
                 h, s, cin = br.enc_a[i], s // 2, co
             r2 = self.res * self.res
             m = br.masks
-            if self.arch == AES:
+            if self.arch in SPATIAL:
                 # autoencoder_spatial.py:16-23: z = Dropout(encoder(x)); decoder = BN -> ReLU -> ...
                 dbn = f'Decoder/{_bn(self.n)}'
                 self._op('bneck01', 'uad_mask_bn_act_fwd', ptr(h), ptr(m['sp']), keep, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')),
                          BN_C, ACT_RELU, 0.0, ptr(br.zr), ptr(br.ar), B * r2, cin, st)
+                if self.arch == GMVAES:
+                    self._gmvaes_latent_fwd(br, h)
             else:
                 self._op('bneck01', 'uad_dense_fwd', ptr(h), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(fp.p('Bottleneck/conv2d/bias')), None,
                    1.0, None, None, ptr(br.zb), None, B * r2, cin, self.cb, ACT_NONE, 0.0, 1.0, ws, wsb, st)
-            if self.arch == AES:
+            if self.arch in SPATIAL:
                 pass
             elif self.arch in (AE, CAE, AAE, CAAE):
                 # autoencoder.py:29: dropout on z honours the flag; :30 dropout on dec_dense(z) has no flag -> identity.
@@ -514,7 +546,7 @@ class ConvAutoencoderEngine:
                 else:
                     zsrc = br.mu      # ce branch decodes z_mu_ce without sampling (ceVAE model :37,43)
                 dd_name, dec_mask = 'Bottleneck/dense_2', m['dec']
-            if self.arch != AES:
+            if self.arch not in SPATIAL:
                 self._op('bneck06', 'uad_dense_fwd', ptr(zsrc), ptr(fp.p(dd_name + '/kernel')), ptr(fp.p(dd_name + '/bias')), ptr(dec_mask),
                    keep, None, None, ptr(br.d), None, B, self.zDim, self.flat, ACT_NONE, 0.0, 1.0, ws, wsb, st)
                 dbn = f'Decoder/{_bn(self.n)}'
@@ -535,7 +567,7 @@ class ConvAutoencoderEngine:
                  ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
-        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE, CAAE, GMVAE) else None, ptr(self.scalars), B, st)
+        self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE, CAAE, GMVAE, GMVAES) else None, ptr(self.scalars), B, st)
         if self.arch in (CAE, CAAE) and (branches is None or 1 in branches):
             # trainers/ConstrainedAE.py:37-43: L2 = mean_hwc (x - x_hat)^2, Rec_z = mean_j (z - z_rec)^2 (per sample);
             # loss = mean_b(L2 + rho * Rec_z).  The same calls leave d loss/d x_hat and d loss/d z_rec (d/dz = -d/dz_rec).
@@ -617,6 +649,66 @@ class ConvAutoencoderEngine:
                 self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
             first = False
 
+    # ------------------------------------------------------------------ spatial GMVAE latent heads (models/..._spatial.py:15-39,58-63)
+    def _gmvaes_latent_fwd(self, br, h):
+        """1x1-conv heads on the encoder output h [B*r*r, C] (a 1x1 conv is a Dense over the rows), w / z per position, the
+        64-filter ReLU layer and the two p(z|w,c) heads on w, the mixture block with one 'sample' per spatial position; the three
+        prior terms are summed over the positions and averaged over the batch (trainers/GMVAE_spatial.py:77-91)."""
+        fp, st = self.fp, self._st()
+        ws, wsb = self._wsargs()
+        B, dz, dw, n, C = self.B, self.zDim, self.dim_w, self.zDim * self.dim_c, self.enc_ch[-1]
+        R = B * self.res * self.res
+        for name, out, width in (('q_wz_x/w_mu', br.w_mu, dw), ('q_wz_x/w_log_sigma', br.w_ls, dw), ('q_wz_x/z_mu', br.mu, dz),
+                                 ('q_wz_x/z_log_sigma', br.ls, dz)):
+            self._op('bneck03', 'uad_dense_fwd', ptr(h), ptr(fp.p(name + '/kernel')), ptr(fp.p(name + '/bias')), None, 1.0, None, None,
+                     ptr(out), None, R, C, width, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+        self._op('bneck05', 'uad_axpby', 0.5, ptr(br.w_ls), 0.0, ptr(br.w_lsh), R * dw, st)
+        self._op('bneck05', 'uad_axpby', 0.5, ptr(br.ls), 0.0, ptr(br.z_lsh), R * dz, st)
+        self._op('bneck05', 'uad_reparam_kl_fwd', ptr(br.w_mu), ptr(br.w_lsh), ptr(br.eps_w), ptr(br.w_sigma), ptr(br.w_s), ptr(br.kl_w), R, dw, st)
+        self._op('bneck05', 'uad_reparam_kl_fwd', ptr(br.mu), ptr(br.z_lsh), ptr(br.eps), ptr(br.sigma), ptr(br.zv), ptr(br.kl_unused), R, dz, st)
+        self._op('bneck05', 'uad_dense_fwd', ptr(br.w_s), ptr(fp.p('p_z_wc/1x1convlayer/kernel')), ptr(fp.p('p_z_wc/1x1convlayer/bias')), None,
+                 1.0, None, None, ptr(br.mid_pre), ptr(br.mid), R, dw, GMVAES_MID, ACT_RELU, 0.0, 1.0, ws, wsb, st)
+        self._op('bneck05', 'uad_dense_fwd', ptr(br.mid), ptr(fp.p('p_z_wc/z_wc_mu/kernel')), ptr(fp.p('p_z_wc/z_wc_mu/bias')), None, 1.0,
+                 None, None, ptr(br.Mz), None, R, GMVAES_MID, n, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+        self._op('bneck05', 'uad_dense_fwd', ptr(br.mid), ptr(fp.p('p_z_wc/z_wc_log_sigma/kernel')), ptr(fp.p('p_z_wc/z_wc_log_sigma/bias')),
+                 None, 1.0, ptr(br.ones_n), ptr(fp.p('Variable')), ptr(br.S0), ptr(br.Sz), R, GMVAES_MID, n, ACT_NONE, 0.0, 1.0, ws, wsb, st)
+        self._op('bneck05', 'uad_gmvae_latent_fwd', ptr(br.mu), ptr(br.ls), ptr(br.zv), ptr(br.Mz), ptr(br.Sz), ptr(br.pc), ptr(br.con),
+                 ptr(br.closs), R, dz, self.dim_c, self.c_lambda, st)
+        for buf, slot in ((br.con, 5), (br.kl_w, 6), (br.closs, 7)):
+            self._op('bneck08', 'uad_sum_scaled', ptr(buf), R, 1.0 / B, self.scalars[slot:].data_ptr(), ws, wsb, st)
+
+    def _gmvaes_latent_bwd(self, br, g, params, scale, acc):
+        """ADDS scale * d(con + w_loss + c_loss) / d(encoder output) to g [B*r*r, C] (which already holds the decoder's path)."""
+        fp, st = self.fp, self._st()
+        ws, wsb = self._wsargs()
+        B, dz, dw, n, C = self.B, self.zDim, self.dim_w, self.zDim * self.dim_c, self.enc_ch[-1]
+        R = B * self.res * self.res
+        G = (lambda name: ptr(fp.g(name))) if params else (lambda name: None)
+        self._op('bneck14', 'uad_gmvae_latent_bwd', ptr(br.mu), ptr(br.ls), ptr(br.zv), ptr(br.Mz), ptr(br.Sz), float(scale), ptr(br.gzmu),
+                 ptr(br.gzls), ptr(br.gzs), ptr(br.dM), ptr(br.dS), R, dz, self.dim_c, self.c_lambda, st)
+        self._op('bneck14', 'uad_reparam_kl_bwd', ptr(br.mu), ptr(br.z_lsh), ptr(br.eps), ptr(br.gzs), 0.0, ptr(br.dmu), ptr(br.dlsh), R, dz, st)
+        self._op('bneck14', 'uad_axpby', 1.0, ptr(br.gzmu), 1.0, ptr(br.dmu), R * dz, st)                    # d/dz_mu
+        self._op('bneck14', 'uad_axpby', 0.5, ptr(br.dlsh), 1.0, ptr(br.gzls), R * dz, st)                   # d/dz_log_sigma (in gzls)
+        self._op('bneck14', 'uad_dense_bwd', ptr(br.mid), ptr(fp.p('p_z_wc/z_wc_mu/kernel')), ptr(br.dM), None, 1.0, ptr(br.dmid),
+                 G('p_z_wc/z_wc_mu/kernel'), G('p_z_wc/z_wc_mu/bias'), R, GMVAES_MID, n, acc, ws, wsb, st)
+        self._op('bneck14', 'uad_dense_bwd', ptr(br.mid), ptr(fp.p('p_z_wc/z_wc_log_sigma/kernel')), ptr(br.dS), None, 1.0, ptr(br.dmid2),
+                 G('p_z_wc/z_wc_log_sigma/kernel'), G('p_z_wc/z_wc_log_sigma/bias'), R, GMVAES_MID, n, acc, ws, wsb, st)
+        if params:
+            self._op('bneck14', 'uad_axpby', 1.0, ptr(fp.g('p_z_wc/z_wc_log_sigma/bias')), 0.0, ptr(fp.g('Variable')), n, st)
+        self._op('bneck14', 'uad_axpby', 1.0, ptr(br.dmid2), 1.0, ptr(br.dmid), R * GMVAES_MID, st)
+        self._op('bneck14', 'uad_activation_bwd', ptr(br.dmid), ptr(br.mid_pre), ptr(br.dmid), R * GMVAES_MID, ACT_RELU, 0.0, st)
+        self._op('bneck14', 'uad_dense_bwd', ptr(br.w_s), ptr(fp.p('p_z_wc/1x1convlayer/kernel')), ptr(br.dmid), None, 1.0, ptr(br.dws),
+                 G('p_z_wc/1x1convlayer/kernel'), G('p_z_wc/1x1convlayer/bias'), R, dw, GMVAES_MID, acc, ws, wsb, st)
+        self._op('bneck14', 'uad_reparam_kl_bwd', ptr(br.w_mu), ptr(br.w_lsh), ptr(br.eps_w), ptr(br.dws), float(scale), ptr(br.dwmu),
+                 ptr(br.dwlsh), R, dw, st)
+        self._op('bneck14', 'uad_axpby', 0.5, ptr(br.dwlsh), 0.0, ptr(br.dwlsh), R * dw, st)                 # d/dw_log_sigma
+        h = br.enc_a[-1]
+        for name, g_in, width in (('q_wz_x/z_mu', br.dmu, dz), ('q_wz_x/z_log_sigma', br.gzls, dz), ('q_wz_x/w_mu', br.dwmu, dw),
+                                  ('q_wz_x/w_log_sigma', br.dwlsh, dw)):
+            self._op('bneck15', 'uad_dense_bwd', ptr(h), ptr(fp.p(name + '/kernel')), ptr(g_in), None, 1.0, ptr(br.dh), G(name + '/kernel'),
+                     G(name + '/bias'), R, C, width, acc, ws, wsb, st)
+            self._op('bneck17', 'uad_axpby', 1.0, ptr(br.dh), 1.0, ptr(g), R * C, st)
+
     # ------------------------------------------------------------------ backward
     def backward(self, want_input_grad=False):
         """tf.gradients of losses['loss'] w.r.t. every trainable variable into the flat gradient buffer.
@@ -666,19 +758,21 @@ class ConvAutoencoderEngine:
             ctop = self.enc_ch[-1]
             dbn = f'Decoder/{_bn(self.n)}'
             self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
-                 ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')) if self.arch != AES else None,
+                 ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')) if self.arch not in SPATIAL else None,
                  B * r2, ctop, ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
             sm = self.small
             m = br.masks
             # keep factor is stored with the mask application: masks carry {0,1}, scale passed explicitly
             keep = self._keep
-            if self.arch == AES:
+            if self.arch in SPATIAL:
                 if m['sp'] is not None:
                     self._op('bneck10', 'uad_mask_scale', ptr(g), ptr(m['sp']), keep, ptr(g), B * r2 * ctop, st)
+                if self.arch == GMVAES:
+                    self._gmvaes_latent_bwd(br, g, True, scale, acc)
             else:
                 self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
                    ptr(fp.g('Bottleneck/conv2d_1/kernel')), None, B * r2, self.cb, ctop, acc, ws, wsb, st)
-            if self.arch == AES:
+            if self.arch in SPATIAL:
                 pass
             elif self.arch == GMVAE:
                 self._gmvae_bottleneck_bwd(br, True, scale, acc)
@@ -709,7 +803,7 @@ class ConvAutoencoderEngine:
                          ptr(fp.g('Bottleneck/dense_1/bias')), B, self.flat, self.zDim, acc, ws, wsb, st)
                     self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
             # bottleneck 1x1 conv backward -> gradient w.r.t. the last encoder activation
-            if self.arch != AES:
+            if self.arch not in SPATIAL:
                 self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
                    ptr(g), ptr(fp.g('Bottleneck/conv2d/kernel')), ptr(fp.g('Bottleneck/conv2d/bias')), B * r2, ctop, self.cb,
                    acc, ws, wsb, st)
@@ -878,13 +972,15 @@ class ConvAutoencoderEngine:
         self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.ar), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
                  None, None, None, B * r2, ctop, ACT_RELU | FO, 0.0, BN_C, 0, ws, wsb, st)
         m, keep = br.masks, self._keep
-        if self.arch == AES:
+        if self.arch in SPATIAL:
             if m['sp'] is not None:
                 self._op('bneck10', 'uad_mask_scale', ptr(g), ptr(m['sp']), keep, ptr(g), B * r2 * ctop, st)
+            if self.arch == GMVAES:
+                self._gmvaes_latent_bwd(br, g, False, float(kl_scale), 0)
         else:
             self._op('bneck10', 'uad_dense_bwd', ptr(br.d), ptr(fp.p('Bottleneck/conv2d_1/kernel')), ptr(g), None, 1.0, ptr(sm['dd']),
                      None, None, B * r2, self.cb, ctop, 0, ws, wsb, st)
-        if self.arch == AES:
+        if self.arch in SPATIAL:
             pass
         elif self.arch == GMVAE:
             self._gmvae_bottleneck_bwd(br, False, float(kl_scale), 0)
@@ -903,7 +999,7 @@ class ConvAutoencoderEngine:
             self._op('bneck16', 'uad_dense_bwd', ptr(br.zb), ptr(fp.p('Bottleneck/dense_1/kernel')), ptr(sm['dls']), ptr(m['ls']), keep,
                      ptr(sm['dflat2']), None, None, B, self.flat, self.zDim, 0, ws, wsb, st)
             self._op('bneck17', 'uad_axpby', 1.0, ptr(sm['dflat2']), 1.0, ptr(sm['dflat']), B * self.flat, st)
-        if self.arch != AES:
+        if self.arch not in SPATIAL:
             self._op('bneck18', 'uad_dense_bwd', ptr(br.enc_a[-1]), ptr(fp.p('Bottleneck/conv2d/kernel')), ptr(sm['dflat']), None, 1.0,
                      ptr(g), None, None, B * r2, ctop, self.cb, 0, ws, wsb, st)
         s = self.res
@@ -1053,7 +1149,7 @@ class ConvAutoencoderEngine:
             return {'reconstructionLoss': float(s[0]), 'L2': float(s[4]), 'loss': float(s[4])}
         if self.arch == VAE:
             return {'reconstructionLoss': float(s[0]), 'kl': float(s[1]), 'loss': float(s[2])}
-        if self.arch == GMVAE:
+        if self.arch in (GMVAE, GMVAES):
             return {'reconstructionLoss': float(s[0]), 'mean_p_loss': float(s[0]), 'conditional_prior_loss': float(s[5]),
                     'w_prior_loss': float(s[6]), 'c_prior_loss': float(s[7]), 'loss': float(s[0]) + float(s[5]) + float(s[6]) + float(s[7])}
         return {'Rec_vae': float(s[0]), 'kl': float(s[1]), 'loss_vae': float(s[2]), 'Rec_ce': float(s[3]),
