@@ -275,6 +275,26 @@ def test_anovaegan_trainer_loop(monkeypatch, tmp_path):
     assert E.calls.count('uad_randn') == t['vae'] + t['gen'] + t['disc'] + ds.num_batches(2, set='VAL')
     ok, step = model.load(model.checkpointDir)
     assert ok and step == 1
+    # reconstruct(): the trainer issues raw ABI calls on data_ptr() integers there - route them through the emulator too
+    import types
+
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    monkeypatch.setattr(abi, 'call', E.call)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    orig = model._engine_for
+
+    def engine_for(n):
+        e = orig(n)
+        E.register(e.eps)
+        return e
+    monkeypatch.setattr(model, '_engine_for', engine_for)
+    x = ds.next_batch(2, set='VAL')[0]
+    rec = model.reconstruct(x)
+    assert rec['reconstruction'].shape == x.shape and np.isfinite(rec['reconstruction']).all() and np.isfinite(rec['l1err'])
+    e2 = model._engine_for(2)
+    assert float(e2.eps.abs().max()) > 0 and e2.kl_weight == model.engine.kl_weight and e2.fp is model.engine.fp
+    one = model.reconstruct(x[0])
+    assert one['reconstruction'].shape == (1, 32, 32, 1)
 
 
 # ------------------------------------------------------------------------------------------------ 3. the AE-family engine
