@@ -1,6 +1,7 @@
 """MSSEG2008 lesion dataset (interface of reference dataloaders/MSSEG2008.py: class MSSEG2008, folders {UNC,CHB}_{train,test}/<patient>/
 <patient>_{FLAIR,T1,T2}.aligned.nii.gz, _lesion.aligned.nii.gz, _skullmap.nii.gz).  Only the `aligned` (NIfTI) format the reference's
-default_config_setup selects is read; the `raw` NRRD files need an NRRD reader that is not carried over."""
+default_config_setup selects is read.  The reference's `raw` path is dead code there: it calls NRRD.denoise() / apply_skullmap(),
+which dataloaders/NRRD.py does not define (MSSEG2008.py:238-262, NRRD.py:7-76) - it is refused here with a clear error."""
 import os
 
 from ._lesion_dataset import LesionDataset
@@ -23,7 +24,7 @@ class MSSEG2008(LesionDataset):
     @staticmethod
     def get_patients(options):
         if options.format != 'aligned':
-            raise NotImplementedError('MSSEG2008: only format="aligned" (NIfTI) is supported; the raw .nhdr volumes need an NRRD reader')
+            raise NotImplementedError('MSSEG2008: only format="aligned" (NIfTI) is supported (the raw NRRD path cannot run in the reference either)')
         patients = []
         for folder in (options.folderTrainUNC, options.folderTestUNC, options.folderTrainCHB, options.folderTestCHB):
             if options.filterScanner and options.filterScanner not in folder:
