@@ -26,28 +26,42 @@ def register(*tensors):
     _registry.extend(tensors)
 
 
-def _resolve(p):
-    """raw int pointer -> flat view starting there (only for registered tensors)."""
+_CTYPES = {torch.float32: 'c_float', torch.uint8: 'c_uint8', torch.int64: 'c_int64'}
+
+
+def _raw(address, n, dtype=torch.float32):
+    """A tensor VIEW over n elements of host memory at a raw address (what `tensor.data_ptr()` hands the ABI when the engine
+    lives on the CPU); the caller's sizes come from the call's own arguments, exactly as the kernels take them."""
+    import ctypes
+    buf = (getattr(ctypes, _CTYPES[dtype]) * int(n)).from_address(int(address))
+    return torch.from_numpy(np.ctypeslib.as_array(buf))
+
+
+def _resolve(p, n=None, dtype=torch.float32):
+    """pointer argument -> flat view starting there: a tensor (ptr() patched to pass tensors through), a registered tensor's
+    interior, or - given the element count - raw host memory."""
     if p is None or isinstance(p, torch.Tensor):
         return None if p is None else p.reshape(-1)
     for t in _registry:
         base, size = t.data_ptr(), t.numel() * t.element_size()
         if base <= p < base + size:
             return t.reshape(-1)[(p - base) // t.element_size():]
-    raise KeyError(f'pointer {p:#x} is not inside a registered tensor')
+    if n is None:
+        raise KeyError(f'pointer {p:#x} is not inside a registered tensor')
+    return _raw(p, n, dtype)
 
 
-def _v(t, *shape):
+def _v(t, *shape, dtype=torch.float32):
     """float64 copy of the first prod(shape) elements behind a pointer, shaped."""
     n = int(np.prod(shape))
-    return _resolve(t)[:n].to(D).reshape(*shape)
+    return _resolve(t, n, dtype)[:n].to(D).reshape(*shape)
 
 
-def _w(t, value):
+def _w(t, value, dtype=torch.float32):
     """write value (any shape) to the first numel elements behind a pointer."""
     if t is None:
         return
-    flat = _resolve(t)
+    flat = _resolve(t, value.numel(), dtype)
     flat[:value.numel()].copy_(value.reshape(-1).to(flat.dtype))
 
 
@@ -394,14 +408,14 @@ def uad_l1_map(x, xhat, l1, rec, B, HW, st):
 
 
 def uad_counter_add(counter, inc, st):
-    c = _resolve(counter)
+    c = _resolve(counter, 1, torch.int64)
     c[0] += int(inc)
 
 
 def uad_adam_tf_step(params, grads, m, v, n, lr, b1, b2, eps, grad_scale, step_dev, st):
     lr_t = lr
     if step_dev is not None:
-        t = int(_resolve(step_dev)[0])
+        t = int(_resolve(step_dev, 1, torch.int64)[0])
         lr_t = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
     g = _v(grads, n) * grad_scale
     mn = b1 * _v(m, n) + (1 - b1) * g
@@ -452,6 +466,44 @@ def uad_restore_update(x, gx, g, lr, grads_out, n, st):
     _w(x, _v(x, n) - lr * gr)
 
 
+# ------------------------------------------------------------------------------------------------ scoring / evaluation stencils
+def uad_binary_erosion_cross(mask, out, N, H, W, iterations, st):
+    import scipy.ndimage
+    m = _resolve(mask, N * H * W, torch.uint8)[:N * H * W].reshape(N, H, W).numpy() != 0
+    se = scipy.ndimage.generate_binary_structure(2, 1)
+    res = np.stack([scipy.ndimage.binary_erosion(sl, structure=se, iterations=int(iterations)) for sl in m])
+    _w(out, torch.from_numpy(res.astype(np.uint8)), torch.uint8)
+
+
+def uad_residual_score(x, xhat, mask, prior_quantile, keep_positive, apply_prior, diff, n, st):
+    xt = _resolve(x, n)[:n].clone()                         # float32 arithmetic, as the kernel (Evaluation.py:282-291)
+    d = xt - _resolve(xhat, n)[:n]
+    d = torch.clamp(d, min=0) if keep_positive else d.abs()
+    if mask is not None:
+        d = d * (_resolve(mask, n, torch.uint8)[:n] != 0).to(d.dtype)
+    if apply_prior:
+        d = torch.where(xt.to(D) < prior_quantile, torch.zeros_like(d), d)
+    _w(diff, d)
+
+
+def uad_median_filter3d_5(vol, out, Z, H, W, st):
+    import scipy.ndimage
+    v = _resolve(vol, Z * H * W)[:Z * H * W].reshape(Z, H, W).numpy()
+    _w(out, torch.from_numpy(scipy.ndimage.median_filter(v, (5, 5, 5), mode='reflect')))
+
+
+def uad_threshold_counts(diff, label, n, thresholds, n_thr, counts, mask_out, st):
+    d = _resolve(diff, n)[:n].to(D)
+    g = (_resolve(label, n, torch.uint8)[:n] != 0) if label is not None else torch.zeros(n, dtype=torch.bool)
+    res = []
+    for i in range(int(n_thr)):
+        p = d > float(thresholds[i])
+        res += [int((p & g).sum()), int(p.sum()), int(g.sum())]
+        if i == 0 and mask_out is not None:
+            _w(mask_out, p.to(torch.uint8), torch.uint8)
+    _w(counts, torch.tensor(res, dtype=torch.int64), torch.int64)
+
+
 _rng = np.random.default_rng(1234)
 
 
@@ -481,8 +533,8 @@ def check_signature(name, args):
     argtypes = SIGNATURES[name][1]
     assert len(args) == len(argtypes), f'{name}: {len(args)} arguments, the ABI takes {len(argtypes)}'
     for i, (a, t) in enumerate(zip(args, argtypes)):
-        if t is C.c_void_p:
-            ok = a is None or isinstance(a, torch.Tensor) or type(a) is int
+        if t is C.c_void_p or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            ok = a is None or isinstance(a, torch.Tensor) or type(a) is int or isinstance(a, C.Array)
         elif t in (C.c_float, C.c_double):
             ok = type(a) in (int, float) or isinstance(a, float)
         else:                                                    # c_int, c_longlong, c_size_t, c_uint64

@@ -6,6 +6,8 @@ function with the header's semantics).
 2. New compositions that have not run on hardware yet (AnoVAEGAN) are then checked the same way against their own oracle:
    every gradient, every loss scalar, the Adam slot ownership of the three optimisers.
 What this does NOT cover: the kernels themselves (GPU parity tests), CUDA-graph capture, device RNG streams."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -984,3 +986,102 @@ def test_gmvae_spatial_trainer_loop(monkeypatch, tmp_path):
     monkeypatch.setattr(model, '_eval_engine', lambda n: E.adopt(orig_eval(n)))
     rec = model.reconstruct(x)
     assert rec['reconstruction'].shape == x.shape and 0 < np.abs(rec['reconstruction'] - x).max() < 0.1
+
+
+# ------------------------------------------------------------------------------------------------ 9. run.py's call sequence end to end
+def _everything_on_the_emulator(monkeypatch):
+    """Engines, trainers, Evaluation and Metrics all through the emulator: module-level call / ptr of the engines, the raw
+    `abi.call(... data_ptr() ...)` sites of trainers / Evaluation / Metrics, and the few torch.cuda entry points the host code touches."""
+    import types
+
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    from unsupervised_anomaly_detection_brain_mri_b200 import engine as eng_mod
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.AEMODEL import AEMODEL
+    E.install(monkeypatch, eng_mod, fanogan_engine, anovaegan_engine)
+    monkeypatch.setattr(abi, 'call', E.call)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(AEMODEL, '_stage', lambda self, key, arr: torch.from_numpy(np.ascontiguousarray(arr, np.float32)))
+    monkeypatch.setattr(AEMODEL, '_prefetch', lambda self, key, arr: None)
+
+
+@pytest.mark.parametrize('tname,mname', [('AE', 'autoencoder'), ('VAE', 'variational_autoencoder')])
+def test_run_py_call_sequence_on_the_emulator(tname, mname, monkeypatch, tmp_path):
+    """The sequence run.py drives (options -> datasets -> config -> Trainer -> train -> checkpoint -> resume -> reconstruct ->
+    Evaluation.evaluate), on CPU: the GPU suite's test_gpu_golden equivalent with every kernel emulated - in particular the
+    evaluation path (batched reconstruction, erosion / residual / median kernels, device threshold counts, best-Dice search,
+    the reference's evalPC result set and files)."""
+    import importlib
+
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_datasets, get_options
+    _everything_on_the_emulator(monkeypatch)
+    PKG = 'unsupervised_anomaly_detection_brain_mri_b200'
+    trainer = getattr(importlib.import_module(f'{PKG}.trainers.{tname}'), tname)
+    network = getattr(importlib.import_module(f'{PKG}.models.{mname}'), mname)
+    cfgjson = {'CHECKPOINTDIR': str(tmp_path / 'ckpt'), 'SAMPLEDIR': str(tmp_path / 'samples'), 'BRAINWEBDIR': '', 'SYNTHETICDIR': ''}
+    options = get_options(batchsize=4, learningrate=1e-3, numEpochs=1, zDim=128, outputWidth=32, outputHeight=32, slices_start=20,
+                          slices_end=32, config=cfgjson)
+    options['data']['dir'] = ''
+    options['data']['numPatients'] = 2
+    options['data']['numTestPatients'] = 2
+    hc, pc = get_datasets(options)
+    config = get_config(trainer, options, 'ADAM', [8, 8], 0.2, hc)
+    config.useTensorboard, config.verbose, config.device, config.math_mode, config.use_cuda_graph = False, False, 'cpu', 0, False
+    model = trainer(None, config, network=network)
+    E.adopt(model.engine)
+    orig_eval = model._eval_engine
+    monkeypatch.setattr(model, '_eval_engine', lambda n: E.adopt(orig_eval(n)))
+    model.train(hc)
+    ckdir = os.path.join(model.checkpointDir, model.model_dir)
+    assert f'{config.modelname}.model-1.npz' in os.listdir(ckdir)
+    model2 = trainer(None, config, network=network)
+    assert model2.load_checkpoint() == 1
+    w, w2 = model.engine.fp.to_numpy(), model2.engine.fp.to_numpy()
+    assert all(np.array_equal(w[k], w2[k]) for k in w)
+    x = hc.next_batch(4, set='VAL')[0]
+    r = model.reconstruct(x[0])
+    assert r['reconstruction'].shape == (1, 32, 32, 1) and np.isfinite(r['l1err'])
+    ev = Evaluation.evaluate(pc, model, options, epoch='1', description='test')
+    assert ev['diffs'].shape == (24, 32, 32) and 0.0 <= ev['bestThreshold'] < 1.0 and np.isfinite(ev['diff_AUC'])
+    for key in ('DiceScore', 'DiceScorePerPatient', 'TPCC', 'FPCC', 'FNCC', 'TP', 'FP', 'TN', 'FN', 'VD', 'DICE', 'AUC', 'thresholdType'):
+        assert key in ev, key
+    assert len(ev['DiceScorePerPatient']) == 2 and ev['TP'] + ev['FP'] + ev['TN'] + ev['FN'] == ev['diffs'].size
+    assert os.path.isfile(os.path.join(ev['evalDir'], 'evalPC.npy')) and os.path.isfile(os.path.join(ev['evalDir'], 'rocPC.npy'))
+    # the device threshold mask is `diffs > t` on the float64 volume (bit-exact on the GPU; the emulator states the same compare)
+    thr_mask = Evaluation.Metrics.DeviceScorer(ev['diffs'], ev['labelmaps'] > 0, device='cpu').threshold_mask(ev['threshold'])
+    assert np.array_equal(thr_mask.numpy().astype(bool).reshape(ev['diffs'].shape), ev['diffs'] > ev['threshold'])
+    best, thr = Evaluation.determine_threshold_on_labeled_patients([pc], model, options, description='VAL')
+    assert best == ev['bestDiceScore'] and thr == ev['bestThreshold']        # the synthetic lesion set has no VAL patients: TEST split
+    options['threshold'] = float(thr)
+    ev2 = Evaluation.evaluate(pc, model, options, epoch='1', description='fixed')
+    assert ev2['thresholdType'] == float(thr) and ev2['DICE'] == pytest.approx(ev['DICE'])
+
+
+def test_fanogan_trainer_reconstruct_and_scoring_on_the_emulator(monkeypatch, tmp_path):
+    """tests/test_gpu_golden.py::test_fanogan_trainer_reconstruct_and_scoring on CPU (untrained weights: reconstruct incl. the MC-dropout
+    path with its raw ABI calls, checkpoint, single-patient evaluation)."""
+    from unsupervised_anomaly_detection_brain_mri_b200.models.fanogan import fanogan
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.fAnoGAN import fAnoGAN
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_datasets, get_options
+    _everything_on_the_emulator(monkeypatch)
+    cfgjson = {'CHECKPOINTDIR': str(tmp_path / 'ckpt'), 'SAMPLEDIR': str(tmp_path / 'samples'), 'BRAINWEBDIR': ''}
+    options = get_options(batchsize=4, learningrate=1e-4, numEpochs=1, zDim=128, outputWidth=32, outputHeight=32, slices_start=20,
+                          slices_end=32, config=cfgjson)
+    options['data']['numPatients'] = 1
+    options['data']['numTestPatients'] = 1
+    hc, pc = get_datasets(options)
+    config = get_config(fAnoGAN, options, 'ADAM', [8, 8], 0.2, hc)
+    config.useTensorboard, config.verbose, config.device, config.math_mode = False, False, 'cpu', 0
+    model = fAnoGAN(None, config, network=fanogan)
+    x = hc.next_batch(4, set='TRAIN')[0]
+    r = model.reconstruct(x)
+    assert r['reconstruction'].shape == x.shape and 0.0 <= r['reconstruction'].min() and r['reconstruction'].max() <= 1.0
+    np.random.seed(1)
+    rd = model.reconstruct(x, dropout=True)                                    # both Dropout sites live, masks drawn by raw ABI calls
+    assert rd['reconstruction'].shape == x.shape and not np.array_equal(rd['reconstruction'], r['reconstruction'])
+    model.save(model.checkpointDir, 1)
+    assert model.load_checkpoint() == 1
+    ev = Evaluation.evaluate(pc, model, options, description='fanogan')
+    assert ev['diffs'].shape == (12, 32, 32) and 0.0 <= ev['bestThreshold'] < 1.0 and len(ev['DiceScorePerPatient']) == 1
