@@ -1085,3 +1085,41 @@ def test_fanogan_trainer_reconstruct_and_scoring_on_the_emulator(monkeypatch, tm
     assert model.load_checkpoint() == 1
     ev = Evaluation.evaluate(pc, model, options, description='fanogan')
     assert ev['diffs'].shape == (12, 32, 32) and 0.0 <= ev['bestThreshold'] < 1.0 and len(ev['DiceScorePerPatient']) == 1
+
+
+@pytest.mark.parametrize('tname,mname', [('AE', 'autoencoder_spatial'), ('ConstrainedAE', 'constrained_autoencoder'),
+                                         ('ceVAE', 'context_encoder_variational_autoencoder'), ('VAE_You', 'variational_autoencoder')])
+def test_remaining_trainer_surfaces_on_the_emulator(tname, mname, monkeypatch, tmp_path):
+    """Every other GPU-verified trainer (spatial AE, constrained AE, ceVAE with its masked second input and anomaly map, VAE_You with
+    the restoration loop as `reconstruct`) through train -> reconstruct on CPU: AEMODEL / the engine were edited after their last GPU run."""
+    import importlib
+
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_datasets, get_options
+    _everything_on_the_emulator(monkeypatch)
+    PKG = 'unsupervised_anomaly_detection_brain_mri_b200'
+    trainer = getattr(importlib.import_module(f'{PKG}.trainers.{tname}'), tname)
+    network = getattr(importlib.import_module(f'{PKG}.models.{mname}'), mname)
+    cfgjson = {'CHECKPOINTDIR': str(tmp_path / 'ckpt'), 'SAMPLEDIR': str(tmp_path / 'samples'), 'BRAINWEBDIR': ''}
+    options = get_options(batchsize=2, learningrate=1e-3, numEpochs=1, zDim=128, outputWidth=64, outputHeight=64, slices_start=40,
+                          slices_end=48, config=cfgjson)
+    options['data']['numPatients'] = 2
+    hc, _ = get_datasets(options)
+    config = get_config(trainer, options, 'ADAM', [8, 8], 0.2, hc)
+    config.useTensorboard, config.verbose, config.device, config.math_mode, config.use_cuda_graph = False, False, 'cpu', 0, False
+    if tname == 'VAE_You':
+        config.restore_steps, config.tv_lambda = 2, 1.5
+    import random
+    random.seed(0)
+    model = trainer(None, config, network=network)
+    w0 = model.engine.fp.to_numpy()
+    model.train(hc)
+    w1 = model.engine.fp.to_numpy()
+    assert all(np.isfinite(v).all() for v in w1.values()) and any(not np.array_equal(w0[k], w1[k]) for k in w0)
+    assert model.engine.t == hc.num_batches(2, set='TRAIN')
+    x = hc.next_batch(2, set='VAL')[0]
+    r = model.reconstruct(x)
+    assert r['reconstruction'].shape == x.shape and np.isfinite(r['reconstruction']).all()
+    if tname == 'VAE_You':
+        assert 0 < np.abs(r['reconstruction'] - x).max() < 0.1               # the restored INPUT, two small gradient steps away
+    if tname == 'ceVAE':
+        assert model.engine.anomaly.shape == (2, 64, 64, 1) and np.isfinite(model.engine.anomaly.numpy()).all()
