@@ -4,12 +4,13 @@ The reference holds no golden vectors and cannot be run here (TensorFlow 1.15), 
 (fp32 torch-CPU restatement, seeds fixed) - they guard the restatement against drift and give the GPU tests a
 committed target that does not depend on the torch build of the GPU box.   Run:  python -m oracle.make_golden
 """
+import json
 import os
 
 import numpy as np
 import torch
 
-from . import scoring
+from . import aae_cpu, anovaegan_cpu, fanogan_cpu, gmvae_cpu, scoring
 from . import tf_graph_cpu as O
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
@@ -72,12 +73,58 @@ def scoring_case():
             'threshs': np.array(ths, np.float64), 'scores': np.array(scs, np.float64)}
 
 
+def sibling_inputs(S=32, B=2, zDim=128):
+    """Seeded feeds shared by make_golden and tests/test_oracle.py (so the fixtures hold outputs only)."""
+    rng = np.random.default_rng(11)
+    x = O.synthetic_slices(B, S, seed=1234)
+    flat = 8 * 8 * (O.stack_plan(S)[1][-1] // 8)
+    mk = lambda n: (rng.uniform(size=(B, n)) >= 0.2).astype(np.float32)  # noqa: E731
+    return dict(x=x, eps=rng.standard_normal((B, zDim)).astype(np.float32), z=rng.standard_normal((B, zDim)).astype(np.float32),
+                alpha=rng.uniform(size=(B, 1)).astype(np.float32), eps_w=rng.standard_normal((B, 1)).astype(np.float32),
+                masks_z=dict(mu=mk(zDim), ls=mk(zDim), dec=mk(flat), z=mk(zDim), w_mu=mk(1), w_ls=mk(1), z_mu=mk(zDim)),
+                eps_w_sp=rng.standard_normal((B, 8, 8, 1)).astype(np.float32),
+                eps_z_sp=rng.standard_normal((B, 8, 8, 1)).astype(np.float32))
+
+
+def _scalars(o):
+    return {k: float(v) for k, v in o.items() if torch.is_tensor(v) and v.ndim == 0}
+
+
+def sibling_outputs(S=32, B=2):
+    """Loss scalars and per-variable gradient L2 norms of every sibling oracle on sibling_inputs() (fp32, dropout 0.2)."""
+    f = sibling_inputs(S, B)
+    m = f['masks_z']
+    out = {}
+    P = fanogan_cpu.perturb(anovaegan_cpu.init_params(S, seed=1))
+    for op in ('vae', 'gen', 'disc'):
+        o, G = anovaegan_cpu.Trainer(P, lr=1e-3, dropout_rate=0.2).step(op, f['x'], f['eps'], f['alpha'],
+                                                                          masks=dict(mu=m['mu'], ls=m['ls'], dec=m['dec']))
+        out['anovaegan_' + op] = dict(scalars=_scalars(o), grad_l2={k: float(g.double().norm()) for k, g in G.items()})
+    for constrained in (False, True):
+        P = aae_cpu.perturb(aae_cpu.init_params(S, seed=1, constrained=constrained))
+        for op in ('ae', 'disc', 'gen'):
+            o, G = aae_cpu.Trainer(P, lr=1e-3, dropout_rate=0.2, constrained=constrained, rho=0.7).step(
+                op, f['x'], f['z'], f['alpha'], masks=dict(z=m['z'], dec=m['dec']))
+            out[('caae_' if constrained else 'aae_') + op] = dict(scalars=_scalars(o),
+                                                                   grad_l2={k: float(g.double().norm()) for k, g in G.items()})
+    P = gmvae_cpu.perturb(gmvae_cpu.init_params(S, seed=1))
+    o, L, G = gmvae_cpu.loss_and_grads(P, f['x'], f['eps_w'], f['eps'], masks=dict(w_mu=m['w_mu'], w_ls=m['w_ls'], z_mu=m['z_mu'],
+                                                                                    dec=m['dec']), dropout_rate=0.2, c_lambda=0.5)
+    out['gmvae'] = dict(scalars=_scalars(L), grad_l2={k: float(g.double().norm()) for k, g in G.items()})
+    P = gmvae_cpu.perturb(gmvae_cpu.init_params_spatial(S, seed=1))
+    o, L, G = gmvae_cpu.loss_and_grads_spatial(P, f['x'], f['eps_w_sp'], f['eps_z_sp'], c_lambda=0.5)
+    out['gmvae_spatial'] = dict(scalars=_scalars(L), grad_l2={k: float(g.double().norm()) for k, g in G.items()})
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, 'ae_32_b2.npz'), **case(O.AE, 32, 2))
     np.savez_compressed(os.path.join(OUT, 'vae_32_b2.npz'), **case(O.VAE, 32, 2))
     np.savez_compressed(os.path.join(OUT, 'cevae_32_b2.npz'), **case(O.CEVAE, 32, 2))
     np.savez_compressed(os.path.join(OUT, 'scoring.npz'), **scoring_case())
+    with open(os.path.join(OUT, 'siblings_32_b2.json'), 'w') as fh:
+        json.dump(sibling_outputs(), fh, indent=1, sort_keys=True)
     print('wrote', sorted(os.listdir(OUT)))
 
 

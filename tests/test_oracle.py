@@ -176,3 +176,20 @@ def test_anovaegan_oracle_gradients_by_central_differences():
             Pm[n][idx] -= h
             fd = (float(loss(Pp, which).detach()) - float(loss(Pm, which).detach())) / (2 * h)
             assert abs(fd - float(gn[idx])) <= 1e-5 * max(abs(fd), 1e-6), (which, n, fd, float(gn[idx]))
+
+
+def test_sibling_oracles_reproduce_golden():
+    """AnoVAEGAN / AAE / constrained AAE / GMVAE / spatial GMVAE oracles against the committed scalars and gradient norms
+    (tests/golden/siblings_32_b2.json, written by oracle/make_golden.py from the same seeded feeds)."""
+    import json
+    from oracle.make_golden import sibling_outputs
+    with open(os.path.join(GOLD, 'siblings_32_b2.json')) as fh:
+        gold = json.load(fh)
+    now = sibling_outputs()
+    assert sorted(now) == sorted(gold)
+    for case, g in gold.items():
+        for k, v in g['scalars'].items():
+            assert abs(now[case]['scalars'][k] - v) <= 2e-4 * max(1e-3, abs(v)), (case, k)
+        assert sorted(now[case]['grad_l2']) == sorted(g['grad_l2'])
+        for k, v in g['grad_l2'].items():
+            assert abs(now[case]['grad_l2'][k] - v) <= 2e-4 * max(1e-4, abs(v)) + 1e-7, (case, k)
