@@ -212,7 +212,7 @@ ITEMS = [[25] * 4, [9, 6, 6, 4] * 3, [4, 4, 4, 4, 4], [100, 100], [25, 9, 6, 6, 
 
 @pytest.mark.parametrize('items', ITEMS)
 @pytest.mark.parametrize('S,NS,n_iss,split', [(4, 4, 2, False), (2, 2, 2, True), (4, 2, 2, True), (6, 6, 2, False), (2, 2, 2, False),
-                                              (8, 4, 2, False)])
+                                              (8, 4, 2, False), (6, 4, 2, False)])
 def test_v2_protocol_random_schedules(items, S, NS, n_iss, split):
     """EVEN stage and slot rings (what the launcher configures): every role owns its stages / slots statically."""
     for seed in range(12):

@@ -29,3 +29,9 @@ tail -15 gpurun_out/${TAG}_unverified_pytest.log
 UAD_TC_V2=5 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_5.txt 2>&1      # N = 128 column-split (odd ring: timing only)
 UAD_TC_V2=0 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v1.txt 2>&1        # first-generation kernel everywhere
 tail -6 gpurun_out/${TAG}_time_tc_v2_5.txt gpurun_out/${TAG}_time_tc_v1.txt
+# 5. swizzled epilogue staging (gather_gemm_tc2_swz): four stages at N = 128 -> column-split dual issue on an EVEN ring, six at N = 64
+UAD_TC_V2=21 timeout 300 python -m pytest tests/test_gpu_swz_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_swz_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_swz_pytest.log
+UAD_TC_V2=21 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_21.txt 2>&1
+UAD_TC_V2=17 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_17.txt 2>&1    # swizzled staging, N = 64 only (6 stages)
+tail -6 gpurun_out/${TAG}_time_tc_v2_21.txt gpurun_out/${TAG}_time_tc_v2_17.txt

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "uad_conv.cuh"
+#include "uad_staging.h"
 
 namespace {
 
@@ -729,8 +730,14 @@ gather_gemm_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 //     (N <= 64; the unpaired N = 128 layout has one shared correction accumulator, so there a single warp issues);
 //     while one warp polls its barriers and commits, the other's MMAs keep the pipe busy.
 // 12 warps: 0 TMA producer | 1 issuer A | 2 TMEM alloc, then issuer B | 3 epilogue constants | 4-7, 8-11 converter groups.
-__global__ void __launch_bounds__(384, 1)
-gather_gemm_tc2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+// kSwzStg (round-2 candidate, opt-in UAD_TC_V2 bit 16, not yet run on hardware): the epilogue's per-warp staging rows are
+// 32 floats with the 16-byte column group XOR-ed by (row & 7) instead of 36 padded floats - 32 KB instead of 36 KB for the
+// eight warps, which is what lets FOUR 48 KB stages fit at N = 128 (an EVEN ring, so the column-split dual issue is legal).
+// Both access patterns stay conflict-free: a quarter-warp writes rows r..r+7 at one logical group (8 distinct physical
+// groups) and reads one row at 8 logical groups.
+template <bool kSwzStg>
+__device__ __forceinline__ void gather_gemm_tc2_body(const CUtensorMap& tmap, const TcParams& p) {
+  constexpr int kLdStg = kSwzStg ? 32 : 36;                 // == uad_stg_ld<kSwzStg>()
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -898,7 +905,7 @@ gather_gemm_tc2(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     const int q = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t swz = (uint32_t)(row & 7);
-    float* stg = stg_base + (size_t)(warp - 4) * 32 * 36;       // this warp's 32 x (32+4) staging rows
+    float* stg = stg_base + (size_t)(warp - 4) * 32 * kLdStg;   // this warp's 32 staging rows (padded or swizzled)
     const int nchunks = N >> 5;
     int s = 0, t = 0;
     uint32_t ph = 0, pht = 0, kc = 0, il = 0;
@@ -990,12 +997,12 @@ gather_gemm_tc2(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
               const float z = __uint_as_float(v[j + e]) + epi[n];
               o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], p.act, p.alpha);
             }
-            *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(stg + uad_stg_write_index<kSwzStg>(lane, j)) = make_float4(o[0], o[1], o[2], o[3]);
           }
           __syncwarp();
           float4 vals[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) vals[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * 36 + cq);
+          for (int it = 0; it < 8; ++it) vals[it] = *reinterpret_cast<const float4*>(stg + uad_stg_read_index<kSwzStg>(lane, it));
 #pragma unroll
           for (int it = 0; it < 8; ++it)
             if (offs[it] >= 0) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = vals[it];
@@ -1015,6 +1022,16 @@ gather_gemm_tc2(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+__global__ void __launch_bounds__(384, 1)
+gather_gemm_tc2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  gather_gemm_tc2_body<false>(tmap, p);
+}
+
+__global__ void __launch_bounds__(384, 1)
+gather_gemm_tc2_swz(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  gather_gemm_tc2_body<true>(tmap, p);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel, v3 (CANDIDATE)
@@ -1713,7 +1730,8 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
     // ---- v2 role structure (two converter groups, two issuers for N <= 64); UAD_TC_V2=0 selects the first-generation kernel
     // UAD_TC_V2 (bit mask, developer switch; default 1): 1 = N = 64 layers (dual issue on alternate k-blocks), 4 = N = 128
     // layers (column-split dual issue, measured 13 % faster; +8: single issuer - no faster than the first generation),
-    // 2 = N = 32 single-class layers (measured SLOWER than the two-CTA-per-SM N = 32 kernel); 0 = never.
+    // 2 = N = 32 single-class layers (measured SLOWER than the two-CTA-per-SM N = 32 kernel); 16 = swizzled epilogue staging
+    // (candidate, see below); 0 = never.
     // Why N = 128 is NOT on by default: a role that handles every other k-block must own its stages statically, i.e. the
     // stage ring must be EVEN (as the slot ring is) - with an odd ring successive uses of full[s] alternate between the
     // two groups, each group waits with the parity of the use BEFORE the one it skipped and can pass while the skipped
@@ -1730,8 +1748,12 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
       p.nslots = ((512 - (p.split_n ? 384 : p.nacc * N)) / 64) & ~1;
       if (p.nslots > 6) p.nslots = 6;
       UAD_REQUIRE(p.nslots >= 2, "gather_gemm_tc2: TMEM budget exceeded");
-      const size_t tail2 = 256 + 3 * N * sizeof(float) + 8 * 32 * 36 * sizeof(float) + 64;
-      p.stages = (int)((226 * 1024 - 1024 - tail2) / stage_bytes);
+      // bit 16 (round-2 candidate, never run on hardware): swizzled 32 x 32 staging -> at N = 128 four 48 KB stages fit in
+      // the 227 KB a block may own (1024 alignment slack + 196608 + 256 + 1536 + 32768 + 64 = 232256 <= 232448), an EVEN
+      // ring, so UAD_TC_V2=21 (1 + 4 + 16) runs the column-split dual issue with static stage ownership.
+      const bool swz_stg = (use_v2 & 16) != 0;
+      const size_t tail2 = 256 + 3 * N * sizeof(float) + 8 * 32 * (swz_stg ? 32 : 36) * sizeof(float) + 64;
+      p.stages = (int)(((swz_stg ? 227 : 226) * 1024 - 1024 - tail2) / stage_bytes);
       if (p.stages > 8) p.stages = 8;
       p.stages &= ~1;                                      // EVEN ring: static stage ownership per converter group / issuer
       UAD_REQUIRE(p.stages >= 2, "gather_gemm_tc2: shared-memory budget exceeded");
@@ -1739,10 +1761,12 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
       static bool attr2 = false;
       if (!attr2) {
         UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc2_swz, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr2 = true;
       }
       const int grid2 = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
-      gather_gemm_tc2<<<grid2, 384, smem2, st>>>(tmap, p);
+      if (swz_stg) gather_gemm_tc2_swz<<<grid2, 384, smem2, st>>>(tmap, p);
+      else gather_gemm_tc2<<<grid2, 384, smem2, st>>>(tmap, p);
       UAD_LAUNCH_CHECK("gather_gemm_tc2");
       return 0;
     }
