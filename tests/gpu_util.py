@@ -2,8 +2,8 @@
 import numpy as np
 import torch
 
-from unsupervised_anomaly_detection_brain_mri_b200 import abi
-from unsupervised_anomaly_detection_brain_mri_b200.abi import call, ptr
+from unsupervised_anomaly_detection_brain_mri_b200 import abi  # noqa: F401  (re-exported to the tests)
+from unsupervised_anomaly_detection_brain_mri_b200.abi import call, ptr  # noqa: F401
 
 DEV = 'cuda:0'
 

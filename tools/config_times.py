@@ -5,7 +5,6 @@ usage: python tools/config_times.py [steps]"""
 import json
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, '.')

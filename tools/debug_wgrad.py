@@ -1,5 +1,6 @@
 """Developer aid for the tcgen05 wgrad kernel: UAD_WGRAD_DEBUG=0/1/2 variants on a tiny case."""
-import math, os, sys
+import os
+import sys
 import numpy as np
 import torch
 sys.path.insert(0, '.')

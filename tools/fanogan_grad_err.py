@@ -1,7 +1,6 @@
 """Per-variable gradient error of the f-AnoGAN train ops vs the float64 oracle (developer aid)."""
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, '.')

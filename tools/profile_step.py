@@ -1,6 +1,5 @@
 """Eager (no CUDA graph) VAE-256 B=64 train steps for ncu: `ncu ... python tools/profile_step.py [steps] [math]`."""
 import sys
-import numpy as np
 import torch
 sys.path.insert(0, '.')
 from unsupervised_anomaly_detection_brain_mri_b200 import abi

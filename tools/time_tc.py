@@ -1,6 +1,5 @@
 """Developer aid: event-times single TC conv ops (VAE-256 layer shapes) under the UAD_TC_DEBUG / UAD_WGRAD_DEBUG switches."""
 import os, sys
-import numpy as np
 import torch
 sys.path.insert(0, '.')
 from unsupervised_anomaly_detection_brain_mri_b200 import abi

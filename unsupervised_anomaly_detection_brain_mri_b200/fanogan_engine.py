@@ -9,7 +9,6 @@ the directional derivative of sum(D(x_hat)) along u, so the critic runs forward 
 kernel the autoencoders use."""
 from __future__ import annotations
 
-import math
 from collections import OrderedDict
 
 import numpy as np

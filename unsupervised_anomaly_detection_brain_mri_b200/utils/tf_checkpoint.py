@@ -26,7 +26,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from .tfrecord_utils import _fields, _len_delimited, _read_varint, _varint, crc32c, masked_crc32c
+from .tfrecord_utils import _fields, _len_delimited, _read_varint, _varint, crc32c
 
 MAGIC = 0xDB4775248B80FB57
 BLOCK_SIZE = 4096           # table::Options::block_size
