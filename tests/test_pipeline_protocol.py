@@ -250,3 +250,109 @@ def test_v2_protocol_instant_mma(S, NS, n_iss, split):
     """The UAD_TC_DEBUG 'no MMA' mode: every commit fires as soon as it is issued."""
     for seed in range(8):
         Sim([25, 25, 9, 6], S, NS, n_iss, split, seed, instant_mma=True).run()
+
+
+class WgradSim:
+    """Protocol of the plane-resident Form-W candidate `wgrad_tc2`: every role visits every pixel block; S stages (raw tiles + B
+    images), two A buffers in tensor memory; both converter groups fill half of each block's A buffer and B images."""
+
+    def __init__(self, nkb, S, seed):
+        self.nkb, self.S, self.rng = nkb, S, random.Random(seed)
+        self.full = [MBar(1) for _ in range(S)]
+        self.empty = [MBar(1) for _ in range(S)]
+        self.afull = [MBar(4) for _ in range(2)]          # 256 converter threads, modelled as 2 groups x 2 threads
+        self.aempty = [MBar(1) for _ in range(2)]
+        self.acc = MBar(1)
+        self.stage = [None] * S                            # block whose raw tiles are in the stage (None: load in flight)
+        self.bimg = [dict() for _ in range(S)]             # stage -> {(group, thread): block} parts of the B images written
+        self.abuf = [dict() for _ in range(2)]             # buffer -> {(group, thread): block} parts of the A planes written
+        self.tma, self.mmaq, self.done_blocks, self.epilogue_ran = [], [], [], 0
+
+    def producer(self):
+        s = ph = 0
+        for i in range(self.nkb):
+            yield ('wait', self.empty[s], ph ^ 1, i // self.S)
+            self.stage[s] = None
+            self.tma.append((s, i))
+            s += 1
+            if s == self.S:
+                s, ph = 0, ph ^ 1
+
+    def issuer(self):
+        s = ph = 0
+        for i in range(self.nkb):
+            buf = i & 1
+            yield ('wait', self.full[s], ph, i // self.S + 1)
+            yield ('wait', self.afull[buf], (i >> 1) & 1, (i >> 1) + 1)
+            self.mmaq += [('mma', i, s, buf), ('commit', self.empty[s]), ('commit', self.aempty[buf])]
+            s += 1
+            if s == self.S:
+                s, ph = 0, ph ^ 1
+        self.mmaq.append(('commit', self.acc))
+
+    def converter(self, grp, thread):
+        s = ph = 0
+        for i in range(self.nkb):
+            buf = i & 1
+            yield ('wait', self.full[s], ph, i // self.S + 1)
+            assert self.stage[s] == i, ('converter read a stage that holds another block', self.stage[s], i)
+            self.bimg[s][(grp, thread)] = i
+            yield ('wait', self.aempty[buf], ((i >> 1) & 1) ^ 1, i >> 1)
+            self.abuf[buf][(grp, thread)] = i
+            self.afull[buf].arrive()
+            s += 1
+            if s == self.S:
+                s, ph = 0, ph ^ 1
+        if self.nkb:
+            yield ('wait', self.acc, 0, 1)
+            assert self.done_blocks == list(range(self.nkb)), 'epilogue read incomplete accumulators'
+        self.epilogue_ran += 1
+
+    def hw_run(self, step):
+        if step[0] == 'tma':
+            s, i = self.tma.pop(step[1])
+            self.stage[s] = i
+            self.full[s].arrive()
+            return
+        op = self.mmaq.pop(0)
+        if op[0] == 'commit':
+            op[1].arrive()
+            return
+        _, i, s, buf = op
+        parts = {(g, t) for g in range(2) for t in range(2)}
+        assert self.stage[s] == i, ('MMA executed on a refilled stage', self.stage[s], i)
+        assert {k for k, v in self.bimg[s].items() if v == i} == parts, ('MMA executed on foreign B images', i, self.bimg[s])
+        assert {k for k, v in self.abuf[buf].items() if v == i} == parts, ('MMA executed on a foreign A buffer', i, self.abuf[buf])
+        self.done_blocks.append(i)
+
+    def run(self):
+        actors = [self.producer(), self.issuer()] + [self.converter(g, t) for g in range(2) for t in range(2)]
+        blocked, alive = [None] * len(actors), [True] * len(actors)
+        for k in range(len(actors)):
+            blocked[k] = next(actors[k], None)
+            alive[k] = blocked[k] is not None
+        guard = 0
+        while any(alive) or self.tma or self.mmaq:
+            guard += 1
+            assert guard < 1_000_000
+            runnable = [k for k in range(len(actors)) if alive[k] and blocked[k][1].done(blocked[k][2])]
+            choices = [('a', k) for k in runnable] + [('h', ('tma', k)) for k in range(len(self.tma))] + ([('h', ('mma',))] if self.mmaq else [])
+            assert choices, 'deadlock'
+            kind, x = self.rng.choice(choices)
+            if kind == 'h':
+                self.hw_run(x)
+                continue
+            _, bar, parity, phase = blocked[x]
+            assert bar.phase == phase, ('parity aliasing: waited for phase %d, barrier is at %d' % (phase, bar.phase))
+            try:
+                blocked[x] = next(actors[x])
+            except StopIteration:
+                alive[x] = False
+        assert self.epilogue_ran == 4 and self.done_blocks == list(range(self.nkb))
+
+
+@pytest.mark.parametrize('S', [2, 3, 4])
+@pytest.mark.parametrize('nkb', [0, 1, 2, 3, 7, 40])
+def test_wgrad_v2_protocol_random_schedules(nkb, S):
+    for seed in range(20):
+        WgradSim(nkb, S, seed).run()

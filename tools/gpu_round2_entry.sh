@@ -35,3 +35,8 @@ tail -5 gpurun_out/${TAG}_swz_pytest.log
 UAD_TC_V2=21 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_21.txt 2>&1
 UAD_TC_V2=17 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_v2_17.txt 2>&1    # swizzled staging, N = 64 only (6 stages)
 tail -6 gpurun_out/${TAG}_time_tc_v2_21.txt gpurun_out/${TAG}_time_tc_v2_17.txt
+# 6. plane-resident Form-W candidate (wgrad_tc2): only meaningful if experiment E7 of the operand probe passed (see step 2's output)
+UAD_WGRAD_V2=1 timeout 300 python -m pytest tests/test_gpu_wgrad_v2_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_wgrad2_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_wgrad2_pytest.log
+UAD_WGRAD_V2=1 timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers_wgrad2.json > gpurun_out/${TAG}_bench_wgrad2.json 2> gpurun_out/${TAG}_bench_wgrad2.err
+cat gpurun_out/${TAG}_bench_wgrad2.json

@@ -21,6 +21,7 @@
 
 #include "uad_conv.cuh"
 #include "uad_staging.h"
+#include "uad_wgrad_tiles.h"
 
 namespace {
 
@@ -1621,6 +1622,226 @@ wgrad_tc(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUt
   }
 }
 
+// ================================================================================================ Form W, v2 (CANDIDATE)
+// Plane-resident A (DESIGN.md 4.2, round-2 redesign; index arithmetic in uad_wgrad_tiles.h).  Written after round 1's GPU
+// budget was spent: compiled, index arithmetic host-tested, NEVER RUN on hardware - opt-in only (UAD_WGRAD_V2=1), and it
+// presumes that tcgen05.mma accepts an A operand at an arbitrary tensor-memory column (tools/ubench/operand_probe.cu, E7).
+//   * per 4 x 8 pixel block TMA loads the 6 x 10 halo of the four stride-2 parity planes (pitch 10, 8 KB per plane) and the O tile
+//   * BOTH converter groups work on EVERY block (no skipped barrier phases, so any stage count is legal): group g splits halo
+//     pixels 32g .. 32g+31 of its lane's plane/channel into tf32 hi / lo and stores them to tensor memory ONCE (lane = 32 * plane
+//     + channel, column = halo pixel; hi at [0,64), lo at [64,128) of the block's A buffer, two buffers), and transposes + splits
+//     half of the O tile into the K-major B_hi / B_lo images
+//   * the issuer then runs the block's MMAs back to back - for each window tile (oh, ow) owned by the CTA and each pixel row r:
+//     a_lo.b_hi + a_hi.b_lo + a_hi.b_hi with A read at column 10 (oh + r) + ow - with ONE barrier round trip per block instead of
+//     one per accumulator tile
+// 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM alloc, 3 idle, 4-7 / 8-11 = converter groups 0 / 1 (then the epilogue).
+constexpr int kW2PlaneBytes = 8192;                  // 60 halo rows of 128 B, padded to the 1024-byte swizzle period
+constexpr int kW2HaloBytes = 4 * kW2PlaneBytes;
+constexpr int kW2HaloTx = 4 * UAD_WT_HALO_H * UAD_WT_HALO_W * 128;
+
+struct TcWgrad2Params {
+  int B, lgMH, lgMW;
+  int Cg, Co, ncb;
+  int ngroups, tiles_per_group;      // window tiles [grp * tiles_per_group, ...) of the 9 per CTA
+  int nblocks, blocks_per_chunk, Mp, stages;
+  float* partial;                    // [nchunks][Mp][Co]
+};
+
+__global__ void __launch_bounds__(384, 1)
+wgrad_tc2(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_o,
+          const __grid_constant__ TcWgrad2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int Co = p.Co;
+  const uint32_t o_bytes = 32u * Co * 4u;                 // raw O tile [32 px][Co]; then K-major B_hi, B_lo [Co][32 px]
+  const uint32_t stage_bytes = kW2HaloBytes + 3 * o_bytes;
+  const int S = p.stages;
+  const uint32_t misc = smem_base + S * stage_bytes;
+  const uint32_t bar_full = misc, bar_empty = misc + 64, bar_afull = misc + 192, bar_aempty = misc + 224, bar_acc = misc + 256,
+                 tmem_slot = misc + 264;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = blockIdx.y % p.ngroups;
+  const int cb = blockIdx.y / p.ngroups;
+  const int tile0 = grp * p.tiles_per_group;
+  const int ntiles = min(p.tiles_per_group, UAD_WT_TILES - tile0);
+  const int blk_begin = blockIdx.x * p.blocks_per_chunk;
+  const int blk_end = min(p.nblocks, blk_begin + p.blocks_per_chunk);
+  const int nkb = blk_end - blk_begin;
+  const int bw = (1 << p.lgMW) / kWPW, bh = (1 << p.lgMH) / kWPH;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_afull + 8 * i, 256); mbar_init(bar_aempty + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  const uint32_t aoff = p.tiles_per_group * Co;         // two 128-column A buffers after the accumulator tiles
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_g) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_o) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        const uint32_t full = bar_full + 8 * s;
+        mbar_expect_tx(full, (uint32_t)kW2HaloTx + o_bytes);
+        const int blk = blk_begin + i;
+        const int bx = blk % bw, by = (blk / bw) % bh, b = blk / (bw * bh);
+        const int r0 = by * kWPH, s0 = bx * kWPW;
+        const uint32_t st_base = smem_base + s * stage_bytes;
+        for (int pl = 0; pl < 4; ++pl)                 // plane (ph, pw) = (pl >> 1, pl & 1)
+          tma_load_5d(st_base + pl * kW2PlaneBytes, &tmap_g, full, (pl & 1) * p.Cg + cb * 32, s0 - 1, pl >> 1, r0 - 1, b);
+        for (int a = 0; a < Co / 32; ++a)
+          tma_load_4d(st_base + kW2HaloBytes + a * 4096, &tmap_o, full, a * 32, s0, r0, b);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // whole warp converged, one elected lane issues.  D=f32, A=B=tf32, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Co >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t bdesc0 = make_sw128_desc(smem_base + kW2HaloBytes + o_bytes);
+    const uint32_t stage_units = stage_bytes >> 4, lo_units = o_bytes >> 4;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkb; ++i) {
+      const uint32_t buf = (uint32_t)i & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      mbar_wait(bar_afull + 8 * buf, ((uint32_t)i >> 1) & 1u);   // A planes in tensor memory + B images in shared memory
+      tc_fence_after();
+      const uint64_t dhi0 = bdesc0 + (uint64_t)(s * stage_units);
+      const uint32_t a_hi0 = tmem_base + aoff + buf * 128, a_lo0 = a_hi0 + 64;
+      for (int tl = 0; tl < ntiles; ++tl) {
+        const uint32_t d = tmem_base + tl * Co;
+        if (elect_one()) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {                          // 8 pixels per instruction = 32 bytes along the swizzle row
+            const uint32_t col = (uint32_t)uad_wt_a_column(tile0 + tl, r);
+            mma_tf32_ts(d, a_lo0 + col, dhi0 + 2 * r, idesc, (i | r) != 0);
+            mma_tf32_ts(d, a_hi0 + col, dhi0 + lo_units + 2 * r, idesc, 1u);
+            mma_tf32_ts(d, a_hi0 + col, dhi0 + 2 * r, idesc, 1u);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        tc_commit(bar_empty + 8 * s);                            // stage (raw tiles + B images) reusable
+        tc_commit(bar_aempty + 8 * buf);                         // A buffer reusable
+      }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+    if (elect_one()) tc_commit(bar_acc);
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int q = warp & 3;                                    // lane group = parity plane
+    const int cg = (warp - 4) >> 2;                            // converter group 0 / 1
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t chunk_swz = (uint32_t)(lane >> 2), word = (uint32_t)(lane & 3) << 2;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int i = 0; i < nkb; ++i) {
+      const uint32_t buf = (uint32_t)i & 1u;
+      mbar_wait(bar_full + 8 * s, ph);
+      uint8_t* st = smem_gen + s * stage_bytes;
+      // ---- this group's half of the O tile: pixel group pg = 2 q + cg (pixels 4 pg .. 4 pg + 3) of every channel
+      {
+        const uint8_t* raw = st + kW2HaloBytes;
+        uint8_t* bhi = st + kW2HaloBytes + o_bytes;
+        uint8_t* blo = bhi + o_bytes;
+        const int pg = 2 * q + cg;
+        for (int a = 0; a < Co / 32; ++a) {
+          const int n = a * 32 + lane;
+          float h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int px = 4 * pg + e;
+            const float v = *reinterpret_cast<const float*>(raw + a * 4096 + px * 128 + (((chunk_swz ^ (px & 7)) << 4) | word));
+            h[e] = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            l[e] = v - h[e];
+          }
+          const uint32_t off = n * 128 + ((pg ^ (n & 7)) << 4);
+          *reinterpret_cast<float4*>(bhi + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(blo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+      }
+      // ---- this group's half of the plane copy: halo pixels 32 cg .. 32 cg + 31 (60 real ones) of (plane q, channel lane)
+      uint32_t hi[32], lo[32];
+      {
+        const uint8_t* plane = st + q * kW2PlaneBytes;
+        const uint8_t* colp[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) colp[c] = plane + (((chunk_swz ^ (uint32_t)c) << 4) | word);   // swizzle phase = row & 7
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int px = 32 * cg + j;                          // row of the plane tile (cg is warp-uniform)
+          float v = 0.f;
+          if (px < UAD_WT_HALO_H * UAD_WT_HALO_W) v = *reinterpret_cast<const float*>(colp[j & 7] + px * 128);
+          const uint32_t h = __float_as_uint(v) & 0xffffe000u;
+          hi[j] = h;
+          lo[j] = __float_as_uint(v - __uint_as_float(h));
+        }
+      }
+      mbar_wait(bar_aempty + 8 * buf, (((uint32_t)i >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t a_buf = lane_base + aoff + buf * 128 + cg * 32;
+      tmem_st32(a_buf, hi);
+      tmem_st32(a_buf + 64, lo);
+      tmem_wait_st();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // B images: generic-proxy stores -> tensor core
+      tc_fence_before();
+      mbar_arrive(bar_afull + 8 * buf);
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+    // ---- epilogue: accumulator tiles -> partial[chunk][(tap, channel)][co]; tiles split between the two groups
+    if (nkb > 0) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+    }
+    for (int tl = cg; tl < ntiles; tl += 2) {
+      const int tap = uad_wt_tap(tile0 + tl, q);
+      for (int c0 = 0; c0 < Co; c0 += 32) {
+        uint32_t v[32];
+        if (nkb > 0) {
+          tmem_ld32(lane_base + tl * Co + c0, v);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (tap >= 0) {
+          const size_t row = (size_t)tap * p.Cg + cb * 32 + lane;
+          float* dst = p.partial + ((size_t)blockIdx.x * p.Mp + row) * Co + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1855,10 +2076,84 @@ static void wgrad_tc_plan(int Cg, int Co, int P, int* ngroups, int* tpg, int* QT
   *nchunks = uad_cdiv(nblocks, *bpc);
 }
 
+// plan of the plane-resident candidate (wgrad_tc2): 9 window tiles over CTA groups so that tiles * Co + 2 * 128 A columns <= 512
+static void wgrad_tc2_plan(int Cg, int Co, int P, int* ngroups, int* tpg, int* nchunks, int* bpc) {
+  const int nt_max = 256 / Co;
+  *ngroups = uad_cdiv(UAD_WT_TILES, nt_max);
+  *tpg = uad_cdiv(UAD_WT_TILES, *ngroups);
+  const int nblocks = P / 32;
+  int target = (4 * UAD_NUM_SMS) / ((*ngroups) * (Cg / 32));
+  if (target < 1) target = 1;
+  if (target > nblocks) target = nblocks;
+  *bpc = uad_cdiv(nblocks, target);
+  *nchunks = uad_cdiv(nblocks, *bpc);
+}
+
 size_t uad_tc_wgrad_ws_bytes(int Cg, int Co, int P) {
   int ng, tpg, qt, nch, bpc;
   wgrad_tc_plan(Cg, Co, P, &ng, &tpg, &qt, &nch, &bpc);
+  if (Co <= 64) {                                       // the candidate kernel shares the workspace: size it for either plan
+    int ng2, tpg2, nch2, bpc2;
+    wgrad_tc2_plan(Cg, Co, P, &ng2, &tpg2, &nch2, &bpc2);
+    if (nch2 > nch) nch = nch2;
+  }
   return (size_t)nch * 25 * Cg * Co * sizeof(float) + 1024;
+}
+
+// UAD_WGRAD_V2=1 (developer switch, default 0): the round-2 CANDIDATE kernel wgrad_tc2 for Co <= 64 - not yet run on hardware
+static int launch_wgrad_tc2(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st,
+                            EncodeTiledFn encode) {
+  const int Cg = w.Cg, Co = w.Co;
+  for (int t = 0; t < 25; ++t)
+    UAD_REQUIRE(w.taps.dh[t] == t / 5 - 1 && w.taps.dw[t] == t % 5 - 1, "wgrad_tc2: unexpected tap table");
+  TcWgrad2Params p;
+  memset(&p, 0, sizeof(p));
+  int nchunks;
+  wgrad_tc2_plan(Cg, Co, w.P, &p.ngroups, &p.tiles_per_group, &nchunks, &p.blocks_per_chunk);
+  UAD_REQUIRE(p.tiles_per_group * Co + 256 <= 512, "wgrad_tc2: TMEM budget exceeded");
+  const size_t need = (size_t)nchunks * w.Mp * Co * sizeof(float);
+  UAD_REQUIRE(ws && ws_bytes >= need, "wgrad_tc2: workspace too small (%zu < %zu)", ws_bytes, need);
+  p.B = w.B; p.lgMH = w.lgMH; p.lgMW = w.lgMW; p.Cg = Cg; p.Co = Co; p.ncb = Cg / 32;
+  p.nblocks = w.P / 32; p.Mp = w.Mp;
+  p.partial = reinterpret_cast<float*>(ws);
+  const size_t stage_bytes = kW2HaloBytes + 3u * 32u * Co * 4u;
+  p.stages = (int)((220 * 1024 - 1024 - 512) / stage_bytes);
+  if (p.stages > 4) p.stages = 4;
+  UAD_REQUIRE(p.stages >= 2, "wgrad_tc2: shared-memory budget exceeded");
+
+  const cuuint64_t e = sizeof(float);
+  const int MH = 1 << w.lgMH, MW = 1 << w.lgMW;
+  CUtensorMap tmap_g, tmap_o;
+  {   // gathered fine tensor [B, GH, GW, Cg] viewed as (2*Cg, GW/2, 2, GH/2, B); box = (32 ch, 10, 1, 6, 1): one plane's halo
+    cuuint64_t dims[5] = {2ull * Cg, (cuuint64_t)w.GW / 2, 2, (cuuint64_t)w.GH / 2, (cuuint64_t)w.B};
+    cuuint64_t strides[4] = {2ull * Cg * e, (cuuint64_t)w.GW * Cg * e, 2ull * w.GW * Cg * e, (cuuint64_t)w.GH * w.GW * Cg * e};
+    cuuint32_t box[5] = {32, UAD_WT_HALO_W, 1, UAD_WT_HALO_H, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = encode(&tmap_g, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(w.g), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAD_REQUIRE(cr == CUDA_SUCCESS, "wgrad_tc2: cuTensorMapEncodeTiled(g) failed (%d)", (int)cr);
+  }
+  {   // coarse tensor [B, MH, MW, Co]; box = (32 ch, 8, 4, 1)
+    cuuint64_t dims[4] = {(cuuint64_t)Co, (cuuint64_t)MW, (cuuint64_t)MH, (cuuint64_t)w.B};
+    cuuint64_t strides[3] = {(cuuint64_t)Co * e, (cuuint64_t)MW * Co * e, (cuuint64_t)MH * MW * Co * e};
+    cuuint32_t box[4] = {32, kWPW, kWPH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(w.o), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAD_REQUIRE(cr == CUDA_SUCCESS, "wgrad_tc2: cuTensorMapEncodeTiled(o) failed (%d)", (int)cr);
+  }
+  const size_t smem = 1024 + p.stages * stage_bytes + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UAD_CUDA(cudaFuncSetAttribute(wgrad_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(nchunks, p.ngroups * p.ncb);
+  wgrad_tc2<<<grid, 384, smem, st>>>(tmap_g, tmap_o, p);
+  UAD_LAUNCH_CHECK("wgrad_tc2");
+  return uad_launch_splitk_reduce(p.partial, nchunks, (size_t)w.Mp * Co, out, accumulate, st);
 }
 
 int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1866,6 +2161,11 @@ int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* 
   UAD_REQUIRE(w.sh == 2 && w.taps.n == 25, "wgrad_tc: only the 5x5 stride-2 gather is implemented");
   EncodeTiledFn encode = get_encode_fn();
   UAD_REQUIRE(encode != nullptr, "wgrad_tc: cuTensorMapEncodeTiled entry point unavailable");
+  {
+    static int use_v2 = -1;
+    if (use_v2 < 0) { const char* ev = getenv("UAD_WGRAD_V2"); use_v2 = ev ? atoi(ev) : 0; }
+    if (use_v2 && Co <= 64) return launch_wgrad_tc2(w, out, accumulate, ws, ws_bytes, st, encode);
+  }
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
   int nchunks;
