@@ -31,10 +31,11 @@ def _run(op, B, H, Cin, Cout, mode, accumulate=0, seed=0):
     return dw.cpu().numpy()
 
 
-# Form W: conv_wgrad gathers x (Cg = Cin, Co = Cout); convT_wgrad gathers dz (Cg = Cout, Co = Cin).  wgrad_tc2 serves Co <= 64.
+# Form W: conv_wgrad gathers x (Cg = Cin, Co = Cout); convT_wgrad gathers dz (Cg = Cout, Co = Cin).  Window tiles per CTA: 5 / 3 / 2 at Co = 32 / 64 / 128.
 @pytest.mark.parametrize('op,B,H,Cin,Cout', [('convT_wgrad', 64, 128, 32, 32), ('convT_wgrad', 16, 64, 64, 32), ('conv_wgrad', 64, 128, 32, 64),
                                              ('conv_wgrad', 16, 64, 64, 64), ('convT_wgrad', 8, 32, 64, 128), ('conv_wgrad', 3, 16, 32, 32),
-                                             ('convT_wgrad', 2, 8, 32, 32)])
+                                             ('convT_wgrad', 2, 8, 32, 32), ('conv_wgrad', 64, 64, 64, 128), ('conv_wgrad', 16, 32, 128, 128),
+                                             ('convT_wgrad', 16, 16, 128, 128)])
 @pytest.mark.parametrize('accumulate', [0, 1])
 def test_plane_resident_wgrad_matches_fp32_simt(op, B, H, Cin, Cout, accumulate):
     a = _run(op, B, H, Cin, Cout, 1, accumulate)

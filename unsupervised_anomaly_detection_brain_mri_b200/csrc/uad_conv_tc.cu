@@ -2092,7 +2092,7 @@ static void wgrad_tc2_plan(int Cg, int Co, int P, int* ngroups, int* tpg, int* n
 size_t uad_tc_wgrad_ws_bytes(int Cg, int Co, int P) {
   int ng, tpg, qt, nch, bpc;
   wgrad_tc_plan(Cg, Co, P, &ng, &tpg, &qt, &nch, &bpc);
-  if (Co <= 64) {                                       // the candidate kernel shares the workspace: size it for either plan
+  {                                                     // the candidate kernel shares the workspace: size it for either plan
     int ng2, tpg2, nch2, bpc2;
     wgrad_tc2_plan(Cg, Co, P, &ng2, &tpg2, &nch2, &bpc2);
     if (nch2 > nch) nch = nch2;
@@ -2100,7 +2100,8 @@ size_t uad_tc_wgrad_ws_bytes(int Cg, int Co, int P) {
   return (size_t)nch * 25 * Cg * Co * sizeof(float) + 1024;
 }
 
-// UAD_WGRAD_V2=1 (developer switch, default 0): the round-2 CANDIDATE kernel wgrad_tc2 for Co <= 64 - not yet run on hardware
+// UAD_WGRAD_V2=1 (developer switch, default 0): the round-2 CANDIDATE kernel wgrad_tc2 - not yet run on hardware
+// (window tiles per CTA: 5 at Co = 32, 3 at Co = 64, 2 at Co = 128; stages 4 / 3 / 2)
 static int launch_wgrad_tc2(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st,
                             EncodeTiledFn encode) {
   const int Cg = w.Cg, Co = w.Co;
@@ -2164,7 +2165,7 @@ int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* 
   {
     static int use_v2 = -1;
     if (use_v2 < 0) { const char* ev = getenv("UAD_WGRAD_V2"); use_v2 = ev ? atoi(ev) : 0; }
-    if (use_v2 && Co <= 64) return launch_wgrad_tc2(w, out, accumulate, ws, ws_bytes, st, encode);
+    if (use_v2) return launch_wgrad_tc2(w, out, accumulate, ws, ws_bytes, st, encode);
   }
   TcWgradParams p;
   memset(&p, 0, sizeof(p));
