@@ -1,13 +1,15 @@
 #!/bin/bash
-# FIRST GPU call of round 2 (~6 GPU-minutes): answers the open hardware questions left at the end of round 1, which
-# had no GPU minutes left when the candidates were written.  usage: gpurun --timeout 900 -- 'bash tools/gpu_round2_entry.sh'
+# FIRST GPU call of round 2 (~15-20 GPU-minutes; every stage has its own timeout, worst case ~55 min): answers the open hardware questions left at the end of round 1, which
+# had no GPU minutes left when the candidates were written.  usage: gpurun --timeout 3400 -- 'bash tools/gpu_round2_entry.sh'
 #   1. the shipped defaults (even stage ring at N = 64, N = 128 on the first-generation kernel) were derived on CPU from the
 #      barrier-protocol model - confirm the GPU suite and re-measure the headline;
 #   2. tools/ubench/operand_probe.cu: tf32 operand forms the Form-W redesign needs (MN-major SWIZZLE_128B_BASE32B operands,
 #      row-shifted descriptors, truncation of raw fp32 words);
 #   3. the N = 32 candidate kernel gather_gemm_tc3 (UAD_TC_V3=1): correctness, then time against the shipped kernel;
 #   4. the compositions that so far only ran through the CPU emulation of the ABI (AnoVAEGAN, AAE / constrained AAE, CE, GMVAE incl. its latent kernel pair):
-#      real-kernel parity, CUDA-graph replay, trainers (UAD_UNVERIFIED=1) - drop the skip markers of the files that pass.
+#      real-kernel parity, CUDA-graph replay, trainers (UAD_UNVERIFIED=1) - drop the skip markers of the files that pass;
+#   5. swizzled epilogue staging (UAD_TC_V2=21): N = 128 column-split dual issue on an even four-stage ring;
+#   6. plane-resident Form-W kernel wgrad_tc2 (UAD_WGRAD_V2=1) - read experiment E7 of step 2 first.
 TAG=${1:-r2a}
 mkdir -p gpurun_out build
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
