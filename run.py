@@ -81,34 +81,45 @@ def get_evaluation_dataset(options, dataset=Dataset.BRAINWEB):
     return get_datasets(options, dataset=dataset)[1]
 
 
+# the reference's command line (reference run.py:119-152): short flag, long flag, default, type, help
+FLAGS = [
+    ('-c', '--config', 'config.default.json', str, 'config-path'),
+    ('-b', '--batchsize', 8, int, 'batchsize'),
+    ('-l', '--lr', 0.0001, float, 'learning rate'),
+    ('-E', '--numEpochs', 1000, int, 'how many epochs to train'),
+    ('-z', '--zDim', 128, int, 'Latent dimension'),
+    ('-w', '--outputWidth', 128, int, 'Output width'),
+    ('-g', '--outputHeight', 128, int, 'Output height'),
+    ('-o', '--optimizer', 'ADAM', str, 'Can be either ADAM, SGD or RMSProp'),
+    ('-s', '--slices_start', 20, int, 'slices start'),
+    ('-e', '--slices_end', 130, int, 'slices end'),
+    ('-t', '--trainer', 'AE', str, 'Can be every class from trainers directory'),
+    ('-m', '--model', 'autoencoder', str, 'Can be every class from models directory'),
+    ('-O', '--threshold', None, float, 'Use predefined ThreshOld'),
+    ('-d', '--ds', None, lambda name: Dataset[name], 'Only evaluate on given dataset'),
+    ('-n', '--numMonteCarloSamples', 0, int, 'Amount of Monte Carlos Samples during restoration'),
+    ('-G', '--use_gradient_based_restoration', False, bool, 'only for ceVAE'),
+    ('-L', '--restore_lr', 1e-3, float, 'only for VAE_You / GMVAE'),
+    ('-S', '--restore_steps', 150, int, 'only for VAE_You / GMVAE'),
+    ('-T', '--tv_lambda', -1.0, float, 'only for VAE_You / GMVAE'),
+    ('-K', '--kappa', 1.0, float, 'only for GANs'),
+    ('-M', '--scale', 10.0, float, 'only for GANs'),
+    ('-R', '--rho', 1.0, float, 'only for ConstrainedAAE'),
+    ('-C', '--dim_c', 9, int, 'only for GMVAE'),
+    ('-Z', '--dim_z', 128, int, 'only for GMVAE'),
+    ('-W', '--dim_w', 1, int, 'only for GMVAE'),
+    ('-A', '--c_lambda', 1, int, 'only for GMVAE'),
+]
+
+
+def build_parser():
+    parser = argparse.ArgumentParser(description='Framework')
+    for short, long_, default, type_, help_ in FLAGS:
+        parser.add_argument(short, long_, default=default, type=type_, help=help_)
+    parser.add_argument('-i', '--intermediateResolutions', default=(8, 8), type=int, nargs=2, help='Spatial Bottleneck resolution')
+    parser.add_argument('--numPatients', default=0, type=int, help='synthetic dataset size (patients x 110 slices)')
+    return parser
+
+
 if __name__ == '__main__':
-    args = argparse.ArgumentParser(description='Framework')
-    args.add_argument('-c', '--config', default='config.default.json', type=str, help='config-path')
-    args.add_argument('-b', '--batchsize', default=8, type=int, help='batchsize')
-    args.add_argument('-l', '--lr', default=0.0001, type=float, help='learning rate')
-    args.add_argument('-E', '--numEpochs', default=1000, type=int, help='how many epochs to train')
-    args.add_argument('-z', '--zDim', default=128, type=int, help='Latent dimension')
-    args.add_argument('-w', '--outputWidth', default=128, type=int, help='Output width')
-    args.add_argument('-g', '--outputHeight', default=128, type=int, help='Output height')
-    args.add_argument('-o', '--optimizer', default='ADAM', type=str, help='Can be either ADAM, SGD or RMSProp')
-    args.add_argument('-i', '--intermediateResolutions', default=(8, 8), type=int, nargs=2, help='Spatial Bottleneck resolution')
-    args.add_argument('-s', '--slices_start', default=20, type=int, help='slices start')
-    args.add_argument('-e', '--slices_end', default=130, type=int, help='slices end')
-    args.add_argument('-t', '--trainer', default='AE', type=str, help='Can be every class from trainers directory')
-    args.add_argument('-m', '--model', default='autoencoder', type=str, help='Can be every class from models directory')
-    args.add_argument('-O', '--threshold', default=None, type=float, help='Use predefined ThreshOld')
-    args.add_argument('-d', '--ds', default=None, type=lambda s: Dataset[s], help='Only evaluate on given dataset')
-    args.add_argument('-n', '--numMonteCarloSamples', default=0, type=int, help='Amount of Monte Carlos Samples during restoration')
-    args.add_argument('-G', '--use_gradient_based_restoration', default=False, type=bool, help='only for ceVAE')
-    args.add_argument('-L', '--restore_lr', default=1e-3, type=float, help='only for VAE_You / GMVAE')
-    args.add_argument('-S', '--restore_steps', default=150, type=int, help='only for VAE_You / GMVAE')
-    args.add_argument('-T', '--tv_lambda', default=-1.0, type=float, help='only for VAE_You / GMVAE')
-    args.add_argument('-K', '--kappa', default=1.0, type=float, help='only for GANs')
-    args.add_argument('-M', '--scale', default=10.0, type=float, help='only for GANs')
-    args.add_argument('-R', '--rho', default=1.0, type=float, help='only for ConstrainedAAE')
-    args.add_argument('-C', '--dim_c', default=9, type=int, help='only for GMVAE')
-    args.add_argument('-Z', '--dim_z', default=128, type=int, help='only for GMVAE')
-    args.add_argument('-W', '--dim_w', default=1, type=int, help='only for GMVAE')
-    args.add_argument('-A', '--c_lambda', default=1, type=int, help='only for GMVAE')
-    args.add_argument('--numPatients', default=0, type=int, help='synthetic dataset size (patients x 110 slices)')
-    main(args.parse_args())
+    main(build_parser().parse_args())

@@ -315,3 +315,22 @@ def test_evaluate_orchestration_keys_and_files(tmp_path, monkeypatch):
     ev2 = Ev.evaluate(None, model, options, epoch='3')
     assert ev2['thresholdType'] == 0.1 and ev2['threshold'] == 0.1 and not ev2['evalDir'].endswith('bestdice')
     assert ev2['FPCC'] == 1
+
+
+def test_run_py_keeps_the_reference_command_line():
+    """Flag set of reference run.py:119-152 (short + long spellings); --numPatients is the one addition (synthetic data size)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('uad_run', os.path.join(root, 'run.py'))
+    run = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(run)
+    have = {tuple(a.option_strings) for a in run.build_parser()._actions if a.dest != 'help'}
+    want = {('-c', '--config'), ('-b', '--batchsize'), ('-l', '--lr'), ('-E', '--numEpochs'), ('-z', '--zDim'), ('-w', '--outputWidth'),
+            ('-g', '--outputHeight'), ('-o', '--optimizer'), ('-i', '--intermediateResolutions'), ('-s', '--slices_start'),
+            ('-e', '--slices_end'), ('-t', '--trainer'), ('-m', '--model'), ('-O', '--threshold'), ('-d', '--ds'),
+            ('-n', '--numMonteCarloSamples'), ('-G', '--use_gradient_based_restoration'), ('-K', '--kappa'), ('-M', '--scale'),
+            ('-R', '--rho'), ('-C', '--dim_c'), ('-Z', '--dim_z'), ('-W', '--dim_w'), ('-A', '--c_lambda'), ('-L', '--restore_lr'),
+            ('-S', '--restore_steps'), ('-T', '--tv_lambda')}
+    assert have == want | {('--numPatients',)}
+    args = run.build_parser().parse_args(['-t', 'VAE', '-m', 'variational_autoencoder', '-d', 'MSLUB', '-i', '16', '16'])
+    assert args.trainer == 'VAE' and args.ds.name == 'MSLUB' and args.intermediateResolutions == [16, 16] and args.lr == 1e-4
