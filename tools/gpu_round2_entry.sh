@@ -9,7 +9,8 @@
 #   4. the compositions that so far only ran through the CPU emulation of the ABI (AnoVAEGAN, AAE / constrained AAE, CE, GMVAE incl. its latent kernel pair):
 #      real-kernel parity, CUDA-graph replay, trainers (UAD_UNVERIFIED=1) - drop the skip markers of the files that pass;
 #   5. swizzled epilogue staging (UAD_TC_V2=21): N = 128 column-split dual issue on an even four-stage ring;
-#   6. plane-resident Form-W kernel wgrad_tc2 (UAD_WGRAD_V2=1) - read experiment E7 of step 2 first.
+#   6. plane-resident Form-W kernel wgrad_tc2 (UAD_WGRAD_V2=1) - read experiment E7 of step 2 first;
+#   7. SS-form gather kernel gather_gemm_ss (UAD_TC_SS bit mask) - pre-split activations, no converter warps.
 TAG=${1:-r2a}
 mkdir -p gpurun_out build
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
@@ -42,3 +43,10 @@ UAD_WGRAD_V2=1 timeout 300 python -m pytest tests/test_gpu_wgrad_v2_candidate.py
 tail -5 gpurun_out/${TAG}_wgrad2_pytest.log
 UAD_WGRAD_V2=1 timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers_wgrad2.json > gpurun_out/${TAG}_bench_wgrad2.json 2> gpurun_out/${TAG}_bench_wgrad2.err
 cat gpurun_out/${TAG}_bench_wgrad2.json
+# 7. SS-form candidate (gather_gemm_ss): pre-split activations, TMA -> MMA ring without converters
+UAD_TC_SS=7 timeout 300 python -m pytest tests/test_gpu_ss_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_ss_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_ss_pytest.log
+for m in 1 3 7; do
+  UAD_TC_SS=$m timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers_ss$m.json > gpurun_out/${TAG}_bench_ss$m.json 2> gpurun_out/${TAG}_bench_ss$m.err
+  cat gpurun_out/${TAG}_bench_ss$m.json
+done

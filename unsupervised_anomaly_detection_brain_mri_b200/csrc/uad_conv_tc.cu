@@ -1336,6 +1336,248 @@ gather_gemm_tc3(const __grid_constant__ CUtensorMap tmap, const __grid_constant_
 }
 
 
+// ------------------------------------------------------------------------------------------------ the kernel, SS form (CANDIDATE)
+// Round-2 candidate written after round 1's GPU budget was spent: compiled, NEVER RUN on hardware, opt-in only (UAD_TC_SS bit
+// mask: 1 = N = 128 layers, 2 = N = 64, 4 = N = 32).  Idea: at N = 128 a tf32 MMA costs 64 cycles whether A comes from tensor
+// memory or from shared memory (profiles/r1_ubench_mma_rate.txt), so the whole converter apparatus (smem -> registers -> split ->
+// tcgen05.st -> barrier round trips, the measured reason the tensor pipe is 25-50 % busy) buys nothing there.  Here the
+// activation tensor is split ONCE per call into tf32 {hi, lo} images in the workspace (split_hilo_kernel, HBM-bound: 12 bytes
+// per element), TMA loads the hi and the lo tile of a k-block straight into the K-major SWIZZLE_128B form the descriptors read,
+// and the issuer's only dependency is the TMA barrier: the classic two-role TMA -> MMA ring.
+// 8 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM alloc | 3 epilogue constants | 4-7 epilogue.
+__global__ void split_hilo_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+// D[tmem] (+)= A[smem desc] . B[smem desc]
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+gather_gemm_ss(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+               const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int N = p.N;
+  const uint32_t b_bytes = 2u * N * 128u;
+  const uint32_t stage_bytes = 2u * kABytes + b_bytes;  // [A_hi tile | A_lo tile | B_hi rows, B_lo rows]
+  const int S = p.stages;
+  const uint32_t misc = smem_base + S * stage_bytes;
+  const uint32_t bar_full = misc;                       // S x 8   (S <= 8)
+  const uint32_t bar_empty = misc + 64;                 // S x 8
+  const uint32_t bar_accfull = misc + 128;              // 2 x 8
+  const uint32_t bar_accempty = misc + 144;             // 2 x 8
+  const uint32_t tmem_slot = misc + 160;
+  float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 320);               // bias[N], scale[N], shift[N]
+  float* stg_base = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 320 + 3 * N * 4);   // 4 warps x 32 x 36 staging
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t acc_cols = p.nacc * N;                 // columns of one accumulator set
+  const int nclasses = p.nclasses;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accempty + 8 * i, 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 3) {
+    for (int n = lane; n < N; n += 32) {
+      epi[n] = p.bias ? p.bias[n] : 0.f;
+      epi[N + n] = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
+      epi[2 * N + n] = p.beta ? p.beta[n] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer: hi tile, lo tile, weight image
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_lo) : "memory");
+      int s = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int cls = item % nclasses, tile = item / nclasses;
+        const TapSet& ts = p.taps[cls];
+        const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tbi = tile / (p.tiles_w * p.tiles_h);
+        const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+        const int nkb = ts.n * p.Cblks;
+        int tap = 0, cb = 0;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t full = bar_full + 8 * s;
+          mbar_expect_tx(full, 2u * (uint32_t)kABytes + b_bytes);
+          const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
+          const uint32_t a_dst = smem_base + s * stage_bytes;
+          if (p.stride2) {
+            tma_load_5d(a_dst, &tmap_hi, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
+            tma_load_5d(a_dst + kABytes, &tmap_lo, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
+          } else {
+            tma_load_5d(a_dst, &tmap_hi, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
+            tma_load_5d(a_dst + kABytes, &tmap_lo, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
+          }
+          const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
+          bulk_load(a_dst + 2 * kABytes, wsrc, b_bytes, full);
+          if (++cb == p.Cblks) { cb = 0; ++tap; }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (whole warp converged, one elected lane issues)
+    const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
+    const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
+    const uint64_t adesc0 = make_sw128_desc(smem_base);                      // A_hi tile of stage 0
+    const uint32_t stage_units = stage_bytes >> 4, a_units = (uint32_t)kABytes >> 4, lo_units = (uint32_t)(N * 128) >> 4;
+    const bool paired = (N <= 64);
+    int s = 0, buf = 0;
+    uint32_t ph = 0, phb = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int nkb = p.taps[item % nclasses].n * p.Cblks;
+      mbar_wait(bar_accempty + 8 * buf, phb ^ 1);               // epilogue has drained this accumulator set
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + buf * acc_cols;
+      int g = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(bar_full + 8 * s, ph);                        // all three TMA transfers of the stage landed
+        tc_fence_after();
+        const uint64_t ahi = adesc0 + (uint64_t)(s * stage_units);
+        const uint64_t alo = ahi + a_units;
+        const uint64_t bhi = ahi + 2 * a_units;                 // B image: hi rows, then lo rows
+        const uint32_t first = (i >= p.G) ? 1u : 0u;            // accumulator g already holds a partial sum of this item?
+        if (elect_one()) {
+          if (paired) {
+            const uint32_t d_pair = acc0 + g * 2 * N;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                       // K = 8 tf32 per instruction -> 32 bytes (2 x 16 B) along the row
+              mma_tf32_ss(d_pair, ahi + 2 * j, bhi + 2 * j, idesc2N, first | (j != 0));
+              mma_tf32_ss(d_pair + N, alo + 2 * j, bhi + 2 * j, idescN, 1u);
+            }
+          } else {
+            const uint32_t d_main = acc0 + g * N;
+            const uint32_t d_corr = acc0 + p.G * N;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              mma_tf32_ss(d_corr, alo + 2 * j, bhi + 2 * j, idescN, (i | j) != 0);
+              mma_tf32_ss(d_corr, ahi + 2 * j, bhi + lo_units + 2 * j, idescN, 1u);
+              mma_tf32_ss(d_main, ahi + 2 * j, bhi + 2 * j, idescN, first | (j != 0));
+            }
+          }
+          tc_commit(bar_empty + 8 * s);                         // smem stage reusable once these MMAs retire
+          if (i == nkb - 1) tc_commit(bar_accfull + 8 * buf);   // accumulators of this item complete
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++g == p.G) g = 0;
+      }
+      if (++buf == p.acc_bufs) { buf = 0; phb ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue group (as gather_gemm_tc3's)
+    const int row = threadIdx.x - 128;                          // tile row == TMEM lane
+    const int q = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* stg = stg_base + (size_t)q * 32 * 36;                // this warp's 32 x (32+4) staging rows
+    const int nchunks = N >> 5;
+    int buf = 0;
+    uint32_t phb = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int cls = item % nclasses, tile = item / nclasses;
+      const TapSet& ts = p.taps[cls];
+      const uint32_t acc_base = lane_base + buf * acc_cols;
+      const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, tbi = tile / (p.tiles_w * p.tiles_h);
+      const int s0 = twi * p.TW, r0 = thi * p.TH, b0 = tbi * p.TB;
+      const int tw = row & (p.TW - 1);
+      const int th = (row >> p.lgTW) & (p.TH - 1);
+      const int tb = row >> (p.lgTW + p.lgTH);
+      const int b = b0 + tb;
+      const long long my_off = (b < p.B)
+          ? (((long long)b * p.OH + ((r0 + th) * p.osh + ts.oh0)) * p.OW + ((s0 + tw) * p.osh + ts.ow0)) * (long long)N
+          : -1;
+      mbar_wait(bar_accfull + 8 * buf, phb);
+      tc_fence_after();
+      long long offs[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + (lane >> 3));
+      const int cq = (lane & 7) * 4;
+      for (int c = 0; c < nchunks; ++c) {
+        const int c0 = c * 32;
+        uint32_t v[32], u[32];
+        tmem_ld32(acc_base + c0, v);                            // accumulator k of output columns c0..c0+31: k * N + c0
+        for (int k = 1; k < p.nacc; ++k) {
+          tmem_ld32(acc_base + k * N + c0, u);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
+        tmem_wait_ld();
+        if (c + 1 == nchunks) {                                 // last TMEM read of this thread for the item: hand the set back
+          tc_fence_before();
+          mbar_arrive(bar_accempty + 8 * buf);
+        }
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {                  // z then a from the SAME registers
+          float* out = pass == 0 ? p.z_out : p.a_out;
+          if (!out) continue;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int n = c0 + j + e;
+              const float z = __uint_as_float(v[j + e]) + epi[n];
+              o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], p.act, p.alpha);
+            }
+            *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          __syncwarp();
+          float4 vals[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) vals[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * 36 + cq);
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (offs[it] >= 0) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = vals[it];
+          __syncwarp();
+        }
+      }
+      if (++buf == p.acc_bufs) { buf = 0; phb ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight images
 // raw weights -> per (tap, 32-channel block): {hi, lo} images of [N rows][32 k] fp32 in the SWIZZLE_128B byte order the
 // UMMA descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n]; true: raw[t][n][c].
@@ -1874,6 +2116,19 @@ size_t uad_tc_gather_ws_bytes(int ksize, int Cin, int N) {
   return (size_t)ksize * ksize * Cin * N * 2 * sizeof(float) + 1024;
 }
 
+// UAD_TC_SS (bit mask, default 0): 1 = N = 128 layers, 2 = N = 64, 4 = N = 32 run the candidate kernel gather_gemm_ss
+static bool tc_ss_enabled(int N) {
+  static int use_ss = -1;
+  if (use_ss < 0) { const char* ev = getenv("UAD_TC_SS"); use_ss = ev ? atoi(ev) : 0; }
+  return (N == 128 && (use_ss & 1)) || (N == 64 && (use_ss & 2)) || (N == 32 && (use_ss & 4));
+}
+
+// extra workspace behind the weight images when the candidate SS kernel is switched on: the {hi, lo} images of the input
+size_t uad_tc_gather_ss_extra_bytes(int N, size_t in_elems) {
+  if (!tc_ss_enabled(N)) return 0;
+  return 2 * ((in_elems * sizeof(float) + 1023) & ~(size_t)1023) + 2048;
+}
+
 int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
                          int math_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   UAD_REQUIRE(math_mode == UAD_MATH_TC_3XTF32, "gather_gemm_tc: only the 3xTF32 mode is implemented (got %d)", math_mode);
@@ -1945,6 +2200,49 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UAD_REQUIRE(cr == CUDA_SUCCESS, "gather_gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+  if (tc_ss_enabled(N)) {
+    // ---- UAD_TC_SS (bit mask, developer switch, default 0): the round-2 CANDIDATE kernel gather_gemm_ss - not yet run on hardware
+    const size_t in_elems = (size_t)g.B * g.IH * g.IW * C;
+    const size_t img_bytes = (need + 1023) & ~(size_t)1023;
+    const size_t in_bytes = (in_elems * sizeof(float) + 1023) & ~(size_t)1023;
+    UAD_REQUIRE(ws_bytes >= img_bytes + 2 * in_bytes, "gather_gemm_ss: workspace too small (%zu < %zu)", ws_bytes,
+                img_bytes + 2 * in_bytes);
+    float* xhi = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + img_bytes);
+    float* xlo = reinterpret_cast<float*>(reinterpret_cast<char*>(xhi) + in_bytes);
+    {
+      const size_t n4 = in_elems / 4;                      // C % 32 == 0
+      size_t blocks = uad_cdiv(n4, 256);
+      if (blocks > (size_t)UAD_NUM_SMS * 16) blocks = (size_t)UAD_NUM_SMS * 16;
+      split_hilo_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(g.in), reinterpret_cast<float4*>(xhi),
+                                                          reinterpret_cast<float4*>(xlo), n4);
+      UAD_LAUNCH_CHECK("split_hilo");
+    }
+    CUtensorMap tmap_hi, tmap_lo;
+    CUresult c1 = encode(&tmap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, xhi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult c2 = encode(&tmap_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, xlo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UAD_REQUIRE(c1 == CUDA_SUCCESS && c2 == CUDA_SUCCESS, "gather_gemm_ss: cuTensorMapEncodeTiled failed (%d, %d)", (int)c1, (int)c2);
+    p.G = 2;                                               // two main accumulators (or pairs): halves the accumulation chains
+    p.nacc = (N <= 64) ? 2 * p.G : p.G + 1;
+    p.acc_bufs = (2 * p.nacc * N <= 512) ? 2 : 1;          // N <= 64: the epilogue overlaps the next item's MMAs
+    const size_t stage_ss = 2u * kABytes + 2u * N * 128u;
+    const size_t tail_ss = 320 + 3 * N * sizeof(float) + 4 * 32 * 36 * sizeof(float) + 64;
+    p.stages = (int)((226 * 1024 - 1024 - tail_ss) / stage_ss);
+    if (p.stages > 8) p.stages = 8;
+    UAD_REQUIRE(p.stages >= 2, "gather_gemm_ss: shared-memory budget exceeded");
+    const size_t smem_ss = 1024 + p.stages * stage_ss + tail_ss;
+    static bool attr_ss = false;
+    if (!attr_ss) {
+      UAD_CUDA(cudaFuncSetAttribute(gather_gemm_ss, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_ss = true;
+    }
+    const int grid_ss = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
+    gather_gemm_ss<<<grid_ss, 256, smem_ss, st>>>(tmap_hi, tmap_lo, p);
+    UAD_LAUNCH_CHECK("gather_gemm_ss");
+    return 0;
+  }
 
   const size_t stage_bytes = kABytes + 2u * N * 128u;
   {
