@@ -53,3 +53,36 @@ def test_product_never_imports_the_oracle():
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(dp, f)
     for f in ('run.py', 'mains/main_AE.py', 'mains/main_VAE.py', 'mains/main_ceVAE.py'):
         assert not re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(ROOT, f)).read(), flags=re.M)
+
+
+def _ws_bytes_in_subprocess(env_extra):
+    """uad_conv_workspace_bytes is host-only code: query it in a fresh process (the developer switches are read once)."""
+    import json
+    import subprocess
+    import sys
+    code = ("import json, sys; sys.path.insert(0, %r)\n"
+            "from unsupervised_anomaly_detection_brain_mri_b200 import abi\n"
+            "L = abi.lib()\n"
+            "cases = [(0, 64, 64, 64, 128), (1, 64, 64, 128, 128), (3, 64, 16, 128, 128), (4, 64, 32, 128, 64), (0, 64, 128, 32, 64),\n"
+            "         (3, 16, 64, 64, 32), (2, 64, 128, 32, 64), (5, 64, 128, 32, 32), (2, 64, 32, 64, 128)]\n"
+            "print(json.dumps([int(L.uad_conv_workspace_bytes(op, B, H, H, ci, co, 5, 1)) for op, B, H, ci, co in cases]))\n") % ROOT
+    env = {k: v for k, v in os.environ.items() if not k.startswith('UAD_')}
+    env.update(env_extra)
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, check=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def test_workspace_query_covers_the_opt_in_kernel_candidates():
+    """Default sizes are untouched by the candidates' switches except where a candidate needs more: UAD_TC_SS adds the two
+    tf32 {hi, lo} images of the gathered tensor behind the weight images for the layers it is switched on for, and the
+    filter-gradient workspace is sized for the larger of the two split-K plans in every mode."""
+    base = _ws_bytes_in_subprocess({})
+    assert base == _ws_bytes_in_subprocess({'UAD_TC_V3': '1', 'UAD_TC_V2': '21', 'UAD_WGRAD_V2': '1'})
+    ss = _ws_bytes_in_subprocess({'UAD_TC_SS': '1'})                  # N = 128 layers only
+    gathered = [64 * 64 * 64 * 64, 64 * 32 * 32 * 128, 64 * 16 * 16 * 128, 64 * 64 * 64 * 64, 0, 0, 0, 0, 0]   # elements, 0 = not N = 128
+    for b, s, n in zip(base, ss, gathered):
+        extra = 0 if n == 0 else 2 * ((4 * n + 1023) // 1024 * 1024) + 2048
+        assert s == b + extra
+    ss_all = _ws_bytes_in_subprocess({'UAD_TC_SS': '7'})
+    assert all(s >= b for s, b in zip(ss_all, base)) and ss_all[4] > base[4] and ss_all[5] > base[5]
+    assert ss_all[6:] == base[6:]                                      # filter-gradient ops never use the SS images
