@@ -3,6 +3,8 @@ once per call into tf32 {hi, lo} images, both operands read from shared memory t
 Written after round 1's GPU budget was spent; never run, so skipped unless the process is started with UAD_TC_SS=7
 (1: N = 128 layers, 2: N = 64, 4: N = 32; the launcher and the workspace-size query read the switch once):
     UAD_TC_SS=7 python -m pytest tests/test_gpu_ss_candidate.py -m gpu
+UAD_TC_SS=15 additionally feeds the RAW fp32 tensor as the hi operand (only the lo image is written): passes iff kind::tf32
+truncates its operands (experiment E1 of tools/ubench/operand_probe.cu) - a failure there is an answer, not a bug.
 Compares the tcgen05 path (3xTF32) with the exact-fp32 SIMT path on shapes of both GEMM forms and all three widths."""
 import os
 
@@ -11,7 +13,7 @@ import pytest
 
 from test_gpu_swz_candidate import _run
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('UAD_TC_SS') != '7', reason='opt-in: UAD_TC_SS=7')]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('UAD_TC_SS') not in ('7', '15'), reason='opt-in: UAD_TC_SS=7 (or 15)')]
 
 
 # GEMM N: conv_fwd / convT_fwd -> Cout, conv_dgrad / convT_dgrad -> Cin

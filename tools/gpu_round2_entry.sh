@@ -46,7 +46,9 @@ cat gpurun_out/${TAG}_bench_wgrad2.json
 # 7. SS-form candidate (gather_gemm_ss): pre-split activations, TMA -> MMA ring without converters
 UAD_TC_SS=7 timeout 300 python -m pytest tests/test_gpu_ss_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_ss_pytest.log 2>&1
 tail -5 gpurun_out/${TAG}_ss_pytest.log
-for m in 1 3 7; do
+UAD_TC_SS=15 timeout 300 python -m pytest tests/test_gpu_ss_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_ss_rawhi_pytest.log 2>&1   # raw tensor as hi operand: passes iff the tensor core truncates (E1)
+tail -3 gpurun_out/${TAG}_ss_rawhi_pytest.log
+for m in 1 3 7 9; do
   UAD_TC_SS=$m timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers_ss$m.json > gpurun_out/${TAG}_bench_ss$m.json 2> gpurun_out/${TAG}_bench_ss$m.err
   cat gpurun_out/${TAG}_bench_ss$m.json
 done

@@ -1353,7 +1353,7 @@ __global__ void split_hilo_kernel(const float4* __restrict__ x, float4* __restri
     h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
     h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
-    hi[i] = h;
+    if (hi) hi[i] = h;                                   // hi == nullptr: UAD_TC_SS bit 8 (the raw tensor serves as the hi operand)
     lo[i] = l;
   }
 }
@@ -2116,11 +2116,17 @@ size_t uad_tc_gather_ws_bytes(int ksize, int Cin, int N) {
   return (size_t)ksize * ksize * Cin * N * 2 * sizeof(float) + 1024;
 }
 
-// UAD_TC_SS (bit mask, default 0): 1 = N = 128 layers, 2 = N = 64, 4 = N = 32 run the candidate kernel gather_gemm_ss
-static bool tc_ss_enabled(int N) {
+// UAD_TC_SS (bit mask, default 0): 1 = N = 128 layers, 2 = N = 64, 4 = N = 32 run the candidate kernel gather_gemm_ss;
+// 8 = the RAW fp32 tensor is the hi operand (only the lo image is written) - valid iff kind::tf32 truncates the low 13 mantissa
+// bits of its operands (experiment E1 of tools/ubench/operand_probe.cu); the numerics are then those of the explicit split
+static int tc_ss_mask() {
   static int use_ss = -1;
   if (use_ss < 0) { const char* ev = getenv("UAD_TC_SS"); use_ss = ev ? atoi(ev) : 0; }
-  return (N == 128 && (use_ss & 1)) || (N == 64 && (use_ss & 2)) || (N == 32 && (use_ss & 4));
+  return use_ss;
+}
+static bool tc_ss_enabled(int N) {
+  const int m = tc_ss_mask();
+  return (N == 128 && (m & 1)) || (N == 64 && (m & 2)) || (N == 32 && (m & 4));
 }
 
 // extra workspace behind the weight images when the candidate SS kernel is switched on: the {hi, lo} images of the input
@@ -2210,16 +2216,18 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
                 img_bytes + 2 * in_bytes);
     float* xhi = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + img_bytes);
     float* xlo = reinterpret_cast<float*>(reinterpret_cast<char*>(xhi) + in_bytes);
+    const bool raw_hi = (tc_ss_mask() & 8) != 0;
     {
       const size_t n4 = in_elems / 4;                      // C % 32 == 0
       size_t blocks = uad_cdiv(n4, 256);
       if (blocks > (size_t)UAD_NUM_SMS * 16) blocks = (size_t)UAD_NUM_SMS * 16;
-      split_hilo_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(g.in), reinterpret_cast<float4*>(xhi),
+      split_hilo_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(g.in),
+                                                          raw_hi ? nullptr : reinterpret_cast<float4*>(xhi),
                                                           reinterpret_cast<float4*>(xlo), n4);
       UAD_LAUNCH_CHECK("split_hilo");
     }
     CUtensorMap tmap_hi, tmap_lo;
-    CUresult c1 = encode(&tmap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, xhi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult c1 = encode(&tmap_hi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, raw_hi ? const_cast<float*>(g.in) : xhi, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CUresult c2 = encode(&tmap_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, xlo, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
