@@ -52,3 +52,7 @@ for m in 1 3 7 9; do
   UAD_TC_SS=$m timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers_ss$m.json > gpurun_out/${TAG}_bench_ss$m.json 2> gpurun_out/${TAG}_bench_ss$m.err
   cat gpurun_out/${TAG}_bench_ss$m.json
 done
+# per-kernel event timings of the two newest candidates (column 0 of each line = the kernel as it would ship)
+UAD_WGRAD_V2=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_wgrad2.txt 2>&1
+UAD_TC_SS=7 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_ss7.txt 2>&1
+tail -11 gpurun_out/${TAG}_time_tc_wgrad2.txt gpurun_out/${TAG}_time_tc_ss7.txt
