@@ -334,3 +334,27 @@ def test_run_py_keeps_the_reference_command_line():
     assert have == want | {('--numPatients',)}
     args = run.build_parser().parse_args(['-t', 'VAE', '-m', 'variational_autoencoder', '-d', 'MSLUB', '-i', '16', '16'])
     assert args.trainer == 'VAE' and args.ds.name == 'MSLUB' and args.intermediateResolutions == [16, 16] and args.lr == 1e-4
+
+
+def test_every_main_script_binds_to_existing_product_symbols():
+    """mains/main_*.py (mirrors of the reference's mains/, which are scripts that train on import): parse, do not run - every
+    `from <package>... import name` must resolve, none may touch the oracle, and the reference's hot-path mains all exist."""
+    import ast
+    import importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = 'unsupervised_anomaly_detection_brain_mri_b200'
+    have = sorted(f for f in os.listdir(os.path.join(root, 'mains')) if f.endswith('.py'))
+    for want in ('main_AE.py', 'main_AE_spatial.py', 'main_VAE.py', 'main_VAE_You.py', 'main_ceVAE.py', 'main_CE.py', 'main_constrainedAE.py',
+                 'main_AAE.py', 'main_constrainedAAE.py', 'main_GMVAE.py', 'main_GMVAE_spatial.py', 'main_fAnoGAN.py'):
+        assert want in have
+    for f in have:
+        tree = ast.parse(open(os.path.join(root, 'mains', f)).read(), f)
+        for node in ast.walk(tree):
+            if isinstance(node, ast.ImportFrom):
+                assert not node.module.startswith('oracle'), f
+                if node.module.startswith(pkg):
+                    mod = importlib.import_module(node.module)
+                    for alias in node.names:
+                        assert hasattr(mod, alias.name), (f, node.module, alias.name)
+            elif isinstance(node, ast.Import):
+                assert not any(a.name.startswith(('oracle', 'tensorflow')) for a in node.names), f
