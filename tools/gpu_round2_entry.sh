@@ -56,3 +56,6 @@ done
 UAD_WGRAD_V2=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_wgrad2.txt 2>&1
 UAD_TC_SS=7 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_ss7.txt 2>&1
 tail -11 gpurun_out/${TAG}_time_tc_wgrad2.txt gpurun_out/${TAG}_time_tc_ss7.txt
+# one-screen summary LAST, so that it is what gpurun's tail shows
+python tools/summarize_round2.py ${TAG} > gpurun_out/${TAG}_summary.txt 2>&1
+cat gpurun_out/${TAG}_summary.txt
