@@ -17,6 +17,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/operand_probe tools/ubench/operand_probe.cu \
   && timeout 120 build/operand_probe > gpurun_out/${TAG}_operand_probe.txt 2>&1
 cat gpurun_out/${TAG}_operand_probe.txt
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/l2_to_sm tools/ubench/l2_to_sm.cu \
+  && timeout 120 build/l2_to_sm > gpurun_out/${TAG}_l2_to_sm.txt 2>&1      # the L2 -> shared-memory ceiling the gather kernels run into next
+cat gpurun_out/${TAG}_l2_to_sm.txt
 ( time timeout 900 python -m pytest tests -m gpu -q --maxfail=15 -p no:cacheprovider ) > gpurun_out/${TAG}_pytest.log 2>&1
 tail -5 gpurun_out/${TAG}_pytest.log
 timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers.json > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err

@@ -42,6 +42,9 @@ def main(tag):
     for ln in (probe or 'missing').splitlines():
         if ln.startswith('E') or 'PASS' in ln or 'FAIL' in ln or 'error' in ln.lower():
             print('  ' + ln.rstrip())
+    print(f'== L2 -> shared memory ceiling ({tag}_l2_to_sm.txt)')
+    for ln in (read(f'{tag}_l2_to_sm.txt') or 'missing').splitlines():
+        print('  ' + ln.rstrip())
     print('== pytest stages')
     for stage, label in (('pytest', 'default -m gpu suite'), ('v3_pytest', 'UAD_TC_V3=1'), ('unverified_pytest', 'UAD_UNVERIFIED=1'),
                          ('swz_pytest', 'UAD_TC_V2=21'), ('wgrad2_pytest', 'UAD_WGRAD_V2=1'), ('ss_pytest', 'UAD_TC_SS=7'),
