@@ -10,7 +10,8 @@
 #      real-kernel parity, CUDA-graph replay, trainers (UAD_UNVERIFIED=1) - drop the skip markers of the files that pass;
 #   5. swizzled epilogue staging (UAD_TC_V2=21): N = 128 column-split dual issue on an even four-stage ring;
 #   6. plane-resident Form-W kernel wgrad_tc2 (UAD_WGRAD_V2=1) - read experiment E7 of step 2 first;
-#   7. SS-form gather kernel gather_gemm_ss (UAD_TC_SS bit mask) - pre-split activations, no converter warps.
+#   7. SS-form gather kernel gather_gemm_ss (UAD_TC_SS bit mask) - pre-split activations, no converter warps;
+#   8. halo-resident N = 32 kernel gather_gemm_tc_np_halo (UAD_TC_HALO=1) - a k-block loads only its weight image.
 TAG=${1:-r2a}
 mkdir -p gpurun_out build
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
@@ -60,5 +61,12 @@ UAD_WGRAD_V2=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_w
 UAD_TC_SS=7 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_ss7.txt 2>&1
 tail -11 gpurun_out/${TAG}_time_tc_wgrad2.txt gpurun_out/${TAG}_time_tc_ss7.txt
 # one-screen summary LAST, so that it is what gpurun's tail shows
+python tools/summarize_round2.py ${TAG} > gpurun_out/${TAG}_summary.txt 2>&1
+cat gpurun_out/${TAG}_summary.txt
+# 8. halo-resident N = 32 candidate (gather_gemm_tc_np_halo, stride-1 form): a k-block moves 8 KB instead of 24 KB
+UAD_TC_HALO=1 timeout 300 python -m pytest tests/test_gpu_halo_candidate.py -m gpu -q -p no:cacheprovider > gpurun_out/${TAG}_halo_pytest.log 2>&1
+tail -5 gpurun_out/${TAG}_halo_pytest.log
+UAD_TC_HALO=1 timeout 200 python tools/time_tc.py > gpurun_out/${TAG}_time_tc_halo.txt 2>&1
+UAD_TC_HALO=1 timeout 300 python bench.py --steps 30 --warmup 5 --layer-table gpurun_out/${TAG}_layers_halo.json > gpurun_out/${TAG}_bench_halo.json 2> gpurun_out/${TAG}_bench_halo.err
 python tools/summarize_round2.py ${TAG} > gpurun_out/${TAG}_summary.txt 2>&1
 cat gpurun_out/${TAG}_summary.txt

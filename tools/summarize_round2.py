@@ -48,7 +48,7 @@ def main(tag):
     print('== pytest stages')
     for stage, label in (('pytest', 'default -m gpu suite'), ('v3_pytest', 'UAD_TC_V3=1'), ('unverified_pytest', 'UAD_UNVERIFIED=1'),
                          ('swz_pytest', 'UAD_TC_V2=21'), ('wgrad2_pytest', 'UAD_WGRAD_V2=1'), ('ss_pytest', 'UAD_TC_SS=7'),
-                         ('ss_rawhi_pytest', 'UAD_TC_SS=15')):
+                         ('ss_rawhi_pytest', 'UAD_TC_SS=15'), ('halo_pytest', 'UAD_TC_HALO=1')):
         print(f'  {label:24s} {pytest_outcome(read(f"{tag}_{stage}.log"))}')
     print('== bench lines (slices/s, ms/step, e2e, dominant kernel frac)')
     for path in sorted(glob.glob(os.path.join(OUT, f'{tag}_bench*.json'))):

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "uad_conv.cuh"
+#include "uad_halo.h"
 #include "uad_staging.h"
 #include "uad_wgrad_tiles.h"
 
@@ -165,14 +166,20 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // N = 32; the persistent kernel wins for N >= 64).  For the transposed form the CTA walks all four output-parity
 // classes of its tile back to back: prologue / TMEM allocation are paid once per tile and the TMA producer keeps
 // prefetching the next class's operands while the current class is being written out.  Same numerics as below.
-__global__ void __launch_bounds__(256, 2)
-gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+// kHalo (round-2 candidate `gather_gemm_tc_np_halo`, opt-in UAD_TC_HALO=1, stride-1 form only, never run on hardware): the
+// activation operand is not TMA-loaded per k-block.  The (TH + 2) x (TW + 2) pixel halo of the 8 x 16 pixel tile is loaded ONCE
+// per 32-channel block and every tap's converter pass reads its shifted window from it, so a k-block moves only its 2 N x 128 B
+// weight image (8 KB instead of 24 KB at N = 32: DESIGN.md 4.1 (6), the L2 -> shared-memory ceiling), and the converters no
+// longer wait on the per-k-block TMA barrier.
+template <bool kHalo>
+__device__ __forceinline__ void gather_gemm_tc_np_body(const CUtensorMap& tmap, const TcParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int N = p.N;
   const uint32_t b_bytes = 2u * N * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t a_bytes = kHalo ? 0u : (uint32_t)kABytes;   // halo form: the stages hold weight images only
+  const uint32_t stage_bytes = a_bytes + b_bytes;
   const int S = p.stages;
   const int NS = p.nslots;
   const uint32_t misc = smem_base + S * stage_bytes;
@@ -182,8 +189,15 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   const uint32_t bar_aempty = misc + 160;               // NS x 8
   const uint32_t bar_acc = misc + 192;
   const uint32_t tmem_slot = misc + 200;
+  const uint32_t bar_halo = misc + 208;                 // halo form: all channel blocks of the tile's halo landed
   float* epi = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256);                 // bias[N], scale[N], shift[N]
   float* stg_base = reinterpret_cast<float*>(smem_gen + S * stage_bytes + 256 + 3 * N * 4);     // 4 x 32 x (N+4) staging
+
+  // halo form: per 32-channel block a (TH + 2) x (TW + 2) pixel tile of 128-byte rows behind the staging rows, 1024-byte aligned
+  const int halo_w = p.TW + 2;
+  const uint32_t halo_rows = (uint32_t)((p.TH + 2) * halo_w);
+  const uint32_t halo_bytes = (halo_rows * 128u + 1023u) & ~1023u;
+  const uint32_t halo_off = (S * stage_bytes + 256u + 3u * N * 4u + 4u * 32u * (N + 4) * 4u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t aoff = p.nacc * N;                     // first A slot column
@@ -200,6 +214,7 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     for (int i = 0; i < S; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < NS; ++i) { mbar_init(bar_afull + 8 * i, 128); mbar_init(bar_aempty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
+    if (kHalo) mbar_init(bar_halo, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -231,6 +246,11 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
       int s = 0;
       uint32_t ph = 0;
+      if (kHalo) {                                              // the tile's halo, once: box (32 ch, TW + 2, 1, TH + 2, 1)
+        mbar_expect_tx(bar_halo, (uint32_t)p.Cblks * halo_rows * 128u);
+        for (int cb = 0; cb < p.Cblks; ++cb)
+          tma_load_5d(smem_base + halo_off + cb * halo_bytes, &tmap, bar_halo, cb * kKBlk, s0 - 1, 0, r0 - 1, b0);
+      }
       for (int cls = 0; cls < ncls; ++cls) {
         const TapSet& ts = p.taps[cls];
         const int nkb = ts.n * p.Cblks;
@@ -239,16 +259,16 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           const uint32_t full = bar_full + 8 * s;
           // developer timing switches: 32 = skip the activation (A) load, 64 = skip the weight (B) load
-          mbar_expect_tx(full, ((p.debug & 32) ? 0u : (uint32_t)kABytes) + ((p.debug & 64) ? 0u : b_bytes));
+          mbar_expect_tx(full, ((kHalo || (p.debug & 32)) ? 0u : (uint32_t)kABytes) + ((p.debug & 64) ? 0u : b_bytes));
           const int dh = ts.dh[tap], dw = ts.dw[tap], wt = ts.wt[tap];
           const uint32_t a_dst = smem_base + s * stage_bytes;
-          if (p.debug & 32) {
+          if (kHalo || (p.debug & 32)) {
           } else if (p.stride2)
             tma_load_5d(a_dst, &tmap, full, (dw & 1) * p.C + cb * kKBlk, s0 + (dw >> 1), dh & 1, r0 + (dh >> 1), b0);
           else
             tma_load_5d(a_dst, &tmap, full, cb * kKBlk, s0 + dw, 0, r0 + dh, b0);
           const float* wsrc = p.wimg + ((size_t)(wt * p.Cblks + cb)) * 2 * N * kKBlk;
-          if (!(p.debug & 64)) bulk_load(a_dst + kABytes, wsrc, b_bytes, full);
+          if (!(p.debug & 64)) bulk_load(a_dst + a_bytes, wsrc, b_bytes, full);
           if (++cb == p.Cblks) { cb = 0; ++tap; }
           if (++s == S) { s = 0; ph ^= 1; }
         }
@@ -259,7 +279,7 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
     const uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
-    const uint64_t bdesc0 = make_sw128_desc(smem_base + kABytes);          // B image of stage 0 (hi rows then lo rows)
+    const uint64_t bdesc0 = make_sw128_desc(smem_base + a_bytes);          // B image of stage 0 (hi rows then lo rows)
     const uint32_t stage_units = stage_bytes >> 4;
     int s = 0, t = 0;
     uint32_t ph = 0, pht = 0;
@@ -309,20 +329,25 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int rows_per_it = 32 / lanes_per_row;
     int s = 0, t = 0;
     uint32_t ph = 0, pht = 0;
+    if (kHalo) mbar_wait(bar_halo, 0);                          // every window of every tap is read from the resident halo
     for (int cls = 0; cls < ncls; ++cls) {
       const TapSet& ts = p.taps[cls];
       const int nkb = ts.n * p.Cblks;
+      int tap = 0, cb = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(bar_full + 8 * s, ph);
+        if (!kHalo) mbar_wait(bar_full + 8 * s, ph);
         if (p.debug & 1) {
           mbar_wait(bar_aempty + 8 * t, pht ^ 1);
           mbar_arrive(bar_afull + 8 * t);
         } else {
-          const uint8_t* arow = smem_gen + s * stage_bytes + row * 128;
+          // halo form: pixel (th + dh, tw + dw) of the tile's halo, i.e. halo row (th + dh + 1) * (TW + 2) + tw + dw + 1
+          const int hrow = kHalo ? uad_halo_row(th, tw, ts.dh[tap], ts.dw[tap], p.TW) : 0;
+          const uint8_t* arow = kHalo ? smem_gen + halo_off + cb * halo_bytes + hrow * 128 : smem_gen + s * stage_bytes + row * 128;
+          const uint32_t swz_k = kHalo ? (uint32_t)(hrow & 7) : swz;
           uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {                         // 16-byte chunk j of this row sits at (j ^ (row & 7))
-            const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz) << 4));
+          for (int j = 0; j < 8; ++j) {                         // 16-byte chunk j of a row sits at (j ^ (row index & 7))
+            const float4 v = *reinterpret_cast<const float4*>(arow + ((j ^ swz_k) << 4));
             const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -340,6 +365,7 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
           tc_fence_before();
           mbar_arrive(bar_afull + 8 * t);
         }
+        if (kHalo) { if (++cb == p.Cblks) { cb = 0; ++tap; } }
         if (++s == S) { s = 0; ph ^= 1; }
         if (++t == NS) { t = 0; pht ^= 1; }
       }
@@ -425,6 +451,16 @@ gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
+}
+
+__global__ void __launch_bounds__(256, 2)
+gather_gemm_tc_np(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  gather_gemm_tc_np_body<false>(tmap, p);
+}
+
+__global__ void __launch_bounds__(256, 2)
+gather_gemm_tc_np_halo(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+  gather_gemm_tc_np_body<true>(tmap, p);
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -2333,6 +2369,39 @@ int uad_launch_gather_tc(const GatherParams& g, int nclasses, int ksize, bool we
     p.tmem_cols = (acc_cols + 128 <= 256) ? 256 : 512;
     p.nslots = (p.tmem_cols - acc_cols) / 64;
     if (p.nslots > 4) p.nslots = 4;
+    {
+      // ---- UAD_TC_HALO=1 (developer switch, default 0): the round-2 CANDIDATE gather_gemm_tc_np_halo - not yet run on hardware.
+      // Stride-1 form only (convT fwd / conv dgrad): 8 x 16 pixel tiles of ONE image, the 10 x 18 halo resident per channel block.
+      static int use_halo = -1;
+      if (use_halo < 0) { const char* ev = getenv("UAD_TC_HALO"); use_halo = ev ? atoi(ev) : 0; }
+      if (use_halo && !p.stride2 && MW >= 16 && MH >= 8) {
+        p.TW = 16; p.TH = 8; p.TB = 1; p.lgTW = 4; p.lgTH = 3;
+        p.tiles_w = MW / p.TW;
+        p.tiles_h = MH / p.TH;
+        p.n_items = p.tiles_w * p.tiles_h * g.B * nclasses;
+        CUtensorMap tmap_halo;
+        cuuint32_t hbox[5] = {(cuuint32_t)kKBlk, (cuuint32_t)(p.TW + 2), 1u, (cuuint32_t)(p.TH + 2), 1u};
+        CUresult ch = encode(&tmap_halo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.in), dims, strides, hbox, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        UAD_REQUIRE(ch == CUDA_SUCCESS, "gather_gemm_tc_np_halo: cuTensorMapEncodeTiled failed (%d)", (int)ch);
+        p.stages = 4;                                      // weight images only: 4 x 2 N x 128 B
+        const size_t stage_h = 2u * N * 128u;
+        const size_t halo_bytes = (((size_t)(p.TH + 2) * (p.TW + 2) * 128u) + 1023u) & ~(size_t)1023u;
+        const size_t halo_off = (p.stages * stage_h + 256 + 3 * N * sizeof(float) + 4 * 32 * (size_t)(N + 4) * sizeof(float) + 1023u) &
+                                ~(size_t)1023u;
+        const size_t smem_h = 1024 + halo_off + p.Cblks * halo_bytes + 64;
+        UAD_REQUIRE(smem_h <= 200 * 1024, "gather_gemm_tc_np_halo: shared-memory budget exceeded (%zu)", smem_h);
+        static bool attr_h = false;
+        if (!attr_h) {
+          UAD_CUDA(cudaFuncSetAttribute(gather_gemm_tc_np_halo, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr_h = true;
+        }
+        gather_gemm_tc_np_halo<<<p.tiles_w * p.tiles_h * g.B, 256, smem_h, st>>>(tmap_halo, p);
+        UAD_LAUNCH_CHECK("gather_gemm_tc_np_halo");
+        return 0;
+      }
+    }
     p.stages = 3;
     const size_t smem_np = 1024 + p.stages * stage_bytes + 256 + 3 * N * sizeof(float) + 4 * 32 * (size_t)(N + 4) * sizeof(float) + 64;
     static bool attr_np = false;
