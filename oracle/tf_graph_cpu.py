@@ -326,6 +326,28 @@ def loss_and_grads(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=
     return out, L, G
 
 
+def cevae_reconstruct(P, x, *, eps, use_gradient_based_restoration=True, l1_sign=None, dtype=torch.float32):
+    """Restates reference trainers/ceVAE.py:119-144 as utils/Evaluation.py:246-253 drives it: ONE slice per ``sess.run``
+    (feed x_ce = x, dropout off), fetches ``reconstruction`` and every loss incl. ``anomaly = L1_vae * |d loss_vae / d x|``
+    (:51) where ``loss_vae = reduce_mean(rec_vae + kl)`` is a mean over that ONE sample; with a truthy
+    ``use_gradient_based_restoration`` the returned reconstruction is ``x - lambda * anomaly`` (:136-139).
+    x: [N,H,W,C]; eps: [N,zDim] (slice i uses eps[i]).  l1_sign: optional caller-fixed sign pattern (see ``losses``).
+    Returns {'x_hat', 'anomaly', 'L1_vae', 'reconstruction'} as float64/float32 numpy arrays, slice by slice."""
+    outs = {'x_hat': [], 'anomaly': [], 'L1_vae': [], 'reconstruction': []}
+    for i in range(x.shape[0]):
+        xi = _t(x[i:i + 1], dtype).clone().requires_grad_(True)
+        o = forward(CEVAE, P, xi, x_ce=x[i:i + 1], eps=eps[i:i + 1], training=False, dtype=dtype)
+        L = losses(CEVAE, o, xi, x_ce=x[i:i + 1], dtype=dtype, l1_sign=None if l1_sign is None else l1_sign[i:i + 1])
+        gx = torch.autograd.grad(L['loss_vae'], xi)[0]
+        an = (L['L1_vae'] * gx.abs()).detach()
+        rec = o['x_hat'].detach()
+        if use_gradient_based_restoration:
+            rec = xi.detach() - use_gradient_based_restoration * an
+        for k, v in (('x_hat', o['x_hat'].detach()), ('anomaly', an), ('L1_vae', L['L1_vae'].detach()), ('reconstruction', rec)):
+            outs[k].append(v.numpy())
+    return {k: np.concatenate(v, 0) for k, v in outs.items()}
+
+
 def total_variation(d):
     """tf.image.total_variation on NHWC images (TF 1.15 image_ops_impl.py): sum |d[:,1:]-d[:,:-1]| + sum |d[:,:,1:]-d[:,:,:-1]|
     per image."""

@@ -1123,3 +1123,49 @@ def test_remaining_trainer_surfaces_on_the_emulator(tname, mname, monkeypatch, t
         assert 0 < np.abs(r['reconstruction'] - x).max() < 0.1               # the restored INPUT, two small gradient steps away
     if tname == 'ceVAE':
         assert model.engine.anomaly.shape == (2, 64, 64, 1) and np.isfinite(model.engine.anomaly.numpy()).all()
+
+
+# ------------------------------------------------------------------------------------------------ ceVAE.reconstruct (reference trainers/ceVAE.py:119-144)
+@pytest.mark.parametrize('lam', [0.1, True, 0])
+def test_cevae_reconstruct_applies_the_gradient_based_restoration(lam, monkeypatch, tmp_path):
+    """``reconstruct`` returns ``x - lambda * anomaly`` with the PER-SLICE gradient of loss_vae (one slice per sess.run in the
+    reference), the plain x_hat when the factor is falsy; the batched device stack must equal N single-slice oracle calls."""
+    from unsupervised_anomaly_detection_brain_mri_b200.models.context_encoder_variational_autoencoder import \
+        context_encoder_variational_autoencoder as net
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.ceVAE import ceVAE
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_datasets, get_options
+    _everything_on_the_emulator(monkeypatch)
+    cfgjson = {'CHECKPOINTDIR': str(tmp_path / 'ckpt'), 'SAMPLEDIR': str(tmp_path / 'samples'), 'BRAINWEBDIR': '', 'SYNTHETICDIR': ''}
+    S, N = 32, 3
+    options = get_options(batchsize=2, learningrate=1e-3, numEpochs=1, zDim=128, outputWidth=S, outputHeight=S, config=cfgjson)
+    options['data']['dir'] = ''
+    hc, _ = get_datasets(options)
+    config = get_config(ceVAE, options, 'ADAM', [8, 8], 0.1, hc)
+    config.useTensorboard, config.verbose, config.device, config.math_mode, config.use_cuda_graph = False, False, 'cpu', 0, False
+    assert config.use_gradient_based_restoration is True            # the reference's Config default (trainers/ceVAE.py:16)
+    config.use_gradient_based_restoration = lam
+    model = ceVAE(None, config, network=net)
+    P = O.perturb_params(O.init_params(O.CEVAE, S, seed=1))
+    model.engine.fp.load(P)
+    eps = np.random.default_rng(5).standard_normal((N, 128)).astype(np.float32)
+    orig_eval = model._eval_engine
+
+    def eval_engine(n):
+        e = E.adopt(orig_eval(n))
+        monkeypatch.setattr(e, 'draw_noise', lambda dropout, rate: e.set_noise(eps[:n]))
+        return e
+    monkeypatch.setattr(model, '_eval_engine', eval_engine)
+    x = O.synthetic_slices(N, S, seed=9)
+    r = model.reconstruct(x)
+    xh = model._eval_engines[N].br[0].xhat.numpy()
+    ref = O.cevae_reconstruct(P, x, eps=eps, use_gradient_based_restoration=lam, dtype=torch.float64, l1_sign=np.sign(xh - x))
+    assert _rel(xh, ref['x_hat']) < TOL
+    assert _rel(r['anomaly'], ref['anomaly']) < 5e-5
+    assert _rel(x - r['reconstruction'], x - ref['reconstruction']) < 5e-5
+    if lam:
+        assert np.allclose(x - r['reconstruction'], np.float32(lam) * r['anomaly'], rtol=0, atol=1e-7)
+    else:
+        assert np.array_equal(r['reconstruction'], xh.astype(np.float32))
+    assert r['l1err'] == pytest.approx(np.sum(np.abs(x - r['reconstruction'])))
+    one = model.reconstruct(x[1])               # [H,W,C] input as Evaluation passes it: same slice, same eps row 0 -> differs only by eps
+    assert one['reconstruction'].shape == (1, S, S, 1)

@@ -227,3 +227,31 @@ def test_constrained_ae_trainer_surface(tmp_path):
     assert np.isfinite(last['loss']) and last['loss'] < first['loss']
     r = model.reconstruct(x)
     assert r['reconstruction'].shape == x.shape and np.isfinite(r['l1err'])
+
+
+@pytest.mark.parametrize('mode', [0, 1])
+def test_cevae_reconstruct_anomaly_parity(mode):
+    """ceVAE.reconstruct (reference trainers/ceVAE.py:119-144): per-slice anomaly = L1_vae * |d(sum|x_hat-x| + kl)/dx| on a
+    batched stack equals N single-slice evaluations of the oracle; reconstruction = x - lambda * anomaly."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
+    S, N, lam = 64, 5, 0.1
+    P = O.perturb_params(O.init_params(O.CEVAE, S, seed=1))
+    x = O.synthetic_slices(N, S, seed=77)
+    eps = np.random.default_rng(8).standard_normal((N, 128)).astype(np.float32)
+    eng = ConvAutoencoderEngine(O.CEVAE, S, batch=N, math_mode=mode)
+    eng.fp.load(P)
+    eng.set_inputs(x, x)
+    eng.set_noise(eps)
+    eng.forward(training=False, dropout_rate=0.0, branches=[0], need_l1=True)
+    eng.anomaly_per_sample()
+    torch.cuda.synchronize()
+    xh = eng.br[0].xhat.cpu().numpy()
+    sgn = np.sign(xh.astype(np.float64) - x)
+    ref = O.cevae_reconstruct(P, x, eps=eps, use_gradient_based_restoration=lam, dtype=torch.float64, l1_sign=sgn)
+    own = np.sign(ref['x_hat'] - x)
+    assert (own != sgn).mean() < 1e-4
+    assert _relerr(xh, ref['x_hat']) < TOL
+    an = eng.anomaly.cpu().numpy()
+    print('ceVAE.reconstruct anomaly rel-err', _relerr(an, ref['anomaly']))
+    assert _relerr(an, ref['anomaly']) < TOL
+    assert _relerr(x - np.float32(lam) * an, ref['reconstruction']) < TOL

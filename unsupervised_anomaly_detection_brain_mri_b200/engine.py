@@ -1137,6 +1137,24 @@ class ConvAutoencoderEngine:
         call('uad_l1_direct_term', ptr(b0.x), ptr(b0.xhat), 1.0 / self.B, ptr(self.gx), b0.x.numel(), st)
         call('uad_mul_abs', ptr(b0.l1), ptr(self.gx), ptr(self.anomaly), b0.x.numel(), st)
 
+    def anomaly_per_sample(self):
+        """ceVAE 'anomaly' map as ``ceVAE.reconstruct`` fetches it (reference trainers/ceVAE.py:51,119-139): the reference
+        evaluates one slice per ``sess.run``, so ``loss_vae = mean_b(rec_vae + kl)`` is normalised by 1/1 - every slice of
+        the stack gets the gradient of ITS OWN ``sum|x_hat - x| + kl`` (no 1/B).  Needs a preceding
+        ``forward(branches=[0], need_l1=True)``; dgrad-only chain, no parameter gradients.  Result in ``self.anomaly``."""
+        b0, st = self.br[0], self._st()
+        ws, wsb = self._wsargs()
+        if not hasattr(self, 'gseed'):
+            self.gseed = self._new(self.B, self.S, self.S, 1)
+            self.tv = self._new(self.B)
+            self.restore_grads = self._new(self.B, self.S, self.S, 1)
+        # seed = d sum|x_hat - x| / d x_hat = sign(x_hat - x)  (the restoration seed kernel with tv_lambda = 0)
+        self._op('anomaly', 'uad_tv_restore_seed', ptr(b0.x), ptr(b0.xhat), 0.0, ptr(self.gseed), ptr(self.tv), self.B, self.S, self.S,
+                 ws, wsb, st)
+        self.backward_to_input(self.gseed, kl_scale=1.0)
+        call('uad_l1_direct_term', ptr(b0.x), ptr(b0.xhat), 1.0, ptr(self.gx), b0.x.numel(), st)
+        call('uad_mul_abs', ptr(b0.l1), ptr(self.gx), ptr(self.anomaly), b0.x.numel(), st)
+
     # ------------------------------------------------------------------ read-back
     def losses(self):
         s = self.scalars.detach().cpu().numpy()
