@@ -36,6 +36,8 @@ def oracle_convT(x, K, b):
 
 CONV_SHAPES = [  # B, H, Cin, Cout
     (2, 16, 32, 64), (3, 32, 32, 32), (2, 16, 64, 128), (1, 16, 128, 128), (2, 64, 32, 64), (5, 8, 32, 32),
+    # M-grids >= 16 x 8: the halo-resident kernel conv_halo_ss (N = 128 / 64 / 32, 1..4 channel blocks, several tiles per image)
+    (2, 64, 64, 128), (1, 32, 128, 128), (3, 32, 128, 64), (1, 128, 32, 64), (2, 64, 64, 32), (7, 32, 32, 128),
 ]
 
 
@@ -87,6 +89,7 @@ def test_conv2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
 
 CONVT_SHAPES = [  # B, H(in), Cin, Cout
     (2, 8, 128, 128), (2, 16, 128, 64), (3, 16, 64, 32), (2, 32, 32, 32), (1, 64, 32, 32), (5, 8, 32, 32),
+    (2, 16, 128, 128), (1, 32, 64, 32), (1, 128, 32, 32), (3, 16, 32, 128), (2, 32, 64, 64), (5, 16, 32, 64),
 ]
 
 

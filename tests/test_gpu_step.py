@@ -10,6 +10,27 @@ pytestmark = pytest.mark.gpu
 from oracle import tf_graph_cpu as O  # noqa: E402
 
 TOL = 1e-4
+# gradients: north_star's 1e-4 against the float64 oracle wherever fp32 arithmetic itself can hold it.  Some gradient tensors
+# are sums of 1e5..1e6 cancelling terms (e.g. Bottleneck/dense_2/kernel: max|g| 0.04 next to 1..3000 elsewhere); the fp32
+# restatement of the reference (torch-CPU float32, the arithmetic the TF CPU path runs in) deviates 1e-3 from float64 there,
+# and so does the exact-fp32 SIMT mode of this library (tools/grad_err_big.py -> profiles/r2_grad_err_big.txt).  The bound per
+# tensor is therefore max(1e-4, 3 x the float32 oracle's own deviation from float64 on that tensor) - tight where fp32 is
+# accurate, never looser than the reference's own rounding noise allows.  The flat 5e-4 of round 1 is gone.
+GRAD_TOL = 1e-4
+NOISE_FACTOR = 3.0
+
+
+def _check_grads(grads, G64, G32, label):
+    worst = (0.0, None, 0.0)
+    for k in G64:
+        ref = G64[k].numpy() if hasattr(G64[k], 'numpy') else G64[k]
+        r32 = G32[k].numpy() if hasattr(G32[k], 'numpy') else G32[k]
+        err, floor = _relerr(grads[k], ref), _relerr(r32, ref)
+        bound = max(GRAD_TOL, NOISE_FACTOR * floor)
+        if err / bound > worst[0]:
+            worst = (err / bound, k, err)
+        assert err < bound, (label, k, err, floor)
+    print(f'{label}: worst gradient error / bound = {worst[0]:.2f} ({worst[1]}, rel-err {worst[2]:.2e})')
 
 
 def _relerr(a, b):
@@ -74,10 +95,9 @@ def test_train_step_parity(arch, S, B, mode, keep_preact):
         assert _relerr(eng.br[1].xhat.cpu().numpy(), out['x_hat_ce'].numpy()) < TOL
         assert _relerr(eng.anomaly.cpu().numpy(), L['anomaly'].numpy()) < TOL
     grads = eng.fp.to_numpy(eng.fp.grads)
-    worst = max((_relerr(grads[k], G[k].numpy()), k) for k in P)
-    # gradients sum 1e5..1e6 cancelling terms: float32 torch-CPU itself deviates ~1e-3 from float64 on these tensors
-    # (tools/grad_err.py), so the bound for them is 5e-4 - forward tensors and losses above hold the 1e-4 of north_star
-    assert worst[0] < 5 * TOL, worst
+    _, _, G32 = O.loss_and_grads(arch, P, x, x_ce=x_ce, eps=eps, masks=om, dropout_rate=rate, training=True,
+                                 dtype=torch.float32, want_anomaly=False, l1_sign=sgn, l1_sign_ce=sgn_ce)
+    _check_grads(grads, G, G32, f'{arch} {S}x{S} B={B} mode {mode}')
     # post-Adam weights: first step is ~ lr*sign(g), so compare the UPDATE relative to lr
     Pn, _, _ = O.adam_tf({k: torch.from_numpy(v).double() for k, v in P.items()}, G,
                          {k: torch.zeros_like(g) for k, g in G.items()}, {k: torch.zeros_like(g) for k, g in G.items()},
@@ -255,3 +275,65 @@ def test_cevae_reconstruct_anomaly_parity(mode):
     print('ceVAE.reconstruct anomaly rel-err', _relerr(an, ref['anomaly']))
     assert _relerr(an, ref['anomaly']) < TOL
     assert _relerr(x - np.float32(lam) * an, ref['reconstruction']) < TOL
+
+
+def _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom, chunk=8, dtype=torch.float64):
+    """float64 oracle of a LARGE batch in sub-batches: samples are independent (frozen BN) and loss = mean_b, so
+    loss / gradients of the batch are the means of the sub-batch ones; bounds the host memory of the autograd graph."""
+    B = x.shape[0]
+    G, Ls, xh, xhc, an = None, {}, [], [], []
+    for i in range(0, B, chunk):
+        sl = slice(i, i + chunk)
+        m = {k: v[sl] for k, v in om.items()}
+        out, L, g = O.loss_and_grads(arch, P, x[sl], x_ce=None if x_ce is None else x_ce[sl], eps=eps[sl], masks=m, dropout_rate=rate,
+                                     training=True, dtype=dtype, want_anomaly=want_anom, l1_sign=sgn[sl],
+                                     l1_sign_ce=None if sgn_ce is None else sgn_ce[sl])
+        w = (min(i + chunk, B) - i) / B
+        G = {k: v.double() * w for k, v in g.items()} if G is None else {k: G[k] + v.double() * w for k, v in g.items()}
+        for k in ('loss', 'reconstructionLoss', 'kl'):
+            if k in L:
+                Ls[k] = Ls.get(k, 0.0) + float(L[k]) * w
+        xh.append(out['x_hat'].numpy())
+        if arch == O.CEVAE:
+            xhc.append(out['x_hat_ce'].numpy())
+        if arch == O.CEVAE and want_anom:
+            an.append(L['anomaly'].numpy() * w)          # d loss_vae / dx carries 1/B of the WHOLE batch
+    return np.concatenate(xh), (np.concatenate(xhc) if xhc else None), (np.concatenate(an) if an else None), Ls, G
+
+
+@pytest.mark.parametrize('arch,S,B', [(O.VAE, 256, 64), (O.CEVAE, 256, 128)], ids=['C2_vae256_b64', 'C3_cevae256_b128'])
+def test_train_step_parity_at_the_benched_configs(arch, S, B):
+    """BASELINE.json configs[1] (VAE 256x256, batch 64) and configs[2] (ceVAE 256x256, batch 128) at their FULL batch: the
+    split-K plans and grid shapes depend on B*H*W, so the launch configurations bench.py times are the ones checked here.
+    Loss, x_hat, (anomaly) <= 1e-4; every gradient tensor is reported and bounded."""
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
+    rate, lr = 0.2, 1e-3
+    P = O.perturb_params(O.init_params(arch, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=1234)
+    x_ce = None
+    if arch == O.CEVAE:
+        x_ce = x.copy()
+        x_ce[:, S // 4:S // 4 + 20, S // 3:S // 3 + 20] = 0
+    eng = ConvAutoencoderEngine(arch, S, batch=B, math_mode=1)
+    eng.fp.load(P)
+    eps, om, em, emc = _noise(arch, B, 128, eng.flat, rate)
+    eng.set_inputs(x, x_ce)
+    eng.set_noise(eps, em, emc)
+    want_anom = arch == O.CEVAE
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True, want_anomaly=want_anom)
+    torch.cuda.synchronize()
+    xh_dev = eng.br[0].xhat.cpu().numpy()
+    sgn = np.sign(xh_dev.astype(np.float64) - x)
+    sgn_ce = np.sign(eng.br[1].xhat.cpu().numpy().astype(np.float64) - x_ce) if arch == O.CEVAE else None
+    xh, xhc, an, L, G = _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom)
+    assert (np.sign(xh - x) != sgn).mean() < 1e-4
+    got = eng.losses()
+    for k in ('loss', 'reconstructionLoss', 'kl'):
+        assert abs(got[k] - L[k]) / abs(L[k]) < TOL, (k, got[k], L[k])
+    assert _relerr(xh_dev, xh) < TOL
+    if arch == O.CEVAE:
+        assert _relerr(eng.br[1].xhat.cpu().numpy(), xhc) < TOL
+        assert _relerr(eng.anomaly.cpu().numpy(), an) < TOL
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    _, _, _, _, G32 = _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, False, dtype=torch.float32)
+    _check_grads(grads, G, G32, f'{arch} {S}x{S} B={B}')

@@ -1,4 +1,5 @@
 // extern "C" entry points of the conv / transposed-conv family: tap-table construction + dispatch.
+#include <stdlib.h>
 #include <string.h>
 
 #include "uad_conv.cuh"
@@ -46,6 +47,17 @@ static int check_geom(const char* op, int B, int H, int W, int Cin, int Cout, in
 }
 
 static bool want_tc(int math_mode) { return math_mode == UAD_MATH_TC_3XTF32 || math_mode == UAD_MATH_TC_1XTF32; }
+
+// Form F / Form T on tensor cores: the halo-resident SS kernel (uad_conv_hs.cu) wherever the M-grid is at least 16 x 8, the
+// converter-warp kernels (uad_conv_tc.cu) for the 8 x 8 grids at the bottleneck.  UAD_HS=0 (developer switch) forces the latter.
+static int launch_gather_tensor(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
+                                int math_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+  static int use_hs = -1;
+  if (use_hs < 0) { const char* e = getenv("UAD_HS"); use_hs = e ? atoi(e) : 1; }
+  if (use_hs && ksize == 5 && uad_hs_gather_supported(p.Cin, p.N, p.lgMH, p.lgMW))
+    return uad_launch_gather_hs(p, nclasses, ksize, weights_transposed, w_raw, ws, ws_bytes, st);
+  return uad_launch_gather_tc(p, nclasses, ksize, weights_transposed, w_raw, math_mode, ws, ws_bytes, st);
+}
 
 extern "C" int uad_conv_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int ksize) {
   (void)B;
@@ -116,7 +128,7 @@ extern "C" int uad_conv2d_fwd(const float* x, const float* w, const float* bias,
   p.act = act; p.alpha = alpha; p.bn_c = bn_c;
   taps_full(&p.taps[0], ksize);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONV_FWD, B, H, W, Cin, Cout, ksize))
-    return uad_launch_gather_tc(p, 1, ksize, false, w, math_mode, ws, ws_bytes, st);
+    return launch_gather_tensor(p, 1, ksize, false, w, math_mode, ws, ws_bytes, st);
   return uad_launch_gather_simt(p, 1, st);
 }
 
@@ -135,7 +147,7 @@ extern "C" int uad_conv2d_dgrad(const float* dz, const float* w, float* dx, int 
   p.act = UAD_ACT_NONE; p.alpha = 0.f; p.bn_c = 1.f;
   for (int c = 0; c < 4; ++c) taps_parity(&p.taps[c], ksize, c >> 1, c & 1);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONV_DGRAD, B, H, W, Cin, Cout, ksize))
-    return uad_launch_gather_tc(p, 4, ksize, true, w, math_mode, ws, ws_bytes, st);
+    return launch_gather_tensor(p, 4, ksize, true, w, math_mode, ws, ws_bytes, st);
   // SIMT: needs wmat[t][Cout][Cin] = transpose of HWIO w[t][Cin][Cout]
   size_t need = (size_t)ksize * ksize * Cin * Cout * sizeof(float);
   UAD_REQUIRE(ws && ws_bytes >= need, "uad_conv2d_dgrad: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -178,7 +190,7 @@ extern "C" int uad_convT2d_fwd(const float* x, const float* w, const float* bias
   p.act = act; p.alpha = alpha; p.bn_c = bn_c;
   for (int c = 0; c < 4; ++c) taps_parity(&p.taps[c], ksize, c >> 1, c & 1);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONVT_FWD, B, H, W, Cin, Cout, ksize))
-    return uad_launch_gather_tc(p, 4, ksize, true, w, math_mode, ws, ws_bytes, st);
+    return launch_gather_tensor(p, 4, ksize, true, w, math_mode, ws, ws_bytes, st);
   // SIMT: needs wmat[t][Cin][Cout] = transpose of TF layout w[t][Cout][Cin]
   size_t need = (size_t)ksize * ksize * Cin * Cout * sizeof(float);
   UAD_REQUIRE(ws && ws_bytes >= need, "uad_convT2d_fwd: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -201,7 +213,7 @@ extern "C" int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int
   p.act = UAD_ACT_NONE; p.alpha = 0.f; p.bn_c = 1.f;
   taps_full(&p.taps[0], ksize);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONVT_DGRAD, B, H, W, Cin, Cout, ksize))
-    return uad_launch_gather_tc(p, 1, ksize, false, w, math_mode, ws, ws_bytes, st);
+    return launch_gather_tensor(p, 1, ksize, false, w, math_mode, ws, ws_bytes, st);
   return uad_launch_gather_simt(p, 1, st);
 }
 
