@@ -67,7 +67,7 @@ size_t uad_tc_gather_ss_extra_bytes(int N, size_t in_elems);   // candidate SS k
 int uad_launch_gather_tc(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
                          int math_mode, void* ws, size_t ws_bytes, cudaStream_t st);
 // ---- halo-resident SS-form tcgen05 launcher (uad_conv_hs.cu; round 2): M-grids of at least 16 x 8
-int uad_hs_gather_supported(int Cin, int N, int lgMH, int lgMW);
+int uad_hs_gather_supported(int Cin, int N, int lgMH, int lgMW, int nclasses);
 size_t uad_hs_gather_ws_bytes(int ksize, int Cin, int N);
 int uad_launch_gather_hs(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
                          void* ws, size_t ws_bytes, cudaStream_t st);

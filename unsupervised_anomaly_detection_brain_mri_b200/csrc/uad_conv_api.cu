@@ -54,7 +54,7 @@ static int launch_gather_tensor(const GatherParams& p, int nclasses, int ksize, 
                                 int math_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   static int use_hs = -1;
   if (use_hs < 0) { const char* e = getenv("UAD_HS"); use_hs = e ? atoi(e) : 1; }
-  if (use_hs && ksize == 5 && uad_hs_gather_supported(p.Cin, p.N, p.lgMH, p.lgMW))
+  if (use_hs && ksize == 5 && uad_hs_gather_supported(p.Cin, p.N, p.lgMH, p.lgMW, nclasses))
     return uad_launch_gather_hs(p, nclasses, ksize, weights_transposed, w_raw, ws, ws_bytes, st);
   return uad_launch_gather_tc(p, nclasses, ksize, weights_transposed, w_raw, math_mode, ws, ws_bytes, st);
 }
