@@ -5,29 +5,36 @@
 //           has to be produced (one elementwise pass over the tile, same byte offsets)
 //   E6/E8   the 128-byte swizzle is a function of the absolute shared-memory address -> a K-major descriptor may start at ANY
 //           128-byte row of a TMA-written tile and its 8-row groups may be any number of rows apart (SBO = halo pitch)
-// and on one measurement of this kernel's first version (profiles/r2_hs_issue_loop.md): with a table-driven issue loop (tap
-// tables in constant memory, ~100 dependent SASS instructions per k-block) the MMA-issuing warp was instruction-latency bound -
-// 880 cycles per k-block with the tensor pipe 25 % busy, and switching off the loads, the lo pass, the stores AND the MMAs
-// still left 55 % of the time.  The tap geometry is therefore COMPILE-TIME here: the kernel is a template over the form and
-// every k-block of a work item is unrolled, so window offsets, accumulator columns and weight-slot offsets are immediates and a
-// k-block costs 8 UTCHMMA + ~12 uniform adds.
+// and on two measurements of this kernel's earlier versions (profiles/r2_hs_issue_loop.md):
+//   (1) a table-driven issue loop (tap tables in constant memory, ~100 dependent SASS instructions per k-block) is
+//       instruction-latency bound - 880 cycles per k-block, tensor pipe 25 % busy.  The tap geometry is therefore COMPILE-TIME:
+//       the kernel is a template over the form and every k-block of a work item is unrolled (window offsets, accumulator columns
+//       and weight-slot offsets are immediates);
+//   (2) even then ONE issuing warp needs ~900 cycles per 16 MMAs (branch resolution ~40 cycles per branch, barrier polls,
+//       uniform-register descriptor arithmetic) while the pipe executes them in ~700: TWO issuing warps share every work item,
+//       each with its own accumulator columns, its own weight ring and its own weight producer, so one polls / commits while
+//       the other's MMAs run.
 //
 // Tile = 16 x 8 pixels of the M-grid (M = 128 rows; one 8-pixel tile row = one 8-row descriptor group).  Per 32-channel block
 // the (16+2) x (8+2) pixel halo of the tile (stride-1 form) or of one stride-2 parity plane (strided form) is TMA-loaded ONCE
 // as 180 rows of 128 bytes (SWIZZLE_128B); every filter tap that reads from it is a descriptor START ADDRESS
 // (halo + (wh * 10 + ww) * 128 bytes, SBO = 1280).  fp32 parity = 3xTF32 with the paired-B trick:
-//     acc[main | corr] (+)= A_raw . [B_hi ; B_lo]^T          one MMA of width 2N  (hi*hi -> main, hi*lo -> corr)
-//     acc[corr]         +=  A_lo  .  B_hi^T                  one MMA of width N
-// Roles (384 threads, one persistent CTA per SM):
+//     acc[main | corr] (+)= A_raw . [B_hi ; B_lo]^T          one MMA of width 2 NI  (hi*hi -> main, hi*lo -> corr)
+//     acc[corr]         +=  A_lo  .  B_hi^T                  one MMA of width NI
+// Work split between the issuers (NI = columns per issuer):
+//   N = 128           column split: issuer W computes output columns [64 W, 64 W + 64) of EVERY k-block (NI = 64)
+//   strided, N <= 64  each parity plane's k-blocks are halved; issuer W accumulates into its own pair, the epilogue adds the two
+//   stride-1, N <= 64 by output-parity class: classes {0, 3} / {1, 2} (N = 32, four classes per item), class 0 / 1 of the pair (N = 64)
+// Roles (416 threads, 544 in the stride-1 form; one persistent CTA per SM):
 //   warp 0      halo TMA producer                                   -> h_full[s]
 //   warps 4-7   lo pass: lo tile = raw - trunc(raw)                 -> h_lo[s]            (once per halo, NOT per tap)
-//   warp 1      weight producer (one bulk copy per CHUNK of k-blocks) -> w_full[t]
-//   warp 2      MMA issuer: 8 x tcgen05.mma per k-block, commits    -> w_empty[t], h_empty[s], acc_full[b]
-//   warp 3      TMEM allocation, epilogue constants
-//   warps 8-11  epilogue: tcgen05.ld, sum of the accumulators (RN), bias / frozen-BN / activation, smem transpose, coalesced
+//   warps 1, 12 weight producers (one bulk copy per 16 KB chunk)    -> w_full[W][t]
+//   warps 2, 3  MMA issuers                                         -> w_empty[W][t], h_empty[s], acc_full[b]
+//   warps 8-11 (+ 13-16 in the stride-1 form: one warpgroup per accumulator set, alternate items)
+//               epilogue: tcgen05.ld, sum of the accumulators (RN), bias / frozen-BN / activation, smem transpose, coalesced
 //               row stores                                          -> acc_empty[b]
-// The tensor core adds into its fp32 accumulator with truncation (round 1, measured): the strided form deals its 32-channel
-// blocks round-robin over G = 2 accumulator pairs when there are several; the epilogue sums them in registers.
+// The tensor core adds into its fp32 accumulator with truncation (round 1, measured): no accumulator pair takes more than
+// ~1600 products per output (N = 128 strided form: channel blocks alternate between G = 2 pairs per issuer).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,8 +54,8 @@ constexpr uint32_t kHaloBytes = kHaloRows * 128u;            // 23040
 constexpr uint32_t kHaloSlot = (kHaloBytes + 1023u) & ~1023u;   // 23552: raw tile, then the lo tile
 constexpr uint32_t kHaloStage = 2u * kHaloSlot;
 constexpr uint32_t kSbo = kHW * 128u;                        // 1280: one tile row down = one halo row down
-constexpr int kThreads = 384;
 constexpr int kTaps = 25;
+constexpr uint32_t kSlot = 16384;                            // weight ring slot (one chunk)
 
 template <int I, int E, class F>
 __host__ __device__ __forceinline__ void static_for(F&& f) {
@@ -66,11 +73,8 @@ __host__ __device__ __forceinline__ void static_for(F&& f) {
 //   FORM 1 (stride-1 gather, four output-parity classes: transposed-conv forward, conv input gradient): group = class (p, q);
 //          tap kh = p + 3 - 2 wh reads window (wh, ww) of the ONE halo; an item covers CG consecutive classes
 // Group g has (2 + g>>1) x (2 + g&1) k-blocks in both forms (4, 6, 6, 9); k-block i of it is window (ih, iw) = (i / nw, i % nw).
-// The weight images are laid out in exactly this order ([channel block][group][k-block]) so a chunk of consecutive k-blocks
-// is one bulk copy.
 struct KbGeom { int a_off16, wt; };
 __host__ __device__ constexpr int grp_nkb(int g) { return (2 + (g >> 1)) * (2 + (g & 1)); }
-__host__ __device__ constexpr int grp_base(int g) { return g == 0 ? 0 : (g == 1 ? 4 : (g == 2 ? 10 : 16)); }
 template <int FORM>
 __host__ __device__ constexpr KbGeom kb_geom(int g, int i) {
   const int p = g >> 1, q = g & 1, nw = 2 + q, ih = i / nw, iw = i % nw;
@@ -81,29 +85,66 @@ __host__ __device__ constexpr KbGeom kb_geom(int g, int i) {
   return KbGeom{(ih * kHW + iw) * 8, (p + 3 - 2 * ih) * 5 + (q + 3 - 2 * iw)};
 }
 
-struct HsOrder { unsigned char wt[kTaps]; };                 // weight tap of the o-th k-block image of a channel block
-
 template <int FORM_, int N_, int CG_, int G_>
 struct Cfg {
   static constexpr int FORM = FORM_, N = N_, CG = CG_, G = G_;
+  static constexpr bool COLSPLIT = N == 128;
+  static constexpr int NI = COLSPLIT ? 64 : N;               // output columns per issuer MMA
   static constexpr int NVAR = FORM == 0 ? 1 : 4 / CG;        // item = tile * NVAR + variant (class group)
   static constexpr int NGRP = FORM == 0 ? 4 : CG;            // k-block groups per (item, channel block)
   static constexpr int NUNITS = FORM == 0 ? 4 : 1;           // halo loads per (item, channel block)
-  static constexpr int CH = N == 32 ? 2 : 1;                 // k-blocks per weight chunk (one barrier round trip per chunk)
-  static constexpr uint32_t W_BYTES = 2u * N * 128u;         // one k-block's {hi, lo} weight image
-  static constexpr uint32_t SLOT = CH * W_BYTES;             // weight ring slot
-  static constexpr int ACC_COLS = (FORM == 0 ? 1 : CG) * G * 2 * N;
+  static constexpr uint32_t WI_BYTES = 2u * NI * 128u;       // one k-block's {hi, lo} weight image of ONE issuer
+  static constexpr int CH = kSlot / WI_BYTES;                // k-blocks per weight chunk (2 at NI = 32, else 1)
+  // the strided form turns a halo over every 4 .. 9 k-blocks and a refill (TMA + lo pass) takes ~2500 cycles: three stages there,
+  // paid for with one weight slot; the stride-1 form keeps a halo for a whole (item, channel block)
+  static constexpr int HS = FORM == 0 ? 3 : 2, WS = FORM == 0 ? 2 : 3;   // halo stages, weight slots per issuer
+  static constexpr int ACC_COLS = FORM == 0 ? (COLSPLIT ? 2 * G * 128 : 4 * NI) : (COLSPLIT ? 256 : CG * 2 * NI);
   static constexpr int ACC_BUFS = 2 * ACC_COLS <= 512 ? 2 : 1;
+  // the stride-1 form writes up to four classes per item: a second epilogue warpgroup (one per accumulator set, alternate items)
+  static constexpr int EPI_WG = (FORM == 1 && ACC_BUFS == 2) ? 2 : 1;
+  static constexpr int THREADS = 416 + (EPI_WG - 1) * 128;
   static_assert(ACC_COLS <= 512, "TMEM budget");
+  static_assert(G == 1 || (FORM == 0 && COLSPLIT), "second accumulator pair per issuer: strided form at N = 128 only");
+
+  // k-blocks [i0, i1) of group g (absolute plane / class index) that issuer W processes
+  __host__ __device__ static constexpr int i0(int W, int g) {
+    if (COLSPLIT) return 0;
+    if (FORM == 0) return W == 0 ? 0 : (grp_nkb(g) + 1) / 2;
+    return 0;
+  }
+  __host__ __device__ static constexpr int i1(int W, int g) {
+    if (COLSPLIT) return grp_nkb(g);
+    if (FORM == 0) return W == 0 ? (grp_nkb(g) + 1) / 2 : grp_nkb(g);
+    const int owner = CG == 4 ? ((g == 0 || g == 3) ? 0 : 1) : (g & 1);
+    return owner == W ? grp_nkb(g) : 0;
+  }
+  // position of issuer W's first k-block of group g in its weight-image sequence of one channel block
+  __host__ __device__ static constexpr int ord_base(int W, int g) {
+    int s = 0;
+    for (int gg = 0; gg < g; ++gg) s += i1(W, gg) - i0(W, gg);
+    return s;
+  }
+  __host__ __device__ static constexpr int cnt(int W) { return ord_base(W, 4); }
+  // first / last group (index within the variant) in which issuer W has work - brackets its use of a stride-1 halo unit
+  __host__ __device__ static constexpr int first_gi(int W, int V) {
+    for (int gi = 0; gi < NGRP; ++gi) { const int g = FORM == 0 ? gi : V * CG + gi; if (i1(W, g) > i0(W, g)) return gi; }
+    return -1;
+  }
+  __host__ __device__ static constexpr int last_gi(int W, int V) {
+    int r = -1;
+    for (int gi = 0; gi < NGRP; ++gi) { const int g = FORM == 0 ? gi : V * CG + gi; if (i1(W, g) > i0(W, g)) r = gi; }
+    return r;
+  }
 };
+
+struct HsOrder { unsigned char wt[2][kTaps]; int cnt[2]; };  // weight tap of the o-th k-block image of issuer W
 
 struct HsParams {
   int tiles_w, tiles_h;
   int B, C, Cblks;
   int OH, OW, osh;
-  int h_stages, w_stages;
   int n_items;
-  int debug;           // developer timing switches (UAD_HS_DEBUG): 1 = no lo pass, 2 = no MMAs, 4 = no global stores, 8 = no weight loads, 16 = no halo loads
+  int debug;           // developer timing switches (UAD_HS_DEBUG): 1 = no lo pass, 2 = no MMAs, 4 = no global stores, 8 = no weight loads, 16 = no halo loads, 32 = no epilogue at all, 64 = epilogue reads the accumulators only
   float* z_out;
   float* a_out;
   const float* bias;
@@ -111,7 +152,7 @@ struct HsParams {
   const float* beta;
   float bn_c, alpha;
   int act;
-  const float* wimg;   // [Cblks][25 k-blocks in group order][2][N][32] pre-swizzled {hi, lo} weight images
+  const float* wimg;   // [Cblks][issuer][k-blocks in the issuer's order][2][NI][32] pre-swizzled {hi, lo} weight images
 };
 
 struct Ring {                                                // ring position + phase parity
@@ -119,26 +160,167 @@ struct Ring {                                                // ring position + 
   __device__ __forceinline__ void next(uint32_t n) { if (++i == n) { i = 0; ph ^= 1; } }
 };
 
+__device__ __noinline__ float act_slow(float t, int act, float alpha) { return uad_act(t, act, alpha); }
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+// one branch on the fast path; the bounded spin (trap instead of hanging the GPU) lives out of line
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+struct Bars {
+  uint32_t hfull, hlo, hempty, wfull, wempty, accfull, accempty;   // wfull / wempty: [issuer][slot], 8 bytes each, 4 per issuer
+};
+
+// ===================================================================== weight producer of issuer W: one bulk copy per chunk
+template <class CF, int W>
+__device__ __forceinline__ void weight_producer(const HsParams& p, const Bars& bars, uint32_t w_base) {
+  constexpr int NVAR = CF::NVAR, NGRP = CF::NGRP, CH = CF::CH, FORM = CF::FORM, CG = CF::CG;
+  constexpr uint32_t WI = CF::WI_BYTES;
+  const uint32_t full = bars.wfull + W * 32, empty = bars.wempty + W * 32, ring = w_base + W * CF::WS * kSlot;
+  const size_t cb_floats = (size_t)kTaps * 2 * CF::N * 32;
+  const float* img0 = p.wimg + (W ? (size_t)CF::cnt(0) * (WI / 4) : 0);
+  Ring ws{0, 0};
+  const bool no_load = (p.debug & 8) != 0;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const int var = NVAR > 1 ? item % NVAR : 0;
+    for (int cb = 0; cb < p.Cblks; ++cb) {
+      const float* cb_img = img0 + (size_t)cb * cb_floats;
+      static_for<0, NVAR>([&](auto VI) {
+        constexpr int V = decltype(VI)::value;
+        if (NVAR > 1 && var != V) return;
+        static_for<0, NGRP>([&](auto GI) {
+          constexpr int g = FORM == 0 ? decltype(GI)::value : V * CG + decltype(GI)::value;
+          constexpr int i0 = CF::i0(W, g), nown = CF::i1(W, g) - i0, ob = CF::ord_base(W, g);
+          static_for<0, (nown + CH - 1) / CH>([&](auto CI) {
+            constexpr int c0 = decltype(CI)::value * CH;
+            constexpr int nk = nown - c0 < CH ? nown - c0 : CH;
+            mbar_wait_fast(empty + 8 * ws.i, ws.ph ^ 1);
+            if (no_load) {
+              mbar_arrive(full + 8 * ws.i);
+            } else {
+              mbar_expect_tx(full + 8 * ws.i, nk * WI);
+              bulk_load(ring + ws.i * kSlot, cb_img + (size_t)(ob + c0) * (WI / 4), nk * WI, full + 8 * ws.i);
+            }
+            ws.next(CF::WS);
+          });
+        });
+      });
+    }
+  }
+}
+
+// ===================================================================== MMA issuer W (whole warp converged, one elected lane issues)
+template <class CF, int W>
+__device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, uint32_t smem_base, uint32_t w_base, uint32_t tmem_base) {
+  constexpr int NVAR = CF::NVAR, NGRP = CF::NGRP, CH = CF::CH, FORM = CF::FORM, CG = CF::CG, NI = CF::NI, G = CF::G;
+  constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t idescN = idesc_base | ((uint32_t)(NI >> 3) << 17);
+  constexpr uint32_t idesc2N = idesc_base | ((uint32_t)((2 * NI) >> 3) << 17);
+  constexpr uint32_t HSTAGE_U = kHaloStage >> 4, LO_U = kHaloSlot >> 4, SLOT_U = kSlot >> 4, W_U = CF::WI_BYTES >> 4;
+  const uint32_t full = bars.wfull + W * 32, empty = bars.wempty + W * 32;
+  const uint64_t adesc0 = make_kmajor_sw128_desc(smem_base, kSbo);                       // raw tile of halo stage 0
+  const uint64_t bdesc0 = make_kmajor_sw128_desc(w_base + W * CF::WS * kSlot, 1024u);       // this issuer's weight slot 0
+  const bool no_mma = (p.debug & 2) != 0;
+  const int Cblks = p.Cblks;
+  Ring hs{0, 0}, ws{0, 0}, ab{0, 0};
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const int var = NVAR > 1 ? item % NVAR : 0;
+    mbar_wait_fast(bars.accempty + 8 * ab.i, ab.ph ^ 1);        // the epilogue has drained this accumulator set
+    tc_fence_after();
+    const uint32_t acc0 = tmem_base + ab.i * CF::ACC_COLS;
+    for (int cb = 0; cb < Cblks; ++cb) {
+      // this issuer's accumulator pair(s); accum0 = 0 -> the pair's first MMA overwrites (zero-initialises) main | corr
+      uint32_t acc_w, accum0;
+      if (FORM == 0 && CF::COLSPLIT) { acc_w = acc0 + W * (G * 128) + (G == 2 ? (uint32_t)(cb & 1) * 128u : 0u); accum0 = cb >= G ? 1u : 0u; }
+      else if (FORM == 0) { acc_w = acc0 + W * 2 * NI; accum0 = cb > 0 ? 1u : 0u; }
+      else { acc_w = acc0 + (CF::COLSPLIT ? W * 128 : 0); accum0 = cb > 0 ? 1u : 0u; }
+      const bool last_cb = cb == Cblks - 1;
+      uint64_t a_base = 0;
+      static_for<0, NVAR>([&](auto VI) {
+        constexpr int V = decltype(VI)::value;
+        if (NVAR > 1 && var != V) return;
+        constexpr int gi_first = CF::first_gi(W, V), gi_last = CF::last_gi(W, V);
+        static_for<0, NGRP>([&](auto GI) {
+          constexpr int gi = decltype(GI)::value;
+          constexpr int g = FORM == 0 ? gi : V * CG + gi;
+          constexpr int i0 = CF::i0(W, g), nown = CF::i1(W, g) - i0;
+          if constexpr (nown > 0) {
+            constexpr int nchunk = (nown + CH - 1) / CH;
+            constexpr bool unit_first = FORM == 0 || gi == gi_first, unit_last = FORM == 0 || gi == gi_last;
+            if (unit_first) {
+              mbar_wait_fast(bars.hfull + 8 * hs.i, hs.ph);     // the issuing thread observes the TMA completion itself
+              mbar_wait_fast(bars.hlo + 8 * hs.i, hs.ph);       // ... and the lo tile written from it
+              a_base = adesc0 + (uint64_t)(hs.i * HSTAGE_U);
+            }
+            const uint32_t d_pair = acc_w + ((FORM == 1 && !CF::COLSPLIT) ? (uint32_t)(gi * 2 * NI) : 0u);
+            static_for<0, nchunk>([&](auto CI) {
+              constexpr int c0 = decltype(CI)::value * CH;
+              constexpr int nk = nown - c0 < CH ? nown - c0 : CH;
+              constexpr bool chunk_last = decltype(CI)::value == nchunk - 1;
+              mbar_wait_fast(full + 8 * ws.i, ws.ph);
+              tc_fence_after();
+              const uint64_t b_base = bdesc0 + (uint64_t)(ws.i * SLOT_U);
+              if (elect_one()) {
+                if (!no_mma) {
+                  static_for<0, nk>([&](auto KI) {
+                    constexpr int ki = decltype(KI)::value, i = i0 + c0 + ki;
+                    constexpr KbGeom kg = kb_geom<FORM>(g, i);
+                    // first k-block this issuer adds to the pair within the channel block
+                    constexpr bool first_kb = (c0 + ki == 0) && (FORM == 1 || gi == 0);
+                    const uint64_t a_raw = a_base + (uint64_t)kg.a_off16, a_lo = a_raw + LO_U, b_img = b_base + (uint64_t)(ki * W_U);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {               // K = 8 tf32 per instruction = 32 bytes along the 128-byte row
+                      mma_tf32_ss(d_pair, a_raw + 2 * j, b_img + 2 * j, idesc2N, (first_kb && j == 0) ? accum0 : 1u);
+                      mma_tf32_ss(d_pair + NI, a_lo + 2 * j, b_img + 2 * j, idescN, 1u);
+                    }
+                  });
+                }
+                tc_commit(empty + 8 * ws.i);                    // weight slot reusable once these MMAs retire
+                if (unit_last && chunk_last) {
+                  tc_commit(bars.hempty + 8 * hs.i);            // so is the halo stage (second arrival: the other issuer's)
+                  if ((FORM == 1 || gi == NGRP - 1) && last_cb) tc_commit(bars.accfull + 8 * ab.i);
+                }
+              }
+              __syncwarp();
+              ws.next(CF::WS);
+            });
+            if (unit_last) hs.next(CF::HS);
+          }
+        });
+      });
+    }
+    ab.next(CF::ACC_BUFS);
+  }
+}
+
 template <class CF>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(CF::THREADS, 1)
 conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ HsParams p) {
-  constexpr int N = CF::N, G = CF::G, FORM = CF::FORM, CG = CF::CG, NVAR = CF::NVAR, NGRP = CF::NGRP, CH = CF::CH;
-  constexpr uint32_t W_BYTES = CF::W_BYTES, SLOT = CF::SLOT;
+  constexpr int N = CF::N, G = CF::G, FORM = CF::FORM, CG = CF::CG, NVAR = CF::NVAR, NI = CF::NI;
   constexpr int ACC_COLS = CF::ACC_COLS, ACC_BUFS = CF::ACC_BUFS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t HS = p.h_stages, WS = p.w_stages;
-  const uint32_t w_base = smem_base + HS * kHaloStage;
-  const uint32_t misc_off = HS * kHaloStage + WS * SLOT;
+  const uint32_t w_base = smem_base + CF::HS * kHaloStage;
+  constexpr uint32_t misc_off = CF::HS * kHaloStage + 2 * CF::WS * kSlot;
   const uint32_t misc = smem_base + misc_off;
-  const uint32_t bar_hfull = misc;                      // 4 x 8
-  const uint32_t bar_hlo = misc + 32;                   // 4 x 8
-  const uint32_t bar_hempty = misc + 64;                // 4 x 8
-  const uint32_t bar_wfull = misc + 96;                 // 8 x 8
-  const uint32_t bar_wempty = misc + 160;               // 8 x 8
-  const uint32_t bar_accfull = misc + 224;              // 2 x 8
-  const uint32_t bar_accempty = misc + 240;             // 2 x 8
+  Bars bars;
+  bars.hfull = misc;                      // 4 x 8
+  bars.hlo = misc + 32;                   // 4 x 8
+  bars.hempty = misc + 64;                // 4 x 8
+  bars.wfull = misc + 96;                 // 2 x 4 x 8
+  bars.wempty = misc + 160;               // 2 x 4 x 8
+  bars.accfull = misc + 224;              // 2 x 8
+  bars.accempty = misc + 240;             // 2 x 8
   const uint32_t tmem_slot = misc + 256;
   float* epi = reinterpret_cast<float*>(smem_gen + misc_off + 320);            // bias[N], scale[N], shift[N]
   float* stg_base = epi + 3 * N;                                               // 4 warps x 32 x 36 staging
@@ -147,18 +329,20 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   const int Cblks = p.Cblks;
 
   if (threadIdx.x == 0) {
-    for (uint32_t i = 0; i < HS; ++i) { mbar_init(bar_hfull + 8 * i, 1); mbar_init(bar_hlo + 8 * i, 128); mbar_init(bar_hempty + 8 * i, 1); }
-    for (uint32_t i = 0; i < WS; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wempty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_accfull + 8 * i, 1); mbar_init(bar_accempty + 8 * i, 128); }
+    for (int i = 0; i < CF::HS; ++i) { mbar_init(bars.hfull + 8 * i, 1); mbar_init(bars.hlo + 8 * i, 128); mbar_init(bars.hempty + 8 * i, 2); }
+    for (int w = 0; w < 2; ++w)
+      for (int i = 0; i < CF::WS; ++i) { mbar_init(bars.wfull + w * 32 + 8 * i, 1); mbar_init(bars.wempty + w * 32 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bars.accfull + 8 * i, 2); mbar_init(bars.accempty + 8 * i, 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
   }
   if (warp == 3) {
     tmem_alloc(tmem_slot, 512u);
     for (int n = lane; n < N; n += 32) {
-      epi[n] = p.bias ? p.bias[n] : 0.f;
-      epi[N + n] = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
-      epi[2 * N + n] = p.beta ? p.beta[n] : 0.f;
+      const float bias = p.bias ? p.bias[n] : 0.f, scale = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
+      epi[n] = bias;
+      epi[N + n] = scale;
+      epi[2 * N + n] = scale * bias + (p.beta ? p.beta[n] : 0.f);         // a = act(scale * acc + shift')
     }
   }
   tc_fence_before();
@@ -181,121 +365,26 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
 #pragma unroll
           for (int u = 0; u < CF::NUNITS; ++u) {
             const int c_plane = (FORM == 0 ? (u & 1) * p.C : 0) + cb * 32, h_plane = FORM == 0 ? (u >> 1) : 0;
-            mbar_wait(bar_hempty + 8 * hs.i, hs.ph ^ 1);
+            mbar_wait_fast(bars.hempty + 8 * hs.i, hs.ph ^ 1);
             if (no_load) {
-              mbar_arrive(bar_hfull + 8 * hs.i);
+              mbar_arrive(bars.hfull + 8 * hs.i);
             } else {
-              mbar_expect_tx(bar_hfull + 8 * hs.i, kHaloBytes);
-              tma_load_5d(smem_base + hs.i * kHaloStage, &tmap, bar_hfull + 8 * hs.i, c_plane, s0, h_plane, r0, b);
+              mbar_expect_tx(bars.hfull + 8 * hs.i, kHaloBytes);
+              tma_load_5d(smem_base + hs.i * kHaloStage, &tmap, bars.hfull + 8 * hs.i, c_plane, s0, h_plane, r0, b);
             }
-            hs.next(HS);
+            hs.next(CF::HS);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== weight producer: one bulk copy per chunk
-    if (lane == 0) {
-      Ring ws{0, 0};
-      const bool no_load = (p.debug & 8) != 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int var = NVAR > 1 ? item % NVAR : 0;
-        for (int cb = 0; cb < Cblks; ++cb) {
-          const float* cb_img = p.wimg + (size_t)cb * kTaps * (W_BYTES / 4);
-          static_for<0, NVAR>([&](auto VI) {
-            constexpr int V = decltype(VI)::value;
-            if (NVAR > 1 && var != V) return;
-            static_for<0, NGRP>([&](auto GI) {
-              constexpr int g = FORM == 0 ? decltype(GI)::value : V * CG + decltype(GI)::value;
-              constexpr int nkb = grp_nkb(g);
-              static_for<0, (nkb + CH - 1) / CH>([&](auto CI) {
-                constexpr int c0 = decltype(CI)::value * CH;
-                constexpr int nk = nkb - c0 < CH ? nkb - c0 : CH;
-                mbar_wait(bar_wempty + 8 * ws.i, ws.ph ^ 1);
-                if (no_load) {
-                  mbar_arrive(bar_wfull + 8 * ws.i);
-                } else {
-                  mbar_expect_tx(bar_wfull + 8 * ws.i, nk * W_BYTES);
-                  bulk_load(w_base + ws.i * SLOT, cb_img + (size_t)(grp_base(g) + c0) * (W_BYTES / 4), nk * W_BYTES, bar_wfull + 8 * ws.i);
-                }
-                ws.next(WS);
-              });
-            });
-          });
-        }
-      }
-    }
+    if (lane == 0) weight_producer<CF, 0>(p, bars, w_base);
+  } else if (warp == 12) {
+    if (lane == 0) weight_producer<CF, 1>(p, bars, w_base);
   } else if (warp == 2) {
-    // ===================================================================== MMA issuer (whole warp converged, one elected lane issues)
-    constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
-    constexpr uint32_t idescN = idesc_base | ((uint32_t)(N >> 3) << 17);
-    constexpr uint32_t idesc2N = idesc_base | ((uint32_t)((2 * N) >> 3) << 17);
-    const uint64_t adesc0 = make_kmajor_sw128_desc(smem_base, kSbo);           // raw tile of halo stage 0
-    const uint64_t bdesc0 = make_kmajor_sw128_desc(w_base, 1024u);             // weight slot 0: N hi rows, N lo rows per k-block
-    constexpr uint32_t HSTAGE_U = kHaloStage >> 4, LO_U = kHaloSlot >> 4, SLOT_U = SLOT >> 4, W_U = W_BYTES >> 4;
-    const bool no_mma = (p.debug & 2) != 0;
-    Ring hs{0, 0}, ws{0, 0}, ab{0, 0};
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int var = NVAR > 1 ? item % NVAR : 0;
-      mbar_wait(bar_accempty + 8 * ab.i, ab.ph ^ 1);           // the epilogue has drained this accumulator set
-      tc_fence_after();
-      const uint32_t acc0 = tmem_base + ab.i * ACC_COLS;
-      for (int cb = 0; cb < Cblks; ++cb) {
-        const uint32_t acc_g = acc0 + (G == 2 ? (uint32_t)(cb & 1) * 2 * N : 0u);   // this channel block's accumulator pair
-        const uint32_t accum0 = cb >= G ? 1u : 0u;             // 0 -> the pair's first MMA overwrites (zero-initialises) main | corr
-        const bool last_cb = cb == Cblks - 1;
-        uint64_t a_base = 0;
-        static_for<0, NVAR>([&](auto VI) {
-          constexpr int V = decltype(VI)::value;
-          if (NVAR > 1 && var != V) return;
-          static_for<0, NGRP>([&](auto GI) {
-            constexpr int gi = decltype(GI)::value;
-            constexpr int g = FORM == 0 ? gi : V * CG + gi;
-            constexpr int nkb = grp_nkb(g);
-            constexpr int nchunk = (nkb + CH - 1) / CH;
-            constexpr bool unit_first = FORM == 0 || gi == 0, unit_last = FORM == 0 || gi == NGRP - 1;
-            if (unit_first) {
-              mbar_wait(bar_hfull + 8 * hs.i, hs.ph);          // the issuing thread observes the TMA completion itself
-              mbar_wait(bar_hlo + 8 * hs.i, hs.ph);            // ... and the lo tile written from it
-              a_base = adesc0 + (uint64_t)(hs.i * HSTAGE_U);
-            }
-            const uint32_t d_pair = acc_g + (FORM == 0 ? 0u : (uint32_t)(gi * G * 2 * N));
-            static_for<0, nchunk>([&](auto CI) {
-              constexpr int c0 = decltype(CI)::value * CH;
-              constexpr int nk = nkb - c0 < CH ? nkb - c0 : CH;
-              constexpr bool chunk_last = decltype(CI)::value == nchunk - 1;
-              mbar_wait(bar_wfull + 8 * ws.i, ws.ph);
-              tc_fence_after();
-              const uint64_t b_base = bdesc0 + (uint64_t)(ws.i * SLOT_U);
-              if (elect_one()) {
-                if (!no_mma) {
-                  static_for<0, nk>([&](auto KI) {
-                    constexpr int ki = decltype(KI)::value, i = c0 + ki;
-                    constexpr KbGeom kg = kb_geom<FORM>(g, i);
-                    constexpr bool first_kb = i == 0 && (FORM == 1 || gi == 0);   // first k-block of this accumulator pair in the channel block
-                    const uint64_t a_raw = a_base + (uint64_t)kg.a_off16, a_lo = a_raw + LO_U, b_img = b_base + (uint64_t)(ki * W_U);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {               // K = 8 tf32 per instruction = 32 bytes along the 128-byte row
-                      mma_tf32_ss(d_pair, a_raw + 2 * j, b_img + 2 * j, idesc2N, (first_kb && j == 0) ? accum0 : 1u);
-                      mma_tf32_ss(d_pair + N, a_lo + 2 * j, b_img + 2 * j, idescN, 1u);
-                    }
-                  });
-                }
-                tc_commit(bar_wempty + 8 * ws.i);               // weight slot reusable once these MMAs retire
-                if (unit_last && chunk_last) {
-                  tc_commit(bar_hempty + 8 * hs.i);             // so is the halo stage after the unit's last k-block
-                  if ((FORM == 1 || gi == NGRP - 1) && last_cb) tc_commit(bar_accfull + 8 * ab.i);
-                }
-              }
-              __syncwarp();
-              ws.next(WS);
-            });
-            if (unit_last) hs.next(HS);
-          });
-        });
-      }
-      ab.next(ACC_BUFS);
-    }
+    mma_issuer<CF, 0>(p, bars, smem_base, w_base, tmem_base);
+  } else if (warp == 3) {
+    mma_issuer<CF, 1>(p, bars, smem_base, w_base, tmem_base);
   } else if (warp >= 4 && warp < 8) {
     // ===================================================================== lo pass (once per halo tile, elementwise, same byte offsets)
     const int tid = threadIdx.x - 128;
@@ -304,7 +393,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     Ring hs{0, 0};
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       for (int uu = 0; uu < units_per_item; ++uu) {
-        mbar_wait(bar_hfull + 8 * hs.i, hs.ph);
+        mbar_wait_fast(bars.hfull + 8 * hs.i, hs.ph);
         if (!skip) {
           const float4* raw = reinterpret_cast<const float4*>(smem_gen + hs.i * kHaloStage);
           float4* lo = reinterpret_cast<float4*>(smem_gen + hs.i * kHaloStage + kHaloSlot);
@@ -320,30 +409,37 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           }
           fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core's operand reads
         }
-        mbar_arrive(bar_hlo + 8 * hs.i);
-        hs.next(HS);
+        mbar_arrive(bars.hlo + 8 * hs.i);
+        hs.next(CF::HS);
       }
     }
-  } else if (warp >= 8) {
-    // ===================================================================== epilogue
-    const int row = threadIdx.x - 256;                          // tile row == TMEM lane
-    const int q = warp & 3;
+  } else if ((warp >= 8 && warp < 12) || warp >= 13) {
+    // ===================================================================== epilogue (warpgroup wg owns accumulator set wg when there are two)
+    const int wg = warp >= 13 ? 1 : 0;
+    const int q = warp & 3;                                     // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                              // tile row == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* stg = stg_base + (size_t)q * 32 * 36;                // this warp's 32 x (32+4) staging rows
+    float* stg = stg_base + (size_t)(wg * 4 + q) * 32 * 36;     // this warp's 32 x (32+4) staging rows
     constexpr int nchunks = N >> 5;
     constexpr int NCLS = FORM == 0 ? 1 : CG;
+    // accumulator pairs that hold partial sums of the same output columns, and how far apart they are
+    constexpr int NP = FORM == 0 ? (CF::COLSPLIT ? G : 2) : 1;
+    constexpr int PSTRIDE = FORM == 0 ? (CF::COLSPLIT ? 128 : 2 * NI) : 0;
     const bool no_store = (p.debug & 4) != 0;
     const int tw = row & (kTW - 1), th = row >> 3;
     const int act = p.act;
-    const float alpha = p.alpha;
-    Ring ab{0, 0};
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    // LeakyReLU / ReLU / identity as one select (the other activations take the generic path)
+    const bool piecewise = act == UAD_ACT_NONE || act == UAD_ACT_LEAKY || act == UAD_ACT_RELU;
+    const float slope = act == UAD_ACT_LEAKY ? p.alpha : (act == UAD_ACT_RELU ? 0.f : 1.f);
+    Ring ab{(uint32_t)(CF::EPI_WG == 2 ? wg : 0), 0};
+    for (int item = blockIdx.x + (CF::EPI_WG == 2 ? wg * gridDim.x : 0); item < p.n_items; item += CF::EPI_WG * gridDim.x) {
       const int var = NVAR > 1 ? item % NVAR : 0, tile = item / NVAR;
       const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
       const int s0 = twi * kTW, r0 = thi * kTH;
       const uint32_t acc_base = lane_base + ab.i * ACC_COLS;
-      mbar_wait(bar_accfull + 8 * ab.i, ab.ph);
+      mbar_wait_fast(bars.accfull + 8 * ab.i, ab.ph);
       tc_fence_after();
+      if (p.debug & 32) { tc_fence_before(); mbar_arrive(bars.accempty + 8 * ab.i); if (CF::EPI_WG == 2) ab.ph ^= 1; else ab.next(ACC_BUFS); continue; }
       const int cq = (lane & 7) * 4;
 #pragma unroll 1
       for (int cls = 0; cls < NCLS; ++cls) {
@@ -353,20 +449,23 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
         long long offs[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + (lane >> 3));
-        const uint32_t cls_base = acc_base + cls * G * 2 * N;
 #pragma unroll 1
         for (int ch = 0; ch < nchunks; ++ch) {
           const int c0 = ch * 32;
+          // TMEM column of output column c0 in the first pair that holds it: main there, corr NI columns further
+          uint32_t col;
+          if (CF::COLSPLIT) col = (uint32_t)((c0 >> 6) * (FORM == 0 ? G * 128 : 128) + (c0 & 63));
+          else col = (uint32_t)((FORM == 1 ? cls * 2 * NI : 0) + c0);
           uint32_t v[32], u[32];
-          tmem_ld32(cls_base + c0, v);                          // pair 0: main columns [0, N), corr columns [N, 2N)
-          tmem_ld32(cls_base + N + c0, u);
+          tmem_ld32(acc_base + col, v);
+          tmem_ld32(acc_base + col + NI, u);
           tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-          if (G == 2) {
+          if (NP == 2) {
             uint32_t w2[32];
-            tmem_ld32(cls_base + 2 * N + c0, u);
-            tmem_ld32(cls_base + 3 * N + c0, w2);
+            tmem_ld32(acc_base + col + PSTRIDE, u);
+            tmem_ld32(acc_base + col + PSTRIDE + NI, w2);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -374,20 +473,22 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           }
           if (cls + 1 == NCLS && ch + 1 == nchunks) {           // last TMEM read of this thread for the item: hand the set back
             tc_fence_before();
-            mbar_arrive(bar_accempty + 8 * ab.i);
+            mbar_arrive(bars.accempty + 8 * ab.i);
           }
 #pragma unroll 1
           for (int pass = 0; pass < 2; ++pass) {                // z then a from the SAME registers
             float* out = pass == 0 ? p.z_out : p.a_out;
-            if (!out) continue;
+            if (!out || (p.debug & 64)) continue;
+            const bool plain = pass == 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int n = c0 + j + e;
-                const float z = __uint_as_float(v[j + e]) + epi[n];
-                o[e] = pass == 0 ? z : uad_act(epi[N + n] * z + epi[2 * N + n], act, alpha);
+                const float acc = __uint_as_float(v[j + e]);
+                const float t = plain ? acc + epi[n] : fmaf(epi[N + n], acc, epi[2 * N + n]);
+                o[e] = (plain || piecewise) ? (t > 0.f || plain ? t : slope * t) : act_slow(t, act, p.alpha);
               }
               *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -403,7 +504,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           }
         }
       }
-      ab.next(ACC_BUFS);
+      if (CF::EPI_WG == 2) ab.ph ^= 1; else ab.next(ACC_BUFS);   // a warpgroup that owns its set sees every one of its phases
     }
   }
 
@@ -415,25 +516,30 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   }
 }
 
-// raw weights -> per (32-channel block, k-block in group order): {hi, lo} images of [N rows][32 k] fp32 in the SWIZZLE_128B byte
-// order the descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n]; true: raw[t][n][c].
-__global__ void hs_weight_image_kernel(const float* __restrict__ w, float* __restrict__ img, HsOrder order, int C, int N, int transposed) {
+// raw weights -> per (32-channel block, issuer, k-block in the issuer's order): {hi, lo} images of [NI rows][32 k] fp32 in the
+// SWIZZLE_128B byte order the descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n];
+// true: raw[t][n][c].  One thread per (cb, issuer-image, row, k); a column-split issuer W holds output columns [64 W, 64 W + 64).
+__global__ void hs_weight_image_kernel(const float* __restrict__ w, float* __restrict__ img, HsOrder order, int C, int N, int NI,
+                                       int transposed) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)kTaps * C * N;
+  const int nimg = order.cnt[0] + order.cnt[1];                // images per channel block (25, or 50 halves when column-split)
+  const size_t total = (size_t)(C / 32) * nimg * NI * 32;
   if (i >= total) return;
   const int k = i % 32;
-  const int n = (i / 32) % N;
-  const int o = (i / ((size_t)32 * N)) % kTaps;
-  const int cb = i / ((size_t)32 * N * kTaps);
-  const int t = order.wt[o];
+  const int r = (i / 32) % NI;
+  const int im = (i / ((size_t)32 * NI)) % nimg;
+  const int cb = i / ((size_t)32 * NI * nimg);
+  const int W = im >= order.cnt[0] ? 1 : 0, o = W ? im - order.cnt[0] : im;
+  const int t = order.wt[W][o];
   const int c = cb * 32 + k;
+  const int n = (NI < N ? W * NI : 0) + r;
   const float v = transposed ? w[((size_t)t * N + n) * C + c] : w[((size_t)t * C + c) * N + n];
   const uint32_t h = __float_as_uint(v) & 0xffffe000u;
   const float lo = v - __uint_as_float(h);
-  const size_t base = ((size_t)(cb * kTaps + o)) * 2 * N * 32;
-  const int pos = n * 32 + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3));
+  const size_t base = ((size_t)cb * nimg + im) * 2 * NI * 32;
+  const int pos = r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));
   img[base + pos] = __uint_as_float(h);
-  img[base + (size_t)N * 32 + pos] = lo;
+  img[base + (size_t)NI * 32 + pos] = lo;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -454,25 +560,62 @@ EncodeTiledFn hs_encode_fn() {
   return fn;
 }
 
+// weight-image order of a configuration + cross-check of the compiled geometry against the caller's runtime tap tables
 template <class CF>
-int launch_cfg(const CUtensorMap& tmap, HsParams& p, cudaStream_t st) {
-  // shared-memory budget: halo stages (raw + lo), weight slots, barriers / constants / staging
-  const size_t tail = 320 + 3 * CF::N * sizeof(float) + 4 * 32 * 36 * sizeof(float) + 64;
-  const size_t budget = 227 * 1024 - 1024 - tail;
-  // the stride-1 form loads one halo per 4 .. 25 k-blocks and N = 128 spends >= 3000 cycles per halo: two stages cover the
-  // refill there and leave room for a deeper weight ring; the strided form at N <= 64 turns a halo over every 4 .. 9 short k-blocks
-  p.h_stages = (CF::FORM == 1 || CF::N == 128) ? 2 : 3;
-  p.w_stages = (int)((budget - p.h_stages * kHaloStage) / CF::SLOT);
-  if (p.w_stages > 8) p.w_stages = 8;
-  UAD_REQUIRE(p.w_stages >= 2, "conv_halo_ss: shared-memory budget exceeded");
-  const size_t smem = 1024 + p.h_stages * kHaloStage + p.w_stages * CF::SLOT + tail;
+int build_order(const GatherParams& g, HsOrder& order) {
+  memset(&order, 0, sizeof(order));
+  for (int W = 0; W < 2; ++W) {
+    order.cnt[W] = CF::cnt(W);
+    for (int grp = 0; grp < 4; ++grp)
+      for (int i = CF::i0(W, grp); i < CF::i1(W, grp); ++i) {
+        const KbGeom kg = kb_geom<CF::FORM>(grp, i);
+        order.wt[W][CF::ord_base(W, grp) + (i - CF::i0(W, grp))] = (unsigned char)kg.wt;
+        const TapSet& ts = g.taps[CF::FORM == 0 ? 0 : grp];
+        bool found = false;
+        for (int t = 0; t < ts.n && !found; ++t) {
+          if (ts.wt[t] != kg.wt) continue;
+          const int dh = ts.dh[t], dw = ts.dw[t];
+          int wh, wwd;
+          if (CF::FORM == 0) {
+            if ((dh & 1) != (grp >> 1) || (dw & 1) != (grp & 1)) continue;
+            wh = (dh >> 1) + 1; wwd = (dw >> 1) + 1;
+          } else {
+            wh = dh + 1; wwd = dw + 1;
+          }
+          found = (wh * kHW + wwd) * 8 == kg.a_off16;
+        }
+        UAD_REQUIRE(found, "conv_halo_ss: tap table does not match the compiled geometry (group %d, k-block %d)", grp, i);
+      }
+  }
+  UAD_REQUIRE(order.cnt[0] + order.cnt[1] == (CF::COLSPLIT ? 2 : 1) * kTaps, "conv_halo_ss: k-block ownership does not cover the filter");
+  if (CF::FORM == 1)
+    for (int c = 0; c < 4; ++c)
+      UAD_REQUIRE(g.taps[c].oh0 == (c >> 1) && g.taps[c].ow0 == (c & 1) && g.taps[c].n == grp_nkb(c), "conv_halo_ss: class table mismatch");
+  return 0;
+}
+
+template <class CF>
+int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, const float* w_raw, bool weights_transposed, cudaStream_t st) {
+  HsOrder order;
+  if (int rc = build_order<CF>(g, order)) return rc;
+  {
+    const size_t total = (size_t)kTaps * p.C * CF::N;
+    hs_weight_image_kernel<<<uad_cdiv(total, 256), 256, 0, st>>>(w_raw, const_cast<float*>(p.wimg), order, p.C, CF::N, CF::NI,
+                                                                 weights_transposed ? 1 : 0);
+    UAD_LAUNCH_CHECK("hs_weight_image");
+  }
+  // shared memory: halo stages (raw + lo), two weight rings, barriers / constants / staging
+  const size_t tail = 320 + 3 * CF::N * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
+  const size_t smem = 1024 + CF::HS * kHaloStage + 2 * CF::WS * kSlot + tail;
+  UAD_REQUIRE(smem <= 227 * 1024, "conv_halo_ss: shared-memory budget exceeded");
   static bool attr = false;
   if (!attr) {
     UAD_CUDA(cudaFuncSetAttribute(conv_halo_ss<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
+  p.n_items = p.tiles_w * p.tiles_h * p.B * CF::NVAR;
   const int grid = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
-  conv_halo_ss<CF><<<grid, kThreads, smem, st>>>(tmap, p);
+  conv_halo_ss<CF><<<grid, CF::THREADS, smem, st>>>(tmap, p);
   UAD_LAUNCH_CHECK("conv_halo_ss");
   return 0;
 }
@@ -505,39 +648,6 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
   UAD_REQUIRE(encode != nullptr, "conv_halo_ss: cuTensorMapEncodeTiled entry point unavailable");
   const int form = g.sh == 2 ? 0 : 1;
 
-  // the compile-time tap geometry must be the caller's tap tables (uad_conv_api.cu: taps_full / taps_parity)
-  HsOrder order;
-  for (int grp = 0; grp < 4; ++grp)
-    for (int i = 0; i < grp_nkb(grp); ++i) {
-      const KbGeom kg = form == 0 ? kb_geom<0>(grp, i) : kb_geom<1>(grp, i);
-      order.wt[grp_base(grp) + i] = (unsigned char)kg.wt;
-      const TapSet& ts = g.taps[form == 0 ? 0 : grp];
-      bool found = false;
-      for (int t = 0; t < ts.n && !found; ++t) {
-        if (ts.wt[t] != kg.wt) continue;
-        const int dh = ts.dh[t], dw = ts.dw[t];
-        int wh, wwd;
-        if (form == 0) {
-          if ((dh & 1) != (grp >> 1) || (dw & 1) != (grp & 1)) continue;
-          wh = (dh >> 1) + 1; wwd = (dw >> 1) + 1;
-        } else {
-          wh = dh + 1; wwd = dw + 1;
-        }
-        found = (wh * kHW + wwd) * 8 == kg.a_off16;
-      }
-      UAD_REQUIRE(found, "conv_halo_ss: tap table does not match the compiled geometry (group %d, k-block %d)", grp, i);
-    }
-  if (form == 1)
-    for (int c = 0; c < 4; ++c)
-      UAD_REQUIRE(g.taps[c].oh0 == (c >> 1) && g.taps[c].ow0 == (c & 1) && g.taps[c].n == grp_nkb(c), "conv_halo_ss: class table mismatch");
-
-  float* img = reinterpret_cast<float*>(ws);
-  {
-    const size_t total = (size_t)kTaps * C * N;
-    hs_weight_image_kernel<<<uad_cdiv(total, 256), 256, 0, st>>>(w_raw, img, order, C, N, weights_transposed ? 1 : 0);
-    UAD_LAUNCH_CHECK("hs_weight_image");
-  }
-
   HsParams p;
   memset(&p, 0, sizeof(p));
   const int MW = 1 << g.lgMW, MH = 1 << g.lgMH;
@@ -547,7 +657,7 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
   p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
   p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
-  p.wimg = img;
+  p.wimg = reinterpret_cast<float*>(ws);
   { const char* dbg = getenv("UAD_HS_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   UAD_REQUIRE(p.z_out || p.a_out, "conv_halo_ss: no output requested");
 
@@ -571,17 +681,14 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UAD_REQUIRE(cr == CUDA_SUCCESS, "conv_halo_ss: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-  const int tiles = p.tiles_w * p.tiles_h * g.B;
-  const bool g2 = p.Cblks >= 2;
   if (form == 0) {
-    p.n_items = tiles;
-    if (N == 32) return g2 ? launch_cfg<Cfg<0, 32, 1, 2>>(tmap, p, st) : launch_cfg<Cfg<0, 32, 1, 1>>(tmap, p, st);
-    if (N == 64) return g2 ? launch_cfg<Cfg<0, 64, 1, 2>>(tmap, p, st) : launch_cfg<Cfg<0, 64, 1, 1>>(tmap, p, st);
-    return g2 ? launch_cfg<Cfg<0, 128, 1, 2>>(tmap, p, st) : launch_cfg<Cfg<0, 128, 1, 1>>(tmap, p, st);
+    if (N == 32) return launch_cfg<Cfg<0, 32, 1, 1>>(g, tmap, p, w_raw, weights_transposed, st);
+    if (N == 64) return launch_cfg<Cfg<0, 64, 1, 1>>(g, tmap, p, w_raw, weights_transposed, st);
+    return p.Cblks >= 2 ? launch_cfg<Cfg<0, 128, 1, 2>>(g, tmap, p, w_raw, weights_transposed, st)
+                        : launch_cfg<Cfg<0, 128, 1, 1>>(g, tmap, p, w_raw, weights_transposed, st);
   }
   UAD_REQUIRE(C <= 128, "conv_halo_ss: stride-1 form supports at most 128 input channels");
-  if (N == 32) { p.n_items = tiles; return launch_cfg<Cfg<1, 32, 4, 1>>(tmap, p, st); }
-  if (N == 64) { p.n_items = tiles * 2; return launch_cfg<Cfg<1, 64, 2, 1>>(tmap, p, st); }
-  p.n_items = tiles * 4;
-  return launch_cfg<Cfg<1, 128, 1, 1>>(tmap, p, st);
+  if (N == 32) return launch_cfg<Cfg<1, 32, 4, 1>>(g, tmap, p, w_raw, weights_transposed, st);
+  if (N == 64) return launch_cfg<Cfg<1, 64, 2, 1>>(g, tmap, p, w_raw, weights_transposed, st);
+  return launch_cfg<Cfg<1, 128, 1, 1>>(g, tmap, p, w_raw, weights_transposed, st);
 }
