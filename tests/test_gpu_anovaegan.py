@@ -1,14 +1,13 @@
-"""GPU, OPT-IN (UAD_UNVERIFIED=1): first hardware check of the AnoVAEGAN engine / trainer, written after round 1's GPU budget was
+"""GPU (first green hardware run: round 2, gpurun call r2d): first hardware check of the AnoVAEGAN engine / trainer, written after round 1's GPU budget was
 spent.  Its call sequences already match the oracle on CPU through the ABI emulator (tests/test_engine_emulated.py); what
-remains to be seen on the B200 is the same comparison with the real kernels, CUDA-graph replay and the device RNG streams.
-Run:  UAD_UNVERIFIED=1 python -m pytest tests/test_gpu_anovaegan.py -m gpu -q    - then drop the skip."""
+remains to be seen on the B200 is the same comparison with the real kernels, CUDA-graph replay and the device RNG streams."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('UAD_UNVERIFIED') != '1', reason='opt-in: UAD_UNVERIFIED=1')]
+pytestmark = pytest.mark.gpu
 
 from oracle import anovaegan_cpu as AO  # noqa: E402
 from oracle import fanogan_cpu as FO  # noqa: E402

@@ -1,4 +1,4 @@
-"""GPU, OPT-IN (UAD_UNVERIFIED=1): the context-encoder trainer's step (reconstruction target decoupled from the input, engine.set_target)
+"""GPU (first green hardware run: round 2, gpurun call r2d): the context-encoder trainer's step (reconstruction target decoupled from the input, engine.set_target)
 with the real kernels; verified on CPU through the ABI emulator (tests/test_engine_emulated.py), not yet run on hardware."""
 import os
 from collections import OrderedDict
@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('UAD_UNVERIFIED') != '1', reason='opt-in: UAD_UNVERIFIED=1')]
+pytestmark = pytest.mark.gpu
 
 from oracle import tf_graph_cpu as O  # noqa: E402
 

@@ -1,4 +1,4 @@
-"""GPU, OPT-IN (UAD_UNVERIFIED=1): first hardware check of the GMVAE pieces written after round 1's GPU budget was spent - the latent
+"""GPU (first green hardware run: round 2, gpurun call r2d): first hardware check of the GMVAE pieces written after round 1's GPU budget was spent - the latent
 kernel pair (uad_gmvae_latent_fwd / _bwd; its arithmetic header already matches float64 autograd in a host build,
 tests/test_gmvae_latent.py), the GMVAE train step and one restoration iteration (both already verified on CPU through the ABI emulator)."""
 import os
@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get('UAD_UNVERIFIED') != '1', reason='opt-in: UAD_UNVERIFIED=1')]
+pytestmark = pytest.mark.gpu
 
 from oracle import gmvae_cpu as GO  # noqa: E402
 from oracle import tf_graph_cpu as O  # noqa: E402

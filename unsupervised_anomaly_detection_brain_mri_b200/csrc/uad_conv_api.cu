@@ -59,6 +59,15 @@ static int launch_gather_tensor(const GatherParams& p, int nclasses, int ksize, 
   return uad_launch_gather_tc(p, nclasses, ksize, weights_transposed, w_raw, math_mode, ws, ws_bytes, st);
 }
 
+// Form W on tensor cores: the MN-major SS kernel (uad_conv_ws.cu) where the M-grid is wide enough for its pixel blocks, the
+// converter-warp kernel (uad_conv_tc.cu) otherwise.  UAD_WGRAD_SS=0 (developer switch) forces the latter.
+static int launch_wgrad_tensor(const WgradParams& p, float* dw, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  static int use_ss = -1;
+  if (use_ss < 0) { const char* e = getenv("UAD_WGRAD_SS"); use_ss = e ? atoi(e) : 1; }
+  if (use_ss && uad_ws_wgrad_supported(p.Cg, p.Co, p.lgMH, p.lgMW)) return uad_launch_wgrad_ss(p, dw, accumulate, ws, ws_bytes, st);
+  return uad_launch_wgrad_tc(p, dw, accumulate, ws, ws_bytes, st);
+}
+
 extern "C" int uad_conv_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int ksize) {
   (void)B;
   if (ksize != 5) return 0;
@@ -96,6 +105,10 @@ extern "C" size_t uad_conv_workspace_bytes(int op, int B, int H, int W, int Cin,
       size_t simt = (size_t)splits * wbytes + 256;
       size_t tc = (ksize == 5 && uad_tc_wgrad_supported(Cin, Cout, uad_ilog2(H / 2), uad_ilog2(W / 2)))
                       ? uad_tc_wgrad_ws_bytes(Cin, Cout, B * (H / 2) * (W / 2)) : 0;
+      if (ksize == 5 && Cin % 32 == 0 && uad_ws_wgrad_supported(Cin, Cout, uad_ilog2(H / 2), uad_ilog2(W / 2))) {
+        const size_t ss = uad_ws_wgrad_ws_bytes(Cin, Cout, B, H / 2, W / 2);
+        if (ss > tc) tc = ss;
+      }
       return simt > tc ? simt : tc;
     }
     case UAD_OP_CONVT_WGRAD: {
@@ -104,6 +117,10 @@ extern "C" size_t uad_conv_workspace_bytes(int op, int B, int H, int W, int Cin,
       size_t simt = (size_t)splits * wbytes + 256;
       size_t tc = (ksize == 5 && uad_tc_wgrad_supported(Cout, Cin, uad_ilog2(H), uad_ilog2(W)))
                       ? uad_tc_wgrad_ws_bytes(Cout, Cin, B * H * W) : 0;
+      if (ksize == 5 && Cout % 32 == 0 && uad_ws_wgrad_supported(Cout, Cin, uad_ilog2(H), uad_ilog2(W))) {
+        const size_t ss = uad_ws_wgrad_ws_bytes(Cout, Cin, B, H, W);
+        if (ss > tc) tc = ss;
+      }
       return simt > tc ? simt : tc;
     }
     default: return 0;
@@ -170,7 +187,7 @@ extern "C" int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int 
   p.P = B << (p.lgMH + p.lgMW);
   taps_full(&p.taps, ksize);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONV_WGRAD, B, H, W, Cin, Cout, ksize))
-    return uad_launch_wgrad_tc(p, dw, accumulate, ws, ws_bytes, st);
+    return launch_wgrad_tensor(p, dw, accumulate, ws, ws_bytes, st);
   return uad_launch_wgrad_simt(p, dw, accumulate, ws, ws_bytes, st);
 }
 
@@ -230,6 +247,6 @@ extern "C" int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int
   p.P = B << (p.lgMH + p.lgMW);
   taps_full(&p.taps, ksize);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONVT_WGRAD, B, H, W, Cin, Cout, ksize))
-    return uad_launch_wgrad_tc(p, dw, accumulate, ws, ws_bytes, st);
+    return launch_wgrad_tensor(p, dw, accumulate, ws, ws_bytes, st);
   return uad_launch_wgrad_simt(p, dw, accumulate, ws, ws_bytes, st);
 }
