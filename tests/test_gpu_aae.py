@@ -1,7 +1,6 @@
 """GPU (first green hardware run: round 2, gpurun call r2d): first hardware check of the adversarial-autoencoder engine / trainer, written after round 1's GPU
 budget was spent.  Its call sequences already match the oracle on CPU through the ABI emulator (tests/test_engine_emulated.py);
 what remains is the same comparison with the real kernels, CUDA-graph replay and the device RNG streams."""
-import os
 
 import numpy as np
 import pytest

@@ -1,6 +1,5 @@
 """GPU (first green hardware run: round 2, gpurun call r2d): the context-encoder trainer's step (reconstruction target decoupled from the input, engine.set_target)
 with the real kernels; verified on CPU through the ABI emulator (tests/test_engine_emulated.py), not yet run on hardware."""
-import os
 from collections import OrderedDict
 
 import numpy as np

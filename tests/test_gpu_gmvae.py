@@ -1,7 +1,6 @@
 """GPU (first green hardware run: round 2, gpurun call r2d): first hardware check of the GMVAE pieces written after round 1's GPU budget was spent - the latent
 kernel pair (uad_gmvae_latent_fwd / _bwd; its arithmetic header already matches float64 autograd in a host build,
 tests/test_gmvae_latent.py), the GMVAE train step and one restoration iteration (both already verified on CPU through the ABI emulator)."""
-import os
 
 import numpy as np
 import pytest

@@ -63,7 +63,6 @@ int uad_launch_conv_c1_dgrad(const float* dz, const float* w, float* dx, int B, 
 // ---- tcgen05 launchers (uad_conv_tc.cu)
 int uad_tc_gather_supported(int Cin, int N, int lgMH, int lgMW);
 size_t uad_tc_gather_ws_bytes(int ksize, int Cin, int N);
-size_t uad_tc_gather_ss_extra_bytes(int N, size_t in_elems);   // candidate SS kernel (UAD_TC_SS), 0 when off
 int uad_launch_gather_tc(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
                          int math_mode, void* ws, size_t ws_bytes, cudaStream_t st);
 // ---- halo-resident SS-form tcgen05 launcher (uad_conv_hs.cu; round 2): M-grids of at least 16 x 8

@@ -91,12 +91,7 @@ extern "C" size_t uad_conv_workspace_bytes(int op, int B, int H, int W, int Cin,
     case UAD_OP_CONV_DGRAD:
     case UAD_OP_CONVT_FWD: {
       size_t tc = uad_tc_gather_ws_bytes(ksize, Cin, Cout);
-      // gathered tensor and GEMM N of the op (for the candidate SS kernel's {hi, lo} input images; 0 extra bytes by default)
-      const size_t in_elems = op == UAD_OP_CONV_DGRAD    ? (size_t)B * (H / 2) * (W / 2) * Cout
-                              : op == UAD_OP_CONVT_DGRAD ? (size_t)B * (2 * H) * (2 * W) * Cout
-                                                         : (size_t)B * H * W * Cin;
-      const int n_gemm = (op == UAD_OP_CONV_FWD || op == UAD_OP_CONVT_FWD) ? Cout : Cin;
-      return (tc > wbytes ? tc : wbytes) + 256 + uad_tc_gather_ss_extra_bytes(n_gemm, in_elems);
+      return (tc > wbytes ? tc : wbytes) + 256;
     }
     case UAD_OP_CONV_WGRAD: {
       if (Cin == 1) return (size_t)uad_conv_c1_wgrad_blocks(B, H) * ksize * ksize * Cout * sizeof(float) + 256;

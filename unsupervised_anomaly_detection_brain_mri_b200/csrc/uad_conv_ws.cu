@@ -289,7 +289,9 @@ WsPlan ws_plan(int Cg, int Co, int B, int MH, int MW) {
   int target = (4 * UAD_NUM_SMS) / (pl.ntypes * (Cg / 32));
   if (target < 1) target = 1;
   const int px_per_block = kBH * pl.BW;
-  const int min_chunks = uad_cdiv((long long)pl.nblocks * px_per_block, 4096);
+  static int depth = -1;                                       // developer switch UAD_WS_DEPTH: pixels per accumulator
+  if (depth < 0) { const char* e = getenv("UAD_WS_DEPTH"); depth = e ? atoi(e) : 4096; }
+  const int min_chunks = uad_cdiv((long long)pl.nblocks * px_per_block, depth);
   if (target < min_chunks) target = min_chunks;
   if (target > pl.nblocks) target = pl.nblocks;
   pl.bpc = uad_cdiv(pl.nblocks, target);
