@@ -145,12 +145,14 @@ def run_reference(args):
     if rank != 0:
         return
     cores = usable_cores()
-    batch = 16      # bounded sample of the workload per step: 16 of the 64 slices of a mini-batch
-    rate, ms = cpu_reference_step_rate(batch, args.steps, max(1, min(args.warmup, 2)), cores)
-    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': args.steps,
+    batch = B_PER_GPU   # the stated mini-batch (64 slices per step: ~1 s per step on 16 cores, so K = 20 steps stay within a minute)
+    steps = min(args.steps, 20)      # bounded: a 64-slice CPU step takes 1 - 5 s
+    rate, ms = cpu_reference_step_rate(batch, steps, max(1, min(args.warmup, 2)), cores)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU * args.gpus, 'parallelism': f'dp{args.gpus}'},
+            'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU, 'parallelism': 'host cores of rank 0 (the CPU arm does not scale with --gpus)',
+                       'fetch': 'scalar losses only (the reference also fetches the reconstruction and L1 maps every step, trainers/VAE.py:83-96)'},
             'cpu_baseline': {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
                              'sample': f'oracle torch-CPU restatement of the TF graph (TensorFlow 1.15 is not installable here); '
                                        f'{batch}-slice train steps of the same VAE-256 workload'},
@@ -161,14 +163,20 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=400, help='timed steps (default long enough for ~20 loaded clock samples)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--math', default='tc3', choices=['simt', 'tc3', 'tc1'])
+    ap.add_argument('--math', default='tc3', choices=['simt', 'tc3'])
+    ap.add_argument('--config', default='c2', choices=['c2', 'c4', 'c5'], help='BASELINE.json configs[1] (the only one this bench times)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layer-table', default=None, help='write the per-kernel timing table (json) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.config != 'c2':
+        # c4 (bf16 storage / kind::f16 MMA) is not built - every tensor-core kernel here is fp32-accurate 3xTF32; c5 (f-AnoGAN) is
+        # measured by tools/fanogan_time.py, not by this line.  Say so instead of timing something else under their name.
+        print(json.dumps({'impl': args.impl, 'config': args.config, 'unavailable': 'only BASELINE.json configs[1] (VAE 256x256 fp32, batch 64 per GPU) is timed by bench.py; bf16 (c4) is not built'}), flush=True)
+        return
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -185,7 +193,7 @@ def main():
     rank, world = udist.init_from_env('nccl')
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
     B = B_PER_GPU
-    math_mode = {'simt': abi.MATH_FP32_SIMT, 'tc3': abi.MATH_TC_3XTF32, 'tc1': abi.MATH_TC_1XTF32}[args.math]
+    math_mode = {'simt': abi.MATH_FP32_SIMT, 'tc3': abi.MATH_TC_3XTF32}[args.math]
 
     # ---- the public API a user of the reference calls: options -> config -> Trainer(sess, config, network)
     options = get_options(batchsize=B, learningrate=1e-4, numEpochs=1, zDim=ZDIM, outputWidth=S, outputHeight=S)
@@ -253,6 +261,35 @@ def main():
     clocks = sampler.stop()
     e2e_value = world * B * args.steps / e2e_s
     assert math.isfinite(float(run['loss']))
+    # the same loop fetching what the reference's sess.run fetches every step (trainers/VAE.py:83-96: reconstruction + L1 maps)
+    nmaps = max(3, min(args.steps, 50))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(nmaps):
+        run = model.run_batch(host_batches[i % nb], Phase.TRAIN, prefetch=host_batches[(i + 1) % nb], fetch_maps=True)
+    barrier()
+    e2e_maps_value = world * B * nmaps / udist.max_over_ranks(time.perf_counter() - t0, dev)
+    maps_bytes = int(run['reconstruction'].nbytes + run['L1'].nbytes)
+
+    # ---- a fast-but-wrong kernel must not pass as a number: one parity step (fixed eps / dropout masks) against the oracle's loss
+    loss_check = None
+    if rank == 0:
+        from oracle import tf_graph_cpu as O
+        rng = np.random.default_rng(11)
+        eps = rng.standard_normal((B, ZDIM)).astype(np.float32)
+        om = {k: (rng.uniform(size=(B, n)) >= config.dropout_rate).astype(np.float32) for k, n in (('mu', ZDIM), ('log_sigma', ZDIM), ('dec', eng.flat))}
+        Pnow = eng.fp.to_numpy(eng.fp.params)
+        eng.set_inputs(dev_batches[0])
+        eng.set_noise(eps, {'mu': om['mu'], 'ls': om['log_sigma'], 'dec': om['dec']}, None)
+        eng.forward(training=True, dropout_rate=config.dropout_rate)      # uses the staged eps / masks (no device draw)
+        torch.cuda.synchronize()
+        got = float(eng.losses()['loss'])
+        ref = 0.0
+        for j in range(0, B, 16):
+            o = O.forward(O.VAE, Pnow, host_batches[0][j:j + 16], eps=eps[j:j + 16], masks={k: v[j:j + 16] for k, v in om.items()},
+                          dropout_rate=config.dropout_rate, training=True, dtype=torch.float32)
+            ref += float(O.losses(O.VAE, o, host_batches[0][j:j + 16])['loss']) * 16 / B
+        loss_check = {'engine': got, 'oracle_fp32': ref, 'rel_err': abs(got - ref) / abs(ref), 'ok': abs(got - ref) / abs(ref) < 1e-4}
 
     # ---- kernels per step (graph replays launch the captured kernels; count one eager step)
     eng.graph, eng._warm = None, None
@@ -316,13 +353,15 @@ def main():
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'global_batch': B * world, 'parallelism': f'dp{world}',
-                       'math': {'simt': 'fp32 FFMA', 'tc3': 'tcgen05 3xTF32 (fp32-accurate) where supported, fp32 FFMA elsewhere',
-                                'tc1': 'tcgen05 1xTF32'}[args.math],
+                       'math': {'simt': 'fp32 FFMA', 'tc3': 'tcgen05 3xTF32 (fp32-accurate) where supported, fp32 FFMA elsewhere'}[args.math],
                        'l2': 'per-step working set (~2 GB of activations) >> 126 MB L2; 4 distinct input batches rotate',
                        'cuda_graph': True},
             'step_tflops': step_flops(B) * world / (ms_step / 1e3) / 1e12,
             'e2e': {'value': e2e_value, 'unit': 'slices/s', 'h2d_bytes_per_step': int(host_batches[0].nbytes),
-                    'd2h_bytes_per_step': int(eng.scalars.numel() * 4)},
+                    'd2h_bytes_per_step': int(eng.scalars.numel() * 4),
+                    'with_maps': {'value': e2e_maps_value, 'unit': 'slices/s', 'd2h_bytes_per_step': maps_bytes + int(eng.scalars.numel() * 4),
+                                  'note': 'also fetches the reconstruction and L1 maps every step, as the reference sess.run does'}},
+            'loss_check': loss_check,
             'gpu_launches': int(per_step * args.steps),
             'gpu_launches_per_step': int(per_step),
             'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu}

@@ -144,6 +144,21 @@ def lrelu(x):
     return F.leaky_relu(x, LRELU_ALPHA)
 
 
+def _act_with_sign(h, slope, signs, key):
+    """LeakyReLU (slope = alpha) / ReLU (slope = 0) of the NCHW pre-activation ``h``.  ``signs`` (test aid, default None = the
+    literal activation): {key: bool array NHWC, True where the IMPLEMENTATION's pre-activation is positive}.  The activations are
+    piecewise linear, so a pre-activation within rounding of 0 legitimately falls on either branch; evaluating the oracle on the
+    implementation's branch removes that non-differentiability from the gradient comparison (same device as ``l1_sign``).  The
+    fraction of elements on which the imposed pattern differs from the oracle's own is appended to signs['_mismatch']."""
+    if signs is None or key not in signs:
+        return torch.where(h > 0, h, slope * h)
+    m = signs[key]
+    m = m if isinstance(m, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(m))
+    m = m.reshape(h.shape[0], h.shape[2], h.shape[3], h.shape[1]).permute(0, 3, 1, 2).to(torch.bool)
+    signs.setdefault('_mismatch', []).append(float(((h.detach() > 0) != m).double().mean()))
+    return torch.where(m, h, slope * h)
+
+
 def dropout(x, mask, rate, training):
     """Keras Dropout: x*mask/(1-rate) when training.  mask is a {0,1} array supplied by the caller."""
     if not training or mask is None:
@@ -161,28 +176,30 @@ def _bn_names(P, scope):
     return ks
 
 
-def encoder(P, x):
-    """build_unified_encoder applied (models/customlayers.py:16-24; autoencoder.py:12-17).  x is NCHW."""
+def encoder(P, x, signs=None, tag=''):
+    """build_unified_encoder applied (models/customlayers.py:16-24; autoencoder.py:12-17).  x is NCHW.
+    signs / tag: optional activation branch patterns, keys 'enc<i><tag>' (see _act_with_sign)."""
     bns = _bn_names(P, 'Encoder')
     h = x
     i = 0
     while f'Encoder/enc_conv2D_{i}/kernel' in P:
         h = conv2d_same_s2(h, P[f'Encoder/enc_conv2D_{i}/kernel'], P[f'Encoder/enc_conv2D_{i}/bias'])
         h = bn_frozen(h, P[bns[i] + '/gamma'], P[bns[i] + '/beta'])
-        h = lrelu(h)
+        h = _act_with_sign(h, LRELU_ALPHA, signs, f'enc{i}{tag}')
         i += 1
     return h
 
 
-def decoder(P, h):
-    """build_unified_decoder applied (models/customlayers.py:27-38).  h is NCHW."""
+def decoder(P, h, signs=None, tag=''):
+    """build_unified_decoder applied (models/customlayers.py:27-38).  h is NCHW.
+    signs / tag: optional activation branch patterns, keys 'dec_entry<tag>', 'dec<i><tag>' (see _act_with_sign)."""
     bns = _bn_names(P, 'Decoder')
-    h = F.relu(bn_frozen(h, P[bns[0] + '/gamma'], P[bns[0] + '/beta']))
+    h = _act_with_sign(bn_frozen(h, P[bns[0] + '/gamma'], P[bns[0] + '/beta']), 0.0, signs, f'dec_entry{tag}')
     i = 0
     while f'Decoder/dec_Conv2DT_{i}/kernel' in P:
         h = conv2dT_same_s2(h, P[f'Decoder/dec_Conv2DT_{i}/kernel'], P[f'Decoder/dec_Conv2DT_{i}/bias'])
         h = bn_frozen(h, P[bns[i + 1] + '/gamma'], P[bns[i + 1] + '/beta'])
-        h = lrelu(h)
+        h = _act_with_sign(h, LRELU_ALPHA, signs, f'dec{i}{tag}')
         i += 1
     return conv1x1(h, P['Decoder/dec_Conv2D_final/kernel'], P['Decoder/dec_Conv2D_final/bias'])
 
@@ -195,19 +212,21 @@ def _unflatten_nhwc(v, res, c):
     return v.reshape(v.shape[0], res, res, c).permute(0, 3, 1, 2)
 
 
-def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, training=False, dtype=torch.float32):
+def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, training=False, dtype=torch.float32, act_signs=None):
     """Restates models/autoencoder.py:9-40, variational_autoencoder.py:9-47,
     context_encoder_variational_autoencoder.py:9-59.
 
     x, x_ce: NHWC.  eps: [B,zDim] standard-normal draw replacing tf.random_normal (always live).
     masks: dict of {0,1} dropout masks: 'z' (AE) | 'mu','log_sigma','dec' (VAE) | + 'mu_ce','dec_ce' (ceVAE).
+    act_signs: optional activation branch patterns of the x branch (keys 'enc<i>', 'dec_entry', 'dec<i>') and of the ceVAE x_ce branch
+    (same keys + '_ce'); VAE / ceVAE graphs only.
     Returns a dict of NHWC / [B,z] torch tensors (autograd-connected to P if P holds leaf tensors).
     """
     masks = masks or {}
     P = {k: _t(v, dtype) for k, v in P.items()}
     xt = _t(x, dtype).permute(0, 3, 1, 2)
     out = {}
-    h = encoder(P, xt)
+    h = encoder(P, xt, act_signs)
 
     def M(name):
         m = masks.get(name)
@@ -251,15 +270,15 @@ def forward(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, tr
     d = dropout(z @ P['Bottleneck/dense_2/kernel'] + P['Bottleneck/dense_2/bias'], M('dec'), dropout_rate, training)
     h = conv1x1(_unflatten_nhwc(d, res, cb), P['Bottleneck/conv2d_1/kernel'], P['Bottleneck/conv2d_1/bias'])
     out.update(z_mu=mu, z_log_sigma=ls, z_sigma=sigma, z=z)
-    out['x_hat'] = decoder(P, h).permute(0, 2, 3, 1)
+    out['x_hat'] = decoder(P, h, act_signs).permute(0, 2, 3, 1)
     if arch == CEVAE:
         xc = _t(x_ce, dtype).permute(0, 3, 1, 2)
-        hc = conv1x1(encoder(P, xc), P['Bottleneck/conv2d/kernel'], P['Bottleneck/conv2d/bias'])
+        hc = conv1x1(encoder(P, xc, act_signs, '_ce'), P['Bottleneck/conv2d/kernel'], P['Bottleneck/conv2d/bias'])
         mu_ce = dropout(_flatten_nhwc(hc) @ P['Bottleneck/dense/kernel'] + P['Bottleneck/dense/bias'], M('mu_ce'), dropout_rate, training)
         dc = dropout(mu_ce @ P['Bottleneck/dense_2/kernel'] + P['Bottleneck/dense_2/bias'], M('dec_ce'), dropout_rate, training)
         hc = conv1x1(_unflatten_nhwc(dc, res, cb), P['Bottleneck/conv2d_1/kernel'], P['Bottleneck/conv2d_1/bias'])
         out['z_mu_ce'] = mu_ce
-        out['x_hat_ce'] = decoder(P, hc).permute(0, 2, 3, 1)
+        out['x_hat_ce'] = decoder(P, hc, act_signs, '_ce').permute(0, 2, 3, 1)
     return out
 
 
@@ -309,11 +328,12 @@ def losses(arch, out, x, x_ce=None, dtype=torch.float32, l1_sign=None, l1_sign_c
 
 
 def loss_and_grads(arch, P, x, *, x_ce=None, eps=None, masks=None, dropout_rate=0.0, training=True, dtype=torch.float32,
-                   want_anomaly=False, l1_sign=None, l1_sign_ce=None, rho=1.0):
+                   want_anomaly=False, l1_sign=None, l1_sign_ce=None, rho=1.0, act_signs=None):
     """tf.gradients of losses['loss'] w.r.t. every trainable variable (DLMODEL.py:112-131); ceVAE 'anomaly' (ceVAE.py:51)."""
     Pt = OrderedDict((k, _t(v, dtype).clone().requires_grad_(True)) for k, v in P.items())
     xt = _t(x, dtype).clone().requires_grad_(want_anomaly)
-    out = forward(arch, Pt, xt, x_ce=x_ce, eps=eps, masks=masks, dropout_rate=dropout_rate, training=training, dtype=dtype)
+    out = forward(arch, Pt, xt, x_ce=x_ce, eps=eps, masks=masks, dropout_rate=dropout_rate, training=training, dtype=dtype,
+                  act_signs=act_signs)
     L = losses(arch, out, xt, x_ce=x_ce, dtype=dtype, l1_sign=l1_sign, l1_sign_ce=l1_sign_ce, rho=rho)
     names = list(Pt.keys())
     grads = torch.autograd.grad(L['loss'], [Pt[k] for k in names], retain_graph=want_anomaly, allow_unused=True)

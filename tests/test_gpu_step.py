@@ -277,7 +277,20 @@ def test_cevae_reconstruct_anomaly_parity(mode):
     assert _relerr(x - np.float32(lam) * an, ref['reconstruction']) < TOL
 
 
-def _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom, chunk=8, dtype=torch.float64):
+def _act_signs(eng):
+    """Branch (u > 0) of every LeakyReLU / ReLU as the ENGINE took it, from the block outputs it keeps (sign(a) == sign(u)):
+    the oracle is differentiated on the same branches (oracle.tf_graph_cpu._act_with_sign)."""
+    signs = {}
+    for tag, br in (('', eng.br[0]),) + ((('_ce', eng.br[1]),) if len(eng.br) > 1 and eng.arch == O.CEVAE else ()):
+        for i, a in enumerate(br.enc_a):
+            signs[f'enc{i}{tag}'] = (a > 0).cpu().numpy()
+        signs[f'dec_entry{tag}'] = (br.ar > 0).cpu().numpy()
+        for i, a in enumerate(br.dec_a):
+            signs[f'dec{i}{tag}'] = (a > 0).cpu().numpy()
+    return signs
+
+
+def _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom, chunk=8, dtype=torch.float64, act_signs=None):
     """float64 oracle of a LARGE batch in sub-batches: samples are independent (frozen BN) and loss = mean_b, so
     loss / gradients of the batch are the means of the sub-batch ones; bounds the host memory of the autograd graph."""
     B = x.shape[0]
@@ -285,9 +298,12 @@ def _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom, c
     for i in range(0, B, chunk):
         sl = slice(i, i + chunk)
         m = {k: v[sl] for k, v in om.items()}
+        sg = None if act_signs is None else {k: v[sl] for k, v in act_signs.items()}
         out, L, g = O.loss_and_grads(arch, P, x[sl], x_ce=None if x_ce is None else x_ce[sl], eps=eps[sl], masks=m, dropout_rate=rate,
                                      training=True, dtype=dtype, want_anomaly=want_anom, l1_sign=sgn[sl],
-                                     l1_sign_ce=None if sgn_ce is None else sgn_ce[sl])
+                                     l1_sign_ce=None if sgn_ce is None else sgn_ce[sl], act_signs=sg)
+        if sg is not None:                                # the imposed branches are the oracle's own except on a negligible set
+            assert max(sg['_mismatch']) < 1e-4, sg['_mismatch']
         w = (min(i + chunk, B) - i) / B
         G = {k: v.double() * w for k, v in g.items()} if G is None else {k: G[k] + v.double() * w for k, v in g.items()}
         for k in ('loss', 'reconstructionLoss', 'kl'):
@@ -325,7 +341,8 @@ def test_train_step_parity_at_the_benched_configs(arch, S, B):
     xh_dev = eng.br[0].xhat.cpu().numpy()
     sgn = np.sign(xh_dev.astype(np.float64) - x)
     sgn_ce = np.sign(eng.br[1].xhat.cpu().numpy().astype(np.float64) - x_ce) if arch == O.CEVAE else None
-    xh, xhc, an, L, G = _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom)
+    signs = _act_signs(eng)
+    xh, xhc, an, L, G = _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, want_anom, act_signs=signs)
     assert (np.sign(xh - x) != sgn).mean() < 1e-4
     got = eng.losses()
     for k in ('loss', 'reconstructionLoss', 'kl'):
@@ -335,5 +352,5 @@ def test_train_step_parity_at_the_benched_configs(arch, S, B):
         assert _relerr(eng.br[1].xhat.cpu().numpy(), xhc) < TOL
         assert _relerr(eng.anomaly.cpu().numpy(), an) < TOL
     grads = eng.fp.to_numpy(eng.fp.grads)
-    _, _, _, _, G32 = _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, False, dtype=torch.float32)
+    _, _, _, _, G32 = _oracle_in_chunks(arch, P, x, x_ce, eps, om, rate, sgn, sgn_ce, False, dtype=torch.float32, act_signs=signs)
     _check_grads(grads, G, G32, f'{arch} {S}x{S} B={B}')

@@ -395,16 +395,15 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       for (int uu = 0; uu < units_per_item; ++uu) {
         mbar_wait_fast(bars.hfull + 8 * hs.i, hs.ph);
         if (!skip) {
-          const float4* raw = reinterpret_cast<const float4*>(smem_gen + hs.i * kHaloStage);
+          float4* raw = reinterpret_cast<float4*>(smem_gen + hs.i * kHaloStage);
           float4* lo = reinterpret_cast<float4*>(smem_gen + hs.i * kHaloStage + kHaloSlot);
 #pragma unroll 4
           for (int i = tid; i < (int)(kHaloBytes / 16); i += 128) {
             const float4 v = raw[i];
-            float4 l;
-            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            float4 h, l;
+            h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+            raw[i] = h;                                         // hi = round-to-nearest tf32 (in place), lo = x - hi
             lo[i] = l;
           }
           fence_proxy_async();                                  // generic-proxy stores -> visible to the tensor core's operand reads
@@ -534,7 +533,7 @@ __global__ void hs_weight_image_kernel(const float* __restrict__ w, float* __res
   const int c = cb * 32 + k;
   const int n = (NI < N ? W * NI : 0) + r;
   const float v = transposed ? w[((size_t)t * N + n) * C + c] : w[((size_t)t * C + c) * N + n];
-  const uint32_t h = __float_as_uint(v) & 0xffffe000u;
+  const uint32_t h = __float_as_uint(tf32_rn(v));
   const float lo = v - __uint_as_float(h);
   const size_t base = ((size_t)cb * nimg + im) * 2 * NI * 32;
   const int pos = r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));

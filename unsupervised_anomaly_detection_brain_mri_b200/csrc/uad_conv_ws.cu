@@ -185,16 +185,15 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
     for (int blk = blk0; blk < blk1; ++blk) {
       mbar_wait(bar_full + 8 * s, ph);
       if (!skip) {
-        const float4* raw = reinterpret_cast<const float4*>(smem_gen + s * STAGE);
+        float4* raw = reinterpret_cast<float4*>(smem_gen + s * STAGE);
         float4* lo = reinterpret_cast<float4*>(smem_gen + s * STAGE + HALF);
 #pragma unroll 4
         for (int i = tid; i < (int)(HALF / 16); i += 128) {
           const float4 v = raw[i];
-          float4 l;
-          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          float4 h, l;
+          h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          raw[i] = h;                                           // hi = round-to-nearest tf32 (in place), lo = x - hi
           lo[i] = l;
         }
         fence_proxy_async();

@@ -103,6 +103,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+// fp32 -> tf32 (10 mantissa bits) with round-to-nearest (ties away): the tensor core would TRUNCATE the word, which makes
+// lo = x - hi one-signed and the dropped lo * lo term of the 3xTF32 scheme a systematic bias in cancelling sums
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups `sbo_bytes` apart.  The 128-byte

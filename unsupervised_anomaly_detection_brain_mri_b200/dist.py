@@ -59,3 +59,12 @@ def max_over_ranks(value, device):
     if world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def mean_over_ranks(value, device):
+    """Mean of a host scalar over the ranks (every rank gets the same number: e.g. the validation loss that decides early stopping)."""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t /= world_size()
+    return float(t.item())

@@ -216,12 +216,19 @@ class AEMODEL(DLMODEL, ABC):
         best_cost = inf
         last_improvement = 0
         last_epoch = self.load_checkpoint()
+        from .. import dist as udist
         for epoch in range(last_epoch, self.config.numEpochs):
             self.process(dataset, epoch, Phase.TRAIN, self.optim)
             last_epoch += 1
-            self.save(self.checkpointDir, last_epoch)
+            if udist.rank() == 0:                          # data parallel: identical weights on every rank, one writer
+                self.save(self.checkpointDir, last_epoch)
             val_scalars = self.process(dataset, epoch, Phase.VAL)
-            best_cost, last_improvement, stop = indicate_early_stopping(val_scalars['loss'], best_cost, last_improvement)
+            # data parallel: every rank must take the same early-stopping decision (a rank that leaves the loop alone would
+            # leave the others blocked in the gradient all-reduce) - decide on the mean validation loss over the ranks
+            val_loss = val_scalars['loss']
+            if self.world > 1:
+                val_loss = udist.mean_over_ranks(float(np.mean(val_loss)), self.device)
+            best_cost, last_improvement, stop = indicate_early_stopping(val_loss, best_cost, last_improvement)
             if stop:
                 print('Early stopping was triggered due to no improvement over the last 5 epochs')
                 break
@@ -230,6 +237,9 @@ class AEMODEL(DLMODEL, ABC):
         scalars = defaultdict(list)
         visuals = []
         num_batches = dataset.num_batches(self.config.batchsize, set=phase.value)
+        if self.world > 1:                                 # every rank steps the same number of times (one all-reduce per step)
+            from .. import dist as udist
+            num_batches = int(-udist.max_over_ranks(-num_batches, self.device))
         every = int(getattr(self.config, 'fetchMapsEvery', 0))      # the reference fetches the full maps EVERY step
         verbose = bool(getattr(self.config, 'verbose', True))
         def fetch():
