@@ -4,7 +4,6 @@ import numpy as np
 import torch
 sys.path.insert(0, '.')
 from oracle import tf_graph_cpu as O
-from unsupervised_anomaly_detection_brain_mri_b200 import abi
 from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
 arch, S, B, lr = O.VAE, 64, 4, 1e-3
 P = O.perturb_params(O.init_params(arch, S, seed=1))

@@ -1,7 +1,6 @@
 """Developer aid: filter-gradient error of the tensor-core Form-W kernels against float64 at VAE-256 layer shapes, as a function of
 the accumulator depth (UAD_WS_DEPTH, read once per process: run one depth per process)."""
 import os, sys
-import numpy as np
 import torch
 sys.path.insert(0, '.')
 from unsupervised_anomaly_detection_brain_mri_b200 import abi
