@@ -80,6 +80,14 @@ int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, i
 int uad_convT2d_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
                     float* z_out, float* a_out, int B, int H, int W, int Cin, int Cout, int ksize, int act, float alpha,
                     float bn_c, int math_mode, void* ws, size_t ws_bytes, void* stream);
+/* the last decoder block fused with the 1x1 conv that follows it (models/customlayers.py:34-37: Conv2DTranspose + BN + LeakyReLU,
+ * then Conv2D(C, 1)): a_out as uad_convT2d_fwd, head_out[b, y, x] = sum_c a_out[b, y, x, c] * head_w[c] + head_b[0].
+ * Tensor-core path only (Cout = 32); ask uad_convT2d_fwd_head_supported first and fall back to uad_convT2d_fwd +
+ * uad_final1x1_l1_fwd when it returns 0.  The L1 residual / per-sample sums then come from uad_l1_map. */
+int uad_convT2d_fwd_head_supported(int B, int H, int W, int Cin, int Cout, int ksize, int math_mode);
+int uad_convT2d_fwd_head(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float* a_out,
+                         const float* head_w, const float* head_b, float* head_out, int B, int H, int W, int Cin, int Cout,
+                         int ksize, int act, float alpha, float bn_c, int math_mode, void* ws, size_t ws_bytes, void* stream);
 int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout, int ksize,
                       int math_mode, void* ws, size_t ws_bytes, void* stream);
 int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout, int ksize,

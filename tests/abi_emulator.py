@@ -143,6 +143,15 @@ def uad_convT2d_fwd(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cin, Cout, k
     _w(a_out, _act(_affine(z, gamma, beta, Cout, bn_c), act, alpha))
 
 
+def uad_convT2d_fwd_head_supported(B, H, W, Cin, Cout, k, mm):
+    return 0          # tensor-core path only: the emulated engines take the unfused sequence (uad_convT2d_fwd + uad_final1x1_l1_fwd)
+
+
+def uad_convT2d_fwd_head(x, w, bias, gamma, beta, a_out, head_w, head_b, head_out, B, H, W, Cin, Cout, k, act, alpha, bn_c, mm, ws, wsb, st):
+    uad_convT2d_fwd(x, w, bias, gamma, beta, None, a_out, B, H, W, Cin, Cout, k, act, alpha, bn_c, mm, ws, wsb, st)
+    _w(head_out, _v(a_out, B * 4 * H * W, Cout) @ _v(head_w, Cout) + _v(head_b, 1))
+
+
 def uad_convT2d_dgrad(dz, w, dx, B, H, W, Cin, Cout, k, mm, ws, wsb, st):
     x = torch.zeros(B, Cin, H, W, dtype=D, requires_grad=True)
     y = conv2dT_same_s2(x, _v(w, k, k, Cout, Cin), torch.zeros(Cout, dtype=D))

@@ -30,6 +30,8 @@ SIGNATURES = {
     'uad_conv2d_dgrad': (_I, [_P] * 3 + [_I] * 7 + [_P, _Z, _P]),
     'uad_conv2d_wgrad': (_I, [_P] * 3 + [_I] * 8 + [_P, _Z, _P]),
     'uad_convT2d_fwd': (_I, [_P] * 7 + [_I] * 7 + [_F, _F, _I, _P, _Z, _P]),
+    'uad_convT2d_fwd_head_supported': (_I, [_I] * 7),
+    'uad_convT2d_fwd_head': (_I, [_P] * 9 + [_I] * 7 + [_F, _F, _I, _P, _Z, _P]),
     'uad_convT2d_dgrad': (_I, [_P] * 3 + [_I] * 7 + [_P, _Z, _P]),
     'uad_convT2d_wgrad': (_I, [_P] * 3 + [_I] * 8 + [_P, _Z, _P]),
     'uad_rowreduce_workspace_bytes': (_Z, [_LL, _I]),

@@ -30,6 +30,10 @@ struct GatherParams {
   int act;
   float alpha, bn_c;
   TapSet taps[4];
+  // optional fused 1x1 head (tensor-core stride-1 form with N = 32 only): head_out[pixel] = sum_n a[pixel][n] * head_w[n] + head_b[0]
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
 };
 
 // Form W: partial[z][(t, cg)][co] = sum_{pix in chunk z} g[gather(pix, t), cg] * o[pix, co]

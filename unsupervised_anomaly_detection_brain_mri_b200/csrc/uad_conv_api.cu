@@ -211,6 +211,36 @@ extern "C" int uad_convT2d_fwd(const float* x, const float* w, const float* bias
   return uad_launch_gather_simt(p, 4, st);
 }
 
+// transposed conv block + the 1x1 conv that follows it (Cout -> 1 channel), fused into the block's epilogue: the tensor-core path
+// only, Cout = 32 (one thread of the epilogue holds a pixel's 32 channels).  Callers ask uad_convT2d_fwd_head_supported first.
+extern "C" int uad_convT2d_fwd_head_supported(int B, int H, int W, int Cin, int Cout, int ksize, int math_mode) {
+  static int use_hs = -1;
+  if (use_hs < 0) { const char* e = getenv("UAD_HS"); use_hs = e ? atoi(e) : 1; }
+  return use_hs && math_mode == UAD_MATH_TC_3XTF32 && ksize == 5 && Cout == 32 && uad_is_pow2(H) && uad_is_pow2(W) && B > 0 &&
+         uad_hs_gather_supported(Cin, Cout, uad_ilog2(H), uad_ilog2(W), 4);
+}
+
+extern "C" int uad_convT2d_fwd_head(const float* x, const float* w, const float* bias, const float* gamma, const float* beta,
+                                    float* a_out, const float* head_w, const float* head_b, float* head_out, int B, int H, int W,
+                                    int Cin, int Cout, int ksize, int act, float alpha, float bn_c, int math_mode, void* ws,
+                                    size_t ws_bytes, void* stream) {
+  if (int e = check_geom("uad_convT2d_fwd_head", B, H, W, Cin, Cout, ksize)) return e;
+  UAD_REQUIRE(uad_convT2d_fwd_head_supported(B, H, W, Cin, Cout, ksize, math_mode), "uad_convT2d_fwd_head: unsupported shape / math mode");
+  UAD_REQUIRE(a_out && head_w && head_b && head_out, "uad_convT2d_fwd_head: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GatherParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = x; p.a_out = a_out; p.bias = bias; p.gamma = gamma; p.beta = beta;
+  p.B = B; p.IH = H; p.IW = W; p.Cin = Cin;
+  p.lgMH = uad_ilog2(H); p.lgMW = uad_ilog2(W); p.sh = 1;
+  p.OH = 2 * H; p.OW = 2 * W; p.N = Cout; p.osh = 2;
+  p.M = B << (p.lgMH + p.lgMW);
+  p.act = act; p.alpha = alpha; p.bn_c = bn_c;
+  p.head_w = head_w; p.head_b = head_b; p.head_out = head_out;
+  for (int c = 0; c < 4; ++c) taps_parity(&p.taps[c], ksize, c >> 1, c & 1);
+  return uad_launch_gather_hs(p, 4, ksize, true, w, ws, ws_bytes, st);
+}
+
 extern "C" int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
                                  int ksize, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_convT2d_dgrad", B, H, W, Cin, Cout, ksize)) return e;

@@ -153,6 +153,10 @@ struct HsParams {
   float bn_c, alpha;
   int act;
   const float* wimg;   // [Cblks][issuer][k-blocks in the issuer's order][2][NI][32] pre-swizzled {hi, lo} weight images
+  // optional fused 1x1 head (stride-1 form, N = 32 only): head_out[pixel] = sum_n a[pixel][n] * head_w[n] + head_b[0]
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
 };
 
 struct Ring {                                                // ring position + phase parity
@@ -323,7 +327,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   bars.accempty = misc + 240;             // 2 x 8
   const uint32_t tmem_slot = misc + 256;
   float* epi = reinterpret_cast<float*>(smem_gen + misc_off + 320);            // bias[N], scale[N], shift[N]
-  float* stg_base = epi + 3 * N;                                               // 4 warps x 32 x 36 staging
+  float* stg_base = epi + (N == 32 ? 4 : 3) * N;                               // N = 32: [3N, 4N) head weights; then 4 warps x 32 x 36 staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cblks = p.Cblks;
@@ -343,6 +347,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       epi[n] = bias;
       epi[N + n] = scale;
       epi[2 * N + n] = scale * bias + (p.beta ? p.beta[n] : 0.f);         // a = act(scale * acc + shift')
+      if (N == 32) epi[3 * N + n] = p.head_out ? p.head_w[n] : 0.f;
     }
   }
   tc_fence_before();
@@ -479,6 +484,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
             float* out = pass == 0 ? p.z_out : p.a_out;
             if (!out || (p.debug & 64)) continue;
             const bool plain = pass == 0;
+            float head = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float o[4];
@@ -488,9 +494,11 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
                 const float acc = __uint_as_float(v[j + e]);
                 const float t = plain ? acc + epi[n] : fmaf(epi[N + n], acc, epi[2 * N + n]);
                 o[e] = (plain || piecewise) ? (t > 0.f || plain ? t : slope * t) : act_slow(t, act, p.alpha);
+                if (FORM == 1 && N == 32) head = fmaf(o[e], epi[3 * N + n], head);
               }
               *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(o[0], o[1], o[2], o[3]);
             }
+            if (FORM == 1 && N == 32 && !plain && p.head_out) p.head_out[my_off / N] = head + p.head_b[0];
             __syncwarp();
             float4 vals[8];
 #pragma unroll
@@ -604,7 +612,7 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
     UAD_LAUNCH_CHECK("hs_weight_image");
   }
   // shared memory: halo stages (raw + lo), two weight rings, barriers / constants / staging
-  const size_t tail = 320 + 3 * CF::N * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
+  const size_t tail = 320 + (CF::N == 32 ? 4 : 3) * CF::N * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
   const size_t smem = 1024 + CF::HS * kHaloStage + 2 * CF::WS * kSlot + tail;
   UAD_REQUIRE(smem <= 227 * 1024, "conv_halo_ss: shared-memory budget exceeded");
   static bool attr = false;
@@ -656,6 +664,8 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
   p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
   p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
+  p.head_w = g.head_w; p.head_b = g.head_b; p.head_out = g.head_out;
+  UAD_REQUIRE(!g.head_out || (form == 1 && N == 32 && g.a_out && g.head_w && g.head_b), "conv_halo_ss: the fused 1x1 head needs the stride-1 form with N = 32");
   p.wimg = reinterpret_cast<float*>(ws);
   { const char* dbg = getenv("UAD_HS_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   UAD_REQUIRE(p.z_out || p.a_out, "conv_halo_ss: no output requested");

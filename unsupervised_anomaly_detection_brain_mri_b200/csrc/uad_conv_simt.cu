@@ -279,13 +279,25 @@ __global__ void __launch_bounds__(BM* BN / 64) wgrad_simt(const __grid_constant_
   }
 }
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n, float* __restrict__ out,
-                                     int accumulate) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = accumulate ? out[i] : 0.f;
-  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * n + i];
-  out[i] = s;
+// deterministic split-K reduction.  A thread per output walking `splits` partials serially is latency bound (292 dependent
+// iterations for the largest layer: 26 us for 30 MB); here a block = 32 outputs x 8 split groups: every thread sums every 8th
+// partial (coalesced 128-byte rows), the 8 group sums are added in a fixed order.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n,
+                                                            float* __restrict__ out, int accumulate) {
+  __shared__ float sh[8][32];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const size_t i = (size_t)blockIdx.x * 32 + o;
+  float s = 0.f;
+  if (i < n)
+    for (int k = g; k < splits; k += 8) s += partial[(size_t)k * n + i];
+  sh[g][o] = s;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    float t = accumulate ? out[i] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][o];
+    out[i] = t;
+  }
 }
 
 int uad_wgrad_plan(int Mp, int Co, int P, int* splits, int* chunk) {
@@ -319,13 +331,13 @@ int uad_launch_wgrad_simt(WgradParams p, float* out, int accumulate, void* ws, s
   }
   UAD_LAUNCH_CHECK("wgrad_simt");
   size_t n = (size_t)p.Mp * p.Co;
-  splitk_reduce_kernel<<<uad_cdiv(n, 256), 256, 0, st>>>(p.partial, splits, n, out, accumulate);
+  splitk_reduce_kernel<<<uad_cdiv(n, 32), 256, 0, st>>>(p.partial, splits, n, out, accumulate);
   UAD_LAUNCH_CHECK("splitk_reduce");
   return 0;
 }
 
 int uad_launch_splitk_reduce(const float* partial, int splits, size_t n, float* out, int accumulate, cudaStream_t st) {
-  splitk_reduce_kernel<<<uad_cdiv(n, 256), 256, 0, st>>>(partial, splits, n, out, accumulate);
+  splitk_reduce_kernel<<<uad_cdiv(n, 32), 256, 0, st>>>(partial, splits, n, out, accumulate);
   UAD_LAUNCH_CHECK("splitk_reduce");
   return 0;
 }

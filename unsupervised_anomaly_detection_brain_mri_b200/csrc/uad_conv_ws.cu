@@ -95,7 +95,7 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
   const uint32_t misc = smem_base + kStages * STAGE;
   const uint32_t bar_full = misc, bar_lo = misc + 32, bar_empty = misc + 64, bar_acc = misc + 96, tmem_slot = misc + 104;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int blk0 = blockIdx.x * p.bpc;
+  const int blk0 = blockIdx.y * p.bpc;
   const int blk1 = blk0 + p.bpc < p.nblocks ? blk0 + p.bpc : p.nblocks;
 
   if (threadIdx.x == 0) {
@@ -206,7 +206,7 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
       mbar_wait(bar_acc, 0);
       tc_fence_after();
       const int g = warp & 3;                                   // this warp reads TMEM lanes 32 g .. 32 g + 31 (row = channel ci = lane)
-      float* part = p.partial + (size_t)blockIdx.x * p.Mp * CO;
+      float* part = p.partial + (size_t)blockIdx.y * p.Mp * CO;
       static_for<0, NREG>([&](auto RI) {
         constexpr int i = decltype(RI)::value;
         constexpr Region rg = CF::region(TYPE, i);
@@ -246,11 +246,11 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
   }
 }
 
-// grid = (pixel chunks, CTA type x 32-channel block of G)
+// grid = (CTA type x 32-channel block of G, pixel chunks): the CTAs that share a chunk's O tiles are scheduled together (L2 reuse)
 template <class CF>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_ss(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ WsParams p) {
-  const int type = blockIdx.y / p.ncb_g, cgb = blockIdx.y % p.ncb_g;
+  const int type = blockIdx.x / p.ncb_g, cgb = blockIdx.x % p.ncb_g;
   static_for<0, CF::NTYPES>([&](auto T) {
     if (type == decltype(T)::value) wgrad_ss_body<CF, decltype(T)::value>(tmap_g, tmap_o, p, cgb);
   });
@@ -307,7 +307,7 @@ int launch_all_types(const CUtensorMap& tg, const CUtensorMap& to, const WsParam
     attr = true;
   }
   UAD_REQUIRE(smem <= 227 * 1024, "wgrad_ss: shared-memory budget exceeded");
-  dim3 grid(nchunks, CF::NTYPES * p.ncb_g);
+  dim3 grid(CF::NTYPES * p.ncb_g, nchunks);
   wgrad_ss<CF><<<grid, kThreads, smem, st>>>(tg, to, p);
   UAD_LAUNCH_CHECK("wgrad_ss");
   return 0;

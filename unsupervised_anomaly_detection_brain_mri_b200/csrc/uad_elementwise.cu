@@ -78,22 +78,29 @@ __global__ void __launch_bounds__(256) act_bn_bwd_kernel(const float* __restrict
   }
 }
 
-// stage 2: reduce block partials, finalise dgamma / dbeta / dbias.  One warp per channel: lanes stride over the block
-// partials (independent loads in flight), fixed-order shuffle tree -> deterministic.
-__global__ void act_bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ gamma,
-                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-                                        int C, float bn_c, int accumulate, int from_a) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+// stage 2: reduce block partials, finalise dgamma / dbeta / dbias.  One BLOCK per channel: 128 threads stride over the block
+// partials (<= 5 independent loads each instead of 19 dependent iterations of one warp: 19 us -> ~3 us per call), then a fixed-order
+// tree -> deterministic.
+__global__ void __launch_bounds__(128) act_bn_bwd_final_kernel(const float* __restrict__ partial, int nblocks, const float* __restrict__ gamma,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+                                                               int C, float bn_c, int accumulate, int from_a) {
+  __shared__ float sh[2][128];
+  const int c = blockIdx.x, t = threadIdx.x;
   float s_du = 0.f, s_duz = 0.f;
-  for (int b = lane; b < nblocks; b += 32) {
+  for (int b = t; b < nblocks; b += 128) {
     s_du += partial[(size_t)b * 2 * C + c];
     s_duz += partial[(size_t)b * 2 * C + C + c];
   }
-  s_du = uad_warp_sum(s_du);
-  s_duz = uad_warp_sum(s_duz);
-  if (lane != 0) return;
+  sh[0][t] = s_du;
+  sh[1][t] = s_duz;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (t < o) { sh[0][t] += sh[0][t + o]; sh[1][t] += sh[1][t + o]; }
+    __syncthreads();
+  }
+  if (t != 0) return;
+  s_du = sh[0][0];
+  s_duz = sh[1][0];
   const float sc = gamma ? gamma[c] * bn_c : 1.f;
   // from_a: s_duz = sum du*(u - beta) = gamma*bn_c*sum du*z  ->  dgamma = s_duz / gamma
   const float dg = from_a ? (gamma ? s_duz / gamma[c] : 0.f) : bn_c * s_duz;
@@ -131,7 +138,7 @@ extern "C" int uad_act_bn_bwd(const float* da, const float* z, const float* gamm
   else
     act_bn_bwd_kernel<false><<<nb, 256, 0, st>>>(da, z, gamma, beta, dz, (float*)ws, rows, C, act, alpha, bn_c);
   UAD_LAUNCH_CHECK("act_bn_bwd");
-  act_bn_bwd_final_kernel<<<uad_cdiv(C * 32, 256), 256, 0, st>>>((const float*)ws, nb, gamma, dgamma, dbeta, dbias, C, bn_c,
+  act_bn_bwd_final_kernel<<<C, 128, 0, st>>>((const float*)ws, nb, gamma, dgamma, dbeta, dbias, C, bn_c,
                                                             accumulate, from_a);
   UAD_LAUNCH_CHECK("act_bn_bwd_final");
   return 0;

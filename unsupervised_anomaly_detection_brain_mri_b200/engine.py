@@ -554,17 +554,33 @@ class ConvAutoencoderEngine:
                    None, 1.0, ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(br.zr) if training else None,
                    ptr(br.ar), B * r2, self.cb, cin, ACT_RELU, 0.0, BN_C, ws, wsb, st)
             h, s = br.ar, self.res
+            fused_head = False
             for i, co in enumerate(self.dec_ch):
                 pre = f'Decoder/dec_Conv2DT_{i}'
                 bnn = f'Decoder/{_bn(self.n + 1 + i)}'
-                self._op(pre.split('/')[-1], 'uad_convT2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
-                     ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_z[i]) if training and self.keep_preact else None,
-                     ptr(br.dec_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
+                keep_z = training and self.keep_preact
+                # the last block + dec_Conv2D_final (customlayers.py:34-37) as ONE launch where the library offers it: x_hat comes out
+                # of the block's epilogue and the 537 MB re-read of the block output by the 1x1 conv disappears
+                if i == len(self.dec_ch) - 1 and not keep_z and self.C == 1 and \
+                        abi.lib().uad_convT2d_fwd_head_supported(B, s, s, cin, co, KSIZE, mm):
+                    self._op(pre.split('/')[-1], 'uad_convT2d_fwd_head', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
+                         ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_a[i]),
+                         ptr(fp.p('Decoder/dec_Conv2D_final/kernel')), ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.xhat),
+                         B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
+                    fused_head = True
+                else:
+                    self._op(pre.split('/')[-1], 'uad_convT2d_fwd', ptr(h), ptr(fp.p(pre + '/kernel')), ptr(fp.p(pre + '/bias')),
+                         ptr(fp.p(bnn + '/gamma')), ptr(fp.p(bnn + '/beta')), ptr(br.dec_z[i]) if keep_z else None,
+                         ptr(br.dec_a[i]), B, s, s, cin, co, KSIZE, ACT_LEAKY, LRELU_ALPHA, BN_C, mm, ws, wsb, st)
                 h, s, cin = br.dec_a[i], s * 2, co
-            self._op('dec_Conv2D_final', 'uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
-                 ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.x if br.target is None else br.target), ptr(br.xhat),
-                 ptr(br.l1) if need_l1 else None,
-                 ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
+            if fused_head:
+                self._op('dec_Conv2D_final', 'uad_l1_map', ptr(br.x if br.target is None else br.target), ptr(br.xhat),
+                     ptr(br.l1) if need_l1 else None, ptr(br.rec), B, self.S * self.S, st)
+            else:
+                self._op('dec_Conv2D_final', 'uad_final1x1_l1_fwd', ptr(h), ptr(fp.p('Decoder/dec_Conv2D_final/kernel')),
+                     ptr(fp.p('Decoder/dec_Conv2D_final/bias')), ptr(br.x if br.target is None else br.target), ptr(br.xhat),
+                     ptr(br.l1) if need_l1 else None,
+                     ptr(br.rec), B, self.S * self.S, cin, ws, wsb, st)
         # loss scalars (trainers/VAE.py:40-42; ceVAE.py:44-49): out = [mean rec, mean kl, mean(rec+kl)] per branch
         b0 = self.br[0]
         self._op('bneck08', 'uad_loss_scalars', ptr(b0.rec), ptr(b0.kl) if self.arch not in (AE, AES, CAE, AAE, CAAE, GMVAE, GMVAES) else None, ptr(self.scalars), B, st)
