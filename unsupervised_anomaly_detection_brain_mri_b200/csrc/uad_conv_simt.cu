@@ -279,11 +279,20 @@ __global__ void __launch_bounds__(BM* BN / 64) wgrad_simt(const __grid_constant_
   }
 }
 
-// deterministic split-K reduction.  A thread per output walking `splits` partials serially is latency bound (292 dependent
-// iterations for the largest layer: 26 us for 30 MB); here a block = 32 outputs x 8 split groups: every thread sums every 8th
-// partial (coalesced 128-byte rows), the 8 group sums are added in a fixed order.
+// deterministic split-K reduction.  A thread per output walking `splits` partials serially is latency bound when there are many
+// (292 dependent iterations for the largest layer: 26 us for 30 MB): from 32 splits on, a block = 32 outputs x 8 split groups -
+// every thread sums every 8th partial (coalesced 128-byte rows), the 8 group sums are added in a fixed order.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n,
                                                             float* __restrict__ out, int accumulate) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s = accumulate ? out[i] : 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * n + i];
+  out[i] = s;
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce8_kernel(const float* __restrict__ partial, int splits, size_t n,
+                                                             float* __restrict__ out, int accumulate) {
   __shared__ float sh[8][32];
   const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
   const size_t i = (size_t)blockIdx.x * 32 + o;
@@ -298,6 +307,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     for (int k = 0; k < 8; ++k) t += sh[k][o];
     out[i] = t;
   }
+}
+
+static void launch_splitk_reduce(const float* partial, int splits, size_t n, float* out, int accumulate, cudaStream_t st) {
+  if (splits >= 32) splitk_reduce8_kernel<<<uad_cdiv(n, 32), 256, 0, st>>>(partial, splits, n, out, accumulate);
+  else splitk_reduce_kernel<<<uad_cdiv(n, 256), 256, 0, st>>>(partial, splits, n, out, accumulate);
 }
 
 int uad_wgrad_plan(int Mp, int Co, int P, int* splits, int* chunk) {
@@ -331,13 +345,13 @@ int uad_launch_wgrad_simt(WgradParams p, float* out, int accumulate, void* ws, s
   }
   UAD_LAUNCH_CHECK("wgrad_simt");
   size_t n = (size_t)p.Mp * p.Co;
-  splitk_reduce_kernel<<<uad_cdiv(n, 32), 256, 0, st>>>(p.partial, splits, n, out, accumulate);
+  launch_splitk_reduce(p.partial, splits, n, out, accumulate, st);
   UAD_LAUNCH_CHECK("splitk_reduce");
   return 0;
 }
 
 int uad_launch_splitk_reduce(const float* partial, int splits, size_t n, float* out, int accumulate, cudaStream_t st) {
-  splitk_reduce_kernel<<<uad_cdiv(n, 32), 256, 0, st>>>(partial, splits, n, out, accumulate);
+  launch_splitk_reduce(partial, splits, n, out, accumulate, st);
   UAD_LAUNCH_CHECK("splitk_reduce");
   return 0;
 }
@@ -371,7 +385,7 @@ __global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restric
                                                           int act, float alpha, float bn_c) {
   extern __shared__ __align__(16) float smem[];
   const int Ho = H / 2, Wo = W / 2;
-  const int XW = W + K;                      // padded row length
+  const int XW = W + K + 8;                  // padded row length (+8: the 4-pixel strip of the last thread may start at Wo - 1)
   float* ws = smem;                          // [K*K][Cout]
   float* xs = smem + K * K * Cout;           // [K][XW]
   const int b = blockIdx.x / Ho, oh = blockIdx.x % Ho;
@@ -395,36 +409,51 @@ __global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restric
     sc[j] = gamma ? gamma[n] * bn_c : 1.f;
     sf[j] = beta ? beta[n] : 0.f;
   }
-  for (int ow = threadIdx.x / ngrp; ow < Wo; ow += pstep) {
-    float acc[8];
+  // four adjacent output pixels per thread: a tap's eight weights are read from shared memory once per four pixels and a filter row's
+  // eleven inputs once per row (one pixel per thread was shared-memory bound: 36 bytes per 8 FMAs -> 0.13 ms for 0.17 GB of HBM traffic)
+  for (int ow0 = 4 * (threadIdx.x / ngrp); ow0 < Wo; ow0 += 4 * pstep) {
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
 #pragma unroll 1
-    for (int kh = 0; kh < K; ++kh)
+    for (int kh = 0; kh < K; ++kh) {
+      float xr[6 + K];
+#pragma unroll
+      for (int i = 0; i < 6 + K; ++i) xr[i] = xs[kh * XW + 2 * ow0 + i];
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
-        float xv = xs[kh * XW + 2 * ow + kw];
         const float4 w0 = *reinterpret_cast<const float4*>(&ws[(kh * K + kw) * Cout + g * 8]);
         const float4 w1 = *reinterpret_cast<const float4*>(&ws[(kh * K + kw) * Cout + g * 8 + 4]);
-        acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
-        acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
-        acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
-        acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
-      }
-    size_t o = (((size_t)b * Ho + oh) * Wo + ow) * Cout + g * 8;
-    float z[8], a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      z[j] = acc[j] + bia[j];
-      a[j] = uad_act(sc[j] * z[j] + sf[j], act, alpha);
+        for (int q = 0; q < 4; ++q) {
+          const float xv = xr[2 * q + kw];
+          acc[q][0] = fmaf(xv, w0.x, acc[q][0]); acc[q][1] = fmaf(xv, w0.y, acc[q][1]);
+          acc[q][2] = fmaf(xv, w0.z, acc[q][2]); acc[q][3] = fmaf(xv, w0.w, acc[q][3]);
+          acc[q][4] = fmaf(xv, w1.x, acc[q][4]); acc[q][5] = fmaf(xv, w1.y, acc[q][5]);
+          acc[q][6] = fmaf(xv, w1.z, acc[q][6]); acc[q][7] = fmaf(xv, w1.w, acc[q][7]);
+        }
+      }
     }
-    if (z_out) {
-      *reinterpret_cast<float4*>(z_out + o) = make_float4(z[0], z[1], z[2], z[3]);
-      *reinterpret_cast<float4*>(z_out + o + 4) = make_float4(z[4], z[5], z[6], z[7]);
-    }
-    if (a_out) {
-      *reinterpret_cast<float4*>(a_out + o) = make_float4(a[0], a[1], a[2], a[3]);
-      *reinterpret_cast<float4*>(a_out + o + 4) = make_float4(a[4], a[5], a[6], a[7]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (ow0 + q >= Wo) break;
+      size_t o = (((size_t)b * Ho + oh) * Wo + ow0 + q) * Cout + g * 8;
+      float z[8], a[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        z[j] = acc[q][j] + bia[j];
+        a[j] = uad_act(sc[j] * z[j] + sf[j], act, alpha);
+      }
+      if (z_out) {
+        *reinterpret_cast<float4*>(z_out + o) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4*>(z_out + o + 4) = make_float4(z[4], z[5], z[6], z[7]);
+      }
+      if (a_out) {
+        *reinterpret_cast<float4*>(a_out + o) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(a_out + o + 4) = make_float4(a[4], a[5], a[6], a[7]);
+      }
     }
   }
 }
@@ -435,7 +464,7 @@ int uad_launch_conv_c1_fwd(const float* x, const float* w, const float* bias, co
   UAD_REQUIRE(ksize == 5, "conv_c1_fwd: only k=5 (got %d)", ksize);
   UAD_REQUIRE(Cout % 8 == 0 && Cout <= 128 && 128 % (Cout / 8) == 0, "conv_c1_fwd: unsupported Cout=%d", Cout);
   const int pad_lo = (ksize - 2) / 2;
-  size_t smem = ((size_t)ksize * ksize * Cout + (size_t)ksize * (W + ksize)) * sizeof(float);
+  size_t smem = ((size_t)ksize * ksize * Cout + (size_t)ksize * (W + ksize + 8)) * sizeof(float);
   UAD_REQUIRE(smem <= 48 * 1024, "conv_c1_fwd: W=%d too large", W);
   conv_c1_fwd_kernel<5><<<B * (H / 2), 128, smem, st>>>(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cout, pad_lo, act,
                                                          alpha, bn_c);
@@ -450,7 +479,7 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
                                                             int pad_lo) {
   extern __shared__ __align__(16) float smem[];
   const int Ho = H / 2, Wo = W / 2;
-  const int XW = W + K;
+  const int XW = W + K + 16;                  // zero padded: an 8-pixel strip may start at the last pixel of a row
   float* xs = smem;                           // [K][XW]
   float* red = smem + K * XW;                 // [nwarps][K*K*Cout]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -471,24 +500,26 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
       xs[i] = v;
     }
     __syncthreads();
-    for (int ow0 = warp * 4; ow0 < Wo; ow0 += nwarps * 4) {      // 4 pixels per iteration: 4 independent dz loads in flight
-      float dv[4][Q];
+    constexpr int U = 8;                                          // pixels per iteration: 8 independent dz loads in flight, and a
+    for (int ow0 = warp * U; ow0 < Wo; ow0 += nwarps * U) {       // filter row's 2 U + 3 inputs are read ONCE (broadcast) for 5 U FMAs
+      float dv[U][Q];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int q = 0; q < Q; ++q)
           dv[u][q] = (ow0 + u < Wo) ? __ldg(dz + ((size_t)row * Wo + ow0 + u) * Cout + lane + 32 * q) : 0.f;
 #pragma unroll
-      for (int kh = 0; kh < K; ++kh)
+      for (int kh = 0; kh < K; ++kh) {
+        float xr[2 * U + K - 2];
 #pragma unroll
-        for (int kw = 0; kw < K; ++kw) {
+        for (int i = 0; i < 2 * U + K - 2; ++i) xr[i] = xs[kh * XW + 2 * ow0 + i];   // zero padded beyond the row
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float xv = xs[kh * XW + 2 * (ow0 + u) + kw];      // zero padded beyond the row (XW = W + K)
+        for (int kw = 0; kw < K; ++kw)
 #pragma unroll
-            for (int q = 0; q < Q; ++q) acc[kh * K + kw][q] = fmaf(xv, dv[u][q], acc[kh * K + kw][q]);
-          }
-        }
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) acc[kh * K + kw][q] = fmaf(xr[2 * u + kw], dv[u][q], acc[kh * K + kw][q]);
+      }
     }
   }
   __syncthreads();
@@ -519,7 +550,7 @@ int uad_launch_conv_c1_wgrad(const float* x, const float* dz, float* dw, int B, 
   size_t n = (size_t)ksize * ksize * Cout;
   size_t need = (size_t)blocks * n * sizeof(float);
   UAD_REQUIRE(ws && ws_bytes >= need, "conv_c1_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
-  size_t smem = ((size_t)ksize * (W + ksize) + (size_t)(nthreads / 32) * n) * sizeof(float);
+  size_t smem = ((size_t)ksize * (W + ksize + 16) + (size_t)(nthreads / 32) * n) * sizeof(float);
   float* partial = reinterpret_cast<float*>(ws);
   static bool attr_set = false;   // set once, outside any stream capture in practice (first eager warm-up step)
   if (!attr_set) {

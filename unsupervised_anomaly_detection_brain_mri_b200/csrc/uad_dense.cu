@@ -95,23 +95,30 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const __grid_constant__
   }
 }
 
-// split-K second stage: deterministic sum of the partials + the fused epilogue.  Block = 32 outputs x 8 split groups (a thread
-// per output walking up to 128 partials serially is latency bound: 16 us); the 8 group sums are added in a fixed order.
+// split-K second stage: deterministic sum of the partials + the fused epilogue.  G = 8 (from 32 splits on): block = 32 outputs x
+// 8 split groups (a thread per output walking up to 128 partials serially is latency bound: 16 us), the group sums are added in
+// a fixed order; G = 1: one thread per output.
+template <int G>
 __global__ void __launch_bounds__(256) small_gemm_epilogue_kernel(const __grid_constant__ SmallGemm g, int splits) {
-  __shared__ float sh[8][32];
-  const int lo = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  const size_t o = (size_t)blockIdx.x * 32 + lo;
+  __shared__ float sh[G][256 / G];
+  constexpr int OUTS = 256 / G;
+  const int lo = threadIdx.x % OUTS, grp = threadIdx.x / OUTS;
+  const size_t o = (size_t)blockIdx.x * OUTS + lo;
   const size_t MN = (size_t)g.M * g.N;
   float part = 0.f;
   if (o < MN)
-    for (int s = grp; s < splits; s += 8) part += g.partial[(size_t)s * MN + o];
-  sh[grp][lo] = part;
-  __syncthreads();
-  if (grp != 0 || o >= MN) return;
-  const int n = (int)(o % g.N);
-  float z = 0.f;
+    for (int s = grp; s < splits; s += G) part += g.partial[(size_t)s * MN + o];
+  float z = part;
+  if (G > 1) {
+    sh[grp][lo] = part;
+    __syncthreads();
+    if (grp != 0) return;
+    z = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) z += sh[k][lo];
+    for (int k = 0; k < G; ++k) z += sh[k][lo];
+  }
+  if (o >= MN) return;
+  const int n = (int)(o % g.N);
   if (g.accumulate) { g.z_out[o] += z; return; }
   if (g.bias) z += g.bias[n];
   if (g.mask) z *= g.mask[o] * g.mask_scale;
@@ -142,7 +149,8 @@ static int launch_small(SmallGemm g, cudaStream_t st, void* ws, size_t ws_bytes)
     dim3 grid(uad_cdiv(g.M, 64), uad_cdiv(g.N, 64), splits);
     small_gemm_kernel<<<grid, 256, 0, st>>>(g);
     UAD_LAUNCH_CHECK("small_gemm");
-    small_gemm_epilogue_kernel<<<uad_cdiv((size_t)g.M * g.N, 32), 256, 0, st>>>(g, splits);
+    if (splits >= 32) small_gemm_epilogue_kernel<8><<<uad_cdiv((size_t)g.M * g.N, 32), 256, 0, st>>>(g, splits);
+    else small_gemm_epilogue_kernel<1><<<uad_cdiv((size_t)g.M * g.N, 256), 256, 0, st>>>(g, splits);
     UAD_LAUNCH_CHECK("small_gemm_epilogue");
     return 0;
   }
