@@ -47,7 +47,7 @@ extern "C" {
 /* math mode of the conv kernels: 0 = fp32 SIMT FFMA; 1 = tcgen05 3xTF32 (fp32-accurate split); 2 = tcgen05 1xTF32 */
 #define UAD_MATH_FP32_SIMT 0
 #define UAD_MATH_TC_3XTF32 1
-#define UAD_MATH_TC_1XTF32 2
+#define UAD_MATH_TC_1XTF32 2 /* reserved, NOT built: every conv entry point rejects it (no silent alias of the 3xTF32 path) */
 
 const char* uad_last_error(void);
 int uad_abi_version(void);

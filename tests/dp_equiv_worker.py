@@ -44,10 +44,36 @@ def main():
         print(f'DP_EQUIV world={world} grad_rel_err={gerr:.3e} max_weight_diff={werr:.3e} frac_diff={frac:.3e}', flush=True)
         assert gerr < 1e-4 and werr <= 2.001 * lr and frac < 5e-3
     torch.distributed.barrier()
+    graph_part(rank, world, local)
     fanogan_part(rank, world, local)
     scoring_part(rank, world, local)
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
+
+
+def graph_part(rank, world, local):
+    """CUDA-graph replay with the NCCL all-reduce and the Adam update INSIDE the captured step == the same steps with the collective
+    issued outside the graph (UAD_GRAPH_ALLREDUCE=0): bit-identical weights after five steps (device RNG, same seeds)."""
+    arch, S, B, lr = 'variational_autoencoder', 64, 4, 1e-3
+    x = udist.shard(make_volume(S, B * world, seed=9, lesions=False)[0][..., None])
+    res = []
+    for inside in ('1', '0'):
+        os.environ['UAD_GRAPH_ALLREDUCE'] = inside
+        eng = ConvAutoencoderEngine(arch, S, batch=B, device=f'cuda:{local}', seed=3)
+        udist.broadcast_(eng.fp.params)
+        eng.set_inputs(x)
+        for _ in range(5):
+            eng.train_step(lr, dropout_rate=0.2, dropout=True, allreduce=udist.allreduce_sum_, world=world, use_graph=True)
+        torch.cuda.synchronize()
+        assert eng.graph is not None and eng._graph_has_update == (inside == '1')
+        res.append(eng.fp.params.clone())
+    os.environ.pop('UAD_GRAPH_ALLREDUCE')
+    same = bool(torch.equal(res[0], res[1]))
+    t = torch.tensor([int(same)], device=f'cuda:{local}')
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    if rank == 0:
+        print(f'DP_EQUIV_GRAPH world={world} all-reduce inside the graph == outside: {bool(t.item())}', flush=True)
+    assert t.item() == 1
 
 
 def fanogan_part(rank, world, local):

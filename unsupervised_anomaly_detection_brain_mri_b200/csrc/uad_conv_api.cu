@@ -46,7 +46,14 @@ static int check_geom(const char* op, int B, int H, int W, int Cin, int Cout, in
   return 0;
 }
 
-static bool want_tc(int math_mode) { return math_mode == UAD_MATH_TC_3XTF32 || math_mode == UAD_MATH_TC_1XTF32; }
+static bool want_tc(int math_mode) { return math_mode == UAD_MATH_TC_3XTF32; }
+// the modes that exist: exact-fp32 SIMT and fp32-accurate 3xTF32 tensor cores.  UAD_MATH_TC_1XTF32 (and a bf16 mode) are NOT built:
+// asking for them is an error, never a silent alias of another mode.
+static int check_mode(const char* op, int math_mode) {
+  UAD_REQUIRE(math_mode == UAD_MATH_FP32_SIMT || math_mode == UAD_MATH_TC_3XTF32,
+              "%s: math_mode %d is not built (UAD_MATH_FP32_SIMT and UAD_MATH_TC_3XTF32 only)", op, math_mode);
+  return 0;
+}
 
 // Form F / Form T on tensor cores: the halo-resident SS kernel (uad_conv_hs.cu) wherever the M-grid is at least 16 x 8, the
 // converter-warp kernels (uad_conv_tc.cu) for the 8 x 8 grids at the bottleneck.  UAD_HS=0 (developer switch) forces the latter.
@@ -127,6 +134,7 @@ extern "C" int uad_conv2d_fwd(const float* x, const float* w, const float* bias,
                               float* z_out, float* a_out, int B, int H, int W, int Cin, int Cout, int ksize, int act,
                               float alpha, float bn_c, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_conv2d_fwd", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_conv2d_fwd", math_mode)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1)
     return uad_launch_conv_c1_fwd(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cout, ksize, act, alpha, bn_c, st);
@@ -147,6 +155,7 @@ extern "C" int uad_conv2d_fwd(const float* x, const float* w, const float* bias,
 extern "C" int uad_conv2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
                                 int ksize, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_conv2d_dgrad", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_conv2d_dgrad", math_mode)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1) return uad_launch_conv_c1_dgrad(dz, w, dx, B, H, W, Cout, ksize, st);
   GatherParams p;
@@ -171,6 +180,7 @@ extern "C" int uad_conv2d_dgrad(const float* dz, const float* w, float* dx, int 
 extern "C" int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout,
                                 int ksize, int accumulate, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_conv2d_wgrad", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_conv2d_wgrad", math_mode)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   if (Cin == 1) return uad_launch_conv_c1_wgrad(x, dz, dw, B, H, W, Cout, ksize, accumulate, ws, ws_bytes, st);
   WgradParams p;
@@ -191,6 +201,7 @@ extern "C" int uad_convT2d_fwd(const float* x, const float* w, const float* bias
                                float* z_out, float* a_out, int B, int H, int W, int Cin, int Cout, int ksize, int act,
                                float alpha, float bn_c, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_convT2d_fwd", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_convT2d_fwd", math_mode)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   GatherParams p;
   memset(&p, 0, sizeof(p));
@@ -225,6 +236,7 @@ extern "C" int uad_convT2d_fwd_head(const float* x, const float* w, const float*
                                     int Cin, int Cout, int ksize, int act, float alpha, float bn_c, int math_mode, void* ws,
                                     size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_convT2d_fwd_head", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_convT2d_fwd_head", math_mode)) return e;
   UAD_REQUIRE(uad_convT2d_fwd_head_supported(B, H, W, Cin, Cout, ksize, math_mode), "uad_convT2d_fwd_head: unsupported shape / math mode");
   UAD_REQUIRE(a_out && head_w && head_b && head_out, "uad_convT2d_fwd_head: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -244,6 +256,7 @@ extern "C" int uad_convT2d_fwd_head(const float* x, const float* w, const float*
 extern "C" int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
                                  int ksize, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_convT2d_dgrad", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_convT2d_dgrad", math_mode)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   GatherParams p;
   memset(&p, 0, sizeof(p));
@@ -262,6 +275,7 @@ extern "C" int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int
 extern "C" int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int B, int H, int W, int Cin, int Cout,
                                  int ksize, int accumulate, int math_mode, void* ws, size_t ws_bytes, void* stream) {
   if (int e = check_geom("uad_convT2d_wgrad", B, H, W, Cin, Cout, ksize)) return e;
+  if (int e = check_mode("uad_convT2d_wgrad", math_mode)) return e;
   cudaStream_t st = (cudaStream_t)stream;
   WgradParams p;
   memset(&p, 0, sizeof(p));

@@ -236,6 +236,7 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
   const bool no_mma = (p.debug & 2) != 0;
   const int Cblks = p.Cblks;
   Ring hs{0, 0}, ws{0, 0}, ab{0, 0};
+  uint32_t next_ok = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     const int var = NVAR > 1 ? item % NVAR : 0;
     mbar_wait_fast(bars.accempty + 8 * ab.i, ab.ph ^ 1);        // the epilogue has drained this accumulator set
@@ -270,7 +271,7 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
               constexpr int c0 = decltype(CI)::value * CH;
               constexpr int nk = nown - c0 < CH ? nown - c0 : CH;
               constexpr bool chunk_last = decltype(CI)::value == nchunk - 1;
-              mbar_wait_fast(full + 8 * ws.i, ws.ph);
+              if (!next_ok) mbar_wait_slow(full + 8 * ws.i, ws.ph);   // next_ok: the probe issued behind the previous chunk's MMAs
               tc_fence_after();
               const uint64_t b_base = bdesc0 + (uint64_t)(ws.i * SLOT_U);
               if (elect_one()) {
@@ -296,6 +297,8 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
               }
               __syncwarp();
               ws.next(CF::WS);
+              // probe the NEXT chunk's barrier now: the ~90-cycle try_wait round trip overlaps the MMAs just queued
+              next_ok = mbar_try(full + 8 * ws.i, ws.ph);
             });
             if (unit_last) hs.next(CF::HS);
           }

@@ -54,6 +54,7 @@ AAE_CRITIC = CRITIC_WIDTHS[AAE]
 
 import contextlib
 import gc
+import os
 
 
 @contextlib.contextmanager
@@ -1120,16 +1121,32 @@ class ConvAutoencoderEngine:
         key = (lr, beta1, rate, dropout, world, want_anomaly, allreduce is None)
         if use_graph and not parity_noise and self._warm == key:
             if self.graph is None:
-                g = torch.cuda.CUDAGraph()
+                # data parallel: the gradient all-reduce (NCCL is stream-capturable; the communicator exists since the eager
+                # warm-up step) and the Adam update CAN be part of the captured step (UAD_GRAPH_ALLREDUCE=1; bit-identical
+                # results, tests/dp_equiv_worker.py).  Measured on 2 x B200 (profiles/r2_dp_2gpu.md): 4.455 ms per step inside
+                # the graph, 4.425 ms with the collective issued behind the replay (1 GPU: 4.346) - the default stays outside.
+                self._graph_has_update = allreduce is None or os.environ.get('UAD_GRAPH_ALLREDUCE', '0') != '0'
                 t_save = self.t
-                with graph_capture(g):
-                    self._fwd_bwd(rate, dropout, False, want_anomaly)
-                    if allreduce is None:
-                        self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with graph_capture(g):
+                        self._fwd_bwd(rate, dropout, False, want_anomaly)
+                        if self._graph_has_update:
+                            if allreduce is not None:
+                                allreduce(self.fp.grads)
+                            self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+                except Exception:
+                    if allreduce is None or not self._graph_has_update:
+                        raise
+                    torch.cuda.synchronize(self.device)           # a collective that cannot be captured here: capture without it
+                    self._graph_has_update = False
+                    g = torch.cuda.CUDAGraph()
+                    with graph_capture(g):
+                        self._fwd_bwd(rate, dropout, False, want_anomaly)
                 self.t = t_save
                 self.graph = g
             self.graph.replay()
-            if allreduce is not None:
+            if not self._graph_has_update:
                 allreduce(self.fp.grads)
                 self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
             else:
