@@ -26,6 +26,16 @@ import torch  # noqa: E402
 S, B_PER_GPU, ZDIM = 256, 64, 128
 METRIC = 'MRI slices/sec (train step, 256x256 fp32)'
 WORKLOAD = 'VAE (variational_autoencoder.py) 256x256 fp32, batch 64 per GPU, L1+KL, synthetic Brainweb slices'
+# BASELINE.json configs[3] (C4: "VAE 256x256 bf16, batch 256, 8 x B200"): 32 slices per GPU.  bf16 STORAGE is not built; the
+# config is timed with fp32 storage and ONE tf32 tensor-core MMA per K-step (UAD_MATH_TC_1XTF32: 10-bit mantissa operands, fp32
+# accumulation - strictly more precise than bf16's 7 bits, the same single-pass tensor-core arithmetic), and the line says so.
+C4_B_PER_GPU = 32
+C4_METRIC = 'MRI slices/sec (train step, 256x256, single-pass tensor-core math)'
+C4_WORKLOAD = ('VAE (variational_autoencoder.py) 256x256, batch 32 per GPU (256 on 8 GPUs), L1+KL, synthetic Brainweb slices; '
+               'fp32 storage + 1xTF32 MMA / fp32 accumulate in place of bf16 storage (not built)')
+MATH_NOTE = {'simt': 'fp32 FFMA', 'tc3': 'tcgen05 3xTF32 (fp32-accurate) where supported, fp32 FFMA elsewhere',
+             'tc1': 'tcgen05 1xTF32 (operands rounded to nearest tf32, fp32 accumulate; ~1e-3 relative) in conv_halo_ss / wgrad_ss, '
+                    '3xTF32 on the four 8x8-grid launches, fp32 FFMA elsewhere'}
 
 
 def load_peaks():
@@ -145,18 +155,159 @@ def run_reference(args):
     if rank != 0:
         return
     cores = usable_cores()
-    batch = B_PER_GPU   # the stated mini-batch (64 slices per step: ~1 s per step on 16 cores, so K = 20 steps stay within a minute)
+    batch = args.batch   # the stated mini-batch (64 slices per step: ~1 s per step on 16 cores, so K = 20 steps stay within a minute)
     steps = min(args.steps, 20)      # bounded: a 64-slice CPU step takes 1 - 5 s
     rate, ms = cpu_reference_step_rate(batch, steps, max(1, min(args.warmup, 2)), cores)
-    line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': steps,
+    line = {'impl': 'reference', 'metric': args.metric, 'value': rate, 'unit': 'slices/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU, 'parallelism': 'host cores of rank 0 (the CPU arm does not scale with --gpus)',
+            'config': {'workload': args.workload, 'global_batch': batch, 'parallelism': 'host cores of rank 0 (the CPU arm does not scale with --gpus)',
                        'fetch': 'scalar losses only (the reference also fetches the reconstruction and L1 maps every step, trainers/VAE.py:83-96)'},
             'cpu_baseline': {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
                              'sample': f'oracle torch-CPU restatement of the TF graph (TensorFlow 1.15 is not installable here); '
                                        f'{batch}-slice train steps of the same VAE-256 workload'},
             'e2e': {'value': rate, 'unit': 'slices/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+C5_B_PER_GPU = 16
+C5_METRIC = 'MRI slices/sec (f-AnoGAN WGAN-GP train batch = 1 generator + 5 critic steps, 256x256 fp32)'
+C5_WORKLOAD = ('fAnoGAN (fanogan.py) generator + discriminator + encoder 256x256 fp32, batch 16 per GPU (128 on 8 GPUs), WGAN-GP phase of '
+               'trainers/fAnoGAN.py:87-140 (per batch: optim_gen once, optim_dis 5 times, fresh z per sess.run), synthetic Brainweb slices')
+
+
+def run_c5(args):
+    """BASELINE.json configs[4]: the f-AnoGAN train loop body (reference trainers/fAnoGAN.py:96-133) on N GPUs, 16 slices per GPU, one
+    gradient all-reduce per train op on the updated scope's slice; plus the encoder phase (:142-176) and the residual scoring of a
+    full synthetic volume (utils/Evaluation.py:246-292) as extra keys.  A 'step' = one mini-batch of the WGAN phase."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi, dist as udist
+    from unsupervised_anomaly_detection_brain_mri_b200.models.fanogan import fanogan
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers.fAnoGAN import fAnoGAN
+    from unsupervised_anomaly_detection_brain_mri_b200.dataloaders.SYNTHETIC import make_volume
+    from unsupervised_anomaly_detection_brain_mri_b200.utils.default_config_setup import get_config, get_options
+
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    rank, world = udist.init_from_env('nccl')
+    B = args.batch
+    options = get_options(batchsize=B, learningrate=1e-4, numEpochs=1, zDim=ZDIM, outputWidth=S, outputHeight=S)
+
+    class _DS:
+        num_channels = 1
+    config = get_config(trainer=fAnoGAN, options=options, optimizer='ADAM', intermediateResolutions=[16, 16], dropout_rate=0.1, dataset=_DS())
+    config.kappa, config.scale = 1.0, 10.0
+    config.useTensorboard = False
+    config.math_mode = abi.MATH_TC_3XTF32
+    config.device = f'cuda:{local}'
+    config.checkpointDir = '/tmp/uad_bench_ckpt'
+    _stdout = sys.stdout
+    sys.stdout = open(os.devnull, 'w')
+    try:
+        model = fAnoGAN(None, config, network=fanogan)
+        if world > 1:
+            model.enable_data_parallel()
+    finally:
+        sys.stdout = _stdout
+    eng = model.engine
+    eng.kappa, eng.scale = 1.0, 10.0
+    eng.enable_training()
+    lr, rate = 1e-4, float(config.dropout_rate)
+    kw = dict(dropout_rate=rate, dropout=True, allreduce=model._allreduce, world=world, use_graph=True)
+    nb = 4
+    vol = np.concatenate([make_volume(S, B, seed=2000 + 17 * rank + j, lesions=False)[0] for j in range(nb)], 0)
+    host_batches = [torch.from_numpy(vol[j * B:(j + 1) * B, :, :, None].copy()).pin_memory() for j in range(nb)]
+    dev_batches = [h.to(dev) for h in host_batches]
+    zs = torch.from_numpy(np.random.default_rng(5 + rank).standard_normal((64, B, ZDIM)).astype(np.float32)).pin_memory()
+    zs_dev = zs.to(dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def wgan_batch(i, batches, lat):
+        k = 6 * i
+        eng.set_inputs(batches[i % nb]); eng.set_latent(lat[k % 64])
+        run = dict(eng.step_gen(lr, **kw))
+        for j in range(5):
+            eng.set_inputs(batches[i % nb]); eng.set_latent(lat[(k + 1 + j) % 64])      # every sess.run feeds the batch and a fresh z
+            run.update(eng.step_disc(lr, **kw))
+        return run
+
+    def enc_batch(i, batches, lat):
+        eng.set_inputs(batches[i % nb]); eng.set_latent(lat[i % 64])
+        return eng.step_enc(lr, dropout_rate=rate, dropout=True, allreduce=model._allreduce, world=world, train=True, use_graph=True)
+
+    for i in range(args.warmup):
+        wgan_batch(i, dev_batches, zs_dev)
+        enc_batch(i, dev_batches, zs_dev)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = abi.lib().uad_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        run = wgan_batch(i, dev_batches, zs_dev)
+    e1.record()
+    barrier()
+    ms_total = udist.max_over_ranks(e0.elapsed_time(e1), dev)
+    value = world * B * args.steps / (ms_total / 1e3)
+    assert all(math.isfinite(float(v)) for v in run.values()), run
+    # encoder phase, device-resident
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        enc_batch(i, dev_batches, zs_dev)
+    e1.record()
+    barrier()
+    enc_value = world * B * args.steps / (udist.max_over_ranks(e0.elapsed_time(e1), dev) / 1e3)
+    # end to end: pinned host batch + z H2D at every train op, loss scalars and the generated images D2H once per batch (the trainer's loop)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        run = wgan_batch(i, host_batches, zs)
+        gen = eng.x_gen.cpu()
+    barrier()
+    e2e_value = world * B * args.steps / udist.max_over_ranks(time.perf_counter() - t0, dev)
+    clocks = sampler.stop()
+    # residual scoring of one full synthetic volume per rank through the trainer's reconstruct() + the device scorer
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation
+    nsl = 128
+    volx, voly = make_volume(S, nsl, seed=4000 + rank, lesions=True)[:2]
+    config.evalBatchsize = 64
+    model.reconstruct(volx[:64, :, :, None])            # warm-up (builds the evaluation engine)
+    barrier()
+    t0 = time.perf_counter()
+    rec = model.reconstruct(volx[:, :, :, None])['reconstruction']
+    scorer = Evaluation.DeviceScorer(np.abs(volx - rec[..., 0]).astype(np.float32), (voly > 0).astype(np.uint8)) if hasattr(Evaluation, 'DeviceScorer') else None
+    barrier()
+    score_value = world * nsl / udist.max_over_ranks(time.perf_counter() - t0, dev)
+    # kernels per WGAN batch (one eager batch)
+    c0 = abi.lib().uad_launch_count()
+    kw_e = dict(kw, use_graph=False)
+    eng.set_inputs(dev_batches[0]); eng.set_latent(zs_dev[0]); eng.step_gen(lr, **kw_e)
+    for j in range(5):
+        eng.set_inputs(dev_batches[0]); eng.set_latent(zs_dev[1 + j]); eng.step_disc(lr, **kw_e)
+    torch.cuda.synchronize()
+    per_step = abi.lib().uad_launch_count() - c0
+    if rank != 0:
+        return
+    line = {'metric': C5_METRIC, 'value': value, 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': C5_WORKLOAD, 'global_batch': B * world, 'parallelism': f'dp{world}', 'math': MATH_NOTE['tc3'],
+                       'l2': 'per-op working set (16 slices x 256^2 x up to 128 channels, ~0.4 GB) >> 126 MB L2; 4 input batches rotate',
+                       'cuda_graph': True},
+            'e2e': {'value': e2e_value, 'unit': 'slices/s', 'h2d_bytes_per_step': int(6 * (host_batches[0].numel() + B * ZDIM) * 4),
+                    'd2h_bytes_per_step': int(gen.numel() * 4 + 6 * 16)},
+            'encoder_phase': {'value': enc_value, 'unit': 'slices/s', 'note': 'izi_f encoder training (trainers/fAnoGAN.py:142-176), device-resident'},
+            'volume_scoring': {'value': score_value, 'unit': 'slices/s',
+                               'note': f'{nsl}-slice 256^2 synthetic volume per rank: host volume -> encode + generate -> residual |x - G(E(x))| on host -> device scorer upload'},
+            'gpu_launches': int(per_step * args.steps), 'gpu_launches_per_step': int(per_step), 'clocks': clocks,
+            'roofline': None, 'cpu_baseline': None}
     print(json.dumps(line), flush=True)
 
 
@@ -166,17 +317,26 @@ def main():
     ap.add_argument('--steps', type=int, default=400, help='timed steps (default long enough for ~20 loaded clock samples)')
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--math', default='tc3', choices=['simt', 'tc3'])
-    ap.add_argument('--config', default='c2', choices=['c2', 'c4', 'c5'], help='BASELINE.json configs[1] (the only one this bench times)')
+    ap.add_argument('--math', default=None, choices=['simt', 'tc3', 'tc1'], help='default: tc3 (c2), tc1 (c4)')
+    ap.add_argument('--config', default='c2', choices=['c2', 'c4', 'c5'],
+                    help='c2 = BASELINE.json configs[1] (the headline); c4 = configs[3] at 32 slices per GPU with 1xTF32 math; c5 = configs[4] (f-AnoGAN WGAN-GP batch, 16 slices per GPU)')
+    ap.add_argument('--batch', type=int, default=None, help='slices per GPU (default: 64 for c2, 32 for c4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--layer-table', default=None, help='write the per-kernel timing table (json) here')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.config != 'c2':
-        # c4 (bf16 storage / kind::f16 MMA) is not built - every tensor-core kernel here is fp32-accurate 3xTF32; c5 (f-AnoGAN) is
-        # measured by tools/fanogan_time.py, not by this line.  Say so instead of timing something else under their name.
-        print(json.dumps({'impl': args.impl, 'config': args.config, 'unavailable': 'only BASELINE.json configs[1] (VAE 256x256 fp32, batch 64 per GPU) is timed by bench.py; bf16 (c4) is not built'}), flush=True)
-        return
+    if args.config == 'c5':
+        if args.impl == 'reference':
+            print(json.dumps({'impl': 'reference', 'config': 'c5', 'unavailable': 'the CPU arm times the VAE configs (c2 / c4) only'}), flush=True)
+            return
+        args.batch = args.batch or C5_B_PER_GPU
+        return run_c5(args)
+    c4 = args.config == 'c4'
+    args.math = args.math or ('tc1' if c4 else 'tc3')
+    args.batch = args.batch or (C4_B_PER_GPU if c4 else B_PER_GPU)
+    args.metric, args.workload = (C4_METRIC, C4_WORKLOAD) if c4 else (METRIC, WORKLOAD)
+    if args.batch != (C4_B_PER_GPU if c4 else B_PER_GPU):
+        args.workload += f' [--batch {args.batch} per GPU]'
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -192,8 +352,8 @@ def main():
     dev = torch.device('cuda', local)
     rank, world = udist.init_from_env('nccl')
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
-    B = B_PER_GPU
-    math_mode = {'simt': abi.MATH_FP32_SIMT, 'tc3': abi.MATH_TC_3XTF32}[args.math]
+    B = args.batch
+    math_mode = {'simt': abi.MATH_FP32_SIMT, 'tc3': abi.MATH_TC_3XTF32, 'tc1': abi.MATH_TC_1XTF32}[args.math]
 
     # ---- the public API a user of the reference calls: options -> config -> Trainer(sess, config, network)
     options = get_options(batchsize=B, learningrate=1e-4, numEpochs=1, zDim=ZDIM, outputWidth=S, outputHeight=S)
@@ -289,7 +449,8 @@ def main():
             o = O.forward(O.VAE, Pnow, host_batches[0][j:j + 16], eps=eps[j:j + 16], masks={k: v[j:j + 16] for k, v in om.items()},
                           dropout_rate=config.dropout_rate, training=True, dtype=torch.float32)
             ref += float(O.losses(O.VAE, o, host_batches[0][j:j + 16])['loss']) * 16 / B
-        loss_check = {'engine': got, 'oracle_fp32': ref, 'rel_err': abs(got - ref) / abs(ref), 'ok': abs(got - ref) / abs(ref) < 1e-4}
+        tol = 5e-3 if args.math == 'tc1' else 1e-4
+        loss_check = {'engine': got, 'oracle_fp32': ref, 'rel_err': abs(got - ref) / abs(ref), 'tol': tol, 'ok': abs(got - ref) / abs(ref) < tol}
 
     # ---- kernels per step (graph replays launch the captured kernels; count one eager step)
     eng.graph, eng._warm = None, None
@@ -349,11 +510,11 @@ def main():
         rate, ms = cpu_reference_step_rate(16, 3, 1, cores)
         cpu = {'value': rate, 'unit': 'slices/s', 'cores': cores, 'kind': 'port',
                'sample': 'oracle torch-CPU restatement (TF 1.15 not installable); 3 timed 16-slice train steps of the same VAE-256 workload'}
-    line = {'metric': METRIC, 'value': value, 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': B * world, 'parallelism': f'dp{world}',
-                       'math': {'simt': 'fp32 FFMA', 'tc3': 'tcgen05 3xTF32 (fp32-accurate) where supported, fp32 FFMA elsewhere'}[args.math],
+    line = {'metric': args.metric, 'value': value, 'unit': 'slices/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'tf32' if args.math == 'tc1' else 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'global_batch': B * world, 'parallelism': f'dp{world}',
+                       'math': MATH_NOTE[args.math],
                        'l2': 'per-step working set (~2 GB of activations) >> 126 MB L2; 4 distinct input batches rotate',
                        'cuda_graph': True},
             'step_tflops': step_flops(B) * world / (ms_step / 1e3) / 1e12,

@@ -47,7 +47,9 @@ extern "C" {
 /* math mode of the conv kernels: 0 = fp32 SIMT FFMA; 1 = tcgen05 3xTF32 (fp32-accurate split); 2 = tcgen05 1xTF32 */
 #define UAD_MATH_FP32_SIMT 0
 #define UAD_MATH_TC_3XTF32 1
-#define UAD_MATH_TC_1XTF32 2 /* reserved, NOT built: every conv entry point rejects it (no silent alias of the 3xTF32 path) */
+#define UAD_MATH_TC_1XTF32 2 /* ONE tf32 MMA per K-step on operands rounded to nearest tf32, fp32 storage / accumulation: ~1e-3 relative, the
+                                 single-pass tensor-core arithmetic of config C4 - not the 1e-4 parity mode.  Shapes only the first-generation
+                                 kernels cover run 3xTF32 in this mode too.  Any other value is rejected (bf16 storage is not built). */
 
 const char* uad_last_error(void);
 int uad_abi_version(void);

@@ -81,10 +81,11 @@ def test_workspace_query_is_independent_of_the_developer_switches():
 
 
 def test_unbuilt_math_modes_are_rejected_not_aliased():
-    """UAD_MATH_TC_1XTF32 (and any other value) is an error at every conv entry point - host-side check, no GPU needed."""
+    """A math mode that is not built (bf16 storage = 3, or any other value) is an error at every conv entry point - host-side
+    check, no GPU needed.  The three built modes are 0 (fp32 SIMT), 1 (3xTF32), 2 (1xTF32)."""
     from unsupervised_anomaly_detection_brain_mri_b200 import abi
     L = abi.lib()
-    rc = L.uad_conv2d_fwd(None, None, None, None, None, None, None, 1, 16, 16, 32, 32, 5, 0, 0.0, 1.0, abi.MATH_TC_1XTF32, None, 0, None)
-    assert rc != 0 and b'math_mode 2 is not built' in L.uad_last_error()
+    rc = L.uad_conv2d_fwd(None, None, None, None, None, None, None, 1, 16, 16, 32, 32, 5, 0, 0.0, 1.0, 3, None, 0, None)
+    assert rc != 0 and b'math_mode 3 is not built' in L.uad_last_error()
     rc = L.uad_convT2d_wgrad(None, None, None, 1, 16, 16, 32, 32, 5, 0, 7, None, 0, None)
     assert rc != 0 and b'math_mode 7 is not built' in L.uad_last_error()

@@ -14,7 +14,14 @@ from oracle import naive64, scoring as oscore  # noqa: E402
 from oracle import tf_graph_cpu as O  # noqa: E402
 
 TOL = 1e-4
+# UAD_MATH_TC_1XTF32 (mode 2): operands rounded to nearest tf32 (2^-11 relative each), fp32 accumulation - the single-pass
+# tensor-core arithmetic of config C4.  Stated bar 2e-3 of the tensor's max-norm (measured ~3e-4); NOT the 1e-4 parity mode.
+TOL_TC1 = 2e-3
 MODES = [0]
+
+
+def tol_of(mode):
+    return TOL_TC1 if mode == 2 else TOL
 
 
 def _modes():
@@ -41,7 +48,7 @@ CONV_SHAPES = [  # B, H, Cin, Cout
 ]
 
 
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode', [0, 1, 2])
 @pytest.mark.parametrize('B,H,Cin,Cout', CONV_SHAPES)
 def test_conv2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
     from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
@@ -65,8 +72,8 @@ def test_conv2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
     call('uad_conv2d_fwd', ptr(dx_), ptr(dw_), ptr(db_), ptr(dg_), ptr(dbe_), ptr(z), ptr(a), B, H, H, Cin, Cout, 5,
          abi.ACT_LEAKY, 0.3, bn_c, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(z.cpu().numpy(), z_ref) < TOL
-    assert relerr(a.cpu().numpy(), a_ref) < TOL
+    assert relerr(z.cpu().numpy(), z_ref) < tol_of(mode)
+    assert relerr(a.cpu().numpy(), a_ref) < tol_of(mode)
     # dgrad / wgrad against autograd of the float64 oracle
     dz = rng.standard_normal(z_ref.shape).astype(np.float32)
     xt, wt = t64(x).requires_grad_(True), t64(w).requires_grad_(True)
@@ -76,15 +83,15 @@ def test_conv2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
     gxd = empty(B, H, H, Cin)
     call('uad_conv2d_dgrad', ptr(ddz), ptr(dw_), ptr(gxd), B, H, H, Cin, Cout, 5, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
+    assert relerr(gxd.cpu().numpy(), gx.numpy()) < tol_of(mode)
     gwd = empty(5, 5, Cin, Cout)
     call('uad_conv2d_wgrad', ptr(dx_), ptr(ddz), ptr(gwd), B, H, H, Cin, Cout, 5, 0, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(gwd.cpu().numpy(), gw.numpy()) < TOL
+    assert relerr(gwd.cpu().numpy(), gw.numpy()) < tol_of(mode)
     # accumulate
     call('uad_conv2d_wgrad', ptr(dx_), ptr(ddz), ptr(gwd), B, H, H, Cin, Cout, 5, 1, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(gwd.cpu().numpy(), 2 * gw.numpy()) < TOL
+    assert relerr(gwd.cpu().numpy(), 2 * gw.numpy()) < tol_of(mode)
 
 
 CONVT_SHAPES = [  # B, H(in), Cin, Cout
@@ -93,7 +100,7 @@ CONVT_SHAPES = [  # B, H(in), Cin, Cout
 ]
 
 
-@pytest.mark.parametrize('mode', [0, 1])
+@pytest.mark.parametrize('mode', [0, 1, 2])
 @pytest.mark.parametrize('B,H,Cin,Cout', CONVT_SHAPES)
 def test_convT2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
     from gpu_util import call, dev, dptr, empty, ptr, relerr, st, sync, workspace
@@ -116,8 +123,8 @@ def test_convT2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
     call('uad_convT2d_fwd', ptr(dx_), ptr(dK_), ptr(db_), ptr(dg_), ptr(dbe_), ptr(z), ptr(a), B, H, H, Cin, Cout, 5,
          abi.ACT_LEAKY, 0.3, bn_c, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(z.cpu().numpy(), z_ref) < TOL
-    assert relerr(a.cpu().numpy(), a_ref) < TOL
+    assert relerr(z.cpu().numpy(), z_ref) < tol_of(mode)
+    assert relerr(a.cpu().numpy(), a_ref) < tol_of(mode)
     dz = rng.standard_normal(z_ref.shape).astype(np.float32)
     xt, Kt = t64(x).requires_grad_(True), t64(K).requires_grad_(True)
     y = O.conv2dT_same_s2(xt.permute(0, 3, 1, 2), Kt, t64(b)).permute(0, 2, 3, 1)
@@ -126,11 +133,11 @@ def test_convT2d_fwd_dgrad_wgrad(B, H, Cin, Cout, mode):
     gxd = empty(B, H, H, Cin)
     call('uad_convT2d_dgrad', ptr(ddz), ptr(dK_), ptr(gxd), B, H, H, Cin, Cout, 5, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(gxd.cpu().numpy(), gx.numpy()) < TOL
+    assert relerr(gxd.cpu().numpy(), gx.numpy()) < tol_of(mode)
     gKd = empty(5, 5, Cout, Cin)
     call('uad_convT2d_wgrad', ptr(dx_), ptr(ddz), ptr(gKd), B, H, H, Cin, Cout, 5, 0, mode, ptr(ws), wsb, st())
     sync()
-    assert relerr(gKd.cpu().numpy(), gK.numpy()) < TOL
+    assert relerr(gKd.cpu().numpy(), gK.numpy()) < tol_of(mode)
 
 
 @pytest.mark.parametrize('B,H,Cout', [(2, 32, 32), (3, 128, 32), (1, 256, 32), (2, 16, 64)])

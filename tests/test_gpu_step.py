@@ -113,6 +113,35 @@ def test_train_step_parity(arch, S, B, mode, keep_preact):
     assert bad / tot < 5e-3, (bad, tot)     # sign flips only where |g| is at rounding level
 
 
+@pytest.mark.parametrize('arch,S,B', [(O.VAE, 64, 4), (O.VAE, 256, 2)])
+def test_train_step_1xtf32_mode(arch, S, B):
+    """UAD_MATH_TC_1XTF32 (config C4's single-pass tensor-core arithmetic: operands rounded to nearest tf32 = 2^-11 relative,
+    fp32 storage / accumulation).  NOT the 1e-4 parity mode - stated bars: losses and x_hat 3e-3, every gradient 3e-2 of its
+    max-norm against the float64 oracle (measured values are printed)."""
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine
+    rate, lr = 0.2, 1e-3
+    P = O.perturb_params(O.init_params(arch, S, seed=1))
+    x = O.synthetic_slices(B, S, seed=1234)
+    eng = ConvAutoencoderEngine(arch, S, batch=B, math_mode=abi.MATH_TC_1XTF32)
+    eng.fp.load(P)
+    eps, om, em, emc = _noise(arch, B, 128, eng.flat, rate)
+    eng.set_inputs(x)
+    eng.set_noise(eps, em, emc)
+    eng.train_step(lr, beta1=0.5, dropout_rate=rate, dropout=True, parity_noise=True)
+    torch.cuda.synchronize()
+    sgn = np.sign(eng.br[0].xhat.cpu().numpy().astype(np.float64) - x)
+    out, L, G = O.loss_and_grads(arch, P, x, eps=eps, masks=om, dropout_rate=rate, training=True, dtype=torch.float64, l1_sign=sgn)
+    got = eng.losses()
+    e_loss = abs(got['loss'] - float(L['loss'])) / abs(float(L['loss']))
+    e_x = _relerr(eng.br[0].xhat.cpu().numpy(), out['x_hat'].numpy())
+    grads = eng.fp.to_numpy(eng.fp.grads)
+    worst = max((_relerr(grads[k], G[k].numpy()), k) for k in G)
+    print(f'1xTF32 {arch} {S}x{S} B={B}: loss rel-err {e_loss:.2e}, x_hat {e_x:.2e}, worst gradient {worst[0]:.2e} ({worst[1]})')
+    assert e_loss < 3e-3 and e_x < 3e-3
+    assert worst[0] < 3e-2, worst
+
+
 @pytest.mark.parametrize('arch', [O.AE, O.VAE])
 def test_inference_forward_matches_training_forward(arch):
     from unsupervised_anomaly_detection_brain_mri_b200.engine import ConvAutoencoderEngine

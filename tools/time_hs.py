@@ -20,6 +20,7 @@ def timeit(fn, reps=REPS):
     return e0.elapsed_time(e1) / reps
 
 B = int(os.environ.get('B', 64))
+MATH = int(os.environ.get('MATH', 1))   # 1 = 3xTF32, 2 = 1xTF32
 cases = {
   'T4.fwd   FormT N=32  C=32  128^2->256^2': ('convT_fwd', 128, 32, 32),
   'T4.dgrad FormF N=32  C=32  256^2->128^2': ('convT_dgrad', 128, 32, 32),
@@ -46,10 +47,10 @@ for name, (op, H, Cin, Cout) in cases.items():
         x = torch.randn(B, H, H, Cin, device=DEV); y = torch.randn(B, H // 2, H // 2, Cout, device=DEV); w = torch.randn(5, 5, Cin, Cout, device=DEV) * 0.05
     dx = torch.empty_like(x)
     def run():
-        if op == 'conv_fwd': call('uad_conv2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, None, y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
-        elif op == 'conv_dgrad': call('uad_conv2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, 1, ws.data_ptr(), wsb, st())
-        elif op == 'convT_fwd': call('uad_convT2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, None, y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, 1, ws.data_ptr(), wsb, st())
-        elif op == 'convT_dgrad': call('uad_convT2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, 1, ws.data_ptr(), wsb, st())
+        if op == 'conv_fwd': call('uad_conv2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, None, y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, MATH, ws.data_ptr(), wsb, st())
+        elif op == 'conv_dgrad': call('uad_conv2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, MATH, ws.data_ptr(), wsb, st())
+        elif op == 'convT_fwd': call('uad_convT2d_fwd', x.data_ptr(), w.data_ptr(), None, None, None, None, y.data_ptr(), B, H, H, Cin, Cout, 5, 1, 0.3, 1.0, MATH, ws.data_ptr(), wsb, st())
+        elif op == 'convT_dgrad': call('uad_convT2d_dgrad', y.data_ptr(), w.data_ptr(), dx.data_ptr(), B, H, H, Cin, Cout, 5, MATH, ws.data_ptr(), wsb, st())
     res = []
     for dbg in modes:
         os.environ['UAD_HS_DEBUG'] = str(dbg)

@@ -72,12 +72,12 @@ int uad_launch_gather_tc(const GatherParams& p, int nclasses, int ksize, bool we
 // ---- halo-resident SS-form tcgen05 launcher (uad_conv_hs.cu; round 2): M-grids of at least 16 x 8
 int uad_hs_gather_supported(int Cin, int N, int lgMH, int lgMW, int nclasses);
 size_t uad_hs_gather_ws_bytes(int ksize, int Cin, int N);
-int uad_launch_gather_hs(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
+int uad_launch_gather_hs(const GatherParams& p, int nclasses, int ksize, bool weights_transposed, const float* w_raw, bool fast,
                          void* ws, size_t ws_bytes, cudaStream_t st);
 // ---- MN-major SS-form Form-W kernel (uad_conv_ws.cu; round 2)
 int uad_ws_wgrad_supported(int Cg, int Co, int lgMH, int lgMW);
 size_t uad_ws_wgrad_ws_bytes(int Cg, int Co, int B, int MH, int MW);
-int uad_launch_wgrad_ss(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);
+int uad_launch_wgrad_ss(const WgradParams& w, float* out, int accumulate, bool fast, void* ws, size_t ws_bytes, cudaStream_t st);
 int uad_tc_wgrad_supported(int Cg, int Co, int lgMH, int lgMW);
 size_t uad_tc_wgrad_ws_bytes(int Cg, int Co, int P);
 int uad_launch_wgrad_tc(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -46,12 +46,14 @@ static int check_geom(const char* op, int B, int H, int W, int Cin, int Cout, in
   return 0;
 }
 
-static bool want_tc(int math_mode) { return math_mode == UAD_MATH_TC_3XTF32; }
-// the modes that exist: exact-fp32 SIMT and fp32-accurate 3xTF32 tensor cores.  UAD_MATH_TC_1XTF32 (and a bf16 mode) are NOT built:
-// asking for them is an error, never a silent alias of another mode.
+static bool want_tc(int math_mode) { return math_mode == UAD_MATH_TC_3XTF32 || math_mode == UAD_MATH_TC_1XTF32; }
+// the modes that exist: exact-fp32 SIMT, fp32-accurate 3xTF32 tensor cores, and UAD_MATH_TC_1XTF32 - one tf32 MMA per K-step on
+// operands rounded to nearest tf32 (fp32 storage, fp32 accumulation: the arithmetic class of a bf16 / TF32 training step, ~1e-3
+// relative, NOT the 1e-4 parity mode).  The 1x form exists in conv_halo_ss / wgrad_ss; a shape only the first-generation kernels
+// cover runs 3xTF32 in that mode too (MORE accurate than asked for, never less).  Any other value is an error, never an alias.
 static int check_mode(const char* op, int math_mode) {
-  UAD_REQUIRE(math_mode == UAD_MATH_FP32_SIMT || math_mode == UAD_MATH_TC_3XTF32,
-              "%s: math_mode %d is not built (UAD_MATH_FP32_SIMT and UAD_MATH_TC_3XTF32 only)", op, math_mode);
+  UAD_REQUIRE(math_mode == UAD_MATH_FP32_SIMT || math_mode == UAD_MATH_TC_3XTF32 || math_mode == UAD_MATH_TC_1XTF32,
+              "%s: math_mode %d is not built (UAD_MATH_FP32_SIMT, UAD_MATH_TC_3XTF32, UAD_MATH_TC_1XTF32 only)", op, math_mode);
   return 0;
 }
 
@@ -62,16 +64,16 @@ static int launch_gather_tensor(const GatherParams& p, int nclasses, int ksize, 
   static int use_hs = -1;
   if (use_hs < 0) { const char* e = getenv("UAD_HS"); use_hs = e ? atoi(e) : 1; }
   if (use_hs && ksize == 5 && uad_hs_gather_supported(p.Cin, p.N, p.lgMH, p.lgMW, nclasses))
-    return uad_launch_gather_hs(p, nclasses, ksize, weights_transposed, w_raw, ws, ws_bytes, st);
-  return uad_launch_gather_tc(p, nclasses, ksize, weights_transposed, w_raw, math_mode, ws, ws_bytes, st);
+    return uad_launch_gather_hs(p, nclasses, ksize, weights_transposed, w_raw, math_mode == UAD_MATH_TC_1XTF32, ws, ws_bytes, st);
+  return uad_launch_gather_tc(p, nclasses, ksize, weights_transposed, w_raw, UAD_MATH_TC_3XTF32, ws, ws_bytes, st);
 }
 
 // Form W on tensor cores: the MN-major SS kernel (uad_conv_ws.cu) where the M-grid is wide enough for its pixel blocks, the
 // converter-warp kernel (uad_conv_tc.cu) otherwise.  UAD_WGRAD_SS=0 (developer switch) forces the latter.
-static int launch_wgrad_tensor(const WgradParams& p, float* dw, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int launch_wgrad_tensor(const WgradParams& p, float* dw, int accumulate, int math_mode, void* ws, size_t ws_bytes, cudaStream_t st) {
   static int use_ss = -1;
   if (use_ss < 0) { const char* e = getenv("UAD_WGRAD_SS"); use_ss = e ? atoi(e) : 1; }
-  if (use_ss && uad_ws_wgrad_supported(p.Cg, p.Co, p.lgMH, p.lgMW)) return uad_launch_wgrad_ss(p, dw, accumulate, ws, ws_bytes, st);
+  if (use_ss && uad_ws_wgrad_supported(p.Cg, p.Co, p.lgMH, p.lgMW)) return uad_launch_wgrad_ss(p, dw, accumulate, math_mode == UAD_MATH_TC_1XTF32, ws, ws_bytes, st);
   return uad_launch_wgrad_tc(p, dw, accumulate, ws, ws_bytes, st);
 }
 
@@ -192,7 +194,7 @@ extern "C" int uad_conv2d_wgrad(const float* x, const float* dz, float* dw, int 
   p.P = B << (p.lgMH + p.lgMW);
   taps_full(&p.taps, ksize);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONV_WGRAD, B, H, W, Cin, Cout, ksize))
-    return launch_wgrad_tensor(p, dw, accumulate, ws, ws_bytes, st);
+    return launch_wgrad_tensor(p, dw, accumulate, math_mode, ws, ws_bytes, st);
   return uad_launch_wgrad_simt(p, dw, accumulate, ws, ws_bytes, st);
 }
 
@@ -227,7 +229,7 @@ extern "C" int uad_convT2d_fwd(const float* x, const float* w, const float* bias
 extern "C" int uad_convT2d_fwd_head_supported(int B, int H, int W, int Cin, int Cout, int ksize, int math_mode) {
   static int use_hs = -1;
   if (use_hs < 0) { const char* e = getenv("UAD_HS"); use_hs = e ? atoi(e) : 1; }
-  return use_hs && math_mode == UAD_MATH_TC_3XTF32 && ksize == 5 && Cout == 32 && uad_is_pow2(H) && uad_is_pow2(W) && B > 0 &&
+  return use_hs && want_tc(math_mode) && ksize == 5 && Cout == 32 && uad_is_pow2(H) && uad_is_pow2(W) && B > 0 &&
          uad_hs_gather_supported(Cin, Cout, uad_ilog2(H), uad_ilog2(W), 4);
 }
 
@@ -250,7 +252,7 @@ extern "C" int uad_convT2d_fwd_head(const float* x, const float* w, const float*
   p.act = act; p.alpha = alpha; p.bn_c = bn_c;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out;
   for (int c = 0; c < 4; ++c) taps_parity(&p.taps[c], ksize, c >> 1, c & 1);
-  return uad_launch_gather_hs(p, 4, ksize, true, w, ws, ws_bytes, st);
+  return uad_launch_gather_hs(p, 4, ksize, true, w, math_mode == UAD_MATH_TC_1XTF32, ws, ws_bytes, st);
 }
 
 extern "C" int uad_convT2d_dgrad(const float* dz, const float* w, float* dx, int B, int H, int W, int Cin, int Cout,
@@ -286,6 +288,6 @@ extern "C" int uad_convT2d_wgrad(const float* x, const float* dz, float* dw, int
   p.P = B << (p.lgMH + p.lgMW);
   taps_full(&p.taps, ksize);
   if (want_tc(math_mode) && uad_conv_tc_supported(UAD_OP_CONVT_WGRAD, B, H, W, Cin, Cout, ksize))
-    return launch_wgrad_tensor(p, dw, accumulate, ws, ws_bytes, st);
+    return launch_wgrad_tensor(p, dw, accumulate, math_mode, ws, ws_bytes, st);
   return uad_launch_wgrad_simt(p, dw, accumulate, ws, ws_bytes, st);
 }

@@ -85,20 +85,28 @@ __host__ __device__ constexpr KbGeom kb_geom(int g, int i) {
   return KbGeom{(ih * kHW + iw) * 8, (p + 3 - 2 * ih) * 5 + (q + 3 - 2 * iw)};
 }
 
-template <int FORM_, int N_, int CG_, int G_>
+template <int FORM_, int N_, int CG_, int G_, bool FAST_ = false>
 struct Cfg {
   static constexpr int FORM = FORM_, N = N_, CG = CG_, G = G_;
+  // FAST = UAD_MATH_TC_1XTF32: ONE tf32 MMA per K-step (operands rounded to nearest tf32, fp32 accumulation), no lo images, no
+  // correction accumulators - the arithmetic of a bf16 / tf32 training step, NOT the fp32-accurate default.  There is no lo pass at
+  // all: the tensor core truncates whatever fp32 word it is given (E1), and every conv epilogue of this mode stores its output
+  // ALREADY rounded to nearest tf32, so tensors that come from a conv block are exact operands; the others (gradients written by
+  // the elementwise kernels, the first layer's output) are truncated.  The lo tile's space becomes extra halo stages.
+  static constexpr bool FAST = FAST_;
   static constexpr bool COLSPLIT = N == 128;
   static constexpr int NI = COLSPLIT ? 64 : N;               // output columns per issuer MMA
+  static constexpr int PW = FAST ? NI : 2 * NI;              // accumulator columns of one [main | corr] pair (main only when FAST)
   static constexpr int NVAR = FORM == 0 ? 1 : 4 / CG;        // item = tile * NVAR + variant (class group)
   static constexpr int NGRP = FORM == 0 ? 4 : CG;            // k-block groups per (item, channel block)
   static constexpr int NUNITS = FORM == 0 ? 4 : 1;           // halo loads per (item, channel block)
-  static constexpr uint32_t WI_BYTES = 2u * NI * 128u;       // one k-block's {hi, lo} weight image of ONE issuer
-  static constexpr int CH = kSlot / WI_BYTES;                // k-blocks per weight chunk (2 at NI = 32, else 1)
+  static constexpr uint32_t WI_BYTES = (FAST ? 1u : 2u) * NI * 128u;   // one k-block's {hi, lo} (FAST: hi) weight image of ONE issuer
+  static constexpr int CH = kSlot / WI_BYTES;                // k-blocks per weight chunk (2 at NI = 32, else 1; twice that when FAST)
   // the strided form turns a halo over every 4 .. 9 k-blocks and a refill (TMA + lo pass) takes ~2500 cycles: three stages there,
   // paid for with one weight slot; the stride-1 form keeps a halo for a whole (item, channel block)
-  static constexpr int HS = FORM == 0 ? 3 : 2, WS = FORM == 0 ? 2 : 3;   // halo stages, weight slots per issuer
-  static constexpr int ACC_COLS = FORM == 0 ? (COLSPLIT ? 2 * G * 128 : 4 * NI) : (COLSPLIT ? 256 : CG * 2 * NI);
+  static constexpr int HS = (FORM == 0 ? 3 : 2) * (FAST ? 2 : 1), WS = FORM == 0 ? 2 : 3;   // halo stages, weight slots per issuer
+  static constexpr uint32_t HSTAGE = FAST ? kHaloSlot : kHaloStage;      // bytes per halo stage (raw [+ lo])
+  static constexpr int ACC_COLS = FORM == 0 ? (COLSPLIT ? 2 * G * PW : 2 * PW) : (COLSPLIT ? 2 * PW : CG * PW);
   static constexpr int ACC_BUFS = 2 * ACC_COLS <= 512 ? 2 : 1;
   // the stride-1 form writes up to four classes per item: a second epilogue warpgroup (one per accumulator set, alternate items)
   static constexpr int EPI_WG = (FORM == 1 && ACC_BUFS == 2) ? 2 : 1;
@@ -190,7 +198,7 @@ __device__ __forceinline__ void weight_producer(const HsParams& p, const Bars& b
   constexpr int NVAR = CF::NVAR, NGRP = CF::NGRP, CH = CF::CH, FORM = CF::FORM, CG = CF::CG;
   constexpr uint32_t WI = CF::WI_BYTES;
   const uint32_t full = bars.wfull + W * 32, empty = bars.wempty + W * 32, ring = w_base + W * CF::WS * kSlot;
-  const size_t cb_floats = (size_t)kTaps * 2 * CF::N * 32;
+  const size_t cb_floats = (size_t)kTaps * (CF::FAST ? 1 : 2) * CF::N * 32;
   const float* img0 = p.wimg + (W ? (size_t)CF::cnt(0) * (WI / 4) : 0);
   Ring ws{0, 0};
   const bool no_load = (p.debug & 8) != 0;
@@ -225,11 +233,11 @@ __device__ __forceinline__ void weight_producer(const HsParams& p, const Bars& b
 // ===================================================================== MMA issuer W (whole warp converged, one elected lane issues)
 template <class CF, int W>
 __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, uint32_t smem_base, uint32_t w_base, uint32_t tmem_base) {
-  constexpr int NVAR = CF::NVAR, NGRP = CF::NGRP, CH = CF::CH, FORM = CF::FORM, CG = CF::CG, NI = CF::NI, G = CF::G;
+  constexpr int NVAR = CF::NVAR, NGRP = CF::NGRP, CH = CF::CH, FORM = CF::FORM, CG = CF::CG, NI = CF::NI, G = CF::G, PW = CF::PW;
   constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t idescN = idesc_base | ((uint32_t)(NI >> 3) << 17);
   constexpr uint32_t idesc2N = idesc_base | ((uint32_t)((2 * NI) >> 3) << 17);
-  constexpr uint32_t HSTAGE_U = kHaloStage >> 4, LO_U = kHaloSlot >> 4, SLOT_U = kSlot >> 4, W_U = CF::WI_BYTES >> 4;
+  constexpr uint32_t HSTAGE_U = CF::HSTAGE >> 4, LO_U = kHaloSlot >> 4, SLOT_U = kSlot >> 4, W_U = CF::WI_BYTES >> 4;
   const uint32_t full = bars.wfull + W * 32, empty = bars.wempty + W * 32;
   const uint64_t adesc0 = make_kmajor_sw128_desc(smem_base, kSbo);                       // raw tile of halo stage 0
   const uint64_t bdesc0 = make_kmajor_sw128_desc(w_base + W * CF::WS * kSlot, 1024u);       // this issuer's weight slot 0
@@ -245,9 +253,9 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
     for (int cb = 0; cb < Cblks; ++cb) {
       // this issuer's accumulator pair(s); accum0 = 0 -> the pair's first MMA overwrites (zero-initialises) main | corr
       uint32_t acc_w, accum0;
-      if (FORM == 0 && CF::COLSPLIT) { acc_w = acc0 + W * (G * 128) + (G == 2 ? (uint32_t)(cb & 1) * 128u : 0u); accum0 = cb >= G ? 1u : 0u; }
-      else if (FORM == 0) { acc_w = acc0 + W * 2 * NI; accum0 = cb > 0 ? 1u : 0u; }
-      else { acc_w = acc0 + (CF::COLSPLIT ? W * 128 : 0); accum0 = cb > 0 ? 1u : 0u; }
+      if (FORM == 0 && CF::COLSPLIT) { acc_w = acc0 + W * (G * PW) + (G == 2 ? (uint32_t)(cb & 1) * (uint32_t)PW : 0u); accum0 = cb >= G ? 1u : 0u; }
+      else if (FORM == 0) { acc_w = acc0 + W * PW; accum0 = cb > 0 ? 1u : 0u; }
+      else { acc_w = acc0 + (CF::COLSPLIT ? W * PW : 0); accum0 = cb > 0 ? 1u : 0u; }
       const bool last_cb = cb == Cblks - 1;
       uint64_t a_base = 0;
       static_for<0, NVAR>([&](auto VI) {
@@ -263,10 +271,10 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
             constexpr bool unit_first = FORM == 0 || gi == gi_first, unit_last = FORM == 0 || gi == gi_last;
             if (unit_first) {
               mbar_wait_fast(bars.hfull + 8 * hs.i, hs.ph);     // the issuing thread observes the TMA completion itself
-              mbar_wait_fast(bars.hlo + 8 * hs.i, hs.ph);       // ... and the lo tile written from it
+              if constexpr (!CF::FAST) mbar_wait_fast(bars.hlo + 8 * hs.i, hs.ph);   // ... and the lo tile written from it
               a_base = adesc0 + (uint64_t)(hs.i * HSTAGE_U);
             }
-            const uint32_t d_pair = acc_w + ((FORM == 1 && !CF::COLSPLIT) ? (uint32_t)(gi * 2 * NI) : 0u);
+            const uint32_t d_pair = acc_w + ((FORM == 1 && !CF::COLSPLIT) ? (uint32_t)(gi * PW) : 0u);
             static_for<0, nchunk>([&](auto CI) {
               constexpr int c0 = decltype(CI)::value * CH;
               constexpr int nk = nown - c0 < CH ? nown - c0 : CH;
@@ -281,11 +289,15 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
                     constexpr KbGeom kg = kb_geom<FORM>(g, i);
                     // first k-block this issuer adds to the pair within the channel block
                     constexpr bool first_kb = (c0 + ki == 0) && (FORM == 1 || gi == 0);
-                    const uint64_t a_raw = a_base + (uint64_t)kg.a_off16, a_lo = a_raw + LO_U, b_img = b_base + (uint64_t)(ki * W_U);
+                    const uint64_t a_raw = a_base + (uint64_t)kg.a_off16, b_img = b_base + (uint64_t)(ki * W_U);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {               // K = 8 tf32 per instruction = 32 bytes along the 128-byte row
-                      mma_tf32_ss(d_pair, a_raw + 2 * j, b_img + 2 * j, idesc2N, (first_kb && j == 0) ? accum0 : 1u);
-                      mma_tf32_ss(d_pair + NI, a_lo + 2 * j, b_img + 2 * j, idescN, 1u);
+                      if constexpr (CF::FAST) {
+                        mma_tf32_ss(d_pair, a_raw + 2 * j, b_img + 2 * j, idescN, (first_kb && j == 0) ? accum0 : 1u);
+                      } else {
+                        mma_tf32_ss(d_pair, a_raw + 2 * j, b_img + 2 * j, idesc2N, (first_kb && j == 0) ? accum0 : 1u);
+                        mma_tf32_ss(d_pair + NI, a_raw + LO_U + 2 * j, b_img + 2 * j, idescN, 1u);
+                      }
                     }
                   });
                 }
@@ -317,19 +329,20 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t w_base = smem_base + CF::HS * kHaloStage;
-  constexpr uint32_t misc_off = CF::HS * kHaloStage + 2 * CF::WS * kSlot;
+  const uint32_t w_base = smem_base + CF::HS * CF::HSTAGE;
+  constexpr uint32_t misc_off = CF::HS * CF::HSTAGE + 2 * CF::WS * kSlot;
   const uint32_t misc = smem_base + misc_off;
   Bars bars;
-  bars.hfull = misc;                      // 4 x 8
-  bars.hlo = misc + 32;                   // 4 x 8
-  bars.hempty = misc + 64;                // 4 x 8
-  bars.wfull = misc + 96;                 // 2 x 4 x 8
-  bars.wempty = misc + 160;               // 2 x 4 x 8
-  bars.accfull = misc + 224;              // 2 x 8
-  bars.accempty = misc + 240;             // 2 x 8
-  const uint32_t tmem_slot = misc + 256;
-  float* epi = reinterpret_cast<float*>(smem_gen + misc_off + 320);            // bias[N], scale[N], shift[N]
+  bars.hfull = misc;                      // 8 x 8
+  bars.hlo = misc + 64;                   // 8 x 8
+  bars.hempty = misc + 128;               // 8 x 8
+  bars.wfull = misc + 192;                // 2 x 4 x 8
+  bars.wempty = misc + 256;               // 2 x 4 x 8
+  bars.accfull = misc + 320;              // 2 x 8
+  bars.accempty = misc + 336;             // 2 x 8
+  const uint32_t tmem_slot = misc + 352;
+  static_assert(CF::HS <= 8 && CF::WS <= 4, "barrier layout");
+  float* epi = reinterpret_cast<float*>(smem_gen + misc_off + 384);            // bias[N], scale[N], shift[N]
   float* stg_base = epi + (N == 32 ? 4 : 3) * N;                               // N = 32: [3N, 4N) head weights; then 4 warps x 32 x 36 staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -378,7 +391,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
               mbar_arrive(bars.hfull + 8 * hs.i);
             } else {
               mbar_expect_tx(bars.hfull + 8 * hs.i, kHaloBytes);
-              tma_load_5d(smem_base + hs.i * kHaloStage, &tmap, bars.hfull + 8 * hs.i, c_plane, s0, h_plane, r0, b);
+              tma_load_5d(smem_base + hs.i * CF::HSTAGE, &tmap, bars.hfull + 8 * hs.i, c_plane, s0, h_plane, r0, b);
             }
             hs.next(CF::HS);
           }
@@ -393,7 +406,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     mma_issuer<CF, 0>(p, bars, smem_base, w_base, tmem_base);
   } else if (warp == 3) {
     mma_issuer<CF, 1>(p, bars, smem_base, w_base, tmem_base);
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 8 && !CF::FAST) {
     // ===================================================================== lo pass (once per halo tile, elementwise, same byte offsets)
     const int tid = threadIdx.x - 128;
     const bool skip = (p.debug & 1) != 0;
@@ -403,8 +416,8 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       for (int uu = 0; uu < units_per_item; ++uu) {
         mbar_wait_fast(bars.hfull + 8 * hs.i, hs.ph);
         if (!skip) {
-          float4* raw = reinterpret_cast<float4*>(smem_gen + hs.i * kHaloStage);
-          float4* lo = reinterpret_cast<float4*>(smem_gen + hs.i * kHaloStage + kHaloSlot);
+          float4* raw = reinterpret_cast<float4*>(smem_gen + hs.i * CF::HSTAGE);
+          float4* lo = reinterpret_cast<float4*>(smem_gen + hs.i * CF::HSTAGE + kHaloSlot);
 #pragma unroll 4
           for (int i = tid; i < (int)(kHaloBytes / 16); i += 128) {
             const float4 v = raw[i];
@@ -431,7 +444,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     constexpr int NCLS = FORM == 0 ? 1 : CG;
     // accumulator pairs that hold partial sums of the same output columns, and how far apart they are
     constexpr int NP = FORM == 0 ? (CF::COLSPLIT ? G : 2) : 1;
-    constexpr int PSTRIDE = FORM == 0 ? (CF::COLSPLIT ? 128 : 2 * NI) : 0;
+    constexpr int PSTRIDE = FORM == 0 ? CF::PW : 0;
     const bool no_store = (p.debug & 4) != 0;
     const int tw = row & (kTW - 1), th = row >> 3;
     const int act = p.act;
@@ -461,57 +474,86 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           const int c0 = ch * 32;
           // TMEM column of output column c0 in the first pair that holds it: main there, corr NI columns further
           uint32_t col;
-          if (CF::COLSPLIT) col = (uint32_t)((c0 >> 6) * (FORM == 0 ? G * 128 : 128) + (c0 & 63));
-          else col = (uint32_t)((FORM == 1 ? cls * 2 * NI : 0) + c0);
+          if (CF::COLSPLIT) col = (uint32_t)((c0 >> 6) * (FORM == 0 ? G * CF::PW : CF::PW) + (c0 & 63));
+          else col = (uint32_t)((FORM == 1 ? cls * CF::PW : 0) + c0);
           uint32_t v[32], u[32];
           tmem_ld32(acc_base + col, v);
-          tmem_ld32(acc_base + col + NI, u);
-          tmem_wait_ld();
+          if constexpr (CF::FAST) {
+            if (NP == 2) tmem_ld32(acc_base + col + PSTRIDE, u);
+            tmem_wait_ld();
+            if (NP == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-          if (NP == 2) {
-            uint32_t w2[32];
-            tmem_ld32(acc_base + col + PSTRIDE, u);
-            tmem_ld32(acc_base + col + PSTRIDE + NI, w2);
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+          } else {
+            tmem_ld32(acc_base + col + NI, u);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(u[j]) + __uint_as_float(w2[j])));
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            if (NP == 2) {
+              uint32_t w2[32];
+              tmem_ld32(acc_base + col + PSTRIDE, u);
+              tmem_ld32(acc_base + col + PSTRIDE + NI, w2);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(u[j]) + __uint_as_float(w2[j])));
+            }
           }
           if (cls + 1 == NCLS && ch + 1 == nchunks) {           // last TMEM read of this thread for the item: hand the set back
             tc_fence_before();
             mbar_arrive(bars.accempty + 8 * ab.i);
           }
+          // transpose the RAW accumulators once through the warp's staging rows: afterwards a thread holds channels
+          // c0 + cq .. + 3 of eight pixels, so bias / scale / shift / head weights are 16 registers (the per-element shared-memory
+          // reads of the pre-transpose form were ~100 LDS per chunk and thread - the epilogue's largest instruction group)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const float4 e_bias = *reinterpret_cast<const float4*>(epi + c0 + cq);
+          const float4 e_scale = *reinterpret_cast<const float4*>(epi + N + c0 + cq);
+          const float4 e_shift = *reinterpret_cast<const float4*>(epi + 2 * N + c0 + cq);
+          const float b4[4] = {e_bias.x, e_bias.y, e_bias.z, e_bias.w}, s4[4] = {e_scale.x, e_scale.y, e_scale.z, e_scale.w},
+                      h4[4] = {e_shift.x, e_shift.y, e_shift.z, e_shift.w};
 #pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {                // z then a from the SAME registers
+          for (int pass = 0; pass < 2; ++pass) {                // z then a from the SAME staged accumulators
             float* out = pass == 0 ? p.z_out : p.a_out;
             if (!out || (p.debug & 64)) continue;
             const bool plain = pass == 0;
-            float head = 0.f;
+            const bool with_head = FORM == 1 && N == 32 && !plain && p.head_out;
+            // fused 1x1 head: x_hat[pixel] = sum_n a[pixel][n] * head_w[n] + head_b; a pixel's 32 channels lie in the 8 lanes that
+            // share lane >> 3 (fixed order of the partial sums: deterministic)
+            float4 hw = make_float4(0.f, 0.f, 0.f, 0.f);
+            float hb = 0.f;
+            if (with_head) { hw = *reinterpret_cast<const float4*>(epi + 3 * N + cq); hb = p.head_b[0]; }
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
+            for (int it = 0; it < 8; ++it) {
+              const float4 r = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * 36 + cq);
+              const float r4[4] = {r.x, r.y, r.z, r.w};
               float o[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int n = c0 + j + e;
-                const float acc = __uint_as_float(v[j + e]);
-                const float t = plain ? acc + epi[n] : fmaf(epi[N + n], acc, epi[2 * N + n]);
+                const float t = plain ? r4[e] + b4[e] : fmaf(s4[e], r4[e], h4[e]);
                 o[e] = (plain || piecewise) ? (t > 0.f || plain ? t : slope * t) : act_slow(t, act, p.alpha);
-                if (FORM == 1 && N == 32) head = fmaf(o[e], epi[3 * N + n], head);
               }
-              *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            if (FORM == 1 && N == 32 && !plain && p.head_out) p.head_out[my_off / N] = head + p.head_b[0];
-            __syncwarp();
-            float4 vals[8];
+              if (FORM == 1 && N == 32) {
+                if (with_head) {
+                  float h = fmaf(o[3], hw.w, fmaf(o[2], hw.z, fmaf(o[1], hw.y, o[0] * hw.x)));
+                  h += __shfl_xor_sync(0xffffffffu, h, 1);
+                  h += __shfl_xor_sync(0xffffffffu, h, 2);
+                  h += __shfl_xor_sync(0xffffffffu, h, 4);
+                  if ((lane & 7) == 0) p.head_out[offs[it] / N] = h + hb;
+                }
+              }
+              if constexpr (CF::FAST) {                         // the next conv reads this tensor as a tf32 operand: store it rounded
 #pragma unroll
-            for (int it = 0; it < 8; ++it) vals[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * 36 + cq);
-            if (!no_store) {
-#pragma unroll
-              for (int it = 0; it < 8; ++it) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = vals[it];
+                for (int e = 0; e < 4; ++e) o[e] = tf32_rn(o[e]);
+              }
+              if (!no_store) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = make_float4(o[0], o[1], o[2], o[3]);
             }
-            __syncwarp();
           }
+          __syncwarp();                                         // the staging rows are rewritten by the next chunk
         }
       }
       if (CF::EPI_WG == 2) ab.ph ^= 1; else ab.next(ACC_BUFS);   // a warpgroup that owns its set sees every one of its phases
@@ -530,7 +572,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
 // SWIZZLE_128B byte order the descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n];
 // true: raw[t][n][c].  One thread per (cb, issuer-image, row, k); a column-split issuer W holds output columns [64 W, 64 W + 64).
 __global__ void hs_weight_image_kernel(const float* __restrict__ w, float* __restrict__ img, HsOrder order, int C, int N, int NI,
-                                       int transposed) {
+                                       int transposed, int parts) {   // parts = 2: {hi, lo} images; 1: hi only (1xTF32)
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nimg = order.cnt[0] + order.cnt[1];                // images per channel block (25, or 50 halves when column-split)
   const size_t total = (size_t)(C / 32) * nimg * NI * 32;
@@ -546,10 +588,10 @@ __global__ void hs_weight_image_kernel(const float* __restrict__ w, float* __res
   const float v = transposed ? w[((size_t)t * N + n) * C + c] : w[((size_t)t * C + c) * N + n];
   const uint32_t h = __float_as_uint(tf32_rn(v));
   const float lo = v - __uint_as_float(h);
-  const size_t base = ((size_t)cb * nimg + im) * 2 * NI * 32;
+  const size_t base = ((size_t)cb * nimg + im) * parts * NI * 32;
   const int pos = r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));
   img[base + pos] = __uint_as_float(h);
-  img[base + (size_t)NI * 32 + pos] = lo;
+  if (parts == 2) img[base + (size_t)NI * 32 + pos] = lo;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -611,12 +653,12 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
   {
     const size_t total = (size_t)kTaps * p.C * CF::N;
     hs_weight_image_kernel<<<uad_cdiv(total, 256), 256, 0, st>>>(w_raw, const_cast<float*>(p.wimg), order, p.C, CF::N, CF::NI,
-                                                                 weights_transposed ? 1 : 0);
+                                                                 weights_transposed ? 1 : 0, CF::FAST ? 1 : 2);
     UAD_LAUNCH_CHECK("hs_weight_image");
   }
   // shared memory: halo stages (raw + lo), two weight rings, barriers / constants / staging
-  const size_t tail = 320 + (CF::N == 32 ? 4 : 3) * CF::N * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
-  const size_t smem = 1024 + CF::HS * kHaloStage + 2 * CF::WS * kSlot + tail;
+  const size_t tail = 384 + (CF::N == 32 ? 4 : 3) * CF::N * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
+  const size_t smem = 1024 + CF::HS * CF::HSTAGE + 2 * CF::WS * kSlot + tail;
   UAD_REQUIRE(smem <= 227 * 1024, "conv_halo_ss: shared-memory budget exceeded");
   static bool attr = false;
   if (!attr) {
@@ -645,7 +687,7 @@ size_t uad_hs_gather_ws_bytes(int ksize, int Cin, int N) {
   return (size_t)ksize * ksize * Cin * N * 2 * sizeof(float) + 1024;
 }
 
-int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool weights_transposed, const float* w_raw,
+int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool weights_transposed, const float* w_raw, bool fast,
                          void* ws, size_t ws_bytes, cudaStream_t st) {
   const int C = g.Cin, N = g.N;
   const size_t need = uad_hs_gather_ws_bytes(ksize, C, N);
@@ -693,6 +735,17 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UAD_REQUIRE(cr == CUDA_SUCCESS, "conv_halo_ss: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
+  if (fast) {   // UAD_MATH_TC_1XTF32
+    if (form == 0) {
+      if (N == 32) return launch_cfg<Cfg<0, 32, 1, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
+      if (N == 64) return launch_cfg<Cfg<0, 64, 1, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
+      return launch_cfg<Cfg<0, 128, 1, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
+    }
+    UAD_REQUIRE(C <= 128, "conv_halo_ss: stride-1 form supports at most 128 input channels");
+    if (N == 32) return launch_cfg<Cfg<1, 32, 4, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
+    if (N == 64) return launch_cfg<Cfg<1, 64, 2, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
+    return launch_cfg<Cfg<1, 128, 1, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
+  }
   if (form == 0) {
     if (N == 32) return launch_cfg<Cfg<0, 32, 1, 1>>(g, tmap, p, w_raw, weights_transposed, st);
     if (N == 64) return launch_cfg<Cfg<0, 64, 1, 1>>(g, tmap, p, w_raw, weights_transposed, st);

@@ -49,9 +49,13 @@ __host__ __device__ __forceinline__ void static_for(F&& f) {
 // one accumulator region of a CTA type: parity plane (ph, pw), row shifts [j0, j0 + nj)
 struct Region { int ph, pw, j0, nj; };
 
-template <int CO_>
+template <int CO_, bool FAST_ = false>
 struct WsCfg {
   static constexpr int CO = CO_;
+  // FAST = UAD_MATH_TC_1XTF32: raw x raw only, no lo pass (the tensor core truncates the fp32 words it reads; activations written by
+  // this mode's conv epilogues are already rounded to nearest tf32), no correction accumulators; the lo images' space = more stages
+  static constexpr bool FAST = FAST_;
+  static constexpr int STAGES = FAST ? 2 * kStages : kStages;
   static constexpr int NCB = CO / 32;                        // 32-channel blocks of O
   static constexpr int BW = CO == 128 ? 8 : 16;              // block width (pixels)
   static constexpr int HW = BW + 2;                          // plane halo width
@@ -72,7 +76,7 @@ struct WsCfg {
   static constexpr uint32_t X_BYTES = kBH * HW * 128u;                         // one plane halo (raw)
   static constexpr uint32_t O_BYTES = (kBH + 2) * NCB * BW * 128u;             // the O tile with its two halo rows (raw)
   static constexpr uint32_t HALF = (CO == 32 ? 2 : 1) * X_BYTES + O_BYTES;     // raw images; the lo images follow at + HALF
-  static constexpr uint32_t STAGE = 2 * HALF;
+  static constexpr uint32_t STAGE = (FAST ? 1 : 2) * HALF;
   static_assert(STAGE % 1024 == 0 && X_BYTES % 512 == 0 && O_BYTES % 512 == 0, "tile alignment");
 };
 
@@ -92,14 +96,15 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t misc = smem_base + kStages * STAGE;
-  const uint32_t bar_full = misc, bar_lo = misc + 32, bar_empty = misc + 64, bar_acc = misc + 96, tmem_slot = misc + 104;
+  constexpr int kSt = CF::STAGES;
+  const uint32_t misc = smem_base + kSt * STAGE;
+  const uint32_t bar_full = misc, bar_lo = misc + 64, bar_empty = misc + 128, bar_acc = misc + 192, tmem_slot = misc + 200;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blk0 = blockIdx.y * p.bpc;
   const int blk1 = blk0 + p.bpc < p.nblocks ? blk0 + p.bpc : p.nblocks;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_lo + 8 * i, 128); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kSt; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_lo + 8 * i, 128); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_proxy_async();
@@ -130,7 +135,7 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
           tma_load_5d(st + i * X_BYTES, &tmap_g, bar_full + 8 * s, rg.pw * p.Cg + cgb * 32, s0 - rg.pw, rg.ph, r0 - rg.ph, b);
         }
         tma_load_5d(st + NREG * X_BYTES, &tmap_o, bar_full + 8 * s, 0, s0, 0, r0 - 2, b);   // rows r0 - 2 .. r0 + 3
-        if (++s == kStages) { s = 0; ph ^= 1; }
+        if (++s == kSt) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 2) {
@@ -143,7 +148,7 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
     uint32_t s = 0, ph = 0;
     for (int blk = blk0; blk < blk1; ++blk) {
       mbar_wait(bar_full + 8 * s, ph);
-      mbar_wait(bar_lo + 8 * s, ph);
+      if constexpr (!CF::FAST) mbar_wait(bar_lo + 8 * s, ph);
       tc_fence_after();
       const uint32_t st = smem_base + s * STAGE;
       const uint64_t xa = da_bits | (uint64_t)((st & 0x3FFFF) >> 4);
@@ -165,8 +170,10 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
                 constexpr uint32_t main_c = CF::col(TYPE, i), corr_c = main_c + rg.nj * CO;
                 const uint32_t acc = (rr == 0 && q == 0) ? accum : 1u;
                 mma_tf32_ss(tmem_base + main_c, xa + a_off, ob + b_off, idesc, acc);                              // raw x raw
-                mma_tf32_ss(tmem_base + corr_c, xa + a_off, ob + b_off + (HALF >> 4), idesc, acc);                // raw x lo
-                mma_tf32_ss(tmem_base + corr_c, xa + a_off + (HALF >> 4), ob + b_off, idesc, 1u);                 // lo x raw
+                if constexpr (!CF::FAST) {
+                  mma_tf32_ss(tmem_base + corr_c, xa + a_off, ob + b_off + (HALF >> 4), idesc, acc);              // raw x lo
+                  mma_tf32_ss(tmem_base + corr_c, xa + a_off + (HALF >> 4), ob + b_off, idesc, 1u);               // lo x raw
+                }
               });
             });
           });
@@ -175,14 +182,14 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
         if (blk == blk1 - 1) tc_commit(bar_acc);
       }
       __syncwarp();
-      if (++s == kStages) { s = 0; ph ^= 1; }
+      if (++s == kSt) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 4) {
     // ===================================================================== lo pass: second half of the stage = first half - trunc
     const int tid = threadIdx.x - 128;
     const bool skip = (p.debug & 1) != 0;
     uint32_t s = 0, ph = 0;
-    for (int blk = blk0; blk < blk1; ++blk) {
+    for (int blk = blk0; blk < (CF::FAST ? blk0 : blk1); ++blk) {
       mbar_wait(bar_full + 8 * s, ph);
       if (!skip) {
         float4* raw = reinterpret_cast<float4*>(smem_gen + s * STAGE);
@@ -199,7 +206,7 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
         fence_proxy_async();
       }
       mbar_arrive(bar_lo + 8 * s);
-      if (++s == kStages) { s = 0; ph ^= 1; }
+      if (++s == kSt) { s = 0; ph ^= 1; }
     }
     // ===================================================================== epilogue: TMEM lane group g = horizontal tap g of each region
     if (blk1 > blk0) {
@@ -224,7 +231,12 @@ __device__ __forceinline__ void wgrad_ss_body(const CUtensorMap& tmap_g, const C
               uint32_t v[32], u[32];
               const uint32_t lane_addr = tmem_base + ((uint32_t)(g * 32) << 16);
               tmem_ld32(lane_addr + main_c + jj * CO + c0, v);
-              tmem_ld32(lane_addr + corr_c + jj * CO + c0, u);
+              if constexpr (CF::FAST) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) u[e] = 0u;
+              } else {
+                tmem_ld32(lane_addr + corr_c + jj * CO + c0, u);
+              }
               tmem_wait_ld();
 #pragma unroll
               for (int e = 0; e < 32; e += 4)
@@ -300,7 +312,7 @@ WsPlan ws_plan(int Cg, int Co, int B, int MH, int MW) {
 
 template <class CF>
 int launch_all_types(const CUtensorMap& tg, const CUtensorMap& to, const WsParams& p, int nchunks, cudaStream_t st) {
-  const size_t smem = 1024 + kStages * CF::STAGE + 128;
+  const size_t smem = 1024 + CF::STAGES * CF::STAGE + 256;
   static bool attr = false;
   if (!attr) {
     UAD_CUDA(cudaFuncSetAttribute(wgrad_ss<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -328,7 +340,7 @@ size_t uad_ws_wgrad_ws_bytes(int Cg, int Co, int B, int MH, int MW) {
   return (size_t)pl.nchunks * 25 * Cg * Co * sizeof(float) + 1024;
 }
 
-int uad_launch_wgrad_ss(const WgradParams& w, float* out, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+int uad_launch_wgrad_ss(const WgradParams& w, float* out, int accumulate, bool fast, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int Cg = w.Cg, Co = w.Co;
   UAD_REQUIRE(w.sh == 2 && w.taps.n == 25, "wgrad_ss: only the 5x5 stride-2 gather is implemented");
   for (int t = 0; t < 25; ++t)
@@ -371,7 +383,11 @@ int uad_launch_wgrad_ss(const WgradParams& w, float* out, int accumulate, void* 
     UAD_REQUIRE(cr == CUDA_SUCCESS, "wgrad_ss: cuTensorMapEncodeTiled(o) failed (%d)", (int)cr);
   }
   int rc;
-  if (Co == 32) rc = launch_all_types<WsCfg<32>>(tmap_g, tmap_o, p, pl.nchunks, st);
+  if (fast) {   // UAD_MATH_TC_1XTF32
+    if (Co == 32) rc = launch_all_types<WsCfg<32, true>>(tmap_g, tmap_o, p, pl.nchunks, st);
+    else if (Co == 64) rc = launch_all_types<WsCfg<64, true>>(tmap_g, tmap_o, p, pl.nchunks, st);
+    else rc = launch_all_types<WsCfg<128, true>>(tmap_g, tmap_o, p, pl.nchunks, st);
+  } else if (Co == 32) rc = launch_all_types<WsCfg<32>>(tmap_g, tmap_o, p, pl.nchunks, st);
   else if (Co == 64) rc = launch_all_types<WsCfg<64>>(tmap_g, tmap_o, p, pl.nchunks, st);
   else rc = launch_all_types<WsCfg<128>>(tmap_g, tmap_o, p, pl.nchunks, st);
   if (rc) return rc;

@@ -1,4 +1,6 @@
 // Small dense / 1x1-conv GEMMs (bottleneck layers: < 0.1 % of the step's FLOPs) with the same fused epilogue as the convs.
+#include <stdlib.h>
+
 #include "uad_common.cuh"
 
 // C[M,N] = sum_k A(m,k) * B(k,n), A(m,k) = A[m*sa_m + k*sa_k] * (Amul ? Amul[...] * mulscale : 1), same for B.
@@ -162,17 +164,44 @@ static int launch_small(SmallGemm g, cudaStream_t st, void* ws, size_t ws_bytes)
   return 0;
 }
 
+// workspace regions of uad_dense_bwd: its three parts (dx, dw, dbias) run concurrently, each with its own split-K partials
+static size_t ws_align(size_t floats) { return (floats * sizeof(float) + 255) & ~(size_t)255; }
+static size_t bwd_dx_bytes(int M, int K, int N) { int kc; return ws_align((size_t)plan_splits(M, K, N, &kc) * M * K); }
+static size_t bwd_dw_bytes(int M, int K, int N) { int kc; return ws_align((size_t)plan_splits(K, N, M, &kc) * K * N); }
+static size_t bwd_db_bytes(int N) { return ws_align((size_t)64 * N); }
+
 extern "C" size_t uad_dense_workspace_bytes(int M, int K, int N) {
-  // the three GEMMs of fwd/bwd: y[M,N] over K, dx[M,K] over N, dw[K,N] over M; plus the column-sum partials
+  // forward: y[M,N] over K; backward: dx[M,K] over N, dw[K,N] over M and the column-sum partials side by side
   int kc;
-  size_t a = (size_t)plan_splits(M, N, K, &kc) * M * N;
-  size_t b = (size_t)plan_splits(M, K, N, &kc) * M * K;
-  size_t c = (size_t)plan_splits(K, N, M, &kc) * K * N;
-  size_t d = (size_t)64 * N;
-  size_t mx = a > b ? a : b;
-  mx = mx > c ? mx : c;
-  mx = mx > d ? mx : d;
-  return mx * sizeof(float) + 256;
+  const size_t fwd = ws_align((size_t)plan_splits(M, N, K, &kc) * M * N);
+  const size_t bwd = bwd_dx_bytes(M, K, N) + bwd_dw_bytes(M, K, N) + bwd_db_bytes(N);
+  return (fwd > bwd ? fwd : bwd) + 256;
+}
+
+// Fork / join of the three independent parts of a dense backward (46 launches of ~5 us each make up the bottleneck chain of a
+// step: latency, not work).  Two internal side streams wait for an event recorded on the caller's stream and the caller's stream
+// waits for theirs, so the call is still ordered like one operation on `st` - also under CUDA-graph capture, where the side
+// streams join the capture as parallel branches.  UAD_DENSE_FORK=0 issues the parts one after the other.
+struct DenseFork {
+  cudaStream_t side[2];
+  cudaEvent_t fork, join[2];
+  bool ok;
+};
+static DenseFork* dense_fork() {
+  static DenseFork f;
+  static int state = 0;   // 0 = untried, 1 = ready, -1 = disabled
+  if (state == 0) {
+    const char* e = getenv("UAD_DENSE_FORK");
+    state = -1;
+    if (!(e && atoi(e) == 0)) {
+      bool ok = cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 2 && ok; ++i)
+        ok = cudaStreamCreateWithFlags(&f.side[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&f.join[i], cudaEventDisableTiming) == cudaSuccess;
+      if (ok) state = 1; else cudaGetLastError();
+    }
+  }
+  return state == 1 ? &f : nullptr;
 }
 
 // dbias[n] (+)= sum_m dz[m,n] * (mask ? mask*scale : 1): grid (N/32, row-splits) -> partial[split][N] -> final (deterministic)
@@ -229,6 +258,21 @@ extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, co
                              void* stream) {
   UAD_REQUIRE(M > 0 && K > 0 && N > 0, "uad_dense_bwd: bad dims");
   cudaStream_t st = (cudaStream_t)stream;
+  // workspace regions (each part falls back to an unsplit GEMM if its region is missing)
+  const size_t dx_b = bwd_dx_bytes(M, K, N), dw_b = bwd_dw_bytes(M, K, N), db_b = bwd_db_bytes(N);
+  const bool regions = ws && ws_bytes >= dx_b + dw_b + db_b;
+  char* wsc = (char*)ws;
+  void* ws_dx = ws; size_t wsb_dx = regions ? dx_b : ws_bytes;
+  void* ws_dw = regions ? wsc + dx_b : ws; size_t wsb_dw = regions ? dw_b : ws_bytes;
+  void* ws_db = regions ? wsc + dx_b + dw_b : ws; size_t wsb_db = regions ? db_b : ws_bytes;
+  const int nparts = (dx ? 1 : 0) + (dw ? 1 : 0) + (dbias ? 1 : 0);
+  DenseFork* fk = (regions && nparts > 1) ? dense_fork() : nullptr;
+  cudaStream_t st_dw = st, st_db = st;
+  if (fk) {
+    UAD_CUDA(cudaEventRecord(fk->fork, st));
+    if (dx && dw) { UAD_CUDA(cudaStreamWaitEvent(fk->side[0], fk->fork, 0)); st_dw = fk->side[0]; }
+    if ((dx || dw) && dbias) { UAD_CUDA(cudaStreamWaitEvent(fk->side[1], fk->fork, 0)); st_db = fk->side[1]; }
+  }
   if (dx) {   // dx[M,K] = (dz*mask)[M,N] . W^T[N,K]
     SmallGemm g = {};
     g.A = dz; g.Amul = mask; g.sa_m = N; g.sa_k = 1;
@@ -236,7 +280,7 @@ extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, co
     g.mulscale = mask_scale;
     g.M = M; g.N = K; g.K = N;
     g.z_out = dx;
-    if (int e = launch_small(g, st, ws, ws_bytes)) return e;
+    if (int e = launch_small(g, st, ws_dx, wsb_dx)) return e;
   }
   if (dw) {   // dw[K,N] (+)= x^T[K,M] . (dz*mask)[M,N]
     SmallGemm g = {};
@@ -245,18 +289,22 @@ extern "C" int uad_dense_bwd(const float* x, const float* w, const float* dz, co
     g.mulscale = mask_scale;
     g.M = K; g.N = N; g.K = M;
     g.z_out = dw; g.accumulate = accumulate;
-    if (int e = launch_small(g, st, ws, ws_bytes)) return e;
+    if (int e = launch_small(g, st_dw, ws_dw, wsb_dw)) return e;
   }
   if (dbias) {
     int splits = uad_cdiv(M, 64);
     if (splits > 64) splits = 64;
     const int rps = uad_cdiv(M, splits);
     splits = uad_cdiv(M, rps);
-    UAD_REQUIRE(ws && ws_bytes >= (size_t)splits * N * sizeof(float), "uad_dense_bwd: workspace too small");
-    colsum_kernel<<<dim3(uad_cdiv(N, 32), splits), 256, 0, st>>>(dz, mask, mask_scale, (float*)ws, M, N, rps);
+    UAD_REQUIRE(ws_db && wsb_db >= (size_t)splits * N * sizeof(float), "uad_dense_bwd: workspace too small");
+    colsum_kernel<<<dim3(uad_cdiv(N, 32), splits), 256, 0, st_db>>>(dz, mask, mask_scale, (float*)ws_db, M, N, rps);
     UAD_LAUNCH_CHECK("colsum");
-    colsum_final_kernel<<<uad_cdiv(N, 128), 128, 0, st>>>((const float*)ws, splits, N, dbias, accumulate);
+    colsum_final_kernel<<<uad_cdiv(N, 128), 128, 0, st_db>>>((const float*)ws_db, splits, N, dbias, accumulate);
     UAD_LAUNCH_CHECK("colsum_final");
+  }
+  if (fk) {
+    if (st_dw != st) { UAD_CUDA(cudaEventRecord(fk->join[0], st_dw)); UAD_CUDA(cudaStreamWaitEvent(st, fk->join[0], 0)); }
+    if (st_db != st) { UAD_CUDA(cudaEventRecord(fk->join[1], st_db)); UAD_CUDA(cudaStreamWaitEvent(st, fk->join[1], 0)); }
   }
   return 0;
 }

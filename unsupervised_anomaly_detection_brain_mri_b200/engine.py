@@ -377,6 +377,11 @@ class ConvAutoencoderEngine:
         need = max(need, L.uad_tv_restore_workspace_bytes(B, S, S))
         self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         self.ws_bytes = need
+        # filter gradients run on a side stream beside the input-gradient chain (backward()): their own workspace
+        self.side_wgrad = os.environ.get('UAD_SIDE_WGRAD', '1') != '0' and torch.device(self.device).type == 'cuda'
+        self.ws2 = torch.empty(need, dtype=torch.uint8, device=self.device) if self.side_wgrad else None
+        self._side = None
+        self._side_last = None
 
     # ------------------------------------------------------------------ helpers
     def _op(self, label, fname, *args):
@@ -388,6 +393,37 @@ class ConvAutoencoderEngine:
         call(fname, *args)
         e1.record()
         self.probes.setdefault(f'{label}:{fname[4:]}', []).append((e0, e1))
+
+    def _op_side(self, label, fname, *args):
+        """Issue a filter-gradient call (its last three arguments are ws, ws_bytes, stream) on the side stream with the side
+        workspace: it reads what the main stream has produced so far (fork event) and runs beside the input-gradient kernel of
+        the same layer, filling the SMs that kernel's tail leaves idle.  Returns the event that marks its completion; the
+        caller makes the main stream wait for it before a buffer the call reads is overwritten (``_wait_side``).  With
+        per-kernel probes on, or UAD_SIDE_WGRAD=0, the call runs in line."""
+        if not self.side_wgrad or self.probes is not None:
+            self._op(label, fname, *args)
+            return None
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        call(fname, *args[:-3], self.ws2.data_ptr(), self.ws_bytes, self._side.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(self._side)
+        self._side_last = done
+        return done
+
+    def _wait_side(self, ev):
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _join_side(self):
+        """Main stream waits for everything issued on the side stream (end of a backward pass; required before a capture ends)."""
+        if self._side_last is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._side_last)
+            self._side_last = None
 
     def probe_times_ms(self):
         torch.cuda.synchronize(self.device)
@@ -755,6 +791,7 @@ class ConvAutoencoderEngine:
                      ptr(fp.g('Decoder/dec_Conv2D_final/kernel')), ptr(fp.g('Decoder/dec_Conv2D_final/bias')), B,
                      self.S * self.S, cin, act_blk, LRELU_ALPHA, BN_C, acc, ws, wsb, st)
             s = self.S
+            prev_wg = None           # completion of the previous layer's filter gradient (it reads the buffer the next dgrad overwrites)
             for i in reversed(range(self.n)):
                 co = self.dec_ch[i]
                 ci = self.dec_ch[i - 1] if i > 0 else self.enc_ch[-1]
@@ -765,10 +802,12 @@ class ConvAutoencoderEngine:
                      ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, act_blk,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.dec_a[i - 1] if i > 0 else br.ar
-                self._op(pre.split('/')[-1], 'uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
+                wg = self._op_side(pre.split('/')[-1], 'uad_convT2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, s // 2, s // 2, ci, co, KSIZE,
                      acc, mm, ws, wsb, st)
+                self._wait_side(prev_wg)
                 self._op(pre.split('/')[-1], 'uad_convT2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, s // 2, s // 2, ci, co, KSIZE, mm,
                      ws, wsb, st)
+                prev_wg = wg
                 g, gn = gn, g
                 s //= 2
             # decoder-entry BN + ReLU on the 1x1 conv output, then the 1x1 conv (as a dense over B*res*res rows)
@@ -834,16 +873,20 @@ class ConvAutoencoderEngine:
                      ptr(fp.g(bnn + '/gamma')), ptr(fp.g(bnn + '/beta')), ptr(fp.g(pre + '/bias')), B * s * s, co, act_blk,
                      LRELU_ALPHA, BN_C, acc, ws, wsb, st)
                 xin = br.enc_a[i - 1] if i > 0 else br.x
-                self._op(pre.split('/')[-1], 'uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE, acc,
+                wg = self._op_side(pre.split('/')[-1], 'uad_conv2d_wgrad', ptr(xin), ptr(g), ptr(fp.g(pre + '/kernel')), B, 2 * s, 2 * s, ci, co, KSIZE, acc,
                      mm, ws, wsb, st)
                 if i > 0:
+                    self._wait_side(prev_wg)
                     self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(gn), B, 2 * s, 2 * s, ci, co, KSIZE, mm,
                          ws, wsb, st)
                     g, gn = gn, g
                 elif want_input_grad and bi == 0:
                     self._op(pre.split('/')[-1], 'uad_conv2d_dgrad', ptr(g), ptr(fp.p(pre + '/kernel')), ptr(self.gx), B, 2 * s, 2 * s, ci, co,
                          KSIZE, mm, ws, wsb, st)
+                prev_wg = wg
                 s *= 2
+            # the next branch (ceVAE) starts by overwriting the gradient buffers the last filter gradients still read
+            self._join_side()
 
     _keep = 1.0
 
