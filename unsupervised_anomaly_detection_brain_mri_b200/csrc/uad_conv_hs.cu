@@ -73,21 +73,30 @@ __host__ __device__ __forceinline__ void static_for(F&& f) {
 //   FORM 1 (stride-1 gather, four output-parity classes: transposed-conv forward, conv input gradient): group = class (p, q);
 //          tap kh = p + 3 - 2 wh reads window (wh, ww) of the ONE halo; an item covers CG consecutive classes
 // Group g has (2 + g>>1) x (2 + g&1) k-blocks in both forms (4, 6, 6, 9); k-block i of it is window (ih, iw) = (i / nw, i % nw).
+// RP = halo pixels between two vertically adjacent window positions: kHW, or 2 kHW in the image-pair layout (see Cfg::PAIR)
 struct KbGeom { int a_off16, wt; };
 __host__ __device__ constexpr int grp_nkb(int g) { return (2 + (g >> 1)) * (2 + (g & 1)); }
-template <int FORM>
+template <int FORM, int RP = kHW>
 __host__ __device__ constexpr KbGeom kb_geom(int g, int i) {
   const int p = g >> 1, q = g & 1, nw = 2 + q, ih = i / nw, iw = i % nw;
   if (FORM == 0) {
     const int wh = 1 - p + ih, ww = 1 - q + iw;
-    return KbGeom{(wh * kHW + ww) * 8, (2 * wh + p - 1) * 5 + (2 * ww + q - 1)};
+    return KbGeom{(wh * RP + ww) * 8, (2 * wh + p - 1) * 5 + (2 * ww + q - 1)};
   }
-  return KbGeom{(ih * kHW + iw) * 8, (p + 3 - 2 * ih) * 5 + (q + 3 - 2 * iw)};
+  return KbGeom{(ih * RP + iw) * 8, (p + 3 - 2 * ih) * 5 + (q + 3 - 2 * iw)};
 }
 
-template <int FORM_, int N_, int CG_, int G_, bool FAST_ = false>
+template <int FORM_, int N_, int CG_, int G_, bool FAST_ = false, bool PAIR_ = false>
 struct Cfg {
   static constexpr int FORM = FORM_, N = N_, CG = CG_, G = G_;
+  // PAIR: M-grids of exactly 8 x 8 pixels (the bottleneck layers).  A 128-row tile is TWO images; their halos (10 x 10 pixels each)
+  // are loaded by ONE 5-D TMA box whose dimension order (channel, W, image, H) interleaves the images row by row in shared memory:
+  // halo row r of image j lies at (2 r + j) * 1280 bytes, so the 16 eight-pixel groups of an operand descriptor (tile row r of
+  // image j = group 2 r + j) are still SBO = 1280 bytes apart, and one window step down is 2 x 10 halo pixels.
+  static constexpr bool PAIR = PAIR_;
+  static constexpr int RP = PAIR ? 2 * kHW : kHW;            // halo pixels per vertical window step
+  static constexpr uint32_t HALO_BYTES = PAIR ? 2u * (kTW + 2) * kHW * 128u : kHaloBytes;   // 25600 | 23040
+  static constexpr uint32_t HALO_SLOT = (HALO_BYTES + 1023u) & ~1023u;
   // FAST = UAD_MATH_TC_1XTF32: ONE tf32 MMA per K-step (operands rounded to nearest tf32, fp32 accumulation), no lo images, no
   // correction accumulators - the arithmetic of a bf16 / tf32 training step, NOT the fp32-accurate default.  There is no lo pass at
   // all: the tensor core truncates whatever fp32 word it is given (E1), and every conv epilogue of this mode stores its output
@@ -104,8 +113,9 @@ struct Cfg {
   static constexpr int CH = kSlot / WI_BYTES;                // k-blocks per weight chunk (2 at NI = 32, else 1; twice that when FAST)
   // the strided form turns a halo over every 4 .. 9 k-blocks and a refill (TMA + lo pass) takes ~2500 cycles: three stages there,
   // paid for with one weight slot; the stride-1 form keeps a halo for a whole (item, channel block)
-  static constexpr int HS = (FORM == 0 ? 3 : 2) * (FAST ? 2 : 1), WS = FORM == 0 ? 2 : 3;   // halo stages, weight slots per issuer
-  static constexpr uint32_t HSTAGE = FAST ? kHaloSlot : kHaloStage;      // bytes per halo stage (raw [+ lo])
+  // (the pair layout's larger halos: one halo stage less in the strided form, one weight slot less in the stride-1 form)
+  static constexpr int HS = (FORM == 0 ? (PAIR ? 2 : 3) : 2) * (FAST ? 2 : 1), WS = (FORM == 0 || PAIR) ? 2 : 3;   // halo stages, weight slots per issuer
+  static constexpr uint32_t HSTAGE = (FAST ? 1u : 2u) * HALO_SLOT;       // bytes per halo stage (raw [+ lo])
   static constexpr int ACC_COLS = FORM == 0 ? (COLSPLIT ? 2 * G * PW : 2 * PW) : (COLSPLIT ? 2 * PW : CG * PW);
   static constexpr int ACC_BUFS = 2 * ACC_COLS <= 512 ? 2 : 1;
   // the stride-1 form writes up to four classes per item: a second epilogue warpgroup (one per accumulator set, alternate items)
@@ -237,7 +247,7 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
   constexpr uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t idescN = idesc_base | ((uint32_t)(NI >> 3) << 17);
   constexpr uint32_t idesc2N = idesc_base | ((uint32_t)((2 * NI) >> 3) << 17);
-  constexpr uint32_t HSTAGE_U = CF::HSTAGE >> 4, LO_U = kHaloSlot >> 4, SLOT_U = kSlot >> 4, W_U = CF::WI_BYTES >> 4;
+  constexpr uint32_t HSTAGE_U = CF::HSTAGE >> 4, LO_U = CF::HALO_SLOT >> 4, SLOT_U = kSlot >> 4, W_U = CF::WI_BYTES >> 4;
   const uint32_t full = bars.wfull + W * 32, empty = bars.wempty + W * 32;
   const uint64_t adesc0 = make_kmajor_sw128_desc(smem_base, kSbo);                       // raw tile of halo stage 0
   const uint64_t bdesc0 = make_kmajor_sw128_desc(w_base + W * CF::WS * kSlot, 1024u);       // this issuer's weight slot 0
@@ -286,7 +296,7 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
                 if (!no_mma) {
                   static_for<0, nk>([&](auto KI) {
                     constexpr int ki = decltype(KI)::value, i = i0 + c0 + ki;
-                    constexpr KbGeom kg = kb_geom<FORM>(g, i);
+                    constexpr KbGeom kg = kb_geom<FORM, CF::RP>(g, i);
                     // first k-block this issuer adds to the pair within the channel block
                     constexpr bool first_kb = (c0 + ki == 0) && (FORM == 1 || gi == 0);
                     const uint64_t a_raw = a_base + (uint64_t)kg.a_off16, b_img = b_base + (uint64_t)(ki * W_U);
@@ -382,6 +392,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
         const int tile = item / NVAR;
         const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
         const int s0 = twi * kTW - 1, r0 = thi * kTH - 1;     // halo origin (the zero fill outside the tensor == SAME padding)
+        // PAIR: tile = image pair (2 tile, 2 tile + 1); an image index past the batch is zero-filled like the padding
         for (int cb = 0; cb < Cblks; ++cb) {
 #pragma unroll
           for (int u = 0; u < CF::NUNITS; ++u) {
@@ -390,8 +401,9 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
             if (no_load) {
               mbar_arrive(bars.hfull + 8 * hs.i);
             } else {
-              mbar_expect_tx(bars.hfull + 8 * hs.i, kHaloBytes);
-              tma_load_5d(smem_base + hs.i * CF::HSTAGE, &tmap, bars.hfull + 8 * hs.i, c_plane, s0, h_plane, r0, b);
+              mbar_expect_tx(bars.hfull + 8 * hs.i, CF::HALO_BYTES);
+              if constexpr (CF::PAIR) tma_load_5d(smem_base + hs.i * CF::HSTAGE, &tmap, bars.hfull + 8 * hs.i, c_plane, -1, 2 * tile, -1, h_plane);
+              else tma_load_5d(smem_base + hs.i * CF::HSTAGE, &tmap, bars.hfull + 8 * hs.i, c_plane, s0, h_plane, r0, b);
             }
             hs.next(CF::HS);
           }
@@ -417,9 +429,9 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
         mbar_wait_fast(bars.hfull + 8 * hs.i, hs.ph);
         if (!skip) {
           float4* raw = reinterpret_cast<float4*>(smem_gen + hs.i * CF::HSTAGE);
-          float4* lo = reinterpret_cast<float4*>(smem_gen + hs.i * CF::HSTAGE + kHaloSlot);
+          float4* lo = reinterpret_cast<float4*>(smem_gen + hs.i * CF::HSTAGE + CF::HALO_SLOT);
 #pragma unroll 4
-          for (int i = tid; i < (int)(kHaloBytes / 16); i += 128) {
+          for (int i = tid; i < (int)(CF::HALO_BYTES / 16); i += 128) {
             const float4 v = raw[i];
             float4 h, l;
             h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
@@ -446,7 +458,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     constexpr int NP = FORM == 0 ? (CF::COLSPLIT ? G : 2) : 1;
     constexpr int PSTRIDE = FORM == 0 ? CF::PW : 0;
     const bool no_store = (p.debug & 4) != 0;
-    const int tw = row & (kTW - 1), th = row >> 3;
+    const int tw = row & (kTW - 1), th = CF::PAIR ? (row >> 4) : (row >> 3);   // PAIR: group 2 r + j = tile row r of image j
     const int act = p.act;
     // LeakyReLU / ReLU / identity as one select (the other activations take the generic path)
     const bool piecewise = act == UAD_ACT_NONE || act == UAD_ACT_LEAKY || act == UAD_ACT_RELU;
@@ -454,8 +466,9 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     Ring ab{(uint32_t)(CF::EPI_WG == 2 ? wg : 0), 0};
     for (int item = blockIdx.x + (CF::EPI_WG == 2 ? wg * gridDim.x : 0); item < p.n_items; item += CF::EPI_WG * gridDim.x) {
       const int var = NVAR > 1 ? item % NVAR : 0, tile = item / NVAR;
-      const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
-      const int s0 = twi * kTW, r0 = thi * kTH;
+      const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h;
+      const int b = CF::PAIR ? 2 * tile + ((row >> 3) & 1) : tile / (p.tiles_w * p.tiles_h);
+      const int s0 = CF::PAIR ? 0 : twi * kTW, r0 = CF::PAIR ? 0 : thi * kTH;
       const uint32_t acc_base = lane_base + ab.i * ACC_COLS;
       mbar_wait_fast(bars.accfull + 8 * ab.i, ab.ph);
       tc_fence_after();
@@ -464,7 +477,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
 #pragma unroll 1
       for (int cls = 0; cls < NCLS; ++cls) {
         const int c = FORM == 0 ? 0 : var * CG + cls;           // output-parity class (p, q) = (c >> 1, c & 1)
-        const long long my_off =
+        const long long my_off = (CF::PAIR && b >= p.B) ? -1ll :       // second image of the last pair of an odd batch: no output
             (((long long)b * p.OH + ((r0 + th) * p.osh + (c >> 1))) * p.OW + ((s0 + tw) * p.osh + (c & 1))) * (long long)N;
         long long offs[8];
 #pragma unroll
@@ -543,14 +556,14 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
                   h += __shfl_xor_sync(0xffffffffu, h, 1);
                   h += __shfl_xor_sync(0xffffffffu, h, 2);
                   h += __shfl_xor_sync(0xffffffffu, h, 4);
-                  if ((lane & 7) == 0) p.head_out[offs[it] / N] = h + hb;
+                  if ((lane & 7) == 0 && (!CF::PAIR || offs[it] >= 0)) p.head_out[offs[it] / N] = h + hb;
                 }
               }
               if constexpr (CF::FAST) {                         // the next conv reads this tensor as a tf32 operand: store it rounded
 #pragma unroll
                 for (int e = 0; e < 4; ++e) o[e] = tf32_rn(o[e]);
               }
-              if (!no_store) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = make_float4(o[0], o[1], o[2], o[3]);
+              if (!no_store && (!CF::PAIR || offs[it] >= 0)) *reinterpret_cast<float4*>(out + offs[it] + c0 + cq) = make_float4(o[0], o[1], o[2], o[3]);
             }
           }
           __syncwarp();                                         // the staging rows are rewritten by the next chunk
@@ -620,7 +633,7 @@ int build_order(const GatherParams& g, HsOrder& order) {
     order.cnt[W] = CF::cnt(W);
     for (int grp = 0; grp < 4; ++grp)
       for (int i = CF::i0(W, grp); i < CF::i1(W, grp); ++i) {
-        const KbGeom kg = kb_geom<CF::FORM>(grp, i);
+        const KbGeom kg = kb_geom<CF::FORM, CF::RP>(grp, i);
         order.wt[W][CF::ord_base(W, grp) + (i - CF::i0(W, grp))] = (unsigned char)kg.wt;
         const TapSet& ts = g.taps[CF::FORM == 0 ? 0 : grp];
         bool found = false;
@@ -634,7 +647,7 @@ int build_order(const GatherParams& g, HsOrder& order) {
           } else {
             wh = dh + 1; wwd = dw + 1;
           }
-          found = (wh * kHW + wwd) * 8 == kg.a_off16;
+          found = (wh * CF::RP + wwd) * 8 == kg.a_off16;
         }
         UAD_REQUIRE(found, "conv_halo_ss: tap table does not match the compiled geometry (group %d, k-block %d)", grp, i);
       }
@@ -665,7 +678,7 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
     UAD_CUDA(cudaFuncSetAttribute(conv_halo_ss<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  p.n_items = p.tiles_w * p.tiles_h * p.B * CF::NVAR;
+  p.n_items = (CF::PAIR ? (p.B + 1) / 2 : p.tiles_w * p.tiles_h * p.B) * CF::NVAR;
   const int grid = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
   conv_halo_ss<CF><<<grid, CF::THREADS, smem, st>>>(tmap, p);
   UAD_LAUNCH_CHECK("conv_halo_ss");
@@ -677,7 +690,8 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
 int uad_hs_gather_supported(int Cin, int N, int lgMH, int lgMW, int nclasses) {
   if (Cin % 32 != 0 || Cin < 32) return 0;
   if (!(N == 32 || N == 64 || N == 128)) return 0;
-  if (lgMH < 4 || lgMW < 3) return 0;          // M-grid at least 16 x 8: one tile never spans two images
+  if (lgMW < 3 || lgMH < 3) return 0;          // M-grid at least 16 x 8 (one tile never spans two images) ...
+  if (lgMH == 3 && lgMW != 3) return 0;        // ... or exactly 8 x 8: the image-pair layout (Cfg::PAIR)
   if (nclasses == 4 && Cin > 128) return 0;    // stride-1 form: one accumulator pair per class (K <= 9 * 128 per pair)
   return 1;
 }
@@ -703,8 +717,9 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
   HsParams p;
   memset(&p, 0, sizeof(p));
   const int MW = 1 << g.lgMW, MH = 1 << g.lgMH;
+  const bool pair = MH == 8 && MW == 8;
   p.tiles_w = MW / kTW;
-  p.tiles_h = MH / kTH;
+  p.tiles_h = pair ? 1 : MH / kTH;
   p.B = g.B; p.C = C; p.Cblks = C / 32;
   p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
@@ -719,7 +734,15 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
   CUtensorMap tmap;
   cuuint64_t dims[5], strides[4];
   const cuuint64_t e = sizeof(float);
-  if (form == 0) {
+  if (pair && form == 0) {          // (channel x column parity, W / 2, image, H / 2, row parity): box = both images' plane halos, row-interleaved
+    dims[0] = 2ull * C; dims[1] = g.IW / 2; dims[2] = g.B; dims[3] = g.IH / 2; dims[4] = 2;
+    strides[0] = 2ull * C * e; strides[1] = (cuuint64_t)g.IH * g.IW * C * e; strides[2] = 2ull * g.IW * C * e;
+    strides[3] = (cuuint64_t)g.IW * C * e;
+  } else if (pair) {                // (channel, W, image, H, 1)
+    dims[0] = C; dims[1] = g.IW; dims[2] = g.B; dims[3] = g.IH; dims[4] = 1;
+    strides[0] = (cuuint64_t)C * e; strides[1] = (cuuint64_t)g.IH * g.IW * C * e; strides[2] = (cuuint64_t)g.IW * C * e;
+    strides[3] = (cuuint64_t)g.IH * g.IW * C * e;
+  } else if (form == 0) {
     dims[0] = 2ull * C; dims[1] = g.IW / 2; dims[2] = 2; dims[3] = g.IH / 2; dims[4] = g.B;
     strides[0] = 2ull * C * e; strides[1] = (cuuint64_t)g.IW * C * e; strides[2] = 2ull * g.IW * C * e;
     strides[3] = (cuuint64_t)g.IH * g.IW * C * e;
@@ -729,12 +752,29 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
     strides[3] = (cuuint64_t)g.IH * g.IW * C * e;
   }
   cuuint32_t box[5] = {32u, (cuuint32_t)kHW, 1u, (cuuint32_t)kHH, 1u};
+  if (pair) { box[2] = 2u; box[3] = (cuuint32_t)(kTW + 2); }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(g.in), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UAD_REQUIRE(cr == CUDA_SUCCESS, "conv_halo_ss: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
+  if (pair) {   // 8 x 8 M-grids: two images per tile
+    if (form == 1) UAD_REQUIRE(C <= 128, "conv_halo_ss: stride-1 form supports at most 128 input channels");
+#define UAD_HS_PAIR(FAST)                                                                                                   \
+    if (form == 0) {                                                                                                         \
+      if (N == 32) return launch_cfg<Cfg<0, 32, 1, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);               \
+      if (N == 64) return launch_cfg<Cfg<0, 64, 1, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);               \
+      if (!FAST && p.Cblks >= 2) return launch_cfg<Cfg<0, 128, 1, 2, false, true>>(g, tmap, p, w_raw, weights_transposed, st); \
+      return launch_cfg<Cfg<0, 128, 1, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                           \
+    }                                                                                                                        \
+    if (N == 32) return launch_cfg<Cfg<1, 32, 4, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                 \
+    if (N == 64) return launch_cfg<Cfg<1, 64, 2, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                 \
+    return launch_cfg<Cfg<1, 128, 1, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);
+    if (fast) { UAD_HS_PAIR(true) }
+    UAD_HS_PAIR(false)
+#undef UAD_HS_PAIR
+  }
   if (fast) {   // UAD_MATH_TC_1XTF32
     if (form == 0) {
       if (N == 32) return launch_cfg<Cfg<0, 32, 1, 1, true>>(g, tmap, p, w_raw, weights_transposed, st);
