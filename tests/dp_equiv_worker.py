@@ -52,12 +52,15 @@ def main():
 
 
 def graph_part(rank, world, local):
-    """CUDA-graph replay with the NCCL all-reduce and the Adam update INSIDE the captured step == the same steps with the collective
-    issued outside the graph (UAD_GRAPH_ALLREDUCE=0): bit-identical weights after five steps (device RNG, same seeds)."""
+    """CUDA-graph replay of the data-parallel step in its three forms - (a) the default: decoder gradient bucket all-reduced on the
+    side while the encoder's backward runs, the rest at the end, Adam, all INSIDE the captured step; (b) one all-reduce inside the
+    graph (UAD_DP_BUCKETS=0 UAD_GRAPH_ALLREDUCE=1); (c) the collective issued behind the replay (both 0) - gives bit-identical
+    weights after five steps (device RNG, same seeds)."""
     arch, S, B, lr = 'variational_autoencoder', 64, 4, 1e-3
     x = udist.shard(make_volume(S, B * world, seed=9, lesions=False)[0][..., None])
     res = []
-    for inside in ('1', '0'):
+    for buckets, inside in (('1', '0'), ('0', '1'), ('0', '0')):
+        os.environ['UAD_DP_BUCKETS'] = buckets
         os.environ['UAD_GRAPH_ALLREDUCE'] = inside
         eng = ConvAutoencoderEngine(arch, S, batch=B, device=f'cuda:{local}', seed=3)
         udist.broadcast_(eng.fp.params)
@@ -65,14 +68,16 @@ def graph_part(rank, world, local):
         for _ in range(5):
             eng.train_step(lr, dropout_rate=0.2, dropout=True, allreduce=udist.allreduce_sum_, world=world, use_graph=True)
         torch.cuda.synchronize()
-        assert eng.graph is not None and eng._graph_has_update == (inside == '1')
+        assert eng.graph is not None and eng._graph_has_update == (inside == '1' or buckets == '1')
+        assert (eng._bucket_async is not None) == (buckets == '1')
         res.append(eng.fp.params.clone())
     os.environ.pop('UAD_GRAPH_ALLREDUCE')
-    same = bool(torch.equal(res[0], res[1]))
+    os.environ.pop('UAD_DP_BUCKETS')
+    same = bool(torch.equal(res[0], res[1])) and bool(torch.equal(res[1], res[2]))
     t = torch.tensor([int(same)], device=f'cuda:{local}')
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
     if rank == 0:
-        print(f'DP_EQUIV_GRAPH world={world} all-reduce inside the graph == outside: {bool(t.item())}', flush=True)
+        print(f'DP_EQUIV_GRAPH world={world} bucketed in-graph == single in-graph == outside the graph: {bool(t.item())}', flush=True)
     assert t.item() == 1
 
 

@@ -358,3 +358,17 @@ def test_every_main_script_binds_to_existing_product_symbols():
                         assert hasattr(mod, alias.name), (f, node.module, alias.name)
             elif isinstance(node, ast.Import):
                 assert not any(a.name.startswith(('oracle', 'tensorflow')) for a in node.names), f
+
+
+def test_combined_predictive_uncertainty_formula():
+    """trainers/Metrics.py:170-173: E[p^2] - E[p]^2 + E[sigma^2] over the Monte-Carlo axis; log_var=True exponentiates sigma first."""
+    from unsupervised_anomaly_detection_brain_mri_b200.trainers import Metrics
+    rng = np.random.default_rng(0)
+    p = rng.uniform(size=(5, 3, 8, 8)).astype(np.float32)
+    sig = rng.uniform(size=p.shape).astype(np.float32)
+    got = Metrics.combined_predictive_uncertainty(p, sig, axis=0)
+    ref = (p.astype(np.float64) ** 2).mean(0) - p.astype(np.float64).mean(0) ** 2 + sig.astype(np.float64).mean(0)
+    assert got.shape == (3, 8, 8) and np.allclose(got, ref, atol=1e-6)
+    got_lv = Metrics.combined_predictive_uncertainty(p, np.log(sig), axis=0, log_var=True)
+    assert np.allclose(got_lv, ref, atol=1e-5)
+    assert np.allclose(Metrics.combined_predictive_uncertainty(p, np.zeros_like(p), axis=0), p.var(axis=0), atol=1e-6)

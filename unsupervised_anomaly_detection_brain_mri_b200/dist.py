@@ -37,6 +37,18 @@ def allreduce_sum_(flat):
     return flat
 
 
+def allreduce_sum_async(flat):
+    """Sum-all-reduce that does not block the calling stream: returns the work handle (``.wait()`` makes the CURRENT stream wait
+    for the result), or None in a single-process run.  The engine uses it for the decoder's gradient bucket, which is complete
+    while the encoder's backward pass is still running."""
+    if world_size() > 1:
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+    return None
+
+
+allreduce_sum_.async_ = allreduce_sum_async
+
+
 def broadcast_(flat, src=0):
     if world_size() > 1:
         dist.broadcast(flat, src=src)

@@ -382,6 +382,13 @@ class ConvAutoencoderEngine:
         self.ws2 = torch.empty(need, dtype=torch.uint8, device=self.device) if self.side_wgrad else None
         self._side = None
         self._side_last = None
+        # data parallel, opt-in (UAD_DP_BUCKETS=1): the decoder's gradient bucket is all-reduced while the encoder's backward pass
+        # runs (train_step).  Bit-identical to the single all-reduce; measured on 2 x B200 it does not pay (the 8.8 MB collective
+        # takes ~25 us there: c2 4.215 vs 4.211 ms, c4 1.743 vs 1.735 ms per step), so the default stays one all-reduce behind the replay
+        self.dp_buckets = os.environ.get('UAD_DP_BUCKETS', '0') != '0' and torch.device(self.device).type == 'cuda'
+        self._bucket_async = None
+        self._bucket_work = None
+        self._bucket_lo = None
 
     # ------------------------------------------------------------------ helpers
     def _op(self, label, fname, *args):
@@ -418,6 +425,36 @@ class ConvAutoencoderEngine:
     def _wait_side(self, ev):
         if ev is not None:
             torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _launch_decoder_bucket(self):
+        """Called by backward() once every Decoder/ gradient of the step has been issued (the decoder's filter gradients on
+        the side stream, its BN / bias gradients on the main stream): start the sum-all-reduce of that contiguous slice of the
+        flat gradient buffer behind both, without blocking either - it travels over NVLink while the bottleneck and encoder
+        backward run.  train_step reduces the rest and waits for this bucket before Adam."""
+        if self._bucket_async is None or self.probes is not None:
+            return
+        lo, hi = self.fp.subset_ranges('Decoder/')
+        if hi != self.fp.numel:
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side is not None:
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):
+                self._bucket_work = self._bucket_async(self.fp.grads[lo:hi])
+        else:
+            self._bucket_work = self._bucket_async(self.fp.grads[lo:hi])
+        self._bucket_lo = lo if self._bucket_work is not None else None
+
+    def _finish_allreduce(self, allreduce):
+        """The gradient all-reduce of a step: everything, or - when the decoder bucket is already in flight - the rest."""
+        if self._bucket_work is not None:
+            allreduce(self.fp.grads[:self._bucket_lo])
+            self._bucket_work.wait()
+            self._bucket_work = None
+        else:
+            allreduce(self.fp.grads)
 
     def _join_side(self):
         """Main stream waits for everything issued on the side stream (end of a backward pass; required before a capture ends)."""
@@ -816,6 +853,8 @@ class ConvAutoencoderEngine:
             self._op('dec_entry_bn', 'uad_act_bn_bwd', ptr(g), ptr(br.zr), ptr(fp.p(dbn + '/gamma')), ptr(fp.p(dbn + '/beta')), ptr(g),
                  ptr(fp.g(dbn + '/gamma')), ptr(fp.g(dbn + '/beta')), ptr(fp.g('Bottleneck/conv2d_1/bias')) if self.arch not in SPATIAL else None,
                  B * r2, ctop, ACT_RELU, 0.0, BN_C, acc, ws, wsb, st)
+            if bi == len(self.br) - 1:
+                self._launch_decoder_bucket()
             sm = self.small
             m = br.masks
             # keep factor is stored with the mask application: masks carry {0,1}, scale passed explicitly
@@ -1161,6 +1200,9 @@ class ConvAutoencoderEngine:
         (the ~90 kernel launches of a step collapse into one graph launch)."""
         rate = dropout_rate if dropout else 0.0
         self._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
+        # decoder gradient bucket in flight during the encoder's backward (needs the collective's non-blocking form, dist.py)
+        self._bucket_async = getattr(allreduce, 'async_', None) if (allreduce is not None and self.dp_buckets and world > 1) else None
+        self._bucket_work = None
         key = (lr, beta1, rate, dropout, world, want_anomaly, allreduce is None)
         if use_graph and not parity_noise and self._warm == key:
             if self.graph is None:
@@ -1168,7 +1210,7 @@ class ConvAutoencoderEngine:
                 # warm-up step) and the Adam update CAN be part of the captured step (UAD_GRAPH_ALLREDUCE=1; bit-identical
                 # results, tests/dp_equiv_worker.py).  Measured on 2 x B200 (profiles/r2_dp_2gpu.md): 4.455 ms per step inside
                 # the graph, 4.425 ms with the collective issued behind the replay (1 GPU: 4.346) - the default stays outside.
-                self._graph_has_update = allreduce is None or os.environ.get('UAD_GRAPH_ALLREDUCE', '0') != '0'
+                self._graph_has_update = allreduce is None or self._bucket_async is not None or os.environ.get('UAD_GRAPH_ALLREDUCE', '0') != '0'
                 t_save = self.t
                 try:
                     g = torch.cuda.CUDAGraph()
@@ -1176,13 +1218,14 @@ class ConvAutoencoderEngine:
                         self._fwd_bwd(rate, dropout, False, want_anomaly)
                         if self._graph_has_update:
                             if allreduce is not None:
-                                allreduce(self.fp.grads)
+                                self._finish_allreduce(allreduce)
                             self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
                 except Exception:
                     if allreduce is None or not self._graph_has_update:
                         raise
                     torch.cuda.synchronize(self.device)           # a collective that cannot be captured here: capture without it
                     self._graph_has_update = False
+                    self._bucket_async, self._bucket_work = None, None
                     g = torch.cuda.CUDAGraph()
                     with graph_capture(g):
                         self._fwd_bwd(rate, dropout, False, want_anomaly)
@@ -1198,7 +1241,7 @@ class ConvAutoencoderEngine:
         self.graph = None
         self._fwd_bwd(rate, dropout, parity_noise, want_anomaly)
         if allreduce is not None:
-            allreduce(self.fp.grads)
+            self._finish_allreduce(allreduce)
         self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
         self._warm = key
 

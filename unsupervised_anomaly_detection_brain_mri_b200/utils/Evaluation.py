@@ -187,6 +187,19 @@ def score_volume_on_device(x, x_rec, brainmask, erode_iterations, prior_quantile
     return sub
 
 
+def brainmask_on_device(brainmask, erode_iterations, device):
+    """The boolean brain mask `apply_brainmask` multiplies with (Evaluation.py:84-89), for a whole [Z,H,W] stack: the cross-shaped
+    12-iteration erosion runs on the GPU (uad_binary_erosion_cross, bit-exact vs scipy)."""
+    m = np.ascontiguousarray(np.asarray(brainmask) != 0).astype(np.uint8)
+    if not erode_iterations:
+        return m.astype(bool)
+    st = torch.cuda.current_stream().cuda_stream
+    md = torch.from_numpy(m).to(device)
+    er = torch.empty_like(md)
+    abi.call('uad_binary_erosion_cross', md.data_ptr(), er.data_ptr(), m.shape[0], m.shape[1], m.shape[2], int(erode_iterations), st)
+    return er.cpu().numpy().astype(bool)
+
+
 def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST", shard=None):
     """shard = (rank, world): score only this rank's volumes (volumes are the unit: the 5x5x5 median couples neighbouring
     slices); the integer Dice counts are all-reduced by Metrics.DeviceScorer."""
@@ -231,22 +244,32 @@ def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST", shard=None
             for i in range(num_samples):                           # MC-dropout loop (:239-267), one batched pass per sample
                 results = modelObj.reconstruct(x[..., None], dropout=num_samples > 1)
                 recs.append(results['reconstruction'][..., 0])
-            x_rec = recs[0] if num_samples == 1 else np.mean(np.array(recs), axis=0).astype(np.float32)
+            skull = np.stack([np.squeeze(m) for m in skulls])
+            erode_it = 12 if should(options, "erodeBrainmask") else 0
+            last_rec = recs[-1]                                    # l1err / l2err are those of the LAST pass (:274-276)
+            var = None
+            if num_samples > 1:
+                # :253-267 - every sample is brain-masked BEFORE the statistics: mean and epistemic variance are 0 outside the
+                # (eroded) mask; the scored reconstruction is the masked mean
+                mask = brainmask_on_device(skull, erode_it, device)
+                x_recs = np.array([np.multiply(mask, r) for r in recs])
+                var = Metrics.combined_predictive_uncertainty(x_recs, np.zeros(x_recs.shape), axis=0, log_var=False)
+                x_rec = np.mean(x_recs, axis=0).astype(np.float32)
+            else:
+                x_rec = recs[0]
             eval_dict['reconstructionTimes'] += [(time.time() - _tmp) / max(len(xs), 1)] * len(xs)
-            subvolume = score_volume_on_device(x, x_rec, np.stack([np.squeeze(m) for m in skulls]),
-                                               12 if should(options, "erodeBrainmask") else 0, prior_quantile,
+            subvolume = score_volume_on_device(x, x_rec, skull, erode_it, prior_quantile,
                                                should(options, "keepOnlyPositiveResiduals"),
                                                should(options, "applyHyperIntensityPrior"), should(options, "medianFiltering"),
                                                device)
-            if num_samples > 1:
-                var = Metrics.combined_predictive_uncertainty(np.array(recs), np.zeros_like(np.array(recs)), axis=0)
+            if var is not None:
                 eval_dict['epistemic_variance'] += list(var)
             eval_dict['x'] += list(x[..., None])
             eval_dict['reconstructions'] += list(x_rec[..., None])
             eval_dict['labelmaps'] += segs
             for i in range(len(xs)):
-                eval_dict['l1reconstructionErrors'] += [np.sum(np.abs(x[i] - x_rec[i]))]
-                eval_dict['l2reconstructionErrors'] += [np.sum(np.sqrt((x[i] - x_rec[i]) ** 2))]
+                eval_dict['l1reconstructionErrors'] += [np.sum(np.abs(x[i] - last_rec[i]))]
+                eval_dict['l2reconstructionErrors'] += [np.sum(np.sqrt((x[i] - last_rec[i]) ** 2))]
             eval_dict['diffs'] += [subvolume]
             if should(options, 'exportVolumes') and hasattr(nii_seg, 'set_subvolume'):
                 export_patient_volume(nii_seg, subvolume, zoom_factor, datasetObj.options, options, sampleDir, patient['name'])
