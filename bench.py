@@ -516,7 +516,9 @@ def main():
             'config': {'workload': args.workload, 'global_batch': B * world, 'parallelism': f'dp{world}',
                        'math': MATH_NOTE[args.math],
                        'l2': 'per-step working set (~2 GB of activations) >> 126 MB L2; 4 distinct input batches rotate',
-                       'cuda_graph': True},
+                       'cuda_graph': True,
+                       'dp_update': (None if world == 1 else 'one fused kernel over NVLink peer memory: reduce-scatter + Adam + all-gather (csrc/uad_peer.cu), inside the captured step'
+                                     if getattr(eng, 'peer', None) is not None else 'NCCL all-reduce + Adam kernel behind the graph replay')},
             'step_tflops': step_flops(B) * world / (ms_step / 1e3) / 1e12,
             'e2e': {'value': e2e_value, 'unit': 'slices/s', 'h2d_bytes_per_step': int(host_batches[0].nbytes),
                     'd2h_bytes_per_step': int(eng.scalars.numel() * 4),

@@ -152,6 +152,22 @@ int uad_adam_tf_step(float* params, const float* grads, float* m, float* v, size
 /* step_dev (nullable): device step counter t (1-based).  When given, `lr_t` is the BASE learning rate and the kernel
  * derives lr_t = lr*sqrt(1-b2^t)/(1-b1^t) itself (float64), so a captured CUDA graph needs no per-step host value. */
 
+/* ---- data-parallel optimiser step as ONE kernel over NVLink peer memory (csrc/uad_peer.cu): reduce-scatter of the ranks' flat
+ * gradient buffers, TF-form Adam (the arithmetic of uad_adam_tf_step; reference trainers/DLMODEL.py:112-131) on the rank's own
+ * shard, all-gather of the updated parameters.  Replaces "all-reduce (NCCL) + uad_adam_tf_step".  Each rank allocates one region
+ * [params | grads | flags] of uad_peer_region_bytes(numel) bytes with uad_peer_alloc, publishes its 64-byte IPC handle
+ * (uad_peer_ipc_handle) through the host-side process group and maps the other ranks' regions with uad_peer_ipc_open;
+ * regions[j] is rank j's region as mapped in the calling process.  m / v are local (only the rank's shard is used).
+ * Every rank must issue the call the same number of times; a peer that never arrives traps after ~4 s instead of hanging. */
+size_t uad_peer_region_bytes(size_t numel);
+int uad_peer_alloc(size_t bytes, void** region_out);
+int uad_peer_free(void* region);
+int uad_peer_ipc_handle(void* region, void* handle64);
+int uad_peer_ipc_open(const void* handle64, void** region_out);
+int uad_peer_ipc_close(void* region);
+int uad_peer_adam_step(void* const* regions, int rank, int world, size_t numel, float* m, float* v, float lr, float b1, float b2,
+                       float eps, float grad_scale, const int64_t* step_dev, void* stream);
+
 /* ---- Philox-4x32-10 streams for the live graph RNG nodes (tf.random_normal variational_autoencoder.py:34; Dropout) */
 int uad_randn(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);
 int uad_dropout_mask(float* mask, size_t n, float rate, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,

@@ -45,6 +45,7 @@ def main():
         assert gerr < 1e-4 and werr <= 2.001 * lr and frac < 5e-3
     torch.distributed.barrier()
     graph_part(rank, world, local)
+    peer_part(rank, world, local)
     fanogan_part(rank, world, local)
     scoring_part(rank, world, local)
     torch.distributed.barrier()
@@ -78,6 +79,46 @@ def graph_part(rank, world, local):
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
     if rank == 0:
         print(f'DP_EQUIV_GRAPH world={world} bucketed in-graph == single in-graph == outside the graph: {bool(t.item())}', flush=True)
+    assert t.item() == 1
+
+
+def peer_part(rank, world, local):
+    """The fused peer-memory optimiser step (csrc/uad_peer.cu: reduce-scatter + Adam + all-gather in one kernel, dist.PeerOptimizer)
+    against NCCL all-reduce + uad_adam_tf_step: eager and CUDA-graph replay, six steps.  Two ranks: a + b is commutative, so the
+    weights must be BIT-identical; more ranks: the summation order differs from NCCL's, equal within rounding (and identical on
+    every rank either way).  The Adam moments of a rank's own shard must equal the NCCL run's."""
+    arch, S, B, lr = 'variational_autoencoder', 64, 4, 1e-3
+    x = udist.shard(make_volume(S, B * world, seed=13, lesions=False)[0][..., None])
+    res = []
+    for peer in (False, True):
+        os.environ['UAD_DP_BUCKETS'] = '0'
+        eng = ConvAutoencoderEngine(arch, S, batch=B, device=f'cuda:{local}', seed=3)
+        udist.broadcast_(eng.fp.params)
+        if peer:
+            eng.enable_peer_optimizer()
+            assert eng.peer is not None
+        eng.set_inputs(x)
+        eng.train_step(lr, dropout_rate=0.2, dropout=True, allreduce=udist.allreduce_sum_, world=world, use_graph=False)
+        for _ in range(5):
+            eng.train_step(lr, dropout_rate=0.2, dropout=True, allreduce=udist.allreduce_sum_, world=world, use_graph=True)
+        torch.cuda.synchronize()
+        assert eng.graph is not None
+        res.append((eng.fp.params.clone(), eng.fp.m.clone(), eng.fp.v.clone(), eng))
+    os.environ.pop('UAD_DP_BUCKETS')
+    p_nccl, p_peer = res[0][0], res[1][0]
+    diff = float((p_nccl - p_peer).abs().max())
+    lo, hi = res[1][3].peer.shard_range()
+    m_ok = bool(torch.equal(res[0][1][lo:hi], res[1][1][lo:hi])) if world == 2 else True
+    # every rank must hold the same parameters after the all-gather
+    ref = p_peer.clone()
+    torch.distributed.broadcast(ref, src=0)
+    same_everywhere = bool(torch.equal(ref, p_peer))
+    ok = (diff == 0.0 if world == 2 else diff <= 2.001 * lr) and m_ok and same_everywhere
+    t = torch.tensor([int(ok)], device=f'cuda:{local}')
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    if rank == 0:
+        print(f'DP_EQUIV_PEER world={world} max |w_peer - w_nccl| = {diff:.3e}, own-shard moments equal: {m_ok}, '
+              f'identical on every rank: {same_everywhere}', flush=True)
     assert t.item() == 1
 
 

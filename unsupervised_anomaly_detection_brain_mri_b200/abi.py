@@ -82,6 +82,13 @@ SIGNATURES = {
     'uad_restore_update': (_I, [_P, _P, _P, _F, _P, _Z, _P]),
     'uad_gmvae_latent_fwd': (_I, [_P] * 8 + [_I, _I, _I, _F, _P]),
     'uad_gmvae_latent_bwd': (_I, [_P] * 5 + [_F] + [_P] * 5 + [_I, _I, _I, _F, _P]),
+    'uad_peer_region_bytes': (_Z, [_Z]),
+    'uad_peer_alloc': (_I, [_Z, C.POINTER(C.c_void_p)]),
+    'uad_peer_free': (_I, [_P]),
+    'uad_peer_ipc_handle': (_I, [_P, _P]),
+    'uad_peer_ipc_open': (_I, [_P, C.POINTER(C.c_void_p)]),
+    'uad_peer_ipc_close': (_I, [_P]),
+    'uad_peer_adam_step': (_I, [C.POINTER(C.c_void_p), _I, _I, _Z, _P, _P] + [_F] * 5 + [_P, _P]),
 }
 
 

@@ -80,3 +80,74 @@ def mean_over_ranks(value, device):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         t /= world_size()
     return float(t.item())
+
+
+class _DeviceArray:
+    """A raw device allocation seen through __cuda_array_interface__ (torch.as_tensor maps it without a copy)."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {'shape': (int(numel),), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 3,
+                                         'strides': None}
+
+
+class PeerOptimizer:
+    """The optimiser step of a data-parallel run as ONE kernel over NVLink peer memory (csrc/uad_peer.cu: reduce-scatter of the
+    gradients, TF-Adam on the own shard, all-gather of the new parameters) instead of `all_reduce` + Adam.
+
+    Moves the flat parameter and gradient buffers of ``fp`` (engine.FlatParams) into a cudaMalloc'ed region whose IPC handle the
+    ranks exchange through the process group; ``fp.params`` / ``fp.grads`` become views of that region, so the engine's kernels
+    write their gradients where the peers read them and read their parameters where the peers write them.  Must be created before
+    the first train step (a captured CUDA graph holds the buffer addresses)."""
+
+    def __init__(self, fp, device):
+        import ctypes as C
+        from . import abi
+        assert dist.is_initialized() and world_size() > 1, 'PeerOptimizer needs an initialised process group'
+        self.rank, self.world, self.numel = rank(), world_size(), int(fp.numel)
+        L = abi.lib()
+        nbytes = L.uad_peer_region_bytes(self.numel)
+        region = C.c_void_p()
+        abi.call('uad_peer_alloc', nbytes, C.byref(region))
+        self.region = region.value
+        half = (self.numel * 4 + 255) & ~255
+        self._holders = (_DeviceArray(self.region, self.numel), _DeviceArray(self.region + half, self.numel))
+        params = torch.as_tensor(self._holders[0], device=device)
+        grads = torch.as_tensor(self._holders[1], device=device)
+        params.copy_(fp.params)
+        grads.zero_()
+        fp.params, fp.grads = params, grads
+        handle = C.create_string_buffer(64)
+        abi.call('uad_peer_ipc_handle', self.region, handle)
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, handle.raw)
+        self.regions = (C.c_void_p * 16)()
+        self._opened = []
+        for j, blob in enumerate(blobs):
+            if j == self.rank:
+                self.regions[j] = self.region
+            else:
+                out = C.c_void_p()
+                abi.call('uad_peer_ipc_open', C.create_string_buffer(blob, 64), C.byref(out))
+                self.regions[j] = out.value
+                self._opened.append(out.value)
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    def step(self, m, v, lr, beta1, beta2, eps, grad_scale, step_dev, stream):
+        from . import abi
+        abi.call('uad_peer_adam_step', self.regions, self.rank, self.world, self.numel, m.data_ptr(), v.data_ptr(), float(lr),
+                 float(beta1), float(beta2), float(eps), float(grad_scale), step_dev.data_ptr(), stream)
+
+    def shard_range(self):
+        chunk = (-(-self.numel // self.world) + 3) & ~3
+        lo = self.rank * chunk
+        return lo, min(self.numel, lo + chunk)
+
+    def gather_adam_state(self, m, v):
+        """Every rank holds the Adam moments of its own shard only; before they are written to a checkpoint, collect them."""
+        lo, hi = self.shard_range()
+        for buf in (m, v):
+            own = torch.zeros_like(buf)
+            own[lo:hi] = buf[lo:hi]
+            dist.all_reduce(own, op=dist.ReduceOp.SUM)
+            buf.copy_(own)

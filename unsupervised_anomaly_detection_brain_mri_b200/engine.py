@@ -389,6 +389,7 @@ class ConvAutoencoderEngine:
         self._bucket_async = None
         self._bucket_work = None
         self._bucket_lo = None
+        self.peer = None                 # dist.PeerOptimizer (enable_peer_optimizer): fused reduce-scatter + Adam + all-gather
 
     # ------------------------------------------------------------------ helpers
     def _op(self, label, fname, *args):
@@ -1176,6 +1177,29 @@ class ConvAutoencoderEngine:
         call('uad_adam_tf_step', ptr(fp.params[lo:]), ptr(fp.grads[lo:]), ptr(fp.m[lo:]), ptr(fp.v[lo:]), hi - lo,
              lr, beta1, beta2, eps, grad_scale, self.step_dev.data_ptr(), st)
 
+    def enable_peer_optimizer(self):
+        """Data parallel: replace `all-reduce + Adam` by the single peer-memory kernel (dist.PeerOptimizer).  Call once, after the
+        initial parameter broadcast and before the first train step."""
+        from . import dist as udist
+        if self.peer is None and udist.world_size() > 1:
+            self.peer = udist.PeerOptimizer(self.fp, self.device)
+            self.graph, self._warm = None, None
+        return self.peer
+
+    def adam_step_peer(self, lr, beta1=0.5, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        self.t += 1
+        call('uad_counter_add', self.step_dev.data_ptr(), 1, self._st())
+        self.peer.step(self.fp.m, self.fp.v, lr, beta1, beta2, eps, grad_scale, self.step_dev, self._st())
+
+    def _reduce_and_update(self, allreduce, lr, beta1, world):
+        """[gradient all-reduce] + TF-Adam: NCCL + the Adam kernel, or the fused peer-memory kernel."""
+        if allreduce is not None and self.peer is not None:
+            self.adam_step_peer(lr, beta1=beta1, grad_scale=1.0 / world)
+            return
+        if allreduce is not None:
+            self._finish_allreduce(allreduce)
+        self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+
     # ------------------------------------------------------------------ one train step (process(TRAIN) body)
     def _fwd_bwd(self, rate, dropout, parity_noise, want_anomaly):
         if not parity_noise:
@@ -1201,7 +1225,8 @@ class ConvAutoencoderEngine:
         rate = dropout_rate if dropout else 0.0
         self._keep = 1.0 / (1.0 - rate) if rate > 0 else 1.0
         # decoder gradient bucket in flight during the encoder's backward (needs the collective's non-blocking form, dist.py)
-        self._bucket_async = getattr(allreduce, 'async_', None) if (allreduce is not None and self.dp_buckets and world > 1) else None
+        self._bucket_async = getattr(allreduce, 'async_', None) if (allreduce is not None and self.dp_buckets and world > 1 and
+                                                                    self.peer is None) else None
         self._bucket_work = None
         key = (lr, beta1, rate, dropout, world, want_anomaly, allreduce is None)
         if use_graph and not parity_noise and self._warm == key:
@@ -1210,18 +1235,17 @@ class ConvAutoencoderEngine:
                 # warm-up step) and the Adam update CAN be part of the captured step (UAD_GRAPH_ALLREDUCE=1; bit-identical
                 # results, tests/dp_equiv_worker.py).  Measured on 2 x B200 (profiles/r2_dp_2gpu.md): 4.455 ms per step inside
                 # the graph, 4.425 ms with the collective issued behind the replay (1 GPU: 4.346) - the default stays outside.
-                self._graph_has_update = allreduce is None or self._bucket_async is not None or os.environ.get('UAD_GRAPH_ALLREDUCE', '0') != '0'
+                self._graph_has_update = (allreduce is None or self._bucket_async is not None or self.peer is not None or
+                                          os.environ.get('UAD_GRAPH_ALLREDUCE', '0') != '0')
                 t_save = self.t
                 try:
                     g = torch.cuda.CUDAGraph()
                     with graph_capture(g):
                         self._fwd_bwd(rate, dropout, False, want_anomaly)
                         if self._graph_has_update:
-                            if allreduce is not None:
-                                self._finish_allreduce(allreduce)
-                            self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+                            self._reduce_and_update(allreduce, lr, beta1, world)
                 except Exception:
-                    if allreduce is None or not self._graph_has_update:
+                    if allreduce is None or not self._graph_has_update or self.peer is not None:
                         raise
                     torch.cuda.synchronize(self.device)           # a collective that cannot be captured here: capture without it
                     self._graph_has_update = False
@@ -1240,9 +1264,7 @@ class ConvAutoencoderEngine:
             return
         self.graph = None
         self._fwd_bwd(rate, dropout, parity_noise, want_anomaly)
-        if allreduce is not None:
-            self._finish_allreduce(allreduce)
-        self.adam_step(lr, beta1=beta1, grad_scale=1.0 / world)
+        self._reduce_and_update(allreduce, lr, beta1, world)
         self._warm = key
 
     _warm = None

@@ -80,6 +80,10 @@ class AEMODEL(DLMODEL, ABC):
         if self.world > 1:
             udist.broadcast_(self.engine.fp.params, src=0)
             self._allreduce = udist.allreduce_sum_
+            # one fused kernel over NVLink peer memory (reduce-scatter + Adam + all-gather) instead of NCCL all-reduce + Adam;
+            # UAD_PEER_ADAM=0 keeps the NCCL form
+            if os.environ.get('UAD_PEER_ADAM', '1') != '0' and udist.dist.get_backend() == 'nccl' and hasattr(self.engine, 'enable_peer_optimizer'):
+                self.engine.enable_peer_optimizer()
 
     # ------------------------------------------------------------------ reference helpers
     def log_to_tensorboard(self, epoch, scalars, visuals, phase: Phase, name='x'):

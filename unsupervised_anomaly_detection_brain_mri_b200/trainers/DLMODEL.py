@@ -106,6 +106,8 @@ class DLMODEL(object):
         weights = self._weights()
         m = v = None
         if with_optimizer and hasattr(eng, 'adam_step') and isinstance(getattr(eng, 't', None), int):
+            if getattr(eng, 'peer', None) is not None:       # fused peer optimiser: every rank holds the moments of its shard only
+                eng.peer.gather_adam_state(eng.fp.m, eng.fp.v)   # (a collective - every rank has to make this call)
             m, v = eng.fp.to_numpy(eng.fp.m), eng.fp.to_numpy(eng.fp.v)
         variables = tfc.saver_variables(weights, m, v, step=int(getattr(eng, 't', 0)) if m is not None else 0,
                                         beta1=float(getattr(self.config, 'beta1', 0.5)), beta2=0.999)
