@@ -162,6 +162,9 @@ struct HsParams {
   int B, C, Cblks;
   int OH, OW, osh;
   int n_items;
+  // column slices: the kernel computes N (template) output columns of an n_total-wide layer per item, item = (tile x variant) x
+  // n_slices + slice - more, narrower items where a layer has too few tiles to occupy the SMs (the 8 x 8 M-grids); 1 otherwise
+  int n_total, n_slices;
   int debug;           // developer timing switches (UAD_HS_DEBUG): 1 = no lo pass, 2 = no MMAs, 4 = no global stores, 8 = no weight loads, 16 = no halo loads, 32 = no epilogue at all, 64 = epilogue reads the accumulators only
   float* z_out;
   float* a_out;
@@ -213,9 +216,9 @@ __device__ __forceinline__ void weight_producer(const HsParams& p, const Bars& b
   Ring ws{0, 0};
   const bool no_load = (p.debug & 8) != 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    const int var = NVAR > 1 ? item % NVAR : 0;
+    const int slice = item % p.n_slices, var = NVAR > 1 ? (item / p.n_slices) % NVAR : 0;
     for (int cb = 0; cb < p.Cblks; ++cb) {
-      const float* cb_img = img0 + (size_t)cb * cb_floats;
+      const float* cb_img = img0 + ((size_t)slice * p.Cblks + cb) * cb_floats;
       static_for<0, NVAR>([&](auto VI) {
         constexpr int V = decltype(VI)::value;
         if (NVAR > 1 && var != V) return;
@@ -256,7 +259,7 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
   Ring hs{0, 0}, ws{0, 0}, ab{0, 0};
   uint32_t next_ok = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    const int var = NVAR > 1 ? item % NVAR : 0;
+    const int var = NVAR > 1 ? (item / p.n_slices) % NVAR : 0;
     mbar_wait_fast(bars.accempty + 8 * ab.i, ab.ph ^ 1);        // the epilogue has drained this accumulator set
     tc_fence_after();
     const uint32_t acc0 = tmem_base + ab.i * CF::ACC_COLS;
@@ -353,7 +356,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   const uint32_t tmem_slot = misc + 352;
   static_assert(CF::HS <= 8 && CF::WS <= 4, "barrier layout");
   float* epi = reinterpret_cast<float*>(smem_gen + misc_off + 384);            // bias[N], scale[N], shift[N]
-  float* stg_base = epi + (N == 32 ? 4 : 3) * N;                               // N = 32: [3N, 4N) head weights; then 4 warps x 32 x 36 staging
+  float* stg_base = epi + (N == 32 ? 4 : 3) * p.n_total;                       // N = 32: [3 NT, 4 NT) head weights; then 4 warps x 32 x 36 staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cblks = p.Cblks;
@@ -368,12 +371,13 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   }
   if (warp == 3) {
     tmem_alloc(tmem_slot, 512u);
-    for (int n = lane; n < N; n += 32) {
+    const int NT = p.n_total;                                                // constants of ALL columns (a CTA may serve several slices)
+    for (int n = lane; n < NT; n += 32) {
       const float bias = p.bias ? p.bias[n] : 0.f, scale = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
       epi[n] = bias;
-      epi[N + n] = scale;
-      epi[2 * N + n] = scale * bias + (p.beta ? p.beta[n] : 0.f);         // a = act(scale * acc + shift')
-      if (N == 32) epi[3 * N + n] = p.head_out ? p.head_w[n] : 0.f;
+      epi[NT + n] = scale;
+      epi[2 * NT + n] = scale * bias + (p.beta ? p.beta[n] : 0.f);        // a = act(scale * acc + shift')
+      if (N == 32 && n < N) epi[3 * NT + n] = p.head_out ? p.head_w[n] : 0.f;   // (the fused head exists for unsliced N = 32 only)
     }
   }
   tc_fence_before();
@@ -389,7 +393,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       Ring hs{0, 0};
       const bool no_load = (p.debug & 16) != 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int tile = item / NVAR;
+        const int tile = item / (NVAR * p.n_slices);
         const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
         const int s0 = twi * kTW - 1, r0 = thi * kTH - 1;     // halo origin (the zero fill outside the tensor == SAME padding)
         // PAIR: tile = image pair (2 tile, 2 tile + 1); an image index past the batch is zero-filled like the padding
@@ -465,7 +469,8 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     const float slope = act == UAD_ACT_LEAKY ? p.alpha : (act == UAD_ACT_RELU ? 0.f : 1.f);
     Ring ab{(uint32_t)(CF::EPI_WG == 2 ? wg : 0), 0};
     for (int item = blockIdx.x + (CF::EPI_WG == 2 ? wg * gridDim.x : 0); item < p.n_items; item += CF::EPI_WG * gridDim.x) {
-      const int var = NVAR > 1 ? item % NVAR : 0, tile = item / NVAR;
+      const int slice = item % p.n_slices, var = NVAR > 1 ? (item / p.n_slices) % NVAR : 0, tile = item / (NVAR * p.n_slices);
+      const int NT = p.n_total, ncol0 = slice * N;              // output row stride, first output column of this item
       const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h;
       const int b = CF::PAIR ? 2 * tile + ((row >> 3) & 1) : tile / (p.tiles_w * p.tiles_h);
       const int s0 = CF::PAIR ? 0 : twi * kTW, r0 = CF::PAIR ? 0 : thi * kTH;
@@ -478,7 +483,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       for (int cls = 0; cls < NCLS; ++cls) {
         const int c = FORM == 0 ? 0 : var * CG + cls;           // output-parity class (p, q) = (c >> 1, c & 1)
         const long long my_off = (CF::PAIR && b >= p.B) ? -1ll :       // second image of the last pair of an odd batch: no output
-            (((long long)b * p.OH + ((r0 + th) * p.osh + (c >> 1))) * p.OW + ((s0 + tw) * p.osh + (c & 1))) * (long long)N;
+            (((long long)b * p.OH + ((r0 + th) * p.osh + (c >> 1))) * p.OW + ((s0 + tw) * p.osh + (c & 1))) * (long long)NT + ncol0;
         long long offs[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) offs[it] = __shfl_sync(0xffffffffu, my_off, it * 4 + (lane >> 3));
@@ -524,9 +529,9 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<uint4*>(stg + lane * 36 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           __syncwarp();
-          const float4 e_bias = *reinterpret_cast<const float4*>(epi + c0 + cq);
-          const float4 e_scale = *reinterpret_cast<const float4*>(epi + N + c0 + cq);
-          const float4 e_shift = *reinterpret_cast<const float4*>(epi + 2 * N + c0 + cq);
+          const float4 e_bias = *reinterpret_cast<const float4*>(epi + ncol0 + c0 + cq);
+          const float4 e_scale = *reinterpret_cast<const float4*>(epi + NT + ncol0 + c0 + cq);
+          const float4 e_shift = *reinterpret_cast<const float4*>(epi + 2 * NT + ncol0 + c0 + cq);
           const float b4[4] = {e_bias.x, e_bias.y, e_bias.z, e_bias.w}, s4[4] = {e_scale.x, e_scale.y, e_scale.z, e_scale.w},
                       h4[4] = {e_shift.x, e_shift.y, e_shift.z, e_shift.w};
 #pragma unroll 1
@@ -539,7 +544,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
             // share lane >> 3 (fixed order of the partial sums: deterministic)
             float4 hw = make_float4(0.f, 0.f, 0.f, 0.f);
             float hb = 0.f;
-            if (with_head) { hw = *reinterpret_cast<const float4*>(epi + 3 * N + cq); hb = p.head_b[0]; }
+            if (with_head) { hw = *reinterpret_cast<const float4*>(epi + 3 * NT + cq); hb = p.head_b[0]; }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const float4 r = *reinterpret_cast<const float4*>(stg + (it * 4 + (lane >> 3)) * 36 + cq);
@@ -584,24 +589,28 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
 // raw weights -> per (32-channel block, issuer, k-block in the issuer's order): {hi, lo} images of [NI rows][32 k] fp32 in the
 // SWIZZLE_128B byte order the descriptor expects (16-byte chunk index XOR (row & 7)).  transposed=false: raw[t][c][n];
 // true: raw[t][n][c].  One thread per (cb, issuer-image, row, k); a column-split issuer W holds output columns [64 W, 64 W + 64).
+// With column slices (NT = total output columns > N): the images of slice q (output columns [q N, q N + N)) follow those of slice q - 1.
 __global__ void hs_weight_image_kernel(const float* __restrict__ w, float* __restrict__ img, HsOrder order, int C, int N, int NI,
-                                       int transposed, int parts) {   // parts = 2: {hi, lo} images; 1: hi only (1xTF32)
+                                       int transposed, int parts, int NT) {   // parts = 2: {hi, lo} images; 1: hi only (1xTF32)
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int nimg = order.cnt[0] + order.cnt[1];                // images per channel block (25, or 50 halves when column-split)
-  const size_t total = (size_t)(C / 32) * nimg * NI * 32;
+  const size_t per_slice = (size_t)(C / 32) * nimg * NI * 32;
+  const size_t total = per_slice * (NT / N);
   if (i >= total) return;
-  const int k = i % 32;
-  const int r = (i / 32) % NI;
-  const int im = (i / ((size_t)32 * NI)) % nimg;
-  const int cb = i / ((size_t)32 * NI * nimg);
+  const int slice = (int)(i / per_slice);
+  const size_t is = i % per_slice;
+  const int k = is % 32;
+  const int r = (is / 32) % NI;
+  const int im = (is / ((size_t)32 * NI)) % nimg;
+  const int cb = is / ((size_t)32 * NI * nimg);
   const int W = im >= order.cnt[0] ? 1 : 0, o = W ? im - order.cnt[0] : im;
   const int t = order.wt[W][o];
   const int c = cb * 32 + k;
-  const int n = (NI < N ? W * NI : 0) + r;
-  const float v = transposed ? w[((size_t)t * N + n) * C + c] : w[((size_t)t * C + c) * N + n];
+  const int n = slice * N + (NI < N ? W * NI : 0) + r;
+  const float v = transposed ? w[((size_t)t * NT + n) * C + c] : w[((size_t)t * C + c) * NT + n];
   const uint32_t h = __float_as_uint(tf32_rn(v));
   const float lo = v - __uint_as_float(h);
-  const size_t base = ((size_t)cb * nimg + im) * parts * NI * 32;
+  const size_t base = (((size_t)slice * (C / 32) + cb) * nimg + im) * parts * NI * 32;
   const int pos = r * 32 + ((((k >> 2) ^ (r & 7)) << 2) | (k & 3));
   img[base + pos] = __uint_as_float(h);
   if (parts == 2) img[base + (size_t)NI * 32 + pos] = lo;
@@ -664,13 +673,13 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
   HsOrder order;
   if (int rc = build_order<CF>(g, order)) return rc;
   {
-    const size_t total = (size_t)kTaps * p.C * CF::N;
+    const size_t total = (size_t)kTaps * p.C * p.n_total;
     hs_weight_image_kernel<<<uad_cdiv(total, 256), 256, 0, st>>>(w_raw, const_cast<float*>(p.wimg), order, p.C, CF::N, CF::NI,
-                                                                 weights_transposed ? 1 : 0, CF::FAST ? 1 : 2);
+                                                                 weights_transposed ? 1 : 0, CF::FAST ? 1 : 2, p.n_total);
     UAD_LAUNCH_CHECK("hs_weight_image");
   }
   // shared memory: halo stages (raw + lo), two weight rings, barriers / constants / staging
-  const size_t tail = 384 + (CF::N == 32 ? 4 : 3) * CF::N * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
+  const size_t tail = 384 + (CF::N == 32 ? 4 : 3) * p.n_total * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
   const size_t smem = 1024 + CF::HS * CF::HSTAGE + 2 * CF::WS * kSlot + tail;
   UAD_REQUIRE(smem <= 227 * 1024, "conv_halo_ss: shared-memory budget exceeded");
   static bool attr = false;
@@ -678,7 +687,7 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
     UAD_CUDA(cudaFuncSetAttribute(conv_halo_ss<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  p.n_items = (CF::PAIR ? (p.B + 1) / 2 : p.tiles_w * p.tiles_h * p.B) * CF::NVAR;
+  p.n_items = (CF::PAIR ? (p.B + 1) / 2 : p.tiles_w * p.tiles_h * p.B) * CF::NVAR * p.n_slices;
   const int grid = p.n_items < UAD_NUM_SMS ? p.n_items : UAD_NUM_SMS;
   conv_halo_ss<CF><<<grid, CF::THREADS, smem, st>>>(tmap, p);
   UAD_LAUNCH_CHECK("conv_halo_ss");
@@ -721,6 +730,13 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
   p.tiles_w = MW / kTW;
   p.tiles_h = pair ? 1 : MH / kTH;
   p.B = g.B; p.C = C; p.Cblks = C / 32;
+  // 8 x 8 M-grids: ceil(B / 2) tiles cannot occupy 148 SMs - the layer is computed in 32-column slices (N / 32 times the items)
+  static int slice_pairs = -1;
+  if (slice_pairs < 0) { const char* e = getenv("UAD_HS_SLICES"); slice_pairs = e ? atoi(e) : 1; }
+  // (measured, 256^2 B = 64, N = C = 128: strided form 0.078 -> 0.046 ms sliced; stride-1 form 0.044 unsliced vs 0.049 sliced - its
+  // items already come in four output-parity variants - so only the strided form is sliced)
+  const bool sliced = pair && form == 0 && N > 32 && slice_pairs && !g.head_out;
+  p.n_total = N; p.n_slices = sliced ? N / 32 : 1;
   p.OH = g.OH; p.OW = g.OW; p.osh = g.osh;
   p.z_out = g.z_out; p.a_out = g.a_out; p.bias = g.bias; p.gamma = g.gamma; p.beta = g.beta;
   p.bn_c = g.bn_c; p.alpha = g.alpha; p.act = g.act;
@@ -771,6 +787,12 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
     if (N == 32) return launch_cfg<Cfg<1, 32, 4, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                 \
     if (N == 64) return launch_cfg<Cfg<1, 64, 2, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                 \
     return launch_cfg<Cfg<1, 128, 1, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);
+    if (sliced) {
+      if (form == 0) return fast ? launch_cfg<Cfg<0, 32, 1, 1, true, true>>(g, tmap, p, w_raw, weights_transposed, st)
+                                 : launch_cfg<Cfg<0, 32, 1, 1, false, true>>(g, tmap, p, w_raw, weights_transposed, st);
+      return fast ? launch_cfg<Cfg<1, 32, 4, 1, true, true>>(g, tmap, p, w_raw, weights_transposed, st)
+                  : launch_cfg<Cfg<1, 32, 4, 1, false, true>>(g, tmap, p, w_raw, weights_transposed, st);
+    }
     if (fast) { UAD_HS_PAIR(true) }
     UAD_HS_PAIR(false)
 #undef UAD_HS_PAIR
