@@ -165,8 +165,10 @@ int uad_peer_free(void* region);
 int uad_peer_ipc_handle(void* region, void* handle64);
 int uad_peer_ipc_open(const void* handle64, void** region_out);
 int uad_peer_ipc_close(void* region);
-int uad_peer_adam_step(void* const* regions, int rank, int world, size_t numel, float* m, float* v, float lr, float b1, float b2,
-                       float eps, float grad_scale, const int64_t* step_dev, void* stream);
+int uad_peer_adam_step(void* const* regions, int rank, int world, size_t numel, size_t offset, size_t count, float* m, float* v,
+                       float lr, float b1, float b2, float eps, float grad_scale, const int64_t* step_dev, void* stream);
+/* [offset, offset + count): the slice of the flat index space this optimiser owns (everything, or one f-AnoGAN scope); m / v
+ * point at the slice's first element. */
 
 /* ---- Philox-4x32-10 streams for the live graph RNG nodes (tf.random_normal variational_autoencoder.py:34; Dropout) */
 int uad_randn(float* out, size_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, void* stream);

@@ -47,6 +47,7 @@ def main():
     graph_part(rank, world, local)
     peer_part(rank, world, local)
     fanogan_part(rank, world, local)
+    fanogan_peer_part(rank, world, local)
     scoring_part(rank, world, local)
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
@@ -154,6 +155,41 @@ def fanogan_part(rank, world, local):
         print(f'DP_EQUIV_FANOGAN world={world} grad_rel_err={gerr:.3e} other_scopes_untouched={same_rest}', flush=True)
         assert gerr < 1e-4 and same_rest
     torch.distributed.barrier()
+
+
+def fanogan_peer_part(rank, world, local):
+    """f-AnoGAN train ops with the fused peer-memory optimiser on the updated scope's slice (three optimisers, three slices, one
+    flag region) == NCCL all-reduce of the slice + Adam: generator, critic and encoder steps, eager then CUDA-graph replay."""
+    from unsupervised_anomaly_detection_brain_mri_b200.fanogan_engine import FanoganEngine
+    S, B, lr = 64, 4, 1e-3
+    x = udist.shard(make_volume(S, B * world, seed=17, lesions=False)[0][..., None])
+    z = udist.shard(np.random.default_rng(4).standard_normal((B * world, 128)).astype(np.float32))
+    res = []
+    for peer in (False, True):
+        e = FanoganEngine(S, batch=B, device=f'cuda:{local}', seed=3)
+        e.enable_training()
+        udist.broadcast_(e.fp.params)
+        if peer:
+            e.enable_peer_optimizer()
+        e.set_inputs(x)
+        e.set_latent(z)
+        for it in range(3):
+            kw = dict(dropout_rate=0.1, dropout=True, allreduce=udist.allreduce_sum_, world=world, use_graph=it > 0)
+            e.step_gen(lr, **kw)
+            e.step_disc(lr, **kw)
+            e.step_disc(lr, **kw)
+            e.step_enc(lr, **kw)
+        torch.cuda.synchronize()
+        res.append(e.fp.params.clone())
+    diff = float((res[0] - res[1]).abs().max())
+    ref = res[1].clone()
+    torch.distributed.broadcast(ref, src=0)
+    ok = (diff == 0.0 if world == 2 else diff <= 2.001 * lr * 12) and bool(torch.equal(ref, res[1]))
+    t = torch.tensor([int(ok)], device=f'cuda:{local}')
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN)
+    if rank == 0:
+        print(f'DP_EQUIV_FANOGAN_PEER world={world} max |w_peer - w_nccl| = {diff:.3e}', flush=True)
+    assert t.item() == 1
 
 
 def scoring_part(rank, world, local):

@@ -16,6 +16,6 @@ def test_two_gpu_step_equals_single_gpu_step_on_concatenated_batch():
            '--master-port', '29533', os.path.join(here, 'dp_equiv_worker.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert 'DP_EQUIV world=2' in out.stdout and 'DP_EQUIV_GRAPH world=2' in out.stdout and 'DP_EQUIV_PEER world=2' in out.stdout
+    assert 'DP_EQUIV world=2' in out.stdout and 'DP_EQUIV_GRAPH world=2' in out.stdout and 'DP_EQUIV_PEER world=2' in out.stdout and 'DP_EQUIV_FANOGAN_PEER world=2' in out.stdout
     print(''.join(l + '\n' for l in out.stdout.splitlines() if l.startswith('DP_EQUIV')))
     assert 'DP_EQUIV_FANOGAN world=2' in out.stdout and 'DP_EQUIV_SCORING world=2' in out.stdout

@@ -88,7 +88,7 @@ SIGNATURES = {
     'uad_peer_ipc_handle': (_I, [_P, _P]),
     'uad_peer_ipc_open': (_I, [_P, C.POINTER(C.c_void_p)]),
     'uad_peer_ipc_close': (_I, [_P]),
-    'uad_peer_adam_step': (_I, [C.POINTER(C.c_void_p), _I, _I, _Z, _P, _P] + [_F] * 5 + [_P, _P]),
+    'uad_peer_adam_step': (_I, [C.POINTER(C.c_void_p), _I, _I, _Z, _Z, _Z, _P, _P] + [_F] * 5 + [_P, _P]),
 }
 
 

@@ -22,7 +22,7 @@
 #include "uad_common.cuh"
 
 #define UAD_PEER_MAX 16
-#define UAD_PEER_FLAG_WORDS 64          // per rank: [0,16) ready[src], [16,32) done[src], 32 block counter, 33 sequence number
+#define UAD_PEER_FLAG_WORDS 64          // per rank: [0,16) ready[src], [16,32) done[src], 32 block counter, 33 sequence number, 34 blocks so far
 
 struct PeerPtrs {
   float* params[UAD_PEER_MAX];
@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(256) peer_rs_adam_ag_kernel(const __grid_const
                                                               const long long* __restrict__ step_dev) {
   unsigned long long* myflags = pp.flags[rank];
   const unsigned long long seq = myflags[33] + 1ull;          // written by this rank's previous invocation only
+  const unsigned long long blocks_done = myflags[34] + (unsigned long long)gridDim.x;   // block counter value once all my blocks have arrived
   // ---- phase 0: my gradients are complete (stream order) -> tell the peers; wait until theirs are
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
@@ -106,17 +107,18 @@ __global__ void __launch_bounds__(256) peer_rs_adam_ag_kernel(const __grid_const
   if (threadIdx.x == 0) {
     atomicAdd(myflags + 32, 1ull);
     if (blockIdx.x == 0) {
-      spin_until(myflags + 32, seq * (unsigned long long)gridDim.x);
+      spin_until(myflags + 32, blocks_done);
       __threadfence_system();
       for (int j = 0; j < world; ++j) st_release_sys(pp.flags[j] + 16 + rank, seq);
     }
   }
   if (threadIdx.x < world) spin_until(myflags + 16 + threadIdx.x, seq);
   __syncthreads();
-  // every block has read seq (they all passed the counter) before the sequence number moves on
+  // every block has read seq / blocks_done (they all passed the counter) before the two values move on
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    spin_until(myflags + 32, seq * (unsigned long long)gridDim.x);
+    spin_until(myflags + 32, blocks_done);
     myflags[33] = seq;
+    myflags[34] = blocks_done;
   }
 }
 
@@ -159,28 +161,32 @@ extern "C" int uad_peer_ipc_close(void* p) {
   return 0;
 }
 
-// regions[j] = base of rank j's region as mapped in THIS process (own region for j == rank); layout [params | grads | flags]
-extern "C" int uad_peer_adam_step(void* const* regions, int rank, int world, size_t numel, float* m, float* v, float lr, float b1,
-                                  float b2, float eps, float grad_scale, const int64_t* step_dev, void* stream) {
+// regions[j] = base of rank j's region as mapped in THIS process (own region for j == rank); layout [params | grads | flags] with
+// `numel` floats per buffer.  The step covers the slice [offset, offset + count) of the flat index space (one optimiser's variables:
+// f-AnoGAN runs three Adam optimisers on scope-contiguous slices); m / v point at the slice's first element.
+extern "C" int uad_peer_adam_step(void* const* regions, int rank, int world, size_t numel, size_t offset, size_t count, float* m,
+                                  float* v, float lr, float b1, float b2, float eps, float grad_scale, const int64_t* step_dev,
+                                  void* stream) {
   UAD_REQUIRE(regions && world >= 1 && world <= UAD_PEER_MAX && rank >= 0 && rank < world, "uad_peer_adam_step: bad rank / world");
   UAD_REQUIRE(m && v && ((uintptr_t)m % 16 == 0) && ((uintptr_t)v % 16 == 0), "uad_peer_adam_step: unaligned Adam state");
-  UAD_REQUIRE(numel % 4 == 0, "uad_peer_adam_step: the flat buffer must be a multiple of 4 floats");
+  UAD_REQUIRE(numel % 4 == 0 && offset % 4 == 0 && count % 4 == 0 && count > 0 && offset + count <= numel,
+              "uad_peer_adam_step: the slice must lie inside the flat buffer and be a multiple of 4 floats");
   const size_t half = (numel * sizeof(float) + 255) & ~(size_t)255;
   PeerPtrs pp;
   memset(&pp, 0, sizeof(pp));
   for (int j = 0; j < world; ++j) {
     UAD_REQUIRE(regions[j] != nullptr, "uad_peer_adam_step: region %d is not mapped", j);
     char* base = (char*)regions[j];
-    pp.params[j] = (float*)base;
-    pp.grads[j] = (const float*)(base + half);
+    pp.params[j] = (float*)base + offset;
+    pp.grads[j] = (const float*)(base + half) + offset;
     pp.flags[j] = (unsigned long long*)(base + 2 * half);
   }
-  size_t chunk = (numel + world - 1) / world;
+  size_t chunk = (count + world - 1) / world;
   chunk = (chunk + 3) & ~(size_t)3;
   long long blocks = (long long)((chunk / 4 + 255) / 256);
   if (blocks > UAD_NUM_SMS) blocks = UAD_NUM_SMS;               // one wave: the in-kernel block counter needs every block resident
   if (blocks < 1) blocks = 1;
-  peer_rs_adam_ag_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pp, rank, world, m, v, numel, chunk, lr, b1, b2, eps,
+  peer_rs_adam_ag_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pp, rank, world, m, v, count, chunk, lr, b1, b2, eps,
                                                                        grad_scale, (const long long*)step_dev);
   UAD_LAUNCH_CHECK("peer_rs_adam_ag");
   return 0;

@@ -133,15 +133,18 @@ class PeerOptimizer:
         torch.cuda.synchronize(device)
         dist.barrier()
 
-    def step(self, m, v, lr, beta1, beta2, eps, grad_scale, step_dev, stream):
+    def step(self, m, v, lr, beta1, beta2, eps, grad_scale, step_dev, stream, lo=0, hi=None):
+        """One optimiser step on the slice [lo, hi) of the flat index space (default: everything); m / v are the FULL moment buffers."""
         from . import abi
-        abi.call('uad_peer_adam_step', self.regions, self.rank, self.world, self.numel, m.data_ptr(), v.data_ptr(), float(lr),
-                 float(beta1), float(beta2), float(eps), float(grad_scale), step_dev.data_ptr(), stream)
+        hi = self.numel if hi is None else hi
+        abi.call('uad_peer_adam_step', self.regions, self.rank, self.world, self.numel, int(lo), int(hi - lo), m[lo:].data_ptr(),
+                 v[lo:].data_ptr(), float(lr), float(beta1), float(beta2), float(eps), float(grad_scale), step_dev.data_ptr(), stream)
 
-    def shard_range(self):
-        chunk = (-(-self.numel // self.world) + 3) & ~3
-        lo = self.rank * chunk
-        return lo, min(self.numel, lo + chunk)
+    def shard_range(self, lo=0, hi=None):
+        hi = self.numel if hi is None else hi
+        chunk = (-(-(hi - lo) // self.world) + 3) & ~3
+        a = lo + self.rank * chunk
+        return a, min(hi, a + chunk)
 
     def gather_adam_state(self, m, v):
         """Every rank holds the Adam moments of its own shard only; before they are written to a checkpoint, collect them."""

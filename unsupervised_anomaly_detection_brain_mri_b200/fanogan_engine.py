@@ -547,10 +547,29 @@ class FanoganEngine:
         lo, hi = self.fp.subset_ranges(scope + '/')
         call('uad_fill', ptr(self.fp.grads[lo:]), 0.0, hi - lo, self._st())
 
+    def _update_in_graph(self, allreduce):
+        """The optimiser step is part of the (capturable) train-op body unless it needs a host-side collective: single GPU, or
+        the fused peer-memory kernel (enable_peer_optimizer)."""
+        return allreduce is None or getattr(self, 'peer', None) is not None
+
+    def enable_peer_optimizer(self):
+        """Data parallel: `all-reduce of the scope's gradient slice + Adam` becomes ONE kernel over NVLink peer memory on that slice
+        (csrc/uad_peer.cu, dist.PeerOptimizer).  Call once after the parameter broadcast, before the first train op."""
+        from . import dist as udist
+        if getattr(self, 'peer', None) is None and udist.world_size() > 1:
+            self.peer = udist.PeerOptimizer(self.fp, self.device)
+            self._graphs, self._warm = {}, {}
+        return getattr(self, 'peer', None)
+
     def _adam(self, scope, lr, allreduce, world):
         """tf.train.AdamOptimizer(lr, beta1=0.5, beta2=0.9) on the scope's contiguous slice (fAnoGAN.py:71-77)."""
         fp, st = self.fp, self._st()
         lo, hi = fp.subset_ranges(scope + '/')
+        if allreduce is not None and world > 1 and getattr(self, 'peer', None) is not None:
+            self.t[scope] += 1
+            call('uad_counter_add', self.steps[scope].data_ptr(), 1, st)
+            self.peer.step(fp.m, fp.v, float(lr), 0.5, 0.9, 1e-8, 1.0 / world, self.steps[scope], st, lo=lo, hi=hi)
+            return
         if allreduce is not None and world > 1:
             allreduce(fp.grads[lo:hi])
         self.t[scope] += 1
@@ -587,13 +606,13 @@ class FanoganEngine:
             self._critic_backward(self.pass0, self.x_gen, params=False, dx_out=self.dxi)
             self._zero_grads('Generator')
             self._generator_backward(self.dxi, params=True)
-            if apply and allreduce is None:
-                self._adam('Generator', lr, None, world)
+            if apply and self._update_in_graph(allreduce):
+                self._adam('Generator', lr, allreduce, world)
 
         key = (float(lr), float(dropout_rate), bool(dropout), bool(parity_noise), allreduce is None, world, bool(apply))
-        self._graph_scopes[('gen', key)] = ('Generator',) if (apply and allreduce is None) else ()
+        self._graph_scopes[('gen', key)] = ('Generator',) if (apply and self._update_in_graph(allreduce)) else ()
         self._run('gen', key, body, use_graph)
-        if apply and allreduce is not None:
+        if apply and not self._update_in_graph(allreduce):
             self._adam('Generator', lr, allreduce, world)
         s = self._scalars(['disc_fake'])
         return {'gen_loss': -s['disc_fake'], 'disc_fake': s['disc_fake']}
@@ -626,13 +645,13 @@ class FanoganEngine:
             call('uad_interpolate', ptr(self.x), ptr(self.x_gen), ptr(self.alpha), ptr(self.x_hat), self.B, self.S * self.S * self.C, st)
             self._critic_forward(self.pass0, self.x_hat, critic=False)
             self._critic_gp(self.pass0, self.x_hat)
-            if apply and allreduce is None:
-                self._adam('Discriminator', lr, None, world)
+            if apply and self._update_in_graph(allreduce):
+                self._adam('Discriminator', lr, allreduce, world)
 
         key = (float(lr), float(dropout_rate), bool(dropout), bool(parity_noise), allreduce is None, world, bool(apply), self.scale)
-        self._graph_scopes[('disc', key)] = ('Discriminator',) if (apply and allreduce is None) else ()
+        self._graph_scopes[('disc', key)] = ('Discriminator',) if (apply and self._update_in_graph(allreduce)) else ()
         self._run('disc', key, body, use_graph)
-        if apply and allreduce is not None:
+        if apply and not self._update_in_graph(allreduce):
             self._adam('Discriminator', lr, allreduce, world)
         s = self._scalars(['disc_fake', 'disc_real', 'gp'])
         s['disc_loss'] = s['disc_fake'] - s['disc_real'] + s['gp']
@@ -669,14 +688,14 @@ class FanoganEngine:
                 call('uad_axpby', 1.0, ptr(self.u), 1.0, ptr(self.dxi), nx, st)
                 self._generator_backward(self.dxi, params=False, dz_out=self.dz_lat)
                 self._encoder_backward(self.dz_lat)
-                if apply and allreduce is None:
-                    self._adam('Encoder', lr, None, world)
+                if apply and self._update_in_graph(allreduce):
+                    self._adam('Encoder', lr, allreduce, world)
 
         key = (float(lr), float(dropout_rate), bool(dropout), bool(parity_noise), allreduce is None, world, bool(apply), bool(train),
                kappa)
-        self._graph_scopes[('enc', key)] = ('Encoder',) if (train and apply and allreduce is None) else ()
+        self._graph_scopes[('enc', key)] = ('Encoder',) if (train and apply and self._update_in_graph(allreduce)) else ()
         self._run('enc', key, body, use_graph)
-        if train and apply and allreduce is not None:
+        if train and apply and not self._update_in_graph(allreduce):
             self._adam('Encoder', lr, allreduce, world)
         s = self._scalars(['loss_img', 'loss_fts', 'reconstructionLoss'])
         s['enc_loss'] = s['loss_img'] + self.kappa * s['loss_fts']

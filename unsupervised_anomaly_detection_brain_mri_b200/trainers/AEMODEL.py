@@ -144,6 +144,20 @@ class AEMODEL(DLMODEL, ABC):
             ev.record()
         self._pf[key] = (id(arr), dev, ev)
 
+    def _fetch_pinned(self, key, dev):
+        """Start the device->host copy of a result tensor into a pinned buffer (two per key, alternating) on the compute stream and
+        return the numpy view; the caller synchronises (the scalar-loss read does) before looking at it."""
+        flip = self._pf_flip_out.get(key, 0) if hasattr(self, '_pf_flip_out') else 0
+        if not hasattr(self, '_pf_flip_out'):
+            self._pf_flip_out = {}
+        self._pf_flip_out[key] = flip ^ 1
+        buf = self._pinned.get(('out', key, flip, tuple(dev.shape)))
+        if buf is None:
+            buf = torch.empty(tuple(dev.shape), dtype=dev.dtype).pin_memory()
+            self._pinned[('out', key, flip, tuple(dev.shape))] = buf
+        buf.copy_(dev, non_blocking=True)
+        return buf.numpy()
+
     def _feed(self, key, arr):
         """Device-side source for this batch: the prefetched copy if one was started for exactly this array, else a
         pinned host buffer (async H2D on the compute stream)."""
@@ -169,10 +183,12 @@ class AEMODEL(DLMODEL, ABC):
             eng.forward(training=False, dropout_rate=0.0)
         self._prefetch('x', prefetch)                 # the GPU is busy with the step: stage the next batch meanwhile
         self._prefetch('x_ce', prefetch_ce)
+        maps = None
+        if fetch_maps:                                # pinned, asynchronous D2H behind the step; the scalar read below waits for all
+            maps = {k: self._fetch_pinned(k, t) for k, t in (('reconstruction', eng.br[0].xhat), ('L1', eng.br[0].l1))}
         run = dict(eng.losses())                      # device -> host read of the step's scalars
-        if fetch_maps:
-            run['reconstruction'] = eng.br[0].xhat.cpu().numpy()
-            run['L1'] = eng.br[0].l1.cpu().numpy()
+        if maps is not None:
+            run.update(maps)                          # views of a two-deep ring of pinned buffers: valid until the second-next fetch
         run = {k: (np.float32(v) if np.ndim(v) == 0 else v) for k, v in run.items()}
         return run
 

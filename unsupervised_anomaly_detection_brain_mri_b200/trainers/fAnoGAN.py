@@ -82,6 +82,10 @@ class fAnoGAN(DLMODEL):
         if self.world > 1:
             udist.broadcast_(self.engine.fp.params, src=0)
             self._allreduce = udist.allreduce_sum_
+            # fused reduce-scatter + Adam + all-gather over NVLink peer memory per train op (UAD_PEER_ADAM=0: NCCL + Adam);
+            # the subclasses with per-optimiser Adam slots (AnoVAEGAN) keep the NCCL form
+            if (os.environ.get('UAD_PEER_ADAM', '1') != '0' and udist.dist.get_backend() == 'nccl' and type(self.engine).__name__ == 'FanoganEngine'):
+                self.engine.enable_peer_optimizer()
 
     def _feed(self, batch):
         """get_feed_dict (fAnoGAN.py:212-218): x <- batch, z <- sample_z()."""
