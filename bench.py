@@ -482,7 +482,7 @@ def main():
                       'tflops': fl / ms / 1e9 if ms > 0 else None, 'gbs': by / ms / 1e6 if ms > 0 else None})
     top = table[0]
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get(top['op'])       # DRAM bytes per launch from the committed ncu --set full capture
     if top['bound'] == 'hbm':
