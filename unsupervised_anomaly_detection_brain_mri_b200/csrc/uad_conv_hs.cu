@@ -86,9 +86,13 @@ __host__ __device__ constexpr KbGeom kb_geom(int g, int i) {
   return KbGeom{(ih * RP + iw) * 8, (p + 3 - 2 * ih) * 5 + (q + 3 - 2 * iw)};
 }
 
-template <int FORM_, int N_, int CG_, int G_, bool FAST_ = false, bool PAIR_ = false>
+template <int FORM_, int N_, int CG_, int G_, bool FAST_ = false, bool PAIR_ = false, bool SLICED_ = false>
 struct Cfg {
   static constexpr int FORM = FORM_, N = N_, CG = CG_, G = G_;
+  // SLICED: the kernel computes N of HsParams::n_total output columns per item (HsParams::n_slices items per tile).  A template
+  // flag because the unsliced kernels must keep N as a compile-time constant in their epilogues (measured: runtime row strides /
+  // constant offsets cost the stride-1 N = 32 kernel 17 %)
+  static constexpr bool SLICED = SLICED_;
   // PAIR: M-grids of exactly 8 x 8 pixels (the bottleneck layers).  A 128-row tile is TWO images; their halos (10 x 10 pixels each)
   // are loaded by ONE 5-D TMA box whose dimension order (channel, W, image, H) interleaves the images row by row in shared memory:
   // halo row r of image j lies at (2 r + j) * 1280 bytes, so the 16 eight-pixel groups of an operand descriptor (tile row r of
@@ -216,7 +220,8 @@ __device__ __forceinline__ void weight_producer(const HsParams& p, const Bars& b
   Ring ws{0, 0};
   const bool no_load = (p.debug & 8) != 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    const int slice = item % p.n_slices, var = NVAR > 1 ? (item / p.n_slices) % NVAR : 0;
+    const int nsl = CF::SLICED ? p.n_slices : 1;
+    const int slice = CF::SLICED ? item % nsl : 0, var = NVAR > 1 ? (item / nsl) % NVAR : 0;
     for (int cb = 0; cb < p.Cblks; ++cb) {
       const float* cb_img = img0 + ((size_t)slice * p.Cblks + cb) * cb_floats;
       static_for<0, NVAR>([&](auto VI) {
@@ -259,7 +264,7 @@ __device__ __forceinline__ void mma_issuer(const HsParams& p, const Bars& bars, 
   Ring hs{0, 0}, ws{0, 0}, ab{0, 0};
   uint32_t next_ok = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-    const int var = NVAR > 1 ? (item / p.n_slices) % NVAR : 0;
+    const int var = NVAR > 1 ? (item / (CF::SLICED ? p.n_slices : 1)) % NVAR : 0;
     mbar_wait_fast(bars.accempty + 8 * ab.i, ab.ph ^ 1);        // the epilogue has drained this accumulator set
     tc_fence_after();
     const uint32_t acc0 = tmem_base + ab.i * CF::ACC_COLS;
@@ -356,7 +361,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   const uint32_t tmem_slot = misc + 352;
   static_assert(CF::HS <= 8 && CF::WS <= 4, "barrier layout");
   float* epi = reinterpret_cast<float*>(smem_gen + misc_off + 384);            // bias[N], scale[N], shift[N]
-  float* stg_base = epi + (N == 32 ? 4 : 3) * p.n_total;                       // N = 32: [3 NT, 4 NT) head weights; then 4 warps x 32 x 36 staging
+  float* stg_base = epi + (N == 32 ? 4 : 3) * (CF::SLICED ? p.n_total : N);                       // N = 32: [3 NT, 4 NT) head weights; then 4 warps x 32 x 36 staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cblks = p.Cblks;
@@ -371,7 +376,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
   }
   if (warp == 3) {
     tmem_alloc(tmem_slot, 512u);
-    const int NT = p.n_total;                                                // constants of ALL columns (a CTA may serve several slices)
+    const int NT = CF::SLICED ? p.n_total : N;                               // constants of ALL columns (a CTA may serve several slices)
     for (int n = lane; n < NT; n += 32) {
       const float bias = p.bias ? p.bias[n] : 0.f, scale = p.gamma ? p.gamma[n] * p.bn_c : 1.f;
       epi[n] = bias;
@@ -393,7 +398,7 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
       Ring hs{0, 0};
       const bool no_load = (p.debug & 16) != 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int tile = item / (NVAR * p.n_slices);
+        const int tile = item / (NVAR * (CF::SLICED ? p.n_slices : 1));
         const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
         const int s0 = twi * kTW - 1, r0 = thi * kTH - 1;     // halo origin (the zero fill outside the tensor == SAME padding)
         // PAIR: tile = image pair (2 tile, 2 tile + 1); an image index past the batch is zero-filled like the padding
@@ -469,8 +474,9 @@ conv_halo_ss(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ H
     const float slope = act == UAD_ACT_LEAKY ? p.alpha : (act == UAD_ACT_RELU ? 0.f : 1.f);
     Ring ab{(uint32_t)(CF::EPI_WG == 2 ? wg : 0), 0};
     for (int item = blockIdx.x + (CF::EPI_WG == 2 ? wg * gridDim.x : 0); item < p.n_items; item += CF::EPI_WG * gridDim.x) {
-      const int slice = item % p.n_slices, var = NVAR > 1 ? (item / p.n_slices) % NVAR : 0, tile = item / (NVAR * p.n_slices);
-      const int NT = p.n_total, ncol0 = slice * N;              // output row stride, first output column of this item
+      const int nsl = CF::SLICED ? p.n_slices : 1;
+      const int slice = CF::SLICED ? item % nsl : 0, var = NVAR > 1 ? (item / nsl) % NVAR : 0, tile = item / (NVAR * nsl);
+      const int NT = CF::SLICED ? p.n_total : N, ncol0 = CF::SLICED ? slice * N : 0;   // output row stride, first output column of this item
       const int twi = tile % p.tiles_w, thi = (tile / p.tiles_w) % p.tiles_h;
       const int b = CF::PAIR ? 2 * tile + ((row >> 3) & 1) : tile / (p.tiles_w * p.tiles_h);
       const int s0 = CF::PAIR ? 0 : twi * kTW, r0 = CF::PAIR ? 0 : thi * kTH;
@@ -679,6 +685,7 @@ int launch_cfg(const GatherParams& g, const CUtensorMap& tmap, HsParams& p, cons
     UAD_LAUNCH_CHECK("hs_weight_image");
   }
   // shared memory: halo stages (raw + lo), two weight rings, barriers / constants / staging
+  UAD_REQUIRE(CF::SLICED || (p.n_total == CF::N && p.n_slices == 1), "conv_halo_ss: column slices need the sliced kernel");
   const size_t tail = 384 + (CF::N == 32 ? 4 : 3) * p.n_total * sizeof(float) + CF::EPI_WG * 4 * 32 * 36 * sizeof(float) + 64;
   const size_t smem = 1024 + CF::HS * CF::HSTAGE + 2 * CF::WS * kSlot + tail;
   UAD_REQUIRE(smem <= 227 * 1024, "conv_halo_ss: shared-memory budget exceeded");
@@ -787,12 +794,9 @@ int uad_launch_gather_hs(const GatherParams& g, int nclasses, int ksize, bool we
     if (N == 32) return launch_cfg<Cfg<1, 32, 4, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                 \
     if (N == 64) return launch_cfg<Cfg<1, 64, 2, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);                 \
     return launch_cfg<Cfg<1, 128, 1, 1, FAST, true>>(g, tmap, p, w_raw, weights_transposed, st);
-    if (sliced) {
-      if (form == 0) return fast ? launch_cfg<Cfg<0, 32, 1, 1, true, true>>(g, tmap, p, w_raw, weights_transposed, st)
-                                 : launch_cfg<Cfg<0, 32, 1, 1, false, true>>(g, tmap, p, w_raw, weights_transposed, st);
-      return fast ? launch_cfg<Cfg<1, 32, 4, 1, true, true>>(g, tmap, p, w_raw, weights_transposed, st)
-                  : launch_cfg<Cfg<1, 32, 4, 1, false, true>>(g, tmap, p, w_raw, weights_transposed, st);
-    }
+    if (sliced)
+      return fast ? launch_cfg<Cfg<0, 32, 1, 1, true, true, true>>(g, tmap, p, w_raw, weights_transposed, st)
+                  : launch_cfg<Cfg<0, 32, 1, 1, false, true, true>>(g, tmap, p, w_raw, weights_transposed, st);
     if (fast) { UAD_HS_PAIR(true) }
     UAD_HS_PAIR(false)
 #undef UAD_HS_PAIR
