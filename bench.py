@@ -453,6 +453,7 @@ def main():
         loss_check = {'engine': got, 'oracle_fp32': ref, 'rel_err': abs(got - ref) / abs(ref), 'tol': tol, 'ok': abs(got - ref) / abs(ref) < tol}
 
     # ---- kernels per step (graph replays launch the captured kernels; count one eager step)
+    barrier()                                   # rank 0 spent seconds in the oracle: line the ranks up before the next collective step
     eng.graph, eng._warm = None, None
     c0 = abi.lib().uad_launch_count()
     eng.set_inputs(dev_batches[0])

@@ -158,7 +158,7 @@ int uad_adam_tf_step(float* params, const float* grads, float* m, float* v, size
  * [params | grads | flags] of uad_peer_region_bytes(numel) bytes with uad_peer_alloc, publishes its 64-byte IPC handle
  * (uad_peer_ipc_handle) through the host-side process group and maps the other ranks' regions with uad_peer_ipc_open;
  * regions[j] is rank j's region as mapped in the calling process.  m / v are local (only the rank's shard is used).
- * Every rank must issue the call the same number of times; a peer that never arrives traps after ~4 s instead of hanging. */
+ * Every rank must issue the call the same number of times; a peer that never arrives traps after ~2 min instead of hanging for good. */
 size_t uad_peer_region_bytes(size_t numel);
 int uad_peer_alloc(size_t bytes, void** region_out);
 int uad_peer_free(void* region);

@@ -15,7 +15,7 @@
 // values are a sequence number kept in device memory).
 // Buffers: each rank allocates ONE region [params | grads | flags] with uad_peer_alloc (cudaMalloc, so it has an IPC handle),
 // exchanges uad_peer_ipc_handle blobs through the host-side process group and maps the others with uad_peer_ipc_open.
-// Spins are bounded (~4 s): a missing peer traps instead of hanging the GPU.
+// Spins are bounded (~2 min): a missing peer traps instead of hanging the GPU for good.
 #include <stdint.h>
 #include <string.h>
 
@@ -49,7 +49,8 @@ __device__ __forceinline__ void st_relaxed_sys_f4(float* p, float4 v) {
 __device__ __forceinline__ void spin_until(const unsigned long long* p, unsigned long long want) {
   const long long t0 = clock64();
   while (ld_acquire_sys(p) < want) {
-    if (clock64() - t0 > (8ll << 30)) __trap();               // ~4 s at 2 GHz: a peer never arrived
+    if (clock64() - t0 > (1ll << 38)) __trap();               // ~2 min at 2 GHz: a peer never arrived (host-side skew between
+                                                              // ranks - a rank that evaluates or logs - is seconds and must not trip it)
     __nanosleep(64);
   }
 }
