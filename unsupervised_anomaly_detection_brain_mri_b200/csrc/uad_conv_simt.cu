@@ -376,31 +376,39 @@ int uad_launch_transpose_taps(const float* w, float* wT, int T, int A, int Bd, c
 }
 
 // ------------------------------------------------------------------------------------------------ Cin == 1 first layer
-// x [B,H,W,1] -> [B,H/2,W/2,Cout]; block = one output row (b, oh); thread = (pixel, 8-channel group) loop.
-template <int K>
-__global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+// x [B,H,W,1] -> [B,H/2,W/2,Cout]; block = R consecutive output rows of one image; thread = (output row, 4-pixel strip, 8-channel
+// group).  The filter and the 2 R + 3 input rows the block needs are staged once (row-wise, no per-element div / mod); a filter
+// row's 11 inputs of a strip are three 16-byte shared-memory reads (the strip starts at a multiple of 8 floats of a row whose pitch
+// is a multiple of 4), a tap's eight weights two.  One output row per block (the first version) paid the staging, two barriers and
+// the tail once per 128 pixels: 0.10 ms for 0.15 GB of HBM traffic.
+template <int K, int R>
+__global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ bias, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float* __restrict__ z_out,
                                                           float* __restrict__ a_out, int B, int H, int W, int Cout, int pad_lo,
                                                           int act, float alpha, float bn_c) {
   extern __shared__ __align__(16) float smem[];
   const int Ho = H / 2, Wo = W / 2;
-  const int XW = W + K + 8;                  // padded row length (+8: the 4-pixel strip of the last thread may start at Wo - 1)
+  const int XW = W + 16;                     // row pitch: pad_lo zeros, W inputs, zeros up to a multiple of 4 (>= 2 Wo + 11 - 1 reads)
+  constexpr int NR = 2 * R + K - 2;          // input rows of R output rows
   float* ws = smem;                          // [K*K][Cout]
-  float* xs = smem + K * K * Cout;           // [K][XW]
-  const int b = blockIdx.x / Ho, oh = blockIdx.x % Ho;
+  float* xs = smem + K * K * Cout;           // [NR][XW]
+  const int blocks_per_img = Ho / R;
+  const int b = blockIdx.x / blocks_per_img, oh0 = (blockIdx.x % blocks_per_img) * R;
   for (int i = threadIdx.x; i < K * K * Cout; i += blockDim.x) ws[i] = w[i];
-  for (int i = threadIdx.x; i < K * XW; i += blockDim.x) {
-    int kh = i / XW, c = i % XW;
-    int ih = 2 * oh + kh - pad_lo, iw = c - pad_lo;
-    float v = 0.f;
-    if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v = x[((size_t)b * H + ih) * W + iw];
-    xs[i] = v;
+  for (int r = threadIdx.x / 64; r < NR; r += blockDim.x / 64) {          // 64 threads per input row
+    const int ih = 2 * oh0 + r - pad_lo;
+    const bool in = (unsigned)ih < (unsigned)H;
+    const float* src = x + ((size_t)b * H + (in ? ih : 0)) * W;
+    for (int c = threadIdx.x % 64; c < XW; c += 64) {
+      const int iw = c - pad_lo;
+      xs[r * XW + c] = (in && (unsigned)iw < (unsigned)W) ? __ldg(src + iw) : 0.f;
+    }
   }
   __syncthreads();
   const int ngrp = Cout / 8;
   const int g = threadIdx.x % ngrp;
-  const int pstep = blockDim.x / ngrp;
+  const int strips = Wo / 4;                 // 4-pixel strips per output row
   float bia[8], sc[8], sf[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -409,9 +417,8 @@ __global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restric
     sc[j] = gamma ? gamma[n] * bn_c : 1.f;
     sf[j] = beta ? beta[n] : 0.f;
   }
-  // four adjacent output pixels per thread: a tap's eight weights are read from shared memory once per four pixels and a filter row's
-  // eleven inputs once per row (one pixel per thread was shared-memory bound: 36 bytes per 8 FMAs -> 0.13 ms for 0.17 GB of HBM traffic)
-  for (int ow0 = 4 * (threadIdx.x / ngrp); ow0 < Wo; ow0 += 4 * pstep) {
+  for (int item = threadIdx.x / ngrp; item < R * strips; item += blockDim.x / ngrp) {
+    const int rr = item / strips, ow0 = 4 * (item % strips);
     float acc[4][8];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -419,9 +426,10 @@ __global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restric
       for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
 #pragma unroll 1
     for (int kh = 0; kh < K; ++kh) {
-      float xr[6 + K];
+      float xr[12];
+      const float4* xrow = reinterpret_cast<const float4*>(xs + (2 * rr + kh) * XW + 2 * ow0);
 #pragma unroll
-      for (int i = 0; i < 6 + K; ++i) xr[i] = xs[kh * XW + 2 * ow0 + i];
+      for (int i = 0; i < 3; ++i) { const float4 t = xrow[i]; xr[4 * i] = t.x; xr[4 * i + 1] = t.y; xr[4 * i + 2] = t.z; xr[4 * i + 3] = t.w; }
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
         const float4 w0 = *reinterpret_cast<const float4*>(&ws[(kh * K + kw) * Cout + g * 8]);
@@ -438,8 +446,7 @@ __global__ void __launch_bounds__(128) conv_c1_fwd_kernel(const float* __restric
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (ow0 + q >= Wo) break;
-      size_t o = (((size_t)b * Ho + oh) * Wo + ow0 + q) * Cout + g * 8;
+      size_t o = (((size_t)b * Ho + oh0 + rr) * Wo + ow0 + q) * Cout + g * 8;
       float z[8], a[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -462,12 +469,17 @@ int uad_launch_conv_c1_fwd(const float* x, const float* w, const float* bias, co
                            float* z_out, float* a_out, int B, int H, int W, int Cout, int ksize, int act, float alpha,
                            float bn_c, cudaStream_t st) {
   UAD_REQUIRE(ksize == 5, "conv_c1_fwd: only k=5 (got %d)", ksize);
-  UAD_REQUIRE(Cout % 8 == 0 && Cout <= 128 && 128 % (Cout / 8) == 0, "conv_c1_fwd: unsupported Cout=%d", Cout);
+  UAD_REQUIRE(Cout % 8 == 0 && Cout <= 128 && 256 % (Cout / 8) == 0, "conv_c1_fwd: unsupported Cout=%d", Cout);
+  UAD_REQUIRE(W % 8 == 0 && H % 2 == 0, "conv_c1_fwd: W=%d must be a multiple of 8, H=%d even", W, H);
   const int pad_lo = (ksize - 2) / 2;
-  size_t smem = ((size_t)ksize * ksize * Cout + (size_t)ksize * (W + ksize + 8)) * sizeof(float);
+  const int Ho = H / 2;
+  const int R = Ho % 4 == 0 ? 4 : (Ho % 2 == 0 ? 2 : 1);
+  size_t smem = ((size_t)ksize * ksize * Cout + (size_t)(2 * R + ksize - 2) * (W + 16)) * sizeof(float);
   UAD_REQUIRE(smem <= 48 * 1024, "conv_c1_fwd: W=%d too large", W);
-  conv_c1_fwd_kernel<5><<<B * (H / 2), 128, smem, st>>>(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cout, pad_lo, act,
-                                                         alpha, bn_c);
+  const int grid = B * (Ho / R);
+  if (R == 4) conv_c1_fwd_kernel<5, 4><<<grid, 256, smem, st>>>(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cout, pad_lo, act, alpha, bn_c);
+  else if (R == 2) conv_c1_fwd_kernel<5, 2><<<grid, 256, smem, st>>>(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cout, pad_lo, act, alpha, bn_c);
+  else conv_c1_fwd_kernel<5, 1><<<grid, 256, smem, st>>>(x, w, bias, gamma, beta, z_out, a_out, B, H, W, Cout, pad_lo, act, alpha, bn_c);
   UAD_LAUNCH_CHECK("conv_c1_fwd");
   return 0;
 }
@@ -479,7 +491,7 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
                                                             int pad_lo) {
   extern __shared__ __align__(16) float smem[];
   const int Ho = H / 2, Wo = W / 2;
-  const int XW = W + K + 16;                  // zero padded: an 8-pixel strip may start at the last pixel of a row
+  const int XW = W + 24;                      // zero padded, pitch a multiple of 4 floats: a filter row's inputs of a strip are 16-byte reads
   float* xs = smem;                           // [K][XW]
   float* red = smem + K * XW;                 // [nwarps][K*K*Cout]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -492,12 +504,14 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
   for (int row = blockIdx.x; row < B * Ho; row += gridDim.x) {
     const int b = row / Ho, oh = row % Ho;
     __syncthreads();
-    for (int i = threadIdx.x; i < K * XW; i += blockDim.x) {
-      int kh = i / XW, c = i % XW;
-      int ih = 2 * oh + kh - pad_lo, iw = c - pad_lo;
-      float v = 0.f;
-      if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) v = x[((size_t)b * H + ih) * W + iw];
-      xs[i] = v;
+    for (int kh = warp; kh < K; kh += nwarps) {                   // one warp per input row: no per-element div / mod
+      const int ih = 2 * oh + kh - pad_lo;
+      const bool in = (unsigned)ih < (unsigned)H;
+      const float* src = x + ((size_t)b * H + (in ? ih : 0)) * W;
+      for (int c = lane; c < XW; c += 32) {
+        const int iw = c - pad_lo;
+        xs[kh * XW + c] = (in && (unsigned)iw < (unsigned)W) ? __ldg(src + iw) : 0.f;
+      }
     }
     __syncthreads();
     constexpr int U = 8;                                          // pixels per iteration: 8 independent dz loads in flight, and a
@@ -510,9 +524,10 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
           dv[u][q] = (ow0 + u < Wo) ? __ldg(dz + ((size_t)row * Wo + ow0 + u) * Cout + lane + 32 * q) : 0.f;
 #pragma unroll
       for (int kh = 0; kh < K; ++kh) {
-        float xr[2 * U + K - 2];
+        float xr[2 * U + 4];                                      // 2 U + K - 2 = 19 inputs: five 16-byte broadcast reads
+        const float4* xrow = reinterpret_cast<const float4*>(xs + kh * XW + 2 * ow0);
 #pragma unroll
-        for (int i = 0; i < 2 * U + K - 2; ++i) xr[i] = xs[kh * XW + 2 * ow0 + i];   // zero padded beyond the row
+        for (int i = 0; i < (2 * U + 4) / 4; ++i) { const float4 t = xrow[i]; xr[4 * i] = t.x; xr[4 * i + 1] = t.y; xr[4 * i + 2] = t.z; xr[4 * i + 3] = t.w; }
 #pragma unroll
         for (int kw = 0; kw < K; ++kw)
 #pragma unroll
@@ -550,7 +565,8 @@ int uad_launch_conv_c1_wgrad(const float* x, const float* dz, float* dw, int B, 
   size_t n = (size_t)ksize * ksize * Cout;
   size_t need = (size_t)blocks * n * sizeof(float);
   UAD_REQUIRE(ws && ws_bytes >= need, "conv_c1_wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
-  size_t smem = ((size_t)ksize * (W + ksize + 16) + (size_t)(nthreads / 32) * n) * sizeof(float);
+  UAD_REQUIRE(W % 4 == 0, "conv_c1_wgrad: W=%d must be a multiple of 4", W);
+  size_t smem = ((size_t)ksize * (W + 24) + (size_t)(nthreads / 32) * n) * sizeof(float);
   float* partial = reinterpret_cast<float*>(ws);
   static bool attr_set = false;   // set once, outside any stream capture in practice (first eager warm-up step)
   if (!attr_set) {
