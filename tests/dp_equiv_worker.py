@@ -203,11 +203,18 @@ def scoring_part(rank, world, local):
     sc = Metrics.DeviceScorer(diffs[mine].reshape(-1, S, S), labels[mine].reshape(-1, S, S), device=f'cuda:{local}',
                               allreduce=udist.allreduce_sum_)
     best = Metrics.compute_dice_curve_recursive(None, None, granularity=6, scorer=sc)
+    # the threshold-free metrics pool the voxels of all ranks (utils/Evaluation.pool_over_ranks): same AUC as one process
+    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation
+    order = np.concatenate([np.arange(r, nvol, world) for r in range(world)])
+    pd_, pl_ = Evaluation.pool_over_ranks(diffs[mine].reshape(-1), labels[mine].reshape(-1).astype(int))
+    assert np.array_equal(pd_, diffs[order].reshape(-1)) and np.array_equal(pl_, labels[order].reshape(-1).astype(int))
+    auc_pooled = Metrics.compute_roc(pd_, pl_)[0]
     if rank == 0:
         full = Metrics.DeviceScorer(diffs.reshape(-1, S, S), labels.reshape(-1, S, S), device=f'cuda:{local}')
         ref = Metrics.compute_dice_curve_recursive(None, None, granularity=6, scorer=full)
-        print(f'DP_EQUIV_SCORING world={world} best={best} ref={ref}', flush=True)
-        assert best == ref
+        auc_ref = Metrics.compute_roc(diffs.reshape(-1), labels.reshape(-1).astype(int))[0]
+        print(f'DP_EQUIV_SCORING world={world} best={best} ref={ref} pooled AUC {auc_pooled:.6f} == {auc_ref:.6f}', flush=True)
+        assert best == ref and abs(auc_pooled - auc_ref) < 1e-12
     torch.distributed.barrier()
 
 

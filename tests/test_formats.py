@@ -251,6 +251,16 @@ def test_trainer_tf_checkpoint_export_import_on_cpu(tmp_path):
     assert c.engine.t == 37 and int(c.engine.step_dev) == 37
     ma, mc = a.engine.fp.to_numpy(a.engine.fp.m), c.engine.fp.to_numpy(c.engine.fp.m)
     assert all(np.array_equal(ma[k], mc[k]) for k in ma)
+    # the exported bundles share the `checkpoint` state file with the native .npz checkpoints: a native save at step 3 followed by
+    # the exports above (steps 4, 5 - no .npz) must not make load() restart from scratch
+    d = make(4)
+    d._load_weights = lambda w: d.engine.fp.load(w)
+    a.curves = {}
+    a.save(str(tmp_path), 3)
+    a.export_tf_checkpoint(str(tmp_path), 6)
+    ok, counter = d.load(str(tmp_path))
+    assert ok and counter == 3
+    assert all(np.array_equal(wa[k], v) for k, v in d._weights().items())
     # a checkpoint of another architecture is refused with a clear error
     ae = make(1)
     ae.engine.specs = E.param_specs(E.CEVAE, 128)

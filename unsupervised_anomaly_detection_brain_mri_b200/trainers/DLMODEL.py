@@ -84,6 +84,14 @@ class DLMODEL(object):
                 m = re.search(r'model_checkpoint_path: "([^"]+)"', open(index).read())
                 if m:
                     ckpt_name = os.path.basename(m.group(1))
+        if iteration is None and not (ckpt_name and os.path.isfile(os.path.join(checkpoint_dir, ckpt_name + '.npz'))):
+            # the state file may name a step that exists only as an exported TF bundle (export_tf_checkpoint shares the
+            # `checkpoint` file, as tf.train.Saver would): fall back to the newest native checkpoint instead of restarting from 0
+            pat = re.compile(re.escape(self.config.modelname) + r'\.model-(\d+)\.npz$')
+            have = sorted((int(m.group(1)), f[:-4]) for f in (os.listdir(checkpoint_dir) if os.path.isdir(checkpoint_dir) else [])
+                          for m in [pat.match(f)] if m)
+            if have:
+                ckpt_name = have[-1][1]
         if ckpt_name and os.path.isfile(os.path.join(checkpoint_dir, ckpt_name + '.npz')):
             with np.load(os.path.join(checkpoint_dir, ckpt_name + '.npz')) as z:
                 self._load_weights({k.replace('|', '/'): z[k] for k in z.files})

@@ -289,6 +289,17 @@ def _evaluate(datasetObj, modelObj, sampleDir, options, split="TEST", shard=None
     return eval_dict, patients
 
 
+def pool_over_ranks(flat_d, flat_l):
+    """Data-parallel evaluation: the threshold-free metrics (ROC / PRC, the 70 %-precision operating point) need every voxel, not
+    just this rank's volumes - concatenate the residuals and labels of all ranks, in rank order, on every rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat_d, flat_l
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, (np.ascontiguousarray(flat_d), np.ascontiguousarray(flat_l).astype(np.uint8)))
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]).astype(int)
+
+
 def _dp_context(model):
     """(shard, int64 all-reduce) when the trainer runs data-parallel (enable_data_parallel), else (None, None)."""
     world = int(getattr(model, 'world', 1) or 1)
@@ -309,15 +320,23 @@ def evaluate(datasetPC, gan, options, epoch='last', description=None):
                             'eval-' + str(epoch) + '-' + time.strftime('%Y-%m-%d %H-%M-%S'))
     if description is not None:
         eval_dir += '-' + str(description)
+    shard, reduce_ = _dp_context(model)
+    if shard is not None and shard[1] > 1:
+        n_test = len(datasetPC.get_patient_idx(split="TEST"))
+        if n_test < shard[1]:                           # every rank sees the same dataset: the same error everywhere, before any collective
+            raise ValueError(f'data-parallel evaluation shards by volume: {n_test} test volumes cannot occupy {shard[1]} ranks')
+        if shard[0] > 0:                                # one directory per rank (rank 0 keeps the reference's name and holds the pooled figures)
+            eval_dir += f'-rank{shard[0]}'
     sample_dir = os.path.join(eval_dir, 'samples_test_PC')
     os.makedirs(sample_dir, exist_ok=True)
-    shard, reduce_ = _dp_context(model)
     eval_pc, patients = _evaluate(datasetPC, model, sample_dir, options, "TEST", shard=shard)
     diffs = eval_pc['diffs']
     labels = (eval_pc['labelmaps'] > 0)
     scorer = Metrics.DeviceScorer(diffs, labels, device=model.device, allreduce=reduce_)
     flat_d, flat_l = diffs.flatten(), labels.flatten().astype(int)
-    eval_pc['diffHistogram'], _ = np.histogram(diffs, bins='auto', range=histogram_range)
+    if reduce_ is not None:                             # ROC / PRC / the precision-70 threshold over ALL ranks' voxels
+        flat_d, flat_l = pool_over_ranks(flat_d, flat_l)
+    eval_pc['diffHistogram'], _ = np.histogram(flat_d, bins='auto', range=histogram_range)
     if len(eval_pc.get('epistemic_variance', [])) > 0:
         ev = np.asarray(eval_pc['epistemic_variance'])
         eval_pc['uncertaintyHistogram'], _ = np.histogram(ev, bins=50, range=(1e-5, np.percentile(ev[ev >= 0], 99.8)))
