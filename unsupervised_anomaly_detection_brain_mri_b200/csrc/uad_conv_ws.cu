@@ -297,7 +297,12 @@ WsPlan ws_plan(int Cg, int Co, int B, int MH, int MW) {
   pl.nblocks = B * pl.nbr * pl.nbc;
   // about four CTAs per SM over all (type, channel block) columns of the grid, and no accumulator deeper than ~4096 pixels
   // (the tensor core adds into its fp32 accumulator with truncation)
-  int target = (4 * UAD_NUM_SMS) / (pl.ntypes * (Cg / 32));
+  // CTAs per SM over the whole grid: four at Co = 32 (the 256^2 layers: tail balance wins), three above (fewer split-K partials to
+  // reduce wins; measured at the VAE-256 shapes, profiles/r2_final_wgrad_waves.txt).  UAD_WS_WAVES overrides (developer switch).
+  static int waves_env = -1;
+  if (waves_env < 0) { const char* e = getenv("UAD_WS_WAVES"); waves_env = e ? atoi(e) : 0; }
+  const int waves = waves_env > 0 ? waves_env : (Co == 32 ? 4 : 3);
+  int target = (waves * UAD_NUM_SMS) / (pl.ntypes * (Cg / 32));
   if (target < 1) target = 1;
   const int px_per_block = kBH * pl.BW;
   static int depth = -1;                                       // developer switch UAD_WS_DEPTH: pixels per accumulator
