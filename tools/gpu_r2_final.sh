@@ -24,9 +24,7 @@ for MODE in "tc3 64" "tc1 32"; do
   python tools/ncu_summary.py gpurun_out/${TAG}_$1.ncu-rep > gpurun_out/${TAG}_$1_summary.json
   rm -f gpurun_out/${TAG}_$1.ncu-rep
 done
-# the dominant kernel (dec_Conv2DT_4 filter gradient = first wgrad_ss<WsCfg<32>> launch of the backward pass), --set full with source
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:wgrad_ss.*WsCfg.*32" --launch-skip 2 -c 1 -f -o gpurun_out/${TAG}_wgrad32_full python tools/profile_step.py 2 tc3 > gpurun_out/${TAG}_wgrad32_full.log 2>&1
-tail -1 gpurun_out/${TAG}_wgrad32_full.log; ls -la gpurun_out/${TAG}_wgrad32_full.ncu-rep
+# (the --set full report of the two largest launches is taken by tools/gpu_r2aa.sh: -k regex:conv_halo_ss|wgrad_ss --launch-skip 36 -c 2)
 unset UAD_SIDE_WGRAD UAD_DENSE_FORK
 ( time timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_ops.py -m gpu -q -x -p no:cacheprovider -k "conv2d_fwd_dgrad_wgrad or convT2d_fwd_dgrad_wgrad" ) > gpurun_out/${TAG}_memcheck.log 2>&1
 echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/${TAG}_memcheck.log | tail -4
