@@ -240,7 +240,12 @@ def test_trainer_tf_checkpoint_export_import_on_cpu(tmp_path):
     prefix = a.export_tf_checkpoint(str(tmp_path), 4)
     assert os.path.basename(prefix) == 'VAE.model-4' and os.path.isfile(prefix + '.index')
     names = list(C.list_bundle(prefix)[1])
-    assert not any(n.endswith('/Adam') for n in names) and 'Decoder/batch_normalization_6/moving_variance' in names
+    # default export: tf.compat.v1.layers' per-scope numbering of the un-named layers (the Decoder's first BN has no suffix)
+    assert not any(n.endswith('/Adam') for n in names) and 'Decoder/batch_normalization/moving_variance' in names
+    assert 'Decoder/batch_normalization_3/gamma' in names and 'Decoder/batch_normalization_6/gamma' not in names   # 64^2: 3 + 4 BN layers
+    assert 'Encoder/batch_normalization_2/beta' in names and 'Bottleneck/dense_2/kernel' in names and 'Encoder/enc_conv2D_2/kernel' in names
+    g_names = list(C.list_bundle(a.export_tf_checkpoint(str(tmp_path / 'graph'), 4, suffix_scheme='graph'))[1])
+    assert 'Decoder/batch_normalization_6/moving_variance' in g_names
     assert b.import_tf_checkpoint(os.path.dirname(prefix)) == 4                      # via the `checkpoint` state file
     wa, wb = a._weights(), b._weights()
     assert all(np.array_equal(wa[k], wb[k]) for k in wa) and b.engine.t == 0

@@ -102,7 +102,7 @@ class DLMODEL(object):
         return False, 0
 
     # ------------------------------------------------------------------ TensorFlow checkpoint files (tf.train.Saver V2)
-    def export_tf_checkpoint(self, checkpoint_dir, step, with_optimizer=False):
+    def export_tf_checkpoint(self, checkpoint_dir, step, with_optimizer=False, suffix_scheme='per_scope'):
         """Writes `<checkpoint_dir>/<model_dir>/<modelname>.model-<step>.{index,data-00000-of-00001}` + the `checkpoint`
         state file in the format the reference's `self.saver.save(...)` produces (trainers/DLMODEL.py:66-74), so a
         TensorFlow installation of the reference can `load()` weights trained here.  Variables: the trainable ones and the
@@ -119,6 +119,12 @@ class DLMODEL(object):
             m, v = eng.fp.to_numpy(eng.fp.m), eng.fp.to_numpy(eng.fp.v)
         variables = tfc.saver_variables(weights, m, v, step=int(getattr(eng, 't', 0)) if m is not None else 0,
                                         beta1=float(getattr(self.config, 'beta1', 0.5)), beta2=0.999)
+        # un-named layers: tf.compat.v1.layers (what the reference's graphs are built from) numbers them per variable scope;
+        # suffix_scheme='graph' keeps this code's graph-wide numbering (import accepts either, tf_checkpoint.resolve_layer_names)
+        if suffix_scheme == 'per_scope':
+            variables = tfc.rename_prefixes(variables, tfc.per_scope_layer_names(list(weights)))
+        elif suffix_scheme != 'graph':
+            raise ValueError(f"suffix_scheme must be 'per_scope' or 'graph', not {suffix_scheme!r}")
         directory = os.path.join(checkpoint_dir, self.model_dir)
         name = f'{self.config.modelname}.model-{step}'
         tfc.write_bundle(os.path.join(directory, name), variables)

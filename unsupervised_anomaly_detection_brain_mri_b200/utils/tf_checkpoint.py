@@ -371,6 +371,37 @@ def resolve_layer_names(wanted, available):
     return mapping
 
 
+def per_scope_layer_names(names):
+    """{layer prefix -> the prefix tf.compat.v1.layers gives it}: the legacy layer classes the reference imports
+    (models/customlayers.py:4) open `variable_scope(None, default_name=<base name>)` when first called, so un-named layers are
+    numbered PER ENCLOSING VARIABLE SCOPE in creation order ('Decoder/batch_normalization', 'Decoder/batch_normalization_1', ...),
+    whereas engine.param_specs numbers them over the whole graph ('Decoder/batch_normalization_6', ...).  Explicitly named layers
+    ('enc_conv2D_3') and layers whose kind appears once per scope keep their names."""
+    order = OrderedDict()
+    for n in names:
+        prefix = n.rpartition('/')[0]
+        scope, kind, idx = _split_layer(prefix)
+        if idx is not None:
+            order.setdefault((scope, kind), {})[idx] = prefix
+    mapping = {}
+    for (scope, kind), layers in order.items():
+        for k, idx in enumerate(sorted(layers)):
+            mapping[layers[idx]] = (scope + '/' if scope else '') + (kind if k == 0 else f'{kind}_{k}')
+    return mapping
+
+
+def rename_prefixes(variables, mapping):
+    """Variables re-keyed by {old layer prefix -> new layer prefix}; slot variables and moving statistics follow their layer."""
+    out = OrderedDict()
+    for name, value in variables.items():
+        hit = None
+        for a in mapping:
+            if name.startswith(a + '/') and (hit is None or len(a) > len(hit)):
+                hit = a
+        out[name if hit is None else mapping[hit] + name[len(hit):]] = value
+    return out
+
+
 def rename_layers(variables, mapping):
     """Checkpoint variables re-keyed to this code's layer prefixes (inverse of ``mapping``'s direction); slot variables and
     moving statistics follow their layer."""
