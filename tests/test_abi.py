@@ -89,3 +89,23 @@ def test_unbuilt_math_modes_are_rejected_not_aliased():
     assert rc != 0 and b'math_mode 3 is not built' in L.uad_last_error()
     rc = L.uad_convT2d_wgrad(None, None, None, 1, 16, 16, 32, 32, 5, 0, 7, None, 0, None)
     assert rc != 0 and b'math_mode 7 is not built' in L.uad_last_error()
+
+
+def test_peer_optimizer_entry_points_validate_on_the_host():
+    """csrc/uad_peer.cu: region sizing and the argument checks of uad_peer_adam_step run before any device work - no GPU needed."""
+    import ctypes as C
+    from unsupervised_anomaly_detection_brain_mri_b200 import abi
+    L = abi.lib()
+    n = 2194176                                            # a flat buffer of 64-float slots
+    half = (n * 4 + 255) & ~255
+    assert L.uad_peer_region_bytes(n) == 2 * half + 64 * 8
+    regions = (C.c_void_p * 16)()
+    assert L.uad_peer_adam_step(regions, 0, 17, n, 0, n, None, None, 1e-4, 0.5, 0.999, 1e-8, 1.0, None, None) != 0
+    assert b'bad rank / world' in L.uad_last_error()
+    assert L.uad_peer_adam_step(regions, 2, 2, n, 0, n, None, None, 1e-4, 0.5, 0.999, 1e-8, 1.0, None, None) != 0
+    dummy = C.c_void_p(0x1000)
+    assert L.uad_peer_adam_step(regions, 0, 2, n, 0, n, dummy, dummy, 1e-4, 0.5, 0.999, 1e-8, 0.5, None, None) != 0
+    assert b'is not mapped' in L.uad_last_error()
+    regions[0] = regions[1] = 0x10000
+    assert L.uad_peer_adam_step(regions, 0, 2, n, 64, n, dummy, dummy, 1e-4, 0.5, 0.999, 1e-8, 0.5, None, None) != 0
+    assert b'must lie inside the flat buffer' in L.uad_last_error()
