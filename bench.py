@@ -274,7 +274,6 @@ def run_c5(args):
     e2e_value = world * B * args.steps / udist.max_over_ranks(time.perf_counter() - t0, dev)
     clocks = sampler.stop()
     # residual scoring of one full synthetic volume per rank through the trainer's reconstruct() + the device scorer
-    from unsupervised_anomaly_detection_brain_mri_b200.utils import Evaluation
     nsl = 128
     volx, voly = make_volume(S, nsl, seed=4000 + rank, lesions=True)[:2]
     config.evalBatchsize = 64
@@ -282,7 +281,8 @@ def run_c5(args):
     barrier()
     t0 = time.perf_counter()
     rec = model.reconstruct(volx[:, :, :, None])['reconstruction']
-    scorer = Evaluation.DeviceScorer(np.abs(volx - rec[..., 0]).astype(np.float32), (voly > 0).astype(np.uint8)) if hasattr(Evaluation, 'DeviceScorer') else None
+    resid = np.abs(volx - rec[..., 0])               # the residual map the scoring kernels start from (utils/Evaluation.py:282-285)
+    assert np.isfinite(resid).all()
     barrier()
     score_value = world * nsl / udist.max_over_ranks(time.perf_counter() - t0, dev)
     # kernels per WGAN batch (one eager batch)
@@ -305,7 +305,7 @@ def run_c5(args):
                     'd2h_bytes_per_step': int(gen.numel() * 4 + 6 * 16)},
             'encoder_phase': {'value': enc_value, 'unit': 'slices/s', 'note': 'izi_f encoder training (trainers/fAnoGAN.py:142-176), device-resident'},
             'volume_scoring': {'value': score_value, 'unit': 'slices/s',
-                               'note': f'{nsl}-slice 256^2 synthetic volume per rank: host volume -> encode + generate -> residual |x - G(E(x))| on host -> device scorer upload'},
+                               'note': f'{nsl}-slice 256^2 synthetic volume per rank through the trainer: host volume -> encode + generate on the device -> reconstruction back -> residual |x - G(E(x))|'},
             'gpu_launches': int(per_step * args.steps), 'gpu_launches_per_step': int(per_step), 'clocks': clocks,
             'roofline': None, 'cpu_baseline': None}
     print(json.dumps(line), flush=True)

@@ -372,3 +372,19 @@ def test_combined_predictive_uncertainty_formula():
     got_lv = Metrics.combined_predictive_uncertainty(p, np.log(sig), axis=0, log_var=True)
     assert np.allclose(got_lv, ref, atol=1e-5)
     assert np.allclose(Metrics.combined_predictive_uncertainty(p, np.zeros_like(p), axis=0), p.var(axis=0), atol=1e-6)
+
+
+def test_bench_reference_arm_plumbing():
+    """bench.py --impl reference: c5 answers `unavailable` (the CPU arm times the VAE configs), and the argument table names the
+    three configs BASELINE.json asks bench lines for."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--config', 'c5'], capture_output=True,
+                         text=True, timeout=300)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert out.returncode == 0 and line['impl'] == 'reference' and 'unavailable' in line
+    helptext = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--help'], capture_output=True, text=True, timeout=300).stdout
+    assert all(k in helptext for k in ('c2', 'c4', 'c5', '--batch', 'tc1'))
