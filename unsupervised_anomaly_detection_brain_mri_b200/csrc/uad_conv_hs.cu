@@ -35,6 +35,12 @@
 //               row stores                                          -> acc_empty[b]
 // The tensor core adds into its fp32 accumulator with truncation (round 1, measured): no accumulator pair takes more than
 // ~1600 products per output (N = 128 strided form: channel blocks alternate between G = 2 pairs per issuer).
+// Variants of the same kernel (template flags of Cfg, each explained there):
+//   FAST    UAD_MATH_TC_1XTF32 - one MMA per K-step, no lo pass, the lo tile's space = twice the halo stages, outputs stored rounded
+//   PAIR    M-grids of exactly 8 x 8: two images per 128-row tile, their halos interleaved row by row by one 5-D TMA box
+//   SLICED  N of n_total output columns per item (more, narrower items for the layers with too few tiles: the strided PAIR form)
+// The epilogue transposes the RAW accumulators through shared memory first, so that a thread owns four channels of eight pixels
+// and keeps bias / BN scale / shift / head weights in registers.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
